@@ -1,0 +1,34 @@
+"""Host API of the K1 rasteriser (device featurisation of MIDI note events).
+
+Mirrors what the reference does on the CPU in ``EventBasedMIDIReader._parse_track``
+(MIDIUtil/midi_io.py:70-93) and what its writer replays (midi_io.py:119-127), batched on the GPU.
+"""
+import ctypes
+
+import torch
+
+from . import lib
+
+
+def rasterize(dtick, pitch, vel, seq_offsets, resolution=120, slices_per_quarter=4, n_slices=64,
+              max_seq_len=64, velocity_roll=False, out=None):
+    """N independent note-event sequences -> (tokens int32 [N,L+1], roll uint8 [N,S,128], n_tokens int32 [N]).
+
+    dtick int32 [E] (ticks since the previous note event), pitch/vel uint8 [E], seq_offsets int32 [N+1];
+    all CUDA tensors.  ``out`` may carry preallocated (tokens, roll, n_tokens)."""
+    assert dtick.is_cuda and dtick.dtype == torch.int32 and dtick.is_contiguous()
+    assert pitch.dtype == torch.uint8 and vel.dtype == torch.uint8 and seq_offsets.dtype == torch.int32
+    assert pitch.is_contiguous() and vel.is_contiguous() and seq_offsets.is_contiguous()
+    n = seq_offsets.numel() - 1
+    dev = dtick.device
+    if out is None:
+        tokens = torch.empty((n, max_seq_len + 1), dtype=torch.int32, device=dev)
+        roll = torch.empty((n, n_slices, 128), dtype=torch.uint8, device=dev)
+        n_tokens = torch.empty((n,), dtype=torch.int32, device=dev)
+    else:
+        tokens, roll, n_tokens = out
+    lib.call("msx_rasterize", lib.ptr(dtick), lib.ptr(pitch), lib.ptr(vel), lib.ptr(seq_offsets),
+             ctypes.c_int(n), ctypes.c_int(resolution), ctypes.c_int(slices_per_quarter),
+             ctypes.c_int(n_slices), ctypes.c_int(max_seq_len), ctypes.c_int(1 if velocity_roll else 0),
+             lib.ptr(tokens), lib.ptr(roll), lib.ptr(n_tokens), lib.stream_ptr())
+    return tokens, roll, n_tokens
