@@ -1,0 +1,108 @@
+// K2a — fused embedding front-end: gather + class embedding + sqrt(D) scale + positional encoding + pad mask.
+//
+// Replaces (reference, /root/reference/music_style_transfer/VarAutoEncoder):
+//   model.py:81-91      Encoder: mask = tokens != 0; tok_emb[tokens] + class_emb[classes][:,None,:]
+//   transformer.py:270  TransformerEncoder: sqrt(D) * x + pos_embeddings[:T]
+//   model.py:241-247    Decoder: concat(initial_state, emb[tokens]); SequenceMask(len+1)
+//   transformer.py:237  TransformerDecoder: sqrt(D) * x + pos_embeddings[:T+1]
+//   model.py:176        LSTMDecoder: emb[tokens]                       (scale 1, no PE, no class term)
+// One warp per output row; rows are D floats, float4 when D % 4 == 0.  Backward scatters with
+// red.global.add (embedding rows collide by construction) and reduces the class term per CTA.
+#include "msx_common.cuh"
+
+namespace {
+
+// out[b, pos, :] = scale * ((pos < prefix ? prefix_vec[b] : tok_emb[tokens[b, pos-prefix]]) + cls_emb[classes[b]]) + pe[pos]
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ tokens, const int* __restrict__ classes,
+                                                        const int* __restrict__ seq_lens,
+                                                        const float* __restrict__ tok_emb,
+                                                        const float* __restrict__ cls_emb,
+                                                        const float* __restrict__ prefix_vec,
+                                                        const float* __restrict__ pe, float* __restrict__ out,
+                                                        float* __restrict__ mask, int B, int T, int D, int prefix,
+                                                        float scale, int vocab) {
+  const int TP = T + prefix;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * TP) return;
+  const int b = (int)(row / TP), pos = (int)(row % TP);
+  const float* src;
+  int tok = 1;
+  if (pos < prefix) {
+    src = prefix_vec + (size_t)b * D;
+  } else {
+    tok = __ldg(tokens + (size_t)b * T + pos - prefix);
+    tok = min(max(tok, 0), vocab - 1);
+    src = tok_emb + (size_t)tok * D;
+  }
+  const float* cls = cls_emb ? cls_emb + (size_t)__ldg(classes + b) * D : nullptr;
+  const float* pr = pe ? pe + (size_t)pos * D : nullptr;
+  float* dst = out + (size_t)row * D;
+  for (int e = lane; e < D; e += 32) {
+    float v = __ldg(src + e);
+    if (cls) v += __ldg(cls + e);
+    v *= scale;
+    if (pr) v += __ldg(pr + e);
+    dst[e] = v;
+  }
+  if (mask && lane == 0) {
+    // encoder: tokens != 0 (model.py:81-83); decoder: position < seq_len + 1 (model.py:246-247)
+    mask[row] = seq_lens ? (pos < __ldg(seq_lens + b) + prefix ? 1.f : 0.f) : (tok != 0 ? 1.f : 0.f);
+  }
+}
+
+// d tok_emb[tok] += scale*dout ; d cls_emb[cls[b]] += scale*sum_t dout[b,t] ; d prefix_vec[b] = scale*dout[b,0]
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ tokens, const int* __restrict__ classes,
+                                                        const float* __restrict__ dout, float* __restrict__ d_tok_emb,
+                                                        float* __restrict__ d_cls_emb, float* __restrict__ d_prefix,
+                                                        int B, int T, int D, int prefix, float scale, int vocab) {
+  const int b = blockIdx.x;
+  const int TP = T + prefix;
+  const int c = d_cls_emb ? __ldg(classes + b) : 0;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) {
+    float csum = 0.f;
+    for (int pos = 0; pos < TP; ++pos) {
+      const float g = scale * __ldg(dout + ((size_t)b * TP + pos) * D + e);
+      csum += g;
+      if (pos < prefix) {
+        d_prefix[(size_t)b * D + e] = g;
+      } else {
+        int tok = __ldg(tokens + (size_t)b * T + pos - prefix);
+        tok = min(max(tok, 0), vocab - 1);
+        atomicAdd(d_tok_emb + (size_t)tok * D + e, g);
+      }
+    }
+    if (d_cls_emb) atomicAdd(d_cls_emb + (size_t)c * D + e, csum);
+  }
+}
+
+}  // namespace
+
+extern "C" int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
+                             const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
+                             float* out, float* mask, int B, int T, int D, int prefix, float scale, int vocab,
+                             void* stream) {
+  MSX_REQUIRE(tokens && tok_emb && out, "msx_embed_fwd: null pointer");
+  MSX_REQUIRE(prefix == 0 || prefix_vec, "msx_embed_fwd: prefix rows need prefix_vec");
+  MSX_REQUIRE(!cls_emb || classes, "msx_embed_fwd: class embedding needs classes");
+  if (B == 0 || T + prefix == 0) return MSX_OK;
+  const long long rows = (long long)B * (T + prefix);
+  const int wpb = 8;
+  embed_fwd_kernel<<<msx_ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb,
+                             float* d_cls_emb, float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab,
+                             void* stream) {
+  MSX_REQUIRE(tokens && dout && d_tok_emb, "msx_embed_bwd: null pointer");
+  MSX_REQUIRE(prefix == 0 || d_prefix, "msx_embed_bwd: prefix rows need d_prefix");
+  MSX_REQUIRE(!d_cls_emb || classes, "msx_embed_bwd: class embedding needs classes");
+  if (B == 0) return MSX_OK;
+  embed_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D,
+                                                        prefix, scale, vocab);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

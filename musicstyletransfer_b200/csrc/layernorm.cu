@@ -1,0 +1,237 @@
+// K2d — fused (dropout) + residual + LayerNorm, forward and backward.
+//
+// Replaces `self.ln1(x + self.dropout(x_att))` / `self.ln2(x + self.dropout(x_att))`
+// (/root/reference/music_style_transfer/VarAutoEncoder/transformer.py:155,158) and the decoder's
+// `self.ln3(x_att + self.dropout(x_att))` (:200), i.e. gluon.nn.Dropout + broadcast add +
+// gluon.nn.LayerNorm (last axis, biased variance, eps 1e-5), plus their autograd backward.
+//
+// One warp per row, row kept in registers (D <= 1024), two-pass mean / variance exactly as
+// (x-mean)^2 averaged, so fp32 results track the un-fused oracle closely.  HBM-bound: reads x and y,
+// writes out (+ 8 B of statistics per row).  Backward re-creates s = x + drop(y) from the saved
+// inputs and the Philox mask, reduces dgamma / dbeta per CTA before one atomic per column.
+#include "msx_common.cuh"
+
+namespace {
+
+constexpr int kMaxPer = 8;      // float4 groups per lane  -> D <= 1024 (vector path), D <= 256 (scalar path)
+constexpr int kWarps = 8;
+
+template <int VEC>
+__device__ __forceinline__ int elem_index(int i, int lane, int j) {
+  return VEC == 4 ? (i * 32 + lane) * 4 + j : i * 32 + lane;
+}
+
+// s = x + drop(y) for this lane's elements of row `row`
+template <int VEC>
+__device__ __forceinline__ void load_sum(const float* __restrict__ x, const float* __restrict__ y, size_t row, int D,
+                                         int nper, int lane, float p, float inv_keep, unsigned long long seed,
+                                         unsigned site, float s[kMaxPer][VEC], float keep[kMaxPer][VEC]) {
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    if (i >= nper) break;
+    if (VEC == 4) {
+      const int e = (i * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(x + row * D + e);
+      const float4 yv = *reinterpret_cast<const float4*>(y + row * D + e);
+      float k4[4] = {1.f, 1.f, 1.f, 1.f};
+      if (p > 0.f) dropout_scale4(seed, site, (row * D + e) >> 2, p, inv_keep, k4);
+      s[i][0] = xv.x + yv.x * k4[0];
+      s[i][1 % VEC] = xv.y + yv.y * k4[1];
+      s[i][2 % VEC] = xv.z + yv.z * k4[2];
+      s[i][3 % VEC] = xv.w + yv.w * k4[3];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) keep[i][j] = k4[j];
+    } else {
+      const int e = i * 32 + lane;
+      float k4[4] = {1.f, 1.f, 1.f, 1.f};
+      if (p > 0.f) dropout_scale4(seed, site, (row * D + e) >> 2, p, inv_keep, k4);
+      const float kk = k4[(row * D + e) & 3];
+      s[i][0] = x[row * D + e] + y[row * D + e] * kk;
+      keep[i][0] = kk;
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ out,
+                                                                 float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                 long long M, int D, float eps, float p, float inv_keep,
+                                                                 unsigned long long seed, unsigned site) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nper = D / (32 * VEC);
+  const float invD = 1.f / D;
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
+    float s[kMaxPer][VEC], keep[kMaxPer][VEC];
+    load_sum<VEC>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i)
+      if (i < nper)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sum += s[i][j];
+    const float mean = warp_sum(sum) * invD;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i)
+      if (i < nper)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float d = s[i][j] - mean;
+          var = fmaf(d, d, var);
+        }
+    var = warp_sum(var) * invD;
+    const float rstd = 1.f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      if (i >= nper) break;
+      if (VEC == 4) {
+        const int e = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
+        float4 o;
+        o.x = (s[i][0] - mean) * rstd * g.x + b.x;
+        o.y = (s[i][1 % VEC] - mean) * rstd * g.y + b.y;
+        o.z = (s[i][2 % VEC] - mean) * rstd * g.z + b.z;
+        o.w = (s[i][3 % VEC] - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(out + (size_t)row * D + e) = o;
+      } else {
+        const int e = i * 32 + lane;
+        out[(size_t)row * D + e] = (s[i][0] - mean) * rstd * __ldg(gamma + e) + __ldg(beta + e);
+      }
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// ds = rstd * (g*dout - mean(g*dout) - xhat * mean(g*dout*xhat));  dres = ds;  dy = ds * keep
+template <int VEC>
+__global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
+    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
+    float* __restrict__ dres, float* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M,
+    int D, float p, float inv_keep, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy) {
+  __shared__ float red[kWarps][32 * VEC + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nper = D / (32 * VEC);
+  const float invD = 1.f / D;
+  float dg[kMaxPer][VEC], db[kMaxPer][VEC];
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = 0.f;
+
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
+    float s[kMaxPer][VEC], keep[kMaxPer][VEC];
+    load_sum<VEC>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float go[kMaxPer][VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      if (i >= nper) break;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int e = elem_index<VEC>(i, lane, j);
+        const float d = dout[(size_t)row * D + e];
+        const float xh = (s[i][j] - mean) * rstd;
+        s[i][j] = xh;
+        dg[i][j] = fmaf(d, xh, dg[i][j]);
+        db[i][j] += d;
+        const float gd = d * __ldg(gamma + e);
+        go[i][j] = gd;
+        s1 += gd;
+        s2 = fmaf(gd, xh, s2);
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      if (i >= nper) break;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int e = elem_index<VEC>(i, lane, j);
+        const float ds = rstd * (go[i][j] - s1 - s[i][j] * s2);
+        const size_t o = (size_t)row * D + e;
+        // fuse_xy: x and y are the same tensor (decoder's ln3(f + drop(f))) -> one gradient ds*(1+keep)
+        if (dy && !fuse_xy) dy[o] = ds * keep[i][j];
+        const float dr = fuse_xy ? ds * (1.f + keep[i][j]) : ds;
+        dres[o] = accumulate_dres ? dres[o] + dr : dr;
+      }
+    }
+  }
+  // CTA-level reduction of dgamma/dbeta, then one atomic per column
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    if (i >= nper) break;
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[warp][lane * VEC + j] = pass == 0 ? dg[i][j] : db[i][j];
+      __syncthreads();
+      for (int c = threadIdx.x; c < 32 * VEC; c += kWarps * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w][c];
+        const int l = c / VEC, j = c % VEC;
+        const int e = elem_index<VEC>(i, l, j);
+        atomicAdd((pass == 0 ? dgamma : dbeta) + e, t);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out,
+                              float* mean, float* rstd, long long M, int D, float eps, float drop_p,
+                              unsigned long long seed, unsigned site, void* stream) {
+  MSX_REQUIRE(x && y && gamma && beta && out && mean && rstd, "msx_add_ln_fwd: null pointer");
+  MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_fwd: D must be a multiple of 32");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_add_ln_fwd: bad dropout");
+  if (M == 0) return MSX_OK;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
+  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  if (vec) {
+    MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
+    add_ln_fwd_kernel<4><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps,
+                                                                         drop_p, inv_keep, seed, site);
+  } else {
+    MSX_REQUIRE(D <= 32 * kMaxPer, "msx_add_ln_fwd: D=%d unsupported (need D%%128==0 or D<=256)", D);
+    add_ln_fwd_kernel<1><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps,
+                                                                         drop_p, inv_keep, seed, site);
+  }
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+                              const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, long long M, int D,
+                              float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
+                              void* stream) {
+  MSX_REQUIRE(x && y && gamma && mean && rstd && dout && dres && dgamma && dbeta, "msx_add_ln_bwd: null pointer");
+  MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
+  if (M == 0) return MSX_OK;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int grid = (int)min((long long)msx_num_sms() * 4, (M + kWarps - 1) / kWarps);
+  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (vec) {
+    MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
+    add_ln_bwd_kernel<4><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma,
+                                                                         dbeta, M, D, drop_p, inv_keep, seed, site,
+                                                                         accumulate_dres, fuse_xy);
+  } else {
+    MSX_REQUIRE(D <= 32 * kMaxPer, "msx_add_ln_bwd: D=%d unsupported", D);
+    add_ln_bwd_kernel<1><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma,
+                                                                         dbeta, M, D, drop_p, inv_keep, seed, site,
+                                                                         accumulate_dres, fuse_xy);
+  }
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

@@ -1,0 +1,308 @@
+// K3 — fused losses: reparameterisation + KL, softmax cross-entropy from logits (+ metrics), sigmoid-BCE.
+//
+// Replaces (reference, /root/reference/music_style_transfer/VarAutoEncoder):
+//   model.py:292            z = means + N(0,1) * vars
+//   loss.py:8-12            VariationalKLLoss    kl_b = sum_z 0.5 (s^2 + m^2 - 1 - log s^2)
+//   model.py:182/256 + loss.py:16-23   softmax(output_layer(x)) -> log -> pick -> mask(label != 0) -> mean over T
+//   loss.py:38-81           BinaryCrossEntropy (sigmoid, label smoothing, eps 1e-12, negative-label
+//                           down-weighting with the (w*bce)*bce quirk, mean over T*P)
+//   trainer.py:107-120,181-186 + metrics.py   Perplexity / Accuracy / TopKAccuracy inputs, accumulated on device
+// All HBM-bound: logits are read once in forward (row statistics) and once in backward (in-place gradient).
+#include "msx_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- reparameterisation + KL
+// lat [B, 2Z] = [means | stds];  z = m + eps * s;  kl_b = sum 0.5 (s^2 + m^2 - 1 - log(s^2))
+__global__ void __launch_bounds__(128) reparam_kl_fwd_kernel(const float* __restrict__ lat, const float* __restrict__ eps,
+                                                             float* __restrict__ z, float* __restrict__ kl, int Z) {
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
+    const float m = lat[(size_t)b * 2 * Z + i], s = lat[(size_t)b * 2 * Z + Z + i];
+    z[(size_t)b * Z + i] = m + eps[(size_t)b * Z + i] * s;
+    acc += 0.5f * (s * s + m * m - 1.f - logf(s * s));
+  }
+  __shared__ float red[4];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    kl[b] = t;
+  }
+}
+
+// dlat = [dz + gkl*m | dz*eps + gkl*(s - 1/s)]
+__global__ void reparam_kl_bwd_kernel(const float* __restrict__ lat, const float* __restrict__ eps,
+                                      const float* __restrict__ dz, const float* __restrict__ gkl, float kl_weight,
+                                      float* __restrict__ dlat, int B, int Z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Z) return;
+  const int b = (int)(i / Z), j = (int)(i % Z);
+  const float m = lat[(size_t)b * 2 * Z + j], s = lat[(size_t)b * 2 * Z + Z + j];
+  const float g = (gkl ? gkl[b] : 1.f) * kl_weight;
+  const float d = dz ? dz[i] : 0.f;
+  dlat[(size_t)b * 2 * Z + j] = d + g * m;
+  dlat[(size_t)b * 2 * Z + Z + j] = d * eps[i] + g * (s - 1.f / s);
+}
+
+__global__ void normal_fill_kernel(float* __restrict__ out, long long n, unsigned long long seed,
+                                   unsigned long long offset) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  const uint4 r = Philox::gen(seed, (unsigned long long)i4, offset);
+  const float u0 = 1.f - u32_to_unit(r.x), u1 = u32_to_unit(r.y), u2 = 1.f - u32_to_unit(r.z), u3 = u32_to_unit(r.w);
+  const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  float v[4];
+  sincospif(2.f * u1, &v[1], &v[0]);
+  sincospif(2.f * u3, &v[3], &v[2]);
+  v[0] *= r0; v[1] *= r0; v[2] *= r1; v[3] *= r1;
+  for (int j = 0; j < 4 && i4 * 4 + j < n; ++j) out[i4 * 4 + j] = v[j];
+}
+
+// ---------------------------------------------------------------- softmax CE from logits
+// One CTA per sample b; warps stride over its T rows.  ce[b] = (1/T) sum_t mask * (lse - logit[label]).
+// metrics[0..3] += {sum of min(nll, -log 1e-10), #non-pad labels, #argmax hits, #top-k hits}.
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int ld,
+                                                     const int* __restrict__ labels, float* __restrict__ ce,
+                                                     float* __restrict__ lse_out, float* __restrict__ metrics, int T,
+                                                     int V, int top_k, int denom) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float ce_acc = 0.f, m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
+  for (int t = warp; t < T; t += nw) {
+    const size_t row = (size_t)b * T + t;
+    const float* x = logits + row * ld;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int v = lane; v < V; v += 32) sum += expf(x[v] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    if (lane == 0) lse_out[row] = lse;
+    const int label = labels[row];
+    if (label != 0) {
+      const float picked = x[min(max(label, 0), V - 1)];
+      int greater = 0;
+      for (int v = lane; v < V; v += 32) greater += x[v] > picked ? 1 : 0;
+      greater = (int)warp_sum((float)greater);
+      const float nll = lse - picked;
+      ce_acc += nll;
+      m_nll += fminf(nll, 23.02585093f);
+      m_tok += 1.f;
+      m_hit += greater == 0 ? 1.f : 0.f;
+      m_topk += greater < top_k ? 1.f : 0.f;
+    }
+  }
+  __shared__ float red[8][5];
+  if (lane == 0) {
+    red[warp][0] = ce_acc; red[warp][1] = m_nll; red[warp][2] = m_tok; red[warp][3] = m_hit; red[warp][4] = m_topk;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < nw; ++w)
+      for (int j = 0; j < 5; ++j) a[j] += red[w][j];
+    ce[b] = a[0] / denom;
+    if (metrics) {
+      atomicAdd(metrics + 0, a[1]);
+      atomicAdd(metrics + 1, a[2]);
+      atomicAdd(metrics + 2, a[3]);
+      atomicAdd(metrics + 3, a[4]);
+    }
+  }
+}
+
+// in place: logits <- d ce_b / d logits * gout[b] = (softmax - onehot) * mask * gout[b] / T ; pad columns zeroed
+__global__ void __launch_bounds__(256) ce_bwd_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
+                                                     const float* __restrict__ lse, const float* __restrict__ gout,
+                                                     long long rows, int T, int V, int denom) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* x = logits + row * ld;
+  const int label = labels[row];
+  const float g = label != 0 ? (gout ? gout[row / T] : 1.f) / denom : 0.f;
+  const float l = lse[row];
+  for (int v = lane; v < ld; v += 32) {
+    float d = 0.f;
+    if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
+    x[v] = d;
+  }
+}
+
+// probs = softmax(logits) (API parity with Model.hybrid_forward's first return value)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ logits, int ld,
+                                                           float* __restrict__ probs, long long rows, int V) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* x = logits + row * ld;
+  float mx = -INFINITY;
+  for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int v = lane; v < V; v += 32) sum += expf(x[v] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int v = lane; v < V; v += 32) probs[row * V + v] = expf(x[v] - mx) * inv;
+}
+
+// SoftmaxCrossEntropy on PROBABILITIES (loss.py:16-23), forward only (API parity; training uses ce_fwd on logits)
+__global__ void __launch_bounds__(128) ce_from_probs_kernel(const float* __restrict__ probs,
+                                                            const int* __restrict__ labels, float* __restrict__ ce,
+                                                            int T, int V) {
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int label = labels[(size_t)b * T + t];
+    if (label != 0) acc -= logf(probs[((size_t)b * T + t) * V + min(max(label, 0), V - 1)]);
+  }
+  __shared__ float red[4];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) ce[b] = (red[0] + red[1] + red[2] + red[3]) / T;
+}
+
+// ---------------------------------------------------------------- sigmoid BCE on piano rolls
+struct BceCfg {
+  int from_sigmoid;
+  float smoothing;
+  int downweight;
+};
+
+__device__ __forceinline__ float bce_elem(float x, float y, const BceCfg& c, float w, float* dldx) {
+  const float p = c.from_sigmoid ? x : 1.f / (1.f + expf(-x));
+  const float ys = (1.f - c.smoothing) * y + c.smoothing * 0.5f;
+  const float lp = logf(1e-12f + p), lq = logf(1e-12f + (1.f - p));
+  float bce = -(ys * lp + (1.f - ys) * lq);
+  float dbdp = -(ys / (1e-12f + p) - (1.f - ys) / (1e-12f + (1.f - p)));
+  float dl = dbdp;
+  if (c.downweight && y == 0.f) {
+    dl = 2.f * w * bce * dbdp;
+    bce = (w * bce) * bce;
+  }
+  if (dldx) *dldx = c.from_sigmoid ? dl : dl * p * (1.f - p);
+  return bce;
+}
+
+// one CTA per sample: count positives, then mean over the S*P cells; optionally write the gradient
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ label,
+                                                  float* __restrict__ out, const float* __restrict__ gout,
+                                                  float* __restrict__ dpred, int n, BceCfg cfg) {
+  const int b = blockIdx.x;
+  const float* x = pred + (size_t)b * n;
+  const uint8_t* y = label + (size_t)b * n;
+  __shared__ float red[8];
+  __shared__ float w_sh;
+  float npos = 0.f;
+  if (cfg.downweight) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) npos += y[i] == 1 ? 1.f : 0.f;
+    npos = warp_sum(npos);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = npos;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+      w_sh = t / ((float)n - t + 1e-12f);
+    }
+    __syncthreads();
+  }
+  const float w = cfg.downweight ? w_sh : 0.f;
+  const float g = dpred ? (gout ? gout[b] : 1.f) / n : 0.f;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float d;
+    acc += bce_elem(x[i], (float)y[i], cfg, w, dpred ? &d : nullptr);
+    if (dpred) dpred[(size_t)b * n + i] = d * g;
+  }
+  acc = warp_sum(acc);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && out) {
+    float t = 0.f;
+    for (int wv = 0; wv < (blockDim.x >> 5); ++wv) t += red[wv];
+    out[b] = t / n;
+  }
+}
+
+}  // namespace
+
+extern "C" int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, int B, int Z, void* stream) {
+  MSX_REQUIRE(lat && eps && z && kl, "msx_reparam_kl_fwd: null pointer");
+  if (B == 0) return MSX_OK;
+  reparam_kl_fwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(lat, eps, z, kl, Z);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_reparam_kl_bwd(const float* lat, const float* eps, const float* dz, const float* gkl, float kl_weight,
+                                  float* dlat, int B, int Z, void* stream) {
+  MSX_REQUIRE(lat && eps && dlat, "msx_reparam_kl_bwd: null pointer");
+  if (B == 0) return MSX_OK;
+  const long long n = (long long)B * Z;
+  reparam_kl_bwd_kernel<<<msx_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(lat, eps, dz, gkl, kl_weight, dlat, B, Z);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_normal_fill(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                               void* stream) {
+  MSX_REQUIRE(out || n == 0, "msx_normal_fill: null pointer");
+  if (n == 0) return MSX_OK;
+  normal_fill_kernel<<<msx_ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, float* ce, float* lse, float* metrics,
+                          int B, int T, int V, int denom, int top_k, void* stream) {
+  MSX_REQUIRE(logits && labels && ce && lse, "msx_ce_fwd: null pointer");
+  MSX_REQUIRE(ld >= V && V > 0, "msx_ce_fwd: bad leading dimension");
+  if (B == 0) return MSX_OK;
+  MSX_REQUIRE(denom > 0, "msx_ce_fwd: denom must be > 0");
+  ce_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, ce, lse, metrics, T, V, top_k, denom);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B,
+                          int T, int V, int denom, void* stream) {
+  MSX_REQUIRE(logits_inout && labels && lse, "msx_ce_bwd: null pointer");
+  if (B == 0) return MSX_OK;
+  const long long rows = (long long)B * T;
+  ce_bwd_kernel<<<msx_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(logits_inout, ld, labels, lse, gout, rows, T, V, denom);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_softmax_rows(const float* logits, int ld, float* probs, long long rows, int V, void* stream) {
+  MSX_REQUIRE(logits && probs, "msx_softmax_rows: null pointer");
+  if (rows == 0) return MSX_OK;
+  softmax_rows_kernel<<<msx_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, probs, rows, V);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_ce_from_probs(const float* probs, const int32_t* labels, float* ce, int B, int T, int V,
+                                 void* stream) {
+  MSX_REQUIRE(probs && labels && ce, "msx_ce_from_probs: null pointer");
+  if (B == 0) return MSX_OK;
+  ce_from_probs_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(probs, labels, ce, T, V);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_bce(const float* pred, const uint8_t* label, float* out, const float* gout, float* dpred, int B,
+                       int n_per_sample, int from_sigmoid, float label_smoothing, int downweight, void* stream) {
+  MSX_REQUIRE(pred && label && (out || dpred), "msx_bce: null pointer");
+  if (B == 0) return MSX_OK;
+  BceCfg cfg{from_sigmoid, label_smoothing, downweight};
+  bce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pred, label, out, gout, dpred, n_per_sample, cfg);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

@@ -1,0 +1,476 @@
+"""VarAutoEncoder step engine: flat parameter arena + hand-scheduled forward / backward / Adam.
+
+Host-side orchestration of the hot path the reference runs as
+``Trainer._step`` (VarAutoEncoder/trainer.py:155-179): ``Model.hybrid_forward`` (model.py:287-296),
+``SoftmaxCrossEntropy`` + ``VariationalKLLoss`` (loss.py), ``loss.backward()`` and
+``gluon.Trainer.step(batch_size)``.  Every device operation is a libmsx kernel (ops.py); torch only
+owns the buffers and the stream.  The schedule is static, so a whole step is CUDA-graph capturable.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+
+NUM_EVENTS = 293     # MIDIUtil/defaults.py:58
+SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 1: ff hidden, 2: ff out}
+
+
+class VAEConfig:
+    """Flat mirror of ModelConfig (model.py:11-54) + TransformerConfig (transformer.py:8-21) + LSTMConfig."""
+
+    def __init__(self, vocab=NUM_EVENTS, num_classes=2, enc_size=256, enc_layers=2, enc_heads=8, latent=256,
+                 dec_type="lstm", dec_size=128, dec_layers=1, dec_heads=8, enc_dropout=0.0, dec_dropout=0.0):
+        assert dec_type in ("lstm", "transformer")
+        assert enc_size % enc_heads == 0
+        if dec_type == "transformer":
+            assert dec_size % dec_heads == 0
+        else:
+            assert dec_layers == 1, "the fused LSTM path implements n_layers == 1 (scripts/train-vae.sh)"
+        self.vocab, self.num_classes = vocab, num_classes
+        self.enc_size, self.enc_layers, self.enc_heads = enc_size, enc_layers, enc_heads
+        self.latent = latent
+        self.dec_type, self.dec_size, self.dec_layers, self.dec_heads = dec_type, dec_size, dec_layers, dec_heads
+        self.enc_dropout, self.dec_dropout = enc_dropout, dec_dropout
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+
+def _tf_layer_entries(prefix, D, ln2):
+    """Arena order inside a transformer layer: the K,Q,V projections are adjacent so that one
+    [3D, D] GEMM serves transformer.py:88-93."""
+    e = []
+    for n in ("W_k", "W_q", "W_v"):
+        e.append((prefix + "self_attention." + n + ".weight", (D, D)))
+    for n in ("W_k", "W_q", "W_v"):
+        e.append((prefix + "self_attention." + n + ".bias", (D,)))
+    e += [(prefix + "self_attention.W_proj.weight", (D, D)), (prefix + "self_attention.W_proj.bias", (D,)),
+          (prefix + "ln1.gamma", (D,)), (prefix + "ln1.beta", (D,)),
+          (prefix + "ff.ff1.weight", (4 * D, D)), (prefix + "ff.ff1.bias", (4 * D,)),
+          (prefix + "ff.ff2.weight", (D, 4 * D)), (prefix + "ff.ff2.bias", (D,)),
+          (prefix + ln2 + ".gamma", (D,)), (prefix + ln2 + ".beta", (D,))]
+    return e
+
+
+def param_entries(cfg):
+    """(name, shape) in arena order.  Names follow the Gluon attribute paths of model.py / transformer.py."""
+    D, Z, V, C, H = cfg.enc_size, cfg.latent, cfg.vocab, cfg.num_classes, cfg.dec_size
+    e = [("encoder.class2hid.weight", (C, D)), ("encoder.encoder_embedding.weight", (V, D))]
+    for l in range(cfg.enc_layers):
+        e += _tf_layer_entries("encoder.encoder.layer%d." % l, D, "ln2")
+    e += [("encoder.latent_proj.weight", (2 * Z, D)), ("encoder.latent_proj.bias", (2 * Z,))]
+    if cfg.dec_type == "lstm":
+        e += [("decoder.latent2hid.weight", (2 * H, Z)), ("decoder.latent2hid.bias", (2 * H,)),
+              ("decoder.class2hid.weight", (C, 2 * H)), ("decoder.embedding.weight", (V, H))]
+        for l in range(cfg.dec_layers):
+            e += [("decoder.decoder.l%d_i2h_weight" % l, (4 * H, H)), ("decoder.decoder.l%d_h2h_weight" % l, (4 * H, H)),
+                  ("decoder.decoder.l%d_i2h_bias" % l, (4 * H,)), ("decoder.decoder.l%d_h2h_bias" % l, (4 * H,))]
+    else:
+        e += [("decoder.latent2hid.weight", (H, Z)), ("decoder.latent2hid.bias", (H,)),
+              ("decoder.class2hid.weight", (C, H)), ("decoder.embedding.weight", (V, H))]
+        for l in range(cfg.dec_layers):
+            e += _tf_layer_entries("decoder.decoder.layer%d." % l, H, "ln3")
+    e += [("decoder.output_layer.weight", (V, H)), ("decoder.output_layer.bias", (V,))]
+    return e
+
+
+def positional_encodings(model_size, max_len):
+    """transformer.py:204-211, computed on the host in float64 exactly as the reference does, cast to fp32."""
+    pe = np.arange(max_len).reshape((-1, 1)) / np.power(10000, (2.0 / model_size) * np.arange(model_size).reshape((1, -1)))
+    pe[:, 0::2] = np.sin(pe[:, 0::2])
+    pe[:, 1::2] = np.cos(pe[:, 1::2])
+    return pe.astype(np.float32)
+
+
+class ParamArena:
+    """Parameters, gradients and Adam moments as four flat fp32 arenas (every tensor 16-byte aligned)."""
+
+    def __init__(self, cfg, device):
+        self.entries = param_entries(cfg)
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shape in self.entries:
+            n = int(np.prod(shape))
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4
+        self.numel = off
+        self.n_params = sum(n for _, n, _ in self.offsets.values())
+        self.w = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        self.adam_state = torch.zeros(4, dtype=torch.float32, device=device)   # [t, lr_t, -, -]
+
+    def view(self, name, arena=None):
+        off, n, shape = self.offsets[name]
+        return (self.w if arena is None else arena)[off:off + n].view(shape)
+
+    def grad(self, name):
+        return self.view(name, self.g)
+
+    def span(self, first, last, arena=None):
+        """Contiguous slab from tensor `first` through tensor `last` (adjacent in the arena, no padding gaps)."""
+        a = self.offsets[first][0]
+        off, n, _ = self.offsets[last]
+        return (self.w if arena is None else arena)[a:off + n]
+
+    def names(self):
+        return list(self.offsets)
+
+    def init_xavier(self, seed=0):
+        """Trainer._initialize_model, trainer.py:103-105: mx.init.Xavier() = uniform(+-sqrt(3 / ((fan_in+fan_out)/2)))
+        on every weight, zeros on bias / beta, ones on gamma.  Host-side generation (one-off)."""
+        g = torch.Generator().manual_seed(seed)
+        for name, (off, n, shape) in self.offsets.items():
+            if name.endswith("gamma"):
+                t = torch.ones(shape)
+            elif name.endswith("bias") or name.endswith("beta"):
+                t = torch.zeros(shape)
+            else:
+                scale = math.sqrt(3.0 / ((shape[0] + shape[1]) / 2.0))
+                t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * scale
+            self.view(name).copy_(t)
+
+    def load_state(self, state):
+        for name in self.offsets:
+            self.view(name).copy_(torch.as_tensor(state[name]).to(self.w.device, torch.float32))
+
+    def state_dict(self):
+        return OrderedDict((name, self.view(name).detach().cpu().clone()) for name in self.offsets)
+
+
+class _Buffers:
+    """Activation / gradient workspace for one (B, T) shape."""
+
+    def __init__(self):
+        self.t = {}
+
+    def get(self, name, shape, device, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        buf = self.t.get(key)
+        if buf is None:
+            buf = torch.empty(shape, dtype=dtype, device=device)
+            self.t[key] = buf
+        return buf
+
+
+class VAEEngine:
+    def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.arena = ParamArena(cfg, self.device)
+        self.arena.init_xavier(seed)
+        self.pe_enc = torch.from_numpy(positional_encodings(cfg.enc_size, max_len)).to(self.device)
+        self.pe_dec = (torch.from_numpy(positional_encodings(cfg.dec_size, max_len)).to(self.device)
+                       if cfg.dec_type == "transformer" else None)
+        self.max_len = max_len
+        self.ldv = (cfg.vocab + 3) // 4 * 4          # padded leading dimension of the logits
+        self.metrics = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._bufs = {}
+        self.dropout_seed = 0x5EED
+        self.step_count = 0
+        self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.ctx = None
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, B, T):
+        b = self._bufs.get((B, T))
+        if b is None:
+            b = _Buffers()
+            self._bufs[(B, T)] = b
+        return b
+
+    def _W(self, name):
+        return self.arena.view(name)
+
+    def _G(self, name):
+        return self.arena.grad(name)
+
+    def _dense_fwd(self, x, ldx, M, name_w, name_b, out, ldo, N, K, relu=False, drop_p=0.0, site=0, accumulate=False,
+                   w=None, b=None):
+        w = self._W(name_w) if w is None else w
+        b = (self._W(name_b) if name_b else None) if b is None else b
+        ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+                 site=site, accumulate=accumulate)
+
+    def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
+                   accumulate_dx=False):
+        """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy), dx [M,K] (=|+=) dy w (optionally masked by aux)."""
+        sk = ops.wgrad_splitk(N, K, M, self.sms)
+        ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=max(sk, 2), colsum=gb)
+        if dx is not None:
+            ops.gemm(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
+                     accumulate=accumulate_dx)
+
+    # ------------------------------------------------------------------ transformer layer
+    def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder):
+        M = B * T
+        dev = self.device
+        a = self.arena
+        qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
+        wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
+        bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
+        self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
+        ctx = bf.get(tag + "ctx", (M, D), dev)
+        ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
+        proj = bf.get(tag + "proj", (M, D), dev)
+        self._dense_fwd(ctx, D, M, prefix + "self_attention.W_proj.weight", prefix + "self_attention.W_proj.bias",
+                        proj, D, D, D)
+        x1 = bf.get(tag + "x1", (M, D), dev)
+        st1 = bf.get(tag + "st1", (2, M), dev)
+        ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
+                       drop_p=p, seed=self.dropout_seed, site=site0)
+        h = bf.get(tag + "h", (M, 4 * D), dev)
+        self._dense_fwd(x1, D, M, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", h, 4 * D, 4 * D, D, relu=True,
+                        drop_p=p, site=site0 + 1)
+        f = bf.get(tag + "f", (M, D), dev)
+        self._dense_fwd(h, 4 * D, M, prefix + "ff.ff2.weight", prefix + "ff.ff2.bias", f, D, D, 4 * D)
+        out = bf.get(tag + "out", (M, D), dev)
+        st2 = bf.get(tag + "st2", (2, M), dev)
+        ln2 = "ln3" if decoder else "ln2"
+        # encoder: ln2(x1 + drop(f)) (transformer.py:158); decoder: ln3(f + drop(f)) (transformer.py:200)
+        ops.add_ln_fwd(f if decoder else x1, f, self._W(prefix + ln2 + ".gamma"), self._W(prefix + ln2 + ".beta"), out,
+                       st2[0], st2[1], M, D, drop_p=p, seed=self.dropout_seed, site=site0 + 2)
+        return out
+
+    def _tf_layer_bwd(self, bf, tag, prefix, x_in, mask, dout, dx_in, B, T, D, H, p, site0, decoder):
+        """dout [M,D] = grad wrt the layer output (overwritten as scratch); writes grad wrt x_in into dx_in."""
+        M = B * T
+        dev = self.device
+        a = self.arena
+        qkv, ctx, proj = bf.t[(tag + "qkv", (M, 3 * D), torch.float32)], bf.t[(tag + "ctx", (M, D), torch.float32)], \
+            bf.t[(tag + "proj", (M, D), torch.float32)]
+        x1, st1 = bf.t[(tag + "x1", (M, D), torch.float32)], bf.t[(tag + "st1", (2, M), torch.float32)]
+        h, f = bf.t[(tag + "h", (M, 4 * D), torch.float32)], bf.t[(tag + "f", (M, D), torch.float32)]
+        st2 = bf.t[(tag + "st2", (2, M), torch.float32)]
+        inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
+        ln2 = "ln3" if decoder else "ln2"
+        dx1 = bf.get(tag + "dx1", (M, D), dev)
+        df = bf.get(tag + "df", (M, D), dev)
+        if decoder:
+            ops.add_ln_bwd(f, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, df, None,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
+                           seed=self.dropout_seed, site=site0 + 2, fuse_xy=True)
+        else:
+            ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, df if p > 0 else None,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
+                           seed=self.dropout_seed, site=site0 + 2)
+            if p <= 0:
+                df = dx1
+        # ff2: f = h W2^T + b2
+        dh = bf.get(tag + "dh", (M, 4 * D), dev)
+        self._dense_bwd(df, D, M, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
+                        self._G(prefix + "ff.ff2.bias"), D, 4 * D, dx=dh, lddx=4 * D, aux=h, ldaux=4 * D,
+                        aux_scale=inv_keep)
+        # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
+        self._dense_bwd(dh, 4 * D, M, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
+                        self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D, accumulate_dx=not decoder)
+        # ln1(x_in + drop(proj))
+        dproj = bf.get(tag + "dproj", (M, D), dev)
+        ops.add_ln_bwd(x_in, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dx_in, dproj if p > 0 else None,
+                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), M, D, drop_p=p,
+                       seed=self.dropout_seed, site=site0)
+        if p <= 0:
+            dproj = dx_in
+        dctx = bf.get(tag + "dctx", (M, D), dev)
+        self._dense_bwd(dproj, D, M, ctx, D, self._W(prefix + "self_attention.W_proj.weight"),
+                        self._G(prefix + "self_attention.W_proj.weight"), self._G(prefix + "self_attention.W_proj.bias"),
+                        D, D, dx=dctx, lddx=D)
+        dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
+        ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
+        wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
+        gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
+        gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
+        self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
+                z_override=None):
+        """tokens int32 [B,T], seq_lens int32 [B], classes int32 [B], labels int32 [B,T] (optional),
+        eps fp32 [B,Z] (None -> Philox N(0,1)).  Returns dict(ce, kl, means, stds[, probs])."""
+        cfg, dev = self.cfg, self.device
+        B, T = tokens.shape
+        D, Z, V, Hd = cfg.enc_size, cfg.latent, cfg.vocab, cfg.dec_size
+        assert T + 1 <= self.max_len
+        bf = self._buf(B, T)
+        M = B * T
+        pe_ = cfg.enc_dropout if train else 0.0
+        pd_ = cfg.dec_dropout if train else 0.0
+        self.dropout_seed = (0x5EED0000 + self.step_count) & 0xFFFFFFFFFFFF
+
+        # ---- encoder (model.py:73-104)
+        x = bf.get("enc.x0", (M, D), dev)
+        mask = bf.get("enc.mask", (M,), dev)
+        ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
+                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V)
+        xs = [x]
+        for l in range(cfg.enc_layers):
+            x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads, pe_,
+                                   l * SITE_STRIDE, False)
+            xs.append(x)
+        lat = bf.get("lat", (B, 2 * Z), dev)
+        self._dense_fwd(x, T * D, B, "encoder.latent_proj.weight", "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
+        if eps is None:
+            eps = bf.get("eps", (B, Z), dev)
+            ops.normal_fill(eps, self.dropout_seed, 0xE95)
+        z = bf.get("z", (B, Z), dev)
+        kl = bf.get("kl", (B,), dev)
+        ops.reparam_kl_fwd(lat, eps, z, kl, B, Z)
+        if z_override is not None:
+            z = z_override
+
+        # ---- decoder
+        if cfg.dec_type == "lstm":
+            tv = bf.get("dec.tvec", (B, 2 * Hd), dev)          # latent2hid(z) + class2hid[classes] (model.py:160)
+            ops.embed_fwd(classes, None, None, self._W("decoder.class2hid.weight"), None, None, None, tv, None, B, 1,
+                          2 * Hd, 0, 1.0, cfg.num_classes)
+            self._dense_fwd(z, Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
+                            accumulate=True)
+            xe = bf.get("dec.xe", (M, Hd), dev)
+            ops.embed_fwd(tokens, None, None, self._W("decoder.embedding.weight"), None, None, None, xe, None, B, T, Hd, 0,
+                          1.0, V)
+            gates = bf.get("dec.gates", (M, 4 * Hd), dev)
+            self._dense_fwd(xe, Hd, M, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
+                            4 * Hd, Hd)
+            hs = bf.get("dec.hs", (M, Hd), dev)
+            hprev = bf.get("dec.hprev", (M, Hd), dev)
+            cs = bf.get("dec.cs", (M, Hd), dev)
+            ops.lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
+                         tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            dec_out, Td = hs, T
+            dmask = None
+        else:
+            Td = T + 1
+            Md = B * Td
+            s0 = bf.get("dec.s0", (B, Hd), dev)                # model.py:229-232
+            ops.embed_fwd(classes, None, None, self._W("decoder.class2hid.weight"), None, None, None, s0, None, B, 1, Hd,
+                          0, 1.0, cfg.num_classes)
+            self._dense_fwd(z, Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", s0, Hd, Hd, Z,
+                            accumulate=True)
+            xd = bf.get("dec.x0", (Md, Hd), dev)
+            dmask = bf.get("dec.mask", (Md,), dev)
+            ops.embed_fwd(tokens, None, seq_lens, self._W("decoder.embedding.weight"), None, s0, self.pe_dec, xd, dmask, B,
+                          T, Hd, 1, math.sqrt(float(Hd)), V)
+            dxs = [xd]
+            for l in range(cfg.dec_layers):
+                xd = self._tf_layer_fwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, xd, dmask, B, Td, Hd,
+                                        cfg.dec_heads, pd_, (8 + l) * SITE_STRIDE, True)
+                dxs.append(xd)
+            dec_out = xd
+        Mo = B * Td
+        logits = bf.get("logits", (Mo, self.ldv), dev)
+        self._dense_fwd(dec_out, Hd, Mo, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V,
+                        Hd)
+        out = {"kl": kl, "means": lat[:, :Z], "stds": lat[:, Z:], "z": z}
+        lab_full = None
+        if labels is not None:
+            if cfg.dec_type == "transformer":
+                lab_full = bf.get("labels_full", (B, Td), dev, torch.int32)
+                lab_full[:, 0] = 0
+                lab_full[:, 1:] = labels
+            else:
+                lab_full = labels
+            ce = bf.get("ce", (B,), dev)
+            lse = bf.get("lse", (Mo,), dev)
+            ops.ce_fwd(logits, self.ldv, lab_full, ce, lse, self.metrics, B, Td, V, T)
+            out["ce"] = ce
+        if want_probs:
+            probs = torch.empty((Mo, V), dtype=torch.float32, device=dev)
+            ops.softmax_rows(logits, self.ldv, probs, Mo, V)
+            probs = probs.view(B, Td, V)
+            out["probs"] = probs[:, 1:, :] if cfg.dec_type == "transformer" else probs
+        self.ctx = dict(B=B, T=T, Td=Td, tokens=tokens, seq_lens=seq_lens, classes=classes, labels=lab_full, eps=eps,
+                        xs=xs, mask=mask, lat=lat, z=z, dec_out=dec_out, logits=logits, pe=pe_, pd=pd_, bf=bf,
+                        dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None)
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, kl_weight=1.0, g_ce=None, g_kl=None):
+        """Accumulates d(sum_b g_ce[b]*ce_b + g_kl[b]*kl_weight*kl_b)/dparams into the gradient arena
+        (trainer.py:172,176: loss = ce + kl_weight*kl, loss.backward() with head gradient ones)."""
+        c = self.ctx
+        cfg, dev, bf = self.cfg, self.device, c["bf"]
+        B, T, Td = c["B"], c["T"], c["Td"]
+        D, Z, V, Hd = cfg.enc_size, cfg.latent, cfg.vocab, cfg.dec_size
+        M, Mo = B * T, B * Td
+        logits = c["logits"]
+        lse = bf.t[("lse", (Mo,), torch.float32)]
+        ops.ce_bwd(logits, self.ldv, c["labels"], lse, g_ce, B, Td, V, T)       # logits now hold dlogits
+        ddec = bf.get("ddec", (Mo, Hd), dev)
+        self._dense_bwd(logits, self.ldv, Mo, c["dec_out"], Hd, self._W("decoder.output_layer.weight"),
+                        self._G("decoder.output_layer.weight"), self._G("decoder.output_layer.bias"), V, Hd,
+                        dx=ddec, lddx=Hd)
+        dz = bf.get("dz", (B, Z), dev)
+        if cfg.dec_type == "lstm":
+            gates = bf.t[("dec.gates", (M, 4 * Hd), torch.float32)]
+            hprev = bf.t[("dec.hprev", (M, Hd), torch.float32)]
+            cs = bf.t[("dec.cs", (M, Hd), torch.float32)]
+            xe = bf.t[("dec.xe", (M, Hd), torch.float32)]
+            tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
+            dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
+            ops.lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
+                         B, T, Hd)                                                  # gates now hold d(pre-activations)
+            dxe = bf.get("dec.dxe", (M, Hd), dev)
+            self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
+                            self._G("decoder.decoder.l0_i2h_weight"), self._G("decoder.decoder.l0_i2h_bias"), 4 * Hd, Hd,
+                            dx=dxe, lddx=Hd)
+            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"),
+                            self._G("decoder.decoder.l0_h2h_bias"), 4 * Hd, Hd)
+            ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
+            ops.embed_bwd(c["classes"], None, dtv, self._G("decoder.class2hid.weight"), None, None, B, 1, 2 * Hd, 0, 1.0,
+                          cfg.num_classes)
+            self._dense_bwd(dtv, 2 * Hd, B, c["z"], Z, self._W("decoder.latent2hid.weight"),
+                            self._G("decoder.latent2hid.weight"), self._G("decoder.latent2hid.bias"), 2 * Hd, Z,
+                            dx=dz, lddx=Z)
+        else:
+            dxs = c["dxs"]
+            dcur = ddec
+            for l in reversed(range(cfg.dec_layers)):
+                dnext = bf.get("dec%d.dxin" % l, (Mo, Hd), dev)
+                self._tf_layer_bwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, dxs[l], c["dmask"], dcur, dnext, B,
+                                   Td, Hd, cfg.dec_heads, c["pd"], (8 + l) * SITE_STRIDE, True)
+                dcur = dnext
+            ds0 = bf.get("dec.ds0", (B, Hd), dev)
+            ops.embed_bwd(c["tokens"], None, dcur, self._G("decoder.embedding.weight"), None, ds0, B, T, Hd, 1,
+                          math.sqrt(float(Hd)), V)
+            ops.embed_bwd(c["classes"], None, ds0, self._G("decoder.class2hid.weight"), None, None, B, 1, Hd, 0, 1.0,
+                          cfg.num_classes)
+            self._dense_bwd(ds0, Hd, B, c["z"], Z, self._W("decoder.latent2hid.weight"),
+                            self._G("decoder.latent2hid.weight"), self._G("decoder.latent2hid.bias"), Hd, Z, dx=dz, lddx=Z)
+        # ---- reparameterisation + KL (model.py:292, loss.py:8-12)
+        dlat = bf.get("dlat", (B, 2 * Z), dev)
+        ops.reparam_kl_bwd(c["lat"], c["eps"], dz, g_kl, kl_weight, dlat, B, Z)
+        # ---- latent projection on the SOS position (model.py:97-100): rows b*T of the last encoder output
+        xs = c["xs"]
+        dx = bf.get("enc.dx_top", (M, D), dev)
+        dx.zero_()
+        self._dense_bwd(dlat, 2 * Z, B, xs[-1], T * D, self._W("encoder.latent_proj.weight"),
+                        self._G("encoder.latent_proj.weight"), self._G("encoder.latent_proj.bias"), 2 * Z, D,
+                        dx=dx, lddx=T * D)
+        for l in reversed(range(cfg.enc_layers)):
+            dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
+            self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
+                               cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+            dx = dnext
+        ops.embed_bwd(c["tokens"], c["classes"], dx, self._G("encoder.encoder_embedding.weight"),
+                      self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, batch_size, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, clip_gradient=None):
+        """gluon.Trainer.step(batch_size) with MXNet-1.3 Adam (trainer.py:94-101,177); also zeroes the gradients."""
+        a = self.arena
+        ops.adam_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, lr, beta1, beta2, eps, wd, 1.0 / batch_size,
+                      clip_gradient, zero_grad=True)
+        self.step_count += 1
+
+    def train_step(self, tokens, seq_lens, classes, labels, eps=None, kl_weight=1.0, global_batch=None, lr=3e-4,
+                   clip_gradient=None, allreduce=None):
+        out = self.forward(tokens, seq_lens, classes, labels, eps=eps, train=True)
+        self.backward(kl_weight)
+        if allreduce is not None:
+            allreduce(self.arena.g)
+        self.adam_step(global_batch or tokens.shape[0], lr=lr, clip_gradient=clip_gradient)
+        return out

@@ -1,0 +1,110 @@
+"""Functional wrappers over the libmsx C ABI (include/msx.h).  No autograd, no allocation policy:
+callers own every buffer (torch CUDA tensors), kernels run on torch's current stream."""
+import ctypes as C
+
+import torch
+
+from . import lib
+
+_i, _f, _ll, _u64, _u32 = C.c_int, C.c_float, C.c_longlong, C.c_ulonglong, C.c_uint
+P = lib.ptr
+
+
+def _chk(t, dtype=torch.float32):
+    assert t.is_cuda and t.dtype == dtype, (t.device, t.dtype)
+    return t
+
+
+def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
+         aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, colsum=None):
+    """C[M,N] = epilogue(opA(A)[M,K] @ opB(B)[K,N]); leading dimensions in elements (row-major storage)."""
+    lib.call("msx_gemm_f32", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
+             _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
+             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr())
+
+
+def wgrad_splitk(M_out, N_out, K_red, sms=148):
+    tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
+    want = max(1, (3 * sms) // max(tiles, 1))
+    return max(1, min(want, (K_red + 511) // 512, 128))
+
+
+def attention_fwd(qkv, mask, ctx, B, T, H, dh):
+    lib.call("msx_attention_fwd", P(qkv), P(mask), P(ctx), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
+def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
+    lib.call("msx_attention_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
+def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0):
+    lib.call("msx_add_ln_fwd", P(x), P(y), P(gamma), P(beta), P(out), P(mean), P(rstd), _ll(M), _i(D), _f(eps),
+             _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
+
+
+def add_ln_bwd(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p=0.0, seed=0, site=0,
+               accumulate_dres=False, fuse_xy=False):
+    lib.call("msx_add_ln_bwd", P(x), P(y), P(gamma), P(mean), P(rstd), P(dout), P(dres), P(dy), P(dgamma), P(dbeta),
+             _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
+             _i(1 if fuse_xy else 0), lib.stream_ptr())
+
+
+def embed_fwd(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab):
+    lib.call("msx_embed_fwd", P(tokens), P(classes), P(seq_lens), P(tok_emb), P(cls_emb), P(prefix_vec), P(pe),
+             P(out), P(mask), _i(B), _i(T), _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
+
+
+def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, prefix, scale, vocab):
+    lib.call("msx_embed_bwd", P(tokens), P(classes), P(dout), P(d_tok_emb), P(d_cls_emb), P(d_prefix), _i(B), _i(T),
+             _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
+
+
+def reparam_kl_fwd(lat, eps, z, kl, B, Z):
+    lib.call("msx_reparam_kl_fwd", P(lat), P(eps), P(z), P(kl), _i(B), _i(Z), lib.stream_ptr())
+
+
+def reparam_kl_bwd(lat, eps, dz, gkl, kl_weight, dlat, B, Z):
+    lib.call("msx_reparam_kl_bwd", P(lat), P(eps), P(dz), P(gkl), _f(kl_weight), P(dlat), _i(B), _i(Z),
+             lib.stream_ptr())
+
+
+def normal_fill(out, seed, offset):
+    lib.call("msx_normal_fill", P(out), _ll(out.numel()), _u64(seed), _u64(offset), lib.stream_ptr())
+
+
+def ce_fwd(logits, ld, labels, ce, lse, metrics, B, T, V, denom, top_k=5):
+    lib.call("msx_ce_fwd", P(logits), _i(ld), P(labels), P(ce), P(lse), P(metrics), _i(B), _i(T), _i(V), _i(denom),
+             _i(top_k), lib.stream_ptr())
+
+
+def ce_bwd(logits, ld, labels, lse, gout, B, T, V, denom):
+    lib.call("msx_ce_bwd", P(logits), _i(ld), P(labels), P(lse), P(gout), _i(B), _i(T), _i(V), _i(denom),
+             lib.stream_ptr())
+
+
+def softmax_rows(logits, ld, probs, rows, V):
+    lib.call("msx_softmax_rows", P(logits), _i(ld), P(probs), _ll(rows), _i(V), lib.stream_ptr())
+
+
+def ce_from_probs(probs, labels, ce, B, T, V):
+    lib.call("msx_ce_from_probs", P(probs), P(labels), P(ce), _i(B), _i(T), _i(V), lib.stream_ptr())
+
+
+def bce(pred, label, out, gout, dpred, B, n, from_sigmoid=False, label_smoothing=0.0, downweight=True):
+    lib.call("msx_bce", P(pred), P(label), P(out), P(gout), P(dpred), _i(B), _i(n), _i(1 if from_sigmoid else 0),
+             _f(label_smoothing), _i(1 if downweight else 0), lib.stream_ptr())
+
+
+def lstm_fwd(gx, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H):
+    lib.call("msx_lstm_fwd", P(gx), P(w_h2h), P(b_h2h), P(h0), P(c0), _i(ld0), P(hs), P(hprev), P(cs), _i(B), _i(T),
+             _i(H), lib.stream_ptr())
+
+
+def lstm_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H):
+    lib.call("msx_lstm_bwd", P(gates), P(w_h2h), P(cs), P(c0), _i(ld0), P(dhs), P(dh0), P(dc0), _i(B), _i(T), _i(H),
+             lib.stream_ptr())
+
+
+def adam_step(w, g, m, v, n, state, lr, beta1, beta2, eps, wd, rescale, clip, zero_grad=True):
+    lib.call("msx_adam_step", P(w), P(g), P(m), P(v), _ll(n), P(state), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd),
+             _f(rescale), _f(clip if clip is not None else 0.0), _i(1 if zero_grad else 0), lib.stream_ptr())
