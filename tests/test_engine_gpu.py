@@ -24,12 +24,16 @@ def _close(name, got, want, rtol=RTOL, atol_frac=1e-3):
     assert not bad.any(), "%s: %d/%d off, max err %.3e (scale %.3e)" % (name, bad.sum(), bad.size, err.max(), scale)
 
 
-def _grad_close(name, got, want):
+def _grad_close(name, got, want, gscale):
+    """1e-3 of the tensor's own gradient scale, plus 2e-5 of the largest gradient in the model: some
+    gradients are exactly zero in exact arithmetic (W_q.bias: the bias shifts every score of a key row
+    by a constant along the reference's softmax axis), so both sides hold only rounding noise there."""
     got = got.detach().cpu().numpy()
     want = want.detach().cpu().numpy()
     scale = float(np.abs(want).max())
     err = float(np.abs(got - want).max())
-    assert err <= 1e-3 * scale + 1e-6, "%s: grad max err %.3e vs scale %.3e" % (name, err, scale)
+    assert err <= 1e-3 * scale + 2e-5 * gscale + 1e-7, "%s: grad max err %.3e vs scale %.3e (global %.3e)" % (
+        name, err, scale, gscale)
 
 
 def _make_engine(cfg_o, params):
@@ -65,7 +69,20 @@ def _dev(t, dtype=torch.int32):
     return t.to(dtype).to("cuda:0").contiguous()
 
 
-def _run_case(cfg_o, params, tokens, seq_lens, classes, labels, eps, clip=1.0, check_probs=None):
+def _condition_sigma(cfg_o, params):
+    """The reference's sigma is the raw latent_proj output (model.py:100-103) and the KL gradient holds
+    1/sigma (loss.py:9): with |sigma| ~ 1e-4 somewhere in the batch an fp32 rounding difference in sigma
+    moves the gradient by per cents.  Gradient parity is therefore checked with sigma kept in ~[2,4]."""
+    Z = cfg_o.latent
+    params = {k: v.clone() for k, v in params.items()}
+    params["encoder.latent_proj.weight"][Z:] *= 0.05
+    params["encoder.latent_proj.bias"][Z:] = 3.0
+    return params
+
+
+def _run_case(cfg_o, params, tokens, seq_lens, classes, labels, eps, clip=1.0, check_probs=None, condition=False):
+    if condition:
+        params = _condition_sigma(cfg_o, params)
     eng = _make_engine(cfg_o, params)
     out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32),
                       want_probs=True)
@@ -81,15 +98,30 @@ def _run_case(cfg_o, params, tokens, seq_lens, classes, labels, eps, clip=1.0, c
         _close("probs-vs-reference", out["probs"], check_probs, rtol=2e-3)
     eng.backward(kl_weight=1.0)
     torch.cuda.synchronize()
+    gscale = max(float(v.abs().max()) for v in grads.values())
+    errors = []
     for name in eng.arena.names():
-        _grad_close(name, eng.arena.grad(name), grads[name])
-    eng.adam_step(tokens.shape[0], lr=3e-4, clip_gradient=clip)
-    torch.cuda.synchronize()
-    for name in eng.arena.names():
-        w_new, w_old = eng.arena.view(name).cpu(), params[name]
-        # the update itself (<= lr per element) must match to 1e-3 of lr-scale
-        d_got, d_want = (w_new - w_old).numpy(), (p[name] - w_old).numpy()
-        assert np.abs(d_got - d_want).max() <= 2e-3 * 3e-4 + 1e-9, name
+        try:
+            _grad_close(name, eng.arena.grad(name), grads[name], gscale)
+        except AssertionError as e:
+            errors.append(str(e).splitlines()[0])
+    assert not errors, "\n".join(errors)
+    # Adam (trainer.py:94-101,177) is checked on the engine's own gradients: first-step Adam maps any
+    # non-zero gradient to +-lr, so exact-zero gradients that hold rounding noise cannot be compared.
+    g_dev = {name: eng.arena.grad(name).cpu().clone() for name in eng.arena.names()}
+    p2 = {k: v.clone() for k, v in params.items()}
+    opt2 = om.Adam(p2, lr=3e-4, clip_gradient=clip)
+    for it in range(3):
+        if it > 0:      # later steps: re-inject the same gradients (arena is zeroed by the fused update)
+            for name in eng.arena.names():
+                eng.arena.grad(name).copy_(g_dev[name] * (1.0 + it))
+        opt2.step(p2, {k: v * (1.0 + it) for k, v in g_dev.items()}, tokens.shape[0])
+        eng.adam_step(tokens.shape[0], lr=3e-4, clip_gradient=clip)
+        torch.cuda.synchronize()
+        for name in eng.arena.names():
+            d_got = (eng.arena.view(name).cpu() - params[name]).numpy()
+            d_want = (p2[name] - params[name]).numpy()
+            assert np.abs(d_got - d_want).max() <= 2e-3 * 3e-4 * (it + 1), (name, it)
     assert float(eng.arena.g.abs().max()) == 0.0     # gradients zeroed for the next step
     return eng
 
@@ -121,11 +153,14 @@ def test_small_ragged_transformer_decoder(golden_dir):
     tokens, seq_lens, classes = (torch.from_numpy(g[k]) for k in ("tokens", "seq_lens", "classes"))
     labels = torch.cat([tokens[:, 1:], torch.zeros(tokens.shape[0], 1)], 1)
     eps = torch.randn(tokens.shape[0], 32, generator=torch.Generator().manual_seed(9))
-    eng = _run_case(cfg, p, tokens, seq_lens, classes, labels, eps)
-    # encoder outputs against the reference-generated golden directly
-    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), None, eps=_dev(eps, torch.float32))
-    # (weights moved by one Adam step of 3e-4 -> compare loosely)
-    assert np.abs(out["means"].cpu().numpy() - g["means"]).max() < 5e-2
+    # forward against the reference-generated golden vectors (raw parameters)
+    eng = _make_engine(cfg, p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), None, eps=_dev(eps, torch.float32),
+                      want_probs=True, z_override=_dev(torch.from_numpy(g["z"]), torch.float32))
+    _close("means-vs-reference", out["means"], g["means"])
+    _close("stds-vs-reference", out["stds"], g["stds"])
+    _close("probs-vs-reference", out["probs"], g["tdec_probs"], rtol=2e-3)
+    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
 
 
 def test_small_ragged_lstm_decoder(golden_dir):
@@ -137,7 +172,11 @@ def test_small_ragged_lstm_decoder(golden_dir):
     tokens, seq_lens, classes = (torch.from_numpy(g[k]) for k in ("tokens", "seq_lens", "classes"))
     labels = torch.cat([tokens[:, 1:], torch.zeros(tokens.shape[0], 1)], 1)
     eps = torch.randn(tokens.shape[0], 32, generator=torch.Generator().manual_seed(9))
-    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps)
+    eng = _make_engine(cfg, p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), None, eps=_dev(eps, torch.float32),
+                      want_probs=True, z_override=_dev(torch.from_numpy(g["z"]), torch.float32))
+    _close("probs-vs-reference", out["probs"], g["ldec_probs"], rtol=2e-3)
+    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
 
 
 @pytest.mark.parametrize("dec_type", ["lstm", "transformer"])
@@ -153,11 +192,18 @@ def test_train_vae_config_step(dec_type):
         elif k.endswith("gamma"):
             p[k] = 1.0 + 0.05 * torch.randn(p[k].shape, generator=gen)
     tokens, seq_lens, classes, labels, eps = _batch(32, 65, 293, 2, 256, seed=1, min_len=33)
-    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps)
+    # raw Xavier init: forward parity (loss, KL, latent means) as BASELINE.json states it
+    eng = _make_engine(cfg, p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
+    _, ce, kl, _, means, stds = om.step_losses(cfg, p, tokens, seq_lens, classes, labels, eps)
+    _close("means", out["means"], means)
+    _close("kl", out["kl"], kl)
+    _close("ce", out["ce"], ce)
+    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
 
 
 def test_odd_batch_sizes_lstm():
     cfg = om.Cfg(enc_size=64, enc_layers=1, enc_heads=2, latent=16, dec_type="lstm", dec_size=64)
     p = om.init_params(cfg, seed=3)
     tokens, seq_lens, classes, labels, eps = _batch(37, 19, 293, 2, 16, seed=7)
-    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps)
+    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
