@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (contract in the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on rank 0.  `value` = whole-job VAE training throughput (sequences/s) with the batch
+resident in HBM; `e2e` = the same step driven from pinned HOST buffers (H2D of the batch + D2H of the
+per-sample losses inside the timed region).  `roofline` describes the dominant kernel of the step,
+`rasteriser` the K1 note-event rasteriser on BASELINE config 2 (roll GB/s), `cpu_baseline` the oracle
+(CPU restatement of the reference step) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "vae_train_sequences_per_sec"
+UNIT = "sequences/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2048, help="sequences per GPU per step")
+    ap.add_argument("--seq-len", type=int, default=64)
+    ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
+    ap.add_argument("--dropout", type=float, default=0.2)
+    ap.add_argument("--cpu-batch", type=int, default=64, help="rows per oracle step (bounded CPU sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-raster", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return ("VarAutoEncoder train step (fwd+bwd+Adam) fp32, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
+            "dec %s 1x128, dropout %.1f, B=%d per GPU, L=%d (T=%d), synthetic 4/4 token rows"
+            % (args.dec_type, args.dropout, args.batch, args.seq_len, args.seq_len + 1))
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def oracle_step_rate(args, steps, warmup, threads=None):
+    """Times the oracle (CPU restatement of Trainer._step, trainer.py:155-179) on a bounded sample."""
+    import torch
+    from musicstyletransfer_b200 import synth
+    from oracle import model as om
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = om.Cfg(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
+    p = om.init_params(cfg, seed=0)
+    opt = om.Adam(p, lr=3e-4, clip_gradient=1.0)
+    Bc = args.cpu_batch
+    tok, lens, cls, lab = synth.token_rows_4_4(Bc * 2, args.seq_len, seed=1)
+    t = lambda a: torch.from_numpy(a).float()
+    batches = [(t(tok[i * Bc:(i + 1) * Bc]), t(lens[i * Bc:(i + 1) * Bc]), t(cls[i * Bc:(i + 1) * Bc]),
+                t(lab[i * Bc:(i + 1) * Bc])) for i in range(2)]
+    g = torch.Generator().manual_seed(0)
+    times = []
+    for i in range(warmup + steps):
+        tk, ln, cl, lb = batches[i % 2]
+        eps = torch.randn(Bc, cfg.latent, generator=g)
+        t0 = time.perf_counter()
+        om.train_step(cfg, p, opt, tk, ln, cl, lb, eps, masks="random" if args.dropout > 0 else None)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return Bc * len(times) / total, total / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    rate, per_step, cores = oracle_step_rate(args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "reference = CPU oracle (the reference's MXNet 1.3 stack "
+                   "cannot run here, SURVEY.md §8(c)); each step is a %d-row sample of the workload" % args.cpu_batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d oracle steps of %d rows (torch-CPU fp32, all host threads)" % (steps, args.cpu_batch)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- our arm
+def bench_rasteriser(peaks):
+    import torch
+    from musicstyletransfer_b200 import featurise, synth
+    dtick, pitch, vel, offs = synth.note_events()
+    dev = "cuda"
+    d = [torch.from_numpy(a).to(dev) for a in (dtick, pitch, vel, offs)]
+    n = offs.size - 1
+    # two output sets (2 x 277 MB) alternate so that consecutive launches never hit the 126 MB L2
+    outs = [(torch.empty((n, 65), dtype=torch.int32, device=dev), torch.empty((n, 64, 128), dtype=torch.uint8, device=dev),
+             torch.empty((n,), dtype=torch.int32, device=dev)) for _ in range(2)]
+    for i in range(4):
+        featurise.rasterize(*d, out=outs[i % 2])
+    torch.cuda.synchronize()
+    reps = 20
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(reps):
+        evs[i][0].record()
+        featurise.rasterize(*d, out=outs[i % 2])
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    med = ms[len(ms) // 2]
+    E = dtick.size
+    bytes_alg = 6 * E + 4 * (n + 1) + n * 64 * 128 + n * 65 * 4 + n * 4
+    gbs = bytes_alg / (med * 1e-3) / 1e9
+    return {"workload": "BASELINE config 2: 1,048,576 note events, 32768 sequences -> tokens int32[N,65] + roll uint8[N,64,128]",
+            "ms": med, "events_per_s": E / (med * 1e-3), "roll_GBps": gbs,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": bytes_alg,
+                         "peak_source": peaks["src"]}}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from musicstyletransfer_b200 import lib, synth
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    peaks = measured_peaks()
+
+    cfg = VAEConfig(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
+    eng = VAEEngine(cfg, dev, seed=0)
+    B, L = args.batch, args.seq_len
+    T = L + 1
+    n_batches = 4
+    tok, lens, cls, lab = synth.token_rows_4_4(B * n_batches, L, seed=100 + rank)
+    host = []
+    for i in range(n_batches):
+        sl = slice(i * B, (i + 1) * B)
+        host.append(tuple(torch.from_numpy(a[sl].copy()).pin_memory() for a in (tok, lens, cls, lab)))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    gbatch = B * world
+
+    def allreduce(g):
+        dist.all_reduce(g)
+
+    ar = allreduce if world > 1 else None
+
+    def step_resident(i):
+        tk, ln, cl, lb = resident[i % n_batches]
+        return eng.train_step(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar)
+
+    stage = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    loss_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hb = host[i % n_batches]
+        db = stage[i % 2]
+        for dst, src in zip(db, hb):
+            dst.copy_(src, non_blocking=True)
+        out = eng.train_step(db[0], db[1], db[2], db[3], kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0,
+                             allreduce=ar)
+        loss_host[0].copy_(out["ce"], non_blocking=True)
+        loss_host[1].copy_(out["kl"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the step's result is read on the host
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.LAUNCHES
+        s.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e.record()
+        barrier()
+        launches = lib.LAUNCHES - l0
+        clocks = sampler.stop() if sampler else None
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    W, K = max(args.warmup, 3), args.steps
+    ms, launches, clocks = timed(step_resident, K, W, sample_clocks=True)
+    value = gbatch * K / (ms * 1e-3)
+    ms_e2e, _, _ = timed(step_e2e, K, 3)
+    e2e_value = gbatch * K / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = loss_host.numel() * loss_host.element_size()
+
+    # ---- dominant kernel (GEMM) roofline: CUDA events around every GEMM launch of a few extra steps
+    roofline = None
+    if rank == 0:
+        prof = {"match": "msx_gemm", "events": []}
+        lib._profile = prof
+        psteps = 3
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(psteps):
+            step_resident(i)
+        e.record()
+        torch.cuda.synchronize()
+        lib._profile = None
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof["events"])
+        gemm_flops = sum(f for _, _, f in prof["events"])
+        step_ms = s.elapsed_time(e)
+        tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)",
+                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
+                    "traffic": None, "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)",
+                    "share_of_step": gemm_ms / step_ms, "launches_per_step": len(prof["events"]) / psteps,
+                    "flops_per_step": gemm_flops / psteps, "avg_launch_ms": gemm_ms / max(1, len(prof["events"]))}
+    if world > 1:
+        barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    raster = None
+    if not args.no_raster:
+        raster = bench_rasteriser(peaks)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, per_step, cores = oracle_step_rate(args, steps=4, warmup=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "4 oracle steps of %d rows (torch-CPU fp32 restatement of Trainer._step, all host threads)" % args.cpu_batch,
+               "ms_per_step": per_step * 1e3}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
+                         (B * T * 4 * 40e3 / 1e9 / 10)},
+        "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+/* libmsx.so — C ABI of the B200-native (sm_100a) hot path of slyforce/MusicStyleTransfer.
+ *
+ * The reference (pure Python on MXNet 1.3) has no FFI layer; its boundary for this path is the L3
+ * Python surface.  Each entry point below names the reference code it replaces
+ * (paths relative to /root/reference/music_style_transfer).  The Python host side
+ * (musicstyletransfer_b200/ops.py, ctypes) binds exactly these symbols; INTEGRATION.md shows the stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (fp32 unless typed otherwise); kernels
+ *     never allocate, never synchronise, and are enqueued on `stream` (a cudaStream_t) — so a whole
+ *     step is CUDA-graph capturable;
+ *   - matrices are row-major, leading dimensions in elements;
+ *   - return value 0 = ok, <0 = error (MSX_ERR_*); msx_last_error() holds the message (thread-local);
+ *   - no C++ types or exceptions cross this boundary.
+ */
+#ifndef MSX_H_
+#define MSX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSX_OK 0
+#define MSX_ERR_ARG (-1)
+#define MSX_ERR_CUDA (-2)
+#define MSX_ERR_UNSUPPORTED (-3)
+
+int msx_version(void);
+const char* msx_last_error(void);
+int msx_device_sm_count(void);
+
+/* K1 — note-event rasteriser.  Replaces EventBasedMIDIReader._parse_track (MIDIUtil/midi_io.py:70-93),
+ * create_{note_on,note_off,timeshift}_event (MIDIUtil/Melody.py:109-126) and the clock semantics of
+ * MelodyWriter._write_track (MIDIUtil/midi_io.py:119-127) for N independent sequences.
+ * dtick int32[E] = ticks since the previous note event; pitch, vel uint8[E]; seq_offsets int32[N+1].
+ * tokens int32[N, max_seq_len+1] (SOS + first L ids, PAD-filled); roll uint8[N, n_slices, 128]
+ * (16-byte aligned); n_tokens int32[N] = untruncated token count. */
+int msx_rasterize(const int32_t* dtick, const uint8_t* pitch, const uint8_t* vel, const int32_t* seq_offsets,
+                  int n_seq, int resolution, int slices_per_quarter, int n_slices, int max_seq_len, int velocity_roll,
+                  int32_t* tokens, uint8_t* roll, int32_t* n_tokens, void* stream);
+
+/* K2 — dense layers.  Replaces every gluon.nn.Dense forward on the path (VarAutoEncoder/transformer.py:36-40,
+ * 65-68,88-93,104; model.py:70-71,139-157,214-227) and its autograd backward (trainer.py:176).
+ * C[M,N] = epilogue(opA(A)[M,K] * opB(B)[K,N]), transX=0: stored as written, transX=1: stored transposed.
+ *   forward  Y = X W^T + b        : transA=0, transB=1, bias, optional relu + dropout(drop_p, seed, site)
+ *   dgrad    dX = dY W            : transA=0, transB=0, optional aux mask (aux>0 ? aux_scale : 0), accumulate
+ *   wgrad    dW += dY^T X, db += : transA=1, transB=0, splitk>1 (atomic adds into a zeroed C), colsum = db
+ * msx_gemm_f32 is the exact-fp32 FFMA kernel; msx_gemm_tc runs the same contract on the tcgen05 tensor
+ * cores (TF32 or BF16 operands, fp32 accumulate in TMEM) for the shapes it supports. */
+int msx_gemm_f32(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
+                 int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
+                 const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, float* colsum,
+                 void* stream);
+
+/* K2c — attention in the reference's convention (softmax over the QUERY axis, additive -1e9 on padded keys,
+ * O = P^T V).  Replaces MultiHeadDotAttention.hybrid_forward lines 91-103 and _mask_logits
+ * (VarAutoEncoder/transformer.py:91-126).  qkv [B*T, 3*H*dh] rows = [K | Q | V]; mask [B*T] (1 = real key). */
+int msx_attention_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
+int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
+                      int dh, void* stream);
+
+/* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
+ * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);
+ * fuse_xy: x and y alias (decoder's ln3(f + drop(f))) and dres receives ds*(1+keep). */
+int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out, float* mean,
+                   float* rstd, long long M, int D, float eps, float drop_p, unsigned long long seed, unsigned site,
+                   void* stream);
+int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+                   const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, long long M, int D,
+                   float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
+                   void* stream);
+
+/* K2a — embedding front end.  Replaces model.py:81-91 + transformer.py:270 (encoder), model.py:241-247 +
+ * transformer.py:237 (Transformer decoder, prefix = 1 latent-state row), model.py:176 (LSTM decoder).
+ * out[b,pos,:] = scale*((pos<prefix ? prefix_vec[b] : tok_emb[tokens[b,pos-prefix]]) + cls_emb[classes[b]]) + pe[pos];
+ * mask[b,pos] = seq_lens ? pos < seq_lens[b]+prefix : token != 0.  NULL disables a term. */
+int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
+                  const float* cls_emb, const float* prefix_vec, const float* pe, float* out, float* mask, int B, int T,
+                  int D, int prefix, float scale, int vocab, void* stream);
+int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
+                  float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
+
+/* K2g — persistent LSTM recurrence.  Replaces the fused gluon.rnn.LSTM call in LSTMDecoder.forward_train
+ * (model.py:148-153,179); gx_inout [B,T,4H] holds x W_i2h^T + b_i2h on entry and the gate activations on exit;
+ * h0/c0 are rows of a [B, ld0] buffer (model.py:159-167).  Backward turns the saved activations into
+ * d(pre-activations) for the surrounding wgrad/dgrad GEMMs and returns dh0/dc0.  H in {32,64,128}. */
+int msx_lstm_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const float* h0, const float* c0, int ld0,
+                 float* hs, float* hprev, float* cs, int B, int T, int H, void* stream);
+int msx_lstm_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0, const float* dhs,
+                 float* dh0, float* dc0, int B, int T, int H, void* stream);
+
+/* K3 — losses.  msx_reparam_kl_*: z = m + eps*s and VariationalKLLoss (model.py:292, loss.py:8-12);
+ * msx_ce_*: softmax(output_layer) + SoftmaxCrossEntropy (model.py:182/256, loss.py:16-23) fused on logits
+ * [B*T, ld], ce[b] = sum_t mask*nll / denom, metrics[4] += {sum nll (clamped like mx.metric.Perplexity),
+ * tokens, top-1 hits, top-k hits} (trainer.py:107-120,181-186, metrics.py); msx_ce_bwd overwrites the logits
+ * with the gradient; msx_softmax_rows / msx_ce_from_probs keep the probability-based API (model.py:296,
+ * loss.py:16-23); msx_bce: BinaryCrossEntropy on uint8 piano rolls (loss.py:27-81), value and/or gradient. */
+int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, int B, int Z, void* stream);
+int msx_reparam_kl_bwd(const float* lat, const float* eps, const float* dz, const float* gkl, float kl_weight,
+                       float* dlat, int B, int Z, void* stream);
+int msx_normal_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, float* ce, float* lse, float* metrics, int B, int T,
+               int V, int denom, int top_k, void* stream);
+int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B, int T,
+               int V, int denom, void* stream);
+int msx_softmax_rows(const float* logits, int ld, float* probs, long long rows, int V, void* stream);
+int msx_ce_from_probs(const float* probs, const int32_t* labels, float* ce, int B, int T, int V, void* stream);
+int msx_bce(const float* pred, const uint8_t* label, float* out, const float* gout, float* dpred, int B,
+            int n_per_sample, int from_sigmoid, float label_smoothing, int downweight, void* stream);
+
+/* K4 — fused multi-tensor Adam over flat arenas.  Replaces gluon.Trainer('adam', ...).step(batch_size)
+ * (trainer.py:94-101,177; MXNet 1.3 Adam: eps outside the bias correction, element-wise clip, rescale = 1/batch).
+ * state[0] = step count t (device-resident), state[1] = lr_t; zero_grad clears g in the same pass. */
+int msx_adam_step(float* w, float* g, float* m, float* v, long long n, float* state, float lr, float beta1, float beta2,
+                  float eps, float wd, float rescale, float clip, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSX_H_ */

@@ -44,6 +44,23 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name, *args):
+# kernels enqueued per C-ABI call (for the bench's gpu_launches claim)
+_KERNELS_PER_CALL = {"msx_adam_step": 2}
+LAUNCHES = 0
+_profile = None     # optional {"match": substring, "events": [(start, end, tag)]} set by bench.py
+
+
+def call(name, *args, tag=None):
+    global LAUNCHES
     fn = getattr(load(), name)
-    check(fn(*args), name)
+    prof = _profile
+    if prof is not None and prof["match"] in name:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(fn(*args), name)
+        e.record()
+        prof["events"].append((s, e, tag))
+    else:
+        check(fn(*args), name)
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)

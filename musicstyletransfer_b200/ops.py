@@ -20,7 +20,8 @@ def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False
     """C[M,N] = epilogue(opA(A)[M,K] @ opB(B)[K,N]); leading dimensions in elements (row-major storage)."""
     lib.call("msx_gemm_f32", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
-             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr())
+             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr(),
+             tag=2.0 * M * N * K)
 
 
 def wgrad_splitk(M_out, N_out, K_red, sms=148):

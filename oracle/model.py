@@ -134,6 +134,8 @@ def dropout(x, rate, masks, site):
     deterministic; rate 0 or masks None -> identity."""
     if rate <= 0.0 or masks is None:
         return x
+    if masks == "random":      # throughput runs: fresh Bernoulli mask per call, as gluon.nn.Dropout does
+        return x * (torch.rand_like(x) >= rate).float() / (1.0 - rate)
     return x * masks[site] / (1.0 - rate)
 
 
