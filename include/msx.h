@@ -55,6 +55,12 @@ int msx_gemm_f32(const float* A, int lda, int transA, const float* B, int ldb, i
                  const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, float* colsum,
                  void* stream);
 
+int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
+                int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
+                const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, void* stream);
+/* 1 when msx_gemm_tc accepts the operands (TMA: 16-byte aligned bases, leading dimensions multiple of 4). */
+int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
+
 /* K2c — attention in the reference's convention (softmax over the QUERY axis, additive -1e9 on padded keys,
  * O = P^T V).  Replaces MultiHeadDotAttention.hybrid_forward lines 91-103 and _mask_logits
  * (VarAutoEncoder/transformer.py:91-126).  qkv [B*T, 3*H*dh] rows = [K | Q | V]; mask [B*T] (1 = real key). */

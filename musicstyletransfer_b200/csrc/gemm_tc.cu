@@ -1,0 +1,383 @@
+// K2 (tensor-core path) — persistent, warp-specialised tcgen05 + TMA GEMM for sm_100a.
+//
+// Same contract as msx_gemm_f32 (gemm_simt.cu): replaces the gluon.nn.Dense forward / backward GEMMs of
+// /root/reference/music_style_transfer/VarAutoEncoder/{transformer.py:36-40,65-68,88-93,104, model.py:70-71,
+// 139-157,214-227}.  Operands stay fp32 in HBM and are consumed as TF32 by `tcgen05.mma.kind::tf32`
+// (fp32 accumulate in TMEM), so the tensor path drops into the fp32 step without conversion passes.
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-stage smem ring
+//   warp 1      TMEM allocator + single-thread MMA issuer: 4 x (128 x 128 x 8) tcgen05.mma per stage,
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout in the row-owner
+//               layout -> smem transpose -> coalesced aux-mask / accumulate / red.add / store
+// Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of
+// tile i+1; CTAs are persistent (one per SM) and walk output tiles N-fastest so the A row-block of a
+// wave is shared through L2.  Operand majors: K-major (reduction dim contiguous: X in X W^T, W in X W^T,
+// dY in dY W) and MN-major (output dim contiguous: W in dY W, dY^T and X in dY^T X) are both fed by TMA;
+// only the shared-memory descriptor and the box geometry differ.
+#include <cuda.h>
+
+#include "msx_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 B = one swizzle row
+constexpr int kStages = 4;
+constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand per stage
+constexpr int kStageBytes = 2 * kTileBytes;
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kStagePad = 33;
+constexpr int kTmemCols = 256;                      // 2 accumulators x 128 fp32 columns
+
+struct TcParams {
+  float* C;
+  int ldc, M, N, K;
+  const float* bias;
+  int relu;
+  float drop_p, inv_keep;
+  unsigned long long seed;
+  unsigned site;
+  const float* aux;
+  int ldaux;
+  float aux_scale;
+  int accumulate, splitk;
+  int m_tiles, n_tiles, kb_total, kb_per_split;
+};
+
+struct __align__(8) Barriers {
+  unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+  unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+// layout 2 = SWIZZLE_128B (16-byte units, 8-row atoms): K-major operands.
+// layout 1 = SWIZZLE_128B_BASE32B (32-byte units, 4-row atoms): the only layout tcgen05 accepts for
+//            MN-major 32-bit (TF32) operands; TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes,
+                                                        unsigned long long layout) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float v[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
+  unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* stage_out = reinterpret_cast<float*>(ring + kStages * kStageBytes);     // [kEpiWarps][32][kStagePad]
+  Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * 32 * kStagePad);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.m_tiles * p.n_tiles * p.splitk;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          unsigned char* sa = ring + stage * kStageBytes;
+          unsigned char* sb = sa + kTileBytes;
+          mbar_expect_tx(&bars->full[stage], kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &bars->full[stage], kb * BK, mt * BM);           // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int s = 0; s < BM / 32; ++s)                                       // 4 slabs {32 m, 32 k}
+              tma_load_2d(sa + s * (BK * 128), &tmA, &bars->full[stage], mt * BM + s * 32, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &bars->full[stage], kb * BK, nt * BN);
+          } else {
+#pragma unroll
+            for (int s = 0; s < BN / 32; ++s)
+              tma_load_2d(sb + s * (BK * 128), &tmB, &bars->full[stage], nt * BN + s * 32, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+      int stage = 0;
+      unsigned phase = 0;
+      int local = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
+        const int ks = it / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int buf = local & 1;
+        const unsigned use = (unsigned)(local >> 1);
+        mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned sa = smem_u32(ring + stage * kStageBytes), sb = sa + kTileBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // K-major: +32 B per K=8 step inside the 128 B swizzle row, SBO = 8 rows * 128 B.
+            // MN-major: +1024 B per 8 k-rows, LBO = slab stride (32 k-rows * 128 B), SBO = 4 k-rows * 128 B.
+            const unsigned long long ad = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
+            const unsigned long long bd = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);                 // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[buf]);                 // accumulator complete
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int ew = warp - 2;                 // staging slot
+    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    float* st = stage_out + ew * 32 * kStagePad;
+    int local = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
+      const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles;
+      const int buf = local & 1;
+      const unsigned use = (unsigned)(local >> 1);
+      mbar_wait(&bars->tmem_full[buf], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row0 = mt * BM + lg * 32;
+      const int my_row = row0 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = nt * BN + ch * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
+        if (col0 < p.N && row0 < p.M) {
+          // ---- row-owner phase: this lane holds 32 consecutive columns of row my_row
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.drop_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float s4[4];
+              dropout_scale4(p.seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
+              v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * kStagePad + j] = v[j];
+          __syncwarp();
+          // ---- coalesced phase: lane = column
+          const int c = col0 + lane;
+          if (c < p.N) {
+            const int rmax = min(32, p.M - row0);
+            for (int r = 0; r < rmax; ++r) {
+              float x = st[r * kStagePad + lane];
+              const size_t row = (size_t)(row0 + r);
+              if (p.aux) x *= __ldg(p.aux + row * p.ldaux + c) > 0.f ? p.aux_scale : 0.f;
+              float* dst = p.C + row * p.ldc + c;
+              if (p.splitk > 1) atomicAdd(dst, x);
+              else *dst = p.accumulate ? *dst + x : x;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// -------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major matrix [rows, cols] with leading dimension ld; box = {box_cols (contiguous), box_rows}
+int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
+             int box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { msx_set_error("msx_gemm_tc: cuTensorMapEncodeTiled is not available from the driver"); return MSX_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { msx_set_error("msx_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MSX_ERR_CUDA; }
+  return MSX_OK;
+}
+
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * 32 * kStagePad * 4 + sizeof(Barriers);
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const int items = p.m_tiles * p.n_tiles * p.splitk;
+  const int grid = items < msx_num_sms() ? items : msx_num_sms();
+  gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, p);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+}  // namespace
+
+// Returns 1 when msx_gemm_tc can take this problem (TMA needs 16-byte aligned bases and row pitches).
+extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K) {
+  if (!A || !B || M <= 0 || N <= 0 || K <= 0) return 0;
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3)) return 0;
+  return 1;
+}
+
+extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
+                           int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed,
+                           unsigned site, const float* aux, int ldaux, float aux_scale, int accumulate, int splitk,
+                           void* stream) {
+  MSX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "msx_gemm_tc: negative dimension");
+  if (M == 0 || N == 0) return MSX_OK;
+  MSX_REQUIRE(A && B && C, "msx_gemm_tc: null operand");
+  MSX_REQUIRE(K > 0, "msx_gemm_tc: K must be > 0");
+  MSX_REQUIRE(msx_gemm_tc_supported(A, lda, B, ldb, M, N, K), "msx_gemm_tc: operands must be 16-byte aligned with ld %% 4 == 0");
+  MSX_REQUIRE(!(transA == 1 && transB == 1), "msx_gemm_tc: A^T B^T is not used on this path");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc: dropout probability must be in [0,1)");
+  if (splitk < 1) splitk = 1;
+  MSX_REQUIRE(!(splitk > 1 && (bias || relu || drop_p > 0.f || aux || accumulate)),
+              "msx_gemm_tc: split-K only supports the plain atomic-add epilogue");
+  // operand majors: A is K-major when stored [M,K] (transA=0), MN-major when stored [K,M] (transA=1);
+  //                 B is K-major when stored [N,K] (transB=1), MN-major when stored [K,N] (transB=0).
+  const bool a_mn = transA == 1, b_mn = transB == 0;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, BN, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
+  if (rc) return rc;
+  TcParams p;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+  p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN); p.kb_total = msx_ceil_div(K, BK);
+  if (splitk > p.kb_total) splitk = p.kb_total;
+  p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
+  p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
+  if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, p, st);
+  if (!a_mn && b_mn) return launch<false, true>(ta, tb, p, st);
+  if (a_mn && b_mn) return launch<true, true>(ta, tb, p, st);
+  msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
+  return MSX_ERR_UNSUPPORTED;
+}

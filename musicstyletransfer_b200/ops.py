@@ -24,6 +24,18 @@ def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False
              tag=2.0 * M * N * K)
 
 
+def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
+            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1):
+    """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
+    lib.call("msx_gemm_tc", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
+             _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
+             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), lib.stream_ptr(), tag=2.0 * M * N * K)
+
+
+def gemm_tc_supported(A, lda, B, ldb, M, N, K):
+    return bool(lib.load().msx_gemm_tc_supported(P(A), _i(lda), P(B), _i(ldb), _i(M), _i(N), _i(K)))
+
+
 def wgrad_splitk(M_out, N_out, K_red, sms=148):
     tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
     want = max(1, (3 * sms) // max(tiles, 1))

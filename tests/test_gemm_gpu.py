@@ -1,0 +1,118 @@
+"""Dense-layer GEMM parity: exact-fp32 FFMA kernel and the tcgen05 TF32 kernel vs a float64 host product,
+for the three operand-major modes of the step (forward, dgrad, wgrad) and their epilogues."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, transA, transB):
+    a = A.double().cpu()
+    b = B.double().cpu()
+    a = a.t() if transA else a
+    b = b.t() if transB else b
+    return a @ b
+
+
+def _mk(rows, cols, ld, seed):
+    g = torch.Generator().manual_seed(seed)
+    buf = torch.randn(rows, ld, generator=g)
+    return buf.cuda(), buf[:, :cols]
+
+
+CASES = [
+    # (M, N, K) as the math sees them
+    (300, 200, 96), (128, 128, 32), (2080, 768, 256), (65, 293, 128), (2080, 256, 1024), (7, 5, 8), (513, 300, 40),
+]
+
+
+@pytest.mark.parametrize("impl", ["f32", "tc"])
+@pytest.mark.parametrize("mode", ["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("M,N,K", CASES)
+def test_gemm_modes(impl, mode, M, N, K):
+    from musicstyletransfer_b200 import ops
+    pad = lambda n: (n + 3) // 4 * 4 + 4
+    if mode == "fwd":      # C = A[M,K] * B[N,K]^T
+        transA, transB = 0, 1
+        Ad, Av = _mk(M, K, pad(K), 1)
+        Bd, Bv = _mk(N, K, pad(K), 2)
+    elif mode == "dgrad":  # C = A[M,K] * B[K,N]
+        transA, transB = 0, 0
+        Ad, Av = _mk(M, K, pad(K), 1)
+        Bd, Bv = _mk(K, N, pad(N), 2)
+    else:                  # C = A[K,M]^T * B[K,N]
+        transA, transB = 1, 0
+        Ad, Av = _mk(K, M, pad(M), 1)
+        Bd, Bv = _mk(K, N, pad(N), 2)
+    ldc = pad(N)
+    want = _ref(Av, Bv, transA, transB)
+    C = torch.full((M, ldc), 7.0, device="cuda")
+    fn = ops.gemm if impl == "f32" else ops.gemm_tc
+    fn(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C, ldc, M, N, K)
+    torch.cuda.synchronize()
+    got = C[:, :N].double().cpu()
+    scale = float(want.abs().max()) + 1e-9
+    err = float((got - want).abs().max()) / scale
+    assert err < (2e-6 if impl == "f32" else 2e-3), (impl, mode, M, N, K, err)
+    assert float((C[:, N:] - 7.0).abs().max()) == 0.0          # padding columns untouched
+    # split-K accumulation into a pre-zeroed C
+    C2 = torch.zeros((M, ldc), device="cuda")
+    fn(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C2, ldc, M, N, K, splitk=3)
+    torch.cuda.synchronize()
+    err = float((C2[:, :N].double().cpu() - want).abs().max()) / scale
+    assert err < (4e-6 if impl == "f32" else 2e-3), ("splitk", impl, mode, err)
+
+
+@pytest.mark.parametrize("impl", ["f32", "tc"])
+def test_gemm_epilogues(impl):
+    from musicstyletransfer_b200 import ops
+    fn = ops.gemm if impl == "f32" else ops.gemm_tc
+    tol = 2e-6 if impl == "f32" else 2e-3
+    M, N, K = 333, 293, 128
+    ldc = 296
+    Ad, Av = _mk(M, K, K, 3)
+    Bd, Bv = _mk(N, K, K, 4)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(5)).cuda()
+    want = _ref(Av, Bv, 0, 1) + bias.double().cpu()
+    # bias + relu
+    C = torch.zeros((M, ldc), device="cuda")
+    fn(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, bias=bias, relu=True)
+    got = C[:, :N].double().cpu()
+    scale = float(want.abs().max())
+    assert float((got - want.clamp(min=0)).abs().max()) / scale < tol
+    # accumulate
+    C0 = torch.randn(M, ldc, generator=torch.Generator().manual_seed(6)).cuda()
+    C = C0.clone()
+    fn(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, bias=bias, accumulate=True)
+    assert float((C[:, :N].double().cpu() - (want + C0[:, :N].double().cpu())).abs().max()) / scale < tol
+    # aux mask (relu' * scale)
+    aux = torch.randn(M, ldc, generator=torch.Generator().manual_seed(7)).cuda()
+    C = torch.zeros((M, ldc), device="cuda")
+    fn(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, aux=aux, ldaux=ldc, aux_scale=1.25)
+    w2 = _ref(Av, Bv, 0, 1) * (aux[:, :N].cpu() > 0).double() * 1.25
+    assert float((C[:, :N].double().cpu() - w2).abs().max()) / scale < tol
+    # dropout: both kernels draw the same Philox mask for (seed, site, element)
+    C = torch.zeros((M, ldc), device="cuda")
+    fn(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, bias=bias, drop_p=0.25, seed=1234, site=3)
+    got = C[:, :N].double().cpu()
+    kept = got != 0
+    frac = float(kept.double().mean())
+    assert 0.70 < frac < 0.80
+    assert float((got[kept] - (want / 0.75)[kept]).abs().max()) / scale < tol * 2
+    Cs = torch.zeros((M, ldc), device="cuda")
+    ops.gemm(Ad, K, 0, Bd, K, 1, Cs, ldc, M, N, K, bias=bias, drop_p=0.25, seed=1234, site=3)
+    assert bool(((Cs[:, :N] != 0) == (C[:, :N] != 0)).all())
+
+
+def test_wgrad_colsum():
+    from musicstyletransfer_b200 import ops
+    Mred, Nout, Kout = 1000, 293, 128
+    dY, dYv = _mk(Mred, Nout, 296, 8)
+    X, Xv = _mk(Mred, Kout, Kout, 9)
+    gw = torch.zeros(Nout, Kout, device="cuda")
+    gb = torch.zeros(Nout, device="cuda")
+    ops.gemm(dY, 296, 1, X, Kout, 0, gw, Kout, Nout, Kout, Mred, splitk=4, colsum=gb)
+    torch.cuda.synchronize()
+    assert float((gw.double().cpu() - dYv.double().t() @ Xv.double()).abs().max()) < 1e-3
+    assert float((gb.double().cpu() - dYv.double().sum(0)).abs().max()) < 1e-3
