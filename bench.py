@@ -34,6 +34,8 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
     ap.add_argument("--dropout", type=float, default=0.2)
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="rows per oracle step (bounded CPU sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
@@ -41,9 +43,10 @@ def parse_args():
 
 
 def workload_name(args):
-    return ("VarAutoEncoder train step (fwd+bwd+Adam) fp32, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
+    return ("VarAutoEncoder train step (fwd+bwd+Adam) fp32 storage, GEMMs %s, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
             "dec %s 1x128, dropout %.1f, B=%d per GPU, L=%d (T=%d), synthetic 4/4 token rows"
-            % (args.dec_type, args.dropout, args.batch, args.seq_len, args.seq_len + 1))
+            % ({"fp32": "fp32 FFMA", "tf32": "tcgen05 TF32 (fp32 accumulate)"}[args.precision], args.dec_type, args.dropout,
+               args.batch, args.seq_len, args.seq_len + 1))
 
 
 def measured_peaks():
@@ -201,7 +204,7 @@ def run_ours(args):
     peaks = measured_peaks()
 
     cfg = VAEConfig(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
-    eng = VAEEngine(cfg, dev, seed=0)
+    eng = VAEEngine(cfg, dev, seed=0, precision=args.precision)
     B, L = args.batch, args.seq_len
     T = L + 1
     n_batches = 4
@@ -288,7 +291,9 @@ def run_ours(args):
         gemm_flops = sum(f for _, _, f in prof["events"])
         step_ms = s.elapsed_time(e)
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)",
+        kname = ("gemm_tc_kernel (msx_gemm_tc, tcgen05 kind::tf32 + TMA)" if args.precision == "tf32"
+                 else "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)")
+        roofline = {"bound": "tensor", "kernel": kname,
                     "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
                     "traffic": None, "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)",
                     "share_of_step": gemm_ms / step_ms, "launches_per_step": len(prof["events"]) / psteps,
@@ -312,7 +317,7 @@ def run_ours(args):
                "ms_per_step": per_step * 1e3}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %

@@ -58,8 +58,13 @@ int msx_gemm_f32(const float* A, int lda, int transA, const float* B, int ldb, i
 int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
                 int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
                 const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, void* stream);
-/* 1 when msx_gemm_tc accepts the operands (TMA: 16-byte aligned bases, leading dimensions multiple of 4). */
-int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
+/* msx_gemm_tc writes C through TMA in 16-byte chunks: padding columns N .. roundup4(N)-1 of C may be overwritten.
+ * 1 when msx_gemm_tc accepts the operands (TMA: 16-byte aligned bases, leading dimensions multiple of 4). */
+int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
+                          int K);
+
+/* out[n] += sum_m X[m,n]: bias gradient of a Dense layer when the wgrad runs on the tensor path. */
+int msx_colsum(const float* X, int ld, long long M, int N, float* out, void* stream);
 
 /* K2c — attention in the reference's convention (softmax over the QUERY axis, additive -1e9 on padded keys,
  * O = P^T V).  Replaces MultiHeadDotAttention.hybrid_forward lines 91-103 and _mask_logits

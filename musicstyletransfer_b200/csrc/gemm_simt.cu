@@ -242,3 +242,36 @@ extern "C" int msx_gemm_f32(const float* A, int lda, int transA, const float* B,
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Bias gradient for the tensor-core path: out[n] += sum_m X[m, n]   (db of a Dense layer, trainer.py:176)
+namespace {
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, long long M, int N,
+                                                     float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < N)
+    for (long long r = (long long)blockIdx.y * 8 + ty; r < M; r += (long long)gridDim.y * 8) acc += X[r * ld + c];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+}  // namespace
+
+extern "C" int msx_colsum(const float* X, int ld, long long M, int N, float* out, void* stream) {
+  MSX_REQUIRE(X && out, "msx_colsum: null pointer");
+  if (M == 0 || N == 0) return MSX_OK;
+  const int gx = msx_ceil_div(N, 32);
+  int gy = (int)min((long long)msx_ceil_div(msx_num_sms() * 8, gx), (M + 63) / 64);
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, out);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

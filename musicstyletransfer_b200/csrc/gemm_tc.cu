@@ -8,8 +8,9 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-stage smem ring
 //   warp 1      TMEM allocator + single-thread MMA issuer: 4 x (128 x 128 x 8) tcgen05.mma per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout in the row-owner
-//               layout -> smem transpose -> coalesced aux-mask / accumulate / red.add / store
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout / aux-mask in the
+//               row-owner layout -> 128B-swizzled smem box -> TMA store, or TMA reduce-add (.add.f32) for
+//               accumulate and split-K, so C is never read by the SM and OOB rows/columns are clipped by TMA
 // Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of
 // tile i+1; CTAs are persistent (one per SM) and walk output tiles N-fastest so the A row-block of a
 // wave is shared through L2.  Operand majors: K-major (reduction dim contiguous: X in X W^T, W in X W^T,
@@ -27,7 +28,7 @@ constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand per sta
 constexpr int kStageBytes = 2 * kTileBytes;
 constexpr int kThreads = 192;
 constexpr int kEpiWarps = 4;
-constexpr int kStagePad = 33;
+constexpr int kOutBoxBytes = 32 * 128;               // epilogue staging box: 32 rows x 32 fp32
 constexpr int kTmemCols = 256;                      // 2 accumulators x 128 fp32 columns
 
 struct TcParams {
@@ -126,12 +127,13 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float v[32]) {
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* stage_out = reinterpret_cast<float*>(ring + kStages * kStageBytes);     // [kEpiWarps][32][kStagePad]
-  Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * 32 * kStagePad);
+  unsigned char* stage_out = ring + kStages * kStageBytes;                        // [kEpiWarps][2][32 rows][128 B]
+  Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.m_tiles * p.n_tiles * p.splitk;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
@@ -224,8 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ================================ epilogue (warps 2..5) ================================
     const int ew = warp - 2;                 // staging slot
     const int lg = warp & 3;                 // TMEM lane group this warp may access
-    float* st = stage_out + ew * 32 * kStagePad;
-    int local = 0;
+    unsigned char* st = stage_out + ew * 2 * kOutBoxBytes;
+    const bool reduce = p.accumulate || p.splitk > 1;
+    int local = 0, sbuf = 0, pending = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
       const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles;
       const int buf = local & 1;
@@ -239,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int col0 = nt * BN + ch * 32;
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
-        if (col0 < p.N && row0 < p.M) {
-          // ---- row-owner phase: this lane holds 32 consecutive columns of row my_row
+        if (col0 < p.N && row0 < p.M) {          // warp-uniform
+          // ---- row-owner layout: this lane holds 32 consecutive columns of row my_row
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
@@ -257,29 +261,56 @@ __global__ void __launch_bounds__(kThreads, 1)
               v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
             }
           }
+          if (p.aux && my_row < p.M) {
+            const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
+            if (col0 + 32 <= p.N && (p.ldaux & 3) == 0) {
+              float4 a4[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane * kStagePad + j] = v[j];
-          __syncwarp();
-          // ---- coalesced phase: lane = column
-          const int c = col0 + lane;
-          if (c < p.N) {
-            const int rmax = min(32, p.M - row0);
-            for (int r = 0; r < rmax; ++r) {
-              float x = st[r * kStagePad + lane];
-              const size_t row = (size_t)(row0 + r);
-              if (p.aux) x *= __ldg(p.aux + row * p.ldaux + c) > 0.f ? p.aux_scale : 0.f;
-              float* dst = p.C + row * p.ldc + c;
-              if (p.splitk > 1) atomicAdd(dst, x);
-              else *dst = p.accumulate ? *dst + x : x;
+              for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(ax) + j);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j + 0] *= a4[j].x > 0.f ? p.aux_scale : 0.f;
+                v[4 * j + 1] *= a4[j].y > 0.f ? p.aux_scale : 0.f;
+                v[4 * j + 2] *= a4[j].z > 0.f ? p.aux_scale : 0.f;
+                v[4 * j + 3] *= a4[j].w > 0.f ? p.aux_scale : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < p.N && __ldg(ax + j) > 0.f) ? p.aux_scale : 0.f;
             }
           }
+          // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
+          unsigned char* box = st + sbuf * kOutBoxBytes;
+          if (pending >= 2) {                     // the box we are about to overwrite must have been read
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          if (lane == 0) {
+            if (reduce)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                           "r"(smem_u32(box)), "r"(col0), "r"(row0)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                           "r"(smem_u32(box)), "r"(col0), "r"(row0)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          sbuf ^= 1;
+          if (pending < 2) ++pending;
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -321,14 +352,14 @@ int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols,
   return MSX_OK;
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * 32 * kStagePad * 4 + sizeof(Barriers);
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers);
 
 template <bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
   MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int grid = items < msx_num_sms() ? items : msx_num_sms();
-  gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, p);
+  gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tc, p);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -336,9 +367,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cuda
 }  // namespace
 
 // Returns 1 when msx_gemm_tc can take this problem (TMA needs 16-byte aligned bases and row pitches).
-extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K) {
-  if (!A || !B || M <= 0 || N <= 0 || K <= 0) return 0;
-  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3)) return 0;
+extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M,
+                                     int N, int K) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return 0;
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || (lda & 3) || (ldb & 3) || (ldc & 3)) return 0;
   return 1;
 }
 
@@ -350,7 +382,8 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   if (M == 0 || N == 0) return MSX_OK;
   MSX_REQUIRE(A && B && C, "msx_gemm_tc: null operand");
   MSX_REQUIRE(K > 0, "msx_gemm_tc: K must be > 0");
-  MSX_REQUIRE(msx_gemm_tc_supported(A, lda, B, ldb, M, N, K), "msx_gemm_tc: operands must be 16-byte aligned with ld %% 4 == 0");
+  MSX_REQUIRE(msx_gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K),
+              "msx_gemm_tc: A, B and C must be 16-byte aligned with leading dimensions %% 4 == 0");
   MSX_REQUIRE(!(transA == 1 && transB == 1), "msx_gemm_tc: A^T B^T is not used on this path");
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc: dropout probability must be in [0,1)");
   if (splitk < 1) splitk = 1;
@@ -359,8 +392,9 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   // operand majors: A is K-major when stored [M,K] (transA=0), MN-major when stored [K,M] (transA=1);
   //                 B is K-major when stored [N,K] (transB=1), MN-major when stored [K,N] (transB=0).
   const bool a_mn = transA == 1, b_mn = transB == 0;
-  CUtensorMap ta, tb;
-  int rc;
+  CUtensorMap ta, tb, tc;
+  int rc = make_map(&tc, C, M, N, ldc, 32, 32, false);     // epilogue box: 32 rows x 32 columns, SWIZZLE_128B
+  if (rc) return rc;
   if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
   if (rc) return rc;
   if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, BN, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
@@ -375,9 +409,9 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
   if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
   cudaStream_t st = (cudaStream_t)stream;
-  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, p, st);
-  if (!a_mn && b_mn) return launch<false, true>(ta, tb, p, st);
-  if (a_mn && b_mn) return launch<true, true>(ta, tb, p, st);
+  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, tc, p, st);
+  if (!a_mn && b_mn) return launch<false, true>(ta, tb, tc, p, st);
+  if (a_mn && b_mn) return launch<true, true>(ta, tb, tc, p, st);
   msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
   return MSX_ERR_UNSUPPORTED;
 }

@@ -158,7 +158,11 @@ class _Buffers:
 
 
 class VAEEngine:
-    def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024):
+    def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024, precision="fp32"):
+        """precision: "fp32" = exact FFMA GEMMs (msx_gemm_f32); "tf32" = tcgen05 tensor-core GEMMs with TF32
+        operands and fp32 accumulation (msx_gemm_tc).  Everything outside the GEMMs is fp32 in both modes."""
+        assert precision in ("fp32", "tf32")
+        self.precision = precision
         self.cfg = cfg
         self.device = torch.device(device)
         self.arena = ParamArena(cfg, self.device)
@@ -193,17 +197,26 @@ class VAEEngine:
                    w=None, b=None):
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
-        ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
-                 site=site, accumulate=accumulate)
+        fn = ops.gemm_tc if self._use_tc(x, ldx, w, K, out, ldo, M, N, K) else ops.gemm
+        fn(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+           site=site, accumulate=accumulate)
+
+    def _use_tc(self, A, lda, B, ldb, C, ldc, M, N, K):
+        return self.precision == "tf32" and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
                    accumulate_dx=False):
         """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy), dx [M,K] (=|+=) dy w (optionally masked by aux)."""
-        sk = ops.wgrad_splitk(N, K, M, self.sms)
-        ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=max(sk, 2), colsum=gb)
+        sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
+        if self._use_tc(dy, lddy, x, ldx, gw, K, N, K, M):
+            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk)
+            ops.colsum(dy, lddy, M, N, gb)
+        else:
+            ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, colsum=gb)
         if dx is not None:
-            ops.gemm(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
-                     accumulate=accumulate_dx)
+            fn = ops.gemm_tc if self._use_tc(dy, lddy, w, K, dx, lddx, M, K, N) else ops.gemm
+            fn(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
+               accumulate=accumulate_dx)
 
     # ------------------------------------------------------------------ transformer layer
     def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder):

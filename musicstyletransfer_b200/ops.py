@@ -32,8 +32,12 @@ def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=Fa
              _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), lib.stream_ptr(), tag=2.0 * M * N * K)
 
 
-def gemm_tc_supported(A, lda, B, ldb, M, N, K):
-    return bool(lib.load().msx_gemm_tc_supported(P(A), _i(lda), P(B), _i(ldb), _i(M), _i(N), _i(K)))
+def gemm_tc_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
+    return bool(lib.load().msx_gemm_tc_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
+
+
+def colsum(X, ld, M, N, out):
+    lib.call("msx_colsum", P(X), _i(ld), _ll(M), _i(N), P(out), lib.stream_ptr())
 
 
 def wgrad_splitk(M_out, N_out, K_red, sms=148):

@@ -207,3 +207,30 @@ def test_odd_batch_sizes_lstm():
     p = om.init_params(cfg, seed=3)
     tokens, seq_lens, classes, labels, eps = _batch(37, 19, 293, 2, 16, seed=7)
     _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
+
+
+def test_tf32_tensor_core_step_deviation():
+    """tcgen05 TF32 GEMMs (precision="tf32"): forward within 1e-3 relative of the fp32 oracle on loss / KL /
+    latent means for the train-vae.sh configuration; gradients within 1 % of each tensor's scale."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    cfg_o = om.Cfg(dec_type="lstm")
+    p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=0))
+    tokens, seq_lens, classes, labels, eps = _batch(64, 65, 293, 2, 256, seed=1, min_len=33)
+    eng = VAEEngine(VAEConfig(dec_type="lstm"), "cuda:0", precision="tf32")
+    eng.arena.load_state(p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
+    opt = om.Adam({k: v.clone() for k, v in p.items()}, clip_gradient=1.0)
+    pp = {k: v.clone() for k, v in p.items()}
+    loss, ce, kl, probs, means, stds, grads = om.train_step(cfg_o, pp, opt, tokens, seq_lens, classes, labels, eps)
+    rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
+    dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
+    print("tf32 forward deviation (max abs / max):", dev)
+    assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 2e-3, dev
+    eng.backward()
+    torch.cuda.synchronize()
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
+                   if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
+    print("tf32 gradient deviation, worst tensors:", devs[:4])
+    assert devs[0][0] < 1e-1
+    assert sum(d for d, _ in devs) / len(devs) < 2e-2
