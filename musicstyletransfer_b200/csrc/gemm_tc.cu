@@ -336,15 +336,17 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major matrix [rows, cols] with leading dimension ld; box = {box_cols (contiguous), box_rows}
+// operand maps use the TFLOAT32 element type so that TMA rounds fp32 -> tf32 to nearest while loading (the MMA
+// itself would truncate the low 13 mantissa bits); the C map stays plain FLOAT32.
 int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
-             int box_rows, bool mn_major) {
+             int box_rows, bool mn_major, bool operand = true) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { msx_set_error("msx_gemm_tc: cuTensorMapEncodeTiled is not available from the driver"); return MSX_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, operand ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -393,7 +395,7 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   //                 B is K-major when stored [N,K] (transB=1), MN-major when stored [K,N] (transB=0).
   const bool a_mn = transA == 1, b_mn = transB == 0;
   CUtensorMap ta, tb, tc;
-  int rc = make_map(&tc, C, M, N, ldc, 32, 32, false);     // epilogue box: 32 rows x 32 columns, SWIZZLE_128B
+  int rc = make_map(&tc, C, M, N, ldc, 32, 32, false, false);     // epilogue box: 32 rows x 32 columns, SWIZZLE_128B
   if (rc) return rc;
   if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
   if (rc) return rc;

@@ -225,12 +225,12 @@ def test_tf32_tensor_core_step_deviation():
     rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
     dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
     print("tf32 forward deviation (max abs / max):", dev)
-    assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 2e-3, dev
+    assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 1e-3, dev
     eng.backward()
     torch.cuda.synchronize()
     gmax = max(float(g.abs().max()) for g in grads.values())
     devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
                    if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
     print("tf32 gradient deviation, worst tensors:", devs[:4])
-    assert devs[0][0] < 1e-1
+    assert devs[0][0] < 5e-2
     assert sum(d for d, _ in devs) / len(devs) < 2e-2
