@@ -274,19 +274,21 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = loss_host.numel() * loss_host.element_size()
 
-    # ---- dominant kernel (GEMM) roofline: CUDA events around every GEMM launch of a few extra steps
+    # ---- dominant kernel (GEMM) roofline: CUDA events around every GEMM launch of a few extra steps.
+    # Every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events.
     roofline = None
+    psteps = 3
+    prof = {"match": "msx_gemm", "events": []}
     if rank == 0:
-        prof = {"match": "msx_gemm", "events": []}
         lib._profile = prof
-        psteps = 3
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(psteps):
-            step_resident(i)
-        e.record()
-        torch.cuda.synchronize()
-        lib._profile = None
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(psteps):
+        step_resident(i)
+    e.record()
+    torch.cuda.synchronize()
+    lib._profile = None
+    if rank == 0:
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof["events"])
         gemm_flops = sum(f for _, _, f in prof["events"])
         step_ms = s.elapsed_time(e)

@@ -122,6 +122,13 @@ int msx_ce_from_probs(const float* probs, const int32_t* labels, float* ce, int 
 int msx_bce(const float* pred, const uint8_t* label, float* out, const float* gout, float* dpred, int B,
             int n_per_sample, int from_sigmoid, float label_smoothing, int downweight, void* stream);
 
+/* A12 — next-token sampling.  Replaces mx.nd.random.multinomial(probs) and the score update of Sampling.sample
+ * (sampler.py:181-184) on softmax(logits): next[b] = first v with cdf(v) > u_b (u from `uniforms` or Philox(seed,
+ * step, b)); score[b] += -log p(next) when given; out_seq[b*out_ld + out_col] = next[b] when given. */
+int msx_sample_multinomial(const float* logits, int ld, int V, const float* uniforms, unsigned long long seed,
+                           unsigned long long step, int32_t* next, float* score, int32_t* out_seq, int out_ld,
+                           int out_col, int B, void* stream);
+
 /* K4 — fused multi-tensor Adam over flat arenas.  Replaces gluon.Trainer('adam', ...).step(batch_size)
  * (trainer.py:94-101,177; MXNet 1.3 Adam: eps outside the bias correction, element-wise clip, rescale = 1/batch).
  * state[0] = step count t (device-resident), state[1] = lr_t; zero_grad clears g in the same pass. */

@@ -1,0 +1,214 @@
+"""Dataset classes with the reference's interface (VarAutoEncoder/data.py).
+
+``Loader`` walks ``path/<class_dir>/*.mid`` and tokenises every first surviving track on the GPU (one K1
+launch for the whole directory tree); ``MelodyDataset`` chunks the ids into rows with the rules of
+``_get_token_arrays`` (data.py:133-173, quirks included) and iterates shuffled batches the way
+``mx.io.NDArrayIter(shuffle=True)`` with ``last_batch_handle='pad'`` does.  Batches carry float32 arrays as
+the reference's do (``data = [tokens, seq_lens, classes]``, ``label = [labels]``)."""
+import glob
+import os
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from ..MIDIUtil.defaults import *  # noqa: F401,F403
+from ..MIDIUtil.defaults import EOS_ID, NUM_EVENTS, PAD_ID, SOS_ID
+from ..MIDIUtil.Melody import Melody
+from ..MIDIUtil.midi_io import EventBasedMIDIReader
+
+
+class DataBatch:
+    def __init__(self, data, label, pad=0):
+        self.data = data
+        self.label = label
+        self.pad = pad
+
+
+class Loader:
+    def __init__(self, path: str, max_sequence_length: int, slices_per_quarter_note: int):
+        self.path = path
+        self.max_sequence_length = max_sequence_length
+        self.slices_per_quarter_note = slices_per_quarter_note
+        self.midi_reader = EventBasedMIDIReader()
+        self.melodies = self.read_melodies()
+
+    def read_melodies(self):
+        print("Reading from {}".format(self.path))
+        melodies = {}
+        directories = next(os.walk(self.path))[1]
+        files = {d: glob.glob(self.path + '/' + d + "/*.mid") for d in sorted(directories)}
+        parsed = self.midi_reader.read_files([f for d in files for f in files[d]])
+        for directory in sorted(directories):
+            melodies[directory] = [parsed[f][0] for f in files[directory]]       # data.py:35 keeps track [0]
+            print("Read {} files from {}".format(len(files[directory]), directory))
+        return melodies
+
+
+class Dataset:
+    def __init__(self, batch_size: int):
+        self.batch_size = batch_size
+
+    def num_classes(self):
+        raise NotImplementedError
+
+    def num_tokens(self):
+        raise NotImplementedError
+
+    def __iter__(self):
+        raise NotImplementedError
+
+
+class _ArrayIter:
+    """mx.io.NDArrayIter semantics used by the reference: optional shuffle once per reset, last batch padded by
+    wrapping around to the first samples."""
+
+    def __init__(self, data, label, batch_size, shuffle, seed=0):
+        self.data, self.label, self.batch_size, self.shuffle = data, label, batch_size, shuffle
+        self.n = data[0].shape[0]
+        self.rng = np.random.RandomState(seed)
+        self.order = np.arange(self.n)
+
+    def reset(self):
+        if self.shuffle:
+            self.rng.shuffle(self.order)
+
+    def __iter__(self):
+        for start in range(0, self.n, self.batch_size):
+            idx = self.order[start:start + self.batch_size]
+            pad = self.batch_size - len(idx)
+            if pad > 0:
+                idx = np.concatenate([idx, self.order[:pad]])
+            yield DataBatch([torch.from_numpy(a[idx]) for a in self.data], [torch.from_numpy(a[idx]) for a in self.label], pad)
+
+
+class ToyData(Dataset):
+    """data.py:57-81."""
+
+    def __init__(self, batch_size: int = 3):
+        super().__init__(batch_size)
+        tokens = np.array([[1, 5, 6, 7, 0], [1, 6, 7, 8, 0], [1, 7, 8, 9, 0]], dtype=np.float32)
+        seq_lens = np.array([4, 4, 4], dtype=np.float32)
+        classes = np.array([0, 1, 2], dtype=np.float32)
+        labels = np.array([[5, 6, 7, 2, 0], [6, 7, 8, 2, 0], [7, 8, 9, 2, 0]], dtype=np.float32)
+        self.iter = _ArrayIter([tokens, seq_lens, classes], [labels], self.batch_size, shuffle=False)
+
+    def num_classes(self):
+        return 3
+
+    def num_tokens(self):
+        return 10
+
+    def __iter__(self):
+        self.iter.reset()
+        for batch in self.iter:
+            yield batch
+
+
+class MelodyDataset(Dataset):
+    def __init__(self, batch_size: int, maximum_sequence_length: int, melodies: Dict[str, List[Melody]], seed: int = 0):
+        super().__init__(batch_size)
+        self.max_seq_len = maximum_sequence_length
+        self.mask_offset = 1
+        self._seed = seed
+        self._initialize(melodies)
+        self._log_dataset()
+        del self.melodies
+
+    def _initialize(self, melodies):
+        self.melodies = dict(sorted(melodies.items(), key=lambda x: x[0]))
+        self.n_classes = len(self.melodies)
+        self.n_melodies = sum(len(m) for m in self.melodies.values())
+        self.seen_max_sequence_length = max(max(len(x.notes) for x in ms) for ms in self.melodies.values())
+        self._get_token_arrays()
+        self.iter = _ArrayIter([self.tokens, self.classes], [self.labels], self.batch_size, shuffle=True, seed=self._seed)
+
+    def _log_dataset(self):
+        print("")
+        print("Dataset information: ")
+        print("Number of classes: {}".format(self.num_classes()))
+        print("Number of tokens: {}".format(self.num_tokens()))
+        print("Tokens dataset shape {}".format(self.tokens.shape))
+        print("Classes dataset shape {}".format(self.classes.shape))
+        for c, m in self.melodies.items():
+            print("Class {} has {} melodies of maximum length {}".format(c, len(m), self.seen_max_sequence_length))
+        print("")
+
+    def num_classes(self):
+        return self.n_classes
+
+    def num_tokens(self):
+        return NUM_EVENTS
+
+    def _get_token_arrays(self):
+        """data.py:133-173: rows of L ids; the remainder row of every melody is flushed even when empty (:149-150);
+        after each class the last row is appended once more when it is non-empty (:152-155); labels are the data
+        shifted by one with EOS written by ``labels[:, seq_lens] = EOS`` (:166-168, NumPy advanced indexing:
+        every row gets EOS in every column that is some row's length)."""
+        L = self.max_seq_len
+        rows, classes = [], []
+        last = None
+        for class_idx, melodies_for_class in enumerate(self.melodies.values()):
+            for melody in melodies_for_class:
+                ids = np.fromiter((e.id for e in melody), dtype=np.int64, count=len(melody))
+                n_full = len(ids) // L
+                for r in range(n_full):
+                    rows.append(ids[r * L:(r + 1) * L])
+                    classes.append(class_idx)
+                last = np.full((L,), PAD_ID, dtype=np.int64)
+                rem = ids[n_full * L:]
+                last[:len(rem)] = rem
+                rows.append(last)
+                classes.append(class_idx)
+            if last[0] != PAD_ID:
+                rows.append(last)
+                classes.append(class_idx)
+        num_samples = len(rows)
+        assert num_samples > 0, "Empty sequences were found"
+        data = np.stack(rows).astype(np.float32)
+        self.tokens = np.concatenate([np.full((num_samples, 1), SOS_ID, np.float32), data], axis=1)
+        seq_lens = self._count_sequence_length(data).astype(np.int64)
+        self.labels = np.concatenate([data, np.full((num_samples, 1), PAD_ID, np.float32)], axis=1)
+        self.labels[:, seq_lens] = EOS_ID
+        self.classes = np.asarray(classes, dtype=np.float32)
+        print("Tokens.shape {}".format(self.tokens.shape))
+        print("Labels.shape {}".format(self.labels.shape))
+        print("classes.shape {}".format(self.classes.shape))
+
+    def _count_sequence_length(self, tokens):
+        t = tokens.numpy() if torch.is_tensor(tokens) else tokens
+        return (t != PAD_ID).sum(axis=1).astype(np.float32)
+
+    def __iter__(self):
+        self.iter.reset()
+        for batch in self.iter:
+            self._preprocess_batch(batch)
+            yield batch
+
+    def _preprocess_batch(self, batch):
+        """data.py:187-198: seq_lens = #non-PAD incl. SOS inserted at data[1]; trim to the batch maximum.
+        The lengths are counted on host copies, so no device synchronisation is involved."""
+        tokens = batch.data[0]
+        seq_lens = torch.from_numpy(self._count_sequence_length(tokens))
+        batch.data.insert(1, seq_lens)
+        max_seq_len = int(seq_lens.max())
+        batch.data[0] = batch.data[0][:, :max_seq_len]
+        batch.label[0] = batch.label[0][:, :max_seq_len]
+
+
+def load_dataset(loader_train: Loader, batch_size: int, split_percentage: float = None, loader_val: Loader = None):
+    """data.py:201-223."""
+    if loader_val is not None:
+        train = MelodyDataset(batch_size, loader_train.max_sequence_length, loader_train.melodies)
+        val = MelodyDataset(batch_size, loader_val.max_sequence_length, loader_val.melodies)
+        return train, val
+    if split_percentage <= 0.:
+        return MelodyDataset(batch_size, loader_train.max_sequence_length, loader_train.melodies), None
+    assert 0.0 < split_percentage < 1.0
+    train_split, valid_split = {}, {}
+    for c, m in loader_train.melodies.items():
+        n_validation_melodies = int(split_percentage * len(m))
+        valid_split[c] = m[:n_validation_melodies]
+        train_split[c] = m[n_validation_melodies:]
+    return (MelodyDataset(batch_size, loader_train.max_sequence_length, train_split),
+            MelodyDataset(batch_size, loader_train.max_sequence_length, valid_split))

@@ -221,7 +221,7 @@ extern "C" int msx_rasterize(const int32_t* dtick, const uint8_t* pitch, const u
   MSX_REQUIRE(dtick && pitch && vel && seq_offsets && tokens && roll && n_tokens, "msx_rasterize: null pointer");
   MSX_REQUIRE(resolution > 0 && slices_per_quarter > 0, "msx_rasterize: resolution and slices_per_quarter must be > 0");
   MSX_REQUIRE(n_slices > 0 && n_slices <= 1024, "msx_rasterize: n_slices must be in [1,1024]");
-  MSX_REQUIRE(max_seq_len > 0 && max_seq_len <= 4096, "msx_rasterize: max_seq_len must be in [1,4096]");
+  MSX_REQUIRE(max_seq_len > 0 && max_seq_len <= 49152, "msx_rasterize: max_seq_len must be in [1,49152]");
   MSX_REQUIRE(((uintptr_t)roll & 15) == 0, "msx_rasterize: roll must be 16-byte aligned");
   const int tile_bytes = n_slices * kPitches;
   int warp_bytes = tile_bytes + ((max_seq_len + 1 + 3) & ~3) * 4 + kPitches * 4 + kPitches;

@@ -299,6 +299,156 @@ class VAEEngine:
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
         self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
 
+    # ------------------------------------------------------------------ encoder
+    def _encode(self, bf, tokens, classes, B, T, p_drop):
+        """Encoder.hybrid_forward (model.py:73-104) -> (layer inputs/outputs, key mask, lat = [means | stds])."""
+        cfg, dev = self.cfg, self.device
+        D, Z, V = cfg.enc_size, cfg.latent, cfg.vocab
+        M = B * T
+        x = bf.get("enc.x0", (M, D), dev)
+        mask = bf.get("enc.mask", (M,), dev)
+        ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
+                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V)
+        xs = [x]
+        for l in range(cfg.enc_layers):
+            x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
+                                   p_drop, l * SITE_STRIDE, False)
+            xs.append(x)
+        lat = bf.get("lat", (B, 2 * Z), dev)
+        self._dense_fwd(x, T * D, B, "encoder.latent_proj.weight", "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
+        return xs, mask, lat
+
+    def decoder_initial_state(self, classes, z):
+        """latent2hid(z) + class2hid[classes] (model.py:160 / :231): [B, 2H] for the LSTM decoder, [B, D_d] else."""
+        cfg, dev = self.cfg, self.device
+        B = z.shape[0]
+        n = 2 * cfg.dec_size if cfg.dec_type == "lstm" else cfg.dec_size
+        out = torch.empty((B, n), dtype=torch.float32, device=dev)
+        ops.embed_fwd(classes, None, None, self._W("decoder.class2hid.weight"), None, None, None, out, None, B, 1, n, 0,
+                      1.0, cfg.num_classes)
+        self._dense_fwd(z, z.stride(0), B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", out, n, n, cfg.latent,
+                        accumulate=True)
+        return out
+
+    def encode(self, tokens, classes):
+        """Inference-mode encoder: (means [B,Z], stds [B,Z]) as views of one [B,2Z] buffer."""
+        B, T = tokens.shape
+        _, _, lat = self._encode(self._buf(B, T), tokens, classes, B, T, 0.0)
+        Z = self.cfg.latent
+        return lat[:, :Z], lat[:, Z:]
+
+    # ------------------------------------------------------------------ style transfer / sampling (A12)
+    def style_transfer(self, tokens, seq_lens, classes_target, uniforms=None, seed=0):
+        """SamplerBase.compute_initial_decoder_state + Sampling.sample (sampler.py:145-151,161-189): the class
+        vector is overwritten BEFORE encoding, z = means, then up to 2T-1 autoregressive multinomial steps.
+        The all-rows-emitted-SOS/PAD stop test (:186) is evaluated on the host afterwards, which truncates the
+        result exactly where the reference's loop would have stopped.  uniforms: optional fp32 [2T, B]."""
+        cfg, dev = self.cfg, self.device
+        B, T = tokens.shape
+        Z, V, Hd = cfg.latent, cfg.vocab, cfg.dec_size
+        I_max = 2 * T
+        bf = self._buf(B, T)
+        _, _, lat = self._encode(bf, tokens, classes_target, B, T, 0.0)
+        seqs = bf.get("st.seqs", (B, I_max), dev, torch.int32)
+        seqs.zero_()
+        seqs[:, 0] = 1
+        nxt = bf.get("st.next", (B,), dev, torch.int32)
+        nxt.fill_(1)
+        score = bf.get("st.score", (B,), dev)
+        score.zero_()
+        logits = bf.get("st.logits", (B, self.ldv), dev)
+        W = self._W
+        u_at = (lambda i: uniforms[i]) if uniforms is not None else (lambda i: None)
+        if cfg.dec_type == "lstm":
+            tv = bf.get("st.tvec", (B, 2 * Hd), dev)
+            ops.embed_fwd(classes_target, None, None, W("decoder.class2hid.weight"), None, None, None, tv, None, B, 1,
+                          2 * Hd, 0, 1.0, cfg.num_classes)
+            self._dense_fwd(lat, 2 * Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
+                            accumulate=True)
+            hb = [bf.get("st.h%d" % i, (B, Hd), dev) for i in range(2)]
+            cb = [bf.get("st.c%d" % i, (B, Hd), dev) for i in range(2)]
+            hp = bf.get("st.hprev", (B, Hd), dev)
+            xe = bf.get("st.xe", (B, Hd), dev)
+            gates = bf.get("st.gates", (B, 4 * Hd), dev)
+            h, c, ld0 = tv, tv[:, Hd:], 2 * Hd
+            for i in range(1, I_max):
+                ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, None, xe, None, B, 1, Hd, 0,
+                              1.0, V)                                                         # model.py:192
+                self._dense_fwd(xe, Hd, B, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates,
+                                4 * Hd, 4 * Hd, Hd)
+                ops.lstm_fwd(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
+                             hb[i & 1], hp, cb[i & 1], B, 1, Hd)                              # model.py:195
+                h, c, ld0 = hb[i & 1], cb[i & 1], Hd
+                self._dense_fwd(h, Hd, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv,
+                                V, Hd)                                                        # model.py:198
+                ops.sample_multinomial(logits, self.ldv, V, u_at(i), seed, i, nxt, score, seqs, I_max, i, B)
+        else:
+            D = Hd
+            H = cfg.dec_heads
+            s0 = bf.get("st.s0", (B, D), dev)
+            ops.embed_fwd(classes_target, None, None, W("decoder.class2hid.weight"), None, None, None, s0, None, B, 1, D,
+                          0, 1.0, cfg.num_classes)
+            self._dense_fwd(lat, 2 * Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", s0, D, D, Z,
+                            accumulate=True)
+            # step 0: positions {latent prefix, SOS} go through the training-path layer (softmax over 2 queries)
+            b2 = self._buf(B, -2)
+            x = b2.get("st.x0", (B * 2, D), dev)
+            m2 = b2.get("st.mask2", (B * 2,), dev)
+            two = b2.get("st.len1", (B,), dev, torch.int32)
+            two.fill_(1)
+            sos = b2.get("st.sos", (B, 1), dev, torch.int32)
+            sos.fill_(1)
+            ops.embed_fwd(sos, None, two, W("decoder.embedding.weight"), None, s0, self.pe_dec, x, m2, B, 1, D, 1,
+                          math.sqrt(float(D)), V)
+            vsums = []
+            for l in range(cfg.dec_layers):
+                prefix = "decoder.decoder.layer%d." % l
+                vs = b2.get("st.vsum%d" % l, (B, D), dev)
+                wv, bv = W(prefix + "self_attention.W_v.weight"), W(prefix + "self_attention.W_v.bias")
+                self._dense_fwd(x, 2 * D, B, None, None, vs, D, D, D, w=wv, b=bv)                     # V of the prefix
+                self._dense_fwd(x[1:], 2 * D, B, None, None, vs, D, D, D, w=wv, b=bv, accumulate=True)  # + V of SOS
+                vsums.append(vs)
+                x = self._tf_layer_fwd(b2, "st%d." % l, prefix, x, m2, B, 2, D, H, 0.0, 0, True)
+            self._dense_fwd(x[1:], 2 * D, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits,
+                            self.ldv, V, D)
+            ops.sample_multinomial(logits, self.ldv, V, u_at(1), seed, 1, nxt, score, seqs, I_max, 1, B)
+            # steps >= 1: one query -> the softmax over the (length-1) query axis is 1 for every key, so the
+            # attended value is the running SUM of the cached values (transformer.py:96-103 with a KV cache)
+            xi = b2.get("st.xi", (B, D), dev)
+            proj = b2.get("st.proj", (B, D), dev)
+            x1 = b2.get("st.x1", (B, D), dev)
+            hbuf = b2.get("st.h", (B, 4 * D), dev)
+            f = b2.get("st.f", (B, D), dev)
+            st = b2.get("st.stats", (2, B), dev)
+            for i in range(2, I_max):
+                ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, self.pe_dec[i:], xi, None, B,
+                              1, D, 0, math.sqrt(float(D)), V)
+                cur = xi
+                for l in range(cfg.dec_layers):
+                    prefix = "decoder.decoder.layer%d." % l
+                    self._dense_fwd(cur, D, B, prefix + "self_attention.W_v.weight", prefix + "self_attention.W_v.bias",
+                                    vsums[l], D, D, D, accumulate=True)
+                    self._dense_fwd(vsums[l], D, B, prefix + "self_attention.W_proj.weight",
+                                    prefix + "self_attention.W_proj.bias", proj, D, D, D)
+                    ops.add_ln_fwd(cur, proj, W(prefix + "ln1.gamma"), W(prefix + "ln1.beta"), x1, st[0], st[1], B, D)
+                    self._dense_fwd(x1, D, B, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", hbuf, 4 * D, 4 * D, D,
+                                    relu=True)
+                    self._dense_fwd(hbuf, 4 * D, B, prefix + "ff.ff2.weight", prefix + "ff.ff2.bias", f, D, D, 4 * D)
+                    out = b2.get("st.out%d" % l, (B, D), dev)
+                    ops.add_ln_fwd(f, f, W(prefix + "ln3.gamma"), W(prefix + "ln3.beta"), out, st[0], st[1], B, D)
+                    cur = out
+                self._dense_fwd(cur, D, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv,
+                                V, D)
+                ops.sample_multinomial(logits, self.ldv, V, u_at(i), seed, i, nxt, score, seqs, I_max, i, B)
+        host = seqs.cpu()
+        done = ((host == 1) | (host == 0)).all(dim=0)            # sampler.py:186
+        stop = I_max - 1
+        for i in range(1, I_max):
+            if bool(done[i]):
+                stop = i
+                break
+        return seqs[:, :stop + 1], score
+
     # ------------------------------------------------------------------ forward
     def forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
                 z_override=None):
@@ -314,18 +464,8 @@ class VAEEngine:
         pd_ = cfg.dec_dropout if train else 0.0
         self.dropout_seed = (0x5EED0000 + self.step_count) & 0xFFFFFFFFFFFF
 
-        # ---- encoder (model.py:73-104)
-        x = bf.get("enc.x0", (M, D), dev)
-        mask = bf.get("enc.mask", (M,), dev)
-        ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
-                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V)
-        xs = [x]
-        for l in range(cfg.enc_layers):
-            x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads, pe_,
-                                   l * SITE_STRIDE, False)
-            xs.append(x)
-        lat = bf.get("lat", (B, 2 * Z), dev)
-        self._dense_fwd(x, T * D, B, "encoder.latent_proj.weight", "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
+        xs, mask, lat = self._encode(bf, tokens, classes, B, T, pe_)
+        x = xs[-1]
         if eps is None:
             eps = bf.get("eps", (B, Z), dev)
             ops.normal_fill(eps, self.dropout_seed, 0xE95)

@@ -32,3 +32,23 @@ def rasterize(dtick, pitch, vel, seq_offsets, resolution=120, slices_per_quarter
              ctypes.c_int(n_slices), ctypes.c_int(max_seq_len), ctypes.c_int(1 if velocity_roll else 0),
              lib.ptr(tokens), lib.ptr(roll), lib.ptr(n_tokens), lib.stream_ptr())
     return tokens, roll, n_tokens
+
+
+def tokenize_tracks(soas, device="cuda"):
+    """A1 for whole tracks: list of (dtick, pitch, vel) NumPy SoAs -> list of int32 id arrays, untruncated.
+    One K1 launch for all tracks (the roll output is a 1-slice dummy window)."""
+    import numpy as np
+    if not soas:
+        return []
+    lens = [len(s[0]) for s in soas]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    if offs[-1] == 0:
+        return [np.zeros(0, np.int32) for _ in soas]
+    cat = lambda i, dt: np.concatenate([np.asarray(s[i], dtype=dt) for s in soas])
+    dtick, pitch, vel = cat(0, np.int32), cat(1, np.uint8), cat(2, np.uint8)
+    # upper bound of the token count of a track: one note token + ceil(d/1000) shift tokens per event
+    bound = max(1, max(int(l + ((np.asarray(s[0], dtype=np.int64) + 999) // 1000).sum()) for l, s in zip(lens, soas)))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    tokens, _, counts = rasterize(t(dtick), t(pitch), t(vel), t(offs), n_slices=1, max_seq_len=bound)
+    tokens, counts = tokens.cpu().numpy(), counts.cpu().numpy()
+    return [tokens[i, 1:1 + counts[i]].copy() for i in range(len(soas))]

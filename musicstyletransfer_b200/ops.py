@@ -125,3 +125,8 @@ def lstm_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H):
 def adam_step(w, g, m, v, n, state, lr, beta1, beta2, eps, wd, rescale, clip, zero_grad=True):
     lib.call("msx_adam_step", P(w), P(g), P(m), P(v), _ll(n), P(state), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd),
              _f(rescale), _f(clip if clip is not None else 0.0), _i(1 if zero_grad else 0), lib.stream_ptr())
+
+
+def sample_multinomial(logits, ld, V, uniforms, seed, step, nxt, score, out_seq, out_ld, out_col, B):
+    lib.call("msx_sample_multinomial", P(logits), _i(ld), _i(V), P(uniforms), _u64(seed), _u64(step), P(nxt), P(score),
+             P(out_seq), _i(out_ld), _i(out_col), _i(B), lib.stream_ptr())

@@ -402,3 +402,48 @@ def style_transfer_lstm(cfg, p, tokens, classes_target, uniforms):
         if int(((nxt == SOS_ID) | (nxt == PAD_ID)).sum()) == B:
             break
     return seq
+
+
+def style_transfer_transformer(cfg, p, tokens, classes_target, uniforms):
+    """Sampling.sample (sampler.py:161-189) over Decoder.forward_inference / TransformerDecoder.forward_inference
+    (model.py:259-272, transformer.py:242-249) with the evident intent of the (buggy at HEAD)
+    incremental path: step 0 feeds [latent prefix, SOS] through the layers as in training; afterwards keys / values
+    of every position stay cached and the single new query position makes the softmax over the query axis
+    (transformer.py:100) identically 1, so the attended value is the SUM of all cached values.  Parity unpinned."""
+    B, T = tokens.shape
+    I_max = 2 * T
+    D, H = cfg.dec_size, cfg.dec_heads
+    means, _ = encoder_forward(cfg, p, tokens, classes_target)
+    s0 = dense(means, p, "decoder.latent2hid") + p["decoder.class2hid.weight"][classes_target.long()]
+    emb = p["decoder.embedding.weight"]
+    pe = positional_encodings(D, I_max + 2)
+    x = torch.cat([s0[:, None, :], emb[torch.full((B, 1), SOS_ID).long()]], dim=1)
+    x = math.sqrt(float(D)) * x + pe[:2]
+    mask = torch.ones(B, 2)
+    vsum = []
+    for l in range(cfg.dec_layers):
+        prefix = "decoder.decoder.layer%d." % l
+        vsum.append(dense(x, p, prefix + "self_attention.W_v").sum(dim=1))
+        x = decoder_layer(x, mask, p, prefix, H, 0.0, None)
+    seq = torch.full((B, 1), float(SOS_ID))
+
+    def emit(h, i, seq):
+        probs = torch.softmax(dense(h, p, "decoder.output_layer"), dim=-1)
+        cdf = torch.cumsum(probs, dim=-1)
+        nxt = (cdf <= uniforms[i][:, None]).sum(dim=-1).clamp(max=probs.shape[-1] - 1).float()
+        return torch.cat([seq, nxt[:, None]], dim=1), nxt
+
+    seq, nxt = emit(x[:, 1, :], 1, seq)
+    for i in range(2, I_max):
+        if int(((nxt == SOS_ID) | (nxt == PAD_ID)).sum()) == B:
+            break
+        cur = math.sqrt(float(D)) * emb[nxt.long()] + pe[i]
+        for l in range(cfg.dec_layers):
+            prefix = "decoder.decoder.layer%d." % l
+            vsum[l] = vsum[l] + dense(cur, p, prefix + "self_attention.W_v")
+            a = dense(vsum[l], p, prefix + "self_attention.W_proj")
+            h1 = layer_norm(cur + a, p, prefix + "ln1")
+            f = feed_forward(h1, p, prefix + "ff.", 0.0, None, prefix)
+            cur = layer_norm(f + f, p, prefix + "ln3")
+        seq, nxt = emit(cur, i, seq)
+    return seq

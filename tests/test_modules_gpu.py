@@ -1,0 +1,189 @@
+"""GPU tests of the reference-facing module surface (musicstyletransfer_b200.VarAutoEncoder / MIDIUtil)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import featurise as of
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_loss_classes_match_reference_golden(golden_dir):
+    """loss.py classes on the inputs / outputs recorded from the reference's own loss.py."""
+    from musicstyletransfer_b200.VarAutoEncoder import loss
+    g = np.load(os.path.join(golden_dir, "loss_golden.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    np.testing.assert_allclose(loss.VariationalKLLoss()(t("kl_means"), t("kl_stds")).cpu().numpy(), g["kl"], rtol=1e-4)
+    ce = loss.SoftmaxCrossEntropy(axis=-1, batch_axis=0)(t("ce_probs"), t("ce_labels"))
+    np.testing.assert_allclose(ce.cpu().numpy(), g["ce"], rtol=1e-4)
+    pred, label = t("bce_pred"), t("bce_label")
+    np.testing.assert_allclose(loss.BinaryCrossEntropy()(pred, label).cpu().numpy(), g["bce_default"], rtol=1e-3)
+    np.testing.assert_allclose(loss.BinaryCrossEntropy(label_smoothing=0.1)(pred, label).cpu().numpy(), g["bce_smooth"], rtol=1e-3)
+    np.testing.assert_allclose(loss.BinaryCrossEntropy(negative_label_downweighting=False)(pred, label).cpu().numpy(),
+                               g["bce_noweight"], rtol=1e-3)
+    np.testing.assert_allclose(loss.BinaryCrossEntropy(from_sigmoid=True)(torch.sigmoid(pred), label).cpu().numpy(),
+                               g["bce_fromsig"], rtol=1e-3)
+
+
+def test_loss_gradients_match_oracle():
+    from musicstyletransfer_b200.VarAutoEncoder import loss
+    gen = torch.Generator().manual_seed(0)
+    pred = (torch.randn(4, 16, 128, generator=gen) * 2)
+    label = (torch.rand(4, 16, 128, generator=gen) < 0.05).float()
+    for kw in ({}, {"label_smoothing": 0.1}, {"negative_label_downweighting": False}):
+        p_o = pred.clone().requires_grad_(True)
+        om.bce_loss(p_o, label, **kw).sum().backward()
+        p_d = pred.to(DEV).requires_grad_(True)
+        loss.BinaryCrossEntropy(**kw)(p_d, label.to(DEV)).sum().backward()
+        scale = float(p_o.grad.abs().max())
+        assert float((p_d.grad.cpu() - p_o.grad).abs().max()) <= 1e-3 * scale
+    m = torch.randn(5, 32, generator=gen)
+    s = torch.randn(5, 32, generator=gen) * 0.5 + 2.0
+    mo, so = m.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    (om.kl_loss(mo, so) * torch.arange(1, 6)).sum().backward()
+    md, sd = m.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True)
+    (loss.VariationalKLLoss()(md, sd) * torch.arange(1, 6, device=DEV)).sum().backward()
+    np.testing.assert_allclose(md.grad.cpu().numpy(), mo.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sd.grad.cpu().numpy(), so.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _write_fixture_tree(golden_dir, root, limit=6):
+    """Re-create MIDI files from the recorded note-event SoAs of the reference fixtures (the .mid files themselves
+    live under /root/reference, which does not exist on the GPU box)."""
+    from musicstyletransfer_b200.MIDIUtil import smf
+    g = np.load(os.path.join(golden_dir, "tokens_fixtures.npz"))
+    names = list(g["names"])
+    keep = [n for n in names if n.startswith("bass/")][:limit // 2] + [n for n in names if n.startswith("guitar/")][:limit // 2]
+    for n in keep:
+        d = os.path.join(root, n.split("/")[0])
+        os.makedirs(d, exist_ok=True)
+        pat = smf.Pattern(resolution=int(g["res:" + n]))
+        tr = smf.Track()
+        tr.append(smf.SetTempoEvent(tick=0, data=[7, 161, 32]))
+        for dt, p, v in zip(g["dtick:" + n], g["pitch:" + n], g["vel:" + n]):
+            tr.append(smf.NoteOnEvent(tick=int(dt), pitch=int(p), velocity=int(v)))
+        tr.append(smf.EndOfTrackEvent(tick=1))
+        pat.append(tr)
+        smf.write_midifile(os.path.join(root, n), pat)
+    return g, keep
+
+
+def test_loader_tokenises_midi_files_like_the_reference_reader(golden_dir, tmp_path):
+    """Loader -> EventBasedMIDIReader (GPU featurisation) == ids recorded from the reference's reader."""
+    from musicstyletransfer_b200.VarAutoEncoder.data import Loader, MelodyDataset
+    g, keep = _write_fixture_tree(golden_dir, str(tmp_path))
+    loader = Loader(str(tmp_path), 64, 4)
+    assert sorted(loader.melodies) == ["bass", "guitar"]
+    got = {}
+    for c, mels in loader.melodies.items():
+        for mel in mels:
+            got[tuple(e.id for e in mel)] = c
+    for n in keep:
+        assert tuple(int(i) for i in g["ids:" + n]) in got, n
+    ds = MelodyDataset(8, 64, loader.melodies)
+    by_class = [[list(g["ids:" + n]) for n in keep if n.startswith(c + "/")] for c in ("bass", "guitar")]
+    # glob order inside a class is file-system order; compare as multisets of rows
+    tok, lab, cls = of.chunk_rows(by_class, 64)
+    assert sorted(map(tuple, ds.tokens.tolist())) == sorted(map(tuple, tok.tolist()))
+
+
+@pytest.mark.parametrize("dec_type", ["lstm", "transformer"])
+def test_style_transfer_matches_oracle(dec_type):
+    """A12: class swap before encoding, z = means, autoregressive multinomial sampling with shared uniforms."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    cfg_o = om.Cfg(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type=dec_type, dec_size=32, dec_heads=4)
+    p = om.init_params(cfg_o, seed=5)
+    gen = torch.Generator().manual_seed(3)
+    for k in p:
+        if k.endswith("bias"):
+            p[k] = 0.1 * torch.randn(p[k].shape, generator=gen)
+    p["decoder.output_layer.weight"] *= 4.0          # peaked distributions -> robust to fp32 cdf rounding
+    B, T = 6, 8
+    tokens = torch.randint(3, 293, (B, T), generator=gen).float()
+    tokens[:, 0] = 1
+    tokens[2, 5:] = 0
+    lens = (tokens != 0).sum(1).float()
+    target = torch.full((B,), 1.0)
+    u = torch.rand(2 * T, B, generator=gen)
+    if dec_type == "lstm":
+        want = om.style_transfer_lstm(cfg_o, p, tokens, target, u)
+    else:
+        want = om.style_transfer_transformer(cfg_o, p, tokens, target, u)
+    eng = VAEEngine(VAEConfig(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type=dec_type, dec_size=32,
+                              dec_heads=4), DEV)
+    eng.arena.load_state(p)
+    i32 = lambda t: t.to(torch.int32).to(DEV)
+    seqs, score = eng.style_transfer(i32(tokens), i32(lens), i32(target), uniforms=u.to(DEV))
+    got = seqs.cpu().float()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert bool((got == want).all()), (got, want)
+    assert bool(torch.isfinite(score).all())
+    # Philox path: deterministic in (seed), tokens inside the vocabulary
+    a, _ = eng.style_transfer(i32(tokens), i32(lens), i32(target), seed=7)
+    a = a.clone()
+    b, _ = eng.style_transfer(i32(tokens), i32(lens), i32(target), seed=7)
+    assert a.shape == b.shape and bool((a == b).all()) and int(a.max()) < 293 and int(a.min()) >= 0
+
+
+def test_model_entry_points_and_toy_training(tmp_path):
+    """Model(config)(tokens, seq_lens, classes) -> (probs, means, vars); Trainer.fit on ToyData (main.py:58-76) lowers
+    the loss; checkpoints (params.N, train_state.pkl, config) are written and resume restores parameters."""
+    from musicstyletransfer_b200.VarAutoEncoder import main as vmain, model, trainer, utils
+    from musicstyletransfer_b200.VarAutoEncoder.data import ToyData
+    data = ToyData()
+    cfg = vmain.create_toy_model_config(data)
+    m = model.Model(cfg, precision="fp32", quiet=True)
+    batch = next(iter(data))
+    probs, means, stds = m(*batch.data)
+    assert probs.shape == (3, 5, 10) and means.shape == (3, 16) and stds.shape == (3, 16)
+    assert torch.allclose(probs.sum(-1), torch.ones(3, 5, device=DEV), atol=1e-4)
+    mu, sd = m.encoder(*batch.data)
+    assert torch.allclose(mu, means)
+    p2 = m.decoder.forward_train(None, batch.data[0], batch.data[1], mu, batch.data[2])
+    assert p2.shape == (3, 5, 10)
+    tc = vmain.create_toy_train_config()
+    tc.checkpoint_frequency = 40
+    folder = str(tmp_path / "toy")
+    os.makedirs(folder)
+    cfg.save(os.path.join(folder, "config"))
+    t = trainer.Trainer(tc, None, m, None, log_dir=str(tmp_path / "tb"), max_steps=120)
+    first = float(t._step(batch, is_train=False).mean())
+    t.fit(data, folder, epochs=1000, validation_dataset=data)
+    last = float(t._step(batch, is_train=False).mean())
+    assert last < first, (first, last)
+    assert utils.get_latest_checkpoint_index(folder) == 3
+    assert os.path.exists(os.path.join(folder, "train_state.pkl")) and os.path.exists(os.path.join(folder, "params.3"))
+    w = {k: v.clone() for k, v in m.collect_params().items()}
+    m2 = model.Model(cfg, precision="fp32", quiet=True, seed=123)
+    t2 = trainer.Trainer(tc, None, m2, None, log_dir=str(tmp_path / "tb2"), max_steps=1)
+    t2._load_latest_checkpoint(folder)
+    assert t2.train_state.n_batches == 120 or t2.train_state.n_checkpoints == 3
+    saved = torch.load(os.path.join(folder, "params.3"))
+    for k in w:
+        assert torch.equal(m2.collect_params()[k].cpu(), saved[k])
+    from musicstyletransfer_b200.VarAutoEncoder.sampler import Sampling
+    s = Sampling(folder, None, None, model_instance=m)
+    out = str(tmp_path / "samples")
+    s.process_batch(next(iter(data)), out, data.num_classes())
+    files = sorted(os.listdir(out))
+    assert "out-0.original.mid" in files and "out-2.class-2.mid" in files and len(files) == 3 + 3 * 3
+
+
+def test_train_vae_cli_runs_on_fixture_files(golden_dir, tmp_path):
+    """scripts/train-vae.sh's command line (shortened with --max-steps) on MIDI files, both decoder types."""
+    from musicstyletransfer_b200.VarAutoEncoder import main as vmain
+    _write_fixture_tree(golden_dir, str(tmp_path / "data"))
+    for dec in ("lstm", "transformer"):
+        out = str(tmp_path / ("model_" + dec))
+        vmain.main(("--batch-size 32 --kl-loss 1.0 --validation-split 0.0 --max-seq-len 64 --slices-per-quarter-note 4 "
+                    "--data %s --model-output %s --out-samples %s --sampling-frequency 2000 --checkpoint-frequency 1000 "
+                    "--num-checkpoints-not-improved 32 --epochs 2 --optimizer adam --optimizer-params clip_gradient:1.0 "
+                    "--learning-rate 0.0003 --label-smoothing 0.0 --e-n-layers 2 --e-dropout 0.2 --e-rnn-hidden-dim 256 "
+                    "--e-emb-hidden-dim 256 --latent-dim 256 --d-n-layers 1 --d-rnn-hidden-dim 128 --d-dropout 0.2 "
+                    "--decoder-type %s --max-steps 12 --log-dir %s"
+                    % (tmp_path / "data", out, tmp_path / "samples", dec, tmp_path / "tb")).split())
+        assert os.path.exists(os.path.join(out, "config"))
