@@ -19,6 +19,9 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("MSX_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "vae_train_sequences_per_sec"
 UNIT = "sequences/s"
@@ -180,7 +183,22 @@ def bench_rasteriser(peaks):
     E = dtick.size
     bytes_alg = 6 * E + 4 * (n + 1) + n * 64 * 128 + n * 65 * 4 + n * 4
     gbs = bytes_alg / (med * 1e-3) / 1e9
-    return {"workload": "BASELINE config 2: 1,048,576 note events, 32768 sequences -> tokens int32[N,65] + roll uint8[N,64,128]",
+    cpu = None
+    try:        # CPU baseline of the same workload: the oracle's C restatement on all host cores
+        from oracle import raster_c
+        if raster_c.available():
+            th = os.cpu_count() or 1
+            raster_c.rasterize_batch(dtick, pitch, vel, offs, threads=th)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                raster_c.rasterize_batch(dtick, pitch, vel, offs, threads=th)
+            sec = (time.perf_counter() - t0) / 5
+            cpu = {"value": bytes_alg / sec / 1e9, "unit": "GB/s", "cores": th, "kind": "port",
+                   "sample": "5 full passes of config 2 through oracle/raster.c (OpenMP, incl. output allocation)",
+                   "events_per_s": E / sec}
+    except Exception as exc:        # the baseline is informative only
+        cpu = {"error": str(exc)}
+    return {"cpu_baseline": cpu, "workload": "BASELINE config 2: 1,048,576 note events, 32768 sequences -> tokens int32[N,65] + roll uint8[N,64,128]",
             "ms": med, "events_per_s": E / (med * 1e-3), "roll_GBps": gbs,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": bytes_alg,

@@ -130,3 +130,24 @@ def test_roll_small_cases():
     assert roll[0, :, 5].tolist() == [0] * 48 + [1] * 16
     # delta 1000 -> one shift token of bin 0 -> clock does not move
     assert of.played_delta(1000) == 0 and of.played_delta(29) == 0 and of.played_delta(59) == 30
+
+
+def test_c_oracle_matches_numpy_oracle():
+    """oracle/raster.c (the full-size checker / CPU baseline) == oracle/featurise.py on ragged and quirky inputs."""
+    import __graft_entry__ as ge
+    from oracle import raster_c
+    if not raster_c.available():
+        ge.build()
+    rng = np.random.RandomState(11)
+    lens = [0, 1, 5, 32, 33, 200, 0, 64]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    E = int(offs[-1])
+    dtick = (rng.randint(0, 5, size=E) * 17).astype(np.int32)
+    dtick[rng.rand(E) < 0.05] = rng.randint(1000, 6000, size=int((rng.rand(E) < 0.05).sum()) or 1)[0]
+    pitch = rng.randint(40, 46, size=E).astype(np.uint8)
+    vel = np.where(rng.rand(E) < 0.5, rng.randint(1, 128, size=E), 0).astype(np.uint8)
+    for vr in (False, True):
+        for S, L, res, spq in ((64, 64, 120, 4), (16, 8, 96, 4), (128, 100, 220, 3)):
+            a = of.rasterize_batch(dtick, pitch, vel, offs, res, spq, S, L, vr)
+            b = raster_c.rasterize_batch(dtick, pitch, vel, offs, res, spq, S, L, vr, threads=2)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), (vr, S, L)

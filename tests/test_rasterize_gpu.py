@@ -91,3 +91,11 @@ def test_full_size_properties():
         a, b = offs[i], offs[i + 1]
         ids, r = of.rasterize_sequence(dtick[a:b], pitch[a:b], vel[a:b], 120, 4, 64, 1)
         assert np.array_equal(roll[i], r[0])
+    # the whole 1 M-event output, bit for bit, against the C restatement of the oracle
+    from oracle import raster_c
+    if raster_c.available():
+        ctok, croll, ccnt = raster_c.rasterize_batch(dtick, pitch, vel, offs, threads=8)
+        assert np.array_equal(tok, ctok) and np.array_equal(roll, croll) and np.array_equal(cnt, ccnt)
+        vtok, vroll, vcnt = _run(dtick, pitch, vel, offs, velocity_roll=True)
+        ctok, croll, ccnt = raster_c.rasterize_batch(dtick, pitch, vel, offs, velocity_roll=True, threads=8)
+        assert np.array_equal(vroll, croll) and np.array_equal(vtok, ctok)
