@@ -73,6 +73,13 @@ int msx_attention_fwd(const float* qkv, const float* mask, float* ctx, int B, in
 int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
                       int dh, void* stream);
 
+/* Tensor-core attention (same contract, d_h == 32 and T <= 128): S = K Q^T and O = P^T V on tcgen05, keys on the TMEM
+ * lanes so the query-axis softmax is thread-local. */
+int msx_attention_tc_supported(const float* qkv, int T, int dh);
+int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
+int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
+                         int dh, void* stream);
+
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
  * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);
  * fuse_xy: x and y alias (decoder's ln3(f + drop(f))) and dres receives ds*(1+keep). */

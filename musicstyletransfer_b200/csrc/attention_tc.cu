@@ -1,0 +1,512 @@
+// K2c (tensor-core path) — attention in the reference's convention on tcgen05, d_h = 32, T <= 128.
+//
+// Same contract as attention.cu (replaces MultiHeadDotAttention.hybrid_forward lines 91-103 and _mask_logits,
+// /root/reference/music_style_transfer/VarAutoEncoder/transformer.py:91-126):
+//   S[k][q] = K_k . Q_q / sqrt(d_h) + (key k padded ? -1e9 : 0);  P = softmax over the QUERY axis;  O[q] = sum_k P[k][q] V[k]
+//
+// One CTA (128 threads) per (batch, head).  TMA loads the K, Q, V head slices straight out of the fused
+// [B*T, 3D] projection (TFLOAT32 maps round to nearest).  MMA 1: S[128 keys x TQ queries] = K Q^T accumulates in
+// TMEM with the KEYS on the 128 TMEM lanes, so each thread owns one key row and the reference's softmax over
+// the query axis is a thread-local loop over TMEM columns (no shuffles, no shared-memory score matrix).  The
+// thread writes its normalised row as the MN-major A operand (SWIZZLE_128B_BASE32B, the only layout tcgen05
+// takes for MN-major 32-bit data) of MMA 2: O[128 queries x 32] = P^T V, whose accumulator has the QUERIES on
+// the lanes: every thread stores one 128-byte row of the context.  Rows beyond T (neighbouring sequence / OOB
+// zeros) only ever meet P == 0 or land in output rows that are not stored.
+#include <cuda.h>
+
+#include "msx_common.cuh"
+
+namespace {
+
+constexpr int DH = 32;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes,
+                                                        unsigned long long layout) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float v[16]) {
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// MN-major operand, SWIZZLE_128B_BASE32B: element (mn, k) of a slab-structured tile with `krows` rows per slab
+__device__ __forceinline__ unsigned mn_major_off(int mn, int k, int krows) {
+  return (unsigned)((mn >> 5) * (krows * 128) + k * 128 + ((((mn & 31) >> 3) ^ (k & 3)) << 5) + ((mn & 7) << 2));
+}
+
+struct AttnTcParams {
+  const float* mask;   // [B*T]
+  float* ctx;          // [B*T, H*32]
+  int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
+  unsigned tmem_cols;
+  float inv_scale;
+};
+
+template <int kTmemCols>
+__global__ void __launch_bounds__(128)
+    attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
+                       const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sK = base;                              // [128 rows][128 B]  K-major, SWIZZLE_128B
+  unsigned char* sQ = sK + 128 * 128;                    // [TQ rows][128 B]   K-major, SWIZZLE_128B
+  unsigned char* sV = sQ + ((p.TQ * 128 + 1023) & ~1023);  // [TK rows][128 B] MN-major (d contiguous), SW128_32B
+  unsigned char* sP = sV + ((p.TK * 128 + 1023) & ~1023);  // 4 slabs x [TK rows][128 B] MN-major (q contiguous)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sP + 4 * p.TK * 128);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int D = p.H * DH;
+  const int T = p.T, TQ = p.TQ, TK = p.TK;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = *tmem_slot;
+  const unsigned tmem_O = tmem, tmem_S = tmem + DH;      // O: columns [0,32), S: columns [32, 32+TQ)
+
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (unsigned)((128 + TQ + TK) * 128));
+    tma_load_2d(sK, &tmK, &bars[0], h * DH, b * T);
+    tma_load_2d(sQ, &tmQ, &bars[0], D + h * DH, b * T);
+    tma_load_2d(sV, &tmV, &bars[0], 2 * D + h * DH, b * T);
+    mbar_wait(&bars[0], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // MMA 1: S[128 x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+#pragma unroll
+    for (int k = 0; k < DH / 8; ++k)
+      umma_tf32(tmem_S, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQ) + k * 32, 16, 1024, 2),
+                idesc, k > 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  // every thread: key row k = tid
+  const int k = tid;
+  const float rowmask = (k < T && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
+  mbar_wait(&bars[1], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+  const unsigned lane_addr = tmem_S + ((unsigned)(warp * 32) << 16);
+  {
+    // tcgen05.ld is warp-collective: every lane runs the same three passes over the TMEM columns of its key
+    // row; only the arithmetic is predicated (rows k >= T hold a neighbouring sequence or zeros).
+    const bool valid = k < T;
+    float mx = -INFINITY;
+    for (int c = 0; c < TQ; c += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (valid && c + j < T) mx = fmaxf(mx, v[j] * p.inv_scale + rowmask);
+    }
+    float sum = 0.f;
+    for (int c = 0; c < TQ; c += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (valid && c + j < T) sum += expf(v[j] * p.inv_scale + rowmask - mx);
+    }
+    const float inv = valid ? 1.f / sum : 0.f;
+    for (int c = 0; c < TQ; c += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c, v);
+      if (k < TK) {      // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = (valid && c + j < T) ? to_tf32(expf(v[j] * p.inv_scale + rowmask - mx) * inv) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(sP + mn_major_off(c + j, k, TK)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // MMA 2: O[128 queries x 32] = P^T[128 x TK] * V[TK x 32]; A MN-major (queries contiguous), B MN-major (d contiguous)
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                           ((unsigned)(128 >> 4) << 24);
+    for (int j = 0; j < TK / 8; ++j)
+      umma_tf32(tmem_O, make_desc(smem_u32(sP) + j * 1024, TK * 128, 512, 1),
+                make_desc(smem_u32(sV) + j * 1024, TK * 128, 512, 1), idesc, j > 0 ? 1u : 0u);
+    umma_commit(&bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int q = tid;
+    float o[32];
+    tmem_ld16(tmem_O + ((unsigned)(warp * 32) << 16), o);
+    tmem_ld16(tmem_O + ((unsigned)(warp * 32) << 16) + 16, o + 16);
+    if (q < T) {
+      float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)b * T + q) * D + h * DH);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ backward
+// S = K Q^T and dP = V dO^T accumulate with the KEYS on the TMEM lanes, so P, delta_k = sum_q P dP and
+// dS = P (dP - delta_k) / sqrt(d_h) are thread-local.  P / dS are then written to shared memory as MN-major A
+// operands: X[k contiguous][q rows] feeds dV = P dO and dK = dS Q (lanes = keys), Y[q contiguous][k rows] feeds
+// dQ = dS^T K (lanes = queries).  The K-major operand tiles of the first two MMAs are dead by then and X aliases them.
+struct AttnTcBwdParams {
+  const float* mask;   // [B*T]
+  float* dqkv;         // [B*T, 3*H*32]
+  int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
+  float inv_scale;
+};
+
+template <int kTmemCols>
+__global__ void __launch_bounds__(128)
+    attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK128, const __grid_constant__ CUtensorMap tmQk,
+                       const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
+                       const __grid_constant__ CUtensorMap tmQKVm, const AttnTcBwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int T = p.T, TQ = p.TQ, TK = p.TK;
+  const int slab = TK * 128;                         // bytes of one 32-wide MN slab with TK reduction rows
+  unsigned char* sY = base;                          // dS^T, q contiguous: ceil(TQ/32) slabs written (4 addressed)
+  unsigned char* sDOm = sY + ((TQ + 31) / 32) * slab;  // dO  MN-major [TK rows][128 B]
+  unsigned char* sQm = sDOm + slab;                  // Q   MN-major
+  unsigned char* sKm = sQm + slab;                   // K   MN-major
+  unsigned char* sR1 = sKm + slab;                   // phase A: K-major K | V | Q | dO ; phase B: X (4 slabs)
+  unsigned char* sKk = sR1;
+  unsigned char* sVk = sKk + 128 * 128;
+  unsigned char* sQk = sVk + 128 * 128;
+  unsigned char* sDOk = sQk + TQ * 128;
+  unsigned char* sX = sR1;
+  const int r1_bytes = max(2 * 128 * 128 + 2 * TQ * 128, 4 * slab);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sR1 + r1_bytes);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int D = p.H * DH;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = *tmem_slot;
+  const unsigned tm_dV = tmem, tm_dK = tmem + 32, tm_dQ = tmem + 64, tm_S = tmem + 96, tm_dP = tmem + 96 + TQ;
+  const unsigned idesc_kk = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  const unsigned idesc_mm = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                            ((unsigned)(128 >> 4) << 24);
+
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (unsigned)((2 * 128 + 2 * TQ + 3 * TK) * 128));
+    tma_load_2d(sKk, &tmK128, &bars[0], h * DH, b * T);
+    tma_load_2d(sVk, &tmK128, &bars[0], 2 * D + h * DH, b * T);
+    tma_load_2d(sQk, &tmQk, &bars[0], D + h * DH, b * T);
+    tma_load_2d(sDOk, &tmDOk, &bars[0], h * DH, b * T);
+    tma_load_2d(sDOm, &tmDOm, &bars[0], h * DH, b * T);
+    tma_load_2d(sQm, &tmQKVm, &bars[0], D + h * DH, b * T);
+    tma_load_2d(sKm, &tmQKVm, &bars[0], h * DH, b * T);
+    mbar_wait(&bars[0], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
+      umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
+                idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < DH / 8; ++k)       // dP = V dO^T
+      umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
+                idesc_kk, k > 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  const int k = tid;
+  const bool valid = k < T;
+  const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned lane_off = (unsigned)(warp * 32) << 16;
+  float mx = -INFINITY, sum = 0.f, delta = 0.f;
+  for (int c = 0; c < TQ; c += 16) {
+    float v[16];
+    tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (valid && c + j < T) mx = fmaxf(mx, v[j] * p.inv_scale + rowmask);
+  }
+  for (int c = 0; c < TQ; c += 16) {
+    float v[16];
+    tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (valid && c + j < T) sum += expf(v[j] * p.inv_scale + rowmask - mx);
+  }
+  const float inv = valid ? 1.f / sum : 0.f;
+  // pass 3: P -> X (k contiguous) for dV, delta_k = sum_q P dP
+  for (int c = 0; c < TQ; c += 16) {
+    float v[16], g[16];
+    tmem_ld16(tm_S + lane_off + c, v);
+    tmem_ld16(tm_dP + lane_off + c, g);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float pr = (valid && c + j < T) ? expf(v[j] * p.inv_scale + rowmask - mx) * inv : 0.f;
+      delta = fmaf(pr, g[j], delta);
+      if (c + j < TK) *reinterpret_cast<float*>(sX + mn_major_off(k, c + j, TK)) = to_tf32(pr);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int j = 0; j < TK / 8; ++j)       // dV[keys x 32] = P[keys x q] dO[q x 32]
+      umma_tf32(tm_dV, make_desc(smem_u32(sX) + j * 1024, slab, 512, 1), make_desc(smem_u32(sDOm) + j * 1024, slab, 512, 1),
+                idesc_mm, j > 0 ? 1u : 0u);
+    umma_commit(&bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);                  // X may be overwritten once dV's MMAs have read it
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // pass 4: dS = P (dP - delta) / sqrt(d_h) -> X (k contiguous, for dK) and Y (q contiguous, for dQ)
+  for (int c = 0; c < TQ; c += 16) {
+    float v[16], g[16];
+    tmem_ld16(tm_S + lane_off + c, v);
+    tmem_ld16(tm_dP + lane_off + c, g);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float pr = (valid && c + j < T) ? expf(v[j] * p.inv_scale + rowmask - mx) * inv : 0.f;
+      v[j] = to_tf32(pr * (g[j] - delta) * p.inv_scale);
+      if (c + j < TK) *reinterpret_cast<float*>(sX + mn_major_off(k, c + j, TK)) = v[j];
+    }
+    if (k < TK) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(sY + mn_major_off(c + j, k, TK)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int j = 0; j < TK / 8; ++j)       // dK[keys x 32] = dS[keys x q] Q[q x 32]
+      umma_tf32(tm_dK, make_desc(smem_u32(sX) + j * 1024, slab, 512, 1), make_desc(smem_u32(sQm) + j * 1024, slab, 512, 1),
+                idesc_mm, j > 0 ? 1u : 0u);
+    for (int j = 0; j < TK / 8; ++j)       // dQ[queries x 32] = dS^T[q x keys] K[keys x 32]
+      umma_tf32(tm_dQ, make_desc(smem_u32(sY) + j * 1024, slab, 512, 1), make_desc(smem_u32(sKm) + j * 1024, slab, 512, 1),
+                idesc_mm, j > 0 ? 1u : 0u);
+    umma_commit(&bars[3]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[3], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
+    float o[32];
+    float* rowp = p.dqkv + ((size_t)b * T + tid) * 3 * D + h * DH;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const unsigned src = m == 0 ? tm_dK : m == 1 ? tm_dQ : tm_dV;
+      tmem_ld16(src + lane_off, o);
+      tmem_ld16(src + lane_off + 16, o + 16);
+      if (tid < T) {
+        float4* dst = reinterpret_cast<float4*>(rowp + m * D);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
+             int box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { msx_set_error("msx_attention_tc: cuTensorMapEncodeTiled unavailable"); return MSX_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { msx_set_error("msx_attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MSX_ERR_CUDA; }
+  return MSX_OK;
+}
+
+}  // namespace
+
+extern "C" int msx_attention_tc_supported(const float* qkv, int T, int dh) {
+  return (qkv && dh == 32 && T >= 1 && T <= 128 && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
+}
+
+extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
+                                    void* stream) {
+  MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
+  MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
+  if (B == 0) return MSX_OK;
+  const int D = H * DH;
+  AttnTcParams p;
+  p.mask = mask; p.ctx = ctx; p.T = T; p.H = H;
+  p.TQ = (T + 15) / 16 * 16;
+  p.TK = (T + 7) / 8 * 8;
+  p.inv_scale = 1.f / sqrtf((float)DH);
+  const long long rows = (long long)B * T;
+  CUtensorMap tk, tq, tv;
+  int rc;
+  if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, 128, false))) return rc;
+  if ((rc = make_map(&tq, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false))) return rc;
+  if ((rc = make_map(&tv, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
+  const size_t smem = 1024 + 128 * 128 + ((p.TQ * 128 + 1023) & ~1023) + ((p.TK * 128 + 1023) & ~1023) +
+                      (size_t)4 * p.TK * 128 + 64;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.TQ + DH <= 128) {
+    p.tmem_cols = 128;
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<128><<<B * H, 128, smem, st>>>(tk, tq, tv, p);
+  } else {
+    p.tmem_cols = 256;
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<256><<<B * H, 128, smem, st>>>(tk, tq, tv, p);
+  }
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T,
+                                    int H, int dh, void* stream) {
+  MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_tc_bwd: null pointer");
+  MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
+              "msx_attention_tc_bwd: needs d_h == 32, T <= 128, 16-byte aligned buffers");
+  if (B == 0) return MSX_OK;
+  const int D = H * DH;
+  AttnTcBwdParams p;
+  p.mask = mask; p.dqkv = dqkv; p.T = T; p.H = H;
+  p.TQ = (T + 15) / 16 * 16;
+  p.TK = (T + 7) / 8 * 8;
+  p.inv_scale = 1.f / sqrtf((float)DH);
+  const long long rows = (long long)B * T;
+  CUtensorMap tK128, tQk, tDOk, tDOm, tQKVm;
+  int rc;
+  if ((rc = make_map(&tK128, qkv, rows, 3 * D, 3 * D, DH, 128, false))) return rc;
+  if ((rc = make_map(&tQk, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false))) return rc;
+  if ((rc = make_map(&tDOk, dctx, rows, D, D, DH, p.TQ, false))) return rc;
+  if ((rc = make_map(&tDOm, dctx, rows, D, D, DH, p.TK, true))) return rc;
+  if ((rc = make_map(&tQKVm, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
+  const int slab = p.TK * 128;
+  const int r1 = max(2 * 128 * 128 + 2 * p.TQ * 128, 4 * slab);
+  const size_t smem = 1024 + (size_t)((p.TQ + 31) / 32) * slab + 3 * (size_t)slab + r1 + 64;
+  MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_bwd: shared memory budget exceeded (T=%d)", T);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (96 + 2 * p.TQ <= 256) {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_bwd_kernel<256><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+  } else {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_bwd_kernel<512><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+  }
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

@@ -228,7 +228,10 @@ class VAEEngine:
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
         ctx = bf.get(tag + "ctx", (M, D), dev)
-        ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
+        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H)
+        else:
+            ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
         proj = bf.get(tag + "proj", (M, D), dev)
         self._dense_fwd(ctx, D, M, prefix + "self_attention.W_proj.weight", prefix + "self_attention.W_proj.bias",
                         proj, D, D, D)
@@ -293,7 +296,10 @@ class VAEEngine:
                         self._G(prefix + "self_attention.W_proj.weight"), self._G(prefix + "self_attention.W_proj.bias"),
                         D, D, dx=dctx, lddx=D)
         dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
-        ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
+        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
+        else:
+            ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)

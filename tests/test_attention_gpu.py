@@ -1,0 +1,73 @@
+"""Attention kernels (reference convention: softmax over the query axis) vs a float64 host computation."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_fwd(qkv, mask, B, T, H, dh):
+    D = H * dh
+    x = qkv.double().view(B, T, 3, H, dh)
+    K, Q, V = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)   # [B,H,T,dh]
+    S = K @ Q.transpose(-1, -2) / np.sqrt(dh)
+    m = torch.where(mask.view(B, T) > 0, 0.0, -1e9).double()
+    # fp32 semantics of the reference: S + (-1e9) rounds to exactly -1e9 (uniform softmax over the row) while
+    # autograd still passes the gradient through the add -> straight-through value replacement
+    pad = (m[:, None, :, None] < 0).to(S.dtype)
+    S = S + pad * (-1e9 - S).detach()
+    P = torch.softmax(S, dim=-1)
+    O = P.transpose(-1, -2) @ V
+    return O.transpose(1, 2).reshape(B * T, D)
+
+
+def _inputs(B, T, H, dh, seed):
+    g = torch.Generator().manual_seed(seed)
+    qkv = torch.randn(B * T, 3 * H * dh, generator=g)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().reshape(-1)
+    return qkv, mask
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8)])
+def test_attention_tc_forward(B, T, H):
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    qkv, mask = _inputs(B, T, H, dh, seed=T)
+    want = _ref_fwd(qkv, mask, B, T, H, dh)
+    qd, md = qkv.cuda(), mask.cuda()
+    assert ops.attention_tc_supported(qd, T, dh)
+    ctx = torch.full((B * T, H * dh), 3.0, device="cuda")
+    ops.attention_tc_fwd(qd, md, ctx, B, T, H, dh)
+    ctx2 = torch.empty((B * T, H * dh), device="cuda")
+    ops.attention_fwd(qd, md, ctx2, B, T, H, dh)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    assert float((ctx2.double().cpu() - want).abs().max()) / scale < 1e-5
+    err = float((ctx.double().cpu() - want).abs().max()) / scale
+    assert err < 3e-3, err
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8)])
+def test_attention_backward(B, T, H):
+    """dqkv of both backward kernels vs torch autograd (float64) through the reference formula."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    qkv, mask = _inputs(B, T, H, dh, seed=100 + T)
+    g = torch.Generator().manual_seed(T)
+    dctx = torch.randn(B * T, H * dh, generator=g)
+    x = qkv.double().requires_grad_(True)
+    (_ref_fwd(x, mask, B, T, H, dh) * dctx.double()).sum().backward()
+    want = x.grad
+    scale = float(want.abs().max())
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    out = torch.empty_like(qd)
+    ops.attention_bwd(qd, md, dd, out, B, T, H, dh)
+    torch.cuda.synchronize()
+    assert float((out.double().cpu() - want).abs().max()) / scale < 1e-4
+    out2 = torch.full_like(qd, 5.0)
+    ops.attention_tc_bwd(qd, md, dd, out2, B, T, H, dh)
+    torch.cuda.synchronize()
+    err = float((out2.double().cpu() - want).abs().max()) / scale
+    assert err < 5e-3, err
