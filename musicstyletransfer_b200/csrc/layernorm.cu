@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int kMaxPer = 8;      // float4 groups per lane  -> D <= 1024 (vector path), D <= 256 (scalar path)
+constexpr int kMaxPer = 8;      // max groups per lane -> D <= 1024 (vector path), D <= 256 (scalar path)
 constexpr int kWarps = 8;
 
 template <int VEC>
@@ -22,12 +22,12 @@ __device__ __forceinline__ int elem_index(int i, int lane, int j) {
 }
 
 // s = x + drop(y) for this lane's elements of row `row`
-template <int VEC>
+template <int VEC, int kPer>
 __device__ __forceinline__ void load_sum(const float* __restrict__ x, const float* __restrict__ y, size_t row, int D,
                                          int nper, int lane, float p, float inv_keep, unsigned long long seed,
-                                         unsigned site, float s[kMaxPer][VEC], float keep[kMaxPer][VEC]) {
+                                         unsigned site, float s[kPer][VEC], float keep[kPer][VEC]) {
 #pragma unroll
-  for (int i = 0; i < kMaxPer; ++i) {
+  for (int i = 0; i < kPer; ++i) {
     if (i >= nper) break;
     if (VEC == 4) {
       const int e = (i * 32 + lane) * 4;
@@ -52,7 +52,7 @@ __device__ __forceinline__ void load_sum(const float* __restrict__ x, const floa
   }
 }
 
-template <int VEC>
+template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ out,
@@ -63,18 +63,18 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
   const int nper = D / (32 * VEC);
   const float invD = 1.f / D;
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
-    float s[kMaxPer][VEC], keep[kMaxPer][VEC];
-    load_sum<VEC>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    float s[kPer][VEC], keep[kPer][VEC];
+    load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPer; ++i)
+    for (int i = 0; i < kPer; ++i)
       if (i < nper)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) sum += s[i][j];
     const float mean = warp_sum(sum) * invD;
     float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPer; ++i)
+    for (int i = 0; i < kPer; ++i)
       if (i < nper)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
     var = warp_sum(var) * invD;
     const float rstd = 1.f / sqrtf(var + eps);
 #pragma unroll
-    for (int i = 0; i < kMaxPer; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       if (i >= nper) break;
       if (VEC == 4) {
         const int e = (i * 32 + lane) * 4;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
 }
 
 // ds = rstd * (g*dout - mean(g*dout) - xhat * mean(g*dout*xhat));  dres = ds;  dy = ds * keep
-template <int VEC>
+template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
@@ -119,30 +119,41 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nper = D / (32 * VEC);
   const float invD = 1.f / D;
-  float dg[kMaxPer][VEC], db[kMaxPer][VEC];
+  float dg[kPer][VEC], db[kPer][VEC];
 #pragma unroll
-  for (int i = 0; i < kMaxPer; ++i)
+  for (int i = 0; i < kPer; ++i)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = 0.f;
 
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
-    float s[kMaxPer][VEC], keep[kMaxPer][VEC];
-    load_sum<VEC>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    float s[kPer][VEC], keep[kPer][VEC];
+    load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float go[kMaxPer][VEC];
+    float go[kPer][VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPer; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       if (i >= nper) break;
+      float dv[VEC], gv[VEC];
+      if (VEC == 4) {
+        const int e = (i * 32 + lane) * 4;
+        const float4 d4 = *reinterpret_cast<const float4*>(dout + (size_t)row * D + e);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        dv[0] = d4.x; dv[1 % VEC] = d4.y; dv[2 % VEC] = d4.z; dv[3 % VEC] = d4.w;
+        gv[0] = g4.x; gv[1 % VEC] = g4.y; gv[2 % VEC] = g4.z; gv[3 % VEC] = g4.w;
+      } else {
+        const int e = i * 32 + lane;
+        dv[0] = dout[(size_t)row * D + e];
+        gv[0] = __ldg(gamma + e);
+      }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const int e = elem_index<VEC>(i, lane, j);
-        const float d = dout[(size_t)row * D + e];
+        const float d = dv[j];
         const float xh = (s[i][j] - mean) * rstd;
         s[i][j] = xh;
         dg[i][j] = fmaf(d, xh, dg[i][j]);
         db[i][j] += d;
-        const float gd = d * __ldg(gamma + e);
+        const float gd = d * gv[j];
         go[i][j] = gd;
         s1 += gd;
         s2 = fmaf(gd, xh, s2);
@@ -151,23 +162,36 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
 #pragma unroll
-    for (int i = 0; i < kMaxPer; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       if (i >= nper) break;
+      float dr[VEC], dyv[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const int e = elem_index<VEC>(i, lane, j);
         const float ds = rstd * (go[i][j] - s1 - s[i][j] * s2);
-        const size_t o = (size_t)row * D + e;
         // fuse_xy: x and y are the same tensor (decoder's ln3(f + drop(f))) -> one gradient ds*(1+keep)
-        if (dy && !fuse_xy) dy[o] = ds * keep[i][j];
-        const float dr = fuse_xy ? ds * (1.f + keep[i][j]) : ds;
-        dres[o] = accumulate_dres ? dres[o] + dr : dr;
+        dyv[j] = ds * keep[i][j];
+        dr[j] = fuse_xy ? ds * (1.f + keep[i][j]) : ds;
+      }
+      if (VEC == 4) {
+        const size_t o = (size_t)row * D + (i * 32 + lane) * 4;
+        if (dy && !fuse_xy)
+          *reinterpret_cast<float4*>(dy + o) = make_float4(dyv[0], dyv[1 % VEC], dyv[2 % VEC], dyv[3 % VEC]);
+        float4 r4 = make_float4(dr[0], dr[1 % VEC], dr[2 % VEC], dr[3 % VEC]);
+        if (accumulate_dres) {
+          const float4 o4 = *reinterpret_cast<const float4*>(dres + o);
+          r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
+        }
+        *reinterpret_cast<float4*>(dres + o) = r4;
+      } else {
+        const size_t o = (size_t)row * D + i * 32 + lane;
+        if (dy && !fuse_xy) dy[o] = dyv[0];
+        dres[o] = accumulate_dres ? dres[o] + dr[0] : dr[0];
       }
     }
   }
   // CTA-level reduction of dgamma/dbeta, then one atomic per column
 #pragma unroll
-  for (int i = 0; i < kMaxPer; ++i) {
+  for (int i = 0; i < kPer; ++i) {
     if (i >= nper) break;
     for (int pass = 0; pass < 2; ++pass) {
       __syncthreads();
@@ -198,15 +222,18 @@ extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps, drop_p, inv_keep, seed, site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
-    add_ln_fwd_kernel<4><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps,
-                                                                         drop_p, inv_keep, seed, site);
+    const int nper = D / 128;
+    if (nper <= 1) LN_FWD(4, 1); else if (nper <= 2) LN_FWD(4, 2); else if (nper <= 4) LN_FWD(4, 4); else LN_FWD(4, 8);
   } else {
     MSX_REQUIRE(D <= 32 * kMaxPer, "msx_add_ln_fwd: D=%d unsupported (need D%%128==0 or D<=256)", D);
-    add_ln_fwd_kernel<1><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps,
-                                                                         drop_p, inv_keep, seed, site);
+    const int nper = D / 32;
+    if (nper <= 2) LN_FWD(1, 2); else LN_FWD(1, 8);
   }
+#undef LN_FWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -219,19 +246,21 @@ extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
   if (M == 0) return MSX_OK;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int grid = (int)min((long long)msx_num_sms() * 4, (M + kWarps - 1) / kWarps);
-  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
+  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
+                                       (uintptr_t)gamma) & 15) == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p, inv_keep, seed, site, accumulate_dres, fuse_xy)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
-    add_ln_bwd_kernel<4><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma,
-                                                                         dbeta, M, D, drop_p, inv_keep, seed, site,
-                                                                         accumulate_dres, fuse_xy);
+    const int nper = D / 128;
+    if (nper <= 1) LN_BWD(4, 1); else if (nper <= 2) LN_BWD(4, 2); else if (nper <= 4) LN_BWD(4, 4); else LN_BWD(4, 8);
   } else {
     MSX_REQUIRE(D <= 32 * kMaxPer, "msx_add_ln_bwd: D=%d unsupported", D);
-    add_ln_bwd_kernel<1><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma,
-                                                                         dbeta, M, D, drop_p, inv_keep, seed, site,
-                                                                         accumulate_dres, fuse_xy);
+    const int nper = D / 32;
+    if (nper <= 2) LN_BWD(1, 2); else LN_BWD(1, 8);
   }
+#undef LN_BWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
