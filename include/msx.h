@@ -57,8 +57,11 @@ int msx_gemm_f32(const float* A, int lda, int transA, const float* B, int ldb, i
 
 int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
                 int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
-                const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, void* stream);
-/* msx_gemm_tc writes C through TMA in 16-byte chunks: padding columns N .. roundup4(N)-1 of C may be overwritten.
+                const float* aux, int ldaux, float aux_scale, int accumulate, int splitk, float* out_colsum,
+                void* stream);
+/* out_colsum (optional, plain stores only): out_colsum[n] += sum_m C[m,n] — the bias gradient of the layer whose
+ * pre-activation gradient this dgrad produces, folded into the epilogue.
+ * msx_gemm_tc writes C through TMA in 16-byte chunks: padding columns N .. roundup4(N)-1 of C may be overwritten.
  * 1 when msx_gemm_tc accepts the operands (TMA: 16-byte aligned bases, leading dimensions multiple of 4). */
 int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
                           int K);
@@ -77,8 +80,8 @@ int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, fl
  * lanes so the query-axis softmax is thread-local. */
 int msx_attention_tc_supported(const float* qkv, int T, int dh);
 int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
-int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
-                         int dh, void* stream);
+int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias, int B,
+                         int T, int H, int dh, void* stream);   /* dbias (optional) [3*H*dh] += column sums of dqkv */
 
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
  * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);
@@ -87,9 +90,9 @@ int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const flo
                    float* rstd, long long M, int D, float eps, float drop_p, unsigned long long seed, unsigned site,
                    void* stream);
 int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
-                   const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, long long M, int D,
-                   float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
-                   void* stream);
+                   const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, float* dybias, long long M,
+                   int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
+                   void* stream);   /* dybias (optional) [D] += column sums of the y-gradient */
 
 /* K2a — embedding front end.  Replaces model.py:81-91 + transformer.py:270 (encoder), model.py:241-247 +
  * transformer.py:237 (Transformer decoder, prefix = 1 latent-state row), model.py:176 (LSTM decoder).
@@ -108,7 +111,7 @@ int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* do
 int msx_lstm_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const float* h0, const float* c0, int ld0,
                  float* hs, float* hprev, float* cs, int B, int T, int H, void* stream);
 int msx_lstm_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0, const float* dhs,
-                 float* dh0, float* dc0, int B, int T, int H, void* stream);
+                 float* dh0, float* dc0, float* db_i2h, float* db_h2h, int B, int T, int H, void* stream);
 
 /* K3 — losses.  msx_reparam_kl_*: z = m + eps*s and VariationalKLLoss (model.py:292, loss.py:8-12);
  * msx_ce_*: softmax(output_layer) + SoftmaxCrossEntropy (model.py:182/256, loss.py:16-23) fused on logits
@@ -123,7 +126,7 @@ int msx_normal_fill(float* out, long long n, unsigned long long seed, unsigned l
 int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, float* ce, float* lse, float* metrics, int B, int T,
                int V, int denom, int top_k, void* stream);
 int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B, int T,
-               int V, int denom, void* stream);
+               int V, int denom, float* dbias, void* stream);   /* dbias (optional) [V] += column sums of the gradient */
 int msx_softmax_rows(const float* logits, int ld, float* probs, long long rows, int V, void* stream);
 int msx_ce_from_probs(const float* probs, const int32_t* labels, float* ce, int B, int T, int V, void* stream);
 int msx_bce(const float* pred, const uint8_t* label, float* out, const float* gout, float* dpred, int B,

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(128)
 struct AttnTcBwdParams {
   const float* mask;   // [B*T]
   float* dqkv;         // [B*T, 3*H*32]
+  float* dbias;        // optional [3*H*32]: += column sums of dqkv (bias gradient of the fused K|Q|V projection)
   int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
   float inv_scale;
 };
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(128)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sR1 + r1_bytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4);
 
+  __shared__ float red[3 * 128];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int D = p.H * DH;
@@ -398,6 +400,20 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       }
+      if (p.dbias) {
+        if (tid >= T) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0.f;
+        }
+        red[m * 128 + warp * 32 + (tid & 31)] = warp_colsum32(o, tid & 31);
+      }
+    }
+    if (p.dbias) {
+      __syncthreads();
+      if (tid < 96) {
+        const int m = tid >> 5, c = tid & 31;
+        atomicAdd(p.dbias + m * D + h * DH + c, red[m * 128 + c] + red[m * 128 + 32 + c] + red[m * 128 + 64 + c] + red[m * 128 + 96 + c]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -475,15 +491,15 @@ extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* 
   return MSX_OK;
 }
 
-extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T,
-                                    int H, int dh, void* stream) {
+extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias,
+                                    int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_tc_bwd: null pointer");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
               "msx_attention_tc_bwd: needs d_h == 32, T <= 128, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnTcBwdParams p;
-  p.mask = mask; p.dqkv = dqkv; p.T = T; p.H = H;
+  p.mask = mask; p.dqkv = dqkv; p.dbias = dbias; p.T = T; p.H = H;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.inv_scale = 1.f / sqrtf((float)DH);

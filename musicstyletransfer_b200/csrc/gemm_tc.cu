@@ -43,6 +43,7 @@ struct TcParams {
   int ldaux;
   float aux_scale;
   int accumulate, splitk;
+  float* out_colsum;   // out_colsum[n] += sum_m C[m,n] of the values this launch writes (bias gradient of the producer)
   int m_tiles, n_tiles, kb_total, kb_per_split;
 };
 
@@ -279,6 +280,13 @@ __global__ void __launch_bounds__(kThreads, 1)
               for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < p.N && __ldg(ax + j) > 0.f) ? p.aux_scale : 0.f;
             }
           }
+          if (p.out_colsum) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = my_row < p.M ? v[j] : 0.f;
+            const float cs = warp_colsum32(t, lane);
+            if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs);
+          }
           // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
           unsigned char* box = st + sbuf * kOutBoxBytes;
           if (pending >= 2) {                     // the box we are about to overwrite must have been read
@@ -379,8 +387,9 @@ extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, in
 extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
                            int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed,
                            unsigned site, const float* aux, int ldaux, float aux_scale, int accumulate, int splitk,
-                           void* stream) {
+                           float* out_colsum, void* stream) {
   MSX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "msx_gemm_tc: negative dimension");
+  MSX_REQUIRE(!(out_colsum && (accumulate || splitk > 1)), "msx_gemm_tc: out_colsum needs a plain (non-accumulating) store");
   if (M == 0 || N == 0) return MSX_OK;
   MSX_REQUIRE(A && B && C, "msx_gemm_tc: null operand");
   MSX_REQUIRE(K > 0, "msx_gemm_tc: K must be > 0");
@@ -405,6 +414,7 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+  p.out_colsum = out_colsum;
   p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN); p.kb_total = msx_ceil_div(K, BK);
   if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = msx_ceil_div(p.kb_total, splitk);

@@ -113,17 +113,17 @@ template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
-    float* __restrict__ dres, float* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M,
-    int D, float p, float inv_keep, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy) {
+    float* __restrict__ dres, float* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy) {
   __shared__ float red[kWarps][32 * VEC + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nper = D / (32 * VEC);
   const float invD = 1.f / D;
-  float dg[kPer][VEC], db[kPer][VEC];
+  float dg[kPer][VEC], db[kPer][VEC], dyb[kPer][VEC];   // dyb: column sums of the y-gradient = bias grad of the Dense that made y
 #pragma unroll
   for (int i = 0; i < kPer; ++i)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = 0.f;
+    for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = dyb[i][j] = 0.f;
 
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
     float s[kPer][VEC], keep[kPer][VEC];
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
         // fuse_xy: x and y are the same tensor (decoder's ln3(f + drop(f))) -> one gradient ds*(1+keep)
         dyv[j] = ds * keep[i][j];
         dr[j] = fuse_xy ? ds * (1.f + keep[i][j]) : ds;
+        dyb[i][j] += fuse_xy ? dr[j] : dyv[j];
       }
       if (VEC == 4) {
         const size_t o = (size_t)row * D + (i * 32 + lane) * 4;
@@ -193,10 +194,10 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     if (i >= nper) break;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < (dybias ? 3 : 2); ++pass) {
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) red[warp][lane * VEC + j] = pass == 0 ? dg[i][j] : db[i][j];
+      for (int j = 0; j < VEC; ++j) red[warp][lane * VEC + j] = pass == 0 ? dg[i][j] : pass == 1 ? db[i][j] : dyb[i][j];
       __syncthreads();
       for (int c = threadIdx.x; c < 32 * VEC; c += kWarps * 32) {
         float t = 0.f;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
         for (int w = 0; w < kWarps; ++w) t += red[w][c];
         const int l = c / VEC, j = c % VEC;
         const int e = elem_index<VEC>(i, l, j);
-        atomicAdd((pass == 0 ? dgamma : dbeta) + e, t);
+        atomicAdd((pass == 0 ? dgamma : pass == 1 ? dbeta : dybias) + e, t);
       }
     }
   }
@@ -239,8 +240,8 @@ extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma
 }
 
 extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
-                              const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, long long M, int D,
-                              float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
+                              const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, float* dybias,
+                              long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
                               void* stream) {
   MSX_REQUIRE(x && y && gamma && mean && rstd && dout && dres && dgamma && dbeta, "msx_add_ln_bwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
@@ -250,7 +251,7 @@ extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
                                        (uintptr_t)gamma) & 15) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p, inv_keep, seed, site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, site, accumulate_dres, fuse_xy)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
     const int nper = D / 128;

@@ -115,21 +115,45 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
   }
 }
 
-// in place: logits <- d ce_b / d logits * gout[b] = (softmax - onehot) * mask * gout[b] / T ; pad columns zeroed
+// in place: logits <- d ce_b / d logits * gout[b] = (softmax - onehot) * mask * gout[b] / denom ; pad columns zeroed.
+// dbias (optional, V <= 512): column sums of the gradient = bias gradient of the output layer, accumulated per
+// warp in registers over its rows and added with one atomic per column per warp.
 __global__ void __launch_bounds__(256) ce_bwd_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
                                                      const float* __restrict__ lse, const float* __restrict__ gout,
-                                                     long long rows, int T, int V, int denom) {
+                                                     long long rows, int T, int V, int denom, float* __restrict__ dbias) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  float* x = logits + row * ld;
-  const int label = labels[row];
-  const float g = label != 0 ? (gout ? gout[row / T] : 1.f) / denom : 0.f;
-  const float l = lse[row];
-  for (int v = lane; v < ld; v += 32) {
-    float d = 0.f;
-    if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
-    x[v] = d;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float bs[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) bs[i] = 0.f;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float* x = logits + row * ld;
+    const int label = labels[row];
+    const float g = label != 0 ? (gout ? gout[row / T] : 1.f) / denom : 0.f;
+    const float l = lse[row];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = lane + 32 * i;
+      if (v < ld) {
+        float d = 0.f;
+        if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
+        x[v] = d;
+        bs[i] += d;
+      }
+    }
+    for (int v = lane + 512; v < ld; v += 32) {       // vocabularies beyond 512 columns (no fused bias sum)
+      float d = 0.f;
+      if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
+      x[v] = d;
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = lane + 32 * i;
+      if (v < V && bs[i] != 0.f) atomicAdd(dbias + v, bs[i]);
+    }
   }
 }
 
@@ -271,11 +295,13 @@ extern "C" int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, fl
 }
 
 extern "C" int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B,
-                          int T, int V, int denom, void* stream) {
+                          int T, int V, int denom, float* dbias, void* stream) {
   MSX_REQUIRE(logits_inout && labels && lse, "msx_ce_bwd: null pointer");
   if (B == 0) return MSX_OK;
   const long long rows = (long long)B * T;
-  ce_bwd_kernel<<<msx_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(logits_inout, ld, labels, lse, gout, rows, T, V, denom);
+  MSX_REQUIRE(dbias == nullptr || V <= 512, "msx_ce_bwd: fused bias gradient supports V <= 512");
+  const int grid = (int)min((long long)msx_num_sms() * 16, (rows + 7) / 8);
+  ce_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits_inout, ld, labels, lse, gout, rows, T, V, denom, dbias);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -125,7 +125,7 @@ template <int H, int RPT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * H)
     lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ w_h2h, const float* __restrict__ cs,
                     const float* __restrict__ c0, int ld0, const float* __restrict__ dhs, float* __restrict__ dh0,
-                    float* __restrict__ dc0, int B, int T) {
+                    float* __restrict__ dc0, float* __restrict__ db_i2h, float* __restrict__ db_h2h, int B, int T) {
   constexpr int UH = H / 2;
   constexpr int R = 8 * RPT;       // batch rows per cluster (8 row groups in the reduction mapping)
   constexpr int RC = R / 4;        // rows per thread in the cell mapping (4 row groups)
@@ -152,6 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * H)
   }
   for (int i = tid; i < R * UH; i += blockDim.x) { dhrec[i] = 0.f; dhin[i] = 0.f; }
   float dc[RC];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // bias gradient of this thread's unit (sum over its rows and all t)
 #pragma unroll
   for (int r = 0; r < RC; ++r) dc[r] = 0.f;
   float* dhin_peer = cluster.map_shared_rank(dhin, crank ^ 1);
@@ -178,6 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * H)
         df = dct * cp * fg * (1.f - fg);
         dc[r] = dct * fg;
         gp[0] = di; gp[H] = df; gp[2 * H] = dgg; gp[3 * H] = dout;
+        bsum[0] += di; bsum[1] += df; bsum[2] += dgg; bsum[3] += dout;
       }
       dg[row * J + 0 * UH + ul] = di;
       dg[row * J + 1 * UH + ul] = df;
@@ -216,6 +218,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * H)
     cluster.sync();   // dhrec / dhin ready for step t-1
   }
 #pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (db_i2h) atomicAdd(db_i2h + g * H + u, bsum[g]);
+    if (db_h2h) atomicAdd(db_h2h + g * H + u, bsum[g]);
+  }
+#pragma unroll
   for (int r = 0; r < RC; ++r) {
     const int row = rgc * RC + r, b = b0 + row;
     if (b < B) {
@@ -239,12 +246,12 @@ int launch_fwd(float* gx, const float* w, const float* bh, const float* h0, cons
 
 template <int H, int RPT>
 int launch_bwd(float* gates, const float* w, const float* cs, const float* c0, int ld0, const float* dhs, float* dh0,
-               float* dc0, int B, int T, cudaStream_t st) {
+               float* dc0, float* dbi, float* dbh, int B, int T, cudaStream_t st) {
   constexpr int R = 8 * RPT;
   const size_t smem = ((size_t)2 * H * H + (size_t)R * 2 * H + 2 * R * (H / 2)) * sizeof(float);
   MSX_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<H, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int clusters = (B + R - 1) / R;
-  lstm_bwd_kernel<H, RPT><<<clusters * 2, 2 * H, smem, st>>>(gates, w, cs, c0, ld0, dhs, dh0, dc0, B, T);
+  lstm_bwd_kernel<H, RPT><<<clusters * 2, 2 * H, smem, st>>>(gates, w, cs, c0, ld0, dhs, dh0, dc0, dbi, dbh, B, T);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -269,18 +276,19 @@ extern "C" int msx_lstm_fwd(float* gx_inout, const float* w_h2h, const float* b_
 }
 
 extern "C" int msx_lstm_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0,
-                            const float* dhs, float* dh0, float* dc0, int B, int T, int H, void* stream) {
+                            const float* dhs, float* dh0, float* dc0, float* db_i2h, float* db_h2h, int B, int T, int H,
+                            void* stream) {
   MSX_REQUIRE(gates_inout && w_h2h && cs && c0 && dhs && dh0 && dc0, "msx_lstm_bwd: null pointer");
   if (B == 0 || T == 0) return MSX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool small = B <= msx_num_sms() * 4;
   switch (H) {
-    case 32: return small ? launch_bwd<32, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st)
-                          : launch_bwd<32, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st);
-    case 64: return small ? launch_bwd<64, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st)
-                          : launch_bwd<64, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st);
-    case 128: return small ? launch_bwd<128, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st)
-                           : launch_bwd<128, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, st);
+    case 32: return small ? launch_bwd<32, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st)
+                          : launch_bwd<32, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st);
+    case 64: return small ? launch_bwd<64, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st)
+                          : launch_bwd<64, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st);
+    case 128: return small ? launch_bwd<128, 1>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st)
+                           : launch_bwd<128, 4>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0, dc0, db_i2h, db_h2h, B, T, st);
     default: msx_set_error("msx_lstm_bwd: hidden size %d unsupported (32, 64, 128)", H); return MSX_ERR_UNSUPPORTED;
   }
 }

@@ -58,6 +58,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Transpose-reduce: every lane holds v[0..31]; afterwards lane L holds sum over all lanes of v[L] (in v[0]).
+// 31 shuffles instead of 32 x 5; used to fold bias-gradient column sums into row-owner epilogues.
+__device__ __forceinline__ float warp_colsum32(float v[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(MSX_FULL, send, s);
+      v[i] = (up ? v[i + s] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
 // Philox4x32-10 (Salmon et al. 2011), counter-based: (seed, subsequence/offset) -> 4 x u32.
 struct Philox {
   static constexpr uint32_t kA = 0xD2511F53u, kB = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;

@@ -205,18 +205,27 @@ class VAEEngine:
         return self.precision == "tf32" and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
-                   accumulate_dx=False):
-        """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy), dx [M,K] (=|+=) dy w (optionally masked by aux)."""
+                   accumulate_dx=False, dx_colsum=None):
+        """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy) (gb=None: the kernel that produced dy already added it),
+        dx [M,K] (=|+=) dy w (optionally masked by aux).  dx_colsum: bias-gradient buffer of the layer whose
+        pre-activation gradient dx is; returns True when the dgrad epilogue accumulated it (tensor path)."""
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
         if self._use_tc(dy, lddy, x, ldx, gw, K, N, K, M):
             ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk)
-            ops.colsum(dy, lddy, M, N, gb)
+            if gb is not None:
+                ops.colsum(dy, lddy, M, N, gb)
         else:
             ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, colsum=gb)
+        fused = False
         if dx is not None:
-            fn = ops.gemm_tc if self._use_tc(dy, lddy, w, K, dx, lddx, M, K, N) else ops.gemm
-            fn(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
-               accumulate=accumulate_dx)
+            if self._use_tc(dy, lddy, w, K, dx, lddx, M, K, N):
+                fused = dx_colsum is not None and not accumulate_dx
+                ops.gemm_tc(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
+                            accumulate=accumulate_dx, out_colsum=dx_colsum if fused else None)
+            else:
+                ops.gemm(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
+                         accumulate=accumulate_dx)
+        return fused
 
     # ------------------------------------------------------------------ transformer layer
     def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder):
@@ -269,40 +278,41 @@ class VAEEngine:
         if decoder:
             ops.add_ln_bwd(f, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, df, None,
                            self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
-                           seed=self.dropout_seed, site=site0 + 2, fuse_xy=True)
+                           seed=self.dropout_seed, site=site0 + 2, fuse_xy=True, dybias=self._G(prefix + "ff.ff2.bias"))
         else:
             ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, df if p > 0 else None,
                            self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
-                           seed=self.dropout_seed, site=site0 + 2)
+                           seed=self.dropout_seed, site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"))
             if p <= 0:
                 df = dx1
         # ff2: f = h W2^T + b2
         dh = bf.get(tag + "dh", (M, 4 * D), dev)
-        self._dense_bwd(df, D, M, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
-                        self._G(prefix + "ff.ff2.bias"), D, 4 * D, dx=dh, lddx=4 * D, aux=h, ldaux=4 * D,
-                        aux_scale=inv_keep)
+        fused = self._dense_bwd(df, D, M, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
+                                None, D, 4 * D, dx=dh, lddx=4 * D, aux=h, ldaux=4 * D, aux_scale=inv_keep,
+                                dx_colsum=self._G(prefix + "ff.ff1.bias"))
         # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
         self._dense_bwd(dh, 4 * D, M, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
-                        self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D, accumulate_dx=not decoder)
+                        None if fused else self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D,
+                        accumulate_dx=not decoder)
         # ln1(x_in + drop(proj))
         dproj = bf.get(tag + "dproj", (M, D), dev)
         ops.add_ln_bwd(x_in, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dx_in, dproj if p > 0 else None,
                        self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), M, D, drop_p=p,
-                       seed=self.dropout_seed, site=site0)
+                       seed=self.dropout_seed, site=site0, dybias=self._G(prefix + "self_attention.W_proj.bias"))
         if p <= 0:
             dproj = dx_in
         dctx = bf.get(tag + "dctx", (M, D), dev)
         self._dense_bwd(dproj, D, M, ctx, D, self._W(prefix + "self_attention.W_proj.weight"),
-                        self._G(prefix + "self_attention.W_proj.weight"), self._G(prefix + "self_attention.W_proj.bias"),
-                        D, D, dx=dctx, lddx=D)
+                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=D)
         dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
-        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
-        else:
-            ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
+        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv)
+            gbqkv = None
+        else:
+            ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
         self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
 
     # ------------------------------------------------------------------ encoder
@@ -557,11 +567,13 @@ class VAEEngine:
         M, Mo = B * T, B * Td
         logits = c["logits"]
         lse = bf.t[("lse", (Mo,), torch.float32)]
-        ops.ce_bwd(logits, self.ldv, c["labels"], lse, g_ce, B, Td, V, T)       # logits now hold dlogits
+        fuse_db = V <= 512
+        ops.ce_bwd(logits, self.ldv, c["labels"], lse, g_ce, B, Td, V, T,       # logits now hold dlogits
+                   dbias=self._G("decoder.output_layer.bias") if fuse_db else None)
         ddec = bf.get("ddec", (Mo, Hd), dev)
         self._dense_bwd(logits, self.ldv, Mo, c["dec_out"], Hd, self._W("decoder.output_layer.weight"),
-                        self._G("decoder.output_layer.weight"), self._G("decoder.output_layer.bias"), V, Hd,
-                        dx=ddec, lddx=Hd)
+                        self._G("decoder.output_layer.weight"), None if fuse_db else self._G("decoder.output_layer.bias"),
+                        V, Hd, dx=ddec, lddx=Hd)
         dz = bf.get("dz", (B, Z), dev)
         if cfg.dec_type == "lstm":
             gates = bf.t[("dec.gates", (M, 4 * Hd), torch.float32)]
@@ -571,13 +583,12 @@ class VAEEngine:
             tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
             dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
             ops.lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
-                         B, T, Hd)                                                  # gates now hold d(pre-activations)
+                         B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
+                         db_h2h=self._G("decoder.decoder.l0_h2h_bias"))            # gates now hold d(pre-activations)
             dxe = bf.get("dec.dxe", (M, Hd), dev)
             self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
-                            self._G("decoder.decoder.l0_i2h_weight"), self._G("decoder.decoder.l0_i2h_bias"), 4 * Hd, Hd,
-                            dx=dxe, lddx=Hd)
-            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"),
-                            self._G("decoder.decoder.l0_h2h_bias"), 4 * Hd, Hd)
+                            self._G("decoder.decoder.l0_i2h_weight"), None, 4 * Hd, Hd, dx=dxe, lddx=Hd)
+            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"), None, 4 * Hd, Hd)
             ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
             ops.embed_bwd(c["classes"], None, dtv, self._G("decoder.class2hid.weight"), None, None, B, 1, 2 * Hd, 0, 1.0,
                           cfg.num_classes)

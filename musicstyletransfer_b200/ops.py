@@ -25,11 +25,11 @@ def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False
 
 
 def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
-            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1):
+            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None):
     """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
     lib.call("msx_gemm_tc", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
-             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), lib.stream_ptr(), tag=2.0 * M * N * K)
+             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(), tag=2.0 * M * N * K)
 
 
 def gemm_tc_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
@@ -58,8 +58,9 @@ def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh):
     lib.call("msx_attention_tc_fwd", P(qkv), P(mask), P(ctx), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
-def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
-    lib.call("msx_attention_tc_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):
+    lib.call("msx_attention_tc_bwd", P(qkv), P(mask), P(dctx), P(dqkv), P(dbias), _i(B), _i(T), _i(H), _i(dh),
+             lib.stream_ptr())
 
 
 def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
@@ -72,9 +73,9 @@ def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, s
 
 
 def add_ln_bwd(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p=0.0, seed=0, site=0,
-               accumulate_dres=False, fuse_xy=False):
+               accumulate_dres=False, fuse_xy=False, dybias=None):
     lib.call("msx_add_ln_bwd", P(x), P(y), P(gamma), P(mean), P(rstd), P(dout), P(dres), P(dy), P(dgamma), P(dbeta),
-             _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
+             P(dybias), _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
              _i(1 if fuse_xy else 0), lib.stream_ptr())
 
 
@@ -106,8 +107,8 @@ def ce_fwd(logits, ld, labels, ce, lse, metrics, B, T, V, denom, top_k=5):
              _i(top_k), lib.stream_ptr())
 
 
-def ce_bwd(logits, ld, labels, lse, gout, B, T, V, denom):
-    lib.call("msx_ce_bwd", P(logits), _i(ld), P(labels), P(lse), P(gout), _i(B), _i(T), _i(V), _i(denom),
+def ce_bwd(logits, ld, labels, lse, gout, B, T, V, denom, dbias=None):
+    lib.call("msx_ce_bwd", P(logits), _i(ld), P(labels), P(lse), P(gout), _i(B), _i(T), _i(V), _i(denom), P(dbias),
              lib.stream_ptr())
 
 
@@ -129,9 +130,9 @@ def lstm_fwd(gx, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H):
              _i(H), lib.stream_ptr())
 
 
-def lstm_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H):
-    lib.call("msx_lstm_bwd", P(gates), P(w_h2h), P(cs), P(c0), _i(ld0), P(dhs), P(dh0), P(dc0), _i(B), _i(T), _i(H),
-             lib.stream_ptr())
+def lstm_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H, db_i2h=None, db_h2h=None):
+    lib.call("msx_lstm_bwd", P(gates), P(w_h2h), P(cs), P(c0), _i(ld0), P(dhs), P(dh0), P(dc0), P(db_i2h), P(db_h2h),
+             _i(B), _i(T), _i(H), lib.stream_ptr())
 
 
 def adam_step(w, g, m, v, n, state, lr, beta1, beta2, eps, wd, rescale, clip, zero_grad=True):

@@ -67,7 +67,10 @@ def test_attention_backward(B, T, H):
     torch.cuda.synchronize()
     assert float((out.double().cpu() - want).abs().max()) / scale < 1e-4
     out2 = torch.full_like(qd, 5.0)
-    ops.attention_tc_bwd(qd, md, dd, out2, B, T, H, dh)
+    db = torch.zeros(3 * H * dh, device="cuda")
+    ops.attention_tc_bwd(qd, md, dd, out2, B, T, H, dh, dbias=db)
     torch.cuda.synchronize()
     err = float((out2.double().cpu() - want).abs().max()) / scale
     assert err < 5e-3, err
+    wb = want.sum(0)
+    assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4

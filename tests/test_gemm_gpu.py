@@ -119,3 +119,19 @@ def test_wgrad_colsum():
     torch.cuda.synchronize()
     assert float((gw.double().cpu() - dYv.double().t() @ Xv.double()).abs().max()) < 1e-3
     assert float((gb.double().cpu() - dYv.double().sum(0)).abs().max()) < 1e-3
+
+
+def test_tc_epilogue_out_colsum():
+    """dgrad epilogue of the tensor path accumulates the column sums of the gradient it writes (bias gradient)."""
+    from musicstyletransfer_b200 import ops
+    M, N, K = 777, 300, 96
+    Ad, Av = _mk(M, K, K, 21)
+    Bd, Bv = _mk(K, N, 304, 22)
+    aux = torch.randn(M, 304, generator=torch.Generator().manual_seed(23)).cuda()
+    C = torch.zeros((M, 304), device="cuda")
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm_tc(Ad, K, 0, Bd, 304, 0, C, 304, M, N, K, aux=aux, ldaux=304, aux_scale=1.25, out_colsum=cs)
+    torch.cuda.synchronize()
+    want = (_ref(Av, Bv, 0, 0) * (aux[:, :N].cpu() > 0).double() * 1.25).sum(0)
+    assert float((cs.double().cpu() - want).abs().max()) / float(want.abs().max()) < 3e-3
+    assert float((cs.double().cpu() - C[:, :N].double().cpu().sum(0)).abs().max()) < 1e-2
