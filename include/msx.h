@@ -65,6 +65,10 @@ int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, in
  * 1 when msx_gemm_tc accepts the operands (TMA: 16-byte aligned bases, leading dimensions multiple of 4). */
 int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
                           int K);
+/* msx_gemm_tc has two kernels: 128x128 tiles on one CTA, and 256x256 / 256x128 tiles on a CTA pair
+ * (tcgen05 cta_group::2, used when M > 128, N >= 64 and K >= 256).  msx_gemm_tc_set_pair(0) forces the 1-CTA kernel,
+ * (1) re-enables the pair kernel; returns the previous setting.  MSX_GEMM_PAIR=0 in the environment does the same. */
+int msx_gemm_tc_set_pair(int enable);
 
 /* out[n] += sum_m X[m,n]: bias gradient of a Dense layer when the wgrad runs on the tensor path. */
 int msx_colsum(const float* X, int ld, long long M, int N, float* out, void* stream);

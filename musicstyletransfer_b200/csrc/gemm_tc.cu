@@ -8,7 +8,7 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-stage smem ring
 //   warp 1      TMEM allocator + single-thread MMA issuer: 4 x (128 x 128 x 8) tcgen05.mma per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout / aux-mask in the
+//   warps 2-9   epilogue (two per TMEM lane group, half of the tile's columns each): tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout / aux-mask in the
 //               row-owner layout -> 128B-swizzled smem box -> TMA store, or TMA reduce-add (.add.f32) for
 //               accumulate and split-K, so C is never read by the SM and OOB rows/columns are clipped by TMA
 // Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of
@@ -17,6 +17,7 @@
 // dY in dY W) and MN-major (output dim contiguous: W in dY W, dY^T and X in dY^T X) are both fed by TMA;
 // only the shared-memory descriptor and the box geometry differ.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "msx_common.cuh"
 
@@ -26,8 +27,8 @@ constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 B = one swi
 constexpr int kStages = 4;
 constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kTileBytes;
-constexpr int kThreads = 192;
-constexpr int kEpiWarps = 4;
+constexpr int kThreads = 320;                      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane group, each takes half of the columns
 constexpr int kOutBoxBytes = 32 * 128;               // epilogue staging box: 32 rows x 32 fp32
 constexpr int kTmemCols = 256;                      // 2 accumulators x 128 fp32 columns
 
@@ -124,6 +125,81 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float v[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Epilogue for one 32-row x 32-column chunk held in the row-owner layout (lane = row, v[j] = column col0 + j):
+// bias / ReLU / dropout / aux mask / bias-gradient column sums, then a SWIZZLE_128B staging box that the TMA
+// engine stores (or reduce-adds) into C.
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensorMap* tmc, float (&v)[32], int row0,
+                                               int my_row, int col0, int lane, unsigned char* st, int& sbuf,
+                                               int& pending, bool reduce) {
+    // ---- row-owner layout: this lane holds 32 consecutive columns of row my_row
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.drop_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float s4[4];
+        dropout_scale4(p.seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
+        v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
+      }
+    }
+    if (p.aux && my_row < p.M) {
+      const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
+      if (col0 + 32 <= p.N && (p.ldaux & 3) == 0) {
+        float4 a4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(ax) + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j + 0] *= a4[j].x > 0.f ? p.aux_scale : 0.f;
+          v[4 * j + 1] *= a4[j].y > 0.f ? p.aux_scale : 0.f;
+          v[4 * j + 2] *= a4[j].z > 0.f ? p.aux_scale : 0.f;
+          v[4 * j + 3] *= a4[j].w > 0.f ? p.aux_scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < p.N && __ldg(ax + j) > 0.f) ? p.aux_scale : 0.f;
+      }
+    }
+    if (p.out_colsum) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = my_row < p.M ? v[j] : 0.f;
+      const float cs = warp_colsum32(t, lane);
+      if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs);
+    }
+    // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
+    unsigned char* box = st + sbuf * kOutBoxBytes;
+    if (pending >= 2) {                     // the box we are about to overwrite must have been read
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if (reduce)
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmc),
+                     "r"(smem_u32(box)), "r"(col0), "r"(row0)
+                     : "memory");
+      else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmc),
+                     "r"(smem_u32(box)), "r"(col0), "r"(row0)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    sbuf ^= 1;
+    if (pending < 2) ++pending;
 }
 
 template <bool A_MN, bool B_MN>
@@ -227,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int ew = warp - 2;                 // staging slot
-    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int lg = warp & 3;                 // TMEM lane group this warp may access (warps w and w+4 share one)
+    const int chalf = ew >> 2;               // which half of the BN columns this warp drains
     unsigned char* st = stage_out + ew * 2 * kOutBoxBytes;
     const bool reduce = p.accumulate || p.splitk > 1;
     int local = 0, sbuf = 0, pending = 0;
@@ -240,78 +317,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int row0 = mt * BM + lg * 32;
       const int my_row = row0 + lane;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = chalf * (BN / 64); ch < (chalf + 1) * (BN / 64); ++ch) {
         const int col0 = nt * BN + ch * 32;
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          // ---- row-owner layout: this lane holds 32 consecutive columns of row my_row
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.drop_p > 0.f) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float s4[4];
-              dropout_scale4(p.seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
-              v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
-            }
-          }
-          if (p.aux && my_row < p.M) {
-            const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
-            if (col0 + 32 <= p.N && (p.ldaux & 3) == 0) {
-              float4 a4[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(ax) + j);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j + 0] *= a4[j].x > 0.f ? p.aux_scale : 0.f;
-                v[4 * j + 1] *= a4[j].y > 0.f ? p.aux_scale : 0.f;
-                v[4 * j + 2] *= a4[j].z > 0.f ? p.aux_scale : 0.f;
-                v[4 * j + 3] *= a4[j].w > 0.f ? p.aux_scale : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < p.N && __ldg(ax + j) > 0.f) ? p.aux_scale : 0.f;
-            }
-          }
-          if (p.out_colsum) {
-            float t[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = my_row < p.M ? v[j] : 0.f;
-            const float cs = warp_colsum32(t, lane);
-            if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs);
-          }
-          // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
-          unsigned char* box = st + sbuf * kOutBoxBytes;
-          if (pending >= 2) {                     // the box we are about to overwrite must have been read
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (reduce)
-              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                           "r"(smem_u32(box)), "r"(col0), "r"(row0)
-                           : "memory");
-            else
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                           "r"(smem_u32(box)), "r"(col0), "r"(row0)
-                           : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          sbuf ^= 1;
-          if (pending < 2) ++pending;
+          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -323,6 +334,220 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN2 output tile.  Each CTA stages
+// 128 rows of A and BN2/2 rows of B per k-block, the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (UMMA M = 256) which reads both CTAs' shared memory, and each CTA's TMEM receives
+// its own 128 x BN2 half of the accumulator.  Per output element the operand traffic L2 -> SM is half of the
+// 1-CTA 128 x 128 kernel's, which is what bounds these K <= 1024 fp32-I/O GEMMs (the chip-wide L2 -> SM cap
+// is ~2x HBM bandwidth and the 1-CTA kernel re-reads a 128 x K weight panel for every 128 x 128 tile).
+//   full[s]        leader only; count 1 (leader's arrive.expect_tx for BOTH CTAs' bytes); the peer's TMA
+//                  completes its bytes on the leader's barrier (cp.async.bulk.tensor .cta_group::2)
+//   empty[s]       both CTAs; tcgen05.commit .multicast::cluster arrives on both
+//   tmem_full[b]   both CTAs; multicast commit
+//   tmem_empty[b]  leader only; count 2 x epilogue warps, the peer's warps arrive remotely
+// ================================================================================================
+template <int BN2>
+struct PairCfg {
+  static constexpr int kBRows = BN2 / 2;
+  static constexpr int kATile = BM * BK * 4;
+  static constexpr int kBTile = kBRows * BK * 4;
+  static constexpr int kStage = kATile + kBTile;
+  static constexpr int kStages2 = BN2 == 256 ? 5 : 6;
+  static constexpr int kTmem = 2 * BN2;
+  static constexpr int kChunks = BN2 / 32;            // 32-column epilogue chunks per tile
+};
+constexpr int kMaxStages2 = 6;
+
+struct __align__(8) Barriers2 {
+  unsigned long long full[kMaxStages2], empty[kMaxStages2], tmem_full[2], tmem_empty[2];
+  unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, unsigned bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                               unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+
+template <int BN2, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  using Cfg = PairCfg<BN2>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* stage_out = ring + Cfg::kStages2 * Cfg::kStage;                  // [kEpiWarps][2][32 rows][128 B]
+  Barriers2* bars = reinterpret_cast<Barriers2*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int items = p.m_tiles * p.n_tiles * p.splitk;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages2; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(Cfg::kTmem)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                       // barriers of both CTAs initialised, TMEM allocated in both
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int it = pair; it < items; it += npairs) {
+        const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = mt * (2 * BM) + (int)rank * BM;               // this CTA's 128 rows of A
+        const int n0 = nt * BN2 + (int)rank * Cfg::kBRows;           // this CTA's BN2/2 rows of B
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          unsigned char* sa = ring + stage * Cfg::kStage;
+          unsigned char* sb = sa + Cfg::kATile;
+          if (leader) mbar_expect_tx(&bars->full[stage], 2 * Cfg::kStage);
+          const unsigned fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);                           // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int s = 0; s < BM / 32; ++s)                                       // 4 slabs {32 m, 32 k}
+              tma_load_2d_pair(sa + s * (BK * 128), &tmA, fb, m0 + s * 32, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, fb, kb * BK, n0);                           // box {32 k, BN2/2 rows}
+          } else {
+#pragma unroll
+            for (int s = 0; s < Cfg::kBRows / 32; ++s)
+              tma_load_2d_pair(sb + s * (BK * 128), &tmB, fb, n0 + s * 32, kb * BK);
+          }
+          if (++stage == Cfg::kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (lane == 0 && leader) {
+      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24 with M = 256 across the pair
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((unsigned)(BN2 >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
+      int stage = 0;
+      unsigned phase = 0;
+      int local = 0;
+      for (int it = pair; it < items; it += npairs, ++local) {
+        const int ks = it / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int buf = local & 1;
+        const unsigned use = (unsigned)(local >> 1);
+        mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned tmem_d = tmem_base + buf * BN2;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned sa = smem_u32(ring + stage * Cfg::kStage), sb = sa + Cfg::kATile;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const unsigned long long ad = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
+            const unsigned long long bd = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&bars->empty[stage]);            // frees this stage in BOTH CTAs
+          if (++stage == Cfg::kStages2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&bars->tmem_full[buf]);            // accumulator halves complete in both CTAs
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9, both CTAs) ================================
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int chalf = ew >> 2;
+    unsigned char* st = stage_out + ew * 2 * kOutBoxBytes;
+    const bool reduce = p.accumulate || p.splitk > 1;
+    int local = 0, sbuf = 0, pending = 0;
+    for (int it = pair; it < items; it += npairs, ++local) {
+      const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles;
+      const int buf = local & 1;
+      const unsigned use = (unsigned)(local >> 1);
+      mbar_wait(&bars->tmem_full[buf], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row0 = mt * (2 * BM) + (int)rank * BM + lg * 32;
+      const int my_row = row0 + lane;
+#pragma unroll 1
+      for (int ch = chalf * (Cfg::kChunks / 2); ch < (chalf + 1) * (Cfg::kChunks / 2); ++ch) {
+        const int col0 = nt * BN2 + ch * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN2 + ch * 32, v);
+        if (col0 < p.N && row0 < p.M) {          // warp-uniform
+          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                       // no CTA leaves (or frees TMEM) while its pair may still touch it
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmem) : "memory");
   }
 }
 
@@ -374,6 +599,35 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   return MSX_OK;
 }
 
+template <int BN2>
+constexpr size_t pair_smem_bytes() {
+  return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers2);
+}
+
+template <int BN2, bool A_MN, bool B_MN>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = pair_smem_bytes<BN2>();
+  static_assert(smem <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = p.m_tiles * p.n_tiles * p.splitk;
+  const int max_pairs = msx_num_sms() / 2;
+  const int pairs = items < max_pairs ? items : max_pairs;
+  gemm_tc2_kernel<BN2, A_MN, B_MN><<<2 * pairs, kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+// 2-CTA path switch: MSX_GEMM_PAIR=0 in the environment or msx_gemm_tc_set_pair(0) forces the 1-CTA kernel
+// (A/B comparisons, bisecting); default on.
+int g_pair_mode = -1;
+bool pair_enabled() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("MSX_GEMM_PAIR");
+    g_pair_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pair_mode == 1;
+}
+
 }  // namespace
 
 // Returns 1 when msx_gemm_tc can take this problem (TMA needs 16-byte aligned bases and row pitches).
@@ -382,6 +636,12 @@ extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, in
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return 0;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || (lda & 3) || (ldb & 3) || (ldc & 3)) return 0;
   return 1;
+}
+
+extern "C" int msx_gemm_tc_set_pair(int enable) {
+  const int prev = pair_enabled() ? 1 : 0;
+  g_pair_mode = enable ? 1 : 0;
+  return prev;
 }
 
 extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
@@ -406,6 +666,43 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   CUtensorMap ta, tb, tc;
   int rc = make_map(&tc, C, M, N, ldc, 32, 32, false, false);     // epilogue box: 32 rows x 32 columns, SWIZZLE_128B
   if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
+  // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
+  if (pair_enabled() && M > BM && N >= 64 && K >= 256) {
+    // ---- 2-CTA path: 256 x 256 (N > 128) or 256 x 128 pair tiles
+    const int bn2 = N > 128 ? 256 : 128;
+    if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, bn2 / 2, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
+    if (rc) return rc;
+    TcParams p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
+    p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+    p.out_colsum = out_colsum;
+    p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2); p.kb_total = msx_ceil_div(K, BK);
+    if (splitk > 1) {                         // re-derive the split for pair tiles: about two waves of pairs
+      const int tiles = p.m_tiles * p.n_tiles, pairs = msx_num_sms() / 2;
+      splitk = (2 * pairs) / tiles;
+      if (splitk < 2) splitk = 2;
+    }
+    if (splitk > p.kb_total) splitk = p.kb_total;
+    p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
+    p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
+    if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
+    if (bn2 == 256) {
+      if (!a_mn && !b_mn) return launch_pair<256, false, false>(ta, tb, tc, p, st);
+      if (!a_mn && b_mn) return launch_pair<256, false, true>(ta, tb, tc, p, st);
+      if (a_mn && b_mn) return launch_pair<256, true, true>(ta, tb, tc, p, st);
+    } else {
+      if (!a_mn && !b_mn) return launch_pair<128, false, false>(ta, tb, tc, p, st);
+      if (!a_mn && b_mn) return launch_pair<128, false, true>(ta, tb, tc, p, st);
+      if (a_mn && b_mn) return launch_pair<128, true, true>(ta, tb, tc, p, st);
+    }
+    msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
+    return MSX_ERR_UNSUPPORTED;
+  }
   if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
   if (rc) return rc;
   if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, BN, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
@@ -420,7 +717,6 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
   p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
   if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
-  cudaStream_t st = (cudaStream_t)stream;
   if (!a_mn && !b_mn) return launch<false, false>(ta, tb, tc, p, st);
   if (!a_mn && b_mn) return launch<false, true>(ta, tb, tc, p, st);
   if (a_mn && b_mn) return launch<true, true>(ta, tb, tc, p, st);

@@ -36,6 +36,11 @@ def gemm_tc_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
     return bool(lib.load().msx_gemm_tc_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
 
 
+def gemm_tc_set_pair(enable):
+    """Selects the 2-CTA (cta_group::2) tensor GEMM kernel (default) or forces the 1-CTA one; returns the previous setting."""
+    return int(lib.load().msx_gemm_tc_set_pair(_i(1 if enable else 0)))
+
+
 def colsum(X, ld, M, N, out):
     lib.call("msx_colsum", P(X), _i(ld), _ll(M), _i(N), P(out), lib.stream_ptr())
 

@@ -24,10 +24,27 @@ def _mk(rows, cols, ld, seed):
 CASES = [
     # (M, N, K) as the math sees them
     (300, 200, 96), (128, 128, 32), (2080, 768, 256), (65, 293, 128), (2080, 256, 1024), (7, 5, 8), (513, 300, 40),
+    (1000, 128, 296), (768, 256, 5000), (4160, 1024, 256),
 ]
 
 
-@pytest.mark.parametrize("impl", ["f32", "tc"])
+def _impl_fn(impl):
+    """f32 = exact FFMA kernel; tc1 = tcgen05 1-CTA 128x128 tiles; tc2 = tcgen05 CTA-pair (cta_group::2) tiles."""
+    from musicstyletransfer_b200 import ops
+    if impl == "f32":
+        return ops.gemm
+    ops.gemm_tc_set_pair(impl == "tc2")
+    return ops.gemm_tc
+
+
+@pytest.fixture(autouse=True)
+def _restore_pair_mode():
+    yield
+    from musicstyletransfer_b200 import ops
+    ops.gemm_tc_set_pair(True)
+
+
+@pytest.mark.parametrize("impl", ["f32", "tc1", "tc2"])
 @pytest.mark.parametrize("mode", ["fwd", "dgrad", "wgrad"])
 @pytest.mark.parametrize("M,N,K", CASES)
 def test_gemm_modes(impl, mode, M, N, K):
@@ -48,13 +65,13 @@ def test_gemm_modes(impl, mode, M, N, K):
     ldc = pad(N)
     want = _ref(Av, Bv, transA, transB)
     C = torch.full((M, ldc), 7.0, device="cuda")
-    fn = ops.gemm if impl == "f32" else ops.gemm_tc
+    fn = _impl_fn(impl)
     fn(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C, ldc, M, N, K)
     torch.cuda.synchronize()
     got = C[:, :N].double().cpu()
     scale = float(want.abs().max()) + 1e-9
     err = float((got - want).abs().max()) / scale
-    assert err < (2e-6 if impl == "f32" else 2e-3), (impl, mode, M, N, K, err)
+    assert err < ((2e-6 if K <= 1024 else 6e-6) if impl == "f32" else 2e-3), (impl, mode, M, N, K, err)
     # padding columns untouched; the TMA-store epilogue of the tensor path writes whole 16-byte chunks, so it may
     # clobber columns N .. roundup4(N)-1 (documented in include/msx.h) but nothing beyond
     first_safe = N if impl == "f32" else (N + 3) // 4 * 4
@@ -64,13 +81,13 @@ def test_gemm_modes(impl, mode, M, N, K):
     fn(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C2, ldc, M, N, K, splitk=3)
     torch.cuda.synchronize()
     err = float((C2[:, :N].double().cpu() - want).abs().max()) / scale
-    assert err < (4e-6 if impl == "f32" else 2e-3), ("splitk", impl, mode, err)
+    assert err < ((4e-6 if K <= 1024 else 8e-6) if impl == "f32" else 2e-3), ("splitk", impl, mode, err)
 
 
-@pytest.mark.parametrize("impl", ["f32", "tc"])
+@pytest.mark.parametrize("impl", ["f32", "tc1", "tc2"])
 def test_gemm_epilogues(impl):
     from musicstyletransfer_b200 import ops
-    fn = ops.gemm if impl == "f32" else ops.gemm_tc
+    fn = _impl_fn(impl)
     tol = 2e-6 if impl == "f32" else 2e-3
     M, N, K = 333, 293, 128
     ldc = 296
@@ -121,9 +138,11 @@ def test_wgrad_colsum():
     assert float((gb.double().cpu() - dYv.double().sum(0)).abs().max()) < 1e-3
 
 
-def test_tc_epilogue_out_colsum():
+@pytest.mark.parametrize("impl", ["tc1", "tc2"])
+def test_tc_epilogue_out_colsum(impl):
     """dgrad epilogue of the tensor path accumulates the column sums of the gradient it writes (bias gradient)."""
     from musicstyletransfer_b200 import ops
+    _impl_fn(impl)
     M, N, K = 777, 300, 96
     Ad, Av = _mk(M, K, K, 21)
     Bd, Bv = _mk(K, N, 304, 22)
