@@ -79,6 +79,43 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float v[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld split into issue + wait so that several loads are in flight; the wait names the destination registers
+// as read-write operands so that the compiler cannot move their consumers above it.
+__device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float* v) {       // caller issues tcgen05.wait::st
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+// A operand from TMEM (lanes = M rows, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
+                                             unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float to_tf32(float x) {
   unsigned r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -93,36 +130,56 @@ struct AttnTcParams {
   const float* mask;   // [B*T]
   float* ctx;          // [B*T, H*32]
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
-  unsigned tmem_cols;
+  int items;           // B * H
+  int group_bytes;     // shared memory of one pipeline group
   float inv_scale;
 };
 
-template <int kTmemCols>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void group_sync(int g) {       // named barrier of one 128-thread pipeline group
+  asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+}
+
+// Forward.  Persistent CTAs (one per SM), each running G independent 128-thread pipeline groups; a group walks its
+// (batch, head) items with its own TMA ring, TMEM slice and mbarriers, so the latency chain of one item
+// (TMA -> MMA 1 -> softmax -> MMA 2 -> store) is hidden by the other groups and by the prefetch of the next item:
+//   K, Q of item n+1 are fetched as soon as MMA 1 of item n has retired, V is double-buffered.
+// NCH = TQ / 16: the key row's scores are held in registers (one tcgen05.ld pass, one exp per score).
+template <int NCH, int G>
+__global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  constexpr int TQ = NCH * 16;
+  constexpr int kTmemStride = (TQ + DH + 31) / 32 * 32;    // per group: O [0,32) | S [32, 32+TQ)
+  constexpr int kTmemCols = G * kTmemStride <= 128 ? 128 : G * kTmemStride <= 256 ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sK = base;                              // [128 rows][128 B]  K-major, SWIZZLE_128B
-  unsigned char* sQ = sK + 128 * 128;                    // [TQ rows][128 B]   K-major, SWIZZLE_128B
-  unsigned char* sV = sQ + ((p.TQ * 128 + 1023) & ~1023);  // [TK rows][128 B] MN-major (d contiguous), SW128_32B
-  unsigned char* sP = sV + ((p.TK * 128 + 1023) & ~1023);  // 4 slabs x [TK rows][128 B] MN-major (q contiguous)
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sP + 4 * p.TK * 128);
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
+  __shared__ unsigned long long bars_all[G][5];            // kq, v0, v1, s_full, o_full
+  __shared__ unsigned tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int D = p.H * DH;
-  const int T = p.T, TQ = p.TQ, TK = p.TK;
+  const int g = warp >> 2, gt = tid & 127;                 // pipeline group, thread within the group (= key row / query row)
+  const int T = p.T, TK = p.TK, D = p.H * DH;
+  const int slab = TK * 128;                               // bytes of a [TK rows][128 B] tile
+  unsigned char* sK = base + (size_t)g * p.group_bytes;    // [TK rows][128 B] K-major SW128; MMA 1 addresses 128 rows, the
+                                                           // rows beyond TK alias the tiles behind it (their S rows are unused)
+  unsigned char* sQ = sK + slab;                           // [TQ rows][128 B] K-major SW128
+  unsigned char* sV = sQ + TQ * 128;                       // 2 x [TK rows][128 B] MN-major (d contiguous), SW128_32B
+  unsigned char* sP = sV + 2 * slab;                       // ceil(TQ/32) slabs x [TK rows][128 B] MN-major (q contiguous)
+  unsigned long long* bar_kq = &bars_all[g][0];
+  unsigned long long* bar_v = &bars_all[g][1];
+  unsigned long long* bar_s = &bars_all[g][3];
+  unsigned long long* bar_o = &bars_all[g][4];
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+    for (int i = 0; i < G; ++i)
+      for (int j = 0; j < 5; ++j) mbar_init(&bars_all[i][j], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -130,96 +187,117 @@ __global__ void __launch_bounds__(128)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem = *tmem_slot;
-  const unsigned tmem_O = tmem, tmem_S = tmem + DH;      // O: columns [0,32), S: columns [32, 32+TQ)
+  const unsigned tmem_O = tmem_slot + g * kTmemStride, tmem_S = tmem_O + DH;
+  const unsigned lane_off = (unsigned)((warp & 3) * 32) << 16;
 
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], (unsigned)((128 + TQ + TK) * 128));
-    tma_load_2d(sK, &tmK, &bars[0], h * DH, b * T);
-    tma_load_2d(sQ, &tmQ, &bars[0], D + h * DH, b * T);
-    tma_load_2d(sV, &tmV, &bars[0], 2 * D + h * DH, b * T);
-    mbar_wait(&bars[0], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // MMA 1: S[128 x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-#pragma unroll
-    for (int k = 0; k < DH / 8; ++k)
-      umma_tf32(tmem_S, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQ) + k * 32, 16, 1024, 2),
-                idesc, k > 0 ? 1u : 0u);
-    umma_commit(&bars[1]);
+  const int first = blockIdx.x * G + g, stride = gridDim.x * G;
+  const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                          ((unsigned)(128 >> 4) << 24);
+
+  if (gt == 0 && first < p.items) {                        // prologue: loads of the group's first item
+    const int b = first / p.H, h = first % p.H;
+    mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
+    tma_load_2d(sK, &tmK, bar_kq, h * DH, b * T);
+    tma_load_2d(sQ, &tmQ, bar_kq, D + h * DH, b * T);
+    mbar_expect_tx(&bar_v[0], (unsigned)slab);
+    tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * DH, b * T);
   }
-  // every thread: key row k = tid
-  const int k = tid;
-  const float rowmask = (k < T && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
-  mbar_wait(&bars[1], 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  __syncwarp();
-  const unsigned lane_addr = tmem_S + ((unsigned)(warp * 32) << 16);
-  {
-    // tcgen05.ld is warp-collective: every lane runs the same three passes over the TMEM columns of its key
-    // row; only the arithmetic is predicated (rows k >= T hold a neighbouring sequence or zeros).
-    const bool valid = k < T;
-    float mx = -INFINITY;
-    for (int c = 0; c < TQ; c += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + c, v);
+  int n = 0;
+  for (int item = first; item < p.items; item += stride, ++n) {
+    const int b = item / p.H, h = item % p.H;
+    const int nxt = item + stride;
+    const unsigned par = (unsigned)(n & 1);
+    if (gt == 0) {
+      mbar_wait(bar_kq, par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (valid && c + j < T) mx = fmaxf(mx, v[j] * p.inv_scale + rowmask);
-    }
-    float sum = 0.f;
-    for (int c = 0; c < TQ; c += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + c, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (valid && c + j < T) sum += expf(v[j] * p.inv_scale + rowmask - mx);
-    }
-    const float inv = valid ? 1.f / sum : 0.f;
-    for (int c = 0; c < TQ; c += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + c, v);
-      if (k < TK) {      // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = (valid && c + j < T) ? to_tf32(expf(v[j] * p.inv_scale + rowmask - mx) * inv) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(sP + mn_major_off(c + j, k, TK)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int k = 0; k < DH / 8; ++k)
+        umma_tf32(tmem_S, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQ) + k * 32, 16, 1024, 2),
+                  idesc1, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+      if (nxt < p.items) {                                 // V of the next item into the other V buffer (free since o_full(n-1))
+        const int b2 = nxt / p.H, h2 = nxt % p.H;
+        mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
+        tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * DH, b2 * T);
       }
     }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
+    const int k = gt;                                      // this thread's key row
+    const bool valid = k < T;
+    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
+    __syncwarp();
+    mbar_wait(bar_s, par);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // MMA 2: O[128 queries x 32] = P^T[128 x TK] * V[TK x 32]; A MN-major (queries contiguous), B MN-major (d contiguous)
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
-                           ((unsigned)(128 >> 4) << 24);
-    for (int j = 0; j < TK / 8; ++j)
-      umma_tf32(tmem_O, make_desc(smem_u32(sP) + j * 1024, TK * 128, 512, 1),
-                make_desc(smem_u32(sV) + j * 1024, TK * 128, 512, 1), idesc, j > 0 ? 1u : 0u);
-    umma_commit(&bars[2]);
-  }
-  __syncwarp();
-  mbar_wait(&bars[2], 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  {
-    const int q = tid;
-    float o[32];
-    tmem_ld16(tmem_O + ((unsigned)(warp * 32) << 16), o);
-    tmem_ld16(tmem_O + ((unsigned)(warp * 32) << 16) + 16, o + 16);
-    if (q < T) {
-      float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)b * T + q) * D + h * DH);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    if (gt == 0 && nxt < p.items) {                        // K, Q tiles are free once MMA 1 has retired
+      const int b2 = nxt / p.H, h2 = nxt % p.H;
+      mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
+      tma_load_2d(sK, &tmK, bar_kq, h2 * DH, b2 * T);
+      tma_load_2d(sQ, &tmQ, bar_kq, D + h2 * DH, b2 * T);
     }
+    __syncwarp();
+    {
+      // the key row's TQ scores live in registers: softmax over the QUERY axis is thread-local
+      float sc[TQ];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tmem_S + lane_off + c * 16, sc + c * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_wait(sc + c * 16);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        sc[j] = sc[j] * p.inv_scale + rowmask;
+        if (j < T) mx = fmaxf(mx, sc[j]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        sc[j] = (valid && j < T) ? __expf(sc[j] - mx) : 0.f;
+        sum += sc[j];
+      }
+      const float inv = valid ? 1.f / sum : 0.f;
+      if (k < TK) {                                        // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
+#pragma unroll
+        for (int j = 0; j < TQ; j += 4)
+          *reinterpret_cast<float4*>(sP + mn_major_off(j, k, TK)) =
+              make_float4(to_tf32(sc[j] * inv), to_tf32(sc[j + 1] * inv), to_tf32(sc[j + 2] * inv), to_tf32(sc[j + 3] * inv));
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(g);
+    if (gt == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(&bar_v[n & 1], (unsigned)((n >> 1) & 1));
+      // MMA 2: O[128 queries x 32] = P^T[128 x TK] * V[TK x 32]; A MN-major (queries contiguous), B MN-major (d contiguous)
+      const unsigned sv = smem_u32(sV + (n & 1) * slab);
+      for (int j = 0; j < TK / 8; ++j)
+        umma_tf32(tmem_O, make_desc(smem_u32(sP) + j * 1024, slab, 512, 1), make_desc(sv + j * 1024, slab, 512, 1), idesc2,
+                  j > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, par);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      const int q = gt;
+      float o[32];
+      tmem_ld16_issue(tmem_O + lane_off, o);
+      tmem_ld16_issue(tmem_O + lane_off + 16, o + 16);
+      tmem_ld16_wait(o);
+      tmem_ld16_wait(o + 16);
+      if (q < T) {
+        float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)b * T + q) * D + h * DH);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -423,6 +501,235 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------------------------ backward, pipelined (T <= 80)
+// Persistent CTAs with G = 2 independent 128-thread pipeline groups (see the forward kernel).  Differences from the
+// one-shot kernel above:
+//   * S and dP rows are held in registers (one TMEM pass, one exp per score);
+//   * P and dS go back into TMEM (tcgen05.st, in place of S and dP) and feed dV = P dO and dK = dS Q as TMEM A operands
+//     (lanes = keys, columns = queries is exactly the layout they were computed in), so only dS^T for dQ = dS^T K is
+//     staged through shared memory, and all three output MMAs are issued in one batch;
+//   * the K-major tiles of the first two MMAs are double-buffered and prefetched one item ahead; the dS^T staging
+//     tile aliases the current stage once its MMAs have retired;
+//   * the bias-gradient column sums accumulate in registers across the items of a group (flushed when the head changes).
+template <int NCH>
+__global__ void __launch_bounds__(256, 1)
+    attn_tc_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmQk,
+                            const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
+                            const __grid_constant__ CUtensorMap tmQKVm, const AttnTcBwdParams p, const int items,
+                            const int group_bytes) {
+  constexpr int G = 2;
+  constexpr int TQ = NCH * 16;
+  constexpr int kTmemStride = 256;                         // dV | dK | dQ | S/P [TQ] | dP/dS [TQ]
+  static_assert(96 + 2 * TQ <= kTmemStride, "TMEM budget");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ unsigned long long bars_all[G][5];            // a0, a1, b, mma_a, mma_b
+  __shared__ float red[G][3 * 128];
+  __shared__ unsigned tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = warp >> 2, gt = tid & 127;
+  const int T = p.T, TK = p.TK, D = p.H * DH;
+  const int slab = TK * 128;
+  const int stage_bytes = 2 * slab + 2 * TQ * 128;         // Kk | Vk | Qk | dOk (K-major, SW128)
+  unsigned char* gbase = base + (size_t)g * group_bytes;
+  unsigned char* sBm = gbase + 2 * stage_bytes;            // dOm | Qm | Km (MN-major, SW128_32B), TK rows each
+  unsigned long long* bar_a = &bars_all[g][0];
+  unsigned long long* bar_b = &bars_all[g][2];
+  unsigned long long* bar_ma = &bars_all[g][3];
+  unsigned long long* bar_mb = &bars_all[g][4];
+
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i)
+      for (int j = 0; j < 5; ++j) mbar_init(&bars_all[i][j], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDOk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDOm) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKVm) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(G * kTmemStride)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = tmem_slot + g * kTmemStride;
+  const unsigned tm_dV = tmem, tm_dK = tmem + 32, tm_dQ = tmem + 64, tm_S = tmem + 96, tm_dP = tmem + 96 + TQ;
+  const unsigned lane_off = (unsigned)((warp & 3) * 32) << 16;
+  const unsigned idesc_kk = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  const unsigned idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                            ((unsigned)(128 >> 4) << 24);   // A from TMEM (K-major), B MN-major
+  const unsigned idesc_mm = idesc_ts | (1u << 15);          // A MN-major from shared memory, B MN-major
+
+  const int first = blockIdx.x * G + g, stride = gridDim.x * G;
+
+  auto load_a = [&](int item, int stage) {                  // K-major tiles of MMA S and MMA dP
+    const int b = item / p.H, h = item % p.H;
+    unsigned char* st = gbase + stage * stage_bytes;
+    mbar_expect_tx(&bar_a[stage], (unsigned)stage_bytes);
+    tma_load_2d(st, &tmKk, &bar_a[stage], h * DH, b * T);
+    tma_load_2d(st + slab, &tmKk, &bar_a[stage], 2 * D + h * DH, b * T);
+    tma_load_2d(st + 2 * slab, &tmQk, &bar_a[stage], D + h * DH, b * T);
+    tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * DH, b * T);
+  };
+
+  float acc_b[3] = {0.f, 0.f, 0.f};                         // lane c: column c of dK / dQ / dV summed over this warp's rows
+  int acc_h = -1;
+  auto flush_bias = [&]() {                                 // group-uniform
+    if (!p.dbias || acc_h < 0) return;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) red[g][m * 128 + (warp & 3) * 32 + lane] = acc_b[m];
+    group_sync(g);
+    if (gt < 96) {
+      const int m = gt >> 5, c = gt & 31;
+      atomicAdd(p.dbias + m * D + acc_h * DH + c,
+                red[g][m * 128 + c] + red[g][m * 128 + 32 + c] + red[g][m * 128 + 64 + c] + red[g][m * 128 + 96 + c]);
+    }
+    group_sync(g);
+    acc_b[0] = acc_b[1] = acc_b[2] = 0.f;
+  };
+
+  if (gt == 0 && first < items) load_a(first, 0);
+  int n = 0;
+  for (int item = first; item < items; item += stride, ++n) {
+    const int b = item / p.H, h = item % p.H;
+    const int nxt = item + stride;
+    const unsigned par = (unsigned)(n & 1);
+    const int stg = n & 1;
+    unsigned char* sA = gbase + stg * stage_bytes;
+    unsigned char* sY = sA;                                 // dS^T (q contiguous) aliases the stage after MMA S / dP retired
+    if (p.dbias && h != acc_h) {
+      flush_bias();
+      acc_h = h;
+    }
+    if (gt == 0) {
+      // MN-major tiles of the output MMAs (free: the previous item's output MMAs have retired)
+      mbar_expect_tx(bar_b, (unsigned)(3 * slab));
+      tma_load_2d(sBm, &tmDOm, bar_b, h * DH, b * T);
+      tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * DH, b * T);
+      tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * DH, b * T);
+      if (nxt < items) load_a(nxt, stg ^ 1);                // the other stage held item n-1 (its MMAs and dS^T are consumed)
+      mbar_wait(&bar_a[stg], (unsigned)((n >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned kk = smem_u32(sA), vk = kk + slab, qk = kk + 2 * slab, dok = qk + TQ * 128;
+#pragma unroll
+      for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
+        umma_tf32(tm_S, make_desc(kk + k * 32, 16, 1024, 2), make_desc(qk + k * 32, 16, 1024, 2), idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < DH / 8; ++k)       // dP = V dO^T
+        umma_tf32(tm_dP, make_desc(vk + k * 32, 16, 1024, 2), make_desc(dok + k * 32, 16, 1024, 2), idesc_kk, k > 0 ? 1u : 0u);
+      umma_commit(bar_ma);
+    }
+    const int k = gt;
+    const bool valid = k < T;
+    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
+    __syncwarp();
+    mbar_wait(bar_ma, par);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float sc[TQ], gp[TQ];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tm_S + lane_off + c * 16, sc + c * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tm_dP + lane_off + c * 16, gp + c * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_wait(sc + c * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld16_wait(gp + c * 16);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        sc[j] = sc[j] * p.inv_scale + rowmask;
+        if (j < T) mx = fmaxf(mx, sc[j]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        sc[j] = (valid && j < T) ? __expf(sc[j] - mx) : 0.f;
+        sum += sc[j];
+      }
+      const float inv = valid ? 1.f / sum : 0.f;
+      float delta = 0.f;
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        sc[j] *= inv;                                       // P
+        delta = fmaf(sc[j], gp[j], delta);
+      }
+#pragma unroll
+      for (int j = 0; j < TQ; ++j) {
+        gp[j] = to_tf32(sc[j] * (gp[j] - delta) * p.inv_scale);   // dS
+        sc[j] = to_tf32(sc[j]);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_st16(tm_S + lane_off + c * 16, sc + c * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_st16(tm_dP + lane_off + c * 16, gp + c * 16);
+      if (k < TK) {
+#pragma unroll
+        for (int j = 0; j < TQ; j += 4)
+          *reinterpret_cast<float4*>(sY + mn_major_off(j, k, TK)) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(g);
+    if (gt == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(bar_b, par);
+      const unsigned dom = smem_u32(sBm), qm = dom + slab, km = dom + 2 * slab;
+      for (int j = 0; j < TK / 8; ++j)       // dV[keys x 32] = P[keys x q] dO[q x 32]
+        umma_tf32_ts(tm_dV, tm_S + j * 8, make_desc(dom + j * 1024, slab, 512, 1), idesc_ts, j > 0 ? 1u : 0u);
+      for (int j = 0; j < TK / 8; ++j)       // dK[keys x 32] = dS[keys x q] Q[q x 32]
+        umma_tf32_ts(tm_dK, tm_dP + j * 8, make_desc(qm + j * 1024, slab, 512, 1), idesc_ts, j > 0 ? 1u : 0u);
+      for (int j = 0; j < TK / 8; ++j)       // dQ[queries x 32] = dS^T[q x keys] K[keys x 32]
+        umma_tf32(tm_dQ, make_desc(smem_u32(sY) + j * 1024, slab, 512, 1), make_desc(km + j * 1024, slab, 512, 1), idesc_mm,
+                  j > 0 ? 1u : 0u);
+      umma_commit(bar_mb);
+    }
+    __syncwarp();
+    mbar_wait(bar_mb, par);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
+      float* rowp = p.dqkv + ((size_t)b * T + gt) * 3 * D + h * DH;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        float o[32];
+        const unsigned src = m == 0 ? tm_dK : m == 1 ? tm_dQ : tm_dV;
+        tmem_ld16_issue(src + lane_off, o);
+        tmem_ld16_issue(src + lane_off + 16, o + 16);
+        tmem_ld16_wait(o);
+        tmem_ld16_wait(o + 16);
+        if (gt < T) {
+          float4* dst = reinterpret_cast<float4*>(rowp + m * D);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        if (p.dbias) {
+          if (gt >= T) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = 0.f;
+          }
+          acc_b[m] += warp_colsum32(o, lane);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  flush_bias();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(G * kTmemStride) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -458,6 +765,21 @@ extern "C" int msx_attention_tc_supported(const float* qkv, int T, int dh) {
   return (qkv && dh == 32 && T >= 1 && T <= 128 && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
 }
 
+namespace {
+template <int NCH, int G>
+int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& tv, AttnTcParams p, cudaStream_t st) {
+  // the last group's MMA descriptors address 128 K rows / 4 P slabs: keep the tail inside the allocation
+  const size_t smem = 1024 + (size_t)G * p.group_bytes + 16 * 1024;
+  MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_fwd: shared memory budget exceeded (T=%d)", p.T);
+  MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int want = (p.items + G - 1) / G;
+  const int grid = want < msx_num_sms() ? want : msx_num_sms();
+  attn_tc_fwd_kernel<NCH, G><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+}  // namespace
+
 extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
                                     void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
@@ -468,27 +790,27 @@ extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* 
   p.mask = mask; p.ctx = ctx; p.T = T; p.H = H;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
+  p.items = B * H;
   p.inv_scale = 1.f / sqrtf((float)DH);
+  // per group: K [TK] + Q [TQ] + 2 x V [TK] + P [ceil(TQ/32) slabs x TK] rows of 128 B, every tile 1024-byte aligned
+  p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK) * 128;
   const long long rows = (long long)B * T;
   CUtensorMap tk, tq, tv;
   int rc;
-  if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, 128, false))) return rc;
+  if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, p.TK, false))) return rc;
   if ((rc = make_map(&tq, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false))) return rc;
   if ((rc = make_map(&tv, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
-  const size_t smem = 1024 + 128 * 128 + ((p.TQ * 128 + 1023) & ~1023) + ((p.TK * 128 + 1023) & ~1023) +
-                      (size_t)4 * p.TK * 128 + 64;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.TQ + DH <= 128) {
-    p.tmem_cols = 128;
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<128><<<B * H, 128, smem, st>>>(tk, tq, tv, p);
-  } else {
-    p.tmem_cols = 256;
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<256><<<B * H, 128, smem, st>>>(tk, tq, tv, p);
+  switch (p.TQ / 16) {
+    case 1: return launch_fwd<1, 3>(tk, tq, tv, p, st);
+    case 2: return launch_fwd<2, 3>(tk, tq, tv, p, st);
+    case 3: return launch_fwd<3, 3>(tk, tq, tv, p, st);
+    case 4: return launch_fwd<4, 3>(tk, tq, tv, p, st);
+    case 5: return launch_fwd<5, 3>(tk, tq, tv, p, st);
+    case 6: return launch_fwd<6, 2>(tk, tq, tv, p, st);
+    case 7: return launch_fwd<7, 1>(tk, tq, tv, p, st);
+    default: return launch_fwd<8, 1>(tk, tq, tv, p, st);
   }
-  MSX_LAUNCH_CHECK();
-  return MSX_OK;
 }
 
 extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias,
@@ -511,11 +833,43 @@ extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const f
   if ((rc = make_map(&tDOk, dctx, rows, D, D, DH, p.TQ, false))) return rc;
   if ((rc = make_map(&tDOm, dctx, rows, D, D, DH, p.TK, true))) return rc;
   if ((rc = make_map(&tQKVm, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.TQ <= 80) {
+    // pipelined kernel: K-major tiles carry TK rows only (MMA rows beyond TK alias the following tiles, their outputs are unused)
+    CUtensorMap tKk;
+    if ((rc = make_map(&tKk, qkv, rows, 3 * D, 3 * D, DH, p.TK, false))) return rc;
+    const int slab = p.TK * 128;
+    const int group_bytes = 2 * (2 * slab + 2 * p.TQ * 128) + 3 * slab;
+    // MMA descriptors over-address: 128 rows of the K / V tiles, 4 slabs of dS^T.  For T = 65 that stays inside the
+    // stage; for short sequences the last group's last stage needs the allocation extended.
+    const int stage_bytes = 2 * slab + 2 * p.TQ * 128;
+    const int extent = max(slab + 128 * 128, 4 * slab);
+    const size_t smem = 1024 + (size_t)max(2 * group_bytes, group_bytes + stage_bytes + extent);
+    MSX_REQUIRE(smem <= 220 * 1024, "msx_attention_tc_bwd: shared memory budget exceeded (T=%d)", T);
+    const int items = B * H;
+    const int want = (items + 1) / 2;
+    const int grid = want < msx_num_sms() ? want : msx_num_sms();
+#define MSX_BWD_PIPE(NCH)                                                                                              \
+  case NCH:                                                                                                            \
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attn_tc_bwd_pipe_kernel<NCH><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes);        \
+    break;
+    switch (p.TQ / 16) {
+      MSX_BWD_PIPE(1)
+      MSX_BWD_PIPE(2)
+      MSX_BWD_PIPE(3)
+      MSX_BWD_PIPE(4)
+      default:
+      MSX_BWD_PIPE(5)
+    }
+#undef MSX_BWD_PIPE
+    MSX_LAUNCH_CHECK();
+    return MSX_OK;
+  }
   const int slab = p.TK * 128;
   const int r1 = max(2 * 128 * 128 + 2 * p.TQ * 128, 4 * slab);
   const size_t smem = 1024 + (size_t)((p.TQ + 31) / 32) * slab + 3 * (size_t)slab + r1 + 64;
   MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_bwd: shared memory budget exceeded (T=%d)", T);
-  cudaStream_t st = (cudaStream_t)stream;
   if (96 + 2 * p.TQ <= 256) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_tc_bwd_kernel<256><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);

@@ -30,7 +30,9 @@ def _inputs(B, T, H, dh, seed):
     return qkv, mask
 
 
-@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8)])
+# the last two cases give every persistent pipeline group several (batch, head) items (mbarrier phases wrap)
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8),
+                                   (70, 65, 8), (300, 65, 8), (500, 97, 2), (400, 120, 2)])
 def test_attention_tc_forward(B, T, H):
     from musicstyletransfer_b200 import ops
     dh = 32
@@ -49,7 +51,10 @@ def test_attention_tc_forward(B, T, H):
     assert err < 3e-3, err
 
 
-@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8)])
+# T <= 80 runs the pipelined kernel (the larger B cases give every pipeline group several items; H = 3 makes the head
+# change between the items of a group, which exercises the bias-gradient flush), T > 80 the one-shot kernel
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8),
+                                   (70, 65, 8), (300, 65, 8), (220, 66, 3), (400, 33, 2)])
 def test_attention_backward(B, T, H):
     """dqkv of both backward kernels vs torch autograd (float64) through the reference formula."""
     from musicstyletransfer_b200 import ops
