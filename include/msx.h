@@ -85,7 +85,10 @@ int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, fl
 int msx_attention_tc_supported(const float* qkv, int T, int dh);
 int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias, int B,
-                         int T, int H, int dh, void* stream);   /* dbias (optional) [3*H*dh] += column sums of dqkv */
+                         int T, int H, int dh, void* stream);
+/* Profiling hook for the pipelined tensor-core backward: device buffer of 2 x 16 x 9 int64 clock64 stamps (block 0,
+ * per pipeline group, first 16 items); NULL disables. */
+int msx_attention_tc_set_trace(long long* buf);   /* dbias (optional) [3*H*dh] += column sums of dqkv */
 
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
  * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);

@@ -19,6 +19,7 @@
 namespace {
 
 constexpr int DH = 32;
+constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -132,6 +133,7 @@ struct AttnTcParams {
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
   int items;           // B * H
   int group_bytes;     // shared memory of one pipeline group
+  int smem_bytes;      // dynamic shared memory behind the 1024-byte aligned base
   float inv_scale;
 };
 
@@ -139,24 +141,45 @@ __device__ __forceinline__ void group_sync(int g) {       // named barrier of on
   asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 }
 
+// One lane of a converged warp.  The tcgen05 / TMA instructions take uniform-register operands: issuing them from
+// `if (lane == 0)` code makes the compiler wrap every one in an ELECT + R2UR "waterfall" loop (~90 cycles each, measured
+// with the clock64 trace), issuing them under elect.sync from warp-uniform values does not.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Forward.  Persistent CTAs (one per SM), each running G independent 128-thread pipeline groups; a group walks its
 // (batch, head) items with its own TMA ring, TMEM slice and mbarriers, so the latency chain of one item
-// (TMA -> MMA 1 -> softmax -> MMA 2 -> store) is hidden by the other groups and by the prefetch of the next item:
-//   K, Q of item n+1 are fetched as soon as MMA 1 of item n has retired, V is double-buffered.
+// (TMA -> MMA 1 -> softmax -> MMA 2 -> store) is hidden by the other groups and by the prefetch of the next item.
+// Roles inside a group: lane 0 of warp 3 is the ISSUER (all TMA loads, both MMAs; for T <= 96 warp 3 owns no valid
+// key row, so the issuer runs ahead of the softmax warps: K, Q of item n+1 are fetched as soon as MMA 1 of item n
+// has retired, V is double-buffered); every warp that owns valid rows does softmax + the output rows.
 // NCH = TQ / 16: the key row's scores are held in registers (one tcgen05.ld pass, one exp per score).
 template <int NCH, int G>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   constexpr int TQ = NCH * 16;
-  constexpr int kTmemStride = (TQ + DH + 31) / 32 * 32;    // per group: O [0,32) | S [32, 32+TQ)
+  constexpr int kTmemStride = (TQ + 2 * DH + 31) / 32 * 32;  // per group: O even [0,32) | O odd [32,64) | S [64, 64+TQ)
   constexpr int kTmemCols = G * kTmemStride <= 128 ? 128 : G * kTmemStride <= 256 ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ unsigned long long bars_all[G][5];            // kq, v0, v1, s_full, o_full
+  __shared__ unsigned long long bars_all[G][6];            // kq, v0, v1, s_full, o_full, p_ready
   __shared__ unsigned tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform as far as the compiler can tell
   const int g = warp >> 2, gt = tid & 127;                 // pipeline group, thread within the group (= key row / query row)
   const int T = p.T, TK = p.TK, D = p.H * DH;
   const int slab = TK * 128;                               // bytes of a [TK rows][128 B] tile
@@ -169,10 +192,17 @@ __global__ void __launch_bounds__(128 * G, 1)
   unsigned long long* bar_v = &bars_all[g][1];
   unsigned long long* bar_s = &bars_all[g][3];
   unsigned long long* bar_o = &bars_all[g][4];
+  unsigned long long* bar_p = &bars_all[g][5];
 
+  // zero-fill the dynamic shared memory once: MMA descriptors over-address tiles (128 K rows, 4 P / dS^T slabs), and
+  // whatever they read must be finite so that the unused accumulator rows never hold NaN / Inf
+  for (int i = tid * 16; i < p.smem_bytes; i += blockDim.x * 16) *reinterpret_cast<float4*>(base + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (tid == 0) {
-    for (int i = 0; i < G; ++i)
+    for (int i = 0; i < G; ++i) {
       for (int j = 0; j < 5; ++j) mbar_init(&bars_all[i][j], 1);
+      mbar_init(&bars_all[i][5], 4);                       // p_ready: lane 0 of each of the group's 4 warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -187,112 +217,148 @@ __global__ void __launch_bounds__(128 * G, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem_O = tmem_slot + g * kTmemStride, tmem_S = tmem_O + DH;
+  const unsigned tmem_O = tmem_slot + g * kTmemStride, tmem_S = tmem_O + 2 * DH;
   const unsigned lane_off = (unsigned)((warp & 3) * 32) << 16;
 
   const int first = blockIdx.x * G + g, stride = gridDim.x * G;
   const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TQ >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
   const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
                           ((unsigned)(128 >> 4) << 24);
+  const bool issuer = (warp & 3) == 3;                     // the group's warp 3 (warp-uniform), one elected lane issues
+  // keys beyond T hold a neighbouring sequence or zeros: a warp whose 32 rows are all >= T (T = 65: warp 3 of every
+  // group) skips the softmax arithmetic and the output rows
+  const bool warp_live = (warp & 3) * 32 < T;
+  // descriptors are fixed per buffer: built once, advanced by constant increments per MMA (a dependent 64-bit
+  // shift/or chain per MMA costs the single issuing thread ~90 cycles)
+  const unsigned long long dK = make_desc(smem_u32(sK), 16, 1024, 2), dQ = make_desc(smem_u32(sQ), 16, 1024, 2);
+  const unsigned long long dP = make_desc(smem_u32(sP), slab, 512, 1), dV = make_desc(smem_u32(sV), slab, 512, 1);
 
-  if (gt == 0 && first < p.items) {                        // prologue: loads of the group's first item
+  if (issuer && first < p.items) {                         // prologue: loads of the group's first item
     const int b = first / p.H, h = first % p.H;
-    mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
-    tma_load_2d(sK, &tmK, bar_kq, h * DH, b * T);
-    tma_load_2d(sQ, &tmQ, bar_kq, D + h * DH, b * T);
-    mbar_expect_tx(&bar_v[0], (unsigned)slab);
-    tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * DH, b * T);
+    if (elect_one()) {
+      mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
+      tma_load_2d(sK, &tmK, bar_kq, h * DH, b * T);
+      tma_load_2d(sQ, &tmQ, bar_kq, D + h * DH, b * T);
+      mbar_expect_tx(&bar_v[0], (unsigned)slab);
+      tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * DH, b * T);
+    }
+    __syncwarp();
   }
+  float mraw_next = (gt < T && first < p.items) ? __ldg(p.mask + (size_t)(first / p.H) * T + gt) : 0.f;
   int n = 0;
   for (int item = first; item < p.items; item += stride, ++n) {
     const int b = item / p.H, h = item % p.H;
     const int nxt = item + stride;
     const unsigned par = (unsigned)(n & 1);
-    if (gt == 0) {
+    const float mraw = mraw_next;                          // key-padding mask of this item (prefetched one item ahead)
+    if (gt < T && nxt < p.items) mraw_next = __ldg(p.mask + (size_t)(nxt / p.H) * T + gt);
+    if (issuer) {                                          // whole warp, warp-uniform control flow
+      const int b2 = nxt / p.H, h2 = nxt % p.H;
       mbar_wait(bar_kq, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major
+      if (elect_one()) {
+        // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major (+32 B per K = 8 step)
 #pragma unroll
-      for (int k = 0; k < DH / 8; ++k)
-        umma_tf32(tmem_S, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQ) + k * 32, 16, 1024, 2),
-                  idesc1, k > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-      if (nxt < p.items) {                                 // V of the next item into the other V buffer (free since o_full(n-1))
-        const int b2 = nxt / p.H, h2 = nxt % p.H;
-        mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
-        tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * DH, b2 * T);
+        for (int k = 0; k < DH / 8; ++k) umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        if (nxt < p.items) {                               // V of the next item into the other V buffer (free since o_full(n-1))
+          mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
+          tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * DH, b2 * T);
+        }
+      }
+      __syncwarp();
+      mbar_wait(bar_s, par);
+      if (nxt < p.items && elect_one()) {                  // K, Q tiles are free once MMA 1 has retired
+        mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
+        tma_load_2d(sK, &tmK, bar_kq, h2 * DH, b2 * T);
+        tma_load_2d(sQ, &tmQ, bar_kq, D + h2 * DH, b2 * T);
       }
     }
-    const int k = gt;                                      // this thread's key row
-    const bool valid = k < T;
-    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
     __syncwarp();
-    mbar_wait(bar_s, par);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (gt == 0 && nxt < p.items) {                        // K, Q tiles are free once MMA 1 has retired
-      const int b2 = nxt / p.H, h2 = nxt % p.H;
-      mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
-      tma_load_2d(sK, &tmK, bar_kq, h2 * DH, b2 * T);
-      tma_load_2d(sQ, &tmQ, bar_kq, D + h2 * DH, b2 * T);
-    }
-    __syncwarp();
-    {
+    if (warp_live) {
+      const int k = gt;                                    // this thread's key row
+      const bool valid = k < T;
+      const float rowmask = (valid && mraw > 0.f) ? 0.f : -1e9f;
+      mbar_wait(bar_s, par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the key row's TQ scores live in registers: softmax over the QUERY axis is thread-local
       float sc[TQ];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tmem_S + lane_off + c * 16, sc + c * 16);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_ld16_wait(sc + c * 16);
-      float mx = -INFINITY;
+      // every score this loop can see is finite (shared memory is zero-filled at kernel start, so even the rows and
+      // columns beyond T, which hold a neighbouring sequence, are), hence rows >= T need no per-element guard: their
+      // normaliser is forced to 0.  Only the last 16 columns can lie beyond T.
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int j = 0; j < TQ; ++j) {
-        sc[j] = sc[j] * p.inv_scale + rowmask;
-        if (j < T) mx = fmaxf(mx, sc[j]);
+        sc[j] = fmaf(sc[j], p.inv_scale, rowmask);
+        if (j < TQ - 16 || j < T) mx4[j & 3] = fmaxf(mx4[j & 3], sc[j]);
       }
-      float sum = 0.f;
+      const float mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < TQ; ++j) {
-        sc[j] = (valid && j < T) ? __expf(sc[j] - mx) : 0.f;
-        sum += sc[j];
+        sc[j] = exp2f(fmaf(sc[j], kLog2e, -mxl));
+        if (j >= TQ - 16 && j >= T) sc[j] = 0.f;
+        sum4[j & 3] += sc[j];
       }
-      const float inv = valid ? 1.f / sum : 0.f;
+      const float inv = valid ? 1.f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) : 0.f;
       if (k < TK) {                                        // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
 #pragma unroll
         for (int j = 0; j < TQ; j += 4)
           *reinterpret_cast<float4*>(sP + mn_major_off(j, k, TK)) =
               make_float4(to_tf32(sc[j] * inv), to_tf32(sc[j + 1] * inv), to_tf32(sc[j + 2] * inv), to_tf32(sc[j + 3] * inv));
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    group_sync(g);
-    if (gt == 0) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);                     // this warp's rows of P are staged (and its reads of S, O(n-1) are done)
+    if (issuer) {
+      mbar_wait(bar_p, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       mbar_wait(&bar_v[n & 1], (unsigned)((n >> 1) & 1));
       // MMA 2: O[128 queries x 32] = P^T[128 x TK] * V[TK x 32]; A MN-major (queries contiguous), B MN-major (d contiguous)
-      const unsigned sv = smem_u32(sV + (n & 1) * slab);
-      for (int j = 0; j < TK / 8; ++j)
-        umma_tf32(tmem_O, make_desc(smem_u32(sP) + j * 1024, slab, 512, 1), make_desc(sv + j * 1024, slab, 512, 1), idesc2,
-                  j > 0 ? 1u : 0u);
-      umma_commit(bar_o);
+      const unsigned long long dv = dV + (unsigned long long)((n & 1) * (slab >> 4));
+      if (elect_one()) {
+        // even and odd k-steps accumulate into two TMEM tiles (two independent chains); the epilogue adds them
+#pragma unroll 4
+        for (int j = 0; j < TK / 8; ++j)
+          umma_tf32(tmem_O + (j & 1) * DH, dP + 64 * j, dv + 64 * j, idesc2, j > 1 ? 1u : 0u);
+        umma_commit(bar_o);
+      }
     }
     __syncwarp();
+    // every warp waits (also the ones without valid rows): it keeps the group in lockstep, one p_ready arrival per
+    // warp and phase; for the issuer it also means P and V(n) are free again
     mbar_wait(bar_o, par);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
+    if (warp_live) {
       const int q = gt;
-      float o[32];
+      float o[32], o2[32];
       tmem_ld16_issue(tmem_O + lane_off, o);
       tmem_ld16_issue(tmem_O + lane_off + 16, o + 16);
+      if (TK > 8) {                                        // the odd accumulator exists only with >= 2 k-steps
+        tmem_ld16_issue(tmem_O + lane_off + DH, o2);
+        tmem_ld16_issue(tmem_O + lane_off + DH + 16, o2 + 16);
+      }
       tmem_ld16_wait(o);
       tmem_ld16_wait(o + 16);
+      if (TK > 8) {
+        tmem_ld16_wait(o2);
+        tmem_ld16_wait(o2 + 16);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] += o2[j];
+      }
       if (q < T) {
         float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)b * T + q) * D + h * DH);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -313,6 +379,7 @@ struct AttnTcBwdParams {
   float* dbias;        // optional [3*H*32]: += column sums of dqkv (bias gradient of the fused K|Q|V projection)
   int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
   float inv_scale;
+  long long* trace;    // optional profiling hook (msx_attention_tc_set_trace): clock64 stamps of block 0's groups
 };
 
 template <int kTmemCols>
@@ -516,18 +583,19 @@ __global__ void __launch_bounds__(256, 1)
     attn_tc_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmQk,
                             const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
                             const __grid_constant__ CUtensorMap tmQKVm, const AttnTcBwdParams p, const int items,
-                            const int group_bytes) {
+                            const int group_bytes, const int smem_bytes) {
   constexpr int G = 2;
   constexpr int TQ = NCH * 16;
   constexpr int kTmemStride = 256;                         // dV | dK | dQ | S/P [TQ] | dP/dS [TQ]
   static_assert(96 + 2 * TQ <= kTmemStride, "TMEM budget");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ unsigned long long bars_all[G][5];            // a0, a1, b, mma_a, mma_b
+  __shared__ unsigned long long bars_all[G][6];            // a0, a1, b, mma_a, mma_b, p_ready
   __shared__ float red[G][3 * 128];
   __shared__ unsigned tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform as far as the compiler can tell
   const int g = warp >> 2, gt = tid & 127;
   const int T = p.T, TK = p.TK, D = p.H * DH;
   const int slab = TK * 128;
@@ -538,10 +606,17 @@ __global__ void __launch_bounds__(256, 1)
   unsigned long long* bar_b = &bars_all[g][2];
   unsigned long long* bar_ma = &bars_all[g][3];
   unsigned long long* bar_mb = &bars_all[g][4];
+  unsigned long long* bar_p = &bars_all[g][5];
 
+  // zero-fill the dynamic shared memory once: MMA descriptors over-address tiles (128 K rows, 4 P / dS^T slabs), and
+  // whatever they read must be finite so that the unused accumulator rows never hold NaN / Inf
+  for (int i = tid * 16; i < smem_bytes; i += blockDim.x * 16) *reinterpret_cast<float4*>(base + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (tid == 0) {
-    for (int i = 0; i < G; ++i)
+    for (int i = 0; i < G; ++i) {
       for (int j = 0; j < 5; ++j) mbar_init(&bars_all[i][j], 1);
+      mbar_init(&bars_all[i][5], 4);                       // p_ready: lane 0 of each of the group's 4 warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKk) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQk) : "memory");
@@ -567,6 +642,11 @@ __global__ void __launch_bounds__(256, 1)
   const unsigned idesc_mm = idesc_ts | (1u << 15);          // A MN-major from shared memory, B MN-major
 
   const int first = blockIdx.x * G + g, stride = gridDim.x * G;
+  const bool issuer = (warp & 3) == 3;                      // the group's warp 3, one elected lane issues (see the forward kernel)
+  const bool warp_live = (warp & 3) * 32 < T;
+  // profiling hook: lane 0 of the issuer warp (stamps 0-3, 6) and thread 0 (stamps 4, 7, 8) of each group of block 0
+  long long* trc = (p.trace && blockIdx.x == 0 && (gt == 0 || gt == 96)) ? p.trace + g * 16 * 9 : nullptr;
+#define MSX_STAMP(i) do { if (trc && n < 16) trc[n * 9 + (i)] = clock64(); } while (0)
 
   auto load_a = [&](int item, int stage) {                  // K-major tiles of MMA S and MMA dP
     const int b = item / p.H, h = item % p.H;
@@ -577,13 +657,27 @@ __global__ void __launch_bounds__(256, 1)
     tma_load_2d(st + 2 * slab, &tmQk, &bar_a[stage], D + h * DH, b * T);
     tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * DH, b * T);
   };
+  // descriptors of stage 0 / the MN-major tiles, advanced by constant increments (see the forward kernel)
+  const unsigned long long dKk = make_desc(smem_u32(gbase), 16, 1024, 2);
+  const unsigned long long dYm = make_desc(smem_u32(gbase), slab, 512, 1);
+  const unsigned long long dBm = make_desc(smem_u32(sBm), slab, 512, 1);
+  const unsigned slab16 = (unsigned)(slab >> 4), tq16 = (unsigned)(TQ * 128) >> 4, stage16 = (unsigned)(stage_bytes >> 4);
 
-  float acc_b[3] = {0.f, 0.f, 0.f};                         // lane c: column c of dK / dQ / dV summed over this warp's rows
+  // bias gradient: every thread sums its own dK / dQ / dV rows over the items of the group (plain adds); the
+  // cross-lane column sums (31 shuffles per 32 columns) run once per head change instead of once per item
+  float acc[96];
+#pragma unroll
+  for (int j = 0; j < 96; ++j) acc[j] = 0.f;
   int acc_h = -1;
   auto flush_bias = [&]() {                                 // group-uniform
     if (!p.dbias || acc_h < 0) return;
 #pragma unroll
-    for (int m = 0; m < 3; ++m) red[g][m * 128 + (warp & 3) * 32 + lane] = acc_b[m];
+    for (int m = 0; m < 3; ++m) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { t[j] = acc[m * 32 + j]; acc[m * 32 + j] = 0.f; }
+      red[g][m * 128 + (warp & 3) * 32 + lane] = warp_colsum32(t, lane);
+    }
     group_sync(g);
     if (gt < 96) {
       const int m = gt >> 5, c = gt & 31;
@@ -591,111 +685,147 @@ __global__ void __launch_bounds__(256, 1)
                 red[g][m * 128 + c] + red[g][m * 128 + 32 + c] + red[g][m * 128 + 64 + c] + red[g][m * 128 + 96 + c]);
     }
     group_sync(g);
-    acc_b[0] = acc_b[1] = acc_b[2] = 0.f;
   };
 
-  if (gt == 0 && first < items) load_a(first, 0);
+  if (issuer && first < items) {
+    if (elect_one()) load_a(first, 0);
+    __syncwarp();
+  }
+  float mraw_next = (gt < T && first < items) ? __ldg(p.mask + (size_t)(first / p.H) * T + gt) : 0.f;
   int n = 0;
   for (int item = first; item < items; item += stride, ++n) {
     const int b = item / p.H, h = item % p.H;
     const int nxt = item + stride;
     const unsigned par = (unsigned)(n & 1);
     const int stg = n & 1;
-    unsigned char* sA = gbase + stg * stage_bytes;
-    unsigned char* sY = sA;                                 // dS^T (q contiguous) aliases the stage after MMA S / dP retired
+    unsigned char* sY = gbase + stg * stage_bytes;          // dS^T (q contiguous) aliases the stage after MMA S / dP retired
+    const float mraw = mraw_next;
+    if (gt < T && nxt < items) mraw_next = __ldg(p.mask + (size_t)(nxt / p.H) * T + gt);
     if (p.dbias && h != acc_h) {
       flush_bias();
       acc_h = h;
     }
-    if (gt == 0) {
-      // MN-major tiles of the output MMAs (free: the previous item's output MMAs have retired)
-      mbar_expect_tx(bar_b, (unsigned)(3 * slab));
-      tma_load_2d(sBm, &tmDOm, bar_b, h * DH, b * T);
-      tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * DH, b * T);
-      tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * DH, b * T);
-      if (nxt < items) load_a(nxt, stg ^ 1);                // the other stage held item n-1 (its MMAs and dS^T are consumed)
+    if (issuer) {                                           // whole warp, warp-uniform control flow
+      MSX_STAMP(0);
+      if (elect_one()) {
+        // MN-major tiles of the output MMAs (free: the previous item's output MMAs have retired)
+        mbar_expect_tx(bar_b, (unsigned)(3 * slab));
+        tma_load_2d(sBm, &tmDOm, bar_b, h * DH, b * T);
+        tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * DH, b * T);
+        tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * DH, b * T);
+        if (nxt < items) load_a(nxt, stg ^ 1);              // the other stage held item n-1 (its MMAs and dS^T are consumed)
+      }
+      __syncwarp();
       mbar_wait(&bar_a[stg], (unsigned)((n >> 1) & 1));
+      MSX_STAMP(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned kk = smem_u32(sA), vk = kk + slab, qk = kk + 2 * slab, dok = qk + TQ * 128;
+      const unsigned long long kk = dKk + (unsigned long long)(stg * stage16), vk = kk + slab16, qk = vk + slab16, dok = qk + tq16;
+      if (elect_one()) {
+        // S = K Q^T and dP = V dO^T: two independent accumulate chains, interleaved
 #pragma unroll
-      for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
-        umma_tf32(tm_S, make_desc(kk + k * 32, 16, 1024, 2), make_desc(qk + k * 32, 16, 1024, 2), idesc_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < DH / 8; ++k)       // dP = V dO^T
-        umma_tf32(tm_dP, make_desc(vk + k * 32, 16, 1024, 2), make_desc(dok + k * 32, 16, 1024, 2), idesc_kk, k > 0 ? 1u : 0u);
-      umma_commit(bar_ma);
+        for (int k = 0; k < DH / 8; ++k) {
+          umma_tf32(tm_S, kk + 2 * k, qk + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+          umma_tf32(tm_dP, vk + 2 * k, dok + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_ma);
+      }
+      __syncwarp();
+      MSX_STAMP(2);
     }
-    const int k = gt;
-    const bool valid = k < T;
-    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + k) > 0.f) ? 0.f : -1e9f;
     __syncwarp();
-    mbar_wait(bar_ma, par);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-      float sc[TQ], gp[TQ];
+    if (warp_live) {
+      const int k = gt;
+      const bool valid = k < T;
+      const float rowmask = (valid && mraw > 0.f) ? 0.f : -1e9f;
+      mbar_wait(bar_ma, par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the key row's scores stay in registers; dP is re-read from TMEM in 16-column chunks (two cheap passes)
+      float sc[TQ];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tm_S + lane_off + c * 16, sc + c * 16);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld16_issue(tm_dP + lane_off + c * 16, gp + c * 16);
-#pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_ld16_wait(sc + c * 16);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld16_wait(gp + c * 16);
-      float mx = -INFINITY;
+      for (int j = 0; j < TQ; ++j) {                        // finite inputs, tail-only guards: see the forward kernel
+        sc[j] = fmaf(sc[j], p.inv_scale, rowmask);
+        if (j < TQ - 16 || j < T) mx4[j & 3] = fmaxf(mx4[j & 3], sc[j]);
+      }
+      const float mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < TQ; ++j) {
-        sc[j] = sc[j] * p.inv_scale + rowmask;
-        if (j < T) mx = fmaxf(mx, sc[j]);
+        sc[j] = exp2f(fmaf(sc[j], kLog2e, -mxl));
+        if (j >= TQ - 16 && j >= T) sc[j] = 0.f;
+        sum4[j & 3] += sc[j];
       }
-      float sum = 0.f;
+      const float inv = valid ? 1.f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) : 0.f;
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < TQ; ++j) {
-        sc[j] = (valid && j < T) ? __expf(sc[j] - mx) : 0.f;
-        sum += sc[j];
+      for (int c = 0; c < NCH; ++c) {
+        float gp[16];
+        tmem_ld16_issue(tm_dP + lane_off + c * 16, gp);
+        tmem_ld16_wait(gp);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          sc[c * 16 + j] *= inv;                            // P
+          d4[j & 3] = fmaf(sc[c * 16 + j], gp[j], d4[j & 3]);
+        }
       }
-      const float inv = valid ? 1.f / sum : 0.f;
-      float delta = 0.f;
+      const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-      for (int j = 0; j < TQ; ++j) {
-        sc[j] *= inv;                                       // P
-        delta = fmaf(sc[j], gp[j], delta);
-      }
+      for (int c = 0; c < NCH; ++c) {
+        float gp[16];
+        tmem_ld16_issue(tm_dP + lane_off + c * 16, gp);
+        tmem_ld16_wait(gp);
 #pragma unroll
-      for (int j = 0; j < TQ; ++j) {
-        gp[j] = to_tf32(sc[j] * (gp[j] - delta) * p.inv_scale);   // dS
-        sc[j] = to_tf32(sc[j]);
-      }
+        for (int j = 0; j < 16; ++j) {
+          gp[j] = to_tf32(sc[c * 16 + j] * ((gp[j] - delta) * p.inv_scale));   // dS
+          sc[c * 16 + j] = to_tf32(sc[c * 16 + j]);
+        }
+        tmem_st16(tm_dP + lane_off + c * 16, gp);
+        tmem_st16(tm_S + lane_off + c * 16, sc + c * 16);
+        if (k < TK) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_st16(tm_S + lane_off + c * 16, sc + c * 16);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_st16(tm_dP + lane_off + c * 16, gp + c * 16);
-      if (k < TK) {
-#pragma unroll
-        for (int j = 0; j < TQ; j += 4)
-          *reinterpret_cast<float4*>(sY + mn_major_off(j, k, TK)) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(sY + mn_major_off(c * 16 + j, k, TK)) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    group_sync(g);
-    if (gt == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      mbar_wait(bar_b, par);
-      const unsigned dom = smem_u32(sBm), qm = dom + slab, km = dom + 2 * slab;
-      for (int j = 0; j < TK / 8; ++j)       // dV[keys x 32] = P[keys x q] dO[q x 32]
-        umma_tf32_ts(tm_dV, tm_S + j * 8, make_desc(dom + j * 1024, slab, 512, 1), idesc_ts, j > 0 ? 1u : 0u);
-      for (int j = 0; j < TK / 8; ++j)       // dK[keys x 32] = dS[keys x q] Q[q x 32]
-        umma_tf32_ts(tm_dK, tm_dP + j * 8, make_desc(qm + j * 1024, slab, 512, 1), idesc_ts, j > 0 ? 1u : 0u);
-      for (int j = 0; j < TK / 8; ++j)       // dQ[queries x 32] = dS^T[q x keys] K[keys x 32]
-        umma_tf32(tm_dQ, make_desc(smem_u32(sY) + j * 1024, slab, 512, 1), make_desc(km + j * 1024, slab, 512, 1), idesc_mm,
-                  j > 0 ? 1u : 0u);
-      umma_commit(bar_mb);
+      if (gt == 0) MSX_STAMP(4);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncwarp();
-    mbar_wait(bar_mb, par);
+    if (lane == 0) mbar_arrive(bar_p);                      // P, dS (TMEM) and dS^T (shared) rows of this warp are staged
+    if (issuer) {
+      mbar_wait(bar_p, par);
+      MSX_STAMP(3);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(bar_b, par);
+      const unsigned long long ym = dYm + (unsigned long long)(stg * stage16);
+      const unsigned long long dom = dBm, qm = dBm + slab16, km = qm + slab16;
+      const int nk = TK / 8;
+      if (elect_one()) {
+        // three independent accumulate chains, interleaved:
+        //   dV[keys x 32] = P[keys x q] dO[q x 32],  dK[keys x 32] = dS[keys x q] Q[q x 32]  (A from TMEM)
+        //   dQ[queries x 32] = dS^T[q x keys] K[keys x 32]                                     (A from shared memory)
+#pragma unroll 3
+        for (int j = 0; j < nk; ++j) {
+          umma_tf32_ts(tm_dV, tm_S + j * 8, dom + 64 * j, idesc_ts, j > 0 ? 1u : 0u);
+          umma_tf32_ts(tm_dK, tm_dP + j * 8, qm + 64 * j, idesc_ts, j > 0 ? 1u : 0u);
+          umma_tf32(tm_dQ, ym + 64 * j, km + 64 * j, idesc_mm, j > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_mb);
+      }
+      __syncwarp();
+      MSX_STAMP(6);
+    }
+    __syncwarp();
+    mbar_wait(bar_mb, par);                                 // every warp: keeps the group in lockstep (see the forward kernel)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
+    if (gt == 0) MSX_STAMP(7);
+    if (warp_live) {
       // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
       float* rowp = p.dqkv + ((size_t)b * T + gt) * 3 * D + h * DH;
 #pragma unroll
@@ -710,18 +840,17 @@ __global__ void __launch_bounds__(256, 1)
           float4* dst = reinterpret_cast<float4*>(rowp + m * D);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        }
-        if (p.dbias) {
-          if (gt >= T) {
+          if (p.dbias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = 0.f;
+            for (int j = 0; j < 32; ++j) acc[m * 32 + j] += o[j];
           }
-          acc_b[m] += warp_colsum32(o, lane);
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (gt == 0) MSX_STAMP(8);
   }
+#undef MSX_STAMP
   flush_bias();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -770,6 +899,7 @@ template <int NCH, int G>
 int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& tv, AttnTcParams p, cudaStream_t st) {
   // the last group's MMA descriptors address 128 K rows / 4 P slabs: keep the tail inside the allocation
   const size_t smem = 1024 + (size_t)G * p.group_bytes + 16 * 1024;
+  p.smem_bytes = (int)smem - 1024;
   MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_fwd: shared memory budget exceeded (T=%d)", p.T);
   MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int want = (p.items + G - 1) / G;
@@ -813,6 +943,15 @@ extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* 
   }
 }
 
+namespace { long long* g_attn_trace = nullptr; }
+// Profiling hook: device buffer of 2 x 16 x 9 int64 receiving clock64 stamps of the pipelined backward kernel
+// (block 0, per group, first 16 items: loop top, tiles landed, MMA S/dP issued, S/dP ready, softmax done,
+// group barrier, output MMAs issued, outputs ready, stores issued).  nullptr disables.
+extern "C" int msx_attention_tc_set_trace(long long* buf) {
+  g_attn_trace = buf;
+  return MSX_OK;
+}
+
 extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias,
                                     int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_tc_bwd: null pointer");
@@ -821,7 +960,7 @@ extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const f
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnTcBwdParams p;
-  p.mask = mask; p.dqkv = dqkv; p.dbias = dbias; p.T = T; p.H = H;
+  p.mask = mask; p.dqkv = dqkv; p.dbias = dbias; p.T = T; p.H = H; p.trace = g_attn_trace;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.inv_scale = 1.f / sqrtf((float)DH);
@@ -852,7 +991,7 @@ extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const f
 #define MSX_BWD_PIPE(NCH)                                                                                              \
   case NCH:                                                                                                            \
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    attn_tc_bwd_pipe_kernel<NCH><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes);        \
+    attn_tc_bwd_pipe_kernel<NCH><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024);        \
     break;
     switch (p.TQ / 16) {
       MSX_BWD_PIPE(1)
