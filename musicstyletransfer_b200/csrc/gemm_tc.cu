@@ -78,6 +78,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
+// One lane of a converged warp (deterministic for a given member mask).  tcgen05 / TMA instructions take
+// uniform-register operands: issued from `if (lane == 0)` code the compiler wraps each one in an ELECT + R2UR
+// waterfall loop (~90 cycles per instruction), issued under elect.sync from warp-uniform values it does not.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -178,7 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
     // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
     unsigned char* box = st + sbuf * kOutBoxBytes;
     if (pending >= 2) {                     // the box we are about to overwrite must have been read
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
 #pragma unroll
@@ -187,7 +201,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
           make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {
       if (reduce)
         asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmc),
                      "r"(smem_u32(box)), "r"(col0), "r"(row0)
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char* stage_out = ring + kStages * kStageBytes;                        // [kEpiWarps][2][32 rows][128 B]
   Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int items = p.m_tiles * p.n_tiles * p.splitk;
 
   if (warp == 0 && lane == 0) {
@@ -235,17 +249,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      unsigned phase = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1);
-          unsigned char* sa = ring + stage * kStageBytes;
-          unsigned char* sb = sa + kTileBytes;
+    // ================================ TMA producer (whole warp waits, one elected lane issues) ================================
+    int stage = 0;
+    unsigned phase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        unsigned char* sa = ring + stage * kStageBytes;
+        unsigned char* sb = sa + kTileBytes;
+        if (elect_one()) {
           mbar_expect_tx(&bars->full[stage], kStageBytes);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &bars->full[stage], kb * BK, mt * BM);           // box {32 k, 128 rows}
@@ -261,43 +275,46 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int s = 0; s < BN / 32; ++s)
               tma_load_2d(sb + s * (BK * 128), &tmB, &bars->full[stage], nt * BN + s * 32, kb * BK);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
-      int stage = 0;
-      unsigned phase = 0;
-      int local = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
-        const int ks = it / (p.n_tiles * p.m_tiles);
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int buf = local & 1;
-        const unsigned use = (unsigned)(local >> 1);
-        mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
+    // ================================ MMA issuer (whole warp waits, one elected lane issues) ================================
+    // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+    // descriptors of stage 0; K-major: +32 B per K=8 step inside the 128 B swizzle row, SBO = 8 rows * 128 B.
+    // MN-major: +1024 B per 8 k-rows, LBO = slab stride (32 k-rows * 128 B), SBO = 4 k-rows * 128 B.
+    const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), BK * 128, 512, 1) : make_desc(smem_u32(ring), 16, 1024, 2);
+    const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + kTileBytes, BK * 128, 512, 1)
+                                        : make_desc(smem_u32(ring) + kTileBytes, 16, 1024, 2);
+    constexpr unsigned kAStep = A_MN ? 64 : 2, kBStep = B_MN ? 64 : 2;      // descriptor address units of 16 B
+    int stage = 0;
+    unsigned phase = 0;
+    int local = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
+      const int ks = it / (p.n_tiles * p.m_tiles);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int buf = local & 1;
+      const unsigned use = (unsigned)(local >> 1);
+      mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned tmem_d = tmem_base + buf * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bars->full[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned tmem_d = tmem_base + buf * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned sa = smem_u32(ring + stage * kStageBytes), sb = sa + kTileBytes;
+        const unsigned long long ad = ad0 + (unsigned long long)(stage * (kStageBytes >> 4));
+        const unsigned long long bd = bd0 + (unsigned long long)(stage * (kStageBytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // K-major: +32 B per K=8 step inside the 128 B swizzle row, SBO = 8 rows * 128 B.
-            // MN-major: +1024 B per 8 k-rows, LBO = slab stride (32 k-rows * 128 B), SBO = 4 k-rows * 128 B.
-            const unsigned long long ad = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
-            const unsigned long long bd = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&bars->empty[stage]);                 // frees the smem stage when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb == kb1 - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete
         }
-        umma_commit(&bars->tmem_full[buf]);                 // accumulator complete
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -421,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   unsigned char* stage_out = ring + Cfg::kStages2 * Cfg::kStage;                  // [kEpiWarps][2][32 rows][128 B]
   Barriers2* bars = reinterpret_cast<Barriers2*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const unsigned rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -447,21 +464,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const unsigned tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ================================
-    if (lane == 0) {
-      int stage = 0;
-      unsigned phase = 0;
-      for (int it = pair; it < items; it += npairs) {
-        const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = mt * (2 * BM) + (int)rank * BM;               // this CTA's 128 rows of A
-        const int n0 = nt * BN2 + (int)rank * Cfg::kBRows;           // this CTA's BN2/2 rows of B
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1);
-          unsigned char* sa = ring + stage * Cfg::kStage;
-          unsigned char* sb = sa + Cfg::kATile;
+    // ================================ TMA producer (both CTAs; whole warp waits, one elected lane issues) ================================
+    int stage = 0;
+    unsigned phase = 0;
+    for (int it = pair; it < items; it += npairs) {
+      const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles, ks = it / (p.n_tiles * p.m_tiles);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int m0 = mt * (2 * BM) + (int)rank * BM;               // this CTA's 128 rows of A
+      const int n0 = nt * BN2 + (int)rank * Cfg::kBRows;           // this CTA's BN2/2 rows of B
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        unsigned char* sa = ring + stage * Cfg::kStage;
+        unsigned char* sb = sa + Cfg::kATile;
+        const unsigned fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&bars->full[stage], 2 * Cfg::kStage);
-          const unsigned fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
           if (!A_MN) {
             tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);                           // box {32 k, 128 rows}
           } else {
@@ -476,16 +493,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int s = 0; s < Cfg::kBRows / 32; ++s)
               tma_load_2d_pair(sb + s * (BK * 128), &tmB, fb, n0 + s * 32, kb * BK);
           }
-          if (++stage == Cfg::kStages2) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages2) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (leader CTA only) ================================
-    if (lane == 0 && leader) {
+    // ================================ MMA issuer (leader CTA only; whole warp waits, one elected lane issues) ================================
+    if (leader) {
       // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24 with M = 256 across the pair
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((unsigned)(BN2 >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
+      const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), BK * 128, 512, 1) : make_desc(smem_u32(ring), 16, 1024, 2);
+      const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + Cfg::kATile, BK * 128, 512, 1)
+                                          : make_desc(smem_u32(ring) + Cfg::kATile, 16, 1024, 2);
+      constexpr unsigned kAStep = A_MN ? 64 : 2, kBStep = B_MN ? 64 : 2;    // descriptor address units of 16 B
       int stage = 0;
       unsigned phase = 0;
       int local = 0;
@@ -500,17 +522,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned sa = smem_u32(ring + stage * Cfg::kStage), sb = sa + Cfg::kATile;
+          const unsigned long long ad = ad0 + (unsigned long long)(stage * (Cfg::kStage >> 4));
+          const unsigned long long bd = bd0 + (unsigned long long)(stage * (Cfg::kStage >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const unsigned long long ad = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
-            const unsigned long long bd = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_pair(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&bars->empty[stage]);            // frees this stage in BOTH CTAs
+            if (kb == kb1 - 1) umma_commit_pair(&bars->tmem_full[buf]);   // accumulator halves complete in both CTAs
           }
-          umma_commit_pair(&bars->empty[stage]);            // frees this stage in BOTH CTAs
+          __syncwarp();
           if (++stage == Cfg::kStages2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&bars->tmem_full[buf]);            // accumulator halves complete in both CTAs
       }
     }
   } else {
@@ -542,7 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();                       // no CTA leaves (or frees TMEM) while its pair may still touch it
