@@ -119,6 +119,13 @@ int msx_lstm_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const 
                  float* hs, float* hprev, float* cs, int B, int T, int H, void* stream);
 int msx_lstm_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0, const float* dhs,
                  float* dh0, float* dc0, float* db_i2h, float* db_h2h, int B, int T, int H, void* stream);
+/* Tensor-core variant (same contract, H == 128, even ld0, 8-byte aligned h0 / c0 / dh0 / dc0): W_h2h resident in
+ * registers as TF32 mma.sync fragments, fp32 accumulation, fp32 gate arithmetic. */
+int msx_lstm_tc_supported(int H, int ld0, const float* h0, const float* c0);
+int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const float* h0, const float* c0, int ld0,
+                    float* hs, float* hprev, float* cs, int B, int T, int H, void* stream);
+int msx_lstm_tc_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0, const float* dhs,
+                    float* dh0, float* dc0, float* db_i2h, float* db_h2h, int B, int T, int H, void* stream);
 
 /* K3 — losses.  msx_reparam_kl_*: z = m + eps*s and VariationalKLLoss (model.py:292, loss.py:8-12);
  * msx_ce_*: softmax(output_layer) + SoftmaxCrossEntropy (model.py:182/256, loss.py:16-23) fused on logits

@@ -201,6 +201,10 @@ class VAEEngine:
         fn(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
            site=site, accumulate=accumulate)
 
+    def _lstm_tc(self, Hd, tv):
+        """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers) in the tf32 precision mode, H = 128."""
+        return self.precision == "tf32" and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
+
     def _use_tc(self, A, lda, B, ldb, C, ldc, M, N, K):
         return self.precision == "tf32" and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
 
@@ -507,8 +511,9 @@ class VAEEngine:
             hs = bf.get("dec.hs", (M, Hd), dev)
             hprev = bf.get("dec.hprev", (M, Hd), dev)
             cs = bf.get("dec.cs", (M, Hd), dev)
-            ops.lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
-                         tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            lstm_fwd = ops.lstm_tc_fwd if self._lstm_tc(Hd, tv) else ops.lstm_fwd
+            lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
+                     tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
             dec_out, Td = hs, T
             dmask = None
         else:
@@ -582,9 +587,10 @@ class VAEEngine:
             xe = bf.t[("dec.xe", (M, Hd), torch.float32)]
             tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
             dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
-            ops.lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
-                         B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
-                         db_h2h=self._G("decoder.decoder.l0_h2h_bias"))            # gates now hold d(pre-activations)
+            lstm_bwd = ops.lstm_tc_bwd if self._lstm_tc(Hd, tv) else ops.lstm_bwd
+            lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
+                     B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
+                     db_h2h=self._G("decoder.decoder.l0_h2h_bias"))                # gates now hold d(pre-activations)
             dxe = bf.get("dec.dxe", (M, Hd), dev)
             self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
                             self._G("decoder.decoder.l0_i2h_weight"), None, 4 * Hd, Hd, dx=dxe, lddx=Hd)

@@ -140,6 +140,20 @@ def lstm_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H, db_i2h=None, db_
              _i(B), _i(T), _i(H), lib.stream_ptr())
 
 
+def lstm_tc_supported(H, ld0, h0, c0):
+    return bool(lib.load().msx_lstm_tc_supported(_i(H), _i(ld0), P(h0), P(c0)))
+
+
+def lstm_tc_fwd(gx, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H):
+    lib.call("msx_lstm_tc_fwd", P(gx), P(w_h2h), P(b_h2h), P(h0), P(c0), _i(ld0), P(hs), P(hprev), P(cs), _i(B), _i(T),
+             _i(H), lib.stream_ptr())
+
+
+def lstm_tc_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H, db_i2h=None, db_h2h=None):
+    lib.call("msx_lstm_tc_bwd", P(gates), P(w_h2h), P(cs), P(c0), _i(ld0), P(dhs), P(dh0), P(dc0), P(db_i2h), P(db_h2h),
+             _i(B), _i(T), _i(H), lib.stream_ptr())
+
+
 def adam_step(w, g, m, v, n, state, lr, beta1, beta2, eps, wd, rescale, clip, zero_grad=True):
     lib.call("msx_adam_step", P(w), P(g), P(m), P(v), _ll(n), P(state), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd),
              _f(rescale), _f(clip if clip is not None else 0.0), _i(1 if zero_grad else 0), lib.stream_ptr())

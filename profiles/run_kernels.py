@@ -53,3 +53,9 @@ for _ in range(2):
     ops.lstm_bwd(g2, w, cs, tv[:, Hd:], 2 * Hd, dhs, dtv, dtv[:, Hd:], B, T, Hd, db_i2h=dbi, db_h2h=dbh)
 torch.cuda.synchronize()
 print("ok2")
+for _ in range(2):
+    g2 = gates.clone()
+    ops.lstm_tc_fwd(g2, w, bh, tv, tv[:, Hd:], 2 * Hd, hs, hp, cs, B, T, Hd)
+    ops.lstm_tc_bwd(g2, w, cs, tv[:, Hd:], 2 * Hd, dhs, dtv, dtv[:, Hd:], B, T, Hd, db_i2h=dbi, db_h2h=dbh)
+torch.cuda.synchronize()
+print("ok3")
