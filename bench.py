@@ -30,7 +30,7 @@ UNIT = "sequences/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2048, help="sequences per GPU per step")
@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="rows per oracle step (bounded CPU sample)")
+    ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
+                    help="train: the contract line (default); sweep: BASELINE config 3 batch / sequence-length sweep, one JSON "
+                         "line per point; style: BASELINE config 5 style-transfer inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
     return ap.parse_args()
@@ -308,16 +311,30 @@ def run_ours(args):
     lib._profile = None
     if rank == 0:
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof["events"])
-        gemm_flops = sum(f for _, _, f in prof["events"])
+        gemm_flops = sum(f[0] for _, _, f in prof["events"])
+        gemm_bytes = sum(f[1] for _, _, f in prof["events"])
         step_ms = s.elapsed_time(e)
+        n_launch = max(1, len(prof["events"]))
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        kname = ("gemm_tc_kernel (msx_gemm_tc, tcgen05 kind::tf32 + TMA)" if args.precision == "tf32"
-                 else "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)")
-        roofline = {"bound": "tensor", "kernel": kname,
-                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
-                    "traffic": None, "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)",
+        gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+        kname = ("gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)"
+                 if args.precision == "tf32" else "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)")
+        # fp32-in / fp32-out GEMMs with K, N <= 1024: 64-102 flop per algorithmic byte, below the TF32 ridge point
+        # (~700 TFLOP/s / 6.55 TB/s = 107 flop/B), so the bounding resource is HBM
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "traffic_gemm.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": kname,
+                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": peaks["src"] + " HBM copy bandwidth",
+                    "algorithmic_bytes_per_launch": gemm_bytes / n_launch,
                     "share_of_step": gemm_ms / step_ms, "launches_per_step": len(prof["events"]) / psteps,
-                    "flops_per_step": gemm_flops / psteps, "avg_launch_ms": gemm_ms / max(1, len(prof["events"]))}
+                    "avg_launch_ms": gemm_ms / n_launch,
+                    "tensor": {"achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
+                               "peak_source": peaks["src"] + " bf16 sustained (cuBLAS); TF32 nominal peak is half of bf16",
+                               "flops_per_step": gemm_flops / psteps}}
     if world > 1:
         barrier()
 
@@ -352,10 +369,100 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------- BASELINE config 3 / 5
+def run_sweep(args):
+    """Config 3: fp32-storage training throughput over batch and sequence length on one GPU (device-resident batch)."""
+    import torch
+    from musicstyletransfer_b200 import lib, synth
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib.load()
+    cfg = VAEConfig(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
+    for L in (64, 128):
+        for B in (32, 128, 512, 2048, 8192):
+            eng = VAEEngine(cfg, dev, seed=0, precision=args.precision)
+            tok, lens, cls, lab = synth.token_rows_4_4(B * 2, L, seed=7)
+            bat = [tuple(torch.from_numpy(a[i * B:(i + 1) * B].copy()).to(dev) for a in (tok, lens, cls, lab)) for i in range(2)]
+            steps = max(5, min(200, int(60000 / max(B, 64))))
+            for i in range(3):
+                eng.train_step(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(steps):
+                eng.train_step(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / steps
+            print(json.dumps({"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+                              "seq_len": L, "T": L + 1, "steps": steps, "precision": args.precision,
+                              "config": {"workload": "config 3 sweep point, device-resident batch, " + args.dec_type}}), flush=True)
+            del eng, bat
+            torch.cuda.empty_cache()
+
+
+def run_style(args):
+    """Config 5: style-transfer inference (encode the source with the target class, z = means, decode 2T steps with
+    multinomial sampling) for every class over a large synthetic batch; the oracle times a small sample on the CPU."""
+    import numpy as np
+    import torch
+    from musicstyletransfer_b200 import lib, synth
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib.load()
+    cfg = VAEConfig(dec_type=args.dec_type)
+    eng = VAEEngine(cfg, dev, seed=0, precision=args.precision)
+    B, L = 8192, args.seq_len
+    tok, lens, cls, lab = synth.token_rows_4_4(B, L, seed=11)
+    tk, ln = torch.from_numpy(tok).to(dev), torch.from_numpy(lens).to(dev)
+    targets = [torch.full((B,), c, dtype=torch.int32, device=dev) for c in range(cfg.num_classes)]
+
+    def one_pass():
+        n = 0
+        for c in range(cfg.num_classes):                      # sampler.py:95 / :126: the class vector is overwritten per class
+            seqs, _ = eng.style_transfer(tk, ln, targets[c], seed=3)
+            n += seqs.shape[1]
+        return n
+    one_pass()
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ntok = one_pass()
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / reps
+    line = {"metric": "style_transfer_sequences_per_sec", "value": B * cfg.num_classes / sec, "unit": "sequences/s",
+            "tokens_per_s": B * ntok / sec, "ms_per_pass": sec * 1e3, "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "config": {"workload": "style transfer: %d rows x %d classes, L=%d, decoder %s, up to 2T=%d sampled steps per class; "
+                                   "wall clock including the host-side stop test" % (B, cfg.num_classes, L, args.dec_type, 2 * (L + 1))}}
+    if not args.no_cpu_baseline:
+        from oracle import model as om
+        cfg_o = om.Cfg(dec_type=args.dec_type)
+        p = om.init_params(cfg_o, seed=0)
+        Bc = 16
+        rng = np.random.default_rng(0)
+        u = torch.from_numpy(rng.random((2 * (L + 1), Bc), dtype=np.float32))
+        fn = om.style_transfer_lstm if args.dec_type == "lstm" else om.style_transfer_transformer
+        t0 = time.perf_counter()
+        for c in range(cfg_o.num_classes):
+            fn(cfg_o, p, torch.from_numpy(tok[:Bc]).float(), torch.full((Bc,), float(c)), u)
+        csec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": Bc * cfg_o.num_classes / csec, "unit": "sequences/s", "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": "%d rows x %d classes through the oracle" % (Bc, cfg_o.num_classes)}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sweep":
+        run_sweep(args)
+    elif args.mode == "style":
+        run_style(args)
     else:
         run_ours(args)
 

@@ -95,9 +95,11 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.
 
 // Dropout keep-mask for elements 4*idx4 .. 4*idx4+3 of dropout site `site`: keep iff u >= p.  Forward and
 // backward regenerate the same mask from (seed, site, element index), nothing is stored.  The generator is a
-// counter-based hash (a Weyl multiply plus the murmur3 32-bit finaliser over the element index, keyed by a 32-bit
-// key derived from seed and site): ~10 integer instructions per element instead of ~25 for Philox4x32-10, which made
-// the GEMM epilogue of the FF1 layer RNG-bound.  Philox stays in use for eps ~ N(0,1) and token sampling.
+// counter-based hash (a Weyl multiply plus the murmur3 32-bit finaliser over the element-pair index, keyed by a
+// 32-bit key derived from seed and site); each 32-bit hash serves TWO elements as 16-bit uniforms (keep iff
+// u16 >= floor(p * 65536), i.e. p is honoured to 1.5e-5), ~7 integer instructions per element instead of ~25 for
+// Philox4x32-10, which made the GEMM epilogue of the FF1 layer RNG-bound.  Philox stays in use for eps ~ N(0,1) and
+// token sampling.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
   return x;
@@ -105,13 +107,15 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __device__ __forceinline__ float dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, float p, float inv_keep,
                                                 float out[4]) {
   const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (site + 1u)));
-  const uint32_t hi = mix32(key ^ (uint32_t)(idx4 >> 30));
-  const uint32_t base = (uint32_t)idx4 << 2;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t r = mix32(((base + j) ^ hi) * 0x9E3779B1u + key);
-    out[j] = u32_to_unit(r) >= p ? inv_keep : 0.f;
-  }
+  const uint32_t hi = mix32(key ^ (uint32_t)(idx4 >> 31));
+  const uint32_t base = (uint32_t)idx4 << 1;
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const uint32_t r0 = mix32((base ^ hi) * 0x9E3779B1u + key);
+  const uint32_t r1 = mix32(((base + 1u) ^ hi) * 0x9E3779B1u + key);
+  out[0] = (r0 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  out[1] = (r0 >> 16) >= thr ? inv_keep : 0.f;
+  out[2] = (r1 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  out[3] = (r1 >> 16) >= thr ? inv_keep : 0.f;
   return 0.f;
 }
 #endif

@@ -15,13 +15,19 @@ def _chk(t, dtype=torch.float32):
     return t
 
 
+def _gemm_tag(M, N, K, accumulate, aux):
+    """(flops, algorithmic HBM bytes) of one GEMM launch for bench.py's roofline: every fp32 operand element read once,
+    C written once (+ read once when accumulating, + the aux mask read once)."""
+    return (2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (1 + (1 if accumulate else 0) + (1 if aux is not None else 0))))
+
+
 def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
          aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, colsum=None):
     """C[M,N] = epilogue(opA(A)[M,K] @ opB(B)[K,N]); leading dimensions in elements (row-major storage)."""
     lib.call("msx_gemm_f32", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
              _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr(),
-             tag=2.0 * M * N * K)
+             tag=_gemm_tag(M, N, K, accumulate, aux))
 
 
 def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
@@ -29,7 +35,8 @@ def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=Fa
     """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
     lib.call("msx_gemm_tc", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
-             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(), tag=2.0 * M * N * K)
+             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
+             tag=_gemm_tag(M, N, K, accumulate, aux))
 
 
 def gemm_tc_supported(A, lda, B, ldb, Cm, ldc, M, N, K):

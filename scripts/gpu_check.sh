@@ -19,7 +19,7 @@ import json
 d = json.loads(open("gpurun_out/bench_$tag.json").read().strip().splitlines()[-1])
 r = d["roofline"]
 print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"])
-print("roofline", {k: r[k] for k in r if k not in ("kernel", "peak_source")})
+print("roofline", {k: r[k] for k in r if k not in ("kernel", "peak_source", "tensor")}, "tensor TF/s", r["tensor"]["achieved"])
 print("raster", (d.get("rasteriser") or {}).get("roofline"))
 print("cpu", d.get("cpu_baseline"))
 EOF
