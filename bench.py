@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
                     help="train: the contract line (default); sweep: BASELINE config 3 batch / sequence-length sweep, one JSON "
                          "line per point; style: BASELINE config 5 style-transfer inference")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
     return ap.parse_args()
@@ -242,7 +243,13 @@ def run_ours(args):
 
     ar = allreduce if world > 1 else None
 
+    train = eng.train_step if args.no_graph else eng.train_step_graphed
+
     def step_resident(i):
+        tk, ln, cl, lb = resident[i % n_batches]
+        return train(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar)
+
+    def step_eager(i):
         tk, ln, cl, lb = resident[i % n_batches]
         return eng.train_step(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar)
 
@@ -254,8 +261,7 @@ def run_ours(args):
         db = stage[i % 2]
         for dst, src in zip(db, hb):
             dst.copy_(src, non_blocking=True)
-        out = eng.train_step(db[0], db[1], db[2], db[3], kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0,
-                             allreduce=ar)
+        out = train(db[0], db[1], db[2], db[3], kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar)
         loss_host[0].copy_(out["ce"], non_blocking=True)
         loss_host[1].copy_(out["kl"], non_blocking=True)
         torch.cuda.current_stream().synchronize()        # the step's result is read on the host
@@ -305,7 +311,7 @@ def run_ours(args):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for i in range(psteps):
-        step_resident(i)
+        step_eager(i)
     e.record()
     torch.cuda.synchronize()
     lib._profile = None
@@ -356,7 +362,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world,
+        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
                    "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                          (B * T * 4 * 40e3 / 1e9 / 10)},
         "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu,
@@ -385,18 +391,19 @@ def run_sweep(args):
             tok, lens, cls, lab = synth.token_rows_4_4(B * 2, L, seed=7)
             bat = [tuple(torch.from_numpy(a[i * B:(i + 1) * B].copy()).to(dev) for a in (tok, lens, cls, lab)) for i in range(2)]
             steps = max(5, min(200, int(60000 / max(B, 64))))
+            train = eng.train_step if args.no_graph else eng.train_step_graphed
             for i in range(3):
-                eng.train_step(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
+                train(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
             torch.cuda.synchronize()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for i in range(steps):
-                eng.train_step(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
+                train(*bat[i % 2], kl_weight=1.0, global_batch=B, lr=3e-4, clip_gradient=1.0)
             e.record()
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / steps
             print(json.dumps({"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
-                              "seq_len": L, "T": L + 1, "steps": steps, "precision": args.precision,
+                              "seq_len": L, "T": L + 1, "steps": steps, "precision": args.precision, "cuda_graph": not args.no_graph,
                               "config": {"workload": "config 3 sweep point, device-resident batch, " + args.dec_type}}), flush=True)
             del eng, bat
             torch.cuda.empty_cache()

@@ -31,6 +31,12 @@ extern "C" {
 int msx_version(void);
 const char* msx_last_error(void);
 int msx_device_sm_count(void);
+/* CUDA-graph support.  Every dropout site and the eps ~ N(0,1) fill derive their stream from (seed, site, element); a
+ * graph freezes the host-side `seed` argument, so a device-side counter can be registered that every such kernel
+ * launched afterwards adds to its seed (NULL = off).  msx_step_counter_tick increments it on the stream (one node at
+ * the end of the captured step).  The gluon loop this replaces draws fresh masks per call (trainer.py:166-168). */
+int msx_set_step_counter(unsigned long long* dev_counter);
+int msx_step_counter_tick(unsigned long long* dev_counter, void* stream);
 
 /* K1 — note-event rasteriser.  Replaces EventBasedMIDIReader._parse_track (MIDIUtil/midi_io.py:70-93),
  * create_{note_on,note_off,timeshift}_event (MIDIUtil/Melody.py:109-126) and the clock semantics of

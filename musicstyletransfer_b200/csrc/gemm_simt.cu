@@ -28,6 +28,7 @@ struct GemmParams {
   float drop_p;          // dropout after relu (0 = off)
   float drop_inv_keep;
   unsigned long long seed;
+  const unsigned long long* seed_ctr;
   unsigned site;
   const float* aux;      // dgrad: multiply by (aux[m,n] > 0 ? aux_scale : 0)
   int ldaux;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
       }
       if (p.drop_p > 0.f) {
         float s[4];
-        dropout_scale4(p.seed, p.site, ((unsigned long long)r * p.N + c) >> 2, p.drop_p, p.drop_inv_keep, s);
+        dropout_scale4(msx_eff_seed(p.seed, p.seed_ctr), p.site, ((unsigned long long)r * p.N + c) >> 2, p.drop_p, p.drop_inv_keep, s);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] *= s[j];
       }
@@ -226,7 +227,7 @@ extern "C" int msx_gemm_f32(const float* A, int lda, int transA, const float* B,
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.bias = bias; p.relu = relu; p.drop_p = drop_p; p.drop_inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+  p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
   p.splitk = splitk < 1 ? 1 : splitk;
   p.colsum = colsum;
   p.vecA = aligned16(A) && (lda % 4 == 0);

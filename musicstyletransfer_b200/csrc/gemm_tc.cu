@@ -39,6 +39,7 @@ struct TcParams {
   int relu;
   float drop_p, inv_keep;
   unsigned long long seed;
+  const unsigned long long* seed_ctr;   // optional device-side step counter added to seed
   unsigned site;
   const float* aux;
   int ldaux;
@@ -157,10 +158,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (p.drop_p > 0.f) {
+      const unsigned long long eff_seed = msx_eff_seed(p.seed, p.seed_ctr);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float s4[4];
-        dropout_scale4(p.seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
+        dropout_scale4(eff_seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
         v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
       }
     }
@@ -702,7 +704,7 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
     TcParams p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
     p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+    p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
     p.out_colsum = out_colsum;
     p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2); p.kb_total = msx_ceil_div(K, BK);
     if (splitk > 1) {                         // re-derive the split for pair tiles: about two waves of pairs
@@ -733,7 +735,7 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
   TcParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.seed = seed; p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
+  p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
   p.out_colsum = out_colsum;
   p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN); p.kb_total = msx_ceil_div(K, BK);
   if (splitk > p.kb_total) splitk = p.kb_total;

@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
                                                                  const float* __restrict__ beta, float* __restrict__ out,
                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                  long long M, int D, float eps, float p, float inv_keep,
-                                                                 unsigned long long seed, unsigned site) {
+                                                                 unsigned long long seed, const unsigned long long* seed_ctr,
+                                                                 unsigned site) {
+  seed = msx_eff_seed(seed, seed_ctr);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nper = D / (32 * VEC);
   const float invD = 1.f / D;
@@ -114,7 +116,9 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
     float* __restrict__ dres, float* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy) {
+    float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed,
+    const unsigned long long* seed_ctr, unsigned site, int accumulate_dres, int fuse_xy) {
+  seed = msx_eff_seed(seed, seed_ctr);
   __shared__ float red[kWarps][32 * VEC + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nper = D / (32 * VEC);
@@ -224,7 +228,7 @@ extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps, drop_p, inv_keep, seed, site)
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -251,7 +255,7 @@ extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
                                        (uintptr_t)gamma) & 15) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
     const int nper = D / 128;

@@ -49,7 +49,8 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ lat, const float
 }
 
 __global__ void normal_fill_kernel(float* __restrict__ out, long long n, unsigned long long seed,
-                                   unsigned long long offset) {
+                                   const unsigned long long* seed_ctr, unsigned long long offset) {
+  seed = msx_eff_seed(seed, seed_ctr);
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   const uint4 r = Philox::gen(seed, (unsigned long long)i4, offset);
@@ -278,7 +279,7 @@ extern "C" int msx_normal_fill(float* out, long long n, unsigned long long seed,
                                void* stream) {
   MSX_REQUIRE(out || n == 0, "msx_normal_fill: null pointer");
   if (n == 0) return MSX_OK;
-  normal_fill_kernel<<<msx_ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  normal_fill_kernel<<<msx_ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, msx_step_counter(), offset);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

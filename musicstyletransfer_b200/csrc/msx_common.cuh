@@ -41,6 +41,9 @@ void msx_set_error(const char* fmt, ...);
   } while (0)
 
 int msx_num_sms();
+// Optional device-side step counter added to every dropout / eps seed (msx_set_step_counter): lets a CUDA graph of the
+// train step draw fresh masks on every replay although the host-side seed argument is frozen in the graph.
+const unsigned long long* msx_step_counter();
 
 static inline int msx_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -91,6 +94,9 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+__device__ __forceinline__ unsigned long long msx_eff_seed(unsigned long long seed, const unsigned long long* ctr) {
+  return ctr ? seed + __ldg(ctr) : seed;
+}
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
 // Dropout keep-mask for elements 4*idx4 .. 4*idx4+3 of dropout site `site`: keep iff u >= p.  Forward and

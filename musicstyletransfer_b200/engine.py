@@ -178,6 +178,7 @@ class VAEEngine:
         self.step_count = 0
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.ctx = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, B, T):
@@ -641,6 +642,50 @@ class VAEEngine:
         ops.adam_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, lr, beta1, beta2, eps, wd, 1.0 / batch_size,
                       clip_gradient, zero_grad=True)
         self.step_count += 1
+
+    def train_step_graphed(self, tokens, seq_lens, classes, labels, kl_weight=1.0, global_batch=None, lr=3e-4,
+                           clip_gradient=None, allreduce=None):
+        """train_step replayed from a CUDA graph (one graph per batch shape and hyper-parameter set).  The schedule of a
+        step is static, so the ~66 kernel launches collapse into one graph launch; this is what keeps the reference's own
+        B = 32 configuration (scripts/train-vae.sh) from being launch-bound.  The first call with a new key runs eagerly
+        (it allocates every buffer), the second captures, later ones only copy the batch into the static input buffers
+        and replay.  Dropout masks and eps stay fresh on every replay through the device-side step counter
+        (msx_set_step_counter).  Returns the same dict as train_step (views of static buffers)."""
+        B, T = tokens.shape
+        key = (B, T, float(kl_weight), global_batch, float(lr), clip_gradient, allreduce is not None)
+        st = self._graphs.get(key)
+        if st is None:
+            out = self.train_step(tokens, seq_lens, classes, labels, kl_weight=kl_weight, global_batch=global_batch, lr=lr,
+                                  clip_gradient=clip_gradient, allreduce=allreduce)
+            self._graphs[key] = {"graph": None}
+            return out
+        if st["graph"] is None:
+            from . import lib
+            st["in"] = tuple(torch.empty_like(t) for t in (tokens, seq_lens, classes, labels))
+            st["counter"] = torch.zeros(1, dtype=torch.int64, device=self.device)
+            graph = torch.cuda.CUDAGraph()
+            l0 = lib.LAUNCHES
+            ops.set_step_counter(st["counter"])
+            try:
+                with torch.cuda.graph(graph):
+                    out = self.forward(*st["in"][:3], st["in"][3], train=True)
+                    self.backward(kl_weight)
+                    if allreduce is not None:
+                        allreduce(self.arena.g)
+                    self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient)
+                    ops.step_counter_tick(st["counter"])
+            finally:
+                ops.set_step_counter(None)
+            self.step_count -= 1                      # the capture pass executed nothing
+            st["graph"], st["out"], st["launches"] = graph, out, lib.LAUNCHES - l0
+            lib.LAUNCHES = l0
+        from . import lib
+        for dst, src in zip(st["in"], (tokens, seq_lens, classes, labels)):
+            dst.copy_(src, non_blocking=True)
+        st["graph"].replay()
+        lib.LAUNCHES += st["launches"]
+        self.step_count += 1
+        return st["out"]
 
     def train_step(self, tokens, seq_lens, classes, labels, eps=None, kl_weight=1.0, global_batch=None, lr=3e-4,
                    clip_gradient=None, allreduce=None):

@@ -48,6 +48,15 @@ def gemm_tc_set_pair(enable):
     return int(lib.load().msx_gemm_tc_set_pair(_i(1 if enable else 0)))
 
 
+def set_step_counter(counter):
+    """Registers (tensor) / clears (None) the device-side step counter that dropout / eps seeds add (CUDA-graph replay)."""
+    lib.check(lib.load().msx_set_step_counter(P(counter)), "msx_set_step_counter")
+
+
+def step_counter_tick(counter):
+    lib.call("msx_step_counter_tick", P(counter), lib.stream_ptr())
+
+
 def colsum(X, ld, M, N, out):
     lib.call("msx_colsum", P(X), _i(ld), _ll(M), _i(N), P(out), lib.stream_ptr())
 

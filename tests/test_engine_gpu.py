@@ -234,3 +234,30 @@ def test_tf32_tensor_core_step_deviation():
     print("tf32 gradient deviation, worst tensors:", devs[:4])
     assert devs[0][0] < 5e-2
     assert sum(d for d, _ in devs) / len(devs) < 2e-2
+
+
+def test_graphed_train_step_matches_eager():
+    """CUDA-graph replay of the step (train_step_graphed) walks the same seed sequence as the eager loop: same dropout
+    masks, same eps, same Adam state -> the parameters agree after several steps (up to the order of atomic adds)."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    tokens, seq_lens, classes, labels, _ = _batch(24, 21, 293, 2, 256, seed=5, min_len=9)
+    args = [_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels)]
+    res = []
+    for graphed in (False, True):
+        eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=0.2, dec_dropout=0.2), "cuda:0", seed=1, precision="tf32")
+        fn = eng.train_step_graphed if graphed else eng.train_step
+        ces = []
+        for _ in range(5):
+            out = fn(*args, kl_weight=1.0, global_batch=24, lr=3e-4, clip_gradient=1.0)
+            ces.append(out["ce"].clone())
+        torch.cuda.synchronize()
+        res.append((eng.arena.w.clone(), torch.stack(ces)))
+    (w0, c0), (w1, c1) = res
+    scale = float(c0.abs().max())
+    # step 0 is eager in both runs, step 1 is the capture + first replay, step 2 the second replay: with frozen masks or
+    # eps the per-sample losses would differ by percents there.  Later steps drift apart legitimately: Adam turns the
+    # summation-order noise of atomically accumulated, analytically-zero gradients (e.g. W_q.bias) into +-lr updates.
+    for i in range(3):
+        assert float((c0[i] - c1[i]).abs().max()) < 1e-4 * scale, (i, float((c0[i] - c1[i]).abs().max()))
+    assert float((c0 - c1).abs().max()) < 5e-2 * scale
+    assert float((w0 - w1).abs().max()) < 1e-2
