@@ -23,6 +23,15 @@ sys.path.insert(0, REPO)
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("MSX_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
+# stdout carries exactly one line (the JSON): everything else any library prints (NCCL banners, warnings) goes to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "vae_train_sequences_per_sec"
 UNIT = "sequences/s"
 
@@ -43,6 +52,9 @@ def parse_args():
     ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
                     help="train: the contract line (default); sweep: BASELINE config 3 batch / sequence-length sweep, one JSON "
                          "line per point; style: BASELINE config 5 style-transfer inference")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (falls back to "
+                         "nccl if symmetric memory cannot be set up), nccl = ncclAllReduce of the gradient arena + full Adam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
@@ -158,7 +170,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------- our arm
@@ -242,6 +254,14 @@ def run_ours(args):
         dist.all_reduce(g)
 
     ar = allreduce if world > 1 else None
+    dp_exchange = "none" if world == 1 else "nccl all-reduce + Adam on every rank"
+    if world > 1 and args.dp == "peer":
+        try:
+            eng.enable_peer_optimizer()
+            ar = "peer"
+            dp_exchange = "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (msx_adam_nvlink_step)"
+        except Exception as exc:        # symmetric memory unavailable: keep the NCCL exchange, say so
+            print("bench: peer optimiser unavailable (%s: %s), using NCCL all-reduce" % (type(exc).__name__, exc), file=sys.stderr)
 
     train = eng.train_step if args.no_graph else eng.train_step_graphed
 
@@ -346,6 +366,8 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            eng._graphs.clear()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
 
@@ -362,7 +384,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange,
                    "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                          (B * T * 4 * 40e3 / 1e9 / 10)},
         "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu,
@@ -370,8 +392,10 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
+        eng._graphs.clear()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -402,9 +426,9 @@ def run_sweep(args):
             e.record()
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / steps
-            print(json.dumps({"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+            emit({"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
                               "seq_len": L, "T": L + 1, "steps": steps, "precision": args.precision, "cuda_graph": not args.no_graph,
-                              "config": {"workload": "config 3 sweep point, device-resident batch, " + args.dec_type}}), flush=True)
+                              "config": {"workload": "config 3 sweep point, device-resident batch, " + args.dec_type}})
             del eng, bat
             torch.cuda.empty_cache()
 
@@ -459,7 +483,7 @@ def run_style(args):
         csec = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": Bc * cfg_o.num_classes / csec, "unit": "sequences/s", "cores": torch.get_num_threads(),
                                 "kind": "port", "sample": "%d rows x %d classes through the oracle" % (Bc, cfg_o.num_classes)}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():

@@ -164,6 +164,18 @@ int msx_sample_multinomial(const float* logits, int ld, int V, const float* unif
  * state[0] = step count t (device-resident), state[1] = lr_t; zero_grad clears g in the same pass. */
 int msx_adam_step(float* w, float* g, float* m, float* v, long long n, float* state, float lr, float beta1, float beta2,
                   float eps, float wd, float rescale, float clip, int zero_grad, void* stream);
+/* K5 — data-parallel optimiser step in one kernel over NVLink peer memory: reduce-scatter of the peer-mapped gradient
+ * arenas (sum in rank order, the trainer.py:176-177 rule), Adam on the owned slice with local (1/world-sharded)
+ * moments, all-gather of the updated parameters into every rank's arena.  peer_g / peer_w / peer_flags are HOST arrays
+ * of `world` device pointers (entry `rank` = the local buffer; flags: msx_adam_nvlink_flag_bytes() zeroed bytes per rank),
+ * done_counter a zeroed local u32, epoch_counter a zeroed local u64 (the kernel numbers its launches with it), max_ctas (0 = one per SM) bounds
+ * the grid.  Every rank must launch it; it completes when the local parameters are complete and the local gradient
+ * arena is no longer read by any peer (it is then zeroed if zero_grad). */
+int msx_adam_nvlink_flag_bytes(void);
+int msx_adam_nvlink_step(float* w, float* g, float* m, float* v, long long n, float* state, const float* const* peer_g,
+                         float* const* peer_w, unsigned long long* const* peer_flags, unsigned* done_counter, int rank,
+                         int world, unsigned long long* epoch_counter, float lr, float beta1, float beta2, float eps, float wd,
+                         float rescale, float clip, int zero_grad, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

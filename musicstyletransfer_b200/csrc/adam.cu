@@ -56,6 +56,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
 
 }  // namespace
 
+// shared with adam_nvlink.cu
+extern "C" void msx_adam_tick_launch(float* state, float lr, float b1, float b2, void* stream) {
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, b1, b2);
+}
+
 extern "C" int msx_adam_step(float* w, float* g, float* m, float* v, long long n, float* state, float lr, float beta1,
                              float beta2, float eps, float wd, float rescale, float clip, int zero_grad, void* stream) {
   MSX_REQUIRE(w && g && m && v && state, "msx_adam_step: null pointer");

@@ -636,12 +636,46 @@ class VAEEngine:
                       self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)
 
     # ------------------------------------------------------------------ optimiser
-    def adam_step(self, batch_size, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, clip_gradient=None):
-        """gluon.Trainer.step(batch_size) with MXNet-1.3 Adam (trainer.py:94-101,177); also zeroes the gradients."""
+    def adam_step(self, batch_size, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, clip_gradient=None, peer=False):
+        """gluon.Trainer.step(batch_size) with MXNet-1.3 Adam (trainer.py:94-101,177); also zeroes the gradients.
+        peer=True (after enable_peer_optimizer): the gradients of all ranks are reduced inside the optimiser kernel."""
         a = self.arena
-        ops.adam_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, lr, beta1, beta2, eps, wd, 1.0 / batch_size,
-                      clip_gradient, zero_grad=True)
+        if peer:
+            pr = self._peer
+            ops.adam_nvlink_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, pr["g"], pr["w"], pr["flags"], pr["done"],
+                                 pr["rank"], pr["world"], pr["epoch"], lr, beta1, beta2, eps, wd, 1.0 / batch_size,
+                                 clip_gradient, zero_grad=True)
+        else:
+            ops.adam_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, lr, beta1, beta2, eps, wd, 1.0 / batch_size,
+                          clip_gradient, zero_grad=True)
         self.step_count += 1
+
+    # ------------------------------------------------------------------ data parallel over NVLink peer memory
+    def enable_peer_optimizer(self, group=None):
+        """Moves the parameter and gradient arenas into torch symmetric memory (peer-mapped over NVLink) so that
+        adam_step(..., peer=True) can run the fused reduce-scatter + Adam + all-gather kernel (msx_adam_nvlink_step)
+        instead of ncclAllReduce + a full Adam pass on every rank.  Collective: every rank of `group` must call it,
+        before any CUDA graph of the step is captured.  Raises if symmetric memory is unavailable."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        a = self.arena
+        n = a.numel
+        fl = ops.adam_nvlink_flag_bytes() // 4
+        buf = symm_mem.empty(2 * n + fl, dtype=torch.float32, device=self.device)
+        hdl = symm_mem.rendezvous(buf, group)
+        buf.zero_()
+        buf[:n].copy_(a.w)
+        a.w, a.g = buf[:n], buf[n:2 * n]
+        base = [int(x) for x in hdl.buffer_ptrs]
+        self._peer = dict(handle=hdl, buf=buf, rank=int(hdl.rank), world=int(hdl.world_size),
+                          w=[b for b in base], g=[b + 4 * n for b in base], flags=[b + 8 * n for b in base],
+                          done=torch.zeros(1, dtype=torch.int32, device=self.device),
+                          epoch=torch.zeros(1, dtype=torch.int64, device=self.device))
+        self._graphs.clear()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)
+        return self._peer["world"]
 
     def train_step_graphed(self, tokens, seq_lens, classes, labels, kl_weight=1.0, global_batch=None, lr=3e-4,
                            clip_gradient=None, allreduce=None):
@@ -652,7 +686,8 @@ class VAEEngine:
         and replay.  Dropout masks and eps stay fresh on every replay through the device-side step counter
         (msx_set_step_counter).  Returns the same dict as train_step (views of static buffers)."""
         B, T = tokens.shape
-        key = (B, T, float(kl_weight), global_batch, float(lr), clip_gradient, allreduce is not None)
+        peer = isinstance(allreduce, str) and allreduce == "peer"
+        key = (B, T, float(kl_weight), global_batch, float(lr), clip_gradient, "peer" if peer else allreduce is not None)
         st = self._graphs.get(key)
         if st is None:
             out = self.train_step(tokens, seq_lens, classes, labels, kl_weight=kl_weight, global_batch=global_batch, lr=lr,
@@ -663,35 +698,47 @@ class VAEEngine:
             from . import lib
             st["in"] = tuple(torch.empty_like(t) for t in (tokens, seq_lens, classes, labels))
             st["counter"] = torch.zeros(1, dtype=torch.int64, device=self.device)
-            graph = torch.cuda.CUDAGraph()
+            # with a collective between backward and the optimiser the step is captured as two graphs around an eagerly
+            # launched all-reduce (NCCL inside a captured graph ties the graph's lifetime to the communicator's)
+            two = allreduce is not None and not peer
+            graph, graph2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if two else None)
             l0 = lib.LAUNCHES
             ops.set_step_counter(st["counter"])
             try:
                 with torch.cuda.graph(graph):
                     out = self.forward(*st["in"][:3], st["in"][3], train=True)
                     self.backward(kl_weight)
-                    if allreduce is not None:
-                        allreduce(self.arena.g)
-                    self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient)
-                    ops.step_counter_tick(st["counter"])
+                    if not two:
+                        self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient, peer=peer)
+                        ops.step_counter_tick(st["counter"])
+                if two:
+                    with torch.cuda.graph(graph2):
+                        self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient)
+                        ops.step_counter_tick(st["counter"])
             finally:
                 ops.set_step_counter(None)
             self.step_count -= 1                      # the capture pass executed nothing
-            st["graph"], st["out"], st["launches"] = graph, out, lib.LAUNCHES - l0
+            st["graph"], st["graph2"], st["out"], st["launches"] = graph, graph2, out, lib.LAUNCHES - l0
             lib.LAUNCHES = l0
         from . import lib
         for dst, src in zip(st["in"], (tokens, seq_lens, classes, labels)):
             dst.copy_(src, non_blocking=True)
         st["graph"].replay()
+        if st["graph2"] is not None:
+            allreduce(self.arena.g)
+            st["graph2"].replay()
         lib.LAUNCHES += st["launches"]
         self.step_count += 1
         return st["out"]
 
     def train_step(self, tokens, seq_lens, classes, labels, eps=None, kl_weight=1.0, global_batch=None, lr=3e-4,
                    clip_gradient=None, allreduce=None):
+        """allreduce: None (single GPU), a callable applied to the flat gradient arena (e.g. NCCL all-reduce), or "peer"
+        (fused NVLink reduce-scatter + Adam + all-gather, after enable_peer_optimizer)."""
         out = self.forward(tokens, seq_lens, classes, labels, eps=eps, train=True)
         self.backward(kl_weight)
-        if allreduce is not None:
+        peer = isinstance(allreduce, str) and allreduce == "peer"
+        if allreduce is not None and not peer:
             allreduce(self.arena.g)
-        self.adam_step(global_batch or tokens.shape[0], lr=lr, clip_gradient=clip_gradient)
+        self.adam_step(global_batch or tokens.shape[0], lr=lr, clip_gradient=clip_gradient, peer=peer)
         return out

@@ -175,6 +175,20 @@ def adam_step(w, g, m, v, n, state, lr, beta1, beta2, eps, wd, rescale, clip, ze
              _f(rescale), _f(clip if clip is not None else 0.0), _i(1 if zero_grad else 0), lib.stream_ptr())
 
 
+def adam_nvlink_flag_bytes():
+    return int(lib.load().msx_adam_nvlink_flag_bytes())
+
+
+def adam_nvlink_step(w, g, m, v, n, state, peer_g, peer_w, peer_flags, done_counter, rank, world, epoch_counter, lr, beta1, beta2,
+                     eps, wd, rescale, clip, zero_grad=True, max_ctas=0):
+    """Fused reduce-scatter + Adam + all-gather over peer memory.  peer_* are sequences of `world` device addresses (ints);
+    entry `rank` must be the local arena / flag block."""
+    arr = lambda ptrs: (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in ptrs])
+    lib.call("msx_adam_nvlink_step", P(w), P(g), P(m), P(v), _ll(n), P(state), arr(peer_g), arr(peer_w), arr(peer_flags),
+             P(done_counter), _i(rank), _i(world), P(epoch_counter), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _f(rescale),
+             _f(clip if clip is not None else 0.0), _i(1 if zero_grad else 0), _i(max_ctas), lib.stream_ptr())
+
+
 def sample_multinomial(logits, ld, V, uniforms, seed, step, nxt, score, out_seq, out_ld, out_col, B):
     lib.call("msx_sample_multinomial", P(logits), _i(ld), _i(V), P(uniforms), _u64(seed), _u64(step), P(nxt), P(score),
              P(out_seq), _i(out_ld), _i(out_col), _i(B), lib.stream_ptr())
