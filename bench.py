@@ -78,23 +78,34 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  nvidia-smi takes up to a
+    second to start on an 8-GPU box, so the sampler is started before the warm-up and the samples are filtered to the
+    timed region by their timestamps (mark_start / mark_end)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.06)                    # let the sample that covers the end of the region land
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -102,24 +113,24 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.05]
+        use = inside or rows[-3:]           # clock skew / too short a region: fall back to the last samples taken under load
+        if use:
+            sm = sorted(r[1] for r in use)
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in use),
+                   "reasons": sorted({n for r in use for n in r[3]}), "samples": len(use), "in_region": bool(inside)}
         return out
 
 
@@ -293,17 +304,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, sample_clocks=False):
+        sampler = ClockSampler(local) if sample_clocks else None
         for i in range(warmup):
             fn(i)
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.LAUNCHES
+        if sampler:
+            sampler.mark_start()
         s.record()
         for i in range(steps):
             fn(warmup + i)
         e.record()
         barrier()
+        if sampler:
+            sampler.mark_end()
         launches = lib.LAUNCHES - l0
         clocks = sampler.stop() if sampler else None
         ms = s.elapsed_time(e)

@@ -64,17 +64,97 @@ __global__ void normal_fill_kernel(float* __restrict__ out, long long n, unsigne
 }
 
 // ---------------------------------------------------------------- softmax CE from logits
-// One CTA per sample b; warps stride over its T rows.  ce[b] = (1/T) sum_t mask * (lse - logit[label]).
-// metrics[0..3] += {sum of min(nll, -log 1e-10), #non-pad labels, #argmax hits, #top-k hits}.
+// One warp per row, the row held in registers (one HBM pass, float4 loads when ld % 4 == 0): log-sum-exp, picked
+// logit, rank of the picked logit (accuracy / top-k).  ce[b] = (1/denom) sum_t mask * (lse - logit[label]) is
+// accumulated with one atomic per row into a zeroed ce; metrics[0..3] += {sum of min(nll, -log 1e-10), #non-pad
+// labels, #argmax hits, #top-k hits} are reduced per CTA first.
+constexpr int kCeMaxPerLane = 16;   // V <= 512 on the register path
+
+template <bool VEC4>
+__device__ __forceinline__ void ce_load_row(const float* __restrict__ x, int V, int ld, int lane, float (&r)[kCeMaxPerLane]) {
+  if (VEC4) {
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane / 4; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (c < ld) q = *reinterpret_cast<const float4*>(x + c);
+      r[4 * i] = c < V ? q.x : -INFINITY;
+      r[4 * i + 1] = c + 1 < V ? q.y : -INFINITY;
+      r[4 * i + 2] = c + 2 < V ? q.z : -INFINITY;
+      r[4 * i + 3] = c + 3 < V ? q.w : -INFINITY;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      r[i] = c < V ? x[c] : -INFINITY;
+    }
+  }
+}
+// column of register slot i of `lane`
+template <bool VEC4>
+__device__ __forceinline__ int ce_col(int lane, int i) { return VEC4 ? (lane + 32 * (i >> 2)) * 4 + (i & 3) : lane + 32 * i; }
+
+template <bool VEC4>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int ld,
                                                      const int* __restrict__ labels, float* __restrict__ ce,
-                                                     float* __restrict__ lse_out, float* __restrict__ metrics, int T,
-                                                     int V, int top_k, int denom) {
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float ce_acc = 0.f, m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
-  for (int t = warp; t < T; t += nw) {
-    const size_t row = (size_t)b * T + t;
-    const float* x = logits + row * ld;
+                                                     float* __restrict__ lse_out, float* __restrict__ metrics, int rows,
+                                                     int T, int V, int top_k, float inv_denom) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    const int label = __ldg(labels + row);
+    float r[kCeMaxPerLane];
+    ce_load_row<VEC4>(logits + (size_t)row * ld, V, ld, lane, r);
+    float mx = r[0];
+#pragma unroll
+    for (int i = 1; i < kCeMaxPerLane; ++i) mx = fmaxf(mx, r[i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane; ++i) sum += expf(r[i] - mx);      // exp(-inf) = 0 for the padding slots
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    if (lane == 0) lse_out[row] = lse;
+    if (label != 0) {
+      const int lc = min(max(label, 0), V - 1);
+      float mine = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane; ++i) mine = ce_col<VEC4>(lane, i) == lc ? r[i] : mine;
+      const float picked = warp_max(mine);
+      int greater = 0;
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane; ++i) greater += r[i] > picked ? 1 : 0;
+      greater = __reduce_add_sync(MSX_FULL, greater);
+      const float nll = lse - picked;
+      if (lane == 0) {
+        atomicAdd(ce + row / T, nll * inv_denom);
+        m_nll += fminf(nll, 23.02585093f);
+        m_tok += 1.f;
+        m_hit += greater == 0 ? 1.f : 0.f;
+        m_topk += greater < top_k ? 1.f : 0.f;
+      }
+    }
+  }
+  if (!metrics) return;
+  __shared__ float red[8][4];
+  if (lane == 0) { red[warp][0] = m_nll; red[warp][1] = m_tok; red[warp][2] = m_hit; red[warp][3] = m_topk; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[w][threadIdx.x];
+    if (a != 0.f) atomicAdd(metrics + threadIdx.x, a);
+  }
+}
+
+// Generic fallback for vocabularies beyond the register path (V > 512): three passes over the row.
+__global__ void __launch_bounds__(256) ce_fwd_big_kernel(const float* __restrict__ logits, int ld,
+                                                         const int* __restrict__ labels, float* __restrict__ ce,
+                                                         float* __restrict__ lse_out, float* __restrict__ metrics, int rows,
+                                                         int T, int V, int top_k, float inv_denom) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    const float* x = logits + (size_t)row * ld;
     float mx = -INFINITY;
     for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
     mx = warp_max(mx);
@@ -88,72 +168,86 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
       const float picked = x[min(max(label, 0), V - 1)];
       int greater = 0;
       for (int v = lane; v < V; v += 32) greater += x[v] > picked ? 1 : 0;
-      greater = (int)warp_sum((float)greater);
+      greater = __reduce_add_sync(MSX_FULL, greater);
       const float nll = lse - picked;
-      ce_acc += nll;
-      m_nll += fminf(nll, 23.02585093f);
-      m_tok += 1.f;
-      m_hit += greater == 0 ? 1.f : 0.f;
-      m_topk += greater < top_k ? 1.f : 0.f;
-    }
-  }
-  __shared__ float red[8][5];
-  if (lane == 0) {
-    red[warp][0] = ce_acc; red[warp][1] = m_nll; red[warp][2] = m_tok; red[warp][3] = m_hit; red[warp][4] = m_topk;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a[5] = {0, 0, 0, 0, 0};
-    for (int w = 0; w < nw; ++w)
-      for (int j = 0; j < 5; ++j) a[j] += red[w][j];
-    ce[b] = a[0] / denom;
-    if (metrics) {
-      atomicAdd(metrics + 0, a[1]);
-      atomicAdd(metrics + 1, a[2]);
-      atomicAdd(metrics + 2, a[3]);
-      atomicAdd(metrics + 3, a[4]);
+      if (lane == 0) {
+        atomicAdd(ce + row / T, nll * inv_denom);
+        if (metrics) {
+          atomicAdd(metrics + 0, fminf(nll, 23.02585093f));
+          atomicAdd(metrics + 1, 1.f);
+          if (greater == 0) atomicAdd(metrics + 2, 1.f);
+          if (greater < top_k) atomicAdd(metrics + 3, 1.f);
+        }
+      }
     }
   }
 }
 
 // in place: logits <- d ce_b / d logits * gout[b] = (softmax - onehot) * mask * gout[b] / denom ; pad columns zeroed.
 // dbias (optional, V <= 512): column sums of the gradient = bias gradient of the output layer, accumulated per
-// warp in registers over its rows and added with one atomic per column per warp.
+// warp in registers over its rows, reduced over the CTA's warps in shared memory, one atomic per column per CTA.
+template <bool VEC4>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
                                                      const float* __restrict__ lse, const float* __restrict__ gout,
-                                                     long long rows, int T, int V, int denom, float* __restrict__ dbias) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  float bs[16];
+                                                     int rows, int T, int V, float inv_denom, float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float bs[kCeMaxPerLane];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) bs[i] = 0.f;
-  for (long long row = warp0; row < rows; row += nwarps) {
-    float* x = logits + row * ld;
-    const int label = labels[row];
-    const float g = label != 0 ? (gout ? gout[row / T] : 1.f) / denom : 0.f;
-    const float l = lse[row];
+  for (int i = 0; i < kCeMaxPerLane; ++i) bs[i] = 0.f;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    float* x = logits + (size_t)row * ld;
+    const int label = __ldg(labels + row);
+    const float l = __ldg(lse + row);
+    const float g = label != 0 ? (gout ? __ldg(gout + row / T) : 1.f) * inv_denom : 0.f;
+    float r[kCeMaxPerLane];
+    ce_load_row<VEC4>(x, V, ld, lane, r);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int v = lane + 32 * i;
-      if (v < ld) {
-        float d = 0.f;
-        if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
-        x[v] = d;
-        bs[i] += d;
+    for (int i = 0; i < kCeMaxPerLane; ++i) {
+      const int c = ce_col<VEC4>(lane, i);
+      r[i] = (c < V && label != 0) ? (expf(r[i] - l) - (c == label ? 1.f : 0.f)) * g : 0.f;
+      bs[i] += r[i];
+    }
+    if (VEC4) {
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane / 4; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < ld) *reinterpret_cast<float4*>(x + c) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < ld) x[c] = r[i];
       }
     }
-    for (int v = lane + 512; v < ld; v += 32) {       // vocabularies beyond 512 columns (no fused bias sum)
+  }
+  if (!dbias) return;
+  __shared__ float red[8][kCeMaxPerLane * 32];
+#pragma unroll
+  for (int i = 0; i < kCeMaxPerLane; ++i) red[warp][i * 32 + lane] = bs[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < kCeMaxPerLane * 32; j += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[w][j];
+    const int i = j >> 5, ln = j & 31;
+    const int c = ce_col<VEC4>(ln, i);
+    if (c < V && a != 0.f) atomicAdd(dbias + c, a);
+  }
+}
+
+__global__ void __launch_bounds__(256) ce_bwd_big_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
+                                                         const float* __restrict__ lse, const float* __restrict__ gout,
+                                                         int rows, int T, int V, float inv_denom) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    float* x = logits + (size_t)row * ld;
+    const int label = labels[row];
+    const float g = label != 0 ? (gout ? gout[row / T] : 1.f) * inv_denom : 0.f;
+    const float l = lse[row];
+    for (int v = lane; v < ld; v += 32) {
       float d = 0.f;
       if (v < V && label != 0) d = (expf(x[v] - l) - (v == label ? 1.f : 0.f)) * g;
       x[v] = d;
-    }
-  }
-  if (dbias) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int v = lane + 32 * i;
-      if (v < V && bs[i] != 0.f) atomicAdd(dbias + v, bs[i]);
     }
   }
 }
@@ -290,7 +384,18 @@ extern "C" int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, fl
   MSX_REQUIRE(ld >= V && V > 0, "msx_ce_fwd: bad leading dimension");
   if (B == 0) return MSX_OK;
   MSX_REQUIRE(denom > 0, "msx_ce_fwd: denom must be > 0");
-  ce_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, ce, lse, metrics, T, V, top_k, denom);
+  MSX_REQUIRE((long long)B * T < (1ll << 31), "msx_ce_fwd: B * T must fit 31 bits");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * T;
+  MSX_CUDA(cudaMemsetAsync(ce, 0, (size_t)B * sizeof(float), st));      // rows add their share atomically
+  const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
+  const bool vec4 = (ld & 3) == 0 && ((uintptr_t)logits & 15) == 0;
+  if (V > 32 * kCeMaxPerLane)
+    ce_fwd_big_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
+  else if (vec4)
+    ce_fwd_kernel<true><<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
+  else
+    ce_fwd_kernel<false><<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -299,10 +404,18 @@ extern "C" int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, co
                           int T, int V, int denom, float* dbias, void* stream) {
   MSX_REQUIRE(logits_inout && labels && lse, "msx_ce_bwd: null pointer");
   if (B == 0) return MSX_OK;
-  const long long rows = (long long)B * T;
-  MSX_REQUIRE(dbias == nullptr || V <= 512, "msx_ce_bwd: fused bias gradient supports V <= 512");
-  const int grid = (int)min((long long)msx_num_sms() * 16, (rows + 7) / 8);
-  ce_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits_inout, ld, labels, lse, gout, rows, T, V, denom, dbias);
+  MSX_REQUIRE((long long)B * T < (1ll << 31), "msx_ce_bwd: B * T must fit 31 bits");
+  const int rows = B * T;
+  MSX_REQUIRE(dbias == nullptr || V <= 32 * kCeMaxPerLane, "msx_ce_bwd: fused bias gradient supports V <= 512");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
+  const bool vec4 = (ld & 3) == 0 && ((uintptr_t)logits_inout & 15) == 0;
+  if (V > 32 * kCeMaxPerLane)
+    ce_bwd_big_kernel<<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom);
+  else if (vec4)
+    ce_bwd_kernel<true><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
+  else
+    ce_bwd_kernel<false><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
