@@ -159,6 +159,18 @@ int msx_sample_multinomial(const float* logits, int ld, int V, const float* unif
                            unsigned long long step, int32_t* next, float* score, int32_t* out_seq, int out_ld,
                            int out_col, int B, void* stream);
 
+/* A12, beam search (sampler.py:192-257, LSTM decoder): one step over logits [B*beam, ld].  Candidates
+ * score_in[hyp] - log softmax(logits[hyp])[v]; a hypothesis whose last token is EOS / PAD is frozen (single candidate
+ * PAD at its own score); at step 1 only beam 0 of every row is expanded; the `beam` smallest win (ties: smaller
+ * hyp * V + v).  Writes the reordered sequences (seq_out[:, :step] = seq_in[parent], seq_out[:, step] = token), the new
+ * scores, parent[B*beam] (flat source hypothesis) and next_tok; unfinished[step] += number of winners that are neither
+ * EOS nor PAD (optional; the host finds the reference's stop step, sampler.py:250, from it).  msx_gather_rows reorders
+ * the recurrent states. */
+int msx_beam_step(const float* logits, int ld, int V, int B, int beam, const int32_t* seq_in, int32_t* seq_out, int seq_ld,
+                  int step, const float* score_in, float* score_out, int32_t* parent, int32_t* next_tok, int32_t* unfinished,
+                  void* stream);
+int msx_gather_rows(const float* in, float* out, const int32_t* parent, int rows, int width, void* stream);
+
 /* K4 — fused multi-tensor Adam over flat arenas.  Replaces gluon.Trainer('adam', ...).step(batch_size)
  * (trainer.py:94-101,177; MXNet 1.3 Adam: eps outside the bias correction, element-wise clip, rescale = 1/batch).
  * state[0] = step count t (device-resident), state[1] = lr_t; zero_grad clears g in the same pass. */

@@ -33,8 +33,8 @@ def get_sampler(type: str, model_folder: str, context, checkpoint: Optional[int]
         return Sampling(model_folder, context, checkpoint, verbose=args.verbose,
                         precision=getattr(args, "precision", "tf32"))
     elif type == 'beam-search':
-        raise NotImplementedError("beam search (sampler.py:192-257, LSTM-era API) is out of scope for this round; "
-                                  "see DESIGN.md")
+        return BeamSearchSampler(model_folder, context, checkpoint, verbose=args.verbose,
+                                 precision=getattr(args, "precision", "tf32"), beam_size=getattr(args, "beam_size", 5))
     raise ValueError("Sampler {} is not implemented".format(type))
 
 
@@ -110,6 +110,24 @@ class Sampling(SamplerBase):
         self.seed += 1
         seqs, _ = self.model.engine.style_transfer(tokens, seq_lens, classes, uniforms=uniforms, seed=self.seed)
         return seqs
+
+
+class BeamSearchSampler(SamplerBase):
+    """sampler.py:192-257 on the LSTM decoder (device-side beam search, engine.beam_search).  `sample` returns the best
+    hypothesis of every batch row ("take every k-th hypothesis"); `sample_all` returns all beam_size * B of them."""
+
+    def __init__(self, *args, beam_size: int, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.beam_size = beam_size
+        self.max_length_factor = 2.
+
+    def sample_all(self, data_batch):
+        [tokens, seq_lens, classes], _ = self.read_batch(data_batch)
+        return self.model.engine.beam_search(tokens, seq_lens, classes, self.beam_size)
+
+    def sample(self, data_batch):
+        seqs, _ = self.sample_all(data_batch)
+        return seqs[::self.beam_size]
 
 
 def sample_toy(args):

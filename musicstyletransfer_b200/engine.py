@@ -470,6 +470,62 @@ class VAEEngine:
                 break
         return seqs[:, :stop + 1], score
 
+    def beam_search(self, tokens, seq_lens, classes_target, beam_size):
+        """BeamSearchSampler.sample (sampler.py:192-257) on the LSTM decoder, device side: encoder with the target class,
+        z = means, beam_size hypotheses per row, up to 2T steps of embed -> i2h GEMM -> LSTM cell -> output GEMM ->
+        msx_beam_step (candidate scores, top-k, reordering) -> msx_gather_rows on (h, c).  Rules: csrc/beam.cu (evident
+        intent of the reference loop, which is inconsistent at HEAD).  Returns (sequences int32 [B*beam, <= 2T],
+        scores fp32 [B*beam]); hypotheses of row b are b*beam .. b*beam+beam-1, best first."""
+        cfg, dev = self.cfg, self.device
+        assert cfg.dec_type == "lstm", "beam search follows the reference's LSTM-decoder API (sampler.py:222)"
+        B, T = tokens.shape
+        K, Z, V, Hd = int(beam_size), cfg.latent, cfg.vocab, cfg.dec_size
+        I_max, R = 2 * T, B * int(beam_size)
+        bf = self._buf(B, T)
+        _, _, lat = self._encode(bf, tokens, classes_target, B, T, 0.0)
+        W = self._W
+        tv = bf.get("bs.tvec", (B, 2 * Hd), dev)
+        ops.embed_fwd(classes_target, None, None, W("decoder.class2hid.weight"), None, None, None, tv, None, B, 1, 2 * Hd, 0,
+                      1.0, cfg.num_classes)
+        self._dense_fwd(lat, 2 * Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
+                        accumulate=True)
+        bb = self._buf(R, -3)
+        h = [bb.get("bs.h%d" % i, (R, Hd), dev) for i in range(2)]
+        c = [bb.get("bs.c%d" % i, (R, Hd), dev) for i in range(2)]
+        h[0].copy_(tv[:, :Hd].repeat_interleave(K, dim=0))           # mx.nd.repeat(state, beam_size, axis=1), sampler.py:212
+        c[0].copy_(tv[:, Hd:].repeat_interleave(K, dim=0))
+        hn, cn, hp = bb.get("bs.hn", (R, Hd), dev), bb.get("bs.cn", (R, Hd), dev), bb.get("bs.hp", (R, Hd), dev)
+        seq = [bb.get("bs.seq%d" % i, (R, I_max), dev, torch.int32) for i in range(2)]
+        for sq in seq:
+            sq.zero_()
+            sq[:, 0] = 1
+        score = [bb.get("bs.score%d" % i, (R,), dev) for i in range(2)]
+        score[0].zero_()
+        nxt = bb.get("bs.next", (R,), dev, torch.int32)
+        nxt.fill_(1)
+        parent = bb.get("bs.parent", (R,), dev, torch.int32)
+        unfinished = bb.get("bs.unfinished", (I_max,), dev, torch.int32)
+        unfinished.zero_()
+        xe, gates = bb.get("bs.xe", (R, Hd), dev), bb.get("bs.gates", (R, 4 * Hd), dev)
+        logits = bb.get("bs.logits", (R, self.ldv), dev)
+        cur = 0
+        for i in range(1, I_max):
+            ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, None, xe, None, R, 1, Hd, 0, 1.0, V)
+            self._dense_fwd(xe, Hd, R, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
+                            4 * Hd, Hd)
+            ops.lstm_fwd(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
+                         hn, hp, cn, R, 1, Hd)
+            self._dense_fwd(hn, Hd, R, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V, Hd)
+            ops.beam_step(logits, self.ldv, V, B, K, seq[cur], seq[cur ^ 1], I_max, i, score[cur], score[cur ^ 1], parent,
+                          nxt, unfinished)
+            ops.gather_rows(hn, h[cur ^ 1], parent, R, Hd)
+            ops.gather_rows(cn, c[cur ^ 1], parent, R, Hd)
+            cur ^= 1
+        left = unfinished.cpu()[1:]
+        done = (left == 0).nonzero()
+        stop = int(done[0]) + 1 if done.numel() else I_max - 1      # sampler.py:250: all current tokens EOS / PAD
+        return seq[cur][:, :stop + 1].clone(), score[cur].clone()
+
     # ------------------------------------------------------------------ forward
     def forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
                 z_override=None):

@@ -192,3 +192,12 @@ def adam_nvlink_step(w, g, m, v, n, state, peer_g, peer_w, peer_flags, done_coun
 def sample_multinomial(logits, ld, V, uniforms, seed, step, nxt, score, out_seq, out_ld, out_col, B):
     lib.call("msx_sample_multinomial", P(logits), _i(ld), _i(V), P(uniforms), _u64(seed), _u64(step), P(nxt), P(score),
              P(out_seq), _i(out_ld), _i(out_col), _i(B), lib.stream_ptr())
+
+
+def beam_step(logits, ld, V, B, beam, seq_in, seq_out, seq_ld, step, score_in, score_out, parent, next_tok, unfinished=None):
+    lib.call("msx_beam_step", P(logits), _i(ld), _i(V), _i(B), _i(beam), P(seq_in), P(seq_out), _i(seq_ld), _i(step),
+             P(score_in), P(score_out), P(parent), P(next_tok), P(unfinished), lib.stream_ptr())
+
+
+def gather_rows(src, dst, parent, rows, width):
+    lib.call("msx_gather_rows", P(src), P(dst), P(parent), _i(rows), _i(width), lib.stream_ptr())

@@ -18,7 +18,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from .featurise import NUM_EVENTS, PAD_ID, SOS_ID
+from .featurise import EOS_ID, NUM_EVENTS, PAD_ID, SOS_ID
 
 
 class Cfg:
@@ -402,6 +402,52 @@ def style_transfer_lstm(cfg, p, tokens, classes_target, uniforms):
         if int(((nxt == SOS_ID) | (nxt == PAD_ID)).sum()) == B:
             break
     return seq
+
+
+def beam_search_lstm(cfg, p, tokens, classes_target, beam_size):
+    """BeamSearchSampler.sample (sampler.py:192-257) on the LSTM decoder, evident intent (the loop at HEAD re-takes the
+    previous states, adds the kept score twice and clobbers its step index):
+    candidate = score[hyp] - log p[hyp, v]; a hypothesis whose last token is EOS or PAD is frozen (one candidate, PAD,
+    at its own score); at step 1 only beam 0 is expanded (all beams are copies); the beam_size smallest candidates win,
+    ties by the smaller flat index hyp * V + v; states, sequences and scores are reordered by the winners; stop when
+    every current token is EOS or PAD (:250).  Returns (sequences [B*beam, <= 2T], scores [B*beam])."""
+    B, T = tokens.shape
+    K, I_max = beam_size, 2 * T
+    means, _ = encoder_forward(cfg, p, tokens, classes_target)
+    h0, c0 = lstm_initial_state(cfg, p, means, classes_target)
+    h = [h0.repeat_interleave(K, dim=0) for _ in range(cfg.dec_layers)]
+    c = [c0.repeat_interleave(K, dim=0) for _ in range(cfg.dec_layers)]
+    seq = torch.full((B * K, I_max), float(PAD_ID))
+    seq[:, 0] = SOS_ID
+    scores = torch.zeros(B * K)
+    stop = I_max - 1
+    for i in range(1, I_max):
+        prev = seq[:, i - 1]
+        probs, hn, cn = lstm_step(cfg, p, prev, h, c)
+        V = probs.shape[-1]
+        logp = torch.log_softmax(torch.log(probs), dim=-1)
+        cand = scores[:, None] - logp
+        fin = (prev == EOS_ID) | (prev == PAD_ID)
+        frozen = torch.full_like(cand, float("inf"))
+        frozen[:, PAD_ID] = scores
+        cand = torch.where(fin[:, None], frozen, cand)
+        if i == 1:
+            cand.view(B, K, V)[:, 1:, :] = float("inf")
+        flat = cand.view(B, K * V)
+        order = torch.argsort(flat, dim=1, stable=True)[:, :K]          # ascending, ties by index
+        vals = torch.gather(flat, 1, order)
+        hyp = (order // V + torch.arange(B)[:, None] * K).reshape(-1)
+        word = (order % V).reshape(-1)
+        new_scores = torch.where(torch.isinf(vals.reshape(-1)), scores[hyp], vals.reshape(-1))
+        seq = seq[hyp].clone()
+        seq[:, i] = word.float()
+        scores = new_scores
+        h = [x[hyp] for x in hn]
+        c = [x[hyp] for x in cn]
+        if int(((word == EOS_ID) | (word == PAD_ID)).sum()) == B * K:
+            stop = i
+            break
+    return seq[:, :stop + 1], scores
 
 
 def style_transfer_transformer(cfg, p, tokens, classes_target, uniforms):

@@ -130,6 +130,39 @@ def test_style_transfer_matches_oracle(dec_type):
     assert a.shape == b.shape and bool((a == b).all()) and int(a.max()) < 293 and int(a.min()) >= 0
 
 
+@pytest.mark.parametrize("beam", [1, 3, 5])
+def test_beam_search_matches_oracle(beam):
+    """Second sampling mode (sampler.py:192-257): device-side beam search on the LSTM decoder vs the oracle's restatement
+    of the same rules; EOS made likely enough that hypotheses finish and get frozen."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    cfg_o = om.Cfg(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type="lstm", dec_size=32)
+    p = om.init_params(cfg_o, seed=11)
+    gen = torch.Generator().manual_seed(4)
+    for k in p:
+        if k.endswith("bias"):
+            p[k] = 0.1 * torch.randn(p[k].shape, generator=gen)
+    p["decoder.output_layer.weight"] *= 3.0          # separated candidate scores -> the fp32 top-k agrees with the oracle
+    p["decoder.output_layer.bias"][2] += 0.5         # EOS wins after a few steps: hypotheses finish at different steps
+    B, T = 5, 7
+    tokens = torch.randint(3, 293, (B, T), generator=gen).float()
+    tokens[:, 0] = 1
+    tokens[1, 4:] = 0
+    lens = (tokens != 0).sum(1).float()
+    target = torch.full((B,), 1.0)
+    want_seq, want_score = om.beam_search_lstm(cfg_o, p, tokens, target, beam)
+    eng = VAEEngine(VAEConfig(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type="lstm", dec_size=32), DEV)
+    eng.arena.load_state(p)
+    i32 = lambda t: t.to(torch.int32).to(DEV)
+    seqs, score = eng.beam_search(i32(tokens), i32(lens), i32(target), beam)
+    got = seqs.cpu().float()
+    assert got.shape == want_seq.shape, (got.shape, want_seq.shape)
+    assert bool((got == want_seq).all()), (got, want_seq)
+    assert float((score.cpu() - want_score).abs().max()) < 1e-3 * (1.0 + float(want_score.abs().max()))
+    # rows of one batch entry are sorted best first
+    sc = score.cpu().view(B, beam)
+    assert bool((sc[:, 1:] >= sc[:, :-1] - 1e-6).all())
+
+
 def test_model_entry_points_and_toy_training(tmp_path):
     """Model(config)(tokens, seq_lens, classes) -> (probs, means, vars); Trainer.fit on ToyData (main.py:58-76) lowers
     the loss; checkpoints (params.N, train_state.pkl, config) are written and resume restores parameters."""
