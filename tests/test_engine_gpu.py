@@ -257,7 +257,8 @@ def test_graphed_train_step_matches_eager():
     # step 0 is eager in both runs, step 1 is the capture + first replay, step 2 the second replay: with frozen masks or
     # eps the per-sample losses would differ by percents there.  Later steps drift apart legitimately: Adam turns the
     # summation-order noise of atomically accumulated, analytically-zero gradients (e.g. W_q.bias) into +-lr updates.
+    # (measured: 1e-5 .. 1.3e-4 of the scale at step 2 depending on the run; the bound is 1e-3)
     for i in range(3):
-        assert float((c0[i] - c1[i]).abs().max()) < 1e-4 * scale, (i, float((c0[i] - c1[i]).abs().max()))
+        assert float((c0[i] - c1[i]).abs().max()) < 1e-3 * scale, (i, float((c0[i] - c1[i]).abs().max()))
     assert float((c0 - c1).abs().max()) < 5e-2 * scale
     assert float((w0 - w1).abs().max()) < 1e-2
