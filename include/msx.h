@@ -76,6 +76,20 @@ int msx_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, cons
  * (1) re-enables the pair kernel; returns the previous setting.  MSX_GEMM_PAIR=0 in the environment does the same. */
 int msx_gemm_tc_set_pair(int enable);
 
+/* bf16 variant of msx_gemm_tc (BASELINE config 4): A and B are bfloat16 in HBM (leading dimensions in elements,
+ * multiples of 8) and feed tcgen05.mma.kind::f16 with fp32 accumulation in TMEM; the epilogue arithmetic is fp32 and
+ * the same as msx_gemm_tc's.  C is fp32 (c_bf16=0; may accumulate / split-K through fp32 TMA reduce-adds) or bfloat16
+ * (c_bf16=1, plain stores only, ldc multiple of 8).  aux (the ReLU-mask source) is fp32 (aux_bf16=0) or bfloat16. */
+int msx_gemm_tc_bf16(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int c_bf16,
+                     int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed,
+                     unsigned site, const void* aux, int ldaux, int aux_bf16, float aux_scale, int accumulate,
+                     int splitk, float* out_colsum, void* stream);
+int msx_gemm_tc_bf16_supported(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, int c_bf16, int M,
+                               int N, int K);
+/* dst[i] = bfloat16(src[i]) (round to nearest even), i < n: builds bf16 operands from fp32 tensors (weights shadow,
+ * tests).  src and dst 16-byte aligned. */
+int msx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
 /* out[n] += sum_m X[m,n]: bias gradient of a Dense layer when the wgrad runs on the tensor path. */
 int msx_colsum(const float* X, int ld, long long M, int N, float* out, void* stream);
 

@@ -47,6 +47,8 @@ struct TcParams {
   int accumulate, splitk;
   float* out_colsum;   // out_colsum[n] += sum_m C[m,n] of the values this launch writes (bias gradient of the producer)
   int m_tiles, n_tiles, kb_total, kb_per_split;
+  int c_bf16;          // C is bf16 [M, ldc] (plain store only); the staging box is 32 rows x 64 B, SWIZZLE_64B
+  int aux_bf16;        // aux is bf16 [M, ldaux]
 };
 
 struct __align__(8) Barriers {
@@ -111,16 +113,48 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned 
          ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 
-__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// BF = false: kind::tf32 (fp32 in memory, K = 8 per instruction); BF = true: kind::f16 with bf16 operands (K = 16).
+// Either way one instruction consumes 32 bytes of the reduction dimension per operand row.
+template <bool BF>
+__device__ __forceinline__ void umma_ss(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                        unsigned idesc, unsigned accumulate) {
+  if (BF)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Operand geometry of one pipeline stage.  A stage row is always 128 bytes of the contiguous dimension:
+//   TF32: 32 elements;  MN-major slabs are 32 mn x 32 k-rows (SWIZZLE_128B_BASE32B, 4-row atoms, SBO 512 B)
+//   BF16: 64 elements;  MN-major slabs are 64 mn x 64 k-rows (SWIZZLE_128B, 8-row atoms, SBO 1024 B)
+template <bool BF>
+struct OpCfg {
+  static constexpr int kBKE = BF ? 64 : 32;                 // elements of K per stage
+  static constexpr int kSlabMN = BF ? 64 : 32;              // mn elements per MN-major slab
+  static constexpr int kSlabBytes = kBKE * 128;             // k-rows per stage x 128 B
+  static constexpr unsigned kMnStep = BF ? 128 : 64;        // descriptor units (16 B) per MMA: 16 / 8 k-rows x 128 B
+  static constexpr unsigned kMnSbo = BF ? 1024 : 512;
+  static constexpr unsigned long long kMnLayout = BF ? 2 : 1;
+  static constexpr unsigned kFmt = BF ? 1u : 2u;            // instruction descriptor operand format: BF16 / TF32
+};
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short b) { return __uint_as_float((unsigned)b << 16); }
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -166,7 +200,29 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
         v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
       }
     }
-    if (p.aux && my_row < p.M) {
+    if (p.aux && p.aux_bf16 && my_row < p.M) {
+      const unsigned short* ax = reinterpret_cast<const unsigned short*>(p.aux) + (size_t)my_row * p.ldaux + col0;
+      if (col0 + 32 <= p.N && (p.ldaux & 7) == 0) {
+        uint4 a4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a4[j] = __ldg(reinterpret_cast<const uint4*>(ax) + j);
+        // relu'(h) from the bf16 sign / zero pattern: positive <=> 0 < bits < 0x8000
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned w[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned lo = w[q] & 0xFFFFu, hi = w[q] >> 16;
+            v[8 * j + 2 * q + 0] *= (lo != 0u && lo < 0x8000u) ? p.aux_scale : 0.f;
+            v[8 * j + 2 * q + 1] *= (hi != 0u && hi < 0x8000u) ? p.aux_scale : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] *= (col0 + j < p.N && bf16_bits_to_float(__ldg(ax + j)) > 0.f) ? p.aux_scale : 0.f;
+      }
+    } else if (p.aux && my_row < p.M) {
       const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
       if (col0 + 32 <= p.N && (p.ldaux & 3) == 0) {
         float4 a4[8];
@@ -197,10 +253,19 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
       if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
+    if (p.c_bf16) {
+      // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk index XOR-ed with (row / 2) % 4
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-          make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (elect_one()) {
@@ -218,7 +283,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
     if (pending < 2) ++pending;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -263,19 +328,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         unsigned char* sb = sa + kTileBytes;
         if (elect_one()) {
           mbar_expect_tx(&bars->full[stage], kStageBytes);
+          using Op = OpCfg<BF>;
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, &bars->full[stage], kb * BK, mt * BM);           // box {32 k, 128 rows}
+            tma_load_2d(sa, &tmA, &bars->full[stage], kb * Op::kBKE, mt * BM);     // box {128 B of k, 128 rows}
           } else {
 #pragma unroll
-            for (int s = 0; s < BM / 32; ++s)                                       // 4 slabs {32 m, 32 k}
-              tma_load_2d(sa + s * (BK * 128), &tmA, &bars->full[stage], mt * BM + s * 32, kb * BK);
+            for (int s = 0; s < BM / Op::kSlabMN; ++s)                              // slabs {128 B of m, kBKE k-rows}
+              tma_load_2d(sa + s * Op::kSlabBytes, &tmA, &bars->full[stage], mt * BM + s * Op::kSlabMN, kb * Op::kBKE);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, &bars->full[stage], kb * BK, nt * BN);
+            tma_load_2d(sb, &tmB, &bars->full[stage], kb * Op::kBKE, nt * BN);
           } else {
 #pragma unroll
-            for (int s = 0; s < BN / 32; ++s)
-              tma_load_2d(sb + s * (BK * 128), &tmB, &bars->full[stage], nt * BN + s * 32, kb * BK);
+            for (int s = 0; s < BN / Op::kSlabMN; ++s)
+              tma_load_2d(sb + s * Op::kSlabBytes, &tmB, &bars->full[stage], nt * BN + s * Op::kSlabMN, kb * Op::kBKE);
           }
         }
         __syncwarp();
@@ -284,15 +350,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (whole warp waits, one elected lane issues) ================================
-    // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+    using Op = OpCfg<BF>;
+    // instruction descriptor: D=F32, A=B=TF32 / BF16, majors, N>>3 @17, M>>4 @24
+    const unsigned idesc = (1u << 4) | (Op::kFmt << 7) | (Op::kFmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                            ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
-    // descriptors of stage 0; K-major: +32 B per K=8 step inside the 128 B swizzle row, SBO = 8 rows * 128 B.
-    // MN-major: +1024 B per 8 k-rows, LBO = slab stride (32 k-rows * 128 B), SBO = 4 k-rows * 128 B.
-    const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), BK * 128, 512, 1) : make_desc(smem_u32(ring), 16, 1024, 2);
-    const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + kTileBytes, BK * 128, 512, 1)
+    // descriptors of stage 0; K-major: +32 B per MMA inside the 128 B swizzle row, SBO = 8 rows * 128 B.
+    // MN-major: LBO = slab stride (all k-rows of the stage * 128 B), SBO / step per MMA: see OpCfg.
+    const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), Op::kSlabBytes, Op::kMnSbo, Op::kMnLayout)
+                                        : make_desc(smem_u32(ring), 16, 1024, 2);
+    const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + kTileBytes, Op::kSlabBytes, Op::kMnSbo, Op::kMnLayout)
                                         : make_desc(smem_u32(ring) + kTileBytes, 16, 1024, 2);
-    constexpr unsigned kAStep = A_MN ? 64 : 2, kBStep = B_MN ? 64 : 2;      // descriptor address units of 16 B
+    constexpr unsigned kAStep = A_MN ? Op::kMnStep : 2, kBStep = B_MN ? Op::kMnStep : 2;      // descriptor address units of 16 B
     int stage = 0;
     unsigned phase = 0;
     int local = 0;
@@ -311,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const unsigned long long bd = bd0 + (unsigned long long)(stage * (kStageBytes >> 4));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) umma_ss<BF>(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&bars->empty[stage]);                 // frees the smem stage when these MMAs retire
           if (kb == kb1 - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete
         }
@@ -411,16 +479,27 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                               unsigned idesc, unsigned accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool BF>
+__device__ __forceinline__ void umma_ss_pair(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                             unsigned idesc, unsigned accumulate) {
+  if (BF)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
   asm volatile(
@@ -430,7 +509,7 @@ __device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
       : "memory");
 }
 
-template <int BN2, bool A_MN, bool B_MN>
+template <int BN2, bool A_MN, bool B_MN, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -480,20 +559,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         unsigned char* sb = sa + Cfg::kATile;
         const unsigned fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
         if (elect_one()) {
+          using Op = OpCfg<BF>;
           if (leader) mbar_expect_tx(&bars->full[stage], 2 * Cfg::kStage);
           if (!A_MN) {
-            tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);                           // box {32 k, 128 rows}
+            tma_load_2d_pair(sa, &tmA, fb, kb * Op::kBKE, m0);                     // box {128 B of k, 128 rows}
           } else {
 #pragma unroll
-            for (int s = 0; s < BM / 32; ++s)                                       // 4 slabs {32 m, 32 k}
-              tma_load_2d_pair(sa + s * (BK * 128), &tmA, fb, m0 + s * 32, kb * BK);
+            for (int s = 0; s < BM / Op::kSlabMN; ++s)                              // slabs {128 B of m, kBKE k-rows}
+              tma_load_2d_pair(sa + s * Op::kSlabBytes, &tmA, fb, m0 + s * Op::kSlabMN, kb * Op::kBKE);
           }
           if (!B_MN) {
-            tma_load_2d_pair(sb, &tmB, fb, kb * BK, n0);                           // box {32 k, BN2/2 rows}
+            tma_load_2d_pair(sb, &tmB, fb, kb * Op::kBKE, n0);                     // box {128 B of k, BN2/2 rows}
           } else {
 #pragma unroll
-            for (int s = 0; s < Cfg::kBRows / 32; ++s)
-              tma_load_2d_pair(sb + s * (BK * 128), &tmB, fb, n0 + s * 32, kb * BK);
+            for (int s = 0; s < Cfg::kBRows / Op::kSlabMN; ++s)
+              tma_load_2d_pair(sb + s * Op::kSlabBytes, &tmB, fb, n0 + s * Op::kSlabMN, kb * Op::kBKE);
           }
         }
         __syncwarp();
@@ -503,13 +583,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only; whole warp waits, one elected lane issues) ================================
     if (leader) {
-      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3 @17, M>>4 @24 with M = 256 across the pair
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      using Op = OpCfg<BF>;
+      // instruction descriptor: D=F32, A=B=TF32 / BF16, majors, N>>3 @17, M>>4 @24 with M = 256 across the pair
+      const unsigned idesc = (1u << 4) | (Op::kFmt << 7) | (Op::kFmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((unsigned)(BN2 >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
-      const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), BK * 128, 512, 1) : make_desc(smem_u32(ring), 16, 1024, 2);
-      const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + Cfg::kATile, BK * 128, 512, 1)
+      const unsigned long long ad0 = A_MN ? make_desc(smem_u32(ring), Op::kSlabBytes, Op::kMnSbo, Op::kMnLayout)
+                                          : make_desc(smem_u32(ring), 16, 1024, 2);
+      const unsigned long long bd0 = B_MN ? make_desc(smem_u32(ring) + Cfg::kATile, Op::kSlabBytes, Op::kMnSbo, Op::kMnLayout)
                                           : make_desc(smem_u32(ring) + Cfg::kATile, 16, 1024, 2);
-      constexpr unsigned kAStep = A_MN ? 64 : 2, kBStep = B_MN ? 64 : 2;    // descriptor address units of 16 B
+      constexpr unsigned kAStep = A_MN ? Op::kMnStep : 2, kBStep = B_MN ? Op::kMnStep : 2;    // descriptor address units of 16 B
       int stage = 0;
       unsigned phase = 0;
       int local = 0;
@@ -529,7 +611,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_pair(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_ss_pair<BF>(tmem_d, ad + kAStep * k, bd + kBStep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit_pair(&bars->empty[stage]);            // frees this stage in BOTH CTAs
             if (kb == kb1 - 1) umma_commit_pair(&bars->tmem_full[buf]);   // accumulator halves complete in both CTAs
           }
@@ -593,33 +675,40 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 row-major matrix [rows, cols] with leading dimension ld; box = {box_cols (contiguous), box_rows}
-// operand maps use the TFLOAT32 element type so that TMA rounds fp32 -> tf32 to nearest while loading (the MMA
-// itself would truncate the low 13 mantissa bits); the C map stays plain FLOAT32.
-int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
-             int box_rows, bool mn_major, bool operand = true) {
+// 2-D row-major matrix [rows, cols] with leading dimension ld (elements); box = {box_cols (contiguous), box_rows}.
+// kind: kMapC32 plain fp32 (the C map), kMapTf32 fp32 in memory read as TFLOAT32 (TMA rounds fp32 -> tf32 to nearest
+// while loading; the MMA itself would truncate the low 13 mantissa bits), kMapBf16 bf16 operand, kMapC16 bf16 C map
+// (32 x 32 box = 64-byte rows, SWIZZLE_64B).
+enum MapKind { kMapC32 = 0, kMapTf32 = 1, kMapBf16 = 2, kMapC16 = 3 };
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+             int box_rows, bool mn_major, MapKind kind) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { msx_set_error("msx_gemm_tc: cuTensorMapEncodeTiled is not available from the driver"); return MSX_ERR_CUDA; }
+  const bool b16 = kind == kMapBf16 || kind == kMapC16;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (b16 ? 2 : 4)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, operand ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = kind == kMapTf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                 : b16            ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = kind == kMapC16                ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : (mn_major && kind == kMapTf32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                                 : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { msx_set_error("msx_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MSX_ERR_CUDA; }
   return MSX_OK;
 }
 
 constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers);
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool BF>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
-  MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int grid = items < msx_num_sms() ? items : msx_num_sms();
-  gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tc, p);
+  gemm_tc_kernel<A_MN, B_MN, BF><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tc, p);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -629,15 +718,15 @@ constexpr size_t pair_smem_bytes() {
   return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers2);
 }
 
-template <int BN2, bool A_MN, bool B_MN>
+template <int BN2, bool A_MN, bool B_MN, bool BF>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = pair_smem_bytes<BN2>();
   static_assert(smem <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
-  MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2_kernel<BN2, A_MN, B_MN><<<2 * pairs, kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
+  gemm_tc2_kernel<BN2, A_MN, B_MN, BF><<<2 * pairs, kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -653,6 +742,74 @@ bool pair_enabled() {
   return g_pair_mode == 1;
 }
 
+template <bool BF>
+int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int c_bf16,
+                 int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
+                 const void* aux, int ldaux, int aux_bf16, float aux_scale, int accumulate, int splitk, float* out_colsum,
+                 void* stream) {
+  using Op = OpCfg<BF>;
+  constexpr MapKind kOp = BF ? kMapBf16 : kMapTf32;
+  if (splitk < 1) splitk = 1;
+  // operand majors: A is K-major when stored [M,K] (transA=0), MN-major when stored [K,M] (transA=1);
+  //                 B is K-major when stored [N,K] (transB=1), MN-major when stored [K,N] (transB=0).
+  const bool a_mn = transA == 1, b_mn = transB == 0;
+  CUtensorMap ta, tb, tc;
+  int rc = make_map(&tc, C, M, N, ldc, 32, 32, false, c_bf16 ? kMapC16 : kMapC32);   // epilogue box: 32 rows x 32 columns
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  TcParams p;
+  p.C = (float*)C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = (const float*)aux; p.ldaux = ldaux;
+  p.aux_scale = aux_scale; p.accumulate = accumulate; p.out_colsum = out_colsum; p.c_bf16 = c_bf16; p.aux_bf16 = aux_bf16;
+  p.kb_total = msx_ceil_div(K, Op::kBKE);
+  // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
+  // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
+  if (pair_enabled() && M > BM && N >= 64 && K >= 256) {
+    // ---- 2-CTA path: 256 x 256 (N > 128) or 256 x 128 pair tiles
+    const int bn2 = N > 128 ? 256 : 128;
+    if (!a_mn) rc = make_map(&ta, A, M, K, lda, Op::kBKE, BM, false, kOp); else rc = make_map(&ta, A, K, M, lda, Op::kSlabMN, Op::kBKE, true, kOp);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(&tb, B, N, K, ldb, Op::kBKE, bn2 / 2, false, kOp); else rc = make_map(&tb, B, K, N, ldb, Op::kSlabMN, Op::kBKE, true, kOp);
+    if (rc) return rc;
+    p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2);
+    if (splitk > 1) {                         // re-derive the split for pair tiles: about two waves of pairs
+      const int tiles = p.m_tiles * p.n_tiles, pairs = msx_num_sms() / 2;
+      splitk = (2 * pairs) / tiles;
+      if (splitk < 2) splitk = 2;
+    }
+    if (splitk > p.kb_total) splitk = p.kb_total;
+    p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
+    p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
+    if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
+    if (bn2 == 256) {
+      if (!a_mn && !b_mn) return launch_pair<256, false, false, BF>(ta, tb, tc, p, st);
+      if (!a_mn && b_mn) return launch_pair<256, false, true, BF>(ta, tb, tc, p, st);
+      if (a_mn && b_mn) return launch_pair<256, true, true, BF>(ta, tb, tc, p, st);
+    } else {
+      if (!a_mn && !b_mn) return launch_pair<128, false, false, BF>(ta, tb, tc, p, st);
+      if (!a_mn && b_mn) return launch_pair<128, false, true, BF>(ta, tb, tc, p, st);
+      if (a_mn && b_mn) return launch_pair<128, true, true, BF>(ta, tb, tc, p, st);
+    }
+    msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
+    return MSX_ERR_UNSUPPORTED;
+  }
+  if (!a_mn) rc = make_map(&ta, A, M, K, lda, Op::kBKE, BM, false, kOp); else rc = make_map(&ta, A, K, M, lda, Op::kSlabMN, Op::kBKE, true, kOp);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tb, B, N, K, ldb, Op::kBKE, BN, false, kOp); else rc = make_map(&tb, B, K, N, ldb, Op::kSlabMN, Op::kBKE, true, kOp);
+  if (rc) return rc;
+  p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN);
+  if (splitk > p.kb_total) splitk = p.kb_total;
+  p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
+  p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
+  if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
+  if (!a_mn && !b_mn) return launch<false, false, BF>(ta, tb, tc, p, st);
+  if (!a_mn && b_mn) return launch<false, true, BF>(ta, tb, tc, p, st);
+  if (a_mn && b_mn) return launch<true, true, BF>(ta, tb, tc, p, st);
+  msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
+  return MSX_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 // Returns 1 when msx_gemm_tc can take this problem (TMA needs 16-byte aligned bases and row pitches).
@@ -660,6 +817,15 @@ extern "C" int msx_gemm_tc_supported(const float* A, int lda, const float* B, in
                                      int N, int K) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return 0;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || (lda & 3) || (ldb & 3) || (ldc & 3)) return 0;
+  return 1;
+}
+
+// Same for msx_gemm_tc_bf16: A and B are bf16 (leading dimensions % 8), C is bf16 (ldc % 8) or fp32 (ldc % 4).
+extern "C" int msx_gemm_tc_bf16_supported(const void* A, int lda, const void* B, int ldb, const void* C, int ldc,
+                                          int c_bf16, int M, int N, int K) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return 0;
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || (lda & 7) || (ldb & 7)) return 0;
+  if (c_bf16 ? (ldc & 7) : (ldc & 3)) return 0;
   return 1;
 }
 
@@ -682,69 +848,31 @@ extern "C" int msx_gemm_tc(const float* A, int lda, int transA, const float* B, 
               "msx_gemm_tc: A, B and C must be 16-byte aligned with leading dimensions %% 4 == 0");
   MSX_REQUIRE(!(transA == 1 && transB == 1), "msx_gemm_tc: A^T B^T is not used on this path");
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc: dropout probability must be in [0,1)");
-  if (splitk < 1) splitk = 1;
   MSX_REQUIRE(!(splitk > 1 && (bias || relu || drop_p > 0.f || aux || accumulate)),
               "msx_gemm_tc: split-K only supports the plain atomic-add epilogue");
-  // operand majors: A is K-major when stored [M,K] (transA=0), MN-major when stored [K,M] (transA=1);
-  //                 B is K-major when stored [N,K] (transB=1), MN-major when stored [K,N] (transB=0).
-  const bool a_mn = transA == 1, b_mn = transB == 0;
-  CUtensorMap ta, tb, tc;
-  int rc = make_map(&tc, C, M, N, ldc, 32, 32, false, false);     // epilogue box: 32 rows x 32 columns, SWIZZLE_128B
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
-  // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
-  if (pair_enabled() && M > BM && N >= 64 && K >= 256) {
-    // ---- 2-CTA path: 256 x 256 (N > 128) or 256 x 128 pair tiles
-    const int bn2 = N > 128 ? 256 : 128;
-    if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
-    if (rc) return rc;
-    if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, bn2 / 2, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
-    if (rc) return rc;
-    TcParams p;
-    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
-    p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
-    p.out_colsum = out_colsum;
-    p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2); p.kb_total = msx_ceil_div(K, BK);
-    if (splitk > 1) {                         // re-derive the split for pair tiles: about two waves of pairs
-      const int tiles = p.m_tiles * p.n_tiles, pairs = msx_num_sms() / 2;
-      splitk = (2 * pairs) / tiles;
-      if (splitk < 2) splitk = 2;
-    }
-    if (splitk > p.kb_total) splitk = p.kb_total;
-    p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
-    p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
-    if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
-    if (bn2 == 256) {
-      if (!a_mn && !b_mn) return launch_pair<256, false, false>(ta, tb, tc, p, st);
-      if (!a_mn && b_mn) return launch_pair<256, false, true>(ta, tb, tc, p, st);
-      if (a_mn && b_mn) return launch_pair<256, true, true>(ta, tb, tc, p, st);
-    } else {
-      if (!a_mn && !b_mn) return launch_pair<128, false, false>(ta, tb, tc, p, st);
-      if (!a_mn && b_mn) return launch_pair<128, false, true>(ta, tb, tc, p, st);
-      if (a_mn && b_mn) return launch_pair<128, true, true>(ta, tb, tc, p, st);
-    }
-    msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
-    return MSX_ERR_UNSUPPORTED;
-  }
-  if (!a_mn) rc = make_map(&ta, A, M, K, lda, BK, BM, false); else rc = make_map(&ta, A, K, M, lda, 32, BK, true);
-  if (rc) return rc;
-  if (!b_mn) rc = make_map(&tb, B, N, K, ldb, BK, BN, false); else rc = make_map(&tb, B, K, N, ldb, 32, BK, true);
-  if (rc) return rc;
-  TcParams p;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.drop_p = drop_p;
-  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.accumulate = accumulate;
-  p.out_colsum = out_colsum;
-  p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN); p.kb_total = msx_ceil_div(K, BK);
-  if (splitk > p.kb_total) splitk = p.kb_total;
-  p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
-  p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
-  if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
-  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, tc, p, st);
-  if (!a_mn && b_mn) return launch<false, true>(ta, tb, tc, p, st);
-  if (a_mn && b_mn) return launch<true, true>(ta, tb, tc, p, st);
-  msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
-  return MSX_ERR_UNSUPPORTED;
+  return gemm_tc_impl<false>(A, lda, transA, B, ldb, transB, C, ldc, 0, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
+                             0, aux_scale, accumulate, splitk, out_colsum, stream);
+}
+
+// bf16 variant: A and B are bf16 in HBM and feed tcgen05.mma.kind::f16 (fp32 accumulation in TMEM); C is fp32, or bf16
+// (c_bf16, plain store only: accumulation and split-K stay fp32 TMA reduce-adds); the epilogue arithmetic is fp32 and
+// identical to msx_gemm_tc's.  aux (the ReLU mask source) may be fp32 or bf16.
+extern "C" int msx_gemm_tc_bf16(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc,
+                                int c_bf16, int M, int N, int K, const float* bias, int relu, float drop_p,
+                                unsigned long long seed, unsigned site, const void* aux, int ldaux, int aux_bf16,
+                                float aux_scale, int accumulate, int splitk, float* out_colsum, void* stream) {
+  MSX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "msx_gemm_tc_bf16: negative dimension");
+  MSX_REQUIRE(!(out_colsum && (accumulate || splitk > 1)), "msx_gemm_tc_bf16: out_colsum needs a plain (non-accumulating) store");
+  if (M == 0 || N == 0) return MSX_OK;
+  MSX_REQUIRE(A && B && C, "msx_gemm_tc_bf16: null operand");
+  MSX_REQUIRE(K > 0, "msx_gemm_tc_bf16: K must be > 0");
+  MSX_REQUIRE(msx_gemm_tc_bf16_supported(A, lda, B, ldb, C, ldc, c_bf16, M, N, K),
+              "msx_gemm_tc_bf16: operands must be 16-byte aligned, bf16 leading dimensions %% 8 == 0, fp32 ones %% 4 == 0");
+  MSX_REQUIRE(!(transA == 1 && transB == 1), "msx_gemm_tc_bf16: A^T B^T is not used on this path");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc_bf16: dropout probability must be in [0,1)");
+  MSX_REQUIRE(!(splitk > 1 && (bias || relu || drop_p > 0.f || aux || accumulate)),
+              "msx_gemm_tc_bf16: split-K only supports the plain atomic-add epilogue");
+  MSX_REQUIRE(!(c_bf16 && (accumulate || splitk > 1)), "msx_gemm_tc_bf16: a bf16 C takes plain stores only");
+  return gemm_tc_impl<true>(A, lda, transA, B, ldb, transB, C, ldc, c_bf16 ? 1 : 0, M, N, K, bias, relu, drop_p, seed, site,
+                            aux, ldaux, aux_bf16 ? 1 : 0, aux_scale, accumulate, splitk, out_colsum, stream);
 }

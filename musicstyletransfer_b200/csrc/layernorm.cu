@@ -13,6 +13,13 @@
 
 namespace {
 
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  uint2 r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(b), "f"(a));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(d), "f"(c));
+  return r;
+}
+
 constexpr int kMaxPer = 8;      // max groups per lane -> D <= 1024 (vector path), D <= 256 (scalar path)
 constexpr int kWarps = 8;
 
@@ -56,6 +63,7 @@ template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ out,
+                                                                 unsigned short* __restrict__ out16,
                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                  long long M, int D, float eps, float p, float inv_keep,
                                                                  unsigned long long seed, const unsigned long long* seed_ctr,
@@ -98,6 +106,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
         o.z = (s[i][2 % VEC] - mean) * rstd * g.z + b.z;
         o.w = (s[i][3 % VEC] - mean) * rstd * g.w + b.w;
         *reinterpret_cast<float4*>(out + (size_t)row * D + e) = o;
+        if (out16) *reinterpret_cast<uint2*>(out16 + (size_t)row * D + e) = pack4_bf16(o.x, o.y, o.z, o.w);
       } else {
         const int e = i * 32 + lane;
         out[(size_t)row * D + e] = (s[i][0] - mean) * rstd * __ldg(gamma + e) + __ldg(beta + e);
@@ -115,8 +124,8 @@ template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
-    float* __restrict__ dres, float* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed,
+    float* __restrict__ dres, float* __restrict__ dy, unsigned short* __restrict__ dy16, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed,
     const unsigned long long* seed_ctr, unsigned site, int accumulate_dres, int fuse_xy) {
   seed = msx_eff_seed(seed, seed_ctr);
   __shared__ float red[kWarps][32 * VEC + 1];
@@ -182,6 +191,9 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
         if (dy && !fuse_xy)
           *reinterpret_cast<float4*>(dy + o) = make_float4(dyv[0], dyv[1 % VEC], dyv[2 % VEC], dyv[3 % VEC]);
         float4 r4 = make_float4(dr[0], dr[1 % VEC], dr[2 % VEC], dr[3 % VEC]);
+        if (dy16)      // bf16 copy of the gradient of the Dense output y (what its dgrad / wgrad GEMMs read)
+          *reinterpret_cast<uint2*>(dy16 + o) = fuse_xy ? pack4_bf16(r4.x, r4.y, r4.z, r4.w)
+                                                        : pack4_bf16(dyv[0], dyv[1 % VEC], dyv[2 % VEC], dyv[3 % VEC]);
         if (accumulate_dres) {
           const float4 o4 = *reinterpret_cast<const float4*>(dres + o);
           r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
@@ -217,18 +229,21 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
 
 }  // namespace
 
-extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out,
-                              float* mean, float* rstd, long long M, int D, float eps, float drop_p,
-                              unsigned long long seed, unsigned site, void* stream) {
+extern "C" int msx_add_ln_fwd_ex(const float* x, const float* y, const float* gamma, const float* beta, float* out,
+                                 void* out_bf16, float* mean, float* rstd, long long M, int D, float eps, float drop_p,
+                                 unsigned long long seed, unsigned site, void* stream) {
   MSX_REQUIRE(x && y && gamma && beta && out && mean && rstd, "msx_add_ln_fwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_fwd: D must be a multiple of 32");
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_add_ln_fwd: bad dropout");
   if (M == 0) return MSX_OK;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
-  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 &&
+                   ((uintptr_t)out_bf16 & 7) == 0;
+  MSX_REQUIRE(!out_bf16 || vec, "msx_add_ln_fwd: the bf16 output needs D %% 128 == 0 and 16-byte aligned tensors");
+  unsigned short* out16 = reinterpret_cast<unsigned short*>(out_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -243,19 +258,27 @@ extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma
   return MSX_OK;
 }
 
-extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
-                              const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, float* dybias,
-                              long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
-                              void* stream) {
+extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out,
+                              float* mean, float* rstd, long long M, int D, float eps, float drop_p,
+                              unsigned long long seed, unsigned site, void* stream) {
+  return msx_add_ln_fwd_ex(x, y, gamma, beta, out, nullptr, mean, rstd, M, D, eps, drop_p, seed, site, stream);
+}
+
+extern "C" int msx_add_ln_bwd_ex(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+                                 const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta,
+                                 float* dybias, long long M, int D, float drop_p, unsigned long long seed, unsigned site,
+                                 int accumulate_dres, int fuse_xy, void* stream) {
   MSX_REQUIRE(x && y && gamma && mean && rstd && dout && dres && dgamma && dbeta, "msx_add_ln_bwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
   if (M == 0) return MSX_OK;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
-                                       (uintptr_t)gamma) & 15) == 0;
+                                       (uintptr_t)gamma) & 15) == 0 && ((uintptr_t)dy_bf16 & 7) == 0;
+  MSX_REQUIRE(!dy_bf16 || vec, "msx_add_ln_bwd: the bf16 output needs D %% 128 == 0 and 16-byte aligned tensors");
+  unsigned short* dy16 = reinterpret_cast<unsigned short*>(dy_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
     const int nper = D / 128;
@@ -268,4 +291,12 @@ extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma
 #undef LN_BWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
+}
+
+extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+                              const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, float* dybias,
+                              long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
+                              void* stream) {
+  return msx_add_ln_bwd_ex(x, y, gamma, mean, rstd, dout, dres, dy, nullptr, dgamma, dbeta, dybias, M, D, drop_p, seed, site,
+                           accumulate_dres, fuse_xy, stream);
 }

@@ -48,3 +48,39 @@ extern "C" int msx_step_counter_tick(unsigned long long* dev_counter, void* stre
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
+
+// ---- fp32 -> bf16 cast (operands of the bf16 GEMM variant)
+static __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, unsigned* __restrict__ dst,
+                                                                    long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+      uint4 o;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
+      *reinterpret_cast<uint4*>(dst + i / 2) = o;
+    } else {
+      unsigned short* d16 = reinterpret_cast<unsigned short*>(dst);
+      for (long long j = i; j < n; ++j) {
+        unsigned r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(src[j]));
+        d16[j] = (unsigned short)(r & 0xFFFFu);
+      }
+    }
+  }
+}
+
+extern "C" int msx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  MSX_REQUIRE(n >= 0, "msx_cast_f32_bf16: negative length");
+  if (n == 0) return MSX_OK;
+  MSX_REQUIRE(src && dst, "msx_cast_f32_bf16: null pointer");
+  MSX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "msx_cast_f32_bf16: pointers must be 16-byte aligned");
+  const long long want = (n + 8 * 256 - 1) / (8 * 256);
+  const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
+  cast_f32_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<unsigned*>(dst), n);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

@@ -39,6 +39,32 @@ def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=Fa
              tag=_gemm_tag(M, N, K, accumulate, aux))
 
 
+def gemm_tc_bf16(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
+                 aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None):
+    """bf16 variant: A, B torch.bfloat16; Cm fp32 or bfloat16 (plain stores only); aux fp32 or bfloat16."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16, (A.dtype, B.dtype)
+    c16 = Cm.dtype == torch.bfloat16
+    a16 = aux is not None and aux.dtype == torch.bfloat16
+    flops = 2.0 * M * N * K
+    nbytes = 2.0 * (M * K + N * K) + M * N * ((2 if c16 else 4) * (1 + (1 if accumulate else 0)) +
+                                              ((2 if a16 else 4) if aux is not None else 0))
+    lib.call("msx_gemm_tc_bf16", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(1 if c16 else 0),
+             _i(M), _i(N), _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
+             _i(1 if a16 else 0), _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
+             tag=(flops, nbytes))
+
+
+def gemm_tc_bf16_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
+    return bool(lib.load().msx_gemm_tc_bf16_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc),
+                                                      _i(1 if Cm.dtype == torch.bfloat16 else 0), _i(M), _i(N), _i(K)))
+
+
+def cast_bf16(src, dst, n=None):
+    """dst (bfloat16) = src (fp32), round to nearest even."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16
+    lib.call("msx_cast_f32_bf16", P(src), P(dst), _ll(src.numel() if n is None else n), lib.stream_ptr())
+
+
 def gemm_tc_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
     return bool(lib.load().msx_gemm_tc_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
 

@@ -154,3 +154,102 @@ def test_tc_epilogue_out_colsum(impl):
     want = (_ref(Av, Bv, 0, 0) * (aux[:, :N].cpu() > 0).double() * 1.25).sum(0)
     assert float((cs.double().cpu() - want).abs().max()) / float(want.abs().max()) < 3e-3
     assert float((cs.double().cpu() - C[:, :N].double().cpu().sum(0)).abs().max()) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ bf16 variant
+def _mk16(rows, cols, ld, seed):
+    """bf16 operand made on the device by msx_cast_f32_bf16 + the exactly representable values the GEMM will see."""
+    from musicstyletransfer_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    buf = torch.randn(rows, ld, generator=g).cuda()
+    b16 = torch.empty((rows, ld), dtype=torch.bfloat16, device="cuda")
+    ops.cast_bf16(buf, b16)
+    torch.cuda.synchronize()
+    assert bool((b16 == buf.to(torch.bfloat16)).all())          # the cast kernel rounds to nearest even
+    return b16, b16[:, :cols].float()
+
+
+@pytest.mark.parametrize("impl", ["tc1", "tc2"])
+@pytest.mark.parametrize("c16", [False, True])
+@pytest.mark.parametrize("mode", ["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("M,N,K", CASES)
+def test_gemm_bf16_modes(impl, c16, mode, M, N, K):
+    """bf16 operands are exact inputs; products are exact in fp32, so only the accumulation order differs from the
+    float64 host product: fp32 C agrees to ~1e-5, a bf16 C to its own rounding (2^-8 relative per element)."""
+    from musicstyletransfer_b200 import ops
+    ops.gemm_tc_set_pair(impl == "tc2")
+    pad = lambda n: (n + 7) // 8 * 8 + 8
+    if mode == "fwd":
+        transA, transB = 0, 1
+        Ad, Av = _mk16(M, K, pad(K), 1)
+        Bd, Bv = _mk16(N, K, pad(K), 2)
+    elif mode == "dgrad":
+        transA, transB = 0, 0
+        Ad, Av = _mk16(M, K, pad(K), 1)
+        Bd, Bv = _mk16(K, N, pad(N), 2)
+    else:
+        transA, transB = 1, 0
+        Ad, Av = _mk16(K, M, pad(M), 1)
+        Bd, Bv = _mk16(K, N, pad(N), 2)
+    ldc = pad(N)
+    want = _ref(Av, Bv, transA, transB)
+    C = torch.full((M, ldc), 7.0, device="cuda", dtype=torch.bfloat16 if c16 else torch.float32)
+    ops.gemm_tc_bf16(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C, ldc, M, N, K)
+    torch.cuda.synchronize()
+    got = C[:, :N].double().cpu()
+    scale = float(want.abs().max()) + 1e-9
+    err = float((got - want).abs().max()) / scale
+    assert err < (5e-3 if c16 else 2e-5), (impl, c16, mode, M, N, K, err)
+    first_safe = (N + 7) // 8 * 8 if c16 else (N + 3) // 4 * 4
+    assert float((C[:, first_safe:].float() - 7.0).abs().max()) == 0.0
+    if not c16:
+        C2 = torch.zeros((M, ldc), device="cuda")
+        ops.gemm_tc_bf16(Ad, Ad.shape[1], transA, Bd, Bd.shape[1], transB, C2, ldc, M, N, K, splitk=3)
+        torch.cuda.synchronize()
+        err = float((C2[:, :N].double().cpu() - want).abs().max()) / scale
+        assert err < 2e-5, ("splitk", impl, mode, err)
+
+
+@pytest.mark.parametrize("impl", ["tc1", "tc2"])
+def test_gemm_bf16_epilogues(impl):
+    from musicstyletransfer_b200 import ops
+    ops.gemm_tc_set_pair(impl == "tc2")
+    M, N, K = 333, 293, 256
+    ldc = 296
+    Ad, Av = _mk16(M, K, K, 3)
+    Bd, Bv = _mk16(N, K, K, 4)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(5)).cuda()
+    want = _ref(Av, Bv, 0, 1) + bias.double().cpu()
+    scale = float(want.abs().max())
+    # bias + relu into a bf16 C (the FF hidden activation of the bf16 step)
+    C = torch.zeros((M, ldc), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tc_bf16(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, bias=bias, relu=True)
+    assert float((C[:, :N].double().cpu() - want.clamp(min=0)).abs().max()) / scale < 5e-3
+    # fp32 accumulate
+    C0 = torch.randn(M, ldc, generator=torch.Generator().manual_seed(6)).cuda()
+    Cf = C0.clone()
+    ops.gemm_tc_bf16(Ad, K, 0, Bd, K, 1, Cf, ldc, M, N, K, bias=bias, accumulate=True)
+    assert float((Cf[:, :N].double().cpu() - (want + C0[:, :N].double().cpu())).abs().max()) / scale < 2e-5
+    # bf16 aux mask (relu' * scale) + column sums of what is written, bf16 C
+    aux32 = torch.randn(M, ldc, generator=torch.Generator().manual_seed(7)).cuda().clamp(min=0)
+    aux = aux32.to(torch.bfloat16)
+    for cdt in (torch.float32, torch.bfloat16):
+        C = torch.zeros((M, ldc), device="cuda", dtype=cdt)
+        cs = torch.zeros(N, device="cuda")
+        ops.gemm_tc_bf16(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, aux=aux, ldaux=ldc, aux_scale=1.25, out_colsum=cs)
+        w2 = _ref(Av, Bv, 0, 1) * (aux[:, :N].float().cpu() > 0).double() * 1.25
+        assert float((C[:, :N].double().cpu() - w2).abs().max()) / scale < (5e-3 if cdt == torch.bfloat16 else 2e-5)
+        assert float((cs.double().cpu() - w2.sum(0)).abs().max()) / float(w2.sum(0).abs().max()) < 1e-4
+    # fp32 aux with a bf16 GEMM, unaligned tail columns (N = 293 is not a multiple of 32)
+    C = torch.zeros((M, ldc), device="cuda")
+    ops.gemm_tc_bf16(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, aux=aux32, ldaux=ldc, aux_scale=2.0)
+    w3 = _ref(Av, Bv, 0, 1) * (aux32[:, :N].cpu() > 0).double() * 2.0
+    assert float((C[:, :N].double().cpu() - w3).abs().max()) / scale < 2e-5
+    # dropout: same counter-hash mask as the fp32-operand kernels for (seed, site, element)
+    C = torch.zeros((M, ldc), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tc_bf16(Ad, K, 0, Bd, K, 1, C, ldc, M, N, K, bias=bias, drop_p=0.25, seed=1234, site=3)
+    Af, Bf = Ad.float().contiguous(), Bd.float().contiguous()
+    Cs = torch.zeros((M, ldc), device="cuda")
+    ops.gemm(Af, K, 0, Bf, K, 1, Cs, ldc, M, N, K, bias=bias, drop_p=0.25, seed=1234, site=3)
+    torch.cuda.synchronize()
+    assert float((C[:, :N].float() - Cs[:, :N]).abs().max()) / scale < 8e-3
