@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
     ap.add_argument("--dropout", type=float, default=0.2)
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
-                    help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation)")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
+                    help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation), bf16 = "
+                         "the tf32 path with the Transformer layers' GEMM operands stored as bfloat16 (BASELINE config 4)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="rows per oracle step (bounded CPU sample)")
     ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
                     help="train: the contract line (default); sweep: BASELINE config 3 batch / sequence-length sweep, one JSON "
@@ -62,9 +63,12 @@ def parse_args():
 
 
 def workload_name(args):
-    return ("VarAutoEncoder train step (fwd+bwd+Adam) fp32 storage, GEMMs %s, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
+    return ("VarAutoEncoder train step (fwd+bwd+Adam) %s, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
             "dec %s 1x128, dropout %.1f, B=%d per GPU, L=%d (T=%d), synthetic 4/4 token rows"
-            % ({"fp32": "fp32 FFMA", "tf32": "tcgen05 TF32 (fp32 accumulate)"}[args.precision], args.dec_type, args.dropout,
+            % ({"fp32": "fp32 storage, GEMMs fp32 FFMA", "tf32": "fp32 storage, GEMMs tcgen05 TF32 (fp32 accumulate)",
+                "bf16": "fp32 master weights / residual stream / LN / softmax / losses / Adam, Transformer-layer GEMM operands "
+                        "bf16 in HBM on tcgen05 kind::f16 (fp32 accumulate), other GEMMs TF32"}[args.precision],
+               args.dec_type, args.dropout,
                args.batch, args.seq_len, args.seq_len + 1))
 
 
@@ -358,8 +362,10 @@ def run_ours(args):
         n_launch = max(1, len(prof["events"]))
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
         gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9
-        kname = ("gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)"
-                 if args.precision == "tf32" else "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)")
+        kname = {"tf32": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)",
+                 "bf16": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc_bf16: tcgen05 kind::f16 bf16 operands; kind::tf32 for the "
+                         "decoder / latent GEMMs; cta_group::2 pair tiles, TMA)",
+                 "fp32": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)"}[args.precision]
         # fp32-in / fp32-out GEMMs with K, N <= 1024: 64-102 flop per algorithmic byte, below the TF32 ridge point
         # (~700 TFLOP/s / 6.55 TB/s = 107 flop/B), so the bounding resource is HBM
         traffic = None
@@ -397,7 +403,7 @@ def run_ours(args):
                "ms_per_step": per_step * 1e3}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange,
                    "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
@@ -481,7 +487,7 @@ def run_style(args):
     sec = (time.perf_counter() - t0) / reps
     line = {"metric": "style_transfer_sequences_per_sec", "value": B * cfg.num_classes / sec, "unit": "sequences/s",
             "tokens_per_s": B * ntok / sec, "ms_per_pass": sec * 1e3, "n_gpus": 1, "higher_is_better": True,
-            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "style transfer: %d rows x %d classes, L=%d, decoder %s, up to 2T=%d sampled steps per class; "
                                    "wall clock including the host-side stop test" % (B, cfg.num_classes, L, args.dec_type, 2 * (L + 1))}}
     if not args.no_cpu_baseline:

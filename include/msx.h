@@ -108,6 +108,11 @@ int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx,
                          int T, int H, int dh, void* stream);
 /* Profiling hook for the pipelined tensor-core backward: device buffer of 2 x 16 x 9 int64 clock64 stamps (block 0,
  * per pipeline group, first 16 items); NULL disables. */
+/* bf16 variant: ctx (forward) / dqkv (backward) are written as bfloat16 when the flag is set (same element layout). */
+int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H, int dh,
+                            void* stream);
+int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
+                            int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);   /* dbias (optional) [3*H*dh] += column sums of dqkv */
 
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
@@ -121,6 +126,17 @@ int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const flo
                    int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
                    void* stream);   /* dybias (optional) [D] += column sums of the y-gradient */
 
+/* bf16 variant: the same kernels with an additional bfloat16 copy of the output that the bf16 GEMMs read
+ * (out_bf16: LN output; dy_bf16: gradient of the Dense output y, or the combined gradient under fuse_xy).  Either may be
+ * NULL; dy may be NULL when only the bf16 gradient is wanted.  Needs D % 128 == 0. */
+int msx_add_ln_fwd_ex(const float* x, const float* y, const float* gamma, const float* beta, float* out, void* out_bf16,
+                      float* mean, float* rstd, long long M, int D, float eps, float drop_p, unsigned long long seed,
+                      unsigned site, void* stream);
+int msx_add_ln_bwd_ex(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+                      const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta, float* dybias,
+                      long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres,
+                      int fuse_xy, void* stream);
+
 /* K2a — embedding front end.  Replaces model.py:81-91 + transformer.py:270 (encoder), model.py:241-247 +
  * transformer.py:237 (Transformer decoder, prefix = 1 latent-state row), model.py:176 (LSTM decoder).
  * out[b,pos,:] = scale*((pos<prefix ? prefix_vec[b] : tok_emb[tokens[b,pos-prefix]]) + cls_emb[classes[b]]) + pe[pos];
@@ -128,6 +144,10 @@ int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const flo
 int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
                   const float* cls_emb, const float* prefix_vec, const float* pe, float* out, float* mask, int B, int T,
                   int D, int prefix, float scale, int vocab, void* stream);
+/* bf16 variant: also (out may be NULL: only) writes a bfloat16 copy of the rows. */
+int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
+                     const float* cls_emb, const float* prefix_vec, const float* pe, float* out, void* out_bf16, float* mask,
+                     int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                   float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 

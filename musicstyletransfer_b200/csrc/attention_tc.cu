@@ -122,6 +122,27 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// one 32-element head row of an output tensor: fp32 (128 B, eight float4) or bf16 (64 B, four uint4); `elem` is the
+// element offset of the row start, the same in both storage types
+__device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, const float* o) {
+  if (bf16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(base) + elem);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(o[8 * j + 1]), "f"(o[8 * j + 0]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(o[8 * j + 3]), "f"(o[8 * j + 2]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.z) : "f"(o[8 * j + 5]), "f"(o[8 * j + 4]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.w) : "f"(o[8 * j + 7]), "f"(o[8 * j + 6]));
+      dst[j] = w;
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+}
+
 // MN-major operand, SWIZZLE_128B_BASE32B: element (mn, k) of a slab-structured tile with `krows` rows per slab
 __device__ __forceinline__ unsigned mn_major_off(int mn, int k, int krows) {
   return (unsigned)((mn >> 5) * (krows * 128) + k * 128 + ((((mn & 31) >> 3) ^ (k & 3)) << 5) + ((mn & 7) << 2));
@@ -129,7 +150,8 @@ __device__ __forceinline__ unsigned mn_major_off(int mn, int k, int krows) {
 
 struct AttnTcParams {
   const float* mask;   // [B*T]
-  float* ctx;          // [B*T, H*32]
+  float* ctx;          // [B*T, H*32] fp32, or bf16 when out_bf16 (the operand of the bf16 W_proj GEMM)
+  int out_bf16;
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
   int items;           // B * H
   int group_bytes;     // shared memory of one pipeline group
@@ -352,11 +374,7 @@ __global__ void __launch_bounds__(128 * G, 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[j] += o2[j];
       }
-      if (q < T) {
-        float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)b * T + q) * D + h * DH);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      }
+      if (q < T) store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
   }
@@ -375,7 +393,8 @@ __global__ void __launch_bounds__(128 * G, 1)
 // dQ = dS^T K (lanes = queries).  The K-major operand tiles of the first two MMAs are dead by then and X aliases them.
 struct AttnTcBwdParams {
   const float* mask;   // [B*T]
-  float* dqkv;         // [B*T, 3*H*32]
+  float* dqkv;         // [B*T, 3*H*32] fp32, or bf16 when out_bf16 (operand of the bf16 K|Q|V dgrad / wgrad GEMMs)
+  int out_bf16;
   float* dbias;        // optional [3*H*32]: += column sums of dqkv (bias gradient of the fused K|Q|V projection)
   int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
   float inv_scale;
@@ -534,17 +553,13 @@ __global__ void __launch_bounds__(128)
   {
     // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
     float o[32];
-    float* rowp = p.dqkv + ((size_t)b * T + tid) * 3 * D + h * DH;
+    const size_t row_elem = ((size_t)b * T + tid) * 3 * D + h * DH;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
       const unsigned src = m == 0 ? tm_dK : m == 1 ? tm_dQ : tm_dV;
       tmem_ld16(src + lane_off, o);
       tmem_ld16(src + lane_off + 16, o + 16);
-      if (tid < T) {
-        float4* dst = reinterpret_cast<float4*>(rowp + m * D);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      }
+      if (tid < T) store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o);
       if (p.dbias) {
         if (tid >= T) {
 #pragma unroll
@@ -827,7 +842,7 @@ __global__ void __launch_bounds__(256, 1)
     if (gt == 0) MSX_STAMP(7);
     if (warp_live) {
       // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
-      float* rowp = p.dqkv + ((size_t)b * T + gt) * 3 * D + h * DH;
+      const size_t row_elem = ((size_t)b * T + gt) * 3 * D + h * DH;
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         float o[32];
@@ -837,9 +852,7 @@ __global__ void __launch_bounds__(256, 1)
         tmem_ld16_wait(o);
         tmem_ld16_wait(o + 16);
         if (gt < T) {
-          float4* dst = reinterpret_cast<float4*>(rowp + m * D);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o);
           if (p.dbias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[m * 32 + j] += o[j];
@@ -910,14 +923,22 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
 }
 }  // namespace
 
+extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
+                                       int dh, void* stream);
 extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
                                     void* stream) {
+  return msx_attention_tc_fwd_ex(qkv, mask, ctx, 0, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
+                                       int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
+  MSX_REQUIRE(((uintptr_t)ctx & 15) == 0, "msx_attention_tc_fwd: ctx must be 16-byte aligned");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnTcParams p;
-  p.mask = mask; p.ctx = ctx; p.T = T; p.H = H;
+  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.items = B * H;
@@ -952,15 +973,23 @@ extern "C" int msx_attention_tc_set_trace(long long* buf) {
   return MSX_OK;
 }
 
+extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
+                                       float* dbias, int B, int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias,
                                     int B, int T, int H, int dh, void* stream) {
+  return msx_attention_tc_bwd_ex(qkv, mask, dctx, dqkv, 0, dbias, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
+                                       float* dbias, int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_tc_bwd: null pointer");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
               "msx_attention_tc_bwd: needs d_h == 32, T <= 128, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnTcBwdParams p;
-  p.mask = mask; p.dqkv = dqkv; p.dbias = dbias; p.T = T; p.H = H; p.trace = g_attn_trace;
+  p.mask = mask; p.dqkv = reinterpret_cast<float*>(dqkv); p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias; p.T = T; p.H = H;
+  p.trace = g_attn_trace;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.inv_scale = 1.f / sqrtf((float)DH);

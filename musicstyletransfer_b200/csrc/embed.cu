@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
                                                         const float* __restrict__ cls_emb,
                                                         const float* __restrict__ prefix_vec,
                                                         const float* __restrict__ pe, float* __restrict__ out,
+                                                        unsigned short* __restrict__ out16,
                                                         float* __restrict__ mask, int B, int T, int D, int prefix,
                                                         float scale, int vocab) {
   const int TP = T + prefix;
@@ -37,13 +38,19 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
   }
   const float* cls = cls_emb ? cls_emb + (size_t)__ldg(classes + b) * D : nullptr;
   const float* pr = pe ? pe + (size_t)pos * D : nullptr;
-  float* dst = out + (size_t)row * D;
+  float* dst = out ? out + (size_t)row * D : nullptr;
+  unsigned short* dst16 = out16 ? out16 + (size_t)row * D : nullptr;
   for (int e = lane; e < D; e += 32) {
     float v = __ldg(src + e);
     if (cls) v += __ldg(cls + e);
     v *= scale;
     if (pr) v += __ldg(pr + e);
-    dst[e] = v;
+    if (dst) dst[e] = v;
+    if (dst16) {                            // bf16 copy (round to nearest even): operand of the bf16 GEMM variant
+      unsigned r;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+      dst16[e] = (unsigned short)(r & 0xFFFFu);
+    }
   }
   if (mask && lane == 0) {
     // encoder: tokens != 0 (model.py:81-83); decoder: position < seq_len + 1 (model.py:246-247)
@@ -78,18 +85,32 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ 
 
 }  // namespace
 
+extern "C" int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
+                                const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
+                                float* out, void* out_bf16, float* mask, int B, int T, int D, int prefix, float scale,
+                                int vocab, void* stream);
 extern "C" int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
                              const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
                              float* out, float* mask, int B, int T, int D, int prefix, float scale, int vocab,
                              void* stream) {
-  MSX_REQUIRE(tokens && tok_emb && out, "msx_embed_fwd: null pointer");
+  MSX_REQUIRE(out, "msx_embed_fwd: null pointer");
+  return msx_embed_fwd_ex(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, nullptr, mask, B, T, D, prefix,
+                          scale, vocab, stream);
+}
+
+extern "C" int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
+                                const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
+                                float* out, void* out_bf16, float* mask, int B, int T, int D, int prefix, float scale,
+                                int vocab, void* stream) {
+  MSX_REQUIRE(tokens && tok_emb && (out || out_bf16), "msx_embed_fwd: null pointer");
   MSX_REQUIRE(prefix == 0 || prefix_vec, "msx_embed_fwd: prefix rows need prefix_vec");
   MSX_REQUIRE(!cls_emb || classes, "msx_embed_fwd: class embedding needs classes");
   if (B == 0 || T + prefix == 0) return MSX_OK;
   const long long rows = (long long)B * (T + prefix);
   const int wpb = 8;
   embed_fwd_kernel<<<msx_ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab);
+      tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, reinterpret_cast<unsigned short*>(out_bf16), mask, B, T,
+      D, prefix, scale, vocab);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

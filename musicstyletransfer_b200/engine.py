@@ -95,7 +95,7 @@ class ParamArena:
         for name, shape in self.entries:
             n = int(np.prod(shape))
             self.offsets[name] = (off, n, shape)
-            off += (n + 3) // 4 * 4
+            off += (n + 7) // 8 * 8          # 32-byte aligned fp32 tensors = 16-byte aligned bf16 shadows (TMA bases)
         self.numel = off
         self.n_params = sum(n for _, n, _ in self.offsets.values())
         self.w = torch.zeros(off, dtype=torch.float32, device=device)
@@ -103,6 +103,23 @@ class ParamArena:
         self.m = torch.zeros(off, dtype=torch.float32, device=device)
         self.v = torch.zeros(off, dtype=torch.float32, device=device)
         self.adam_state = torch.zeros(4, dtype=torch.float32, device=device)   # [t, lr_t, -, -]
+        self.w16 = None                      # bf16 shadow of w at the same element offsets (precision="bf16" only)
+
+    def enable_bf16_shadow(self):
+        if self.w16 is None:
+            self.w16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.w.device)
+
+    def refresh_bf16_shadow(self):
+        ops.cast_bf16(self.w, self.w16, self.numel)
+
+    def view16(self, name):
+        off, n, shape = self.offsets[name]
+        return self.w16[off:off + n].view(shape)
+
+    def span16(self, first, last):
+        a = self.offsets[first][0]
+        off, n, _ = self.offsets[last]
+        return self.w16[a:off + n]
 
     def view(self, name, arena=None):
         off, n, shape = self.offsets[name]
@@ -160,13 +177,20 @@ class _Buffers:
 class VAEEngine:
     def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024, precision="fp32"):
         """precision: "fp32" = exact FFMA GEMMs (msx_gemm_f32); "tf32" = tcgen05 tensor-core GEMMs with TF32
-        operands and fp32 accumulation (msx_gemm_tc).  Everything outside the GEMMs is fp32 in both modes."""
-        assert precision in ("fp32", "tf32")
+        operands and fp32 accumulation (msx_gemm_tc); "bf16" = the tf32 path with the Transformer layers' GEMM operands
+        (activations, their gradients and a shadow copy of the weights) stored as bfloat16 in HBM and multiplied by
+        tcgen05 kind::f16 (msx_gemm_tc_bf16), fp32 accumulation.  Softmax, LayerNorm, residuals, losses, the LSTM
+        recurrence, master weights, gradients and Adam are fp32 in every mode."""
+        assert precision in ("fp32", "tf32", "bf16")
         self.precision = precision
+        self.tensor = precision in ("tf32", "bf16")      # tcgen05 / mma.sync kernels (vs the exact FFMA ones)
+        self.bf16 = precision == "bf16"
         self.cfg = cfg
         self.device = torch.device(device)
         self.arena = ParamArena(cfg, self.device)
         self.arena.init_xavier(seed)
+        if self.bf16:
+            self.arena.enable_bf16_shadow()
         self.pe_enc = torch.from_numpy(positional_encodings(cfg.enc_size, max_len)).to(self.device)
         self.pe_dec = (torch.from_numpy(positional_encodings(cfg.dec_size, max_len)).to(self.device)
                        if cfg.dec_type == "transformer" else None)
@@ -204,10 +228,10 @@ class VAEEngine:
 
     def _lstm_tc(self, Hd, tv):
         """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers) in the tf32 precision mode, H = 128."""
-        return self.precision == "tf32" and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
+        return self.tensor and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
 
     def _use_tc(self, A, lda, B, ldb, C, ldc, M, N, K):
-        return self.precision == "tf32" and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
+        return self.tensor and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
                    accumulate_dx=False, dx_colsum=None):
@@ -242,7 +266,7 @@ class VAEEngine:
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
         ctx = bf.get(tag + "ctx", (M, D), dev)
-        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
+        if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H)
         else:
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
@@ -313,12 +337,118 @@ class VAEEngine:
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
-        if self.precision == "tf32" and ops.attention_tc_supported(qkv, T, D // H):
+        if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv)
             gbqkv = None
         else:
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
         self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
+
+    # ------------------------------------------------------------------ transformer layer, bf16 variant
+    def _layer16_ok(self, D):
+        """bf16 GEMM operands need 16-byte aligned rows (D % 8) and the vectorised LayerNorm path (D % 128)."""
+        return self.bf16 and D % 128 == 0
+
+    def _tf_layer_fwd16(self, bf, tag, prefix, x_in, x_in16, mask, B, T, D, H, p, site0, decoder):
+        """_tf_layer_fwd with bf16 GEMM operands: x_in16 / ctx / x1 / the FF hidden activation are read by the GEMMs as
+        bfloat16 (the hidden activation and the context exist only in bf16), weights come from the bf16 shadow arena;
+        qkv, the projection output, f and the LayerNorm arithmetic stay fp32.  Returns (out fp32, out bf16)."""
+        M = B * T
+        dev, a, b16 = self.device, self.arena, torch.bfloat16
+        seed = self.dropout_seed
+        qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
+        wqkv = a.span16(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
+        bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
+        ops.gemm_tc_bf16(x_in16, D, 0, wqkv, D, 1, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
+        ctx16 = bf.get(tag + "ctx16", (M, D), dev, b16)
+        if ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H)
+        else:                                           # T > 128: FFMA attention in fp32, then one cast
+            ctx = bf.get(tag + "ctx", (M, D), dev)
+            ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
+            ops.cast_bf16(ctx, ctx16)
+        proj = bf.get(tag + "proj", (M, D), dev)
+        ops.gemm_tc_bf16(ctx16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 1, proj, D, M, D, D,
+                         bias=self._W(prefix + "self_attention.W_proj.bias"))
+        x1 = bf.get(tag + "x1", (M, D), dev)
+        x1h = bf.get(tag + "x1_16", (M, D), dev, b16)
+        st1 = bf.get(tag + "st1", (2, M), dev)
+        ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
+                       drop_p=p, seed=seed, site=site0, out16=x1h)
+        h16 = bf.get(tag + "h16", (M, 4 * D), dev, b16)
+        ops.gemm_tc_bf16(x1h, D, 0, a.view16(prefix + "ff.ff1.weight"), D, 1, h16, 4 * D, M, 4 * D, D,
+                         bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1)
+        f = bf.get(tag + "f", (M, D), dev)
+        ops.gemm_tc_bf16(h16, 4 * D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 1, f, D, M, D, 4 * D,
+                         bias=self._W(prefix + "ff.ff2.bias"))
+        out = bf.get(tag + "out", (M, D), dev)
+        out16 = bf.get(tag + "out16", (M, D), dev, b16)
+        st2 = bf.get(tag + "st2", (2, M), dev)
+        ln2 = "ln3" if decoder else "ln2"
+        ops.add_ln_fwd(f if decoder else x1, f, self._W(prefix + ln2 + ".gamma"), self._W(prefix + ln2 + ".beta"), out,
+                       st2[0], st2[1], M, D, drop_p=p, seed=seed, site=site0 + 2, out16=out16)
+        return out, out16
+
+    def _wgrad16(self, dy16, lddy, x16, ldx, gw, N, K, M):
+        """gw [N,K] += dy16[M,N]^T x16[M,K] (bf16 operands, fp32 split-K reduce-adds into the gradient arena)."""
+        sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
+        ops.gemm_tc_bf16(dy16, lddy, 1, x16, ldx, 0, gw, K, N, K, M, splitk=sk)
+
+    def _tf_layer_bwd16(self, bf, tag, prefix, x_in, x_in16, mask, dout, dx_in, B, T, D, H, p, site0, decoder):
+        """Backward of _tf_layer_fwd16.  Every gradient that only feeds GEMMs (d f, d hidden, d proj, d qkv) is produced
+        directly as bfloat16 by the kernel that computes it (LayerNorm backward, dgrad epilogue, attention backward);
+        the residual-stream gradients and all parameter gradients are fp32."""
+        M = B * T
+        dev, a, b16, f32 = self.device, self.arena, torch.bfloat16, torch.float32
+        seed = self.dropout_seed
+        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj", (M, D), f32)]
+        ctx16 = bf.t[(tag + "ctx16", (M, D), b16)]
+        x1, x1h = bf.t[(tag + "x1", (M, D), f32)], bf.t[(tag + "x1_16", (M, D), b16)]
+        st1, st2 = bf.t[(tag + "st1", (2, M), f32)], bf.t[(tag + "st2", (2, M), f32)]
+        h16, f = bf.t[(tag + "h16", (M, 4 * D), b16)], bf.t[(tag + "f", (M, D), f32)]
+        inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
+        ln2 = "ln3" if decoder else "ln2"
+        dx1 = bf.get(tag + "dx1", (M, D), dev)
+        df16 = bf.get(tag + "df16", (M, D), dev, b16)
+        if decoder:
+            dfull = bf.get(tag + "df", (M, D), dev)
+            ops.add_ln_bwd(f, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dfull, None,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p, seed=seed,
+                           site=site0 + 2, fuse_xy=True, dybias=self._G(prefix + "ff.ff2.bias"), dy16=df16)
+        else:
+            ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, None,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p, seed=seed,
+                           site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"), dy16=df16)
+        # ff2: f = h W2^T + b2
+        self._wgrad16(df16, D, h16, 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, M)
+        dh16 = bf.get(tag + "dh16", (M, 4 * D), dev, b16)
+        ops.gemm_tc_bf16(df16, D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 0, dh16, 4 * D, M, 4 * D, D, aux=h16,
+                         ldaux=4 * D, aux_scale=inv_keep, out_colsum=self._G(prefix + "ff.ff1.bias"))
+        # ff1: h = drop(relu(x1 W1^T + b1)); dh16 holds d(pre-activation)
+        self._wgrad16(dh16, 4 * D, x1h, D, self._G(prefix + "ff.ff1.weight"), 4 * D, D, M)
+        ops.gemm_tc_bf16(dh16, 4 * D, 0, a.view16(prefix + "ff.ff1.weight"), D, 0, dx1, D, M, D, 4 * D,
+                         accumulate=not decoder)
+        # ln1(x_in + drop(proj))
+        dproj16 = bf.get(tag + "dproj16", (M, D), dev, b16)
+        ops.add_ln_bwd(x_in, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dx_in, None,
+                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), M, D, drop_p=p, seed=seed, site=site0,
+                       dybias=self._G(prefix + "self_attention.W_proj.bias"), dy16=dproj16)
+        self._wgrad16(dproj16, D, ctx16, D, self._G(prefix + "self_attention.W_proj.weight"), D, D, M)
+        dctx = bf.get(tag + "dctx", (M, D), dev)
+        ops.gemm_tc_bf16(dproj16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 0, dctx, D, M, D, D)
+        dqkv16 = bf.get(tag + "dqkv16", (M, 3 * D), dev, b16)
+        gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
+        if ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_bwd(qkv, mask, dctx, dqkv16, B, T, H, D // H, dbias=gbqkv)
+        else:
+            dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
+            ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
+            ops.colsum(dqkv, 3 * D, M, 3 * D, gbqkv)
+            ops.cast_bf16(dqkv, dqkv16)
+        gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
+        self._wgrad16(dqkv16, 3 * D, x_in16, D, gwqkv, 3 * D, D, M)
+        wqkv = a.span16(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
+        ops.gemm_tc_bf16(dqkv16, 3 * D, 0, wqkv, D, 0, dx_in, D, M, D, 3 * D, accumulate=True)
 
     # ------------------------------------------------------------------ encoder
     def _encode(self, bf, tokens, classes, B, T, p_drop):
@@ -328,12 +458,23 @@ class VAEEngine:
         M = B * T
         x = bf.get("enc.x0", (M, D), dev)
         mask = bf.get("enc.mask", (M,), dev)
+        l16 = self._layer16_ok(D)
+        x16 = bf.get("enc.x0_16", (M, D), dev, torch.bfloat16) if l16 else None
+        if l16:
+            self.arena.refresh_bf16_shadow()          # 8 MB read + 4 MB written per step; always current, also under graphs
         ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
-                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V)
+                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V,
+                      out16=x16)
         xs = [x]
+        self._xs16 = [x16]
         for l in range(cfg.enc_layers):
-            x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
-                                   p_drop, l * SITE_STRIDE, False)
+            if l16:
+                x, x16 = self._tf_layer_fwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
+                                              cfg.enc_heads, p_drop, l * SITE_STRIDE, False)
+                self._xs16.append(x16)
+            else:
+                x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
+                                       p_drop, l * SITE_STRIDE, False)
             xs.append(x)
         lat = bf.get("lat", (B, 2 * Z), dev)
         self._dense_fwd(x, T * D, B, "encoder.latent_proj.weight", "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
@@ -615,7 +756,7 @@ class VAEEngine:
             out["probs"] = probs[:, 1:, :] if cfg.dec_type == "transformer" else probs
         self.ctx = dict(B=B, T=T, Td=Td, tokens=tokens, seq_lens=seq_lens, classes=classes, labels=lab_full, eps=eps,
                         xs=xs, mask=mask, lat=lat, z=z, dec_out=dec_out, logits=logits, pe=pe_, pd=pd_, bf=bf,
-                        dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None)
+                        dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None, xs16=self._xs16)
         return out
 
     # ------------------------------------------------------------------ backward
@@ -685,8 +826,12 @@ class VAEEngine:
                         dx=dx, lddx=T * D)
         for l in reversed(range(cfg.enc_layers)):
             dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
-            self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
-                               cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+            if self._layer16_ok(D):
+                self._tf_layer_bwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["xs16"][l], c["mask"], dx,
+                                     dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+            else:
+                self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
+                                   cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
             dx = dnext
         ops.embed_bwd(c["tokens"], c["classes"], dx, self._G("encoder.encoder_embedding.weight"),
                       self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)

@@ -102,33 +102,39 @@ def attention_tc_supported(qkv, T, dh):
 
 
 def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh):
-    lib.call("msx_attention_tc_fwd", P(qkv), P(mask), P(ctx), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+    """ctx: fp32, or bfloat16 (bf16 variant: the context only feeds the W_proj GEMMs)."""
+    lib.call("msx_attention_tc_fwd_ex", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), _i(B), _i(T),
+             _i(H), _i(dh), lib.stream_ptr())
 
 
 def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):
-    lib.call("msx_attention_tc_bwd", P(qkv), P(mask), P(dctx), P(dqkv), P(dbias), _i(B), _i(T), _i(H), _i(dh),
-             lib.stream_ptr())
+    """dqkv: fp32, or bfloat16 (bf16 variant: it only feeds the K|Q|V dgrad / wgrad GEMMs)."""
+    lib.call("msx_attention_tc_bwd_ex", P(qkv), P(mask), P(dctx), P(dqkv), _i(1 if dqkv.dtype == torch.bfloat16 else 0),
+             P(dbias), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
 def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
     lib.call("msx_attention_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
-def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0):
-    lib.call("msx_add_ln_fwd", P(x), P(y), P(gamma), P(beta), P(out), P(mean), P(rstd), _ll(M), _i(D), _f(eps),
+def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0, out16=None):
+    """out16: optional bfloat16 copy of the output (operand of the bf16 GEMMs)."""
+    lib.call("msx_add_ln_fwd_ex", P(x), P(y), P(gamma), P(beta), P(out), P(out16), P(mean), P(rstd), _ll(M), _i(D), _f(eps),
              _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
 
 
 def add_ln_bwd(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p=0.0, seed=0, site=0,
-               accumulate_dres=False, fuse_xy=False, dybias=None):
-    lib.call("msx_add_ln_bwd", P(x), P(y), P(gamma), P(mean), P(rstd), P(dout), P(dres), P(dy), P(dgamma), P(dbeta),
-             P(dybias), _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
+               accumulate_dres=False, fuse_xy=False, dybias=None, dy16=None):
+    """dy16: optional bfloat16 copy of the y-gradient (of the combined gradient under fuse_xy)."""
+    lib.call("msx_add_ln_bwd_ex", P(x), P(y), P(gamma), P(mean), P(rstd), P(dout), P(dres), P(dy), P(dy16), P(dgamma),
+             P(dbeta), P(dybias), _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
              _i(1 if fuse_xy else 0), lib.stream_ptr())
 
 
-def embed_fwd(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab):
-    lib.call("msx_embed_fwd", P(tokens), P(classes), P(seq_lens), P(tok_emb), P(cls_emb), P(prefix_vec), P(pe),
-             P(out), P(mask), _i(B), _i(T), _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
+def embed_fwd(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab,
+              out16=None):
+    lib.call("msx_embed_fwd_ex", P(tokens), P(classes), P(seq_lens), P(tok_emb), P(cls_emb), P(prefix_vec), P(pe),
+             P(out), P(out16), P(mask), _i(B), _i(T), _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
 
 
 def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, prefix, scale, vocab):

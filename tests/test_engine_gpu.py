@@ -262,3 +262,85 @@ def test_graphed_train_step_matches_eager():
         assert float((c0[i] - c1[i]).abs().max()) < 1e-3 * scale, (i, float((c0[i] - c1[i]).abs().max()))
     assert float((c0 - c1).abs().max()) < 5e-2 * scale
     assert float((w0 - w1).abs().max()) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ bf16 variant
+# Tolerances of the bf16 variant (BASELINE config 4), stated separately from the fp32 / TF32 bar as the north star
+# allows: the Transformer layers' GEMM operands carry an 8-bit mantissa (relative rounding 2^-9 per element), every
+# accumulation, LayerNorm, softmax and loss is fp32.
+# Measured on B200 (T = 65 / 129): ce 8e-6 / 2e-6, kl 9e-5 / 6e-5, latent means 5.1e-3 / 5.1e-3 of their scale;
+# gradients: worst tensor 2.1 % / 5.7 % of its own scale (ff1 weights), mean over tensors 0.75 % / 1.4 %.
+BF16_FWD_TOL = {"ce": 1e-4, "kl": 1e-3, "means": 1e-2}
+BF16_GRAD_WORST, BF16_GRAD_MEAN = 0.10, 0.03
+
+
+def _bf16_run(T, B=64, dropout=0.0):
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    cfg_o = om.Cfg(dec_type="lstm")
+    p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=0))
+    tokens, seq_lens, classes, labels, eps = _batch(B, T, 293, 2, 256, seed=1, min_len=T // 2 + 1)
+    eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=dropout, dec_dropout=dropout), "cuda:0", precision="bf16")
+    eng.arena.load_state(p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
+    return cfg_o, p, (tokens, seq_lens, classes, labels, eps), eng, out
+
+
+@pytest.mark.parametrize("T", [65, 129])
+def test_bf16_variant_step_vs_oracle(T):
+    """bf16 variant vs the fp32 oracle: forward losses / latent means and every parameter gradient.  T = 129 takes the
+    FFMA attention fallback (tcgen05 attention covers T <= 128) with casts around it."""
+    cfg_o, p, batch, eng, out = _bf16_run(T, B=64 if T == 65 else 16)
+    tokens, seq_lens, classes, labels, eps = batch
+    opt = om.Adam({k: v.clone() for k, v in p.items()}, clip_gradient=1.0)
+    pp = {k: v.clone() for k, v in p.items()}
+    loss, ce, kl, probs, means, stds, grads = om.train_step(cfg_o, pp, opt, tokens, seq_lens, classes, labels, eps)
+    rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
+    dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
+    print("bf16 forward deviation (max abs / max):", dev)
+    for k, tol in BF16_FWD_TOL.items():
+        assert dev[k] < tol, dev
+    eng.backward()
+    torch.cuda.synchronize()
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
+                   if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
+    print("bf16 gradient deviation, worst tensors:", devs[:4], "mean", sum(d for d, _ in devs) / len(devs))
+    assert devs[0][0] < BF16_GRAD_WORST
+    assert sum(d for d, _ in devs) / len(devs) < BF16_GRAD_MEAN
+
+
+def test_bf16_variant_matches_tf32_dropout_masks_and_trains():
+    """Same seed -> the bf16 and TF32 steps draw the same dropout masks (per-sample losses agree to bf16 rounding, a
+    different mask would move them by per cents), and 30 bf16 Adam steps on one batch reduce the loss like TF32 does."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    tokens, seq_lens, classes, labels, _ = _batch(32, 33, 293, 2, 256, seed=7, min_len=17)
+    args = [_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels)]
+    hist = {}
+    for prec in ("tf32", "bf16"):
+        eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=0.2, dec_dropout=0.2), "cuda:0", seed=3, precision=prec)
+        ces = []
+        for _ in range(30):
+            out = eng.train_step(*args, kl_weight=1.0, global_batch=32, lr=1e-3, clip_gradient=1.0)
+            ces.append(out["ce"].clone())
+        torch.cuda.synchronize()
+        hist[prec] = torch.stack(ces).cpu()
+    a, b = hist["tf32"], hist["bf16"]
+    assert float((a[0] - b[0]).abs().max()) < 1e-2 * float(a[0].abs().max())
+    assert float(b[-1].mean()) < float(b[0].mean()) - 0.05             # the loss goes down ...
+    assert abs(float(b[-1].mean()) - float(a[-1].mean())) < 0.02 * float(a[-1].mean())   # ... along the TF32 trajectory
+
+
+def test_bf16_graphed_step_runs():
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    tokens, seq_lens, classes, labels, _ = _batch(24, 21, 293, 2, 256, seed=5, min_len=9)
+    args = [_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels)]
+    res = []
+    for graphed in (False, True):
+        eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=0.2, dec_dropout=0.2), "cuda:0", seed=1, precision="bf16")
+        fn = eng.train_step_graphed if graphed else eng.train_step
+        ces = [fn(*args, kl_weight=1.0, global_batch=24, lr=3e-4, clip_gradient=1.0)["ce"].clone() for _ in range(4)]
+        torch.cuda.synchronize()
+        res.append(torch.stack(ces))
+    scale = float(res[0].abs().max())
+    for i in range(3):
+        assert float((res[0][i] - res[1][i]).abs().max()) < 2e-3 * scale, i
