@@ -268,6 +268,8 @@ class VAEEngine:
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H)
+        elif self.tensor and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
+            ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
         proj = bf.get(tag + "proj", (M, D), dev)
@@ -340,6 +342,10 @@ class VAEEngine:
         if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv)
             gbqkv = None
+        elif self.tensor and ops.attention_tcl_supported(qkv, T, D // H):
+            ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), torch.float32)], dqkv, B, T, H,
+                                  D // H, dbias=gbqkv)
+            gbqkv = None
         else:
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
         self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
@@ -363,7 +369,9 @@ class VAEEngine:
         ctx16 = bf.get(tag + "ctx16", (M, D), dev, b16)
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H)
-        else:                                           # T > 128: FFMA attention in fp32, then one cast
+        elif ops.attention_tcl_supported(qkv, T, D // H):
+            ops.attention_tcl_fwd(qkv, mask, ctx16, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
+        else:                                           # T > 384: FFMA attention in fp32, then one cast
             ctx = bf.get(tag + "ctx", (M, D), dev)
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.cast_bf16(ctx, ctx16)
@@ -440,6 +448,9 @@ class VAEEngine:
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_bwd(qkv, mask, dctx, dqkv16, B, T, H, D // H, dbias=gbqkv)
+        elif ops.attention_tcl_supported(qkv, T, D // H):
+            ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), f32)], dqkv16, B, T, H, D // H,
+                                  dbias=gbqkv)
         else:
             dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)

@@ -113,6 +113,21 @@ def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):
              P(dbias), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
+def attention_tcl_supported(qkv, T, dh):
+    """tcgen05 attention for long rows (128 < T <= 384)."""
+    return bool(lib.load().msx_attention_tcl_supported(P(qkv), _i(T), _i(dh)))
+
+
+def attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh):
+    lib.call("msx_attention_tcl_fwd", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), P(stats), _i(B),
+             _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
+def attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=None):
+    lib.call("msx_attention_tcl_bwd", P(qkv), P(mask), P(dctx), P(stats), P(dqkv),
+             _i(1 if dqkv.dtype == torch.bfloat16 else 0), P(dbias), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
 def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
     lib.call("msx_attention_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 

@@ -79,3 +79,39 @@ def test_attention_backward(B, T, H):
     assert err < 5e-3, err
     wb = want.sum(0)
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ long rows (T > 128)
+@pytest.mark.parametrize("B,T,H", [(2, 129, 2), (3, 257, 2), (2, 200, 3), (5, 256, 1), (2, 384, 2), (40, 129, 8), (3, 144, 2)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_attention_long_rows(B, T, H, out16):
+    """msx_attention_tcl_fwd / _bwd (key tiles + query chunks of 128) vs the float64 reference formula and autograd."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    qkv, mask = _inputs(B, T, H, dh, seed=T)
+    g = torch.Generator().manual_seed(T)
+    dctx = torch.randn(B * T, H * dh, generator=g)
+    x = qkv.double().requires_grad_(True)
+    want = _ref_fwd(x, mask, B, T, H, dh)
+    (want * dctx.double()).sum().backward()
+    wg = x.grad
+    want = want.detach()
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    assert ops.attention_tcl_supported(qd, T, dh) and not ops.attention_tc_supported(qd, T, dh)
+    odt = torch.bfloat16 if out16 else torch.float32
+    ctx = torch.full((B * T, H * dh), 3.0, device="cuda", dtype=odt)
+    stats = torch.zeros((B * H * T, 2), device="cuda")
+    ops.attention_tcl_fwd(qd, md, ctx, stats, B, T, H, dh)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = float((ctx.double().cpu() - want).abs().max()) / scale
+    assert err < (8e-3 if out16 else 3e-3), err
+    out = torch.full((B * T, 3 * H * dh), 5.0, device="cuda", dtype=odt)
+    db = torch.zeros(3 * H * dh, device="cuda")
+    ops.attention_tcl_bwd(qd, md, dd, stats, out, B, T, H, dh, dbias=db)
+    torch.cuda.synchronize()
+    gs = float(wg.abs().max())
+    err = float((out.double().cpu() - wg).abs().max()) / gs
+    assert err < (1e-2 if out16 else 5e-3), err
+    wb = wg.sum(0)
+    assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
