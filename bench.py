@@ -58,6 +58,7 @@ def parse_args():
                          "nccl if symmetric memory cannot be set up), nccl = ncclAllReduce of the gradient arena + full Adam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-table", action="store_true", help="also print a per-shape table of the step's GEMM launches to stderr")
     ap.add_argument("--no-raster", action="store_true")
     return ap.parse_args()
 
@@ -360,6 +361,14 @@ def run_ours(args):
         gemm_bytes = sum(f[1] for _, _, f in prof["events"])
         step_ms = s.elapsed_time(e)
         n_launch = max(1, len(prof["events"]))
+        if args.gemm_table:
+            tab = {}
+            for a, b, f in prof["events"]:
+                t = tab.setdefault(f[2] if len(f) > 2 else "?", [0, 0.0, 0.0, 0.0])
+                t[0] += 1; t[1] += a.elapsed_time(b); t[2] += f[0]; t[3] += f[1]
+            for k, t in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+                print("gemm %-58s n/step=%4.1f %8.1f us  %7.1f TFLOP/s %7.1f GB/s" % (
+                    k, t[0] / psteps, 1e3 * t[1] / t[0], t[2] / (t[1] * 1e-3) / 1e12, t[3] / (t[1] * 1e-3) / 1e9), file=sys.stderr)
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
         gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9
         kname = {"tf32": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)",
@@ -430,7 +439,7 @@ def run_sweep(args):
     dev = torch.device("cuda", 0)
     lib.load()
     cfg = VAEConfig(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
-    for L in (64, 128):
+    for L in (64, 128, 256):
         for B in (32, 128, 512, 2048, 8192):
             eng = VAEEngine(cfg, dev, seed=0, precision=args.precision)
             tok, lens, cls, lab = synth.token_rows_4_4(B * 2, L, seed=7)

@@ -18,7 +18,8 @@ def _chk(t, dtype=torch.float32):
 def _gemm_tag(M, N, K, accumulate, aux):
     """(flops, algorithmic HBM bytes) of one GEMM launch for bench.py's roofline: every fp32 operand element read once,
     C written once (+ read once when accumulating, + the aux mask read once)."""
-    return (2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (1 + (1 if accumulate else 0) + (1 if aux is not None else 0))))
+    return (2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (1 + (1 if accumulate else 0) + (1 if aux is not None else 0))),
+            "f32 M=%d N=%d K=%d%s%s" % (M, N, K, " acc" if accumulate else "", " aux" if aux is not None else ""))
 
 
 def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
@@ -27,7 +28,7 @@ def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False
     lib.call("msx_gemm_f32", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
              _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr(),
-             tag=_gemm_tag(M, N, K, accumulate, aux))
+             tag=_gemm_tag(M, N, K, accumulate, aux)[:2] + ("ffma M=%d N=%d K=%d tA=%d tB=%d sk=%d" % (M, N, K, transA, transB, splitk),))
 
 
 def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
@@ -36,7 +37,8 @@ def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=Fa
     lib.call("msx_gemm_tc", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
              _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
-             tag=_gemm_tag(M, N, K, accumulate, aux))
+             tag=_gemm_tag(M, N, K, accumulate, aux)[:2] + ("tf32 M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s" % (
+                 M, N, K, transA, transB, splitk, " acc" if accumulate else "", " aux" if aux is not None else ""),))
 
 
 def gemm_tc_bf16(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
@@ -51,7 +53,9 @@ def gemm_tc_bf16(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, re
     lib.call("msx_gemm_tc_bf16", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(1 if c16 else 0),
              _i(M), _i(N), _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
              _i(1 if a16 else 0), _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
-             tag=(flops, nbytes))
+             tag=(flops, nbytes, "bf16 M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s%s" % (
+                 M, N, K, transA, transB, splitk, " acc" if accumulate else "", " aux" if aux is not None else "",
+                 " c16" if c16 else "")))
 
 
 def gemm_tc_bf16_supported(A, lda, B, ldb, Cm, ldc, M, N, K):

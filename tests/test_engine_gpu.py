@@ -344,3 +344,30 @@ def test_bf16_graphed_step_runs():
     scale = float(res[0].abs().max())
     for i in range(3):
         assert float((res[0][i] - res[1][i]).abs().max()) < 2e-3 * scale, i
+
+
+@pytest.mark.parametrize("T", [129, 257])
+def test_tf32_long_rows_step_vs_oracle(T):
+    """The L = 128 / 256 sweep points: the step with the long-row tcgen05 attention (msx_attention_tcl_*) vs the oracle."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    cfg_o = om.Cfg(dec_type="lstm")
+    p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=0))
+    tokens, seq_lens, classes, labels, eps = _batch(8, T, 293, 2, 256, seed=T, min_len=T // 2)
+    eng = VAEEngine(VAEConfig(dec_type="lstm"), "cuda:0", precision="tf32")
+    eng.arena.load_state(p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
+    opt = om.Adam({k: v.clone() for k, v in p.items()}, clip_gradient=1.0)
+    pp = {k: v.clone() for k, v in p.items()}
+    loss, ce, kl, probs, means, stds, grads = om.train_step(cfg_o, pp, opt, tokens, seq_lens, classes, labels, eps)
+    rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
+    dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
+    print("tf32 long-row forward deviation:", dev)
+    assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 1e-3, dev
+    eng.backward()
+    torch.cuda.synchronize()
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
+                   if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
+    print("tf32 long-row gradient deviation, worst tensors:", devs[:4])
+    assert devs[0][0] < 5e-2
+    assert sum(d for d, _ in devs) / len(devs) < 2e-2
