@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
 
 // ds = rstd * (g*dout - mean(g*dout) - xhat * mean(g*dout*xhat));  dres = ds;  dy = ds * keep
 template <int VEC, int kPer>
-__global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
+__global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
     float* __restrict__ dres, float* __restrict__ dy, unsigned short* __restrict__ dy16, float* __restrict__ dgamma,
@@ -139,8 +139,19 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
     for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = dyb[i][j] = 0.f;
 
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
-    float s[kPer][VEC], keep[kPer][VEC];
-    load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    // s = x + drop(y); the keep mask is held as one bit per element (registers: 88 -> 4 CTAs per SM; the kernel is
+    // latency-bound on its three row loads, occupancy is what hides them)
+    float s[kPer][VEC];
+    unsigned keepbits = 0u;
+    {
+      float keep[kPer][VEC];
+      load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+#pragma unroll
+      for (int i = 0; i < kPer; ++i)
+        if (i < nper)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) keepbits |= (keep[i][j] > 0.f ? 1u : 0u) << (i * VEC + j);
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
     float go[kPer][VEC];
     float s1 = 0.f, s2 = 0.f;
@@ -182,8 +193,9 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_bwd_kernel(
       for (int j = 0; j < VEC; ++j) {
         const float ds = rstd * (go[i][j] - s1 - s[i][j] * s2);
         // fuse_xy: x and y are the same tensor (decoder's ln3(f + drop(f))) -> one gradient ds*(1+keep)
-        dyv[j] = ds * keep[i][j];
-        dr[j] = fuse_xy ? ds * (1.f + keep[i][j]) : ds;
+        const float kp = ((keepbits >> (i * VEC + j)) & 1u) ? inv_keep : 0.f;
+        dyv[j] = ds * kp;
+        dr[j] = fuse_xy ? ds * (1.f + kp) : ds;
         dyb[i][j] += fuse_xy ? dr[j] : dyv[j];
       }
       if (VEC == 4) {
