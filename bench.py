@@ -58,8 +58,12 @@ def parse_args():
                          "nccl if symmetric memory cannot be set up), nccl = ncclAllReduce of the gradient arena + full Adam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="also print the step's per-entry-point time table (CUDA events "
+                    "around every libmsx call of three eager steps) to stderr")
     ap.add_argument("--gemm-table", action="store_true", help="also print a per-shape table of the step's GEMM launches to stderr")
     ap.add_argument("--no-raster", action="store_true")
+    ap.add_argument("--no-bf16-variant", action="store_true",
+                    help="skip the bf16-variant leg (BASELINE config 4) that the default tf32 line carries as a sub-object")
     return ap.parse_args()
 
 
@@ -378,7 +382,7 @@ def run_ours(args):
         # fp32-in / fp32-out GEMMs with K, N <= 1024: 64-102 flop per algorithmic byte, below the TF32 ridge point
         # (~700 TFLOP/s / 6.55 TB/s = 107 flop/B), so the bounding resource is HBM
         traffic = None
-        tpath = os.path.join(REPO, "profiles", "traffic_gemm.json")
+        tpath = os.path.join(REPO, "profiles", "traffic_gemm_bf16.json" if args.precision == "bf16" else "traffic_gemm.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
@@ -391,8 +395,49 @@ def run_ours(args):
                     "tensor": {"achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
                                "peak_source": peaks["src"] + " bf16 sustained (cuBLAS); TF32 nominal peak is half of bf16",
                                "flops_per_step": gemm_flops / psteps}}
+    if args.kernel_table and rank == 0 and world == 1:
+        kp = {"match": "msx_", "events": [], "names": True}
+        lib._profile = kp
+        for i in range(psteps):
+            step_eager(i)
+        torch.cuda.synchronize()
+        lib._profile = None
+        tab = {}
+        for a, b, f in kp["events"]:
+            name = f if isinstance(f, str) else (f[2].split(" ")[0] + " gemm" if isinstance(f, tuple) and len(f) > 2 else "?")
+            t = tab.setdefault(name, [0, 0.0])
+            t[0] += 1; t[1] += a.elapsed_time(b)
+        tot = sum(t[1] for t in tab.values())
+        for k, t in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+            print("kernel %-28s n/step=%5.1f %8.1f us/call %8.3f ms/step %5.1f%%" % (
+                k, t[0] / psteps, 1e3 * t[1] / t[0], t[1] / psteps, 100 * t[1] / tot), file=sys.stderr)
     if world > 1:
         barrier()
+
+    # ---- bf16 variant (BASELINE config 4), stated separately: same model, batch, data and timing protocol with
+    # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
+    bf16_variant = None
+    if args.precision == "tf32" and not args.no_bf16_variant:
+        eng2 = VAEEngine(cfg, dev, seed=0, precision="bf16")
+        train2 = eng2.train_step if args.no_graph else eng2.train_step_graphed
+        ar2 = allreduce if world > 1 else None
+
+        def step_bf16(i):
+            tk, ln, cl, lb = resident[i % n_batches]
+            return train2(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar2)
+
+        ms2, _, _ = timed(step_bf16, K, W)
+        bf16_variant = {"value": gbatch * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K, "dtype": "bf16",
+                        "dp_exchange": "none" if world == 1 else "nccl all-reduce + Adam on every rank",
+                        "what": "Transformer-layer GEMM operands (activations, their gradients, weight shadow) bf16 in HBM on "
+                                "tcgen05 kind::f16, fp32 accumulate; fp32 master weights / LN / softmax / losses / Adam",
+                        "parity": "vs fp32 oracle: loss 1e-4, KL 1e-3, latent means 1e-2, gradients 10 % worst tensor / 3 % "
+                                  "mean (tests/test_engine_gpu.py::test_bf16_variant_step_vs_oracle)"}
+        eng2._graphs.clear()
+        del eng2, train2
+        torch.cuda.synchronize()
+        if world > 1:
+            barrier()
 
     if rank != 0:
         if world > 1:
@@ -417,7 +462,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange,
                    "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                          (B * T * 4 * 40e3 / 1e9 / 10)},
-        "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu,
+        "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu, "bf16_variant": bf16_variant,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches, "clocks": clocks,

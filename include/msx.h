@@ -86,6 +86,15 @@ int msx_gemm_tc_bf16(const void* A, int lda, int transA, const void* B, int ldb,
                      int splitk, float* out_colsum, void* stream);
 int msx_gemm_tc_bf16_supported(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, int c_bf16, int M,
                                int N, int K);
+/* General form of msx_gemm_tc / msx_gemm_tc_bf16 (ab_bf16 / c_bf16 select the storage types) plus the ReLU bit mask:
+ * aux_kind 0 = fp32 matrix, 1 = bfloat16 matrix, 2 = bit mask uint32 [M, ldaux words] (bit j of word [m, n/32] <=>
+ * element [m, 32*(n/32)+j] > 0); mask_out (optional, N % 32 == 0, plain stores) receives that mask of the values this
+ * launch writes after bias / ReLU / dropout.  FF1 forward emits the mask, FF2 dgrad reads 4 bytes per 32 elements instead
+ * of re-reading the hidden activation (transformer.py:36-46 backward). */
+int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int M, int N,
+                   int K, int ab_bf16, int c_bf16, const float* bias, int relu, float drop_p, unsigned long long seed,
+                   unsigned site, const void* aux, int ldaux, int aux_kind, float aux_scale, int accumulate, int splitk,
+                   float* out_colsum, uint32_t* mask_out, int ldmask, void* stream);
 /* dst[i] = bfloat16(src[i]) (round to nearest even), i < n: builds bf16 operands from fp32 tensors (weights shadow,
  * tests).  src and dst 16-byte aligned. */
 int msx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);

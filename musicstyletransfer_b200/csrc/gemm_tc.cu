@@ -27,8 +27,18 @@ constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 B = one swi
 constexpr int kStages = 4;
 constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kTileBytes;
-constexpr int kThreads = 320;                      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane group, each takes half of the columns
+// Epilogue warps: kColSplit warps per TMEM lane group (a warp may only touch lanes 32 * (warp % 4) ..), each draining
+// 1 / kColSplit of the tile's columns.  The wide-N, short-K GEMMs of the step (QKV, FF1 forward, FF2 dgrad) are paced
+// by the epilogue's instruction issue (ncu: 2 epilogue warps per scheduler reach ~50 % issue utilisation), hence four
+// warps per lane group with one staging box each is available (-DMSX_GEMM_EPI_WARPS=16); measured on the step it
+// speeds the dropout epilogue up by 12 % and slows the mainloop-paced GEMMs down by 1-3 %: a wash, the default stays 8.
+#ifndef MSX_GEMM_EPI_WARPS
+#define MSX_GEMM_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = MSX_GEMM_EPI_WARPS;
+constexpr int kColSplit = kEpiWarps / 4;
+constexpr int kBoxes = kEpiWarps == 8 ? 2 : 1;       // staging boxes per epilogue warp
+constexpr int kThreads = 32 * (2 + kEpiWarps);       // warp 0 TMA, warp 1 MMA, then the epilogue warps
 constexpr int kOutBoxBytes = 32 * 128;               // epilogue staging box: 32 rows x 32 fp32
 constexpr int kTmemCols = 256;                      // 2 accumulators x 128 fp32 columns
 
@@ -48,7 +58,10 @@ struct TcParams {
   float* out_colsum;   // out_colsum[n] += sum_m C[m,n] of the values this launch writes (bias gradient of the producer)
   int m_tiles, n_tiles, kb_total, kb_per_split;
   int c_bf16;          // C is bf16 [M, ldc] (plain store only); the staging box is 32 rows x 64 B, SWIZZLE_64B
-  int aux_bf16;        // aux is bf16 [M, ldaux]
+  int aux_bf16;        // aux storage: 0 fp32 [M, ldaux], 1 bf16 [M, ldaux], 2 bit mask uint32 [M, ldaux words] (bit j of word
+                       // [m, n / 32] <=> element [m, n] > 0, n = 32 * (n / 32) + j), as written through mask_out
+  unsigned* mask_out;  // optional: bit mask of (C > 0) after the epilogue, [M, ldmask words]; needs N % 32 == 0
+  int ldmask;
 };
 
 struct __align__(8) Barriers {
@@ -176,16 +189,73 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// aux (ReLU-mask source) of one 32-column chunk of this lane's row, fetched one chunk AHEAD of its use: the loads do not
+// depend on the accumulator, so they are issued before the warp waits for the tile / while it works on the previous
+// chunk, which takes the DRAM round trip out of the per-chunk dependency chain (the dgrad-with-mask GEMM was paced by it).
+struct AuxPref { uint4 r[8]; };     // bf16 aux: r[0..3] (64 B); fp32 aux: r[0..7] (128 B)
+__device__ __forceinline__ bool aux_fast(const TcParams& p, int col0) {       // warp-uniform
+  if (p.aux_bf16 == 2) return p.aux != nullptr;                               // bit mask: one word per lane and chunk
+  return p.aux && col0 + 32 <= p.N && (p.aux_bf16 ? (p.ldaux & 7) == 0 : (p.ldaux & 3) == 0) && ((uintptr_t)p.aux & 15) == 0;
+}
+__device__ __forceinline__ void aux_prefetch(const TcParams& p, int my_row, int col0, AuxPref& a) {
+  if (!aux_fast(p, col0) || my_row >= p.M) return;
+  if (p.aux_bf16 == 2) {
+    a.r[0].x = col0 < p.N ? __ldg(reinterpret_cast<const unsigned*>(p.aux) + (size_t)my_row * p.ldaux + (col0 >> 5)) : 0u;
+  } else if (p.aux_bf16) {
+    const uint4* ax = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(p.aux) + (size_t)my_row * p.ldaux + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.r[j] = __ldg(ax + j);
+  } else {
+    const uint4* ax = reinterpret_cast<const uint4*>(p.aux + (size_t)my_row * p.ldaux + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.r[j] = __ldg(ax + j);
+  }
+}
+// bit j set <=> aux[row, col0 + j] > 0 (bf16: 0 < bits < 0x8000 tested on the raw halves; fp32: sign clear and non-zero)
+__device__ __forceinline__ unsigned aux_mask(const TcParams& p, const AuxPref& a) {
+  unsigned m = 0u;
+  if (p.aux_bf16 == 2) {
+    m = a.r[0].x;
+  } else if (p.aux_bf16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned w[4] = {a.r[j].x, a.r[j].y, a.r[j].z, a.r[j].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        m |= ((int)(w[q] << 16) > 0 ? 1u : 0u) << (8 * j + 2 * q);          // low half in [0x0001, 0x7FFF]
+        m |= ((int)w[q] > 0xFFFF ? 1u : 0u) << (8 * j + 2 * q + 1);         // high half in [0x0001, 0x7FFF]
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m |= (__uint_as_float(a.r[j].x) > 0.f ? 1u : 0u) << (4 * j);
+      m |= (__uint_as_float(a.r[j].y) > 0.f ? 1u : 0u) << (4 * j + 1);
+      m |= (__uint_as_float(a.r[j].z) > 0.f ? 1u : 0u) << (4 * j + 2);
+      m |= (__uint_as_float(a.r[j].w) > 0.f ? 1u : 0u) << (4 * j + 3);
+    }
+  }
+  return m;
+}
+
 // Epilogue for one 32-row x 32-column chunk held in the row-owner layout (lane = row, v[j] = column col0 + j):
 // bias / ReLU / dropout / aux mask / bias-gradient column sums, then a SWIZZLE_128B staging box that the TMA
 // engine stores (or reduce-adds) into C.
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensorMap* tmc, float (&v)[32], int row0,
                                                int my_row, int col0, int lane, unsigned char* st, int& sbuf,
-                                               int& pending, bool reduce) {
+                                               int& pending, bool reduce, unsigned amask) {
     // ---- row-owner layout: this lane holds 32 consecutive columns of row my_row
     if (p.bias) {
+      if (col0 + 32 <= p.N && (((uintptr_t)(p.bias + col0)) & 15) == 0) {   // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+      }
     }
     if (p.relu) {
 #pragma unroll
@@ -193,49 +263,25 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
     }
     if (p.drop_p > 0.f) {
       const unsigned long long eff_seed = msx_eff_seed(p.seed, p.seed_ctr);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float s4[4];
-        dropout_scale4(eff_seed, p.site, ((unsigned long long)my_row * p.N + col0 + j) >> 2, p.drop_p, p.inv_keep, s4);
-        v[j] *= s4[0]; v[j + 1] *= s4[1]; v[j + 2] *= s4[2]; v[j + 3] *= s4[3];
-      }
+      dropout_apply32(eff_seed, p.site, (unsigned long long)my_row * p.N + col0, p.drop_p, p.inv_keep, v);
     }
-    if (p.aux && p.aux_bf16 && my_row < p.M) {
-      const unsigned short* ax = reinterpret_cast<const unsigned short*>(p.aux) + (size_t)my_row * p.ldaux + col0;
-      if (col0 + 32 <= p.N && (p.ldaux & 7) == 0) {
-        uint4 a4[4];
+    if (p.mask_out && my_row < p.M) {         // N % 32 == 0 (checked on the host): every chunk is a whole mask word
+      unsigned m = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a4[j] = __ldg(reinterpret_cast<const uint4*>(ax) + j);
-        // relu'(h) from the bf16 sign / zero pattern: positive <=> 0 < bits < 0x8000
+      for (int j = 0; j < 32; ++j) m |= v[j] > 0.f ? (1u << j) : 0u;
+      p.mask_out[(size_t)my_row * p.ldmask + (col0 >> 5)] = m;
+    }
+    if (p.aux && my_row < p.M) {
+      if (aux_fast(p, col0)) {                // mask prefetched by the caller (aux_prefetch / aux_mask)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned w[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const unsigned lo = w[q] & 0xFFFFu, hi = w[q] >> 16;
-            v[8 * j + 2 * q + 0] *= (lo != 0u && lo < 0x8000u) ? p.aux_scale : 0.f;
-            v[8 * j + 2 * q + 1] *= (hi != 0u && hi < 0x8000u) ? p.aux_scale : 0.f;
-          }
-        }
-      } else {
+        for (int j = 0; j < 32; ++j) v[j] = (amask & (1u << j)) ? v[j] * p.aux_scale : 0.f;
+      } else if (p.aux_bf16) {
+        const unsigned short* ax = reinterpret_cast<const unsigned short*>(p.aux) + (size_t)my_row * p.ldaux + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] *= (col0 + j < p.N && bf16_bits_to_float(__ldg(ax + j)) > 0.f) ? p.aux_scale : 0.f;
-      }
-    } else if (p.aux && my_row < p.M) {
-      const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
-      if (col0 + 32 <= p.N && (p.ldaux & 3) == 0) {
-        float4 a4[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(ax) + j);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[4 * j + 0] *= a4[j].x > 0.f ? p.aux_scale : 0.f;
-          v[4 * j + 1] *= a4[j].y > 0.f ? p.aux_scale : 0.f;
-          v[4 * j + 2] *= a4[j].z > 0.f ? p.aux_scale : 0.f;
-          v[4 * j + 3] *= a4[j].w > 0.f ? p.aux_scale : 0.f;
-        }
       } else {
+        const float* ax = p.aux + (size_t)my_row * p.ldaux + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < p.N && __ldg(ax + j) > 0.f) ? p.aux_scale : 0.f;
       }
@@ -249,8 +295,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
     }
     // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
     unsigned char* box = st + sbuf * kOutBoxBytes;
-    if (pending >= 2) {                     // the box we are about to overwrite must have been read
-      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    if (pending >= kBoxes) {                // the box we are about to overwrite must have been read
+      if (elect_one()) {
+        if (kBoxes == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       __syncwarp();
     }
     if (p.c_bf16) {
@@ -279,8 +328,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
                      : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    sbuf ^= 1;
-    if (pending < 2) ++pending;
+    if (kBoxes == 2) sbuf ^= 1;
+    if (pending < kBoxes) ++pending;
 }
 
 template <bool A_MN, bool B_MN, bool BF>
@@ -291,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* stage_out = ring + kStages * kStageBytes;                        // [kEpiWarps][2][32 rows][128 B]
-  Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
+  Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * kBoxes * kOutBoxBytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int items = p.m_tiles * p.n_tiles * p.splitk;
@@ -391,25 +440,33 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ================================ epilogue (warps 2..5) ================================
     const int ew = warp - 2;                 // staging slot
     const int lg = warp & 3;                 // TMEM lane group this warp may access (warps w and w+4 share one)
-    const int chalf = ew >> 2;               // which half of the BN columns this warp drains
-    unsigned char* st = stage_out + ew * 2 * kOutBoxBytes;
+    const int chalf = ew >> 2;               // which 1 / kColSplit of the BN columns this warp drains
+    unsigned char* st = stage_out + ew * kBoxes * kOutBoxBytes;
     const bool reduce = p.accumulate || p.splitk > 1;
     int local = 0, sbuf = 0, pending = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
       const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles;
       const int buf = local & 1;
       const unsigned use = (unsigned)(local >> 1);
-      mbar_wait(&bars->tmem_full[buf], use & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row0 = mt * BM + lg * 32;
       const int my_row = row0 + lane;
+      constexpr int kChPerWarp = BN / 32 / kColSplit;
+      AuxPref apre;
+      if (p.aux) aux_prefetch(p, my_row, nt * BN + chalf * kChPerWarp * 32, apre);      // before waiting for the accumulator
+      mbar_wait(&bars->tmem_full[buf], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int ch = chalf * (BN / 64); ch < (chalf + 1) * (BN / 64); ++ch) {
+      for (int ch = chalf * kChPerWarp; ch < (chalf + 1) * kChPerWarp; ++ch) {
         const int col0 = nt * BN + ch * 32;
+        unsigned amask = 0u;
+        if (p.aux) {
+          amask = aux_mask(p, apre);
+          if (ch + 1 < (chalf + 1) * kChPerWarp) aux_prefetch(p, my_row, col0 + 32, apre);
+        }
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce);
+          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -517,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* stage_out = ring + Cfg::kStages2 * Cfg::kStage;                  // [kEpiWarps][2][32 rows][128 B]
-  Barriers2* bars = reinterpret_cast<Barriers2*>(stage_out + kEpiWarps * 2 * kOutBoxBytes);
+  Barriers2* bars = reinterpret_cast<Barriers2*>(stage_out + kEpiWarps * kBoxes * kOutBoxBytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const unsigned rank = cluster_ctarank();
@@ -625,24 +682,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int ew = warp - 2;
     const int lg = warp & 3;
     const int chalf = ew >> 2;
-    unsigned char* st = stage_out + ew * 2 * kOutBoxBytes;
+    unsigned char* st = stage_out + ew * kBoxes * kOutBoxBytes;
     const bool reduce = p.accumulate || p.splitk > 1;
     int local = 0, sbuf = 0, pending = 0;
     for (int it = pair; it < items; it += npairs, ++local) {
       const int nt = it % p.n_tiles, mt = (it / p.n_tiles) % p.m_tiles;
       const int buf = local & 1;
       const unsigned use = (unsigned)(local >> 1);
-      mbar_wait(&bars->tmem_full[buf], use & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row0 = mt * (2 * BM) + (int)rank * BM + lg * 32;
       const int my_row = row0 + lane;
+      constexpr int kChPerWarp = Cfg::kChunks / kColSplit;
+      AuxPref apre;
+      if (p.aux) aux_prefetch(p, my_row, nt * BN2 + chalf * kChPerWarp * 32, apre);     // before waiting for the accumulator
+      mbar_wait(&bars->tmem_full[buf], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int ch = chalf * (Cfg::kChunks / 2); ch < (chalf + 1) * (Cfg::kChunks / 2); ++ch) {
+      for (int ch = chalf * kChPerWarp; ch < (chalf + 1) * kChPerWarp; ++ch) {
         const int col0 = nt * BN2 + ch * 32;
+        unsigned amask = 0u;
+        if (p.aux) {
+          amask = aux_mask(p, apre);
+          if (ch + 1 < (chalf + 1) * kChPerWarp) aux_prefetch(p, my_row, col0 + 32, apre);
+        }
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN2 + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce);
+          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -701,7 +766,7 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
   return MSX_OK;
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers);
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * kBoxes * kOutBoxBytes + sizeof(Barriers);
 
 template <bool A_MN, bool B_MN, bool BF>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
@@ -715,7 +780,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 
 template <int BN2>
 constexpr size_t pair_smem_bytes() {
-  return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)kEpiWarps * 2 * kOutBoxBytes + sizeof(Barriers2);
+  return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)kEpiWarps * kBoxes * kOutBoxBytes + sizeof(Barriers2);
 }
 
 template <int BN2, bool A_MN, bool B_MN, bool BF>
@@ -746,7 +811,7 @@ template <bool BF>
 int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int c_bf16,
                  int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
                  const void* aux, int ldaux, int aux_bf16, float aux_scale, int accumulate, int splitk, float* out_colsum,
-                 void* stream) {
+                 void* stream, unsigned* mask_out = nullptr, int ldmask = 0) {
   using Op = OpCfg<BF>;
   constexpr MapKind kOp = BF ? kMapBf16 : kMapTf32;
   if (splitk < 1) splitk = 1;
@@ -762,6 +827,7 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = (const float*)aux; p.ldaux = ldaux;
   p.aux_scale = aux_scale; p.accumulate = accumulate; p.out_colsum = out_colsum; p.c_bf16 = c_bf16; p.aux_bf16 = aux_bf16;
+  p.mask_out = mask_out; p.ldmask = ldmask;
   p.kb_total = msx_ceil_div(K, Op::kBKE);
   // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
   // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
@@ -875,4 +941,40 @@ extern "C" int msx_gemm_tc_bf16(const void* A, int lda, int transA, const void* 
   MSX_REQUIRE(!(c_bf16 && (accumulate || splitk > 1)), "msx_gemm_tc_bf16: a bf16 C takes plain stores only");
   return gemm_tc_impl<true>(A, lda, transA, B, ldb, transB, C, ldc, c_bf16 ? 1 : 0, M, N, K, bias, relu, drop_p, seed, site,
                             aux, ldaux, aux_bf16 ? 1 : 0, aux_scale, accumulate, splitk, out_colsum, stream);
+}
+
+// General entry point: the two above plus the ReLU bit mask.  ab_bf16 selects the operand type (0: fp32 memory read as
+// TF32, 1: bfloat16), c_bf16 the C type; aux_kind: 0 fp32 matrix, 1 bfloat16 matrix, 2 bit mask (uint32 [M, ldaux words],
+// bit j of word [m, n / 32] <=> element [m, 32 * (n / 32) + j] > 0).  mask_out (optional, N % 32 == 0) receives that bit
+// mask of the values this launch writes (after bias / ReLU / dropout): the FF1 forward emits it and the FF2 dgrad reads
+// 4 bytes per 32 elements instead of re-reading the hidden activation.
+extern "C" int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int M,
+                              int N, int K, int ab_bf16, int c_bf16, const float* bias, int relu, float drop_p,
+                              unsigned long long seed, unsigned site, const void* aux, int ldaux, int aux_kind,
+                              float aux_scale, int accumulate, int splitk, float* out_colsum, unsigned* mask_out, int ldmask,
+                              void* stream) {
+  MSX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "msx_gemm_tc_ex: negative dimension");
+  MSX_REQUIRE(!(out_colsum && (accumulate || splitk > 1)), "msx_gemm_tc_ex: out_colsum needs a plain (non-accumulating) store");
+  if (M == 0 || N == 0) return MSX_OK;
+  MSX_REQUIRE(A && B && C, "msx_gemm_tc_ex: null operand");
+  MSX_REQUIRE(K > 0, "msx_gemm_tc_ex: K must be > 0");
+  MSX_REQUIRE(aux_kind >= 0 && aux_kind <= 2, "msx_gemm_tc_ex: aux_kind must be 0 (fp32), 1 (bf16) or 2 (bit mask)");
+  if (ab_bf16)
+    MSX_REQUIRE(msx_gemm_tc_bf16_supported(A, lda, B, ldb, C, ldc, c_bf16, M, N, K),
+                "msx_gemm_tc_ex: operands must be 16-byte aligned, bf16 leading dimensions %% 8 == 0, fp32 ones %% 4 == 0");
+  else
+    MSX_REQUIRE(!c_bf16 && msx_gemm_tc_supported((const float*)A, lda, (const float*)B, ldb, (const float*)C, ldc, M, N, K),
+                "msx_gemm_tc_ex: TF32 operands need fp32 A, B, C, 16-byte aligned, leading dimensions %% 4 == 0");
+  MSX_REQUIRE(!(transA == 1 && transB == 1), "msx_gemm_tc_ex: A^T B^T is not used on this path");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc_ex: dropout probability must be in [0,1)");
+  MSX_REQUIRE(!(splitk > 1 && (bias || relu || drop_p > 0.f || aux || accumulate || mask_out)),
+              "msx_gemm_tc_ex: split-K only supports the plain atomic-add epilogue");
+  MSX_REQUIRE(!(c_bf16 && (accumulate || splitk > 1)), "msx_gemm_tc_ex: a bf16 C takes plain stores only");
+  MSX_REQUIRE(!(mask_out && ((N & 31) || accumulate || ldmask < N / 32)), "msx_gemm_tc_ex: mask_out needs N %% 32 == 0, a plain store and ldmask >= N / 32");
+  MSX_REQUIRE(!(aux && aux_kind == 2 && ((N & 31) || ldaux < N / 32)), "msx_gemm_tc_ex: a bit-mask aux needs N %% 32 == 0 and ldaux >= N / 32 words");
+  if (ab_bf16)
+    return gemm_tc_impl<true>(A, lda, transA, B, ldb, transB, C, ldc, c_bf16 ? 1 : 0, M, N, K, bias, relu, drop_p, seed, site, aux,
+                              ldaux, aux_kind, aux_scale, accumulate, splitk, out_colsum, stream, mask_out, ldmask);
+  return gemm_tc_impl<false>(A, lda, transA, B, ldb, transB, C, ldc, 0, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
+                             aux_kind, aux_scale, accumulate, splitk, out_colsum, stream, mask_out, ldmask);
 }

@@ -124,4 +124,28 @@ __device__ __forceinline__ float dropout_scale4(uint64_t seed, uint32_t site, ui
   out[3] = (r1 >> 16) >= thr ? inv_keep : 0.f;
   return 0.f;
 }
+// Same masks as dropout_scale4 for the 32 consecutive elements e0 .. e0+31 of one row chunk, applied in place
+// (v[j] = keep ? v[j] * inv_keep : 0): the key and (outside the one chunk in 2^33 elements that straddles it) the
+// high-word hash are computed once per chunk, and the 16-bit threshold tests are done on the full hash word.
+__device__ __forceinline__ void dropout_apply32(uint64_t seed, uint32_t site, uint64_t e0, float p, float inv_keep,
+                                                float v[32]) {
+  const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (site + 1u)));
+  const uint64_t idx4_0 = e0 >> 2;
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const uint32_t thr_hi = thr << 16;
+  const uint32_t hi0 = mix32(key ^ (uint32_t)(idx4_0 >> 31));
+  const bool same_hi = ((idx4_0 + 7) >> 31) == (idx4_0 >> 31);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint64_t idx4 = idx4_0 + g;
+    const uint32_t hi = same_hi ? hi0 : mix32(key ^ (uint32_t)(idx4 >> 31));
+    const uint32_t base = (uint32_t)idx4 << 1;
+    const uint32_t r0 = mix32((base ^ hi) * 0x9E3779B1u + key);
+    const uint32_t r1 = mix32(((base + 1u) ^ hi) * 0x9E3779B1u + key);
+    v[4 * g + 0] = ((r0 << 16) >= thr_hi) ? v[4 * g + 0] * inv_keep : 0.f;
+    v[4 * g + 1] = (r0 >= thr_hi) ? v[4 * g + 1] * inv_keep : 0.f;
+    v[4 * g + 2] = ((r1 << 16) >= thr_hi) ? v[4 * g + 2] * inv_keep : 0.f;
+    v[4 * g + 3] = (r1 >= thr_hi) ? v[4 * g + 3] * inv_keep : 0.f;
+  }
+}
 #endif

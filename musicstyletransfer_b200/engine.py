@@ -203,6 +203,7 @@ class VAEEngine:
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.ctx = None
         self._graphs = {}
+        self._hmask_ok = {}                   # layer tag -> the FF1 forward wrote the ReLU bit mask
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, B, T):
@@ -219,12 +220,19 @@ class VAEEngine:
         return self.arena.grad(name)
 
     def _dense_fwd(self, x, ldx, M, name_w, name_b, out, ldo, N, K, relu=False, drop_p=0.0, site=0, accumulate=False,
-                   w=None, b=None):
+                   w=None, b=None, mask_out=None):
+        """mask_out (tensor path only, N % 32 == 0): int32 [M, N/32] bit mask of (out > 0), the ReLU / dropout mask the
+        dgrad of the next layer applies; returns True when it was written."""
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
-        fn = ops.gemm_tc if self._use_tc(x, ldx, w, K, out, ldo, M, N, K) else ops.gemm
-        fn(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
-           site=site, accumulate=accumulate)
+        if self._use_tc(x, ldx, w, K, out, ldo, M, N, K):
+            use_mask = mask_out is not None and N % 32 == 0
+            ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+                        site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32)
+            return use_mask
+        ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+                 site=site, accumulate=accumulate)
+        return False
 
     def _lstm_tc(self, Hd, tv):
         """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers) in the tf32 precision mode, H = 128."""
@@ -280,8 +288,9 @@ class VAEEngine:
         ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
                        drop_p=p, seed=self.dropout_seed, site=site0)
         h = bf.get(tag + "h", (M, 4 * D), dev)
-        self._dense_fwd(x1, D, M, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", h, 4 * D, 4 * D, D, relu=True,
-                        drop_p=p, site=site0 + 1)
+        hmask = bf.get(tag + "hmask", (M, (4 * D + 31) // 32), dev, torch.int32)
+        self._hmask_ok[tag] = self._dense_fwd(x1, D, M, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", h, 4 * D, 4 * D, D,
+                                              relu=True, drop_p=p, site=site0 + 1, mask_out=hmask)
         f = bf.get(tag + "f", (M, D), dev)
         self._dense_fwd(h, 4 * D, M, prefix + "ff.ff2.weight", prefix + "ff.ff2.bias", f, D, D, 4 * D)
         out = bf.get(tag + "out", (M, D), dev)
@@ -318,8 +327,14 @@ class VAEEngine:
                 df = dx1
         # ff2: f = h W2^T + b2
         dh = bf.get(tag + "dh", (M, 4 * D), dev)
+        # ReLU / dropout mask of the hidden activation: the bit mask the FF1 forward epilogue wrote (4 B per 32 elements)
+        # when it ran on the tensor path, else the activation itself
+        if self._hmask_ok.get(tag):
+            aux, ldaux = bf.t[(tag + "hmask", (M, (4 * D + 31) // 32), torch.int32)], 4 * D // 32
+        else:
+            aux, ldaux = h, 4 * D
         fused = self._dense_bwd(df, D, M, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
-                                None, D, 4 * D, dx=dh, lddx=4 * D, aux=h, ldaux=4 * D, aux_scale=inv_keep,
+                                None, D, 4 * D, dx=dh, lddx=4 * D, aux=aux, ldaux=ldaux, aux_scale=inv_keep,
                                 dx_colsum=self._G(prefix + "ff.ff1.bias"))
         # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
         self._dense_bwd(dh, 4 * D, M, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
@@ -384,8 +399,10 @@ class VAEEngine:
         ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
                        drop_p=p, seed=seed, site=site0, out16=x1h)
         h16 = bf.get(tag + "h16", (M, 4 * D), dev, b16)
+        hmask = bf.get(tag + "hmask", (M, 4 * D // 32), dev, torch.int32)     # ReLU / dropout bit mask for the FF2 dgrad
         ops.gemm_tc_bf16(x1h, D, 0, a.view16(prefix + "ff.ff1.weight"), D, 1, h16, 4 * D, M, 4 * D, D,
-                         bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1)
+                         bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1,
+                         mask_out=hmask, ldmask=4 * D // 32)
         f = bf.get(tag + "f", (M, D), dev)
         ops.gemm_tc_bf16(h16, 4 * D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 1, f, D, M, D, 4 * D,
                          bias=self._W(prefix + "ff.ff2.bias"))
@@ -430,8 +447,9 @@ class VAEEngine:
         # ff2: f = h W2^T + b2
         self._wgrad16(df16, D, h16, 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, M)
         dh16 = bf.get(tag + "dh16", (M, 4 * D), dev, b16)
-        ops.gemm_tc_bf16(df16, D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 0, dh16, 4 * D, M, 4 * D, D, aux=h16,
-                         ldaux=4 * D, aux_scale=inv_keep, out_colsum=self._G(prefix + "ff.ff1.bias"))
+        ops.gemm_tc_bf16(df16, D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 0, dh16, 4 * D, M, 4 * D, D,
+                         aux=bf.t[(tag + "hmask", (M, 4 * D // 32), torch.int32)], ldaux=4 * D // 32, aux_scale=inv_keep,
+                         out_colsum=self._G(prefix + "ff.ff1.bias"))
         # ff1: h = drop(relu(x1 W1^T + b1)); dh16 holds d(pre-activation)
         self._wgrad16(dh16, 4 * D, x1h, D, self._G(prefix + "ff.ff1.weight"), 4 * D, D, M)
         ops.gemm_tc_bf16(dh16, 4 * D, 0, a.view16(prefix + "ff.ff1.weight"), D, 0, dx1, D, M, D, 4 * D,

@@ -60,7 +60,7 @@ def call(name, *args, tag=None):
         s.record()
         check(fn(*args), name)
         e.record()
-        prof["events"].append((s, e, tag))
+        prof["events"].append((s, e, tag if tag is not None or not prof.get("names") else name))
     else:
         check(fn(*args), name)
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)

@@ -25,37 +25,55 @@ def _gemm_tag(M, N, K, accumulate, aux):
 def gemm(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
          aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, colsum=None):
     """C[M,N] = epilogue(opA(A)[M,K] @ opB(B)[K,N]); leading dimensions in elements (row-major storage)."""
+    assert aux is None or aux.dtype == torch.float32, "the FFMA kernel takes an fp32 aux matrix (bit masks: tensor path only)"
     lib.call("msx_gemm_f32", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
              _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
              _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(colsum), lib.stream_ptr(),
              tag=_gemm_tag(M, N, K, accumulate, aux)[:2] + ("ffma M=%d N=%d K=%d tA=%d tB=%d sk=%d" % (M, N, K, transA, transB, splitk),))
 
 
+def _aux_kind(aux):
+    """0 fp32 matrix, 1 bfloat16 matrix, 2 ReLU bit mask (int32 words, msx_gemm_tc_ex)."""
+    if aux is None or aux.dtype == torch.float32:
+        return 0
+    if aux.dtype == torch.bfloat16:
+        return 1
+    assert aux.dtype == torch.int32, aux.dtype
+    return 2
+
+
+def _gemm_tc_ex(ab16, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux, aux_scale,
+                accumulate, splitk, out_colsum, mask_out, ldmask):
+    c16 = Cm.dtype == torch.bfloat16
+    ak = _aux_kind(aux)
+    eb = 2 if ab16 else 4
+    flops = 2.0 * M * N * K
+    aux_bytes = 0 if aux is None else (M * N / 8.0 if ak == 2 else M * N * (2 if ak == 1 else 4))
+    nbytes = eb * (M * K + N * K) + M * N * (2 if c16 else 4) * (1 + (1 if accumulate else 0)) + aux_bytes + \
+        (M * N / 8.0 if mask_out is not None else 0)
+    lib.call("msx_gemm_tc_ex", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N), _i(K),
+             _i(1 if ab16 else 0), _i(1 if c16 else 0), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site),
+             P(aux), _i(ldaux), _i(ak), _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), P(mask_out),
+             _i(ldmask), lib.stream_ptr(),
+             tag=(flops, nbytes, "%s M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s%s%s" % (
+                 "bf16" if ab16 else "tf32", M, N, K, transA, transB, splitk, " acc" if accumulate else "",
+                 (" aux%d" % ak) if aux is not None else "", " c16" if c16 else "", " mask" if mask_out is not None else "")))
+
+
 def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
-            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None):
-    """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
-    lib.call("msx_gemm_tc", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N),
-             _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
-             _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
-             tag=_gemm_tag(M, N, K, accumulate, aux)[:2] + ("tf32 M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s" % (
-                 M, N, K, transA, transB, splitk, " acc" if accumulate else "", " aux" if aux is not None else ""),))
+            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None, mask_out=None, ldmask=0):
+    """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate).  aux: fp32 matrix or an int32
+    ReLU bit mask (ldaux in words); mask_out: optional int32 [M, ldmask] bit mask of (C > 0), N % 32 == 0."""
+    _gemm_tc_ex(False, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
+                aux_scale, accumulate, splitk, out_colsum, mask_out, ldmask)
 
 
 def gemm_tc_bf16(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
-                 aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None):
-    """bf16 variant: A, B torch.bfloat16; Cm fp32 or bfloat16 (plain stores only); aux fp32 or bfloat16."""
+                 aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None, mask_out=None, ldmask=0):
+    """bf16 variant: A, B torch.bfloat16; Cm fp32 or bfloat16 (plain stores only); aux fp32 / bfloat16 / int32 bit mask."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16, (A.dtype, B.dtype)
-    c16 = Cm.dtype == torch.bfloat16
-    a16 = aux is not None and aux.dtype == torch.bfloat16
-    flops = 2.0 * M * N * K
-    nbytes = 2.0 * (M * K + N * K) + M * N * ((2 if c16 else 4) * (1 + (1 if accumulate else 0)) +
-                                              ((2 if a16 else 4) if aux is not None else 0))
-    lib.call("msx_gemm_tc_bf16", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(1 if c16 else 0),
-             _i(M), _i(N), _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux),
-             _i(1 if a16 else 0), _f(aux_scale), _i(1 if accumulate else 0), _i(splitk), P(out_colsum), lib.stream_ptr(),
-             tag=(flops, nbytes, "bf16 M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s%s" % (
-                 M, N, K, transA, transB, splitk, " acc" if accumulate else "", " aux" if aux is not None else "",
-                 " c16" if c16 else "")))
+    _gemm_tc_ex(True, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
+                aux_scale, accumulate, splitk, out_colsum, mask_out, ldmask)
 
 
 def gemm_tc_bf16_supported(A, lda, B, ldb, Cm, ldc, M, N, K):

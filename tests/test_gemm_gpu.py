@@ -253,3 +253,41 @@ def test_gemm_bf16_epilogues(impl):
     ops.gemm(Af, K, 0, Bf, K, 1, Cs, ldc, M, N, K, bias=bias, drop_p=0.25, seed=1234, site=3)
     torch.cuda.synchronize()
     assert float((C[:, :N].float() - Cs[:, :N]).abs().max()) / scale < 8e-3
+
+
+@pytest.mark.parametrize("impl", ["tc1", "tc2"])
+@pytest.mark.parametrize("ab16", [False, True])
+def test_gemm_relu_bit_mask(impl, ab16):
+    """msx_gemm_tc_ex: the forward epilogue writes the bit mask of (C > 0) after bias / ReLU / dropout, and a dgrad that
+    takes that mask as aux (4 bytes per 32 elements) equals the dgrad that re-reads C itself."""
+    from musicstyletransfer_b200 import ops
+    ops.gemm_tc_set_pair(impl == "tc2")
+    M, N, K = 333, 256, 256
+    mk = _mk16 if ab16 else (lambda r, c, ld, s: _mk(r, c, ld, s))
+    fn = ops.gemm_tc_bf16 if ab16 else ops.gemm_tc
+    Ad, Av = mk(M, K, K, 31)
+    Bd, Bv = mk(N, K, K, 32)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(33)).cuda()
+    for cdt in ([torch.float32, torch.bfloat16] if ab16 else [torch.float32]):
+        C = torch.zeros((M, N), device="cuda", dtype=cdt)
+        mask = torch.full((M, N // 32), -1, device="cuda", dtype=torch.int32)
+        fn(Ad, K, 0, Bd, K, 1, C, N, M, N, K, bias=bias, relu=True, drop_p=0.3, seed=77, site=1, mask_out=mask, ldmask=N // 32)
+        torch.cuda.synchronize()
+        bits = ((mask.cpu().numpy().astype(np.uint32)[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(M, N)
+        pos = (C.float() > 0).cpu().numpy()
+        if cdt == torch.float32:
+            assert (bits == pos).all()
+        else:       # the mask is taken on the fp32 value before the bf16 rounding: tiny positives may round to +0
+            assert (bits >= pos).all() and (bits != pos).mean() < 1e-3
+        # dgrad dX = (dY W) * mask * scale: bit mask vs the matrix itself
+        dY, _ = mk(M, K, K, 34)            # [M, K'] with K' = K as the reduction dim
+        W, _ = mk(K, N, N, 35)             # [K', N] stored as written (transB = 0)
+        out_a = torch.zeros((M, N), device="cuda", dtype=cdt)
+        out_b = torch.zeros((M, N), device="cuda", dtype=cdt)
+        cs_a, cs_b = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+        Cpos = (torch.from_numpy(bits.astype(np.float32)).cuda()).to(cdt).contiguous()      # same mask as a matrix
+        fn(dY, K, 0, W, N, 0, out_a, N, M, N, K, aux=Cpos, ldaux=N, aux_scale=1.25, out_colsum=cs_a)
+        fn(dY, K, 0, W, N, 0, out_b, N, M, N, K, aux=mask, ldaux=N // 32, aux_scale=1.25, out_colsum=cs_b)
+        torch.cuda.synchronize()
+        assert bool((out_a == out_b).all())
+        assert float((cs_a - cs_b).abs().max()) <= 1e-3 * float(cs_a.abs().max())
