@@ -146,13 +146,13 @@ int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const flo
 /* bf16 variant: the same kernels with an additional bfloat16 copy of the output that the bf16 GEMMs read
  * (out_bf16: LN output; dy_bf16: gradient of the Dense output y, or the combined gradient under fuse_xy).  Either may be
  * NULL; dy may be NULL when only the bf16 gradient is wanted.  Needs D % 128 == 0. */
-int msx_add_ln_fwd_ex(const float* x, const float* y, const float* gamma, const float* beta, float* out, void* out_bf16,
-                      float* mean, float* rstd, long long M, int D, float eps, float drop_p, unsigned long long seed,
-                      unsigned site, void* stream);
-int msx_add_ln_bwd_ex(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
+int msx_add_ln_fwd_ex(const float* x, const void* y, int y_bf16, const float* gamma, const float* beta, float* out,
+                      void* out_bf16, float* mean, float* rstd, long long M, int D, float eps, float drop_p,
+                      unsigned long long seed, unsigned site, void* stream);
+int msx_add_ln_bwd_ex(const float* x, const void* y, int y_bf16, const float* gamma, const float* mean, const float* rstd,
                       const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta, float* dybias,
                       long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres,
-                      int fuse_xy, void* stream);
+                      int fuse_xy, void* stream);   /* y_bf16: the Dense output y is bfloat16 (read only by this LayerNorm) */
 
 /* K2a — embedding front end.  Replaces model.py:81-91 + transformer.py:270 (encoder), model.py:241-247 +
  * transformer.py:237 (Transformer decoder, prefix = 1 latent-state row), model.py:176 (LSTM decoder).
@@ -167,6 +167,12 @@ int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_
                      int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                   float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
+
+/* num_classes = rows of the class table (0 = unknown).  Large problems without prefix rows and with <= 2 classes run a
+ * gather kernel (one CTA per vocabulary row and position segment, one atomic per column and CTA) instead of one
+ * red.global.add per element. */
+int msx_embed_bwd_ex(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
+                     float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, int num_classes, void* stream);
 
 /* K2g — persistent LSTM recurrence.  Replaces the fused gluon.rnn.LSTM call in LSTMDecoder.forward_train
  * (model.py:148-153,179); gx_inout [B,T,4H] holds x W_i2h^T + b_i2h on entry and the gate activations on exit;

@@ -29,9 +29,10 @@ __device__ __forceinline__ int elem_index(int i, int lane, int j) {
 }
 
 // s = x + drop(y) for this lane's elements of row `row`
+// y_bf16: y is bfloat16 (bf16 variant: the Dense output that only this LayerNorm reads), vector path only
 template <int VEC, int kPer>
-__device__ __forceinline__ void load_sum(const float* __restrict__ x, const float* __restrict__ y, size_t row, int D,
-                                         int nper, int lane, float p, float inv_keep, unsigned long long seed,
+__device__ __forceinline__ void load_sum(const float* __restrict__ x, const float* __restrict__ y, bool y_bf16, size_t row,
+                                         int D, int nper, int lane, float p, float inv_keep, unsigned long long seed,
                                          unsigned site, float s[kPer][VEC], float keep[kPer][VEC]) {
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
@@ -39,7 +40,14 @@ __device__ __forceinline__ void load_sum(const float* __restrict__ x, const floa
     if (VEC == 4) {
       const int e = (i * 32 + lane) * 4;
       const float4 xv = *reinterpret_cast<const float4*>(x + row * D + e);
-      const float4 yv = *reinterpret_cast<const float4*>(y + row * D + e);
+      float4 yv;
+      if (y_bf16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(y) + row * D + e);
+        yv = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                         __uint_as_float(u.y & 0xFFFF0000u));
+      } else {
+        yv = *reinterpret_cast<const float4*>(y + row * D + e);
+      }
       float k4[4] = {1.f, 1.f, 1.f, 1.f};
       if (p > 0.f) dropout_scale4(seed, site, (row * D + e) >> 2, p, inv_keep, k4);
       s[i][0] = xv.x + yv.x * k4[0];
@@ -60,7 +68,7 @@ __device__ __forceinline__ void load_sum(const float* __restrict__ x, const floa
 }
 
 template <int VEC, int kPer>
-__global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+__global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int y_bf16,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ out,
                                                                  unsigned short* __restrict__ out16,
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
   const float invD = 1.f / D;
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
     float s[kPer][VEC], keep[kPer][VEC];
-    load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    load_sum<VEC, kPer>(x, y, y_bf16 != 0, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kPer; ++i)
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
 // ds = rstd * (g*dout - mean(g*dout) - xhat * mean(g*dout*xhat));  dres = ds;  dy = ds * keep
 template <int VEC, int kPer>
 __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_kernel(
-    const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
+    const float* __restrict__ x, const float* __restrict__ y, int y_bf16, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
     float* __restrict__ dres, float* __restrict__ dy, unsigned short* __restrict__ dy16, float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed,
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
     unsigned keepbits = 0u;
     {
       float keep[kPer][VEC];
-      load_sum<VEC, kPer>(x, y, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+      load_sum<VEC, kPer>(x, y, y_bf16 != 0, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
 #pragma unroll
       for (int i = 0; i < kPer; ++i)
         if (i < nper)
@@ -241,9 +249,10 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
 
 }  // namespace
 
-extern "C" int msx_add_ln_fwd_ex(const float* x, const float* y, const float* gamma, const float* beta, float* out,
-                                 void* out_bf16, float* mean, float* rstd, long long M, int D, float eps, float drop_p,
-                                 unsigned long long seed, unsigned site, void* stream) {
+extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* beta,
+                                 float* out, void* out_bf16, float* mean, float* rstd, long long M, int D, float eps,
+                                 float drop_p, unsigned long long seed, unsigned site, void* stream) {
+  const float* y = reinterpret_cast<const float*>(y_any);
   MSX_REQUIRE(x && y && gamma && beta && out && mean && rstd, "msx_add_ln_fwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_fwd: D must be a multiple of 32");
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_add_ln_fwd: bad dropout");
@@ -252,10 +261,10 @@ extern "C" int msx_add_ln_fwd_ex(const float* x, const float* y, const float* ga
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 &&
                    ((uintptr_t)out_bf16 & 7) == 0;
-  MSX_REQUIRE(!out_bf16 || vec, "msx_add_ln_fwd: the bf16 output needs D %% 128 == 0 and 16-byte aligned tensors");
+  MSX_REQUIRE(!(out_bf16 || y_bf16) || vec, "msx_add_ln_fwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* out16 = reinterpret_cast<unsigned short*>(out_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -273,13 +282,15 @@ extern "C" int msx_add_ln_fwd_ex(const float* x, const float* y, const float* ga
 extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out,
                               float* mean, float* rstd, long long M, int D, float eps, float drop_p,
                               unsigned long long seed, unsigned site, void* stream) {
-  return msx_add_ln_fwd_ex(x, y, gamma, beta, out, nullptr, mean, rstd, M, D, eps, drop_p, seed, site, stream);
+  return msx_add_ln_fwd_ex(x, y, 0, gamma, beta, out, nullptr, mean, rstd, M, D, eps, drop_p, seed, site, stream);
 }
 
-extern "C" int msx_add_ln_bwd_ex(const float* x, const float* y, const float* gamma, const float* mean, const float* rstd,
-                                 const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta,
-                                 float* dybias, long long M, int D, float drop_p, unsigned long long seed, unsigned site,
-                                 int accumulate_dres, int fuse_xy, void* stream) {
+extern "C" int msx_add_ln_bwd_ex(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma,
+                                 float* dbeta, float* dybias, long long M, int D, float drop_p, unsigned long long seed,
+                                 unsigned site, int accumulate_dres, int fuse_xy, void* stream) {
+  const float* y = reinterpret_cast<const float*>(y_any);
+  MSX_REQUIRE(!(y_bf16 && fuse_xy), "msx_add_ln_bwd: fuse_xy (x and y alias) needs an fp32 y");
   MSX_REQUIRE(x && y && gamma && mean && rstd && dout && dres && dgamma && dbeta, "msx_add_ln_bwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
   if (M == 0) return MSX_OK;
@@ -287,10 +298,10 @@ extern "C" int msx_add_ln_bwd_ex(const float* x, const float* y, const float* ga
   const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
                                        (uintptr_t)gamma) & 15) == 0 && ((uintptr_t)dy_bf16 & 7) == 0;
-  MSX_REQUIRE(!dy_bf16 || vec, "msx_add_ln_bwd: the bf16 output needs D %% 128 == 0 and 16-byte aligned tensors");
+  MSX_REQUIRE(!(dy_bf16 || y_bf16) || vec, "msx_add_ln_bwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* dy16 = reinterpret_cast<unsigned short*>(dy_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
     const int nper = D / 128;
@@ -309,6 +320,6 @@ extern "C" int msx_add_ln_bwd(const float* x, const float* y, const float* gamma
                               const float* dout, float* dres, float* dy, float* dgamma, float* dbeta, float* dybias,
                               long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres, int fuse_xy,
                               void* stream) {
-  return msx_add_ln_bwd_ex(x, y, gamma, mean, rstd, dout, dres, dy, nullptr, dgamma, dbeta, dybias, M, D, drop_p, seed, site,
+  return msx_add_ln_bwd_ex(x, y, 0, gamma, mean, rstd, dout, dres, dy, nullptr, dgamma, dbeta, dybias, M, D, drop_p, seed, site,
                            accumulate_dres, fuse_xy, stream);
 }

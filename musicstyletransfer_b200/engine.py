@@ -390,7 +390,9 @@ class VAEEngine:
             ctx = bf.get(tag + "ctx", (M, D), dev)
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.cast_bf16(ctx, ctx16)
-        proj = bf.get(tag + "proj", (M, D), dev)
+        # the projection output and f feed only their LayerNorm (forward + backward): bf16 when LayerNorm reads x and y
+        # separately (encoder); the decoder's ln3(f + drop(f)) aliases x and y and keeps f fp32
+        proj = bf.get(tag + "proj16", (M, D), dev, b16)
         ops.gemm_tc_bf16(ctx16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 1, proj, D, M, D, D,
                          bias=self._W(prefix + "self_attention.W_proj.bias"))
         x1 = bf.get(tag + "x1", (M, D), dev)
@@ -403,7 +405,7 @@ class VAEEngine:
         ops.gemm_tc_bf16(x1h, D, 0, a.view16(prefix + "ff.ff1.weight"), D, 1, h16, 4 * D, M, 4 * D, D,
                          bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1,
                          mask_out=hmask, ldmask=4 * D // 32)
-        f = bf.get(tag + "f", (M, D), dev)
+        f = bf.get(tag + "f", (M, D), dev) if decoder else bf.get(tag + "f16", (M, D), dev, b16)
         ops.gemm_tc_bf16(h16, 4 * D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 1, f, D, M, D, 4 * D,
                          bias=self._W(prefix + "ff.ff2.bias"))
         out = bf.get(tag + "out", (M, D), dev)
@@ -426,11 +428,12 @@ class VAEEngine:
         M = B * T
         dev, a, b16, f32 = self.device, self.arena, torch.bfloat16, torch.float32
         seed = self.dropout_seed
-        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj", (M, D), f32)]
+        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj16", (M, D), b16)]
         ctx16 = bf.t[(tag + "ctx16", (M, D), b16)]
         x1, x1h = bf.t[(tag + "x1", (M, D), f32)], bf.t[(tag + "x1_16", (M, D), b16)]
         st1, st2 = bf.t[(tag + "st1", (2, M), f32)], bf.t[(tag + "st2", (2, M), f32)]
-        h16, f = bf.t[(tag + "h16", (M, 4 * D), b16)], bf.t[(tag + "f", (M, D), f32)]
+        h16 = bf.t[(tag + "h16", (M, 4 * D), b16)]
+        f = bf.t[(tag + "f", (M, D), f32)] if decoder else bf.t[(tag + "f16", (M, D), b16)]
         inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
         ln2 = "ln3" if decoder else "ln2"
         dx1 = bf.get(tag + "dx1", (M, D), dev)

@@ -156,14 +156,16 @@ def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
 
 def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0, out16=None):
     """out16: optional bfloat16 copy of the output (operand of the bf16 GEMMs)."""
-    lib.call("msx_add_ln_fwd_ex", P(x), P(y), P(gamma), P(beta), P(out), P(out16), P(mean), P(rstd), _ll(M), _i(D), _f(eps),
+    lib.call("msx_add_ln_fwd_ex", P(x), P(y), _i(1 if y.dtype == torch.bfloat16 else 0), P(gamma), P(beta), P(out), P(out16),
+             P(mean), P(rstd), _ll(M), _i(D), _f(eps),
              _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
 
 
 def add_ln_bwd(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, drop_p=0.0, seed=0, site=0,
                accumulate_dres=False, fuse_xy=False, dybias=None, dy16=None):
     """dy16: optional bfloat16 copy of the y-gradient (of the combined gradient under fuse_xy)."""
-    lib.call("msx_add_ln_bwd_ex", P(x), P(y), P(gamma), P(mean), P(rstd), P(dout), P(dres), P(dy), P(dy16), P(dgamma),
+    lib.call("msx_add_ln_bwd_ex", P(x), P(y), _i(1 if y.dtype == torch.bfloat16 else 0), P(gamma), P(mean), P(rstd), P(dout),
+             P(dres), P(dy), P(dy16), P(dgamma),
              P(dbeta), P(dybias), _ll(M), _i(D), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate_dres else 0),
              _i(1 if fuse_xy else 0), lib.stream_ptr())
 
@@ -175,8 +177,9 @@ def embed_fwd(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, 
 
 
 def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, prefix, scale, vocab):
-    lib.call("msx_embed_bwd", P(tokens), P(classes), P(dout), P(d_tok_emb), P(d_cls_emb), P(d_prefix), _i(B), _i(T),
-             _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
+    ncls = int(d_cls_emb.shape[0]) if d_cls_emb is not None else 0
+    lib.call("msx_embed_bwd_ex", P(tokens), P(classes), P(dout), P(d_tok_emb), P(d_cls_emb), P(d_prefix), _i(B), _i(T),
+             _i(D), _i(prefix), _f(scale), _i(vocab), _i(ncls), lib.stream_ptr())
 
 
 def reparam_kl_fwd(lat, eps, z, kl, B, Z):
