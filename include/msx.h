@@ -204,6 +204,10 @@ int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, float* ce, fl
                int V, int denom, int top_k, void* stream);
 int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B, int T,
                int V, int denom, float* dbias, void* stream);   /* dbias (optional) [V] += column sums of the gradient */
+/* msx_ce_fwd followed by msx_ce_bwd with head gradient 1 in one pass over the logits (training step): logits are read
+ * once and overwritten with the gradient.  V <= 512, 16-byte aligned rows; MSX_ERR_UNSUPPORTED otherwise. */
+int msx_ce_fwd_bwd(float* logits_inout, int ld, const int32_t* labels, float* ce, float* lse, float* metrics, int B, int T,
+                   int V, int denom, int top_k, float* dbias, void* stream);
 int msx_softmax_rows(const float* logits, int ld, float* probs, long long rows, int V, void* stream);
 int msx_ce_from_probs(const float* probs, const int32_t* labels, float* ce, int B, int T, int V, void* stream);
 int msx_bce(const float* pred, const uint8_t* label, float* out, const float* gout, float* dpred, int B,

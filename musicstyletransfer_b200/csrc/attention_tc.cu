@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(128 * G, 1)
     __syncwarp();
   }
   float mraw_next = (gt < T && first < p.items) ? __ldg(p.mask + (size_t)(first / p.H) * T + gt) : 0.f;
+  // coalesced context store through the dead P tile: pays off for fp32 rows (16-byte pieces of 32 different lines per
+  // store instruction otherwise; measured 167 -> 152 us); bf16 rows are 64 contiguous bytes per lane already and the
+  // extra group barrier costs more than the staging saves (138 -> 143 us), so they keep the row-per-lane store
+  const bool stage_ok = !p.out_bf16 && ((T + 31) / 32) * 4096 <= ((TQ + 31) / 32) * slab;
   int n = 0;
   for (int item = first; item < p.items; item += stride, ++n) {
     const int b = item / p.H, h = item % p.H;
@@ -242,9 +246,19 @@ __global__ void __launch_bounds__(128 * G, 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[j] += o2[j];
       }
-      if (q < T) store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
+      // P staging (this group's sP) is dead once MMA 2 has retired: the warp's 4 KB slice of it stages the context rows
+      // for a coalesced store; very short rows (the slice would not fit) keep the row-per-lane store
+      const int w4 = warp & 3;
+      if (stage_ok) {
+        store_tile32_coalesced(sP + w4 * 4096, p.ctx, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * D + h * DH, (size_t)D,
+                               T - w4 * 32, o, lane);
+      } else if (q < T) {
+        store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    // the staging slices overlap P rows that OTHER warps of the group write in the next item's softmax
+    if (stage_ok) group_sync(g);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(128)
 //   * the K-major tiles of the first two MMAs are double-buffered and prefetched one item ahead; the dS^T staging
 //     tile aliases the current stage once its MMAs have retired;
 //   * the bias-gradient column sums accumulate in registers across the items of a group (flushed when the head changes).
-template <int NCH>
+template <int NCH, bool STAGE>
 __global__ void __launch_bounds__(256, 1)
     attn_tc_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmQk,
                             const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
@@ -575,6 +589,10 @@ __global__ void __launch_bounds__(256, 1)
     __syncwarp();
   }
   float mraw_next = (gt < T && first < items) ? __ldg(p.mask + (size_t)(first / p.H) * T + gt) : 0.f;
+  // coalesced output store through the dead stage, fp32 outputs only (414 -> 397 us; bf16 outputs: 268 -> 348 us with
+  // it, the end-of-item group barrier stalls the pipeline more than the 64-byte-per-lane stores cost)
+  // (STAGE is a template parameter: the staged store costs registers the row-per-lane variant must not pay for)
+  constexpr bool stage_ok = STAGE;
   int n = 0;
   for (int item = first; item < items; item += stride, ++n) {
     const int b = item / p.H, h = item % p.H;
@@ -719,17 +737,26 @@ __global__ void __launch_bounds__(256, 1)
         tmem_ld16_issue(src + lane_off + 16, o + 16);
         tmem_ld16_wait(o);
         tmem_ld16_wait(o + 16);
-        if (gt < T) {
+        // the stage (K-major tiles / dS^T) is dead once the output MMAs have retired: the warp's 4 KB slice of it stages
+        // the rows for a coalesced store
+        if (stage_ok) {
+          const int w4 = warp & 3;
+          store_tile32_coalesced(sY + w4 * 4096, p.dqkv, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * 3 * D + h * DH + m * D,
+                                 (size_t)3 * D, T - w4 * 32, o, lane);
+        } else if (gt < T) {
           store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o);
-          if (p.dbias) {
+        }
+        if (gt < T && p.dbias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[m * 32 + j] += o[j];
-          }
+          for (int j = 0; j < 32; ++j) acc[m * 32 + j] += o[j];
         }
       }
+      if (stage_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staging (generic proxy) before the next TMA fill
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     if (gt == 0) MSX_STAMP(8);
+    // the issuer refills this stage (item n + 2) at the top of the next item: every warp must be done staging in it
+    if (stage_ok) group_sync(g);
   }
 #undef MSX_STAMP
   flush_bias();
@@ -856,10 +883,17 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
     const int items = B * H;
     const int want = (items + 1) / 2;
     const int grid = want < msx_num_sms() ? want : msx_num_sms();
+    // fp32 outputs leave through a shared-memory staging tile (coalesced rows) when it fits into a pipeline stage
+    const bool stage = !p.out_bf16 && ((T + 31) / 32) * 4096 <= stage_bytes;
 #define MSX_BWD_PIPE(NCH)                                                                                              \
   case NCH:                                                                                                            \
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    attn_tc_bwd_pipe_kernel<NCH><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024);        \
+    if (stage) {                                                                                                       \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    } else {                                                                                                           \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, false><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    }                                                                                                                  \
     break;
     switch (p.TQ / 16) {
       MSX_BWD_PIPE(1)

@@ -134,6 +134,49 @@ __device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, 
   }
 }
 
+// Coalesced form of store_row32 for a whole warp: lane l holds row l of a 32-row x 32-column tile; the tile goes through
+// a 4 KB shared-memory staging area `wst` (private to the warp, swizzled so that both directions are conflict-free) and
+// leaves with every quarter-warp writing one full 128-byte (bf16: eighth-warp, 64-byte) row segment.  With one row per
+// lane a store instruction touches 32 lines at 16 bytes each; this way it touches 4 full lines.  elem0 = element offset
+// of (row 0, column 0) of the tile, pitch = elements between rows, rows_valid = rows of the tile to write (<= 0: none).
+__device__ __forceinline__ void store_tile32_coalesced(unsigned char* wst, void* base, bool bf16, size_t elem0, size_t pitch,
+                                                       int rows_valid, const float* o, int lane) {
+  if (bf16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(o[8 * j + 1]), "f"(o[8 * j + 0]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(o[8 * j + 3]), "f"(o[8 * j + 2]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.z) : "f"(o[8 * j + 5]), "f"(o[8 * j + 4]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.w) : "f"(o[8 * j + 7]), "f"(o[8 * j + 6]));
+      *reinterpret_cast<uint4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+    }
+    __syncwarp();
+    unsigned short* dst = reinterpret_cast<unsigned short*>(base) + elem0;
+    const int c = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2);
+      const uint4 w = *reinterpret_cast<const uint4*>(wst + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * pitch + 8 * c) = w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(wst + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    __syncwarp();
+    float* dst = reinterpret_cast<float*>(base) + elem0;
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3);
+      const float4 w = *reinterpret_cast<const float4*>(wst + r * 128 + ((c ^ (r & 7)) << 4));
+      if (r < rows_valid) *reinterpret_cast<float4*>(dst + (size_t)r * pitch + 4 * c) = w;
+    }
+  }
+  __syncwarp();
+}
+
 // MN-major operand, SWIZZLE_128B_BASE32B: element (mn, k) of a slab-structured tile with `krows` rows per slab
 __device__ __forceinline__ unsigned mn_major_off(int mn, int k, int krows) {
   return (unsigned)((mn >> 5) * (krows * 128) + k * 128 + ((((mn & 31) >> 3) ^ (k & 3)) << 5) + ((mn & 7) << 2));

@@ -27,18 +27,18 @@ constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 B = one swi
 constexpr int kStages = 4;
 constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kTileBytes;
-// Epilogue warps: kColSplit warps per TMEM lane group (a warp may only touch lanes 32 * (warp % 4) ..), each draining
-// 1 / kColSplit of the tile's columns.  The wide-N, short-K GEMMs of the step (QKV, FF1 forward, FF2 dgrad) are paced
-// by the epilogue's instruction issue (ncu: 2 epilogue warps per scheduler reach ~50 % issue utilisation), hence four
-// warps per lane group with one staging box each is available (-DMSX_GEMM_EPI_WARPS=16); measured on the step it
-// speeds the dropout epilogue up by 12 % and slows the mainloop-paced GEMMs down by 1-3 %: a wash, the default stays 8.
-#ifndef MSX_GEMM_EPI_WARPS
-#define MSX_GEMM_EPI_WARPS 8
-#endif
-constexpr int kEpiWarps = MSX_GEMM_EPI_WARPS;
-constexpr int kColSplit = kEpiWarps / 4;
-constexpr int kBoxes = kEpiWarps == 8 ? 2 : 1;       // staging boxes per epilogue warp
-constexpr int kThreads = 32 * (2 + kEpiWarps);       // warp 0 TMA, warp 1 MMA, then the epilogue warps
+// Epilogue warps: EW / 4 warps per TMEM lane group (a warp may only touch lanes 32 * (warp % 4) ..), each draining
+// 4 / EW of the tile's columns.  EW = 8 (two staging boxes per warp) is the default; the wide-N, short-K GEMMs of the
+// step (QKV, FF1 forward, FF2 dgrad: K <= 256, N >= 512) are paced by the epilogue's instruction issue (ncu: 2 epilogue
+// warps per scheduler reach ~50 % issue utilisation) and run with EW = 16 (one box per warp): measured 202 -> 162 us
+// (FF1 forward, bf16), 155 -> 137 us (FF2 dgrad), 112 -> 103 us (QKV); the mainloop-paced shapes are 1-3 % slower with
+// 16 and keep 8.
+template <int EW>
+struct EpiCfg {
+  static constexpr int kColSplit = EW / 4;
+  static constexpr int kBoxes = EW == 8 ? 2 : 1;     // staging boxes per epilogue warp
+  static constexpr int kThreads = 32 * (2 + EW);     // warp 0 TMA, warp 1 MMA, then the epilogue warps
+};
 constexpr int kOutBoxBytes = 32 * 128;               // epilogue staging box: 32 rows x 32 fp32
 constexpr int kTmemCols = 256;                      // 2 accumulators x 128 fp32 columns
 
@@ -241,6 +241,7 @@ __device__ __forceinline__ unsigned aux_mask(const TcParams& p, const AuxPref& a
 // Epilogue for one 32-row x 32-column chunk held in the row-owner layout (lane = row, v[j] = column col0 + j):
 // bias / ReLU / dropout / aux mask / bias-gradient column sums, then a SWIZZLE_128B staging box that the TMA
 // engine stores (or reduce-adds) into C.
+template <int EW>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensorMap* tmc, float (&v)[32], int row0,
                                                int my_row, int col0, int lane, unsigned char* st, int& sbuf,
                                                int& pending, bool reduce, unsigned amask) {
@@ -294,6 +295,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
       if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs);
     }
     // ---- stage as a SWIZZLE_128B box (row = lane, 8 x 16 B chunks XOR-ed with row % 8) and let TMA write it
+    constexpr int kBoxes = EpiCfg<EW>::kBoxes;
     unsigned char* box = st + sbuf * kOutBoxBytes;
     if (pending >= kBoxes) {                // the box we are about to overwrite must have been read
       if (elect_one()) {
@@ -332,14 +334,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
     if (pending < kBoxes) ++pending;
 }
 
-template <bool A_MN, bool B_MN, bool BF>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool A_MN, bool B_MN, bool BF, int EW>
+__global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* stage_out = ring + kStages * kStageBytes;                        // [kEpiWarps][2][32 rows][128 B]
+  constexpr int kEpiWarps = EW, kColSplit = EpiCfg<EW>::kColSplit, kBoxes = EpiCfg<EW>::kBoxes;
+  unsigned char* stage_out = ring + kStages * kStageBytes;                        // [kEpiWarps][kBoxes][32 rows][128 B]
   Barriers* bars = reinterpret_cast<Barriers*>(stage_out + kEpiWarps * kBoxes * kOutBoxBytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
+          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -566,14 +569,15 @@ __device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
       : "memory");
 }
 
-template <int BN2, bool A_MN, bool B_MN, bool BF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int BN2, bool A_MN, bool B_MN, bool BF, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   using Cfg = PairCfg<BN2>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* stage_out = ring + Cfg::kStages2 * Cfg::kStage;                  // [kEpiWarps][2][32 rows][128 B]
+  constexpr int kEpiWarps = EW, kColSplit = EpiCfg<EW>::kColSplit, kBoxes = EpiCfg<EW>::kBoxes;
+  unsigned char* stage_out = ring + Cfg::kStages2 * Cfg::kStage;                  // [kEpiWarps][kBoxes][32 rows][128 B]
   Barriers2* bars = reinterpret_cast<Barriers2*>(stage_out + kEpiWarps * kBoxes * kOutBoxBytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
@@ -707,7 +711,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN2 + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
+          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -766,34 +770,51 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
   return MSX_OK;
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiWarps * kBoxes * kOutBoxBytes + sizeof(Barriers);
+template <int EW>
+constexpr size_t smem_bytes_1cta() {
+  return 1024 + (size_t)kStages * kStageBytes + (size_t)EW * EpiCfg<EW>::kBoxes * kOutBoxBytes + sizeof(Barriers);
+}
 
-template <bool A_MN, bool B_MN, bool BF>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
-  MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+template <bool A_MN, bool B_MN, bool BF, int EW>
+int launch_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = smem_bytes_1cta<EW>();
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int grid = items < msx_num_sms() ? items : msx_num_sms();
-  gemm_tc_kernel<A_MN, B_MN, BF><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tc, p);
+  gemm_tc_kernel<A_MN, B_MN, BF, EW><<<grid, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, p);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
-
-template <int BN2>
-constexpr size_t pair_smem_bytes() {
-  return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)kEpiWarps * kBoxes * kOutBoxBytes + sizeof(Barriers2);
+template <bool A_MN, bool B_MN, bool BF>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+  return launch_ew<A_MN, B_MN, BF, 8>(ta, tb, tc, p, st);        // K < 256 here: mainloop too short for pair tiles, 8 warps
 }
 
-template <int BN2, bool A_MN, bool B_MN, bool BF>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = pair_smem_bytes<BN2>();
+template <int BN2, int EW>
+constexpr size_t pair_smem_bytes() {
+  return 1024 + (size_t)PairCfg<BN2>::kStages2 * PairCfg<BN2>::kStage + (size_t)EW * EpiCfg<EW>::kBoxes * kOutBoxBytes + sizeof(Barriers2);
+}
+
+template <int BN2, bool A_MN, bool B_MN, bool BF, int EW>
+int launch_pair_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = pair_smem_bytes<BN2, EW>();
   static_assert(smem <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
-  MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2_kernel<BN2, A_MN, B_MN, BF><<<2 * pairs, kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
+  gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW><<<2 * pairs, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
   MSX_LAUNCH_CHECK();
   return MSX_OK;
+}
+// epilogue-paced shapes (short K, wide N, plain stores) take 16 epilogue warps: see EpiCfg
+
+template <int BN2, bool A_MN, bool B_MN, bool BF>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+  static const int forced = [] { const char* e = getenv("MSX_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  const bool wide = forced == 16 || (forced != 8 && p.K <= 256 && p.N >= 512 && !p.accumulate && p.splitk == 1);
+  if (wide) return launch_pair_ew<BN2, A_MN, B_MN, BF, 16>(ta, tb, tc, p, st);
+  return launch_pair_ew<BN2, A_MN, B_MN, BF, 8>(ta, tb, tc, p, st);
 }
 
 // 2-CTA path switch: MSX_GEMM_PAIR=0 in the environment or msx_gemm_tc_set_pair(0) forces the 1-CTA kernel

@@ -31,9 +31,11 @@ __device__ __forceinline__ int elem_index(int i, int lane, int j) {
 // s = x + drop(y) for this lane's elements of row `row`
 // y_bf16: y is bfloat16 (bf16 variant: the Dense output that only this LayerNorm reads), vector path only
 template <int VEC, int kPer>
-__device__ __forceinline__ void load_sum(const float* __restrict__ x, const float* __restrict__ y, bool y_bf16, size_t row,
+__device__ __forceinline__ void load_sum(const float* x, const float* y, bool y_bf16, size_t row, size_t rng_row,
                                          int D, int nper, int lane, float p, float inv_keep, unsigned long long seed,
                                          unsigned site, float s[kPer][VEC], float keep[kPer][VEC]) {
+  // row addresses x / y (0 when they point at this warp's shared-memory copy of the row), rng_row is the row's index in
+  // the tensor (dropout counter)
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     if (i >= nper) break;
@@ -49,7 +51,7 @@ __device__ __forceinline__ void load_sum(const float* __restrict__ x, const floa
         yv = *reinterpret_cast<const float4*>(y + row * D + e);
       }
       float k4[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p > 0.f) dropout_scale4(seed, site, (row * D + e) >> 2, p, inv_keep, k4);
+      if (p > 0.f) dropout_scale4(seed, site, (rng_row * D + e) >> 2, p, inv_keep, k4);
       s[i][0] = xv.x + yv.x * k4[0];
       s[i][1 % VEC] = xv.y + yv.y * k4[1];
       s[i][2 % VEC] = xv.z + yv.z * k4[2];
@@ -59,8 +61,8 @@ __device__ __forceinline__ void load_sum(const float* __restrict__ x, const floa
     } else {
       const int e = i * 32 + lane;
       float k4[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p > 0.f) dropout_scale4(seed, site, (row * D + e) >> 2, p, inv_keep, k4);
-      const float kk = k4[(row * D + e) & 3];
+      if (p > 0.f) dropout_scale4(seed, site, (rng_row * D + e) >> 2, p, inv_keep, k4);
+      const float kk = k4[(rng_row * D + e) & 3];
       s[i][0] = x[row * D + e] + y[row * D + e] * kk;
       keep[i][0] = kk;
     }
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
   const float invD = 1.f / D;
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
     float s[kPer][VEC], keep[kPer][VEC];
-    load_sum<VEC, kPer>(x, y, y_bf16 != 0, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+    load_sum<VEC, kPer>(x, y, y_bf16 != 0, (size_t)row, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kPer; ++i)
@@ -128,7 +130,20 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
 }
 
 // ds = rstd * (g*dout - mean(g*dout) - xhat * mean(g*dout*xhat));  dres = ds;  dy = ds * keep
-template <int VEC, int kPer>
+// kAsync (vector path, kPer <= 2): the three input rows of the NEXT row this warp will process are already on their way
+// into a per-warp shared-memory slot (cp.async, each lane copies exactly the elements it will read back, so a
+// cp.async.wait_group is the only synchronisation) while the current row is reduced and stored.  The kernel is
+// latency-bound (ncu: 0.3 eligible warps per scheduler, 72 % of the stall cycles on the row loads): this keeps one row
+// per warp in flight all the time instead of only between the load and the first reduction.
+__device__ __forceinline__ void ln_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ln_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+constexpr int kLnStages = 2;
+
+template <int VEC, int kPer, bool kAsync>
 __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, int y_bf16, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
@@ -146,14 +161,46 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
 #pragma unroll
     for (int j = 0; j < VEC; ++j) dg[i][j] = db[i][j] = dyb[i][j] = 0.f;
 
-  for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
-    // s = x + drop(y); the keep mask is held as one bit per element (registers: 88 -> 4 CTAs per SM; the kernel is
-    // latency-bound on its three row loads, occupancy is what hides them)
+  extern __shared__ __align__(16) unsigned char ln_dyn[];
+  // per warp and stage: x | y | dout slots of kPer * 32 float4 (a bf16 y uses the first half of its slot)
+  float* wbuf = reinterpret_cast<float*>(ln_dyn) + (size_t)warp * kLnStages * 3 * kPer * 128;
+  const long long row_first = (long long)blockIdx.x * kWarps + warp, row_stride = (long long)gridDim.x * kWarps;
+  auto issue = [&](long long r, int stage) {
+    if (r < M) {
+      float* sb = wbuf + (size_t)stage * 3 * kPer * 128;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        if (i >= nper) break;
+        const int e = (i * 32 + lane) * 4;
+        ln_cp_async16(sb + e, x + (size_t)r * D + e);
+        if (y_bf16) ln_cp_async8(reinterpret_cast<unsigned short*>(sb + kPer * 128) + e, reinterpret_cast<const unsigned short*>(y) + (size_t)r * D + e);
+        else ln_cp_async16(sb + kPer * 128 + e, y + (size_t)r * D + e);
+        ln_cp_async16(sb + 2 * kPer * 128 + e, dout + (size_t)r * D + e);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (kAsync) issue(row_first, 0);
+  int it = 0;
+  for (long long row = row_first; row < M; row += row_stride, ++it) {
+    // s = x + drop(y); the keep mask is held as one bit per element
     float s[kPer][VEC];
     unsigned keepbits = 0u;
+    const float* xsrc = x;
+    const float* ysrc = y;
+    const float* dsrc = dout;
+    size_t arow = (size_t)row;
+    if (kAsync) {
+      issue(row + row_stride, (it + 1) % kLnStages);          // next row on its way before this one is consumed
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      xsrc = wbuf + (size_t)(it % kLnStages) * 3 * kPer * 128;
+      ysrc = xsrc + kPer * 128;
+      dsrc = xsrc + 2 * kPer * 128;
+      arow = 0;
+    }
     {
       float keep[kPer][VEC];
-      load_sum<VEC, kPer>(x, y, y_bf16 != 0, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
+      load_sum<VEC, kPer>(xsrc, ysrc, y_bf16 != 0, arow, (size_t)row, D, nper, lane, p, inv_keep, seed, site, s, keep);
 #pragma unroll
       for (int i = 0; i < kPer; ++i)
         if (i < nper)
@@ -169,7 +216,7 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
       float dv[VEC], gv[VEC];
       if (VEC == 4) {
         const int e = (i * 32 + lane) * 4;
-        const float4 d4 = *reinterpret_cast<const float4*>(dout + (size_t)row * D + e);
+        const float4 d4 = *reinterpret_cast<const float4*>(dsrc + arow * D + e);
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + e));
         dv[0] = d4.x; dv[1 % VEC] = d4.y; dv[2 % VEC] = d4.z; dv[3 % VEC] = d4.w;
         gv[0] = g4.x; gv[1 % VEC] = g4.y; gv[2 % VEC] = g4.z; gv[3 % VEC] = g4.w;
@@ -301,17 +348,29 @@ extern "C" int msx_add_ln_bwd_ex(const float* x, const void* y_any, int y_bf16, 
   MSX_REQUIRE(!(dy_bf16 || y_bf16) || vec, "msx_add_ln_bwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* dy16 = reinterpret_cast<unsigned short*>(dy_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P, false><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD_ASYNC(P)                                                                                                   \
+  do {                                                                                                                    \
+    const int dyn = kWarps * kLnStages * 3 * P * 128 * 4;                                                                 \
+    MSX_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<4, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));      \
+    add_ln_bwd_kernel<4, P, true><<<grid, kWarps * 32, dyn, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16,  \
+        dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy);         \
+  } while (0)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");
     const int nper = D / 128;
-    if (nper <= 1) LN_BWD(4, 1); else if (nper <= 2) LN_BWD(4, 2); else if (nper <= 4) LN_BWD(4, 4); else LN_BWD(4, 8);
+    // accumulate_dres reads dres in the same pass and fuse_xy aliases x and y: both keep the direct-load kernel
+    const bool async_ok = !accumulate_dres && !fuse_xy;
+    if (nper <= 1) { if (async_ok) LN_BWD_ASYNC(1); else LN_BWD(4, 1); }
+    else if (nper <= 2) { if (async_ok) LN_BWD_ASYNC(2); else LN_BWD(4, 2); }
+    else if (nper <= 4) LN_BWD(4, 4); else LN_BWD(4, 8);
   } else {
     MSX_REQUIRE(D <= 32 * kMaxPer, "msx_add_ln_bwd: D=%d unsupported", D);
     const int nper = D / 32;
     if (nper <= 2) LN_BWD(1, 2); else LN_BWD(1, 8);
   }
 #undef LN_BWD
+#undef LN_BWD_ASYNC
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

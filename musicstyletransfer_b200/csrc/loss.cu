@@ -235,6 +235,88 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(float* __restrict__ logits,
   }
 }
 
+// Training path: forward and backward of the cross-entropy in ONE pass over the logits (the row is in registers anyway):
+// ce / lse / metrics as ce_fwd_kernel, then the row is overwritten with d(sum_b ce_b) / d logits as ce_bwd_kernel with
+// head gradient 1 — the logits are read once and written once instead of read twice and written once.
+__global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
+                                                         float* __restrict__ ce, float* __restrict__ lse_out,
+                                                         float* __restrict__ metrics, int rows, int T, int V, int top_k,
+                                                         float inv_denom, float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
+  float bs[kCeMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kCeMaxPerLane; ++i) bs[i] = 0.f;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    float* x = logits + (size_t)row * ld;
+    const int label = __ldg(labels + row);
+    float r[kCeMaxPerLane];
+    ce_load_row<true>(x, V, ld, lane, r);
+    float mx = r[0];
+#pragma unroll
+    for (int i = 1; i < kCeMaxPerLane; ++i) mx = fmaxf(mx, r[i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane; ++i) sum += expf(r[i] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    if (lane == 0) lse_out[row] = lse;
+    if (label != 0) {
+      const int lc = min(max(label, 0), V - 1);
+      float mine = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane; ++i) mine = ce_col<true>(lane, i) == lc ? r[i] : mine;
+      const float picked = warp_max(mine);
+      int greater = 0;
+#pragma unroll
+      for (int i = 0; i < kCeMaxPerLane; ++i) greater += r[i] > picked ? 1 : 0;
+      greater = __reduce_add_sync(MSX_FULL, greater);
+      const float nll = lse - picked;
+      if (lane == 0) {
+        atomicAdd(ce + row / T, nll * inv_denom);
+        m_nll += fminf(nll, 23.02585093f);
+        m_tok += 1.f;
+        m_hit += greater == 0 ? 1.f : 0.f;
+        m_topk += greater < top_k ? 1.f : 0.f;
+      }
+    }
+    const float g = label != 0 ? inv_denom : 0.f;
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane; ++i) {
+      const int c = ce_col<true>(lane, i);
+      r[i] = (c < V && label != 0) ? (expf(r[i] - lse) - (c == label ? 1.f : 0.f)) * g : 0.f;
+      bs[i] += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane / 4; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < ld) *reinterpret_cast<float4*>(x + c) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+  }
+  __shared__ float red[8][kCeMaxPerLane * 32];
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < kCeMaxPerLane; ++i) red[warp][i * 32 + lane] = bs[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < kCeMaxPerLane * 32; j += blockDim.x) {
+      float a = 0.f;
+      for (int w = 0; w < nw; ++w) a += red[w][j];
+      const int c = ce_col<true>(j & 31, j >> 5);
+      if (c < V && a != 0.f) atomicAdd(dbias + c, a);
+    }
+    __syncthreads();
+  }
+  if (!metrics) return;
+  if (lane == 0) { red[warp][0] = m_nll; red[warp][1] = m_tok; red[warp][2] = m_hit; red[warp][3] = m_topk; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[w][threadIdx.x];
+    if (a != 0.f) atomicAdd(metrics + threadIdx.x, a);
+  }
+}
+
 __global__ void __launch_bounds__(256) ce_bwd_big_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
                                                          const float* __restrict__ lse, const float* __restrict__ gout,
                                                          int rows, int T, int V, float inv_denom) {
@@ -416,6 +498,28 @@ extern "C" int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, co
     ce_bwd_kernel<true><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
   else
     ce_bwd_kernel<false><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
+// Fused training path (head gradient 1): see ce_fwd_bwd_kernel.  Needs the register path (V <= 512) and 16-byte aligned rows;
+// returns MSX_ERR_UNSUPPORTED otherwise (callers then use msx_ce_fwd + msx_ce_bwd).
+extern "C" int msx_ce_fwd_bwd(float* logits_inout, int ld, const int32_t* labels, float* ce, float* lse, float* metrics, int B,
+                              int T, int V, int denom, int top_k, float* dbias, void* stream) {
+  MSX_REQUIRE(logits_inout && labels && ce && lse, "msx_ce_fwd_bwd: null pointer");
+  MSX_REQUIRE(ld >= V && V > 0, "msx_ce_fwd_bwd: bad leading dimension");
+  if (B == 0) return MSX_OK;
+  MSX_REQUIRE(denom > 0, "msx_ce_fwd_bwd: denom must be > 0");
+  MSX_REQUIRE((long long)B * T < (1ll << 31), "msx_ce_fwd_bwd: B * T must fit 31 bits");
+  if (V > 32 * kCeMaxPerLane || (ld & 3) != 0 || ((uintptr_t)logits_inout & 15) != 0) {
+    msx_set_error("msx_ce_fwd_bwd: needs V <= 512 and 16-byte aligned rows");
+    return MSX_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * T;
+  MSX_CUDA(cudaMemsetAsync(ce, 0, (size_t)B * sizeof(float), st));
+  const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
+  ce_fwd_bwd_kernel<<<grid, 256, 0, st>>>(logits_inout, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom, dbias);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

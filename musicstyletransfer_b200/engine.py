@@ -701,7 +701,7 @@ class VAEEngine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
-                z_override=None):
+                z_override=None, fuse_ce_bwd=False):
         """tokens int32 [B,T], seq_lens int32 [B], classes int32 [B], labels int32 [B,T] (optional),
         eps fp32 [B,Z] (None -> Philox N(0,1)).  Returns dict(ce, kl, means, stds[, probs])."""
         cfg, dev = self.cfg, self.device
@@ -779,7 +779,14 @@ class VAEEngine:
                 lab_full = labels
             ce = bf.get("ce", (B,), dev)
             lse = bf.get("lse", (Mo,), dev)
-            ops.ce_fwd(logits, self.ldv, lab_full, ce, lse, self.metrics, B, Td, V, T)
+            # fuse_ce_bwd (train_step): the cross-entropy backward with head gradient 1 runs in the same pass — the
+            # logits are read once and leave this call holding d loss / d logits (backward() then skips msx_ce_bwd)
+            ce_fused = bool(fuse_ce_bwd and not want_probs and ops.ce_fwd_bwd_supported(logits, self.ldv, V))
+            if ce_fused:
+                ops.ce_fwd_bwd(logits, self.ldv, lab_full, ce, lse, self.metrics, B, Td, V, T,
+                               dbias=self._G("decoder.output_layer.bias"))
+            else:
+                ops.ce_fwd(logits, self.ldv, lab_full, ce, lse, self.metrics, B, Td, V, T)
             out["ce"] = ce
         if want_probs:
             probs = torch.empty((Mo, V), dtype=torch.float32, device=dev)
@@ -788,7 +795,8 @@ class VAEEngine:
             out["probs"] = probs[:, 1:, :] if cfg.dec_type == "transformer" else probs
         self.ctx = dict(B=B, T=T, Td=Td, tokens=tokens, seq_lens=seq_lens, classes=classes, labels=lab_full, eps=eps,
                         xs=xs, mask=mask, lat=lat, z=z, dec_out=dec_out, logits=logits, pe=pe_, pd=pd_, bf=bf,
-                        dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None, xs16=self._xs16)
+                        dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None, xs16=self._xs16,
+                        ce_fused=bool(labels is not None and ce_fused))
         return out
 
     # ------------------------------------------------------------------ backward
@@ -803,8 +811,11 @@ class VAEEngine:
         logits = c["logits"]
         lse = bf.t[("lse", (Mo,), torch.float32)]
         fuse_db = V <= 512
-        ops.ce_bwd(logits, self.ldv, c["labels"], lse, g_ce, B, Td, V, T,       # logits now hold dlogits
-                   dbias=self._G("decoder.output_layer.bias") if fuse_db else None)
+        if c.get("ce_fused"):
+            assert g_ce is None, "forward(fuse_ce_bwd=True) already wrote d ce / d logits with head gradient 1"
+        else:
+            ops.ce_bwd(logits, self.ldv, c["labels"], lse, g_ce, B, Td, V, T,       # logits now hold dlogits
+                       dbias=self._G("decoder.output_layer.bias") if fuse_db else None)
         ddec = bf.get("ddec", (Mo, Hd), dev)
         self._dense_bwd(logits, self.ldv, Mo, c["dec_out"], Hd, self._W("decoder.output_layer.weight"),
                         self._G("decoder.output_layer.weight"), None if fuse_db else self._G("decoder.output_layer.bias"),
@@ -939,7 +950,7 @@ class VAEEngine:
             ops.set_step_counter(st["counter"])
             try:
                 with torch.cuda.graph(graph):
-                    out = self.forward(*st["in"][:3], st["in"][3], train=True)
+                    out = self.forward(*st["in"][:3], st["in"][3], train=True, fuse_ce_bwd=True)
                     self.backward(kl_weight)
                     if not two:
                         self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient, peer=peer)
@@ -968,7 +979,7 @@ class VAEEngine:
                    clip_gradient=None, allreduce=None):
         """allreduce: None (single GPU), a callable applied to the flat gradient arena (e.g. NCCL all-reduce), or "peer"
         (fused NVLink reduce-scatter + Adam + all-gather, after enable_peer_optimizer)."""
-        out = self.forward(tokens, seq_lens, classes, labels, eps=eps, train=True)
+        out = self.forward(tokens, seq_lens, classes, labels, eps=eps, train=True, fuse_ce_bwd=True)
         self.backward(kl_weight)
         peer = isinstance(allreduce, str) and allreduce == "peer"
         if allreduce is not None and not peer:

@@ -200,6 +200,16 @@ def ce_fwd(logits, ld, labels, ce, lse, metrics, B, T, V, denom, top_k=5):
              _i(top_k), lib.stream_ptr())
 
 
+def ce_fwd_bwd(logits, ld, labels, ce, lse, metrics, B, T, V, denom, dbias=None, top_k=5):
+    """Training path: msx_ce_fwd + msx_ce_bwd (head gradient 1) in one pass; the logits are overwritten with the gradient."""
+    lib.call("msx_ce_fwd_bwd", P(logits), _i(ld), P(labels), P(ce), P(lse), P(metrics), _i(B), _i(T), _i(V), _i(denom),
+             _i(top_k), P(dbias), lib.stream_ptr())
+
+
+def ce_fwd_bwd_supported(logits, ld, V):
+    return V <= 512 and ld % 4 == 0 and logits.data_ptr() % 16 == 0
+
+
 def ce_bwd(logits, ld, labels, lse, gout, B, T, V, denom, dbias=None):
     lib.call("msx_ce_bwd", P(logits), _i(ld), P(labels), P(lse), P(gout), _i(B), _i(T), _i(V), _i(denom), P(dbias),
              lib.stream_ptr())

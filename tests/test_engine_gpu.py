@@ -371,3 +371,24 @@ def test_tf32_long_rows_step_vs_oracle(T):
     print("tf32 long-row gradient deviation, worst tensors:", devs[:4])
     assert devs[0][0] < 5e-2
     assert sum(d for d, _ in devs) / len(devs) < 2e-2
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_fused_ce_backward_equals_two_pass(prec):
+    """forward(fuse_ce_bwd=True) (msx_ce_fwd_bwd: one pass over the logits) gives the same losses, metrics and gradients
+    as msx_ce_fwd followed by msx_ce_bwd."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    tokens, seq_lens, classes, labels, eps = _batch(16, 33, 293, 2, 256, seed=11, min_len=9)
+    args = [_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels)]
+    res = []
+    for fused in (False, True):
+        eng = VAEEngine(VAEConfig(dec_type="lstm"), "cuda:0", seed=2, precision=prec)
+        out = eng.forward(*args, eps=_dev(eps, torch.float32), fuse_ce_bwd=fused)
+        ce = out["ce"].clone()
+        eng.backward()
+        torch.cuda.synchronize()
+        res.append((ce, eng.arena.g.clone(), eng.metrics.clone()))
+    (ce0, g0, m0), (ce1, g1, m1) = res
+    assert float((ce0 - ce1).abs().max()) <= 1e-6 * float(ce0.abs().max())
+    assert float((m0 - m1).abs().max()) <= 1e-5 * float(m0.abs().max())
+    assert float((g0 - g1).abs().max()) <= 2e-5 * float(g0.abs().max())        # atomics: summation order only
