@@ -83,54 +83,86 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ 
   }
 }
 
-// Backward without per-element atomics (prefix == 0, at most two classes).  The scatter d_tok_emb[tok] += dout[row] has few
-// distinct targets (V = 293 rows, and on 4/4 material a third of all positions hit the four TIMESHIFT rows), so
-// red.global.add from every position serialises on a handful of L2 lines (88-150 us for a 136 MB read).  Here a CTA owns
-// ONE vocabulary row and one segment of the positions: it scans the segment's token ids (L2-resident), lists the
-// matching positions in shared memory, sums their dout rows in registers (coalesced row reads, every dout row is read
-// exactly once overall) and issues one atomic per column at the end.  The class-embedding gradient rides along: the sum
-// is kept per class of the position's sequence and added to d_cls_emb as well.
-constexpr int kGatherThreads = 256, kGatherWarps = 8, kGatherChunk = 2048, kGatherMaxD = 256;
+// Backward without per-element atomics (prefix == 0, at most two classes, vocab <= 512, D <= 256).  The scatter
+// d_tok_emb[tok] += dout[row] has few distinct targets (V = 293 rows, and on 4/4 material a third of all positions hit the
+// four TIMESHIFT rows), so red.global.add from every position serialises on a handful of L2 lines (80-150 us for a
+// 136 MB read).  Here a CTA takes a segment of 512 positions, counting-sorts them by token id in shared memory
+// (histogram with integer atomics, warp-scan prefix, scatter), and its warps then walk the vocabulary: a warp sums the
+// dout rows of one token in registers (coalesced float4 row reads, every row read exactly once overall) and issues one
+// 16-byte vector atomic per lane for that token.  The class-embedding gradient is the per-class total of the same rows:
+// it accumulates in registers across all tokens of the warp and leaves once per CTA.
+constexpr int kSortThreads = 256, kSortWarps = 8, kSortSeg = 512, kSortMaxV = 512, kSortMaxD = 256;
 
-__global__ void __launch_bounds__(kGatherThreads) embed_bwd_gather_kernel(
+__global__ void __launch_bounds__(kSortThreads) embed_bwd_sorted_kernel(
     const int* __restrict__ tokens, const int* __restrict__ classes, const float* __restrict__ dout,
-    float* __restrict__ d_tok_emb, float* __restrict__ d_cls_emb, long long rows, int T, int D, float scale, int vocab,
-    int segments) {
-  __shared__ int list[kGatherChunk];
-  __shared__ int cnt;
-  __shared__ __align__(16) float red[kGatherWarps][kGatherMaxD];
-  const int v = blockIdx.x / segments, sgm = blockIdx.x % segments;
-  const long long seg = (rows + segments - 1) / segments;
-  const long long r0 = (long long)sgm * seg, r1 = min(rows, r0 + seg);
+    float* __restrict__ d_tok_emb, float* __restrict__ d_cls_emb, long long rows, int T, int D, float scale, int vocab) {
+  __shared__ int cnt[kSortMaxV];
+  __shared__ int start[kSortMaxV];
+  __shared__ int sorted[kSortSeg];
+  __shared__ int wsum[kSortWarps];
+  __shared__ __align__(16) float red[kSortWarps][kSortMaxD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // a warp sums whole rows: lane owns the float4 groups lane and lane + 32 (D <= 256), one partial sum per class
-  float4 acc[2][2];
+  const long long r0 = (long long)blockIdx.x * kSortSeg;
+  const int n = (int)min((long long)kSortSeg, rows - r0);
+  for (int i = tid; i < kSortMaxV; i += kSortThreads) cnt[i] = 0;
+  __syncthreads();
+  // histogram: every position takes a rank within its token's bucket
+  int tok[2], rank[2], cls[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * kSortThreads;
+    tok[j] = -1;
+    if (i < n) {
+      int t = __ldg(tokens + r0 + i);
+      t = min(max(t, 0), vocab - 1);
+      tok[j] = t;
+      rank[j] = atomicAdd(&cnt[t], 1);
+      cls[j] = d_cls_emb ? (__ldg(classes + (r0 + i) / T) & 1) : 0;
+    }
+  }
+  __syncthreads();
+  // exclusive prefix sum of the 512 bucket sizes: 2 per thread, warp scan, then the warp totals
+  {
+    const int a = cnt[2 * tid], b2 = cnt[2 * tid + 1];
+    int v = a + b2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(MSX_FULL, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    const int excl = base + v - (a + b2);
+    start[2 * tid] = excl;
+    start[2 * tid + 1] = excl + a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    if (tok[j] >= 0) sorted[start[tok[j]] + rank[j]] = (tid + j * kSortThreads) | (cls[j] << 30);
+  __syncthreads();
+  // warps walk the vocabulary; lane owns the float4 groups lane and lane + 32 of a row
+  const int nv4 = D >> 2;
+  float4 cacc[2][2];
 #pragma unroll
   for (int c = 0; c < 2; ++c)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int nv4 = D >> 2;
-  bool any = false;
-  for (long long base = r0; base < r1; base += kGatherChunk) {
-    if (tid == 0) cnt = 0;
-    __syncthreads();
-    const long long end = min(r1, base + (long long)kGatherChunk);
-    for (long long i = base + tid; i < end; i += kGatherThreads) {
-      int tok = __ldg(tokens + i);
-      tok = min(max(tok, 0), vocab - 1);
-      if (tok == v) {
-        // position within the chunk and, when the class gradient is wanted, the class of its sequence in bit 30
-        const int cls = d_cls_emb ? (__ldg(classes + i / T) & 1) : 0;
-        list[atomicAdd(&cnt, 1)] = (int)(i - base) | (cls << 30);
-      }
-    }
-    __syncthreads();
-    const int n = cnt;
-    any |= n > 0;
-#pragma unroll 2
-    for (int k = warp; k < n; k += kGatherWarps) {
-      const int e = list[k];
-      const float4* src = reinterpret_cast<const float4*>(dout + (size_t)(base + (e & 0x3FFFFFFF)) * D);
+    for (int j = 0; j < 2; ++j) cacc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = warp; v < vocab; v += kSortWarps) {
+    const int m = cnt[v];
+    if (m == 0) continue;                                  // warp-uniform
+    const int s0 = start[v];
+    float4 acc[2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < m; ++k) {
+      const int e = sorted[s0 + k];
+      const float4* src = reinterpret_cast<const float4*>(dout + (size_t)(r0 + (e & 0x3FFFFFFF)) * D);
       const bool c1 = (e >> 30) != 0;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -142,29 +174,39 @@ __global__ void __launch_bounds__(kGatherThreads) embed_bwd_gather_kernel(
         }
       }
     }
-    __syncthreads();
-  }
-  if (!any) return;                          // block-uniform
-  for (int c = 0; c < (d_cls_emb ? 2 : 1); ++c) {
-    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int c4 = lane + 32 * j;
       if (c4 < nv4) {
-        // without a class table everything sits in acc[0]; with one, class c's sum goes out on round c
-        *reinterpret_cast<float4*>(&red[warp][4 * c4]) = acc[c][j];
+        const float4 t = make_float4(scale * (acc[0][j].x + acc[1][j].x), scale * (acc[0][j].y + acc[1][j].y),
+                                     scale * (acc[0][j].z + acc[1][j].z), scale * (acc[0][j].w + acc[1][j].w));
+        atomicAdd(reinterpret_cast<float4*>(d_tok_emb + (size_t)v * D) + c4, t);      // red.global.add.v4.f32
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          cacc[c][j].x += acc[c][j].x; cacc[c][j].y += acc[c][j].y; cacc[c][j].z += acc[c][j].z; cacc[c][j].w += acc[c][j].w;
+        }
       }
     }
+  }
+  if (!d_cls_emb) return;
+  for (int c = 0; c < 2; ++c) {
     __syncthreads();
-    if (tid < D) {
-      float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < kGatherWarps; ++w) t += red[w][tid];
-      t *= scale;
-      if (t != 0.f) {
-        atomicAdd(d_tok_emb + (size_t)v * D + tid, t);
-        if (d_cls_emb) atomicAdd(d_cls_emb + (size_t)c * D + tid, t);
+    for (int j = 0; j < 2; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < nv4) *reinterpret_cast<float4*>(&red[warp][4 * c4]) = cacc[c][j];
+    }
+    __syncthreads();
+    if (tid < nv4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const float4 r4 = *reinterpret_cast<const float4*>(&red[w][4 * tid]);
+        t.x += r4.x; t.y += r4.y; t.z += r4.z; t.w += r4.w;
       }
+      t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+      if (t.x != 0.f || t.y != 0.f || t.z != 0.f || t.w != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(d_cls_emb + (size_t)c * D) + tid, t);
     }
   }
 }
@@ -219,15 +261,14 @@ extern "C" int msx_embed_bwd_ex(const int32_t* tokens, const int32_t* classes, c
   MSX_REQUIRE(!d_cls_emb || classes, "msx_embed_bwd: class embedding needs classes");
   if (B == 0) return MSX_OK;
   const long long rows = (long long)B * T;
-  // large problems without prefix rows and with at most two classes: gather kernel (one CTA per vocabulary row and
-  // position segment, no per-element atomics); the class term needs class ids in {0, 1}, which the caller guarantees
-  // through num_classes <= 2 (msx_embed_bwd_ex) — other shapes keep the scatter kernel below
-  if (prefix == 0 && rows >= 8192 && D <= kGatherMaxD && (D & 3) == 0 && (((uintptr_t)dout) & 15) == 0 && (!d_cls_emb || (num_classes >= 1 && num_classes <= 2))) {
-    int segments = (int)((rows + 4095) / 4096);
-    if (segments > 64) segments = 64;
-    if (segments < 1) segments = 1;
-    embed_bwd_gather_kernel<<<vocab * segments, kGatherThreads, 0, (cudaStream_t)stream>>>(
-        tokens, classes, dout, d_tok_emb, d_cls_emb, rows, T, D, scale, vocab, segments);
+  // large problems without prefix rows and with at most two classes: sort-and-reduce kernel (see above); the class term
+  // needs class ids in {0, 1} (num_classes <= 2, msx_embed_bwd_ex) — other shapes keep the scatter kernel below
+  if (prefix == 0 && rows >= 8192 && vocab <= kSortMaxV && D <= kSortMaxD && (D & 3) == 0 &&
+      ((((uintptr_t)dout) | ((uintptr_t)d_tok_emb) | ((uintptr_t)d_cls_emb)) & 15) == 0 &&
+      (!d_cls_emb || (num_classes >= 1 && num_classes <= 2))) {
+    const int grid = (int)((rows + kSortSeg - 1) / kSortSeg);
+    embed_bwd_sorted_kernel<<<grid, kSortThreads, 0, (cudaStream_t)stream>>>(tokens, classes, dout, d_tok_emb, d_cls_emb, rows,
+                                                                             T, D, scale, vocab);
     MSX_LAUNCH_CHECK();
     return MSX_OK;
   }

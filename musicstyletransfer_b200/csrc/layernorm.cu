@@ -296,6 +296,17 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
 
 }  // namespace
 
+// Grid = exactly one wave of resident CTAs (persistent row loop): with the former 8 CTAs per SM the last partial wave
+// ran at a fraction of the machine and every CTA paid the dgamma / dbeta atomics.
+template <typename K>
+static int ln_wave_grid(K kernel, int dyn_smem, long long M) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+  const long long want = (M + kWarps - 1) / kWarps;
+  const long long wave = (long long)msx_num_sms() * per_sm;
+  return (int)(want < wave ? want : wave);
+}
+
 extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* beta,
                                  float* out, void* out_bf16, float* mean, float* rstd, long long M, int D, float eps,
                                  float drop_p, unsigned long long seed, unsigned site, void* stream) {
@@ -305,13 +316,12 @@ extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, 
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_add_ln_fwd: bad dropout");
   if (M == 0) return MSX_OK;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 &&
                    ((uintptr_t)out_bf16 & 7) == 0;
   MSX_REQUIRE(!(out_bf16 || y_bf16) || vec, "msx_add_ln_fwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* out16 = reinterpret_cast<unsigned short*>(out_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<ln_wave_grid(add_ln_fwd_kernel<V, P>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -342,18 +352,17 @@ extern "C" int msx_add_ln_bwd_ex(const float* x, const void* y_any, int y_bf16, 
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_bwd: D must be a multiple of 32");
   if (M == 0) return MSX_OK;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int grid = (int)min((long long)msx_num_sms() * 8, (M + kWarps - 1) / kWarps);
   const bool vec = (D % 128 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)dy |
                                        (uintptr_t)gamma) & 15) == 0 && ((uintptr_t)dy_bf16 & 7) == 0;
   MSX_REQUIRE(!(dy_bf16 || y_bf16) || vec, "msx_add_ln_bwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* dy16 = reinterpret_cast<unsigned short*>(dy_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P, false><<<grid, kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) add_ln_bwd_kernel<V, P, false><<<ln_wave_grid(add_ln_bwd_kernel<V, P, false>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
 #define LN_BWD_ASYNC(P)                                                                                                   \
   do {                                                                                                                    \
     const int dyn = kWarps * kLnStages * 3 * P * 128 * 4;                                                                 \
     MSX_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<4, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));      \
-    add_ln_bwd_kernel<4, P, true><<<grid, kWarps * 32, dyn, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16,  \
+    add_ln_bwd_kernel<4, P, true><<<ln_wave_grid(add_ln_bwd_kernel<4, P, true>, dyn, M), kWarps * 32, dyn, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16,  \
         dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy);         \
   } while (0)
   if (vec) {
