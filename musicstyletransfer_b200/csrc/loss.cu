@@ -518,7 +518,10 @@ extern "C" int msx_ce_fwd_bwd(float* logits_inout, int ld, const int32_t* labels
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = B * T;
   MSX_CUDA(cudaMemsetAsync(ce, 0, (size_t)B * sizeof(float), st));
-  const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
+  // one resident wave of CTAs (persistent row loop): no partial last wave, and the per-CTA bias-gradient flush is paid once
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ce_fwd_bwd_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  const int grid = min(msx_num_sms() * per_sm, (rows + 7) / 8);
   ce_fwd_bwd_kernel<<<grid, 256, 0, st>>>(logits_inout, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom, dbias);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
