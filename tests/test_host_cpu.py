@@ -185,3 +185,31 @@ def test_data_parallel_rule_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "DP_OK" in out.stdout
+
+
+def test_param_arena_layout_for_tma_and_bf16_shadow():
+    """Host-side layout rules of the flat parameter arena (engine.ParamArena): every tensor starts on a 32-byte boundary
+    (so that its bf16 shadow at the same element offset is a 16-byte aligned TMA base), the K | Q | V projections are
+    adjacent without gaps (one [3D, D] GEMM), and the parameter count is the reference's."""
+    import torch
+    from musicstyletransfer_b200.engine import ParamArena, VAEConfig, param_entries
+    for dec, n_ref in (("lstm", 2060325), ("transformer", 2093349)):
+        cfg = VAEConfig(dec_type=dec)
+        a = ParamArena(cfg, torch.device("cpu"))
+        assert a.n_params == n_ref
+        for name, (off, n, shape) in a.offsets.items():
+            assert off % 8 == 0, name
+        D = cfg.enc_size
+        for l in range(cfg.enc_layers):
+            pre = "encoder.encoder.layer%d.self_attention." % l
+            ok, oq, ov = (a.offsets[pre + k + ".weight"][0] for k in ("W_k", "W_q", "W_v"))
+            assert oq == ok + D * D and ov == oq + D * D
+            assert a.span(pre + "W_k.weight", pre + "W_v.weight").numel() == 3 * D * D
+        assert [n for n, _ in param_entries(cfg)] == a.names()
+
+
+def test_cli_accepts_bf16_precision():
+    from musicstyletransfer_b200.VarAutoEncoder import config as cfgmod
+    got = cfgmod.get_config(["--precision", "bf16"])
+    args = got[0] if isinstance(got, tuple) else got
+    assert args.precision == "bf16"
