@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // key row, so the issuer runs ahead of the softmax warps: K, Q of item n+1 are fetched as soon as MMA 1 of item n
 // has retired, V is double-buffered); every warp that owns valid rows does softmax + the output rows.
 // NCH = TQ / 16: the key row's scores are held in registers (one tcgen05.ld pass, one exp per score).
-template <int NCH, int G>
+template <int NCH, int G, bool STAGE>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(128 * G, 1)
     __syncwarp();
   }
   float mraw_next = (gt < T && first < p.items) ? __ldg(p.mask + (size_t)(first / p.H) * T + gt) : 0.f;
-  // coalesced context store through the dead P tile: pays off for fp32 rows (16-byte pieces of 32 different lines per
-  // store instruction otherwise; measured 167 -> 152 us); bf16 rows are 64 contiguous bytes per lane already and the
-  // extra group barrier costs more than the staging saves (138 -> 143 us), so they keep the row-per-lane store
-  const bool stage_ok = !p.out_bf16 && ((T + 31) / 32) * 4096 <= ((TQ + 31) / 32) * slab;
+  // coalesced context store through the dead P tile (STAGE, chosen by the host): pays off for fp32 rows (16-byte pieces
+  // of 32 different lines per store instruction otherwise; measured 167 -> 152 us); bf16 rows are 64 contiguous bytes per
+  // lane already and the extra group barrier costs more than the staging saves (138 -> 143 us), so they keep the
+  // row-per-lane store.  A template parameter: the staged store costs registers the other variant must not pay for.
+  constexpr bool stage_ok = STAGE;
   int n = 0;
   for (int item = first; item < p.items; item += stride, ++n) {
     const int b = item / p.H, h = item % p.H;
@@ -780,10 +781,17 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
   const size_t smem = 1024 + (size_t)G * p.group_bytes + 16 * 1024;
   p.smem_bytes = (int)smem - 1024;
   MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_fwd: shared memory budget exceeded (T=%d)", p.T);
-  MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int want = (p.items + G - 1) / G;
   const int grid = want < msx_num_sms() ? want : msx_num_sms();
-  attn_tc_fwd_kernel<NCH, G><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  // fp32 context rows leave through the dead P tile (coalesced) when the per-warp staging slices fit into it
+  const bool stage = !p.out_bf16 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
+  if (stage) {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, true><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  } else {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
