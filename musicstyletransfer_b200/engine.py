@@ -756,13 +756,20 @@ class VAEEngine:
                             accumulate=True)
             xd = bf.get("dec.x0", (Md, Hd), dev)
             dmask = bf.get("dec.mask", (Md,), dev)
+            d16 = self._layer16_ok(Hd)                  # bf16 variant: the decoder layers take the bf16 operand path too
+            xd16 = bf.get("dec.x0_16", (Md, Hd), dev, torch.bfloat16) if d16 else None
             ops.embed_fwd(tokens, None, seq_lens, self._W("decoder.embedding.weight"), None, s0, self.pe_dec, xd, dmask, B,
-                          T, Hd, 1, math.sqrt(float(Hd)), V)
-            dxs = [xd]
+                          T, Hd, 1, math.sqrt(float(Hd)), V, out16=xd16)
+            dxs, dxs16 = [xd], [xd16]
             for l in range(cfg.dec_layers):
-                xd = self._tf_layer_fwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, xd, dmask, B, Td, Hd,
-                                        cfg.dec_heads, pd_, (8 + l) * SITE_STRIDE, True)
+                if d16:
+                    xd, xd16 = self._tf_layer_fwd16(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, xd, xd16, dmask, B, Td,
+                                                    Hd, cfg.dec_heads, pd_, (8 + l) * SITE_STRIDE, True)
+                else:
+                    xd = self._tf_layer_fwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, xd, dmask, B, Td, Hd,
+                                            cfg.dec_heads, pd_, (8 + l) * SITE_STRIDE, True)
                 dxs.append(xd)
+                dxs16.append(xd16)
             dec_out = xd
         Mo = B * Td
         logits = bf.get("logits", (Mo, self.ldv), dev)
@@ -796,7 +803,8 @@ class VAEEngine:
         self.ctx = dict(B=B, T=T, Td=Td, tokens=tokens, seq_lens=seq_lens, classes=classes, labels=lab_full, eps=eps,
                         xs=xs, mask=mask, lat=lat, z=z, dec_out=dec_out, logits=logits, pe=pe_, pd=pd_, bf=bf,
                         dmask=dmask, dxs=dxs if cfg.dec_type == "transformer" else None, xs16=self._xs16,
-                        ce_fused=bool(labels is not None and ce_fused))
+                        ce_fused=bool(labels is not None and ce_fused),
+                        dxs16=dxs16 if cfg.dec_type == "transformer" else None)
         return out
 
     # ------------------------------------------------------------------ backward
@@ -847,8 +855,12 @@ class VAEEngine:
             dcur = ddec
             for l in reversed(range(cfg.dec_layers)):
                 dnext = bf.get("dec%d.dxin" % l, (Mo, Hd), dev)
-                self._tf_layer_bwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, dxs[l], c["dmask"], dcur, dnext, B,
-                                   Td, Hd, cfg.dec_heads, c["pd"], (8 + l) * SITE_STRIDE, True)
+                if self._layer16_ok(Hd):
+                    self._tf_layer_bwd16(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, dxs[l], c["dxs16"][l], c["dmask"],
+                                         dcur, dnext, B, Td, Hd, cfg.dec_heads, c["pd"], (8 + l) * SITE_STRIDE, True)
+                else:
+                    self._tf_layer_bwd(bf, "dec%d." % l, "decoder.decoder.layer%d." % l, dxs[l], c["dmask"], dcur, dnext, B,
+                                       Td, Hd, cfg.dec_heads, c["pd"], (8 + l) * SITE_STRIDE, True)
                 dcur = dnext
             ds0 = bf.get("dec.ds0", (B, Hd), dev)
             ops.embed_bwd(c["tokens"], None, dcur, self._G("decoder.embedding.weight"), None, ds0, B, T, Hd, 1,

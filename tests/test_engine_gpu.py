@@ -274,22 +274,23 @@ BF16_FWD_TOL = {"ce": 1e-4, "kl": 1e-3, "means": 1e-2}
 BF16_GRAD_WORST, BF16_GRAD_MEAN = 0.10, 0.03
 
 
-def _bf16_run(T, B=64, dropout=0.0):
+def _bf16_run(T, B=64, dropout=0.0, dec_type="lstm"):
     from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
-    cfg_o = om.Cfg(dec_type="lstm")
+    cfg_o = om.Cfg(dec_type=dec_type)
     p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=0))
     tokens, seq_lens, classes, labels, eps = _batch(B, T, 293, 2, 256, seed=1, min_len=T // 2 + 1)
-    eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=dropout, dec_dropout=dropout), "cuda:0", precision="bf16")
+    eng = VAEEngine(VAEConfig(dec_type=dec_type, enc_dropout=dropout, dec_dropout=dropout), "cuda:0", precision="bf16")
     eng.arena.load_state(p)
     out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
     return cfg_o, p, (tokens, seq_lens, classes, labels, eps), eng, out
 
 
-@pytest.mark.parametrize("T", [65, 129])
-def test_bf16_variant_step_vs_oracle(T):
+@pytest.mark.parametrize("T,dec_type", [(65, "lstm"), (129, "lstm"), (65, "transformer")])
+def test_bf16_variant_step_vs_oracle(T, dec_type):
     """bf16 variant vs the fp32 oracle: forward losses / latent means and every parameter gradient.  T = 129 takes the
-    FFMA attention fallback (tcgen05 attention covers T <= 128) with casts around it."""
-    cfg_o, p, batch, eng, out = _bf16_run(T, B=64 if T == 65 else 16)
+    long-row tcgen05 attention; the Transformer decoder (the class Model instantiates at HEAD, d_h = 16: FFMA attention
+    with casts around it) runs its layer on the bf16 operand path as well."""
+    cfg_o, p, batch, eng, out = _bf16_run(T, B=64 if T == 65 else 16, dec_type=dec_type)
     tokens, seq_lens, classes, labels, eps = batch
     opt = om.Adam({k: v.clone() for k, v in p.items()}, clip_gradient=1.0)
     pp = {k: v.clone() for k, v in p.items()}
@@ -298,10 +299,28 @@ def test_bf16_variant_step_vs_oracle(T):
     dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
     print("bf16 forward deviation (max abs / max):", dev)
     for k, tol in BF16_FWD_TOL.items():
-        assert dev[k] < tol, dev
+        # with the Transformer decoder the logits themselves come from bf16-operand GEMMs: measured 1.2e-3 on the loss
+        assert dev[k] < (5e-3 if (k == "ce" and dec_type == "transformer") else tol), dev
     eng.backward()
     torch.cuda.synchronize()
     gmax = max(float(g.abs().max()) for g in grads.values())
+    if dec_type == "transformer":
+        # In the Transformer decoder the K / Q projection gradients (and everything upstream of them through the latent
+        # prefix row: latent2hid, class2hid) are cancellation-dominated: sum_q dS[k, q] = 0 under the query-axis softmax
+        # and the decoder's query rows are nearly parallel, so rounding the operands to 8-11 mantissa bits (bf16 AND TF32
+        # alike: profiles/micro/diag_tfdec.py prints 1.7-2.5x of those tensors' own scale for TF32, 2.7-4.5x for bf16)
+        # leaves an error of <= 1 % of the global gradient scale; the exact-fp32 path matches to 1e-3
+        # (test_train_vae_config_step).  Every other tensor stays within 10 % of its own scale.
+        worst = 0.0
+        for n in eng.arena.names():
+            err = float((eng.arena.grad(n).cpu() - grads[n]).abs().max())
+            scale = float(grads[n].abs().max())
+            assert err <= 0.10 * scale + 1e-2 * gmax, (n, err, scale, gmax)
+            if not any(k in n for k in ("W_k", "W_q", "latent2hid", "class2hid", "decoder.embedding")):
+                worst = max(worst, err / max(scale, 1e-4 * gmax))
+        print("bf16 gradient deviation (transformer decoder), worst well-conditioned tensor:", worst)
+        assert worst < BF16_GRAD_WORST
+        return
     devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
                    if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
     print("bf16 gradient deviation, worst tensors:", devs[:4], "mean", sum(d for d, _ in devs) / len(devs))
