@@ -21,6 +21,8 @@ struct AttnTcParams {
   float* ctx;          // [B*T, H*32] fp32, or bf16 when out_bf16 (the operand of the bf16 W_proj GEMM)
   int out_bf16;
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
+  int dh;              // head width: 32, or 16 ("half heads": 32-wide tiles are still loaded, the score MMAs reduce over the
+                       // first 16 columns only and only 16 output columns are stored; the other half belongs to the next head)
   int items;           // B * H
   int group_bytes;     // shared memory of one pipeline group
   int smem_bytes;      // dynamic shared memory behind the 1024-byte aligned base
@@ -56,7 +58,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // key row, so the issuer runs ahead of the softmax warps: K, Q of item n+1 are fetched as soon as MMA 1 of item n
 // has retired, V is double-buffered); every warp that owns valid rows does softmax + the output rows.
 // NCH = TQ / 16: the key row's scores are held in registers (one tcgen05.ld pass, one exp per score).
-template <int NCH, int G, bool STAGE>
+template <int NCH, int G, bool STAGE, int kDh>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(128 * G, 1)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform as far as the compiler can tell
   const int g = warp >> 2, gt = tid & 127;                 // pipeline group, thread within the group (= key row / query row)
-  const int T = p.T, TK = p.TK, D = p.H * DH;
+  const int T = p.T, TK = p.TK, D = p.H * kDh;
   const int slab = TK * 128;                               // bytes of a [TK rows][128 B] tile
   unsigned char* sK = base + (size_t)g * p.group_bytes;    // [TK rows][128 B] K-major SW128; MMA 1 addresses 128 rows, the
                                                            // rows beyond TK alias the tiles behind it (their S rows are unused)
@@ -127,10 +129,10 @@ __global__ void __launch_bounds__(128 * G, 1)
     const int b = first / p.H, h = first % p.H;
     if (elect_one()) {
       mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
-      tma_load_2d(sK, &tmK, bar_kq, h * DH, b * T);
-      tma_load_2d(sQ, &tmQ, bar_kq, D + h * DH, b * T);
+      tma_load_2d(sK, &tmK, bar_kq, h * kDh, b * T);
+      tma_load_2d(sQ, &tmQ, bar_kq, D + h * kDh, b * T);
       mbar_expect_tx(&bar_v[0], (unsigned)slab);
-      tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * DH, b * T);
+      tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * kDh, b * T);
     }
     __syncwarp();
   }
@@ -154,19 +156,19 @@ __global__ void __launch_bounds__(128 * G, 1)
       if (elect_one()) {
         // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major (+32 B per K = 8 step)
 #pragma unroll
-        for (int k = 0; k < DH / 8; ++k) umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kDh / 8; ++k) umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
         if (nxt < p.items) {                               // V of the next item into the other V buffer (free since o_full(n-1))
           mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
-          tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * DH, b2 * T);
+          tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * kDh, b2 * T);
         }
       }
       __syncwarp();
       mbar_wait(bar_s, par);
       if (nxt < p.items && elect_one()) {                  // K, Q tiles are free once MMA 1 has retired
         mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
-        tma_load_2d(sK, &tmK, bar_kq, h2 * DH, b2 * T);
-        tma_load_2d(sQ, &tmQ, bar_kq, D + h2 * DH, b2 * T);
+        tma_load_2d(sK, &tmK, bar_kq, h2 * kDh, b2 * T);
+        tma_load_2d(sQ, &tmQ, bar_kq, D + h2 * kDh, b2 * T);
       }
     }
     __syncwarp();
@@ -251,10 +253,10 @@ __global__ void __launch_bounds__(128 * G, 1)
       // for a coalesced store; very short rows (the slice would not fit) keep the row-per-lane store
       const int w4 = warp & 3;
       if (stage_ok) {
-        store_tile32_coalesced(sP + w4 * 4096, p.ctx, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * D + h * DH, (size_t)D,
+        store_tile32_coalesced(sP + w4 * 4096, p.ctx, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * D + h * kDh, (size_t)D,
                                T - w4 * 32, o, lane);
       } else if (q < T) {
-        store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
+        store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * kDh, o, kDh);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -280,11 +282,12 @@ struct AttnTcBwdParams {
   int out_bf16;
   float* dbias;        // optional [3*H*32]: += column sums of dqkv (bias gradient of the fused K|Q|V projection)
   int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
+  int dh;              // head width 32 or 16 (see AttnTcParams)
   float inv_scale;
   long long* trace;    // optional profiling hook (msx_attention_tc_set_trace): clock64 stamps of block 0's groups
 };
 
-template <int kTmemCols>
+template <int kTmemCols, int kDh>
 __global__ void __launch_bounds__(128)
     attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK128, const __grid_constant__ CUtensorMap tmQk,
                        const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(128)
   __shared__ float red[3 * 128];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int D = p.H * DH;
+  const int D = p.H * kDh;
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
@@ -333,21 +336,21 @@ __global__ void __launch_bounds__(128)
 
   if (tid == 0) {
     mbar_expect_tx(&bars[0], (unsigned)((2 * 128 + 2 * TQ + 3 * TK) * 128));
-    tma_load_2d(sKk, &tmK128, &bars[0], h * DH, b * T);
-    tma_load_2d(sVk, &tmK128, &bars[0], 2 * D + h * DH, b * T);
-    tma_load_2d(sQk, &tmQk, &bars[0], D + h * DH, b * T);
-    tma_load_2d(sDOk, &tmDOk, &bars[0], h * DH, b * T);
-    tma_load_2d(sDOm, &tmDOm, &bars[0], h * DH, b * T);
-    tma_load_2d(sQm, &tmQKVm, &bars[0], D + h * DH, b * T);
-    tma_load_2d(sKm, &tmQKVm, &bars[0], h * DH, b * T);
+    tma_load_2d(sKk, &tmK128, &bars[0], h * kDh, b * T);
+    tma_load_2d(sVk, &tmK128, &bars[0], 2 * D + h * kDh, b * T);
+    tma_load_2d(sQk, &tmQk, &bars[0], D + h * kDh, b * T);
+    tma_load_2d(sDOk, &tmDOk, &bars[0], h * kDh, b * T);
+    tma_load_2d(sDOm, &tmDOm, &bars[0], h * kDh, b * T);
+    tma_load_2d(sQm, &tmQKVm, &bars[0], D + h * kDh, b * T);
+    tma_load_2d(sKm, &tmQKVm, &bars[0], h * kDh, b * T);
     mbar_wait(&bars[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
+    for (int k = 0; k < kDh / 8; ++k)       // S = K Q^T
       umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
                 idesc_kk, k > 0 ? 1u : 0u);
 #pragma unroll
-    for (int k = 0; k < DH / 8; ++k)       // dP = V dO^T
+    for (int k = 0; k < kDh / 8; ++k)       // dP = V dO^T
       umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
                 idesc_kk, k > 0 ? 1u : 0u);
     umma_commit(&bars[1]);
@@ -436,13 +439,13 @@ __global__ void __launch_bounds__(128)
   {
     // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
     float o[32];
-    const size_t row_elem = ((size_t)b * T + tid) * 3 * D + h * DH;
+    const size_t row_elem = ((size_t)b * T + tid) * 3 * D + h * kDh;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
       const unsigned src = m == 0 ? tm_dK : m == 1 ? tm_dQ : tm_dV;
       tmem_ld16(src + lane_off, o);
       tmem_ld16(src + lane_off + 16, o + 16);
-      if (tid < T) store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o);
+      if (tid < T) store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o, kDh);
       if (p.dbias) {
         if (tid >= T) {
 #pragma unroll
@@ -453,9 +456,9 @@ __global__ void __launch_bounds__(128)
     }
     if (p.dbias) {
       __syncthreads();
-      if (tid < 96) {
+      if (tid < 96 && (tid & 31) < kDh) {
         const int m = tid >> 5, c = tid & 31;
-        atomicAdd(p.dbias + m * D + h * DH + c, red[m * 128 + c] + red[m * 128 + 32 + c] + red[m * 128 + 64 + c] + red[m * 128 + 96 + c]);
+        atomicAdd(p.dbias + m * D + h * kDh + c, red[m * 128 + c] + red[m * 128 + 32 + c] + red[m * 128 + 64 + c] + red[m * 128 + 96 + c]);
       }
     }
   }
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(128)
 //   * the K-major tiles of the first two MMAs are double-buffered and prefetched one item ahead; the dS^T staging
 //     tile aliases the current stage once its MMAs have retired;
 //   * the bias-gradient column sums accumulate in registers across the items of a group (flushed when the head changes).
-template <int NCH, bool STAGE>
+template <int NCH, bool STAGE, int kDh>
 __global__ void __launch_bounds__(256, 1)
     attn_tc_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmQk,
                             const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(256, 1)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform as far as the compiler can tell
   const int g = warp >> 2, gt = tid & 127;
-  const int T = p.T, TK = p.TK, D = p.H * DH;
+  const int T = p.T, TK = p.TK, D = p.H * kDh;
   const int slab = TK * 128;
   const int stage_bytes = 2 * slab + 2 * TQ * 128;         // Kk | Vk | Qk | dOk (K-major, SW128)
   unsigned char* gbase = base + (size_t)g * group_bytes;
@@ -550,10 +553,10 @@ __global__ void __launch_bounds__(256, 1)
     const int b = item / p.H, h = item % p.H;
     unsigned char* st = gbase + stage * stage_bytes;
     mbar_expect_tx(&bar_a[stage], (unsigned)stage_bytes);
-    tma_load_2d(st, &tmKk, &bar_a[stage], h * DH, b * T);
-    tma_load_2d(st + slab, &tmKk, &bar_a[stage], 2 * D + h * DH, b * T);
-    tma_load_2d(st + 2 * slab, &tmQk, &bar_a[stage], D + h * DH, b * T);
-    tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * DH, b * T);
+    tma_load_2d(st, &tmKk, &bar_a[stage], h * kDh, b * T);
+    tma_load_2d(st + slab, &tmKk, &bar_a[stage], 2 * D + h * kDh, b * T);
+    tma_load_2d(st + 2 * slab, &tmQk, &bar_a[stage], D + h * kDh, b * T);
+    tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * kDh, b * T);
   };
   // descriptors of stage 0 / the MN-major tiles, advanced by constant increments (see the forward kernel)
   const unsigned long long dKk = make_desc(smem_u32(gbase), 16, 1024, 2);
@@ -577,9 +580,9 @@ __global__ void __launch_bounds__(256, 1)
       red[g][m * 128 + (warp & 3) * 32 + lane] = warp_colsum32(t, lane);
     }
     group_sync(g);
-    if (gt < 96) {
+    if (gt < 96 && (gt & 31) < kDh) {
       const int m = gt >> 5, c = gt & 31;
-      atomicAdd(p.dbias + m * D + acc_h * DH + c,
+      atomicAdd(p.dbias + m * D + acc_h * kDh + c,
                 red[g][m * 128 + c] + red[g][m * 128 + 32 + c] + red[g][m * 128 + 64 + c] + red[g][m * 128 + 96 + c]);
     }
     group_sync(g);
@@ -612,9 +615,9 @@ __global__ void __launch_bounds__(256, 1)
       if (elect_one()) {
         // MN-major tiles of the output MMAs (free: the previous item's output MMAs have retired)
         mbar_expect_tx(bar_b, (unsigned)(3 * slab));
-        tma_load_2d(sBm, &tmDOm, bar_b, h * DH, b * T);
-        tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * DH, b * T);
-        tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * DH, b * T);
+        tma_load_2d(sBm, &tmDOm, bar_b, h * kDh, b * T);
+        tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * kDh, b * T);
+        tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * kDh, b * T);
         if (nxt < items) load_a(nxt, stg ^ 1);              // the other stage held item n-1 (its MMAs and dS^T are consumed)
       }
       __syncwarp();
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(256, 1)
       if (elect_one()) {
         // S = K Q^T and dP = V dO^T: two independent accumulate chains, interleaved
 #pragma unroll
-        for (int k = 0; k < DH / 8; ++k) {
+        for (int k = 0; k < kDh / 8; ++k) {
           umma_tf32(tm_S, kk + 2 * k, qk + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
           umma_tf32(tm_dP, vk + 2 * k, dok + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
         }
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(256, 1)
     if (gt == 0) MSX_STAMP(7);
     if (warp_live) {
       // lanes = keys for dK / dV, lanes = queries for dQ: each thread stores three 128-byte rows
-      const size_t row_elem = ((size_t)b * T + gt) * 3 * D + h * DH;
+      const size_t row_elem = ((size_t)b * T + gt) * 3 * D + h * kDh;
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         float o[32];
@@ -742,10 +745,10 @@ __global__ void __launch_bounds__(256, 1)
         // the rows for a coalesced store
         if (stage_ok) {
           const int w4 = warp & 3;
-          store_tile32_coalesced(sY + w4 * 4096, p.dqkv, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * 3 * D + h * DH + m * D,
+          store_tile32_coalesced(sY + w4 * 4096, p.dqkv, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * 3 * D + h * kDh + m * D,
                                  (size_t)3 * D, T - w4 * 32, o, lane);
         } else if (gt < T) {
-          store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o);
+          store_row32(p.dqkv, p.out_bf16 != 0, row_elem + m * D, o, kDh);
         }
         if (gt < T && p.dbias) {
 #pragma unroll
@@ -771,7 +774,9 @@ __global__ void __launch_bounds__(256, 1)
 }  // namespace
 
 extern "C" int msx_attention_tc_supported(const float* qkv, int T, int dh) {
-  return (qkv && dh == 32 && T >= 1 && T <= 128 && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
+  // dh == 16 ("half heads", e.g. the 128-wide Transformer decoder with 8 heads): the kernels still move 32-wide tiles
+  // and reduce / store only the first 16 columns, see AttnTcParams::dh
+  return (qkv && (dh == 32 || dh == 16) && T >= 1 && T <= 128 && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
 }
 
 namespace {
@@ -784,13 +789,16 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
   const int want = (p.items + G - 1) / G;
   const int grid = want < msx_num_sms() ? want : msx_num_sms();
   // fp32 context rows leave through the dead P tile (coalesced) when the per-warp staging slices fit into it
-  const bool stage = !p.out_bf16 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
-  if (stage) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, true><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  const bool stage = !p.out_bf16 && p.dh == 32 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
+  if (p.dh == 16) {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false, 16><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  } else if (stage) {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, true, 32><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   } else {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false, 32><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
@@ -810,13 +818,13 @@ extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void
   MSX_REQUIRE(((uintptr_t)ctx & 15) == 0, "msx_attention_tc_fwd: ctx must be 16-byte aligned");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
   if (B == 0) return MSX_OK;
-  const int D = H * DH;
+  const int D = H * dh;
   AttnTcParams p;
-  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H;
+  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H; p.dh = dh;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.items = B * H;
-  p.inv_scale = 1.f / sqrtf((float)DH);
+  p.inv_scale = 1.f / sqrtf((float)dh);
   // per group: K [TK] + Q [TQ] + 2 x V [TK] + P [ceil(TQ/32) slabs x TK] rows of 128 B, every tile 1024-byte aligned
   p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK) * 128;
   const long long rows = (long long)B * T;
@@ -860,13 +868,14 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
               "msx_attention_tc_bwd: needs d_h == 32, T <= 128, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
-  const int D = H * DH;
+  const int D = H * dh;
   AttnTcBwdParams p;
   p.mask = mask; p.dqkv = reinterpret_cast<float*>(dqkv); p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias; p.T = T; p.H = H;
+  p.dh = dh;
   p.trace = g_attn_trace;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
-  p.inv_scale = 1.f / sqrtf((float)DH);
+  p.inv_scale = 1.f / sqrtf((float)dh);
   const long long rows = (long long)B * T;
   CUtensorMap tK128, tQk, tDOk, tDOm, tQKVm;
   int rc;
@@ -892,15 +901,18 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
     const int want = (items + 1) / 2;
     const int grid = want < msx_num_sms() ? want : msx_num_sms();
     // fp32 outputs leave through a shared-memory staging tile (coalesced rows) when it fits into a pipeline stage
-    const bool stage = !p.out_bf16 && ((T + 31) / 32) * 4096 <= stage_bytes;
+    const bool stage = !p.out_bf16 && dh == 32 && ((T + 31) / 32) * 4096 <= stage_bytes;
 #define MSX_BWD_PIPE(NCH)                                                                                              \
   case NCH:                                                                                                            \
-    if (stage) {                                                                                                       \
-      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    if (dh == 16) {                                                                                                    \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, false, 16><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    } else if (stage) {                                                                                                \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, true, 32><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
     } else {                                                                                                           \
-      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, false><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, false, 32><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
     }                                                                                                                  \
     break;
     switch (p.TQ / 16) {
@@ -920,11 +932,21 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
   const size_t smem = 1024 + (size_t)((p.TQ + 31) / 32) * slab + 3 * (size_t)slab + r1 + 64;
   MSX_REQUIRE(smem <= 227 * 1024, "msx_attention_tc_bwd: shared memory budget exceeded (T=%d)", T);
   if (96 + 2 * p.TQ <= 256) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_bwd_kernel<256><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    if (dh == 16) {
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attn_tc_bwd_kernel<256, 16><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    } else {
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attn_tc_bwd_kernel<256, 32><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    }
   } else {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_bwd_kernel<512><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    if (dh == 16) {
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attn_tc_bwd_kernel<512, 16><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    } else {
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attn_tc_bwd_kernel<512, 32><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+    }
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;

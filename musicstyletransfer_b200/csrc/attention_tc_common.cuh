@@ -115,11 +115,13 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 // one 32-element head row of an output tensor: fp32 (128 B, eight float4) or bf16 (64 B, four uint4); `elem` is the
 // element offset of the row start, the same in both storage types
-__device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, const float* o) {
+// (ncols = 16 writes the first half only: 16-wide heads)
+__device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, const float* o, int ncols = 32) {
   if (bf16) {
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(base) + elem);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      if (8 * j >= ncols) break;
       uint4 w;
       asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(o[8 * j + 1]), "f"(o[8 * j + 0]));
       asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(o[8 * j + 3]), "f"(o[8 * j + 2]));
@@ -130,7 +132,8 @@ __device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, 
   } else {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    for (int j = 0; j < 8; ++j)
+      if (4 * j < ncols) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
   }
 }
 

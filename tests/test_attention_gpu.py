@@ -115,3 +115,37 @@ def test_attention_long_rows(B, T, H, out16):
     assert err < (1e-2 if out16 else 5e-3), err
     wb = wg.sum(0)
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ 16-wide heads
+@pytest.mark.parametrize("B,T,H", [(3, 66, 8), (5, 65, 3), (2, 16, 4), (4, 97, 2), (2, 128, 8), (300, 66, 8)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_attention_tc_half_heads(B, T, H, out16):
+    """d_h = 16 (the 128-wide Transformer decoder with 8 heads): the tcgen05 kernels load 32-wide tiles, reduce over and
+    store the first 16 columns only; forward, backward and the fused K|Q|V bias gradient vs float64 / autograd."""
+    from musicstyletransfer_b200 import ops
+    dh = 16
+    qkv, mask = _inputs(B, T, H, dh, seed=T + 1)
+    g = torch.Generator().manual_seed(T)
+    dctx = torch.randn(B * T, H * dh, generator=g)
+    x = qkv.double().requires_grad_(True)
+    want = _ref_fwd(x, mask, B, T, H, dh)
+    (want * dctx.double()).sum().backward()
+    wg = x.grad
+    want = want.detach()
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    assert ops.attention_tc_supported(qd, T, dh)
+    odt = torch.bfloat16 if out16 else torch.float32
+    ctx = torch.full((B * T, H * dh), 3.0, device="cuda", dtype=odt)
+    ops.attention_tc_fwd(qd, md, ctx, B, T, H, dh)
+    torch.cuda.synchronize()
+    err = float((ctx.double().cpu() - want).abs().max()) / float(want.abs().max())
+    assert err < (8e-3 if out16 else 3e-3), err
+    out = torch.full((B * T, 3 * H * dh), 5.0, device="cuda", dtype=odt)
+    db = torch.zeros(3 * H * dh, device="cuda")
+    ops.attention_tc_bwd(qd, md, dd, out, B, T, H, dh, dbias=db)
+    torch.cuda.synchronize()
+    err = float((out.double().cpu() - wg).abs().max()) / float(wg.abs().max())
+    assert err < (1e-2 if out16 else 5e-3), err
+    wb = wg.sum(0)
+    assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
