@@ -81,6 +81,8 @@ b200_arg.add_argument('--precision', choices=["fp32", "tf32", "bf16"], default="
                       help="GEMM path: exact fp32 FFMA, tcgen05 TF32 tensor cores (fp32 storage / accumulation), or bf16 = "
                            "the TF32 path with the Transformer layers' GEMM operands stored as bfloat16 (fp32 accumulation, "
                            "fp32 master weights / LayerNorm / softmax / losses / Adam)")
+b200_arg.add_argument('--cuda-graph', type=str2bool, default=True,
+                      help="replay the train step from a CUDA graph per batch shape (one launch instead of ~70)")
 b200_arg.add_argument('--seed', type=int, default=0)
 b200_arg.add_argument('--max-steps', type=int, default=-1, help="stop fit() after this many batches (-1: no limit)")
 b200_arg.add_argument('--log-dir', type=str, default='/tmp/out')

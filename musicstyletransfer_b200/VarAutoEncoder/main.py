@@ -115,7 +115,7 @@ def main(argv=None):
     log_model_variables(m)
     sampler = Sampling(args.model_output, None, None, verbose=args.verbose, model_instance=m)
     t = trainer.Trainer(config=create_train_config(args), context=None, model=m, sampler=sampler, log_dir=args.log_dir,
-                        max_steps=args.max_steps)
+                        max_steps=args.max_steps, cuda_graph=getattr(args, "cuda_graph", True))
     t.fit(dataset=train_dataset, validation_dataset=valid_dataset, model_folder=args.model_output, epochs=args.epochs)
     print("Training finished.")
 

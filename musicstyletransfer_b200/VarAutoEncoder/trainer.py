@@ -57,8 +57,11 @@ class TrainingState:
 
 
 class Trainer:
-    def __init__(self, config: TrainConfig, context, model, sampler=None, log_dir='/tmp/out', max_steps=-1):
+    def __init__(self, config: TrainConfig, context, model, sampler=None, log_dir='/tmp/out', max_steps=-1, cuda_graph=True):
         self.config = config
+        # replay the train step from a CUDA graph per batch shape (engine.train_step_graphed): at the reference's own
+        # batch size (32, scripts/train-vae.sh) the ~70 launches of an eagerly issued step are host-bound
+        self.cuda_graph = cuda_graph
         self.context = context
         self.model = model
         self.engine = model.engine
@@ -131,12 +134,25 @@ class Trainer:
             print("classes: {}, {}".format(tuple(classes.shape), classes))
             print("labels:  {}, {}".format(tuple(labels.shape), labels))
         # the reference keeps autograd.record() (train mode, dropout on) for validation too (trainer.py:166-168)
-        out = self.engine.forward(tokens, seq_lens, classes, labels, train=True)
-        if is_train:
-            self.engine.backward(kl_weight=self.config.kl_loss_weight)
-            if self.world > 1:
-                torch.distributed.all_reduce(self.engine.arena.g)
-            self.engine.adam_step(global_batch, **self.opt)
+        o = self.opt
+        graph_ok = (is_train and self.cuda_graph and not self.config.verbose and o['beta1'] == 0.9 and o['beta2'] == 0.999
+                    and o['eps'] == 1e-8 and o['wd'] == 0.0)
+        if graph_ok:
+            # forward + backward (+ all-reduce) + Adam as one graph replay per (batch, length) shape; the optimiser
+            # hyper-parameters baked into the graph are the reference's defaults checked above
+            ar = (lambda g: torch.distributed.all_reduce(g)) if self.world > 1 else None
+            if ar is not None and not hasattr(self, "_ar"):
+                self._ar = ar                      # one callable object: it is part of the graph cache key
+            out = self.engine.train_step_graphed(tokens, seq_lens, classes, labels, kl_weight=self.config.kl_loss_weight,
+                                                 global_batch=global_batch, lr=o['lr'], clip_gradient=o['clip_gradient'],
+                                                 allreduce=getattr(self, "_ar", None))
+        else:
+            out = self.engine.forward(tokens, seq_lens, classes, labels, train=True)
+            if is_train:
+                self.engine.backward(kl_weight=self.config.kl_loss_weight)
+                if self.world > 1:
+                    torch.distributed.all_reduce(self.engine.arena.g)
+                self.engine.adam_step(global_batch, **self.opt)
         loss = out["ce"] + self.config.kl_loss_weight * out["kl"]
         self.metrics.update(out["kl"], loss)
         return loss
