@@ -34,6 +34,29 @@ def rasterize(dtick, pitch, vel, seq_offsets, resolution=120, slices_per_quarter
     return tokens, roll, n_tokens
 
 
+def rasterize_windows(dtick, pitch, vel, seq_offsets, resolution=120, slices_per_quarter=4, n_slices=64, max_windows=8,
+                      velocity_roll=False):
+    """Whole tracks as consecutive windows of ``n_slices`` slices (the roll rows of SURVEY.md §8(c): one row per window):
+    returns (roll uint8 [N, max_windows, n_slices, 128], n_windows int32 [N]).  Window w of track i is valid for
+    w < n_windows[i] = min(max_windows, last event's slice // n_slices + 1); notes sounding at the end of a track run to
+    the end of its last window, events beyond window max_windows - 1 are dropped (oracle/featurise.py:rasterize_sequence).
+    One K1 launch on a tall tile of max_windows * n_slices slices (<= 1024); the window count comes from the played
+    clock of the last event (a segmented sum, plain tensor plumbing)."""
+    total = n_slices * max_windows
+    assert total <= 1024, "max_windows * n_slices must not exceed 1024 slices (one shared-memory tile per warp)"
+    n = seq_offsets.numel() - 1
+    _, roll, _ = rasterize(dtick, pitch, vel, seq_offsets, resolution, slices_per_quarter, total, 1, velocity_roll)
+    d = dtick.to(torch.int64)
+    # played clock of an event (midi_io.py:81-83 replayed by Melody.py:82-83): ceil(d/1000) shifts of 30 * ((d%1000)//30)
+    played = torch.where(d > 0, ((d + 999) // 1000) * (30 * ((d % 1000) // 30)), torch.zeros_like(d))
+    csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=d.device), torch.cumsum(played, 0)])
+    offs = seq_offsets.to(torch.int64)
+    clock = csum[offs[1:]] - csum[offs[:-1]]
+    last_slice = (clock * slices_per_quarter) // resolution
+    n_windows = torch.clamp(last_slice // n_slices + 1, max=max_windows).to(torch.int32)
+    return roll.view(n, max_windows, n_slices, 128), n_windows
+
+
 def tokenize_tracks(soas, device="cuda"):
     """A1 for whole tracks: list of (dtick, pitch, vel) NumPy SoAs -> list of int32 id arrays, untruncated.
     One K1 launch for all tracks (the roll output is a 1-slice dummy window)."""

@@ -99,3 +99,30 @@ def test_full_size_properties():
         vtok, vroll, vcnt = _run(dtick, pitch, vel, offs, velocity_roll=True)
         ctok, croll, ccnt = raster_c.rasterize_batch(dtick, pitch, vel, offs, velocity_roll=True, threads=8)
         assert np.array_equal(vroll, croll) and np.array_equal(vtok, ctok)
+
+
+@pytest.mark.parametrize("velocity_roll", [False, True])
+def test_whole_tracks_as_windows(velocity_roll):
+    """featurise.rasterize_windows: ragged tracks of up to a few hundred events as consecutive 64-slice windows, every
+    valid window bit-exact against oracle rasterize_sequence(max_windows); empty and one-event tracks included."""
+    from musicstyletransfer_b200 import featurise
+    rng = np.random.RandomState(11)
+    lens = [0, 1, 5, 40, 130, 260, 33, 700, 64, 2]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    E = int(offs[-1])
+    dtick = (30 * rng.randint(0, 9, size=E)).astype(np.int32)
+    dtick[rng.rand(E) < 0.02] = rng.randint(1000, 5000, size=int((rng.rand(E) < 0.02).sum()) or 1)[0]
+    pitch = rng.randint(40, 72, size=E).astype(np.uint8)
+    vel = np.where(rng.rand(E) < 0.5, rng.randint(1, 128, size=E), 0).astype(np.uint8)
+    S, W = 64, 8
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    roll, nwin = featurise.rasterize_windows(t(dtick), t(pitch), t(vel), t(offs), n_slices=S, max_windows=W,
+                                             velocity_roll=velocity_roll)
+    torch.cuda.synchronize()
+    roll, nwin = roll.cpu().numpy(), nwin.cpu().numpy()
+    for i in range(len(lens)):
+        a, b = offs[i], offs[i + 1]
+        _, want = of.rasterize_sequence(dtick[a:b], pitch[a:b], vel[a:b], 120, 4, S, W, velocity_roll=velocity_roll)
+        want = want.reshape(-1, S, 128)
+        assert nwin[i] == want.shape[0], (i, nwin[i], want.shape)
+        assert np.array_equal(roll[i, :nwin[i]], want), i
