@@ -570,8 +570,10 @@ class VAEEngine:
                               1.0, V)                                                         # model.py:192
                 self._dense_fwd(xe, Hd, B, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates,
                                 4 * Hd, 4 * Hd, Hd)
-                ops.lstm_fwd(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
-                             hb[i & 1], hp, cb[i & 1], B, 1, Hd)                              # model.py:195
+                # one recurrence step; the tensor-core kernel (W_h2h as mma fragments in registers) in the tensor modes
+                step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
+                step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
+                     hb[i & 1], hp, cb[i & 1], B, 1, Hd)                                      # model.py:195
                 h, c, ld0 = hb[i & 1], cb[i & 1], Hd
                 self._dense_fwd(h, Hd, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv,
                                 V, Hd)                                                        # model.py:198
@@ -686,8 +688,9 @@ class VAEEngine:
             ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, None, xe, None, R, 1, Hd, 0, 1.0, V)
             self._dense_fwd(xe, Hd, R, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
                             4 * Hd, Hd)
-            ops.lstm_fwd(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
-                         hn, hp, cn, R, 1, Hd)
+            step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, Hd, h[cur], c[cur])) else ops.lstm_fwd
+            step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
+                 hn, hp, cn, R, 1, Hd)
             self._dense_fwd(hn, Hd, R, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V, Hd)
             ops.beam_step(logits, self.ldv, V, B, K, seq[cur], seq[cur ^ 1], I_max, i, score[cur], score[cur ^ 1], parent,
                           nxt, unfinished)
