@@ -565,11 +565,13 @@ class VAEEngine:
             xe = bf.get("st.xe", (B, Hd), dev)
             gates = bf.get("st.gates", (B, 4 * Hd), dev)
             h, c, ld0 = tv, tv[:, Hd:], 2 * Hd
+            # embedding lookup + i2h Dense of a step (model.py:192-195) = a lookup into the [V, 4H] table
+            # emb W_i2h^T + b_i2h, computed once per call: one gather per step instead of a gather and a GEMM
+            tab = bf.get("st.i2h_table", (V, 4 * Hd), dev)
+            self._dense_fwd(W("decoder.embedding.weight"), Hd, V, "decoder.decoder.l0_i2h_weight",
+                            "decoder.decoder.l0_i2h_bias", tab, 4 * Hd, 4 * Hd, Hd)
             for i in range(1, I_max):
-                ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, None, xe, None, B, 1, Hd, 0,
-                              1.0, V)                                                         # model.py:192
-                self._dense_fwd(xe, Hd, B, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates,
-                                4 * Hd, 4 * Hd, Hd)
+                ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, B, 1, 4 * Hd, 0, 1.0, V)
                 # one recurrence step; the tensor-core kernel (W_h2h as mma fragments in registers) in the tensor modes
                 step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
                 step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
@@ -684,10 +686,11 @@ class VAEEngine:
         xe, gates = bb.get("bs.xe", (R, Hd), dev), bb.get("bs.gates", (R, 4 * Hd), dev)
         logits = bb.get("bs.logits", (R, self.ldv), dev)
         cur = 0
+        tab = bb.get("bs.i2h_table", (V, 4 * Hd), dev)              # emb W_i2h^T + b_i2h, see style_transfer
+        self._dense_fwd(W("decoder.embedding.weight"), Hd, V, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias",
+                        tab, 4 * Hd, 4 * Hd, Hd)
         for i in range(1, I_max):
-            ops.embed_fwd(nxt, None, None, W("decoder.embedding.weight"), None, None, None, xe, None, R, 1, Hd, 0, 1.0, V)
-            self._dense_fwd(xe, Hd, R, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
-                            4 * Hd, Hd)
+            ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, R, 1, 4 * Hd, 0, 1.0, V)
             step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, Hd, h[cur], c[cur])) else ops.lstm_fwd
             step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
                  hn, hp, cn, R, 1, Hd)
