@@ -75,11 +75,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int crank = (int)cluster.block_rank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int b0 = (blockIdx.x >> 1) * R;
   const int ul0 = warp * 8 + 2 * t4;                        // this thread's two local units (accumulator columns 2t, 2t+1)
   const int u0 = crank * UH + ul0;
   const int un = crank * UH + warp * 8 + g;                 // the unit whose W rows this thread holds as B fragments (n = lane / 4)
 
+  // A cluster is persistent over blocks of R batch rows (grid = min(#row blocks, resident clusters)): W_h2h goes into
+  // registers once per CTA.  With T = 1 (one decode step over a large batch: style transfer / beam search) the launch
+  // used to be 3-4 waves of CTAs that each re-loaded their 128 KB of W for a single step.
+  int b0 = 0;
   // gx slab of step t -> gxs[t & 1]: 32 rows x 4 gates x 64 units = 2048 16-byte chunks, 8 per thread
   auto prefetch_gx = [&](int t) {
     float* dst = sm.gxs[t & 1];
@@ -91,8 +94,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     cp_async_commit();
   };
-  prefetch_gx(0);
-
   // W_h2h slice as B fragments: breg[gate][k-step] = W[gate*H + un][8s + 2t], W[gate*H + un][8s + 2t + 1]
   float breg[4][16][2];
 #pragma unroll
@@ -105,17 +106,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       breg[j][s][1] = tf32r(w2.y);
     }
   }
-  for (int i = tid; i < R * H; i += kThreads) {
-    const int r = i / H, k = i % H;
-    sm.hfrag[0][afrag_index(r, k, 16)] = (b0 + r < B) ? tf32r(__ldg(h0 + (size_t)(b0 + r) * ld0 + k)) : 0.f;
-  }
-  // cells of this thread: rows 16m + 8hi + g (index q = 2m + hi), units u0, u0 + 1
-  float c[4][2], hp[4][2], bias[4][2];
+  float bias[4][2];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     bias[j][0] = __ldg(b_h2h + j * H + u0);
     bias[j][1] = __ldg(b_h2h + j * H + u0 + 1);
   }
+  float* hfrag_peer = cluster.map_shared_rank(&sm.hfrag[0][0], crank ^ 1);
+  const int n_blocks = (B + R - 1) / R, n_clusters = gridDim.x >> 1;
+  for (int blk = blockIdx.x >> 1; blk < n_blocks; blk += n_clusters) {
+  b0 = blk * R;
+  cluster.sync();                                           // both CTAs are done with the previous row block's buffers
+  prefetch_gx(0);
+  for (int i = tid; i < R * H; i += kThreads) {
+    const int r = i / H, k = i % H;
+    sm.hfrag[0][afrag_index(r, k, 16)] = (b0 + r < B) ? tf32r(__ldg(h0 + (size_t)(b0 + r) * ld0 + k)) : 0.f;
+  }
+  // cells of this thread: rows 16m + 8hi + g (index q = 2m + hi), units u0, u0 + 1
+  float c[4][2], hp[4][2];
   int brow[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -126,7 +134,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     hp[q][0] = __ldg(h0 + (size_t)b * ld0 + u0);
     hp[q][1] = __ldg(h0 + (size_t)b * ld0 + u0 + 1);
   }
-  float* hfrag_peer = cluster.map_shared_rank(&sm.hfrag[0][0], crank ^ 1);
   cp_async_wait_all();
   cluster.sync();
 
@@ -197,6 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     cluster_wait();
   }
+  }                                                         // row blocks
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -409,7 +417,10 @@ extern "C" int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float*
   MSX_REQUIRE(gx_inout && w_h2h && b_h2h && h0 && c0 && hs && hprev && cs, "msx_lstm_tc_fwd: null pointer");
   MSX_REQUIRE(msx_lstm_tc_supported(H_, ld0, h0, c0), "msx_lstm_tc_fwd: needs H == 128, even ld0, 8-byte aligned h0 / c0");
   if (B == 0 || T == 0) return MSX_OK;
-  const int clusters = (B + R - 1) / R;
+  // persistent clusters: one 2-CTA cluster per SM pair at most, each walks its row blocks with W_h2h kept in registers
+  const int blocks = (B + R - 1) / R;
+  const int resident = msx_num_sms() / 2;
+  const int clusters = blocks < resident ? blocks : resident;
   MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
   lstm_tc_fwd_kernel<<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0, hs,
                                                                                        hprev, cs, B, T);
