@@ -141,10 +141,10 @@ __device__ __forceinline__ void ln_cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void ln_cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-constexpr int kLnStages = 2;
+constexpr int kLnStages = 3;   // rows in flight per warp: the one being reduced + two on their way (2 CTAs / SM, no spills)
 
 template <int VEC, int kPer, bool kAsync>
-__global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_kernel(
+__global__ void __launch_bounds__(kWarps * 32, (kAsync ? 2 : (kPer <= 2 ? 3 : 1))) add_ln_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ y, int y_bf16, const float* __restrict__ gamma,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dout,
     float* __restrict__ dres, float* __restrict__ dy, unsigned short* __restrict__ dy16, float* __restrict__ dgamma,
@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (kAsync) issue(row_first, 0);
+  if (kAsync) {
+#pragma unroll
+    for (int st = 0; st < kLnStages - 1; ++st) issue(row_first + st * row_stride, st);
+  }
   int it = 0;
   for (long long row = row_first; row < M; row += row_stride, ++it) {
     // s = x + drop(y); the keep mask is held as one bit per element
@@ -191,8 +194,8 @@ __global__ void __launch_bounds__(kWarps * 32, (kPer <= 2 ? 3 : 1)) add_ln_bwd_k
     const float* dsrc = dout;
     size_t arow = (size_t)row;
     if (kAsync) {
-      issue(row + row_stride, (it + 1) % kLnStages);          // next row on its way before this one is consumed
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      issue(row + (kLnStages - 1) * row_stride, (it + kLnStages - 1) % kLnStages);   // keep kLnStages - 1 rows on their way
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLnStages - 1) : "memory");
       xsrc = wbuf + (size_t)(it % kLnStages) * 3 * kPer * 128;
       ysrc = xsrc + kPer * 128;
       dsrc = xsrc + 2 * kPer * 128;
