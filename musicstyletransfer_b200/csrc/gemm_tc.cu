@@ -2,20 +2,27 @@
 //
 // Same contract as msx_gemm_f32 (gemm_simt.cu): replaces the gluon.nn.Dense forward / backward GEMMs of
 // /root/reference/music_style_transfer/VarAutoEncoder/{transformer.py:36-40,65-68,88-93,104, model.py:70-71,
-// 139-157,214-227}.  Operands stay fp32 in HBM and are consumed as TF32 by `tcgen05.mma.kind::tf32`
-// (fp32 accumulate in TMEM), so the tensor path drops into the fp32 step without conversion passes.
+// 139-157,214-227}.  Two operand types, one kernel body (template BF):
+//   TF32  operands stay fp32 in HBM and are consumed by `tcgen05.mma.kind::tf32` (TMA rounds them to nearest while
+//         loading), so the tensor path drops into the fp32 step without conversion passes;
+//   BF16  operands are bfloat16 in HBM (`kind::f16`); a stage row is 128 bytes either way, so the ring, the K-major
+//         descriptors and the 4 MMAs per stage are byte-identical (OpCfg holds what differs for MN-major operands).
+// Accumulation is fp32 in TMEM in both cases.
 //
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-stage smem ring
-//   warp 1      TMEM allocator + single-thread MMA issuer: 4 x (128 x 128 x 8) tcgen05.mma per stage,
-//               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-9   epilogue (two per TMEM lane group, half of the tile's columns each): tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout / aux-mask in the
-//               row-owner layout -> 128B-swizzled smem box -> TMA store, or TMA reduce-add (.add.f32) for
-//               accumulate and split-K, so C is never read by the SM and OOB rows/columns are clipped by TMA
-// Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of
-// tile i+1; CTAs are persistent (one per SM) and walk output tiles N-fastest so the A row-block of a
-// wave is shared through L2.  Operand majors: K-major (reduction dim contiguous: X in X W^T, W in X W^T,
-// dY in dY W) and MN-major (output dim contiguous: W in dY W, dY^T and X in dY^T X) are both fed by TMA;
-// only the shared-memory descriptor and the box geometry differ.
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-6 stage smem ring
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 tcgen05.mma per stage, tcgen05.commit releases the
+//               smem stage / publishes the accumulator
+//   warps 2..   epilogue, EW = 8 or 16 warps (EpiCfg: EW / 4 per TMEM lane group, each draining 4 / EW of the tile's
+//               columns): tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout / ReLU bit mask out / aux mask in /
+//               bias-gradient column sums in the row-owner layout -> swizzled smem box -> TMA store (fp32 or bf16 C),
+//               or TMA reduce-add (.add.f32) for accumulate and split-K, so C is never read by the SM and OOB rows /
+//               columns are clipped by TMA
+// Two TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1; CTAs are
+// persistent (one per SM) and walk output tiles N-fastest so the A row-block of a wave is shared through L2.
+// gemm_tc_kernel: 128 x 128 tiles on one CTA; gemm_tc2_kernel: 256 x 256 / 256 x 128 tiles on a CTA pair
+// (cta_group::2).  Operand majors: K-major (reduction dim contiguous: X in X W^T, W in X W^T, dY in dY W) and MN-major
+// (output dim contiguous: W in dY W, dY^T and X in dY^T X) are both fed by TMA; only the shared-memory descriptor and
+// the box geometry differ.
 #include <cuda.h>
 #include <stdlib.h>
 
