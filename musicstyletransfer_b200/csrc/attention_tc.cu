@@ -1,4 +1,5 @@
-// K2c (tensor-core path) — attention in the reference's convention on tcgen05, d_h = 32, T <= 128.
+// K2c (tensor-core path) — attention in the reference's convention on tcgen05, T <= 128, head width 32 or 16
+// (template parameter kDh; 16-wide heads still move 32-wide tiles and reduce over / store the first 16 columns).
 //
 // Same contract as attention.cu (replaces MultiHeadDotAttention.hybrid_forward lines 91-103 and _mask_logits,
 // /root/reference/music_style_transfer/VarAutoEncoder/transformer.py:91-126):

@@ -6,8 +6,9 @@
 //   model.py:241-247    Decoder: concat(initial_state, emb[tokens]); SequenceMask(len+1)
 //   transformer.py:237  TransformerDecoder: sqrt(D) * x + pos_embeddings[:T+1]
 //   model.py:176        LSTMDecoder: emb[tokens]                       (scale 1, no PE, no class term)
-// One warp per output row; rows are D floats, float4 when D % 4 == 0.  Backward scatters with
-// red.global.add (embedding rows collide by construction) and reduces the class term per CTA.
+// One warp per output row; rows are D floats.  Backward: large problems sort the positions of a 512-position segment
+// by token id in shared memory and sum whole rows per token in registers (embed_bwd_sorted_kernel); small problems and
+// prefix rows scatter with red.global.add (embedding rows collide by construction) and reduce the class term per CTA.
 #include "msx_common.cuh"
 
 namespace {

@@ -8,7 +8,10 @@
 // One warp per row, row kept in registers (D <= 1024), two-pass mean / variance exactly as
 // (x-mean)^2 averaged, so fp32 results track the un-fused oracle closely.  HBM-bound: reads x and y,
 // writes out (+ 8 B of statistics per row).  Backward re-creates s = x + drop(y) from the saved
-// inputs and the Philox mask, reduces dgamma / dbeta per CTA before one atomic per column.
+// inputs and the counter-hash mask, reduces dgamma / dbeta per CTA before one atomic per column; for D <= 256 the
+// rows it will process next are prefetched into per-warp shared-memory slots with cp.async (kAsync).  Grids are one
+// resident wave of CTAs.  The _ex entry points add the bf16-variant options: a bfloat16 copy of the output / of the
+// y-gradient for the bf16 GEMMs, and a bfloat16 y input.
 #include "msx_common.cuh"
 
 namespace {
