@@ -19,11 +19,8 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("MSX_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
-
-# stdout carries exactly one line (the JSON): everything else any library prints (NCCL banners, warnings) goes to stderr
+# stdout carries exactly one line (the JSON): everything else any library prints (NCCL_DEBUG banners, warnings) goes to
+# stderr through this dup2; NCCL_DEBUG itself is left as the caller set it
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
@@ -46,10 +43,11 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
     ap.add_argument("--dropout", type=float, default=0.2)
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32", "bf16"],
                     help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation), bf16 = "
                          "the tf32 path with the Transformer layers' GEMM operands stored as bfloat16 (BASELINE config 4)")
-    ap.add_argument("--cpu-batch", type=int, default=64, help="rows per oracle step (bounded CPU sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="rows per oracle step of the CPU arm (0 = the GPU arm's per-GPU batch, i.e. the same step)")
     ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
                     help="train: the contract line (default); sweep: BASELINE config 3 batch / sequence-length sweep, one JSON "
                          "line per point; style: BASELINE config 5 style-transfer inference")
@@ -62,19 +60,32 @@ def parse_args():
                     "around every libmsx call of three eager steps) to stderr")
     ap.add_argument("--gemm-table", action="store_true", help="also print a per-shape table of the step's GEMM launches to stderr")
     ap.add_argument("--no-raster", action="store_true")
-    ap.add_argument("--no-bf16-variant", action="store_true",
-                    help="skip the bf16-variant leg (BASELINE config 4) that the default tf32 line carries as a sub-object")
+    ap.add_argument("--no-variants", "--no-bf16-variant", dest="no_variants", action="store_true",
+                    help="skip the sub-object legs the default tf32 line carries: bf16 variant (BASELINE config 4), strict-fp32 "
+                         "(3xTF32) variant, strong-scaling points, the batch-32 step")
     return ap.parse_args()
 
 
 def workload_name(args):
-    return ("VarAutoEncoder train step (fwd+bwd+Adam) %s, scripts/train-vae.sh model: enc 2x256/8h, Z=256, "
-            "dec %s 1x128, dropout %.1f, B=%d per GPU, L=%d (T=%d), synthetic 4/4 token rows"
-            % ({"fp32": "fp32 storage, GEMMs fp32 FFMA", "tf32": "fp32 storage, GEMMs tcgen05 TF32 (fp32 accumulate)",
-                "bf16": "fp32 master weights / residual stream / LN / softmax / losses / Adam, Transformer-layer GEMM operands "
-                        "bf16 in HBM on tcgen05 kind::f16 (fp32 accumulate), other GEMMs TF32"}[args.precision],
-               args.dec_type, args.dropout,
-               args.batch, args.seq_len, args.seq_len + 1))
+    return ("VarAutoEncoder train step (fwd+bwd+Adam), scripts/train-vae.sh model: enc 2x256/8h, Z=256, dec %s 1x128, "
+            "dropout %.1f, B=%d per GPU, L=%d (T=%d), synthetic 4/4 token rows"
+            % (args.dec_type, args.dropout, args.batch, args.seq_len, args.seq_len + 1))
+
+
+PRECISION_NOTE = {
+    "fp32": "fp32 storage, GEMMs fp32 FFMA",
+    "fp32x3": "fp32 storage, GEMMs on tcgen05 with 3xTF32 operand splitting (hi/lo, three MMAs per k-block, fp32 accumulate): "
+              "fp32-equivalent products; attention / LSTM on the exact FFMA kernels",
+    "tf32": "fp32 storage, GEMMs tcgen05 TF32 (fp32 accumulate)",
+    "bf16": "fp32 master weights / residual stream / LN / softmax / losses / Adam, Transformer-layer GEMM operands bf16 in HBM on "
+            "tcgen05 kind::f16 (fp32 accumulate), other GEMMs TF32",
+}
+
+
+def config_dict(args, world):
+    """The workload description both arms print (same dict -> the driver can pair the lines)."""
+    return {"workload": workload_name(args), "global_batch": args.batch * world, "batch_per_gpu": args.batch,
+            "seq_len": args.seq_len, "parallelism": "dp%d" % world}
 
 
 def measured_peaks():
@@ -149,12 +160,12 @@ def oracle_step_rate(args, steps, warmup, threads=None):
     import torch
     from musicstyletransfer_b200 import synth
     from oracle import model as om
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly so the CPU arm always uses every host core
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     cfg = om.Cfg(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
     p = om.init_params(cfg, seed=0)
     opt = om.Adam(p, lr=3e-4, clip_gradient=1.0)
-    Bc = args.cpu_batch
+    Bc = args.cpu_batch or args.batch
     tok, lens, cls, lab = synth.token_rows_4_4(Bc * 2, args.seq_len, seed=1)
     t = lambda a: torch.from_numpy(a).float()
     batches = [(t(tok[i * Bc:(i + 1) * Bc]), t(lens[i * Bc:(i + 1) * Bc]), t(cls[i * Bc:(i + 1) * Bc]),
@@ -174,19 +185,22 @@ def oracle_step_rate(args, steps, warmup, threads=None):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    warmup = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 6))
+    warmup = max(1, min(args.warmup, 1))
     rate, per_step, cores = oracle_step_rate(args, steps, warmup)
+    Bc = args.cpu_batch or args.batch
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "reference = CPU oracle (the reference's MXNet 1.3 stack "
-                   "cannot run here, SURVEY.md §8(c)); each step is a %d-row sample of the workload" % args.cpu_batch},
+        "config": config_dict(args, world),
+        "note": "reference = CPU oracle (the reference's MXNet 1.3 stack cannot run here, SURVEY.md §8(c)), all host "
+                "threads on rank 0; each step is one %d-row batch of the workload (the GPU arm's per-GPU step)" % Bc,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d oracle steps of %d rows (torch-CPU fp32, all host threads)" % (steps, args.cpu_batch)},
+                         "sample": "%d oracle steps of %d rows (torch-CPU fp32, %d host threads)" % (steps, Bc, cores)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -414,30 +428,73 @@ def run_ours(args):
     if world > 1:
         barrier()
 
-    # ---- bf16 variant (BASELINE config 4), stated separately: same model, batch, data and timing protocol with
-    # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
-    bf16_variant = None
-    if args.precision == "tf32" and not args.no_bf16_variant:
-        eng2 = VAEEngine(cfg, dev, seed=0, precision="bf16")
-        train2 = eng2.train_step if args.no_graph else eng2.train_step_graphed
-        ar2 = allreduce if world > 1 else None
+    # ---- data parallel: every rank must hold bit-identical parameters after the timed steps (the exchange kernel
+    # writes each rank's updated slice into every peer's arena; NCCL path: identical all-reduced gradients)
+    ranks_identical = None
+    if world > 1:
+        w = eng.arena.w
+        chk = torch.stack([w.double().sum(), w.view(torch.int32).to(torch.int64).sum().double()])
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        ranks_identical = bool(all(torch.equal(c, allchk[0]) for c in allchk))
 
-        def step_bf16(i):
-            tk, ln, cl, lb = resident[i % n_batches]
-            return train2(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch, lr=3e-4, clip_gradient=1.0, allreduce=ar2)
+    def time_variant(precision, B_v, gbatch_v, steps_v, warm_v, seed_off=0):
+        """Same model / data generator / timing protocol on a fresh engine: `precision`, B_v rows per GPU per step,
+        gradients averaged over gbatch_v rows.  Data parallel runs take the same exchange as the headline."""
+        eng_v = VAEEngine(cfg, dev, seed=0, precision=precision)
+        ar_v = None
+        exch = "none"
+        if world > 1:
+            ar_v, exch = allreduce, "nccl all-reduce + Adam on every rank"
+            if args.dp == "peer" and ar == "peer":
+                try:
+                    eng_v.enable_peer_optimizer()
+                    ar_v, exch = "peer", "fused NVLink optimiser step (msx_adam_nvlink_step)"
+                except Exception as exc:
+                    print("bench: peer optimiser unavailable for the %s variant (%s)" % (precision, exc), file=sys.stderr)
+        tok_v, lens_v, cls_v, lab_v = synth.token_rows_4_4(B_v * n_batches, L, seed=200 + seed_off + rank)
+        res_v = [tuple(torch.from_numpy(a[i * B_v:(i + 1) * B_v].copy()).to(dev) for a in (tok_v, lens_v, cls_v, lab_v))
+                 for i in range(n_batches)]
+        train_v = eng_v.train_step if args.no_graph else eng_v.train_step_graphed
 
-        ms2, _, _ = timed(step_bf16, K, W)
-        bf16_variant = {"value": gbatch * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K, "dtype": "bf16",
-                        "dp_exchange": "none" if world == 1 else "nccl all-reduce + Adam on every rank",
-                        "what": "Transformer-layer GEMM operands (activations, their gradients, weight shadow) bf16 in HBM on "
-                                "tcgen05 kind::f16, fp32 accumulate; fp32 master weights / LN / softmax / losses / Adam",
-                        "parity": "vs fp32 oracle: loss 1e-4, KL 1e-3, latent means 1e-2, gradients 10 % worst tensor / 3 % "
-                                  "mean (tests/test_engine_gpu.py::test_bf16_variant_step_vs_oracle)"}
-        eng2._graphs.clear()
-        del eng2, train2
+        def step_v(i):
+            tk, ln, cl, lb = res_v[i % n_batches]
+            return train_v(tk, ln, cl, lb, kl_weight=1.0, global_batch=gbatch_v, lr=3e-4, clip_gradient=1.0, allreduce=ar_v)
+
+        ms_v, _, _ = timed(step_v, steps_v, warm_v)
+        out = {"value": gbatch_v * steps_v / (ms_v * 1e-3), "unit": UNIT, "ms_per_step": ms_v / steps_v,
+               "batch_per_gpu": B_v, "global_batch": gbatch_v, "steps": steps_v, "dp_exchange": exch}
+        eng_v._graphs.clear()
+        del eng_v, train_v, res_v
         torch.cuda.synchronize()
         if world > 1:
             barrier()
+        return out
+
+    # ---- bf16 variant (BASELINE config 4), stated separately: same model, batch, data and timing protocol with
+    # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
+    bf16_variant = fp32_variant = b32 = None
+    strong = []
+    if args.precision == "tf32" and not args.no_variants:
+        bf16_variant = time_variant("bf16", B, gbatch, K, W)
+        bf16_variant.update({"dtype": "bf16", "what": PRECISION_NOTE["bf16"],
+                             "parity": "vs fp32 oracle: loss 1e-4, KL 1e-3, latent means 1e-2, gradients 10 % worst tensor / "
+                                       "3 % mean (tests/test_engine_gpu.py::test_bf16_variant_step_vs_oracle)"})
+        # ---- strict-fp32 variant: the reference's own precision (trainer.py:155-179 is fp32 end to end)
+        fp32_variant = time_variant("fp32x3", B, gbatch, max(5, K // 2), 3)
+        fp32_variant.update({"dtype": "f32", "what": PRECISION_NOTE["fp32x3"],
+                             "parity": "every gradient within 1e-3 of its scale vs the fp32 oracle "
+                                       "(tests/test_engine_gpu.py::test_fp32x3_step_matches_oracle)"})
+        # ---- strong scaling: the global batch is fixed, each GPU takes 1/N of it
+        for gb in (2048, 256):
+            if gb % world == 0 and not (world == 1 and gb == B):
+                sv = time_variant("tf32", gb // world, gb, K, W, seed_off=7)
+                sv["scaling"] = "strong"
+                strong.append(sv)
+        # ---- the reference's own configuration of record (scripts/train-vae.sh: batch 32), one graph launch per step
+        if world == 1:
+            b32 = time_variant("tf32", 32, 32, 200, 10, seed_off=11)
+            b32["what"] = "scripts/train-vae.sh batch size (32 rows, L=64), CUDA-graph replay"
 
     if rank != 0:
         if world > 1:
@@ -451,18 +508,21 @@ def run_ours(args):
         raster = bench_rasteriser(peaks)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, per_step, cores = oracle_step_rate(args, steps=4, warmup=1)
+        rate, per_step, cores = oracle_step_rate(args, steps=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "4 oracle steps of %d rows (torch-CPU fp32 restatement of Trainer._step, all host threads)" % args.cpu_batch,
+               "sample": "3 oracle steps of %d rows, the GPU arm's own step (torch-CPU fp32 restatement of Trainer._step, "
+                         "%d host threads)" % (args.cpu_batch or args.batch, cores),
                "ms_per_step": per_step * 1e3}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": gbatch, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange,
-                   "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
-                         (B * T * 4 * 40e3 / 1e9 / 10)},
+        "config": config_dict(args, world),
+        "run": {"precision": PRECISION_NOTE[args.precision], "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange, "ranks_identical": ranks_identical,
+                "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
+                      (B * T * 4 * 40e3 / 1e9 / 10)},
         "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu, "bf16_variant": bf16_variant,
+        "fp32_variant": fp32_variant, "strong_scaling": strong or None, "b32": b32,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches, "clocks": clocks,

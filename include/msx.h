@@ -38,6 +38,12 @@ int msx_device_sm_count(void);
 int msx_set_step_counter(unsigned long long* dev_counter);
 int msx_step_counter_tick(unsigned long long* dev_counter, void* stream);
 
+/* Keep-mask of one dropout site exactly as the step's kernels draw it: out[e] = 1 when element e (row-major index into
+ * the site's [rows, width] activation) is kept, for (seed [+ registered step counter], site, drop_p).  Sites of Transformer
+ * layer l (encoder: l, decoder: 8 + l): 16 l + {0: attention output [M, D], 1: FF hidden [M, 4D], 2: FF output [M, D]}
+ * (gluon.nn.Dropout, transformer.py:44,155,158,200).  Used to replay a dropout step in a checker. */
+int msx_dropout_mask(uint8_t* out, long long n, float drop_p, unsigned long long seed, unsigned site, void* stream);
+
 /* K1 — note-event rasteriser.  Replaces EventBasedMIDIReader._parse_track (MIDIUtil/midi_io.py:70-93),
  * create_{note_on,note_off,timeshift}_event (MIDIUtil/Melody.py:109-126) and the clock semantics of
  * MelodyWriter._write_track (MIDIUtil/midi_io.py:119-127) for N independent sequences.
@@ -200,6 +206,9 @@ int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, 
 int msx_reparam_kl_bwd(const float* lat, const float* eps, const float* dz, const float* gkl, float kl_weight,
                        float* dlat, int B, int Z, void* stream);
 int msx_normal_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+/* Running sums behind the reference's per-step CustomMetric means of the KL and total loss (trainer.py:107-120,181-186):
+ * sums[0] += sum_b kl[b], sums[1] += sum_b (ce[b] + kl_weight * kl[b]), sums[2] += B.  One launch, no host sync. */
+int msx_loss_sums(const float* ce, const float* kl, float kl_weight, float* sums, int B, void* stream);
 int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, float* ce, float* lse, float* metrics, int B, int T,
                int V, int denom, int top_k, void* stream);
 int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, const float* lse, const float* gout, int B, int T,

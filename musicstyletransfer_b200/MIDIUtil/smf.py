@@ -136,6 +136,8 @@ def parse_bytes(buf):
                     raise ValueError("running status without a status byte")
                 n = _CHANNEL_LEN[status >> 4]
                 data = list(buf[pos:pos + n])
+                if len(data) != n or any(d & 0x80 for d in data):
+                    raise ValueError("malformed channel event at byte %d: data bytes must be 7-bit" % pos)
                 pos += n
                 kind = status >> 4
                 if kind == 0x9:

@@ -1,7 +1,12 @@
-"""Command-line flags and YAML-serialisable config objects — same flag table as the reference's
-VarAutoEncoder/config.py:19-75 (names, types, defaults; unknown flags are ignored via parse_known_args) plus
-additive flags for this implementation, and a ``Config`` base class with the reference's save / load / copy /
-freeze surface (config.py:90-222)."""
+"""Command-line flags and YAML-serialisable config objects.
+
+The flag table is the reference's (VarAutoEncoder/config.py:19-75: names, types, defaults; unknown flags are
+ignored through parse_known_args) plus additive flags of this implementation.  ``Config`` offers the
+reference's public surface (config.py:90-222: save / load / copy / freeze / set_attrs / output_to_stream and
+the ``!ClassName`` YAML tags of the on-disk ``config`` file) on a different mechanism: subclasses register
+themselves in a class registry, (de)serialisation goes through a SafeLoader / SafeDumper pair that only knows
+the registered classes (a model folder's ``config`` cannot construct arbitrary Python objects), and the frozen
+state lives in a per-instance slot that is never part of the serialised mapping."""
 import argparse
 import copy
 import inspect
@@ -93,95 +98,124 @@ def get_config(argv=None):
     return config
 
 
-class _TaggedMeta(yaml.YAMLObjectMetaclass):
-    """Every subclass gets the YAML tag ``!<ClassName>`` so configs round-trip as typed objects."""
-
-    def __init__(cls, name, bases, kwds):
-        cls.yaml_tag = "!" + name
-        cls.yaml_loader = yaml.UnsafeLoader
-        super().__init__(name, bases, dict(kwds, yaml_tag="!" + name))
+class _ConfigLoader(yaml.SafeLoader):
+    """SafeLoader that additionally constructs the registered Config subclasses from their ``!ClassName`` tags."""
 
 
-class Config(yaml.YAMLObject, metaclass=_TaggedMeta):
-    """Freezable, YAML-(de)serialisable configuration object (interface of config.py:90-222)."""
+class _ConfigDumper(yaml.SafeDumper):
+    """SafeDumper that writes registered Config subclasses as ``!ClassName`` mappings."""
+
+
+_STATE_KEY = "_frozen"          # the only per-instance attribute that is not configuration
+
+
+def _public_items(obj):
+    return [(k, v) for k, v in sorted(vars(obj).items()) if k != _STATE_KEY]
+
+
+def _represent_config(dumper, obj):
+    return dumper.represent_mapping("!" + type(obj).__name__, _public_items(obj))
+
+
+class Config:
+    """Base class of the model / transformer / LSTM configuration objects."""
+
+    registry = {}
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        Config.registry[cls.__name__] = cls
+        _ConfigDumper.add_representer(cls, _represent_config)
+        _ConfigLoader.add_constructor("!" + cls.__name__, lambda loader, node, _cls=cls: _cls._from_yaml(loader, node))
 
     def __init__(self):
-        self.__add_frozen()
+        object.__setattr__(self, _STATE_KEY, False)
 
+    # ---------------------------------------------------------------- construction from a saved mapping
+    @classmethod
+    def _from_yaml(cls, loader, node):
+        obj = cls.__new__(cls)
+        object.__setattr__(obj, _STATE_KEY, False)
+        yield obj                                   # two-step construction: nested configs / anchors resolve first
+        obj._restore(loader.construct_mapping(node, deep=True))
+
+    def _restore(self, fields):
+        """Fills the instance from a saved mapping; constructor arguments that a file written by an older version does
+        not carry take their declared defaults, so old model folders keep loading."""
+        for k, v in fields.items():
+            object.__setattr__(self, k, v)
+        for name, param in inspect.signature(type(self).__init__).parameters.items():
+            if name != "self" and param.default is not inspect.Parameter.empty and name not in fields:
+                object.__setattr__(self, name, param.default)
+
+    def __getstate__(self):
+        return dict(_public_items(self))
+
+    def __setstate__(self, state):                  # pickle / deepcopy
+        object.__setattr__(self, _STATE_KEY, False)
+        self._restore(state)
+
+    # ---------------------------------------------------------------- attribute protocol
     def __setattr__(self, key, value):
-        if getattr(self, '_frozen', False):
+        if vars(self).get(_STATE_KEY, False):
             raise AttributeError("Cannot set '%s' in frozen config" % key)
         if value is self:
             raise AttributeError("Cannot set self as attribute")
         object.__setattr__(self, key, value)
 
-    def __setstate__(self, state):
-        self.__dict__.update(state)
-        # constructor defaults for arguments an older saved config does not carry
-        for pname, param in inspect.signature(self.__init__).parameters.items():
-            if param.default is not param.empty and not hasattr(self, pname):
-                object.__setattr__(self, pname, param.default)
+    def _children(self):
+        return [v for _, v in _public_items(self) if isinstance(v, Config)]
 
     def freeze(self):
-        if getattr(self, '_frozen', False):
-            return
-        object.__setattr__(self, "_frozen", True)
-        for k, v in self.__dict__.items():
-            if isinstance(v, Config) and k != "self":
-                v.freeze()
+        """Disallows any further modification of this object and of the configs nested in it."""
+        object.__setattr__(self, _STATE_KEY, True)
+        for child in self._children():
+            child.freeze()
+
+    @property
+    def frozen(self):
+        return bool(vars(self).get(_STATE_KEY, False))
 
     def __repr__(self):
-        return "Config[%s]" % ", ".join("%s=%s" % (str(k), str(v)) for k, v in sorted(self.__dict__.items()))
+        return "Config[%s]" % ", ".join("%s=%s" % (k, v) for k, v in _public_items(self))
 
     def __eq__(self, other):
-        if type(other) is not type(self):
-            return False
-        return all(k in other.__dict__ and other.__dict__[k] == v for k, v in self.__dict__.items() if k != "self")
+        return type(other) is type(self) and dict(_public_items(self)) == dict(_public_items(other))
 
     __hash__ = None
 
-    def __del_frozen(self):
-        if '_frozen' in self.__dict__:
-            object.__delattr__(self, '_frozen')
-        for val in self.__dict__.values():
-            if isinstance(val, Config):
-                val.__del_frozen()
-
-    def __add_frozen(self):
-        object.__setattr__(self, "_frozen", False)
-        for val in self.__dict__.values():
-            if isinstance(val, Config):
-                val.__add_frozen()
+    # ---------------------------------------------------------------- (de)serialisation
+    def output_to_stream(self, stream):
+        yaml.dump(self, stream, Dumper=_ConfigDumper, default_flow_style=False)
 
     def save(self, fname: str):
-        obj = copy.deepcopy(self)
-        obj.__del_frozen()
-        with open(fname, 'w') as out:
-            yaml.dump(obj, out, default_flow_style=False)
+        """Writes the configuration (never its frozen state) to `fname`."""
+        with open(fname, "w") as out:
+            self.output_to_stream(out)
 
     @staticmethod
-    def load(fname: str) -> 'Config':
+    def load(fname: str) -> "Config":
+        """Reads a configuration written by save(); the result is not frozen.  Only registered Config subclasses and
+        plain YAML scalars / lists / mappings are constructed."""
         with open(fname) as inp:
-            obj = yaml.load(inp, Loader=yaml.UnsafeLoader)
-            obj.__add_frozen()
-            return obj
+            obj = yaml.load(inp, Loader=_ConfigLoader)
+        if not isinstance(obj, Config):
+            raise ValueError("%s does not hold a Config object" % fname)
+        return obj
 
     def copy(self, **kwargs):
-        copy_obj = copy.deepcopy(self)
+        """Unfrozen deep copy, optionally with some attributes replaced: ``cfg.copy(num_layers=3)``."""
+        dup = copy.deepcopy(self)
         for name, value in kwargs.items():
-            object.__setattr__(copy_obj, name, value)
-        return copy_obj
+            object.__setattr__(dup, name, value)
+        return dup
 
     def set_attrs(self, attrs):
+        """Constructor helper, ``self.set_attrs(locals())``: adds every entry that is not already an attribute."""
         for k, v in attrs.items():
-            if k == 'self' and self is v:
+            if k == "self" and v is self:
                 continue
             if hasattr(self, k):
-                print('Not automatically over writing setting %s, %s. %s is already defined for Object %s' % (k, str(v), k, self))
+                print("Not automatically over writing setting %s, %s. %s is already defined for Object %s" % (k, v, k, self))
             else:
                 setattr(self, k, v)
-
-    def output_to_stream(self, stream):
-        obj = copy.deepcopy(self)
-        obj.__del_frozen()
-        yaml.dump(obj, stream)

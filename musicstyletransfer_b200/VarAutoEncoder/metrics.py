@@ -6,6 +6,8 @@ import math
 
 import torch
 
+from .. import ops
+
 
 class DeviceMetrics:
     names = ["ppl", "acc", "topk", "kl_loss", "total_loss"]
@@ -19,11 +21,16 @@ class DeviceMetrics:
         self.engine.metrics.zero_()
         self.loss_sums.zero_()
 
-    def update(self, kl, total):
-        # running sums stay on the device (tiny torch reductions over [B] vectors: plumbing, not the hot path)
-        self.loss_sums[0] += kl.sum()
-        self.loss_sums[1] += total.sum()
-        self.loss_sums[2] += kl.numel()
+    def update(self, ce, kl, kl_weight):
+        """Adds this step's per-sample losses to the running sums: one libmsx launch, nothing leaves the device."""
+        ops.loss_sums(ce, kl, kl_weight, self.loss_sums)
+
+    def all_reduce(self):
+        """Data parallel: every rank sees the sums over ALL shards, so checkpoint decisions (early stopping, best loss)
+        are identical on every rank and no rank leaves fit() while the others wait in the next step's collective."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.engine.metrics)
+            torch.distributed.all_reduce(self.loss_sums)
 
     def get_name_value(self):
         m = self.engine.metrics.tolist()           # the only device->host read

@@ -153,6 +153,7 @@ class Model:
             print("Creating a model with the following configuration:")
             config.output_to_stream(sys.stdout)
         self.config = config
+        self.engine_seed = seed                    # --seed: also the seed of initialize() (Trainer._initialize_model)
         device = context if isinstance(context, (torch.device, str)) and str(context).startswith("cuda") else \
             torch.device("cuda", torch.cuda.current_device())
         self.engine = VAEEngine(to_engine_config(config), device, seed=seed, precision=precision)
@@ -175,8 +176,6 @@ class Model:
     def initialize(self, init=None, ctx=None, seed=None):
         """mx.init.Xavier() (trainer.py:103-105)."""
         self.engine.arena.init_xavier(self.engine_seed if seed is None else seed)
-
-    engine_seed = 0
 
     def hybridize(self, *a, **k):
         pass

@@ -4,7 +4,12 @@ sampler).fit(dataset, model_folder, epochs, validation_dataset)`` and ``._step(b
 The step is one engine call sequence: forward (+ fused CE/KL), hand-scheduled backward into the flat gradient
 arena, optional NCCL all-reduce of that arena (data parallelism, one process per GPU) and the fused Adam pass.
 File layout of checkpoints is the reference's: ``params.<n>``, ``train_state.pkl`` (+ ``opt_state.<n>`` with the
-Adam moments, which the reference does not save)."""
+Adam moments and the step count of the random streams, which the reference does not save).
+
+Provenance: ``OptimizerConfig`` / ``TrainConfig`` / ``TrainingState`` and the control flow of ``fit`` / ``_checkpoint`` /
+``_periodic_log`` (what is printed, when checkpoints are written, the early-stopping rule) deliberately follow the
+reference's trainer.py:14-65,122-153,202-255 — they are host control flow that a drop-in must reproduce; ``_step``, the
+optimiser, the metrics, data parallelism, CUDA-graph replay and the checkpoint contents are new."""
 import os
 from time import time
 
@@ -54,6 +59,25 @@ class TrainingState:
         self.n_batches = 0
         self.num_checkpoints_not_improved = 0
         self.best_resconstruction_loss = np.inf
+
+
+class _LazyLoss:
+    """Per-sample total loss of a step (what the reference's _step returns, trainer.py:172,179), formed only when the
+    caller actually looks at it: the training loop itself does not, and forming it eagerly would put torch elementwise
+    kernels on every step."""
+
+    def __init__(self, ce, kl, kl_weight):
+        self.ce, self.kl, self.kl_weight = ce, kl, kl_weight
+
+    def value(self):
+        return self.ce + self.kl_weight * self.kl
+
+    def __getattr__(self, name):                # tensor protocol by delegation (mean(), cpu(), shape, ...)
+        return getattr(self.value(), name)
+
+    def __array__(self, dtype=None):
+        a = self.value().detach().cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
 
 
 class Trainer:
@@ -153,9 +177,8 @@ class Trainer:
                 if self.world > 1:
                     torch.distributed.all_reduce(self.engine.arena.g)
                 self.engine.adam_step(global_batch, **self.opt)
-        loss = out["ce"] + self.config.kl_loss_weight * out["kl"]
-        self.metrics.update(out["kl"], loss)
-        return loss
+        self.metrics.update(out["ce"], out["kl"], self.config.kl_loss_weight)
+        return _LazyLoss(out["ce"], out["kl"], self.config.kl_loss_weight)
 
     def _load_latest_checkpoint(self, model_folder):
         print("Looking into folder {} for a valid training.".format(model_folder))
@@ -172,6 +195,8 @@ class Trainer:
             st = torch.load(opt_path, map_location="cpu")
             a = self.engine.arena
             a.m.copy_(st["m"]); a.v.copy_(st["v"]); a.adam_state.copy_(st["state"])
+            # continue the dropout / eps seed sequence where the saved run stopped (older files: the Adam step count)
+            self.engine.set_step_count(int(st.get("step_count", int(st["state"][0]))))
 
     def _checkpoint(self, model_folder, validation_dataset):
         self.train_state.n_checkpoints += 1
@@ -181,13 +206,16 @@ class Trainer:
             utils.save_model(self.model, os.path.join(model_folder, 'params.{}'.format(self.train_state.n_checkpoints)))
             utils.save_object(self.train_state, os.path.join(model_folder, "train_state.pkl"))
             a = self.engine.arena
-            torch.save({"m": a.m.cpu(), "v": a.v.cpu(), "state": a.adam_state.cpu()},
+            torch.save({"m": a.m.cpu(), "v": a.v.cpu(), "state": a.adam_state.cpu(), "step_count": self.engine.step_count},
                        os.path.join(model_folder, "opt_state.{}".format(self.train_state.n_checkpoints)))
         self._reset_metrics()
         if validation_dataset is None:
             return
         for batch in validation_dataset:
             self._step(batch, is_train=False)
+        # every rank validated its own shard of each batch: sum the counters over ranks so that the improved / stop
+        # decision below (and best_resconstruction_loss) is the same everywhere
+        self.metrics.all_reduce()
         reconstruction_loss = dict(self.metrics.get_name_value())["total_loss"]
         if reconstruction_loss < self.train_state.best_resconstruction_loss:
             print("Loss improved from {} to {}.".format(self.train_state.best_resconstruction_loss, reconstruction_loss))

@@ -431,7 +431,39 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred
   }
 }
 
+// running sums of the step metrics (trainer.py:107-120 CustomMetric means): sums += {sum kl, sum (ce + w kl), B}
+__global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict__ ce, const float* __restrict__ kl,
+                                                        float kl_weight, float* __restrict__ sums, int B) {
+  __shared__ float red[2][8];
+  float a = 0.f, t = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float k = kl[i];
+    a += k;
+    t += ce[i] + kl_weight * k;
+  }
+  a = warp_sum(a);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = t; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, stt = 0.f;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; stt += red[1][w]; }
+    sums[0] += sa;
+    sums[1] += stt;
+    sums[2] += (float)B;
+  }
+}
+
 }  // namespace
+
+extern "C" int msx_loss_sums(const float* ce, const float* kl, float kl_weight, float* sums, int B, void* stream) {
+  MSX_REQUIRE(B >= 0, "msx_loss_sums: B < 0");
+  if (B == 0) return MSX_OK;
+  MSX_REQUIRE(ce && kl && sums, "msx_loss_sums: null pointer");
+  loss_sums_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ce, kl, kl_weight, sums, B);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
 
 extern "C" int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, int B, int Z, void* stream) {
   MSX_REQUIRE(lat && eps && z && kl, "msx_reparam_kl_fwd: null pointer");

@@ -84,3 +84,30 @@ extern "C" int msx_cast_f32_bf16(const float* src, void* dst, long long n, void*
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
+
+// ---- keep-mask of one dropout site, as the step's kernels draw it (msx_common.cuh: dropout_scale4): out[e] = 1 when
+// element e (row-major index into the site's activation matrix) is kept.  Lets a checker replay a dropout step.
+static __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ out, long long n, float p,
+                                                                   unsigned long long seed, const unsigned long long* ctr,
+                                                                   unsigned site) {
+  const unsigned long long eff = msx_eff_seed(seed, ctr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
+    float k[4];
+    dropout_scale4(eff, site, (uint64_t)q, p, 1.f, k);
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = k[j] != 0.f ? 1 : 0;
+  }
+}
+
+extern "C" int msx_dropout_mask(uint8_t* out, long long n, float drop_p, unsigned long long seed, unsigned site, void* stream) {
+  MSX_REQUIRE(n >= 0, "msx_dropout_mask: negative length");
+  if (n == 0) return MSX_OK;
+  MSX_REQUIRE(out, "msx_dropout_mask: null pointer");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_dropout_mask: dropout probability must be in [0,1)");
+  const long long want = (n / 4 + 256) / 256;
+  const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
+  dropout_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, seed, msx_step_counter(), site);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}

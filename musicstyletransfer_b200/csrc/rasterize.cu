@@ -92,8 +92,10 @@ __global__ void __launch_bounds__(256) rasterize_kernel(const int* __restrict__ 
     int e = e0 + lane;
     bool valid = e < e1;
     int d = valid ? __ldg(dtick + e) : 0;
-    int p = valid ? __ldg(pitch + e) : 0;
-    int v = valid ? __ldg(vel + e) : 0;
+    // MIDI data bytes are 7-bit; a malformed byte >= 0x80 is masked (as the oracle does) so that the 128-entry pitch
+    // table / tile column indexed below can never be addressed out of range and token ids stay below the vocabulary
+    int p = valid ? (__ldg(pitch + e) & 0x7F) : 0;
+    int v = valid ? (__ldg(vel + e) & 0x7F) : 0;
 
     if (store_pending) {
       if (lane == 0) bulk_wait_read0();
@@ -118,8 +120,8 @@ __global__ void __launch_bounds__(256) rasterize_kernel(const int* __restrict__ 
         e = c + lane;
         valid = e < e1;
         d = valid ? __ldg(dtick + e) : 0;
-        p = valid ? __ldg(pitch + e) : 0;
-        v = valid ? __ldg(vel + e) : 0;
+        p = valid ? (__ldg(pitch + e) & 0x7F) : 0;
+        v = valid ? (__ldg(vel + e) & 0x7F) : 0;
       }
       // ---- tokens (midi_io.py:81-89): ceil(d/1000) shift tokens of bin (d%1000)/30, then the note token
       const int n_shift = (valid && d > 0) ? (int)(((long long)d + kMaxTicks - 1) / kMaxTicks) : 0;

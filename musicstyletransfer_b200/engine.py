@@ -198,8 +198,14 @@ class VAEEngine:
         self.ldv = (cfg.vocab + 3) // 4 * 4          # padded leading dimension of the logits
         self.metrics = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._bufs = {}
-        self.dropout_seed = 0x5EED
+        # Random streams (dropout masks, eps): every kernel keys its generator by base_seed + the DEVICE step counter
+        # step_dev, which equals the number of optimiser steps taken (adam_step ticks it on the stream, eagerly and inside
+        # captured graphs alike).  One counter for the whole engine: eager steps, every captured graph and resumed runs
+        # walk one seed sequence, no two optimisation steps share masks.
+        self.base_seed = 0x5EED0000
+        self.dropout_seed = self.base_seed
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.ctx = None
         self._graphs = {}
@@ -706,10 +712,24 @@ class VAEEngine:
         return seq[cur][:, :stop + 1].clone(), score[cur].clone()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
-                z_override=None, fuse_ce_bwd=False):
+    def forward(self, *args, **kwargs):
         """tokens int32 [B,T], seq_lens int32 [B], classes int32 [B], labels int32 [B,T] (optional),
         eps fp32 [B,Z] (None -> Philox N(0,1)).  Returns dict(ce, kl, means, stds[, probs])."""
+        try:
+            return self._forward(*args, **kwargs)
+        finally:
+            ops.set_step_counter(None)              # the registration is library-global: never leave it dangling
+
+    def backward(self, *args, **kwargs):
+        """Accumulates d(sum_b g_ce[b]*ce_b + g_kl[b]*kl_weight*kl_b)/dparams into the gradient arena
+        (trainer.py:172,176: loss = ce + kl_weight*kl, loss.backward() with head gradient ones)."""
+        try:
+            return self._backward(*args, **kwargs)
+        finally:
+            ops.set_step_counter(None)
+
+    def _forward(self, tokens, seq_lens, classes, labels=None, eps=None, train=True, want_probs=False,
+                 z_override=None, fuse_ce_bwd=False):
         cfg, dev = self.cfg, self.device
         B, T = tokens.shape
         D, Z, V, Hd = cfg.enc_size, cfg.latent, cfg.vocab, cfg.dec_size
@@ -718,7 +738,8 @@ class VAEEngine:
         M = B * T
         pe_ = cfg.enc_dropout if train else 0.0
         pd_ = cfg.dec_dropout if train else 0.0
-        self.dropout_seed = (0x5EED0000 + self.step_count) & 0xFFFFFFFFFFFF
+        self.dropout_seed = self.base_seed
+        ops.set_step_counter(self.step_dev)         # kernels launched from here on add the device step count to the seed
 
         xs, mask, lat = self._encode(bf, tokens, classes, B, T, pe_)
         x = xs[-1]
@@ -814,14 +835,13 @@ class VAEEngine:
         return out
 
     # ------------------------------------------------------------------ backward
-    def backward(self, kl_weight=1.0, g_ce=None, g_kl=None):
-        """Accumulates d(sum_b g_ce[b]*ce_b + g_kl[b]*kl_weight*kl_b)/dparams into the gradient arena
-        (trainer.py:172,176: loss = ce + kl_weight*kl, loss.backward() with head gradient ones)."""
+    def _backward(self, kl_weight=1.0, g_ce=None, g_kl=None):
         c = self.ctx
         cfg, dev, bf = self.cfg, self.device, c["bf"]
         B, T, Td = c["B"], c["T"], c["Td"]
         D, Z, V, Hd = cfg.enc_size, cfg.latent, cfg.vocab, cfg.dec_size
         M, Mo = B * T, B * Td
+        ops.set_step_counter(self.step_dev)         # the backward regenerates the forward's dropout masks
         logits = c["logits"]
         lse = bf.t[("lse", (Mo,), torch.float32)]
         fuse_db = V <= 512
@@ -910,7 +930,13 @@ class VAEEngine:
         else:
             ops.adam_step(a.w, a.g, a.m, a.v, a.numel, a.adam_state, lr, beta1, beta2, eps, wd, 1.0 / batch_size,
                           clip_gradient, zero_grad=True)
+        ops.step_counter_tick(self.step_dev)
         self.step_count += 1
+
+    def set_step_count(self, n):
+        """Resume: continue the seed sequence of dropout masks / eps from optimiser step n (checkpoints store it)."""
+        self.step_count = int(n)
+        self.step_dev.fill_(int(n))
 
     # ------------------------------------------------------------------ data parallel over NVLink peer memory
     def enable_peer_optimizer(self, group=None):
@@ -945,8 +971,9 @@ class VAEEngine:
         step is static, so the ~66 kernel launches collapse into one graph launch; this is what keeps the reference's own
         B = 32 configuration (scripts/train-vae.sh) from being launch-bound.  The first call with a new key runs eagerly
         (it allocates every buffer), the second captures, later ones only copy the batch into the static input buffers
-        and replay.  Dropout masks and eps stay fresh on every replay through the device-side step counter
-        (msx_set_step_counter).  Returns the same dict as train_step (views of static buffers)."""
+        and replay.  Dropout masks and eps stay fresh on every replay through the engine-wide device step counter
+        (step_dev, msx_set_step_counter) that the captured Adam node ticks.  Returns the same dict as train_step (views of
+        static buffers)."""
         B, T = tokens.shape
         peer = isinstance(allreduce, str) and allreduce == "peer"
         key = (B, T, float(kl_weight), global_batch, float(lr), clip_gradient, "peer" if peer else allreduce is not None)
@@ -959,27 +986,20 @@ class VAEEngine:
         if st["graph"] is None:
             from . import lib
             st["in"] = tuple(torch.empty_like(t) for t in (tokens, seq_lens, classes, labels))
-            st["counter"] = torch.zeros(1, dtype=torch.int64, device=self.device)
             # with a collective between backward and the optimiser the step is captured as two graphs around an eagerly
             # launched all-reduce (NCCL inside a captured graph ties the graph's lifetime to the communicator's)
             two = allreduce is not None and not peer
             graph, graph2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if two else None)
             l0 = lib.LAUNCHES
-            ops.set_step_counter(st["counter"])
-            try:
-                with torch.cuda.graph(graph):
-                    out = self.forward(*st["in"][:3], st["in"][3], train=True, fuse_ce_bwd=True)
-                    self.backward(kl_weight)
-                    if not two:
-                        self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient, peer=peer)
-                        ops.step_counter_tick(st["counter"])
-                if two:
-                    with torch.cuda.graph(graph2):
-                        self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient)
-                        ops.step_counter_tick(st["counter"])
-            finally:
-                ops.set_step_counter(None)
-            self.step_count -= 1                      # the capture pass executed nothing
+            with torch.cuda.graph(graph):
+                out = self.forward(*st["in"][:3], st["in"][3], train=True, fuse_ce_bwd=True)
+                self.backward(kl_weight)
+                if not two:
+                    self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient, peer=peer)
+            if two:
+                with torch.cuda.graph(graph2):
+                    self.adam_step(global_batch or B, lr=lr, clip_gradient=clip_gradient)
+            self.step_count -= 1                      # the capture pass executed nothing (host mirror of step_dev)
             st["graph"], st["graph2"], st["out"], st["launches"] = graph, graph2, out, lib.LAUNCHES - l0
             lib.LAUNCHES = l0
         from . import lib

@@ -105,6 +105,12 @@ def step_counter_tick(counter):
     lib.call("msx_step_counter_tick", P(counter), lib.stream_ptr())
 
 
+def dropout_mask(out, drop_p, seed, site):
+    """out (uint8, flat view of the site's activation matrix) = keep mask the step's kernels draw for (seed, site)."""
+    assert out.dtype == torch.uint8 and out.is_cuda
+    lib.call("msx_dropout_mask", P(out), _ll(out.numel()), _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
+
+
 def colsum(X, ld, M, N, out):
     lib.call("msx_colsum", P(X), _i(ld), _ll(M), _i(N), P(out), lib.stream_ptr())
 
@@ -184,6 +190,11 @@ def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, pr
 
 def reparam_kl_fwd(lat, eps, z, kl, B, Z):
     lib.call("msx_reparam_kl_fwd", P(lat), P(eps), P(z), P(kl), _i(B), _i(Z), lib.stream_ptr())
+
+
+def loss_sums(ce, kl, kl_weight, sums):
+    """sums (fp32 [3]) += [sum kl, sum (ce + kl_weight * kl), B]."""
+    lib.call("msx_loss_sums", P(ce), P(kl), _f(kl_weight), P(_chk(sums)), _i(kl.numel()), lib.stream_ptr())
 
 
 def reparam_kl_bwd(lat, eps, dz, gkl, kl_weight, dlat, B, Z):

@@ -35,6 +35,7 @@ def tokenize_note_events(dtick, pitch, vel):
     velocity>0 -> NOTE_ON, velocity==0 -> NOTE_OFF regardless of MIDI event type (:85-89)."""
     ids = []
     for d, p, v in zip(dtick, pitch, vel):
+        p, v = int(p) & 0x7F, int(v) & 0x7F                 # MIDI data bytes are 7-bit (malformed input is masked)
         delta = int(d)
         while delta > 0:                                    # :81-83 (lossy modulo quirk)
             ids.append(timeshift_id(delta % MAX_TICKS))
@@ -165,7 +166,7 @@ def rasterize_sequence(dtick, pitch, vel, resolution, slices_per_quarter, n_slic
     clock = 0
     for d, p, v, s in zip(dtick, pitch, vel, ev_slice):
         clock += played_delta(d)
-        p = int(p)
+        p, v = int(p) & 0x7F, int(v) & 0x7F
         if s >= total:
             break                      # events are time-ordered: everything after is dropped too
         if v > 0:

@@ -31,7 +31,7 @@ static void one_sequence(const int32_t* dtick, const uint8_t* pitch, const uint8
   int count = 0, open = 1;
   for (int e = 0; e < n_ev; ++e) {
     long long delta = dtick[e];
-    const int p = pitch[e], v = vel[e];
+    const int p = pitch[e] & 0x7F, v = vel[e] & 0x7F;   /* 7-bit MIDI data bytes */
     long long played = 0;
     while (delta > 0) {                                   /* midi_io.py:81-83 */
       const int bin = (int)((delta % MAX_TICKS) / TICKS_PER_BIN);

@@ -126,3 +126,26 @@ def test_whole_tracks_as_windows(velocity_roll):
         want = want.reshape(-1, S, 128)
         assert nwin[i] == want.shape[0], (i, nwin[i], want.shape)
         assert np.array_equal(roll[i, :nwin[i]], want), i
+
+
+def test_malformed_data_bytes_are_masked():
+    """Data bytes >= 0x80 (malformed MIDI: pitch 200, velocity 255) must not index past the 128-entry pitch table or
+    produce ids >= the vocabulary; kernel and oracle both treat them as 7-bit."""
+    rng = np.random.RandomState(11)
+    n_seq, ev = 300, 40
+    offs = (np.arange(n_seq + 1) * ev).astype(np.int32)
+    E = n_seq * ev
+    dtick = (rng.randint(0, 6, size=E) * 30).astype(np.int32)
+    pitch = rng.randint(0, 256, size=E).astype(np.uint8)
+    pitch[::7] = 200
+    vel = np.where(rng.rand(E) < 0.5, rng.randint(1, 256, size=E), 0).astype(np.uint8)
+    for vr in (False, True):
+        tok, roll, cnt = _run(dtick, pitch, vel, offs, velocity_roll=vr)
+        otok, oroll, ocnt = of.rasterize_batch(dtick, pitch, vel, offs, velocity_roll=vr)
+        assert tok.max() < 293 and tok.min() >= 0
+        assert np.array_equal(tok, otok) and np.array_equal(roll, oroll) and np.array_equal(cnt, ocnt)
+    # a clean launch afterwards proves no sticky fault / corrupted neighbour tile
+    d2, p2, v2, o2 = of.synth_note_events(n_seq=64, ev_per_seq=32, seed=1)
+    tok, roll, cnt = _run(d2, p2, v2, o2)
+    otok, oroll, ocnt = of.rasterize_batch(d2, p2, v2, o2)
+    assert np.array_equal(tok, otok) and np.array_equal(roll, oroll)
