@@ -392,6 +392,8 @@ def run_ours(args):
         kname = {"tf32": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)",
                  "bf16": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc_bf16: tcgen05 kind::f16 bf16 operands; kind::tf32 for the "
                          "decoder / latent GEMMs; cta_group::2 pair tiles, TMA)",
+                 "fp32x3": "gemm_tc2x3_kernel (msx_gemm_tc_x3: tcgen05 kind::tf32 with in-kernel hi/lo operand splitting, three "
+                           "MMAs per k-block, cta_group::2 pair tiles, TMA)",
                  "fp32": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)"}[args.precision]
         # fp32-in / fp32-out GEMMs with K, N <= 1024: 64-102 flop per algorithmic byte, below the TF32 ridge point
         # (~700 TFLOP/s / 6.55 TB/s = 107 flop/B), so the bounding resource is HBM

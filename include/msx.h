@@ -101,6 +101,17 @@ int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B, int ldb, i
                    int K, int ab_bf16, int c_bf16, const float* bias, int relu, float drop_p, unsigned long long seed,
                    unsigned site, const void* aux, int ldaux, int aux_kind, float aux_scale, int accumulate, int splitk,
                    float* out_colsum, uint32_t* mask_out, int ldmask, void* stream);
+/* Strict-fp32 tensor-core GEMM (the reference step is fp32 end to end, trainer.py:155-179): same contract and epilogues as
+ * msx_gemm_tc_ex with fp32 operands, but every operand value is split into hi + lo TF32 parts inside the kernel and a
+ * k-block contributes A_lo B_hi + A_hi B_lo + A_hi B_hi ("3xTF32"), fp32 accumulation in TMEM: products carry ~2^-21
+ * relative error instead of 2^-11.  cta_group::2 pair tiles only: M > 128 and N >= 64 (msx_gemm_tc_x3_supported; the call
+ * returns MSX_ERR_UNSUPPORTED otherwise and the caller uses msx_gemm_f32).  aux_kind 0 (fp32 matrix) or 2 (bit mask). */
+int msx_gemm_tc_x3_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
+                             int K);
+int msx_gemm_tc_x3(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
+                   int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
+                   const void* aux, int ldaux, int aux_kind, float aux_scale, int accumulate, int splitk,
+                   float* out_colsum, uint32_t* mask_out, int ldmask, void* stream);
 /* dst[i] = bfloat16(src[i]) (round to nearest even), i < n: builds bf16 operands from fp32 tensors (weights shadow,
  * tests).  src and dst 16-byte aligned. */
 int msx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);

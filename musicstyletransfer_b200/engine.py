@@ -181,10 +181,14 @@ class VAEEngine:
         (activations, their gradients and a shadow copy of the weights) stored as bfloat16 in HBM and multiplied by
         tcgen05 kind::f16 (msx_gemm_tc_bf16), fp32 accumulation.  Softmax, LayerNorm, residuals, losses, the LSTM
         recurrence, master weights, gradients and Adam are fp32 in every mode."""
-        assert precision in ("fp32", "tf32", "bf16")
+        assert precision in ("fp32", "fp32x3", "tf32", "bf16")
         self.precision = precision
         self.tensor = precision in ("tf32", "bf16")      # tcgen05 / mma.sync kernels (vs the exact FFMA ones)
         self.bf16 = precision == "bf16"
+        # "fp32x3": strict fp32 on the tensor cores — GEMMs through msx_gemm_tc_x3 (3xTF32 operand splitting, fp32-equivalent
+        # products), attention and the LSTM recurrence on the exact FFMA kernels; shapes the pair tiles do not cover fall
+        # back to msx_gemm_f32
+        self.x3 = precision == "fp32x3"
         self.cfg = cfg
         self.device = torch.device(device)
         self.arena = ParamArena(cfg, self.device)
@@ -234,7 +238,8 @@ class VAEEngine:
         if self._use_tc(x, ldx, w, K, out, ldo, M, N, K):
             use_mask = mask_out is not None and N % 32 == 0
             ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
-                        site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32)
+                        site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32,
+                        x3=self.x3)
             return use_mask
         ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
                  site=site, accumulate=accumulate)
@@ -245,6 +250,9 @@ class VAEEngine:
         return self.tensor and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
 
     def _use_tc(self, A, lda, B, ldb, C, ldc, M, N, K):
+        """True when the GEMM runs on tcgen05: single-pass TF32 in the tensor modes, 3xTF32 in the fp32x3 mode."""
+        if self.x3:
+            return ops.gemm_tc_x3_supported(A, lda, B, ldb, C, ldc, M, N, K)
         return self.tensor and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
@@ -254,7 +262,7 @@ class VAEEngine:
         pre-activation gradient dx is; returns True when the dgrad epilogue accumulated it (tensor path)."""
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
         if self._use_tc(dy, lddy, x, ldx, gw, K, N, K, M):
-            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk)
+            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=self.x3)
             if gb is not None:
                 ops.colsum(dy, lddy, M, N, gb)
         else:
@@ -264,7 +272,7 @@ class VAEEngine:
             if self._use_tc(dy, lddy, w, K, dx, lddx, M, K, N):
                 fused = dx_colsum is not None and not accumulate_dx
                 ops.gemm_tc(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
-                            accumulate=accumulate_dx, out_colsum=dx_colsum if fused else None)
+                            accumulate=accumulate_dx, out_colsum=dx_colsum if fused else None, x3=self.x3)
             else:
                 ops.gemm(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
                          accumulate=accumulate_dx)

@@ -60,10 +60,27 @@ def _gemm_tc_ex(ab16, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, re
                  (" aux%d" % ak) if aux is not None else "", " c16" if c16 else "", " mask" if mask_out is not None else "")))
 
 
+def gemm_tc_x3_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
+    return bool(lib.load().msx_gemm_tc_x3_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
+
+
 def gemm_tc(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
-            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None, mask_out=None, ldmask=0):
+            aux=None, ldaux=0, aux_scale=1.0, accumulate=False, splitk=1, out_colsum=None, mask_out=None, ldmask=0, x3=False):
     """Same contract as gemm() on the tcgen05 tensor cores (TF32 operands, fp32 accumulate).  aux: fp32 matrix or an int32
-    ReLU bit mask (ldaux in words); mask_out: optional int32 [M, ldmask] bit mask of (C > 0), N % 32 == 0."""
+    ReLU bit mask (ldaux in words); mask_out: optional int32 [M, ldmask] bit mask of (C > 0), N % 32 == 0.
+    x3: 3xTF32 operand splitting (msx_gemm_tc_x3): fp32-equivalent products at three MMAs per k-block."""
+    if x3:
+        ak = _aux_kind(aux)
+        aux_bytes = 0 if aux is None else (M * N / 8.0 if ak == 2 else M * N * 4)
+        nbytes = 4.0 * (M * K + N * K) + M * N * 4.0 * (1 + (1 if accumulate else 0)) + aux_bytes + \
+            (M * N / 8.0 if mask_out is not None else 0)
+        lib.call("msx_gemm_tc_x3", P(A), _i(lda), _i(transA), P(B), _i(ldb), _i(transB), P(Cm), _i(ldc), _i(M), _i(N), _i(K),
+                 P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), P(aux), _i(ldaux), _i(ak), _f(aux_scale),
+                 _i(1 if accumulate else 0), _i(splitk), P(out_colsum), P(mask_out), _i(ldmask), lib.stream_ptr(),
+                 tag=(2.0 * M * N * K, nbytes, "tf32x3 M=%d N=%d K=%d tA=%d tB=%d sk=%d%s%s%s" % (
+                     M, N, K, transA, transB, splitk, " acc" if accumulate else "", (" aux%d" % ak) if aux is not None else "",
+                     " mask" if mask_out is not None else "")))
+        return
     _gemm_tc_ex(False, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
                 aux_scale, accumulate, splitk, out_colsum, mask_out, ldmask)
 
