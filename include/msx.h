@@ -171,6 +171,12 @@ int msx_add_ln_bwd_ex(const float* x, const void* y, int y_bf16, const float* ga
                       long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres,
                       int fuse_xy, void* stream);   /* y_bf16: the Dense output y is bfloat16 (read only by this LayerNorm) */
 
+/* Strided row copy (add = 0) / accumulate (add = 1): out[r, :width] (+)= in[r, :width], row r of X at X + r * ldX.  The
+ * encoder output is only read at the SOS position (model.py:97-100), so the top encoder layer runs on one row per sequence
+ * after its attention; this moves those rows between the [B*T, D] and [B, D] layouts.  width, ld % 4 == 0. */
+int msx_rows_strided(const float* in, long long ld_in, float* out, long long ld_out, int rows, int width, int add,
+                     void* stream);
+
 /* K2a — embedding front end.  Replaces model.py:81-91 + transformer.py:270 (encoder), model.py:241-247 +
  * transformer.py:237 (Transformer decoder, prefix = 1 latent-state row), model.py:176 (LSTM decoder).
  * out[b,pos,:] = scale*((pos<prefix ? prefix_vec[b] : tok_emb[tokens[b,pos-prefix]]) + cls_emb[classes[b]]) + pe[pos];

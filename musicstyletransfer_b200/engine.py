@@ -18,6 +18,23 @@ NUM_EVENTS = 293     # MIDIUtil/defaults.py:58
 SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 1: ff hidden, 2: ff out}
 
 
+# precision mode -> (single-pass tensor GEMMs, 3xTF32 forward GEMMs, 3xTF32 backward GEMMs, tensor-core attention,
+#                    tensor-core LSTM recurrence).  Storage is fp32 in every mode except the bf16 operand copies of "bf16".
+#   fp32      every product exact fp32 on FFMA kernels (reference arithmetic, the slowest)
+#   fp32x3    strict fp32 on the tensor cores: all GEMMs 3xTF32, attention / LSTM exact -> every gradient within 1e-3
+#   tf32x3f   fp32-equivalent FORWARD GEMMs (3xTF32) -> loss / KL / latent means within the north star's 1e-3 with margin;
+#             backward GEMMs, attention and the LSTM recurrence single-pass TF32 (gradients to TF32 accuracy)
+#   tf32      every tensor-core product single-pass TF32
+#   bf16      tf32 with the Transformer layers' GEMM operands stored as bfloat16
+PRECISIONS = {
+    "fp32": (False, False, False, False, False),
+    "fp32x3": (False, True, True, False, False),
+    "tf32x3f": (True, True, False, True, True),
+    "tf32": (True, False, False, True, True),
+    "bf16": (True, False, False, True, True),
+}
+
+
 class VAEConfig:
     """Flat mirror of ModelConfig (model.py:11-54) + TransformerConfig (transformer.py:8-21) + LSTMConfig."""
 
@@ -173,22 +190,36 @@ class _Buffers:
             self.t[key] = buf
         return buf
 
+    def get_zero(self, name, shape, device, dtype=torch.float32):
+        """A buffer that is zero-filled ONCE, when it is created: for gradients of which a step only ever writes the same
+        few rows (the SOS rows), so the remaining rows stay zero without a per-step memset."""
+        key = (name, tuple(shape), dtype)
+        buf = self.t.get(key)
+        if buf is None:
+            buf = torch.zeros(shape, dtype=dtype, device=device)
+            self.t[key] = buf
+        return buf
+
 
 class VAEEngine:
-    def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024, precision="fp32"):
+    def __init__(self, cfg, device="cuda:0", seed=0, max_len=1024, precision="fp32", sos_rows_only=True):
         """precision: "fp32" = exact FFMA GEMMs (msx_gemm_f32); "tf32" = tcgen05 tensor-core GEMMs with TF32
         operands and fp32 accumulation (msx_gemm_tc); "bf16" = the tf32 path with the Transformer layers' GEMM operands
         (activations, their gradients and a shadow copy of the weights) stored as bfloat16 in HBM and multiplied by
         tcgen05 kind::f16 (msx_gemm_tc_bf16), fp32 accumulation.  Softmax, LayerNorm, residuals, losses, the LSTM
         recurrence, master weights, gradients and Adam are fp32 in every mode."""
-        assert precision in ("fp32", "fp32x3", "tf32", "bf16")
+        assert precision in PRECISIONS, precision
         self.precision = precision
-        self.tensor = precision in ("tf32", "bf16")      # tcgen05 / mma.sync kernels (vs the exact FFMA ones)
         self.bf16 = precision == "bf16"
-        # "fp32x3": strict fp32 on the tensor cores — GEMMs through msx_gemm_tc_x3 (3xTF32 operand splitting, fp32-equivalent
-        # products), attention and the LSTM recurrence on the exact FFMA kernels; shapes the pair tiles do not cover fall
-        # back to msx_gemm_f32
-        self.x3 = precision == "fp32x3"
+        # What each mode runs (PRECISIONS): single-pass TF32 / bf16 GEMMs (`tensor`), 3xTF32 GEMMs in the forward and / or
+        # backward pass (`x3_fwd`, `x3_bwd`: msx_gemm_tc_x3, fp32-equivalent products; shapes the pair tiles do not cover
+        # fall back to msx_gemm_f32), tensor-core attention / LSTM recurrence (`attn_tc`, `lstm_tc`) or the exact FFMA ones.
+        self.tensor, self.x3_fwd, self.x3_bwd, self.attn_tc, self.lstm_tc = PRECISIONS[precision]
+        # The encoder output is read at position 0 only (model.py:97-100), so in the top encoder layer everything after the
+        # attention is computed for the B SOS rows instead of all B*T rows: same losses, same gradients (the other rows'
+        # outputs have no consumer and their gradients are exactly zero), ~30 % less GEMM / LayerNorm work per step.
+        # sos_rows_only=False computes every position as the reference does (tests compare the two).
+        self.sos_rows_only = bool(sos_rows_only)
         self.cfg = cfg
         self.device = torch.device(device)
         self.arena = ParamArena(cfg, self.device)
@@ -235,25 +266,30 @@ class VAEEngine:
         dgrad of the next layer applies; returns True when it was written."""
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
-        if self._use_tc(x, ldx, w, K, out, ldo, M, N, K):
+        mode = self._gemm_mode(self.x3_fwd, x, ldx, w, K, out, ldo, M, N, K)
+        if mode:
             use_mask = mask_out is not None and N % 32 == 0
             ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
                         site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32,
-                        x3=self.x3)
+                        x3=mode == "x3")
             return use_mask
         ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
                  site=site, accumulate=accumulate)
         return False
 
     def _lstm_tc(self, Hd, tv):
-        """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers) in the tf32 precision mode, H = 128."""
-        return self.tensor and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
+        """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers), H = 128."""
+        return self.lstm_tc and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
 
-    def _use_tc(self, A, lda, B, ldb, C, ldc, M, N, K):
-        """True when the GEMM runs on tcgen05: single-pass TF32 in the tensor modes, 3xTF32 in the fp32x3 mode."""
-        if self.x3:
-            return ops.gemm_tc_x3_supported(A, lda, B, ldb, C, ldc, M, N, K)
-        return self.tensor and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K)
+    def _gemm_mode(self, want_x3, A, lda, B, ldb, C, ldc, M, N, K):
+        """"x3" (3xTF32 on tcgen05), "tc" (single-pass TF32 on tcgen05) or None (exact FFMA kernel) for one GEMM."""
+        if want_x3:
+            if ops.gemm_tc_x3_supported(A, lda, B, ldb, C, ldc, M, N, K):
+                return "x3"
+            return None                         # small shapes of a 3xTF32 pass stay exact
+        if self.tensor and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K):
+            return "tc"
+        return None
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
                    accumulate_dx=False, dx_colsum=None):
@@ -261,25 +297,32 @@ class VAEEngine:
         dx [M,K] (=|+=) dy w (optionally masked by aux).  dx_colsum: bias-gradient buffer of the layer whose
         pre-activation gradient dx is; returns True when the dgrad epilogue accumulated it (tensor path)."""
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
-        if self._use_tc(dy, lddy, x, ldx, gw, K, N, K, M):
-            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=self.x3)
+        mode = self._gemm_mode(self.x3_bwd, dy, lddy, x, ldx, gw, K, N, K, M)
+        if mode:
+            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=mode == "x3")
             if gb is not None:
                 ops.colsum(dy, lddy, M, N, gb)
         else:
             ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, colsum=gb)
         fused = False
         if dx is not None:
-            if self._use_tc(dy, lddy, w, K, dx, lddx, M, K, N):
+            mode = self._gemm_mode(self.x3_bwd, dy, lddy, w, K, dx, lddx, M, K, N)
+            if mode:
                 fused = dx_colsum is not None and not accumulate_dx
                 ops.gemm_tc(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
-                            accumulate=accumulate_dx, out_colsum=dx_colsum if fused else None, x3=self.x3)
+                            accumulate=accumulate_dx, out_colsum=dx_colsum if fused else None, x3=mode == "x3")
             else:
                 ops.gemm(dy, lddy, 0, w, K, 0, dx, lddx, M, K, N, aux=aux, ldaux=ldaux, aux_scale=aux_scale,
                          accumulate=accumulate_dx)
         return fused
 
     # ------------------------------------------------------------------ transformer layer
-    def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder):
+    def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder, sos_only=False):
+        """One post-LN Transformer layer (transformer.py:151-159 / :192-201).  sos_only: the caller reads the layer's output
+        at position 0 of every sequence only (the encoder's top layer: model.py:97-100 takes `out[:, 0, :]`), so everything
+        after the attention — projection, LayerNorms, feed-forward — runs on those B rows instead of B*T; attention itself
+        still sees every position (keys / values of all rows, and the reference's softmax normalises over the queries).
+        Returns [B*T, D], or [B, D] when sos_only."""
         M = B * T
         dev = self.device
         a = self.arena
@@ -288,96 +331,110 @@ class VAEEngine:
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
         ctx = bf.get(tag + "ctx", (M, D), dev)
-        if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
+        if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H)
-        elif self.tensor and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
+        elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
             ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
-        proj = bf.get(tag + "proj", (M, D), dev)
-        self._dense_fwd(ctx, D, M, prefix + "self_attention.W_proj.weight", prefix + "self_attention.W_proj.bias",
+        if sos_only:
+            R, ldr = B, T * D                   # rows b*T of ctx / x_in: read in place through the leading dimension
+            xres = bf.get(tag + "xin_c", (B, D), dev)
+            ops.rows_strided(x_in, T * D, xres, D, B, D)
+        else:
+            R, ldr, xres = M, D, x_in
+        proj = bf.get(tag + "proj", (R, D), dev)
+        self._dense_fwd(ctx, ldr, R, prefix + "self_attention.W_proj.weight", prefix + "self_attention.W_proj.bias",
                         proj, D, D, D)
-        x1 = bf.get(tag + "x1", (M, D), dev)
-        st1 = bf.get(tag + "st1", (2, M), dev)
-        ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
+        x1 = bf.get(tag + "x1", (R, D), dev)
+        st1 = bf.get(tag + "st1", (2, R), dev)
+        ops.add_ln_fwd(xres, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], R, D,
                        drop_p=p, seed=self.dropout_seed, site=site0)
-        h = bf.get(tag + "h", (M, 4 * D), dev)
-        hmask = bf.get(tag + "hmask", (M, (4 * D + 31) // 32), dev, torch.int32)
-        self._hmask_ok[tag] = self._dense_fwd(x1, D, M, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", h, 4 * D, 4 * D, D,
+        h = bf.get(tag + "h", (R, 4 * D), dev)
+        hmask = bf.get(tag + "hmask", (R, (4 * D + 31) // 32), dev, torch.int32)
+        self._hmask_ok[tag] = self._dense_fwd(x1, D, R, prefix + "ff.ff1.weight", prefix + "ff.ff1.bias", h, 4 * D, 4 * D, D,
                                               relu=True, drop_p=p, site=site0 + 1, mask_out=hmask)
-        f = bf.get(tag + "f", (M, D), dev)
-        self._dense_fwd(h, 4 * D, M, prefix + "ff.ff2.weight", prefix + "ff.ff2.bias", f, D, D, 4 * D)
-        out = bf.get(tag + "out", (M, D), dev)
-        st2 = bf.get(tag + "st2", (2, M), dev)
+        f = bf.get(tag + "f", (R, D), dev)
+        self._dense_fwd(h, 4 * D, R, prefix + "ff.ff2.weight", prefix + "ff.ff2.bias", f, D, D, 4 * D)
+        out = bf.get(tag + "out", (R, D), dev)
+        st2 = bf.get(tag + "st2", (2, R), dev)
         ln2 = "ln3" if decoder else "ln2"
         # encoder: ln2(x1 + drop(f)) (transformer.py:158); decoder: ln3(f + drop(f)) (transformer.py:200)
         ops.add_ln_fwd(f if decoder else x1, f, self._W(prefix + ln2 + ".gamma"), self._W(prefix + ln2 + ".beta"), out,
-                       st2[0], st2[1], M, D, drop_p=p, seed=self.dropout_seed, site=site0 + 2)
+                       st2[0], st2[1], R, D, drop_p=p, seed=self.dropout_seed, site=site0 + 2)
         return out
 
-    def _tf_layer_bwd(self, bf, tag, prefix, x_in, mask, dout, dx_in, B, T, D, H, p, site0, decoder):
-        """dout [M,D] = grad wrt the layer output (overwritten as scratch); writes grad wrt x_in into dx_in."""
+    def _tf_layer_bwd(self, bf, tag, prefix, x_in, mask, dout, dx_in, B, T, D, H, p, site0, decoder, sos_only=False):
+        """dout = grad wrt the layer output ([B*T, D]; [B, D] when sos_only); writes grad wrt x_in into dx_in [B*T, D]."""
         M = B * T
+        R = B if sos_only else M
+        ldr = T * D if sos_only else D
         dev = self.device
         a = self.arena
-        qkv, ctx, proj = bf.t[(tag + "qkv", (M, 3 * D), torch.float32)], bf.t[(tag + "ctx", (M, D), torch.float32)], \
-            bf.t[(tag + "proj", (M, D), torch.float32)]
-        x1, st1 = bf.t[(tag + "x1", (M, D), torch.float32)], bf.t[(tag + "st1", (2, M), torch.float32)]
-        h, f = bf.t[(tag + "h", (M, 4 * D), torch.float32)], bf.t[(tag + "f", (M, D), torch.float32)]
-        st2 = bf.t[(tag + "st2", (2, M), torch.float32)]
+        f32 = torch.float32
+        qkv, ctx, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "ctx", (M, D), f32)], bf.t[(tag + "proj", (R, D), f32)]
+        x1, st1 = bf.t[(tag + "x1", (R, D), f32)], bf.t[(tag + "st1", (2, R), f32)]
+        h, f = bf.t[(tag + "h", (R, 4 * D), f32)], bf.t[(tag + "f", (R, D), f32)]
+        st2 = bf.t[(tag + "st2", (2, R), f32)]
+        xres = bf.t[(tag + "xin_c", (B, D), f32)] if sos_only else x_in
         inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
         ln2 = "ln3" if decoder else "ln2"
-        dx1 = bf.get(tag + "dx1", (M, D), dev)
-        df = bf.get(tag + "df", (M, D), dev)
+        dx1 = bf.get(tag + "dx1", (R, D), dev)
+        df = bf.get(tag + "df", (R, D), dev)
         if decoder:
             ops.add_ln_bwd(f, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, df, None,
-                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), R, D, drop_p=p,
                            seed=self.dropout_seed, site=site0 + 2, fuse_xy=True, dybias=self._G(prefix + "ff.ff2.bias"))
         else:
             ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, df if p > 0 else None,
-                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), R, D, drop_p=p,
                            seed=self.dropout_seed, site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"))
             if p <= 0:
                 df = dx1
         # ff2: f = h W2^T + b2
-        dh = bf.get(tag + "dh", (M, 4 * D), dev)
+        dh = bf.get(tag + "dh", (R, 4 * D), dev)
         # ReLU / dropout mask of the hidden activation: the bit mask the FF1 forward epilogue wrote (4 B per 32 elements)
         # when it ran on the tensor path, else the activation itself
         if self._hmask_ok.get(tag):
-            aux, ldaux = bf.t[(tag + "hmask", (M, (4 * D + 31) // 32), torch.int32)], 4 * D // 32
+            aux, ldaux = bf.t[(tag + "hmask", (R, (4 * D + 31) // 32), torch.int32)], 4 * D // 32
         else:
             aux, ldaux = h, 4 * D
-        fused = self._dense_bwd(df, D, M, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
+        fused = self._dense_bwd(df, D, R, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
                                 None, D, 4 * D, dx=dh, lddx=4 * D, aux=aux, ldaux=ldaux, aux_scale=inv_keep,
                                 dx_colsum=self._G(prefix + "ff.ff1.bias"))
         # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
-        self._dense_bwd(dh, 4 * D, M, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
+        self._dense_bwd(dh, 4 * D, R, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
                         None if fused else self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D,
                         accumulate_dx=not decoder)
-        # ln1(x_in + drop(proj))
-        dproj = bf.get(tag + "dproj", (M, D), dev)
-        ops.add_ln_bwd(x_in, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dx_in, dproj if p > 0 else None,
-                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), M, D, drop_p=p,
+        # ln1(x_in + drop(proj)); sos_only: the residual gradient of the B rows is kept aside and added to dx_in at the end
+        dres = bf.get(tag + "dxin_c", (B, D), dev) if sos_only else dx_in
+        dproj = bf.get(tag + "dproj", (R, D), dev)
+        ops.add_ln_bwd(xres, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dres, dproj if p > 0 else None,
+                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), R, D, drop_p=p,
                        seed=self.dropout_seed, site=site0, dybias=self._G(prefix + "self_attention.W_proj.bias"))
         if p <= 0:
-            dproj = dx_in
-        dctx = bf.get(tag + "dctx", (M, D), dev)
-        self._dense_bwd(dproj, D, M, ctx, D, self._W(prefix + "self_attention.W_proj.weight"),
-                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=D)
+            dproj = dres
+        # sos_only: the context gradient is non-zero at rows b*T only; the dgrad writes exactly those rows of a buffer that
+        # was zero-filled when it was created and is written by nothing else
+        dctx = bf.get_zero(tag + "dctx_sos", (M, D), dev) if sos_only else bf.get(tag + "dctx", (M, D), dev)
+        self._dense_bwd(dproj, D, R, ctx, ldr, self._W(prefix + "self_attention.W_proj.weight"),
+                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=ldr)
         dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
-        if self.tensor and ops.attention_tc_supported(qkv, T, D // H):
+        if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv)
             gbqkv = None
-        elif self.tensor and ops.attention_tcl_supported(qkv, T, D // H):
+        elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), torch.float32)], dqkv, B, T, H,
                                   D // H, dbias=gbqkv)
             gbqkv = None
         else:
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
-        self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=True)
+        self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=not sos_only)
+        if sos_only:
+            ops.rows_strided(dres, D, dx_in, T * D, B, D, add=True)
 
     # ------------------------------------------------------------------ transformer layer, bf16 variant
     def _layer16_ok(self, D):
@@ -520,11 +577,17 @@ class VAEEngine:
                 self._xs16.append(x16)
             else:
                 x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
-                                       p_drop, l * SITE_STRIDE, False)
+                                       p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
             xs.append(x)
         lat = bf.get("lat", (B, 2 * Z), dev)
-        self._dense_fwd(x, T * D, B, "encoder.latent_proj.weight", "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
+        # latent projection on the SOS position (model.py:97-100): row b of the compact top-layer output, else row b*T
+        self._dense_fwd(x, D if self._sos_only(cfg.enc_layers - 1) else T * D, B, "encoder.latent_proj.weight",
+                        "encoder.latent_proj.bias", lat, 2 * Z, 2 * Z, D)
         return xs, mask, lat
+
+    def _sos_only(self, l):
+        """Encoder layer l is the top layer and runs its row-wise part on the SOS rows only (see _tf_layer_fwd)."""
+        return self.sos_rows_only and l == self.cfg.enc_layers - 1 and not self._layer16_ok(self.cfg.enc_size)
 
     def decoder_initial_state(self, classes, z):
         """latent2hid(z) + class2hid[classes] (model.py:160 / :231): [B, 2H] for the LSTM decoder, [B, D_d] else."""
@@ -587,7 +650,7 @@ class VAEEngine:
             for i in range(1, I_max):
                 ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, B, 1, 4 * Hd, 0, 1.0, V)
                 # one recurrence step; the tensor-core kernel (W_h2h as mma fragments in registers) in the tensor modes
-                step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
+                step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
                 step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
                      hb[i & 1], hp, cb[i & 1], B, 1, Hd)                                      # model.py:195
                 h, c, ld0 = hb[i & 1], cb[i & 1], Hd
@@ -705,7 +768,7 @@ class VAEEngine:
                         tab, 4 * Hd, 4 * Hd, Hd)
         for i in range(1, I_max):
             ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, R, 1, 4 * Hd, 0, 1.0, V)
-            step = ops.lstm_tc_fwd if (self.tensor and ops.lstm_tc_supported(Hd, Hd, h[cur], c[cur])) else ops.lstm_fwd
+            step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, Hd, h[cur], c[cur])) else ops.lstm_fwd
             step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
                  hn, hp, cn, R, 1, Hd)
             self._dense_fwd(hn, Hd, R, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V, Hd)
@@ -908,11 +971,16 @@ class VAEEngine:
         ops.reparam_kl_bwd(c["lat"], c["eps"], dz, g_kl, kl_weight, dlat, B, Z)
         # ---- latent projection on the SOS position (model.py:97-100): rows b*T of the last encoder output
         xs = c["xs"]
-        dx = bf.get("enc.dx_top", (M, D), dev)
-        dx.zero_()
-        self._dense_bwd(dlat, 2 * Z, B, xs[-1], T * D, self._W("encoder.latent_proj.weight"),
+        if self._sos_only(cfg.enc_layers - 1):
+            dx = bf.get("enc.dx_top_c", (B, D), dev)             # compact: one row per sequence
+            ldt = D
+        else:
+            # only rows b*T are ever written (by the dgrad below); the rest stays zero from the buffer's creation
+            dx = bf.get_zero("enc.dx_top", (M, D), dev)
+            ldt = T * D
+        self._dense_bwd(dlat, 2 * Z, B, xs[-1], ldt, self._W("encoder.latent_proj.weight"),
                         self._G("encoder.latent_proj.weight"), self._G("encoder.latent_proj.bias"), 2 * Z, D,
-                        dx=dx, lddx=T * D)
+                        dx=dx, lddx=ldt)
         for l in reversed(range(cfg.enc_layers)):
             dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
             if self._layer16_ok(D):
@@ -920,7 +988,7 @@ class VAEEngine:
                                      dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
             else:
                 self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
-                                   cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+                                   cfg.enc_heads, c["pe"], l * SITE_STRIDE, False, sos_only=self._sos_only(l))
             dx = dnext
         ops.embed_bwd(c["tokens"], c["classes"], dx, self._G("encoder.encoder_embedding.weight"),
                       self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)

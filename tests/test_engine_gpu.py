@@ -411,3 +411,36 @@ def test_fused_ce_backward_equals_two_pass(prec):
     assert float((ce0 - ce1).abs().max()) <= 1e-6 * float(ce0.abs().max())
     assert float((m0 - m1).abs().max()) <= 1e-5 * float(m0.abs().max())
     assert float((g0 - g1).abs().max()) <= 2e-5 * float(g0.abs().max())        # atomics: summation order only
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 2e-3), ("fp32x3", 2e-5)])
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_sos_rows_only_top_layer_equals_full_layer(prec, tol, dropout):
+    """The encoder output is read at position 0 only (model.py:97-100).  sos_rows_only=True runs the top encoder layer's
+    row-wise part (projection, LayerNorms, feed-forward) on the B SOS rows; sos_rows_only=False computes every position as
+    the reference does.  Losses, latent statistics and every parameter gradient must agree (dropout: only the losses'
+    distribution can be compared, the two layouts index their masks differently)."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    tokens, seq_lens, classes, labels, eps = _batch(48, 33, 293, 2, 256, seed=13, min_len=9)
+    args = [_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels)]
+    res = []
+    for sos in (False, True):
+        eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=dropout, dec_dropout=dropout), "cuda:0", seed=2, precision=prec,
+                        sos_rows_only=sos)
+        out = eng.forward(*args, eps=_dev(eps, torch.float32), train=True)
+        res.append({k: out[k].clone() for k in ("ce", "kl", "means", "stds")})
+        eng.backward()
+        torch.cuda.synchronize()
+        res[-1]["g"] = eng.arena.g.clone()
+        res[-1]["names"] = {n: eng.arena.grad(n).clone() for n in eng.arena.names()}
+    full, sos = res
+    if dropout > 0:
+        assert abs(float(full["ce"].mean()) - float(sos["ce"].mean())) < 0.05 * float(full["ce"].mean())
+        return
+    for k in ("ce", "kl", "means", "stds"):
+        assert float((full[k] - sos[k]).abs().max()) <= tol * float(full[k].abs().max()), k
+    gmax = float(full["g"].abs().max())
+    for n in full["names"]:
+        scale = float(full["names"][n].abs().max())
+        err = float((full["names"][n] - sos["names"][n]).abs().max())
+        assert err <= tol * scale + 1e-5 * gmax, (n, err, scale)
