@@ -43,9 +43,10 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
     ap.add_argument("--dropout", type=float, default=0.2)
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32", "bf16"],
-                    help="GEMM path: fp32 = exact FFMA, tf32 = tcgen05 tensor cores (fp32 storage and accumulation), bf16 = "
-                         "the tf32 path with the Transformer layers' GEMM operands stored as bfloat16 (BASELINE config 4)")
+    ap.add_argument("--precision", default="tf32x3f", choices=["fp32", "fp32x3", "tf32x3f", "tf32", "bf16"],
+                    help="engine precision mode (musicstyletransfer_b200/engine.py PRECISIONS): tf32x3f (default) = fp32-equivalent "
+                         "forward (3xTF32 GEMMs, compensated attention scores), TF32 backward; tf32 = every product single-pass TF32; "
+                         "fp32x3 = strict fp32 on the tensor cores; fp32 = exact FFMA; bf16 = BASELINE config 4")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="rows per oracle step of the CPU arm (0 = the GPU arm's per-GPU batch, i.e. the same step)")
     ap.add_argument("--mode", default="train", choices=["train", "sweep", "style"],
@@ -76,7 +77,11 @@ PRECISION_NOTE = {
     "fp32": "fp32 storage, GEMMs fp32 FFMA",
     "fp32x3": "fp32 storage, GEMMs on tcgen05 with 3xTF32 operand splitting (hi/lo, three MMAs per k-block, fp32 accumulate): "
               "fp32-equivalent products; attention / LSTM on the exact FFMA kernels",
-    "tf32": "fp32 storage, GEMMs tcgen05 TF32 (fp32 accumulate)",
+    "tf32x3f": "fp32 storage; FORWARD GEMMs 3xTF32 on tcgen05 (fp32-equivalent products) and attention scores compensated the "
+               "same way -> loss / KL / latent means within 1e-3 of the fp32 oracle with 10x margin (measured 1.0e-4); BACKWARD "
+               "GEMMs, attention and the LSTM recurrence single-pass TF32 (fp32 accumulate)",
+    "tf32": "fp32 storage, every tensor-core product single-pass TF32 (fp32 accumulate); latent means deviate 1.3e-3 from the "
+            "fp32 oracle at the bench shape (over the 1e-3 bar, hence a variant and not the headline)",
     "bf16": "fp32 master weights / residual stream / LN / softmax / losses / Adam, Transformer-layer GEMM operands bf16 in HBM on "
             "tcgen05 kind::f16 (fp32 accumulate), other GEMMs TF32",
 }
@@ -361,7 +366,7 @@ def run_ours(args):
 
     # ---- dominant kernel (GEMM) roofline: CUDA events around every GEMM launch of a few extra steps.
     # Every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events.
-    roofline = None
+    roofline = roofline_other = None
     psteps = 3
     prof = {"match": "msx_gemm", "events": []}
     if rank == 0:
@@ -387,30 +392,51 @@ def run_ours(args):
             for k, t in sorted(tab.items(), key=lambda kv: -kv[1][1]):
                 print("gemm %-58s n/step=%4.1f %8.1f us  %7.1f TFLOP/s %7.1f GB/s" % (
                     k, t[0] / psteps, 1e3 * t[1] / t[0], t[2] / (t[1] * 1e-3) / 1e12, t[3] / (t[1] * 1e-3) / 1e9), file=sys.stderr)
-        tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9
-        kname = {"tf32": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)",
-                 "bf16": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc_bf16: tcgen05 kind::f16 bf16 operands; kind::tf32 for the "
-                         "decoder / latent GEMMs; cta_group::2 pair tiles, TMA)",
-                 "fp32x3": "gemm_tc2x3_kernel (msx_gemm_tc_x3: tcgen05 kind::tf32 with in-kernel hi/lo operand splitting, three "
-                           "MMAs per k-block, cta_group::2 pair tiles, TMA)",
-                 "fp32": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)"}[args.precision]
-        # fp32-in / fp32-out GEMMs with K, N <= 1024: 64-102 flop per algorithmic byte, below the TF32 ridge point
-        # (~700 TFLOP/s / 6.55 TB/s = 107 flop/B), so the bounding resource is HBM
-        traffic = None
-        tpath = os.path.join(REPO, "profiles", "traffic_gemm_bf16.json" if args.precision == "bf16" else "traffic_gemm.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": kname,
-                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                    "traffic": traffic, "peak_source": peaks["src"] + " HBM copy bandwidth",
-                    "algorithmic_bytes_per_launch": gemm_bytes / n_launch,
-                    "share_of_step": gemm_ms / step_ms, "launches_per_step": len(prof["events"]) / psteps,
-                    "avg_launch_ms": gemm_ms / n_launch,
-                    "tensor": {"achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
-                               "peak_source": peaks["src"] + " bf16 sustained (cuBLAS); TF32 nominal peak is half of bf16",
-                               "flops_per_step": gemm_flops / psteps}}
+        # Two GEMM kernels share a step in the mixed modes: the single-pass one (HBM-bound: fp32-in / fp32-out GEMMs with
+        # K, N <= 1024 carry 64-102 flop per algorithmic byte, below the TF32 ridge point ~700 TFLOP/s / 6.55 TB/s = 107) and
+        # the 3xTF32 one (tensor-bound: it executes 3 MMAs per algorithmic multiply-add).  `roofline` describes the group
+        # with the larger share of the step, `roofline_other` the other one.
+        KN = {"tf32": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc: tcgen05 kind::tf32, cta_group::2 pair tiles, TMA)",
+              "bf16": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc_bf16: tcgen05 kind::f16, bf16 operands, cta_group::2 pair tiles, TMA)",
+              "tf32x3": "gemm_tc2x3_kernel (msx_gemm_tc_x3: tcgen05 kind::tf32 with in-kernel hi/lo operand splitting, three "
+                        "MMAs per k-block, cta_group::2 pair tiles, TMA)",
+              "ffma": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)", "f32": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)"}
+        groups = {}
+        for a_, b_, f_ in prof["events"]:
+            kind = (f_[2].split(" ")[0] if len(f_) > 2 else "?")
+            gsum = groups.setdefault(kind, [0, 0.0, 0.0, 0.0])
+            gsum[0] += 1; gsum[1] += a_.elapsed_time(b_); gsum[2] += f_[0]; gsum[3] += f_[1]
+        tf32_peak = peaks["tflops"] / 2.0
+        rl = []
+        for kind, (cnt, tms, fl, by) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+            tfk = fl / (tms * 1e-3) / 1e12
+            gbk = by / (tms * 1e-3) / 1e9
+            common = {"kernel": KN.get(kind, kind), "share_of_step": tms / step_ms, "launches_per_step": cnt / psteps,
+                      "avg_launch_ms": tms / cnt, "algorithmic_bytes_per_launch": by / cnt, "algorithmic_flops_per_launch": fl / cnt,
+                      "measured": "CUDA events around every launch of %d eager steps (the graph-replayed step is what `value` times)" % psteps}
+            if kind == "tf32x3":
+                rl.append(dict(common, bound="tensor", achieved=tfk, peak=tf32_peak, unit="TFLOP/s", frac=tfk / tf32_peak,
+                               executed_tflops=3 * tfk, executed_frac=3 * tfk / tf32_peak, traffic=None,
+                               peak_source=peaks["src"] + " bf16 sustained (cuBLAS) / 2 = TF32 dense; `achieved` counts the "
+                               "algorithmic 2MNK, the kernel executes 3 MMAs per multiply-add (executed_*)",
+                               hbm={"achieved": gbk, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbk / peaks["hbm_gbs"]}))
+            else:
+                traffic = None
+                tpath = os.path.join(REPO, "profiles", "traffic_gemm_bf16.json" if kind == "bf16" else "traffic_gemm.json")
+                if kind in ("tf32", "bf16") and os.path.exists(tpath):
+                    with open(tpath) as f:
+                        traffic = json.load(f).get("dram_bytes_per_launch")
+                rl.append(dict(common, bound="hbm", achieved=gbk, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbk / peaks["hbm_gbs"],
+                               traffic=traffic, traffic_source="one ncu --set full capture of a round-1 step's GEMM launches "
+                               "(profiles/traffic_gemm*.json), per launch" if traffic else None,
+                               peak_source=peaks["src"] + " HBM copy bandwidth",
+                               tensor={"achieved": tfk, "peak": tf32_peak if kind != "bf16" else peaks["tflops"], "unit": "TFLOP/s",
+                                       "frac": tfk / (tf32_peak if kind != "bf16" else peaks["tflops"])}))
+        roofline = rl[0] if rl else None
+        roofline_other = rl[1:] or None
+        if roofline:
+            roofline["gemm_share_of_step"] = gemm_ms / step_ms
+            roofline["gemm_flops_per_step"] = gemm_flops / psteps
     if args.kernel_table and rank == 0 and world == 1:
         kp = {"match": "msx_", "events": [], "names": True}
         lib._profile = kp
@@ -477,7 +503,10 @@ def run_ours(args):
     # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
     bf16_variant = fp32_variant = b32 = None
     strong = []
-    if args.precision == "tf32" and not args.no_variants:
+    tf32_variant = None
+    if args.precision == "tf32x3f" and not args.no_variants:
+        tf32_variant = time_variant("tf32", B, gbatch, K, W)
+        tf32_variant.update({"dtype": "tf32", "what": PRECISION_NOTE["tf32"]})
         bf16_variant = time_variant("bf16", B, gbatch, K, W)
         bf16_variant.update({"dtype": "bf16", "what": PRECISION_NOTE["bf16"],
                              "parity": "vs fp32 oracle: loss 1e-4, KL 1e-3, latent means 1e-2, gradients 10 % worst tensor / "
@@ -485,17 +514,17 @@ def run_ours(args):
         # ---- strict-fp32 variant: the reference's own precision (trainer.py:155-179 is fp32 end to end)
         fp32_variant = time_variant("fp32x3", B, gbatch, max(5, K // 2), 3)
         fp32_variant.update({"dtype": "f32", "what": PRECISION_NOTE["fp32x3"],
-                             "parity": "every gradient within 1e-3 of its scale vs the fp32 oracle "
-                                       "(tests/test_engine_gpu.py::test_fp32x3_step_matches_oracle)"})
+                             "parity": "loss / KL / latent means 1e-5, every gradient within 1e-3 of its scale vs the fp32 oracle "
+                                       "(tests/test_parity_bench_gpu.py::test_bench_shape_gradients_vs_oracle[fp32x3])"})
         # ---- strong scaling: the global batch is fixed, each GPU takes 1/N of it
         for gb in (2048, 256):
             if gb % world == 0 and not (world == 1 and gb == B):
-                sv = time_variant("tf32", gb // world, gb, K, W, seed_off=7)
+                sv = time_variant(args.precision, gb // world, gb, K, W, seed_off=7)
                 sv["scaling"] = "strong"
                 strong.append(sv)
         # ---- the reference's own configuration of record (scripts/train-vae.sh: batch 32), one graph launch per step
         if world == 1:
-            b32 = time_variant("tf32", 32, 32, 200, 10, seed_off=11)
+            b32 = time_variant(args.precision, 32, 32, 200, 10, seed_off=11)
             b32["what"] = "scripts/train-vae.sh batch size (32 rows, L=64), CUDA-graph replay"
 
     if rank != 0:
@@ -517,13 +546,13 @@ def run_ours(args):
                "ms_per_step": per_step * 1e3}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32", "tf32x3f": "f32 forward (3xTF32) / tf32 backward", "tf32": "tf32", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
         "config": config_dict(args, world),
         "run": {"precision": PRECISION_NOTE[args.precision], "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange, "ranks_identical": ranks_identical,
                 "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                       (B * T * 4 * 40e3 / 1e9 / 10)},
-        "roofline": roofline, "rasteriser": raster, "cpu_baseline": cpu, "bf16_variant": bf16_variant,
+        "roofline": roofline, "roofline_other": roofline_other, "rasteriser": raster, "cpu_baseline": cpu, "tf32_variant": tf32_variant, "bf16_variant": bf16_variant,
         "fp32_variant": fp32_variant, "strong_scaling": strong or None, "b32": b32,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
@@ -603,7 +632,7 @@ def run_style(args):
     sec = (time.perf_counter() - t0) / reps
     line = {"metric": "style_transfer_sequences_per_sec", "value": B * cfg.num_classes / sec, "unit": "sequences/s",
             "tokens_per_s": B * ntok / sec, "ms_per_pass": sec * 1e3, "n_gpus": 1, "higher_is_better": True,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "style transfer: %d rows x %d classes, L=%d, decoder %s, up to 2T=%d sampled steps per class; "
                                    "wall clock including the host-side stop test" % (B, cfg.num_classes, L, args.dec_type, 2 * (L + 1))}}
     if not args.no_cpu_baseline:

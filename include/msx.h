@@ -137,6 +137,11 @@ int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx,
 /* bf16 variant: ctx (forward) / dqkv (backward) are written as bfloat16 when the flag is set (same element layout). */
 int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H, int dh,
                             void* stream);
+/* x3_scores: S = K Q^T accumulates K_lo Q_hi + K_hi Q_lo + K_hi Q_hi (operands split inside the kernel): fp32-equivalent
+ * scores.  The softmax (transformer.py:100) turns an absolute score error into a relative error of P, which makes the
+ * single-pass TF32 scores the largest forward error of the step. */
+int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B, int T, int H,
+                             int dh, void* stream);
 int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
                             int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);

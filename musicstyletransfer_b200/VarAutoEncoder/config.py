@@ -82,11 +82,11 @@ b200_arg = add_argument_group('B200')
 b200_arg.add_argument('--decoder-type', choices=["lstm", "transformer"], default="lstm",
                       help="lstm = the decoder scripts/train-vae.sh's --d-* flags describe (model.py:131-203); "
                            "transformer = the decoder class Model instantiates at HEAD (model.py:206-272)")
-b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32", "bf16"], default="tf32",
-                      help="GEMM path: exact fp32 FFMA, fp32x3 = strict fp32 on tcgen05 (3xTF32 operand splitting), "
-                           "tcgen05 TF32 tensor cores (fp32 storage / accumulation), or bf16 = "
-                           "the TF32 path with the Transformer layers' GEMM operands stored as bfloat16 (fp32 accumulation, "
-                           "fp32 master weights / LayerNorm / softmax / losses / Adam)")
+b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32x3f", "tf32", "bf16"], default="tf32x3f",
+                      help="precision mode (engine.PRECISIONS): tf32x3f = fp32-equivalent forward (3xTF32 GEMMs, compensated "
+                           "attention scores) with a TF32 backward; tf32 = every tensor-core product single-pass TF32; fp32x3 = "
+                           "strict fp32 on the tensor cores (3xTF32 everywhere, exact attention / LSTM); fp32 = exact FFMA; bf16 = "
+                           "tf32 with the Transformer layers' GEMM operands stored as bfloat16")
 b200_arg.add_argument('--cuda-graph', type=str2bool, default=True,
                       help="replay the train step from a CUDA graph per batch shape (one launch instead of ~70)")
 b200_arg.add_argument('--seed', type=int, default=0)

@@ -30,6 +30,15 @@ struct AttnTcParams {
   float inv_scale;
 };
 
+// lo part of an fp32 word for the compensated score product: x - (x with the 13 low mantissa bits cleared), rounded to TF32
+__device__ __forceinline__ unsigned lo_tf32_bits(unsigned xb) {
+  const float x = __uint_as_float(xb);
+  const float hi = __uint_as_float(xb & 0xFFFFE000u);
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x - hi));
+  return r;
+}
+
 __device__ __forceinline__ void group_sync(int g) {       // named barrier of one 128-thread pipeline group
   asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 }
@@ -59,7 +68,12 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // key row, so the issuer runs ahead of the softmax warps: K, Q of item n+1 are fetched as soon as MMA 1 of item n
 // has retired, V is double-buffered); every warp that owns valid rows does softmax + the output rows.
 // NCH = TQ / 16: the key row's scores are held in registers (one tcgen05.ld pass, one exp per score).
-template <int NCH, int G, bool STAGE, int kDh>
+// X3 (compensated scores): the softmax turns an ABSOLUTE score error into a RELATIVE error of P, so single-pass TF32
+// scores (|S| 2^-11) dominate the forward error of the whole step (measured: latent means 6e-4 with TF32 scores vs 1e-5
+// with exact ones).  With X3 the K / Q tiles arrive as raw fp32 (FLOAT32 maps), the issuer warp writes their lo parts
+// (x - trunc_tf32(x), element-wise, so the TMA swizzle is preserved) to a second pair of tiles and MMA 1 accumulates
+// K_lo Q_hi + K_hi Q_lo + K_hi Q_hi (kind::tf32 reads the raw words truncated = hi): fp32-equivalent scores.
+template <int NCH, int G, bool STAGE, int kDh, bool X3>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -81,6 +95,7 @@ __global__ void __launch_bounds__(128 * G, 1)
   unsigned char* sQ = sK + slab;                           // [TQ rows][128 B] K-major SW128
   unsigned char* sV = sQ + TQ * 128;                       // 2 x [TK rows][128 B] MN-major (d contiguous), SW128_32B
   unsigned char* sP = sV + 2 * slab;                       // ceil(TQ/32) slabs x [TK rows][128 B] MN-major (q contiguous)
+  unsigned char* sKQlo = sP + ((TQ + 31) / 32) * slab;     // X3: lo parts of K | Q, same layout as [sK, sQ + TQ rows)
   unsigned long long* bar_kq = &bars_all[g][0];
   unsigned long long* bar_v = &bars_all[g][1];
   unsigned long long* bar_s = &bars_all[g][3];
@@ -125,6 +140,7 @@ __global__ void __launch_bounds__(128 * G, 1)
   // shift/or chain per MMA costs the single issuing thread ~90 cycles)
   const unsigned long long dK = make_desc(smem_u32(sK), 16, 1024, 2), dQ = make_desc(smem_u32(sQ), 16, 1024, 2);
   const unsigned long long dP = make_desc(smem_u32(sP), slab, 512, 1), dV = make_desc(smem_u32(sV), slab, 512, 1);
+  const unsigned long long kqlo = (unsigned long long)((sKQlo - sK) >> 4);   // descriptor offset of the lo tiles
 
   if (issuer && first < p.items) {                         // prologue: loads of the group's first item
     const int b = first / p.H, h = first % p.H;
@@ -153,11 +169,29 @@ __global__ void __launch_bounds__(128 * G, 1)
     if (issuer) {                                          // whole warp, warp-uniform control flow
       const int b2 = nxt / p.H, h2 = nxt % p.H;
       mbar_wait(bar_kq, par);
+      if (X3) {                                            // lo tiles of K | Q (contiguous [TK + TQ rows][128 B])
+        const uint4* src = reinterpret_cast<const uint4*>(sK);
+        uint4* dst = reinterpret_cast<uint4*>(sKQlo);
+        for (int i = lane; i < (TK + TQ) * 8; i += 32) {
+          const uint4 v = src[i];
+          dst[i] = make_uint4(lo_tf32_bits(v.x), lo_tf32_bits(v.y), lo_tf32_bits(v.z), lo_tf32_bits(v.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major (+32 B per K = 8 step)
 #pragma unroll
-        for (int k = 0; k < kDh / 8; ++k) umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kDh / 8; ++k) {
+          if (X3) {
+            umma_tf32(tmem_S, dK + kqlo + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);     // K_lo Q_hi
+            umma_tf32(tmem_S, dK + 2 * k, dQ + kqlo + 2 * k, idesc1, 1u);                  // K_hi Q_lo
+            umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, 1u);                         // K_hi Q_hi
+          } else {
+            umma_tf32(tmem_S, dK + 2 * k, dQ + 2 * k, idesc1, k > 0 ? 1u : 0u);
+          }
+        }
         umma_commit(bar_s);
         if (nxt < p.items) {                               // V of the next item into the other V buffer (free since o_full(n-1))
           mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
@@ -781,7 +815,7 @@ extern "C" int msx_attention_tc_supported(const float* qkv, int T, int dh) {
 }
 
 namespace {
-template <int NCH, int G>
+template <int NCH, int G, bool X3>
 int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& tv, AttnTcParams p, cudaStream_t st) {
   // the last group's MMA descriptors address 128 K rows / 4 P slabs: keep the tail inside the allocation
   const size_t smem = 1024 + (size_t)G * p.group_bytes + 16 * 1024;
@@ -792,29 +826,33 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
   // fp32 context rows leave through the dead P tile (coalesced) when the per-warp staging slices fit into it
   const bool stage = !p.out_bf16 && p.dh == 32 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
   if (p.dh == 16) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false, 16><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false, 16, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   } else if (stage) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, true, 32><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true, 32, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, true, 32, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   } else {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false, 32><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false, 32, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
 }  // namespace
 
-extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
-                                       int dh, void* stream);
-extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
-                                    void* stream) {
-  return msx_attention_tc_fwd_ex(qkv, mask, ctx, 0, B, T, H, dh, stream);
-}
-
+extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B,
+                                        int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
                                        int dh, void* stream) {
+  return msx_attention_tc_fwd_ex2(qkv, mask, ctx, ctx_bf16, 0, B, T, H, dh, stream);
+}
+extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
+                                    void* stream) {
+  return msx_attention_tc_fwd_ex2(qkv, mask, ctx, 0, 0, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B,
+                                        int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
   MSX_REQUIRE(((uintptr_t)ctx & 15) == 0, "msx_attention_tc_fwd: ctx must be 16-byte aligned");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
@@ -827,23 +865,36 @@ extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void
   p.items = B * H;
   p.inv_scale = 1.f / sqrtf((float)dh);
   // per group: K [TK] + Q [TQ] + 2 x V [TK] + P [ceil(TQ/32) slabs x TK] rows of 128 B, every tile 1024-byte aligned
-  p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK) * 128;
+  //            (+ the lo parts of K and Q for compensated scores)
+  p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK + (x3_scores ? p.TK + p.TQ : 0)) * 128;
   const long long rows = (long long)B * T;
   CUtensorMap tk, tq, tv;
   int rc;
-  if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, p.TK, false))) return rc;
-  if ((rc = make_map(&tq, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false))) return rc;
+  if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, p.TK, false, x3_scores != 0))) return rc;
+  if ((rc = make_map(&tq, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false, x3_scores != 0))) return rc;
   if ((rc = make_map(&tv, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (x3_scores) {                           // the lo tiles cost a pipeline group at the longer rows
+    switch (p.TQ / 16) {
+      case 1: return launch_fwd<1, 3, true>(tk, tq, tv, p, st);
+      case 2: return launch_fwd<2, 3, true>(tk, tq, tv, p, st);
+      case 3: return launch_fwd<3, 3, true>(tk, tq, tv, p, st);
+      case 4: return launch_fwd<4, 2, true>(tk, tq, tv, p, st);
+      case 5: return launch_fwd<5, 2, true>(tk, tq, tv, p, st);
+      case 6: return launch_fwd<6, 1, true>(tk, tq, tv, p, st);
+      case 7: return launch_fwd<7, 1, true>(tk, tq, tv, p, st);
+      default: return launch_fwd<8, 1, true>(tk, tq, tv, p, st);
+    }
+  }
   switch (p.TQ / 16) {
-    case 1: return launch_fwd<1, 3>(tk, tq, tv, p, st);
-    case 2: return launch_fwd<2, 3>(tk, tq, tv, p, st);
-    case 3: return launch_fwd<3, 3>(tk, tq, tv, p, st);
-    case 4: return launch_fwd<4, 3>(tk, tq, tv, p, st);
-    case 5: return launch_fwd<5, 3>(tk, tq, tv, p, st);
-    case 6: return launch_fwd<6, 2>(tk, tq, tv, p, st);
-    case 7: return launch_fwd<7, 1>(tk, tq, tv, p, st);
-    default: return launch_fwd<8, 1>(tk, tq, tv, p, st);
+    case 1: return launch_fwd<1, 3, false>(tk, tq, tv, p, st);
+    case 2: return launch_fwd<2, 3, false>(tk, tq, tv, p, st);
+    case 3: return launch_fwd<3, 3, false>(tk, tq, tv, p, st);
+    case 4: return launch_fwd<4, 3, false>(tk, tq, tv, p, st);
+    case 5: return launch_fwd<5, 3, false>(tk, tq, tv, p, st);
+    case 6: return launch_fwd<6, 2, false>(tk, tq, tv, p, st);
+    case 7: return launch_fwd<7, 1, false>(tk, tq, tv, p, st);
+    default: return launch_fwd<8, 1, false>(tk, tq, tv, p, st);
   }
 }
 

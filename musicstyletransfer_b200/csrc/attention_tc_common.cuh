@@ -201,15 +201,17 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
+// raw: the tile is loaded as FLOAT32 (bits unchanged) instead of TFLOAT32 (rounded to nearest TF32 by the TMA unit) —
+// for kernels that split the value into hi + lo TF32 parts themselves.
 int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
-             int box_rows, bool mn_major) {
+             int box_rows, bool mn_major, bool raw = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { msx_set_error("msx_attention_tc: cuTensorMapEncodeTiled unavailable"); return MSX_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { msx_set_error("msx_attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MSX_ERR_CUDA; }

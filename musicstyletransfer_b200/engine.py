@@ -332,7 +332,7 @@ class VAEEngine:
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H)
+            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=self.x3_fwd)
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
             ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:

@@ -152,10 +152,11 @@ def attention_tc_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tc_supported(P(qkv), _i(T), _i(dh)))
 
 
-def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh):
-    """ctx: fp32, or bfloat16 (bf16 variant: the context only feeds the W_proj GEMMs)."""
-    lib.call("msx_attention_tc_fwd_ex", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), _i(B), _i(T),
-             _i(H), _i(dh), lib.stream_ptr())
+def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False):
+    """ctx: fp32, or bfloat16 (bf16 variant: the context only feeds the W_proj GEMMs).  x3_scores: S = K Q^T with 3xTF32
+    operand splitting (fp32-equivalent scores; the softmax turns their absolute error into a relative error of P)."""
+    lib.call("msx_attention_tc_fwd_ex2", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0),
+             _i(1 if x3_scores else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
 def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):

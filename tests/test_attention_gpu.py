@@ -51,6 +51,27 @@ def test_attention_tc_forward(B, T, H):
     assert err < 3e-3, err
 
 
+@pytest.mark.parametrize("B,T,H,dh", [(3, 65, 8, 32), (300, 65, 8, 32), (5, 66, 2, 32), (2, 16, 4, 32), (4, 97, 3, 32),
+                                      (2, 128, 2, 32), (7, 1, 2, 32), (500, 97, 2, 32), (64, 66, 8, 16)])
+def test_attention_tc_forward_compensated_scores(B, T, H, dh):
+    """x3_scores: S = K Q^T with 3xTF32 operand splitting.  Scores are scaled up (|S| ~ 10) so that the softmax turns the
+    single-pass TF32 score error into a visible error of the output; the compensated kernel must be >= 10x closer."""
+    from musicstyletransfer_b200 import ops
+    qkv, mask = _inputs(B, T, H, dh, seed=T + 7)
+    qkv[:, :2 * H * dh] *= 1.8                      # K and Q: score standard deviation ~ 3.2 * sqrt(dh) / sqrt(dh)
+    want = _ref_fwd(qkv, mask, B, T, H, dh)
+    qd, md = qkv.cuda(), mask.cuda()
+    outs = []
+    for x3 in (False, True):
+        ctx = torch.full((B * T, H * dh), 3.0, device="cuda")
+        ops.attention_tc_fwd(qd, md, ctx, B, T, H, dh, x3_scores=x3)
+        torch.cuda.synchronize()
+        outs.append(float((ctx.double().cpu() - want).abs().max()) / float(want.abs().max()))
+    print("attention forward B=%d T=%d H=%d dh=%d: TF32 scores err %.2e, compensated %.2e" % (B, T, H, dh, outs[0], outs[1]))
+    assert outs[1] < 6e-4, outs                     # what is left: P and V rounded to TF32 in O = P^T V
+    assert outs[1] < 0.7 * outs[0] or T == 1, outs   # T == 1: one query, P == 1 whatever the score
+
+
 # T <= 80 runs the pipelined kernel (the larger B cases give every pipeline group several items; H = 3 makes the head
 # change between the items of a group, which exercises the bias-gradient flush), T > 80 the one-shot kernel
 @pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8),

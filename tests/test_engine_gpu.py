@@ -438,7 +438,9 @@ def test_sos_rows_only_top_layer_equals_full_layer(prec, tol, dropout):
         assert abs(float(full["ce"].mean()) - float(sos["ce"].mean())) < 0.05 * float(full["ce"].mean())
         return
     for k in ("ce", "kl", "means", "stds"):
-        assert float((full[k] - sos[k]).abs().max()) <= tol * float(full[k].abs().max()), k
+        # raw Xavier weights: KL holds log sigma^2 with |sigma| down to ~1e-4, which amplifies rounding-order differences
+        ktol = max(tol, 2e-4) if k == "kl" else tol
+        assert float((full[k] - sos[k]).abs().max()) <= ktol * float(full[k].abs().max()), k
     gmax = float(full["g"].abs().max())
     for n in full["names"]:
         scale = float(full["names"][n].abs().max())
