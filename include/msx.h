@@ -44,6 +44,25 @@ int msx_step_counter_tick(unsigned long long* dev_counter, void* stream);
  * (gluon.nn.Dropout, transformer.py:44,155,158,200).  Used to replay a dropout step in a checker. */
 int msx_dropout_mask(uint8_t* out, long long n, float drop_p, unsigned long long seed, unsigned site, void* stream);
 
+/* (f3) — Standard MIDI File bytes -> note-event SoA for K1.  HOST function (plain C++ inside libmsx.so, no device work,
+ * host pointers).  Replaces python-midi's midi.read_midifile + the event walk of EventBasedMIDIReader.read_file /
+ * _parse_track (MIDIUtil/midi_io.py:35-93) and _extract_bpm (:16-25): every event's delta time advances the clock, Note-On /
+ * Note-Off events emit (ticks since the previous note event, data[0], data[1]); bpm = first Set-Tempo event, else 120.
+ * Events of track t occupy [track_offsets[t], track_offsets[t+1]); track_tokens[t] = number of tokens A1 makes of the track
+ * (the caller's "< 10 tokens: discard" filter, midi_io.py:60-63).  Capacities: note events <= n_bytes / 3, tracks = the
+ * header's count (read it with event_capacity = 0: the call then fails with info filled in).  Errors: MSX_ERR_ARG for
+ * malformed files (bad chunk ids, truncated events, running status without a status byte, data bytes >= 0x80),
+ * MSX_ERR_UNSUPPORTED for SMPTE time division. */
+typedef struct msx_smf_info {
+  int resolution;      /* ticks per quarter note */
+  int format;          /* SMF format 0 / 1 / 2 */
+  int n_tracks;
+  double bpm;
+  long long n_events;  /* note events in the file (also when they did not fit) */
+} msx_smf_info;
+int msx_smf_parse(const uint8_t* bytes, long long n_bytes, long long event_capacity, int track_capacity, int32_t* dtick,
+                  uint8_t* pitch, uint8_t* vel, int32_t* track_offsets, int32_t* track_tokens, msx_smf_info* info);
+
 /* K1 — note-event rasteriser.  Replaces EventBasedMIDIReader._parse_track (MIDIUtil/midi_io.py:70-93),
  * create_{note_on,note_off,timeshift}_event (MIDIUtil/Melody.py:109-126) and the clock semantics of
  * MelodyWriter._write_track (MIDIUtil/midi_io.py:119-127) for N independent sequences.
@@ -175,6 +194,23 @@ int msx_add_ln_bwd_ex(const float* x, const void* y, int y_bf16, const float* ga
                       const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta, float* dybias,
                       long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres,
                       int fuse_xy, void* stream);   /* y_bf16: the Dense output y is bfloat16 (read only by this LayerNorm) */
+
+/* A2 — dataset rows on the device.  Replace MelodyDataset._get_token_arrays / _count_sequence_length and the per-batch part
+ * of _preprocess_batch (VarAutoEncoder/data.py:133-198).  Input: K1's token streams, one per track — ids[t * ld + col0 + j],
+ * j < n_tokens[t] — with the tracks grouped by class in the reference's iteration order (class_start[c] .. class_start[c+1]).
+ * msx_rows_plan (one CTA) -> row_start[n_tracks + 1] (row_start[n_tracks] = total rows R), dup_row / dup_src [n_classes]
+ * (the duplicated last row per class, data.py:152-155) and len_present[L + 1] (the columns `labels[:, seq_lens] = EOS`
+ * hits, data.py:166-168).  msx_rows_build -> tokens / labels int32 [R, L + 1], classes [R], seq_lens [R] (non-PAD count
+ * including SOS).  msx_rows_gather_batch gathers `batch` rows by index, trimmed to t_out columns (data.py:196-198). */
+int msx_rows_plan(const int32_t* n_tokens, const int32_t* class_start, int n_tracks, int n_classes, int max_seq_len,
+                  int32_t* row_start, int32_t* dup_row, int32_t* dup_src, int32_t* len_present, void* stream);
+int msx_rows_build(const int32_t* ids, long long ld, int col0, const int32_t* n_tokens, const int32_t* track_class,
+                   int n_tracks, int n_classes, int max_seq_len, const int32_t* row_start, const int32_t* dup_row,
+                   const int32_t* dup_src, const int32_t* len_present, int32_t* tokens, int32_t* labels, int32_t* classes,
+                   int32_t* seq_lens, void* stream);
+int msx_rows_gather_batch(const int32_t* tokens, const int32_t* labels, const int32_t* classes, const int32_t* seq_lens,
+                          const int32_t* index, int batch, int ld, int t_out, int32_t* b_tokens, int32_t* b_labels,
+                          int32_t* b_classes, int32_t* b_seq_lens, void* stream);
 
 /* Strided row copy (add = 0) / accumulate (add = 1): out[r, :width] (+)= in[r, :width], row r of X at X + r * ldX.  The
  * encoder output is only read at the SOS position (model.py:97-100), so the top encoder layer runs on one row per sequence

@@ -2,9 +2,10 @@
 
 ``EventBasedMIDIReader.read_file`` keeps its contract (list of Melody, tracks with < 10 tokens dropped,
 at least one must survive) but the per-event featurisation loop of ``_parse_track`` (midi_io.py:70-93)
-runs on the GPU: the host parses the SMF container, folds every track into the note-event SoA
-(dtick since the previous note event, pitch, velocity) and ``featurise.tokenize_tracks`` launches the K1
-kernel once for all tracks of all files handed to ``read_files``."""
+runs on the GPU: the C++ parser in libmsx.so (``msx_smf_parse``) turns the .mid bytes of every track into the
+note-event SoA (dtick since the previous note event, pitch, velocity) and ``featurise.tokenize_tracks`` launches the
+K1 kernel once for all tracks of all files handed to ``read_files``.  The pure-Python SMF module (``smf.py``) remains for
+writing files (``MelodyWriter``) and as an independent reader in the tests."""
 import numpy as np
 
 from . import smf as midi
@@ -52,22 +53,23 @@ class EventBasedMIDIReader(MIDIReader):
     def read_files(self, file_names):
         """Batched form: one kernel launch tokenises every track of every file.  Returns {file: [Melody]}."""
         from .. import featurise
-        patterns = [midi.read_midifile(f) for f in file_names]
+        # .mid bytes -> note-event SoA in the C++ parser of libmsx.so (msx_smf_parse), SoA -> token ids in K1
+        parsed = [featurise.parse_smf_file(f) for f in file_names]
         soas, owners = [], []
-        for fi, pattern in enumerate(patterns):
-            for track in pattern:
-                soas.append(note_event_soa(track))
+        for fi, (_, tracks, _) in enumerate(parsed):
+            for soa in tracks:
+                soas.append(soa)
                 owners.append(fi)
         ids_per_track = featurise.tokenize_tracks(soas)
         out = {}
-        for fi, (fname, pattern) in enumerate(zip(file_names, patterns)):
-            bpm = self._extract_bpm(pattern)
+        for fi, (fname, (info, _, _)) in enumerate(zip(file_names, parsed)):
             result = []
             for ti, owner in enumerate(owners):
                 if owner != fi:
                     continue
-                new_melody = Melody(bpm=bpm, resolution=pattern.resolution, slices_per_quarter=self.slices_per_quarter_note)
+                new_melody = Melody(bpm=info["bpm"], resolution=info["resolution"], slices_per_quarter=self.slices_per_quarter_note)
                 new_melody.notes = [create_event_from_id(int(i)) for i in ids_per_track[ti]]
+                new_melody.soa = soas[ti]                        # note-event SoA: lets the device dataset re-tokenise in place
                 if len(new_melody) < 10:                         # midi_io.py:60-63
                     print('Warning: {} contains melodies of length {} < 10. Discarding'.format(fname, len(new_melody.notes)))
                     continue

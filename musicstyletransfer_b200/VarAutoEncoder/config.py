@@ -89,6 +89,9 @@ b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32x3f", "tf32
                            "tf32 with the Transformer layers' GEMM operands stored as bfloat16")
 b200_arg.add_argument('--cuda-graph', type=str2bool, default=True,
                       help="replay the train step from a CUDA graph per batch shape (one launch instead of ~70)")
+b200_arg.add_argument('--device-dataset', type=str2bool, default=True,
+                      help="build the dataset rows on the GPU and gather every batch there (A2 on the device); false = the "
+                           "host NumPy rows of the reference's MelodyDataset")
 b200_arg.add_argument('--seed', type=int, default=0)
 b200_arg.add_argument('--max-steps', type=int, default=-1, help="stop fit() after this many batches (-1: no limit)")
 b200_arg.add_argument('--log-dir', type=str, default='/tmp/out')

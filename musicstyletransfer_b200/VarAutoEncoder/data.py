@@ -196,19 +196,83 @@ class MelodyDataset(Dataset):
         batch.label[0] = batch.label[0][:, :max_seq_len]
 
 
-def load_dataset(loader_train: Loader, batch_size: int, split_percentage: float = None, loader_val: Loader = None):
-    """data.py:201-223."""
+class DeviceMelodyDataset(Dataset):
+    """MelodyDataset with the rows built and kept on the GPU (A2 on the device): the tracks' note events are tokenised by
+    K1, ``msx_rows_plan`` / ``msx_rows_build`` chunk them with the rules of ``_get_token_arrays`` (data.py:133-173, quirks
+    included) and every batch is one ``msx_rows_gather_batch`` launch — no row ever exists on the host.  Batches carry int32
+    CUDA tensors (``data = [tokens, seq_lens, classes]``, ``label = [labels]``), shuffled and wrap-padded like
+    ``mx.io.NDArrayIter(shuffle=True)`` and trimmed to the batch's longest row (data.py:187-198; the lengths are known on
+    the host from one copy made when the dataset is built, so iterating never synchronises)."""
+
+    def __init__(self, batch_size: int, maximum_sequence_length: int, melodies: Dict[str, List[Melody]], seed: int = 0,
+                 device="cuda"):
+        super().__init__(batch_size)
+        from .. import featurise
+        self.max_seq_len = maximum_sequence_length
+        melodies = dict(sorted(melodies.items(), key=lambda x: x[0]))
+        self.n_classes = len(melodies)
+        flat = [(c, m) for c, ms in enumerate(melodies.values()) for m in ms]
+        assert flat, "Empty sequences were found"
+        class_start = np.zeros(self.n_classes + 1, np.int32)
+        for c, _ in flat:
+            class_start[c + 1:] += 1
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        if all(getattr(m, "soa", None) is not None for _, m in flat):
+            tokens, n_tokens = featurise.tokenize_tracks_device([m.soa for _, m in flat], device)      # A1 on the device
+        else:                                                   # melodies given as ids (no note events): upload the ids
+            width = max(1, max(len(m) for _, m in flat))
+            host = np.zeros((len(flat), width + 1), np.int32)
+            host[:, 0] = SOS_ID
+            for i, (_, m) in enumerate(flat):
+                host[i, 1:1 + len(m)] = [e.id for e in m]
+            tokens, n_tokens = t(host), t(np.asarray([len(m) for _, m in flat], np.int32))
+        self.rows = featurise.build_rows(tokens, n_tokens, t(np.asarray([c for c, _ in flat], np.int32)), t(class_start),
+                                         self.max_seq_len)
+        self.tokens, self.labels, self.classes, self.seq_lens = self.rows
+        self._host_lens = self.seq_lens.cpu().numpy()
+        self.n = int(self.tokens.shape[0])
+        self.rng = np.random.RandomState(seed)
+        self.order = np.arange(self.n)
+        self.device = device
+        print("Tokens.shape {}".format(tuple(self.tokens.shape)))
+        print("Labels.shape {}".format(tuple(self.labels.shape)))
+        print("classes.shape {}".format(tuple(self.classes.shape)))
+
+    def num_classes(self):
+        return self.n_classes
+
+    def num_tokens(self):
+        return NUM_EVENTS
+
+    def __iter__(self):
+        from .. import featurise
+        self.rng.shuffle(self.order)
+        B = self.batch_size
+        for start in range(0, self.n, B):
+            idx = self.order[start:start + B]
+            pad = B - len(idx)
+            if pad > 0:
+                idx = np.concatenate([idx, self.order[:pad]])
+            t_out = int(self._host_lens[idx].max())
+            index = torch.from_numpy(idx.astype(np.int32)).to(self.device, non_blocking=True)
+            tok, lab, cls, lens = featurise.gather_batch(self.rows, index, t_out)
+            yield DataBatch([tok, lens, cls], [lab], pad)
+
+
+def load_dataset(loader_train: Loader, batch_size: int, split_percentage: float = None, loader_val: Loader = None,
+                 device_rows: bool = False):
+    """data.py:201-223.  device_rows: build and iterate the rows on the GPU (DeviceMelodyDataset)."""
+    make = DeviceMelodyDataset if device_rows else MelodyDataset
     if loader_val is not None:
-        train = MelodyDataset(batch_size, loader_train.max_sequence_length, loader_train.melodies)
-        val = MelodyDataset(batch_size, loader_val.max_sequence_length, loader_val.melodies)
-        return train, val
+        return (make(batch_size, loader_train.max_sequence_length, loader_train.melodies),
+                make(batch_size, loader_val.max_sequence_length, loader_val.melodies))
     if split_percentage <= 0.:
-        return MelodyDataset(batch_size, loader_train.max_sequence_length, loader_train.melodies), None
+        return make(batch_size, loader_train.max_sequence_length, loader_train.melodies), None
     assert 0.0 < split_percentage < 1.0
     train_split, valid_split = {}, {}
     for c, m in loader_train.melodies.items():
         n_validation_melodies = int(split_percentage * len(m))
         valid_split[c] = m[:n_validation_melodies]
         train_split[c] = m[n_validation_melodies:]
-    return (MelodyDataset(batch_size, loader_train.max_sequence_length, train_split),
-            MelodyDataset(batch_size, loader_train.max_sequence_length, valid_split))
+    return (make(batch_size, loader_train.max_sequence_length, train_split),
+            make(batch_size, loader_train.max_sequence_length, valid_split))

@@ -104,7 +104,8 @@ def main(argv=None):
     if args.validation_data is not None:
         val_loader = Loader(path=args.validation_data, max_sequence_length=args.max_seq_len,
                             slices_per_quarter_note=args.slices_per_quarter_note)
-    train_dataset, valid_dataset = load_dataset(loader, args.batch_size, args.validation_split, val_loader)
+    train_dataset, valid_dataset = load_dataset(loader, args.batch_size, args.validation_split, val_loader,
+                                               device_rows=getattr(args, "device_dataset", True))
     create_directory_if_not_present(args.model_output)
     if args.out_samples:
         create_directory_if_not_present(args.out_samples)

@@ -93,6 +93,30 @@ def gen_fixture_tokens():
         len(names), sum(len(out["ids:" + n]) for n in names), rows["tokens_L64"].shape))
 
 
+def gen_midi_bytes():
+    """The reference's own .mid inputs (work/data/guitar_bass: the 37 parity fixtures; work/data/splits: 73 more single-track
+    files) as raw bytes, so that the SMF parser tests run where /root/reference does not exist (the GPU box).  Per file also
+    what the reference reader makes of it: resolution, bpm and, for every track, the note-event walk of
+    EventBasedMIDIReader._parse_track (midi_io.py:70-93) through the `midi` stand-in."""
+    out, names = {}, []
+    for sub in ("guitar_bass/bass", "guitar_bass/guitar", "splits"):
+        for f in sorted(glob.glob(os.path.join(REF, "work/data", sub, "*.mid"))):
+            key = "%s/%s" % (sub, os.path.basename(f))
+            names.append(key)
+            with open(f, "rb") as fh:
+                out["bytes:" + key] = np.frombuffer(fh.read(), dtype=np.uint8)
+            pat = smf.read_midifile(f)
+            out["res:" + key] = np.int32(pat.resolution)
+            out["bpm:" + key] = np.float64(quiet(ref_midi_io.EventBasedMIDIReader)._extract_bpm(pat))
+            out["ntracks:" + key] = np.int32(len(pat))
+            for ti, track in enumerate(pat):
+                dt, pi, ve = featurise.note_events_of_track(track)
+                out["dtick:%d:%s" % (ti, key)], out["pitch:%d:%s" % (ti, key)], out["vel:%d:%s" % (ti, key)] = dt, pi, ve
+    out["names"] = np.asarray(names)
+    np.savez_compressed(os.path.join(HERE, "midi_fixtures.npz"), **out)
+    print("midi bytes: %d files, %d bytes" % (len(names), sum(out["bytes:" + n].size for n in names)))
+
+
 # ----------------------------------------------------------------------------- losses
 def gen_losses():
     rng = np.random.RandomState(0)
@@ -221,6 +245,7 @@ def gen_model_small():
 
 if __name__ == "__main__":
     gen_fixture_tokens()
+    gen_midi_bytes()
     gen_losses()
     gen_model_toy()
     gen_model_small()
