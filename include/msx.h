@@ -238,6 +238,18 @@ int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* do
 int msx_embed_bwd_ex(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                      float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, int num_classes, void* stream);
 
+/* Piano-roll front end (`--featurisation roll`, the north star's "step over piano-roll tensors ... sigmoid-BCE"; model side:
+ * derived spec oracle/roll_model.py).  msx_roll_features: uint8 roll [B, S, 128] (K1 output) -> fp32 GEMM operands
+ * renc [B, S+1, 132] (row 0 = start flag in column 128, rows 1..S = (roll > 0)) and rdec [B, S, 132] (row t = renc row t,
+ * i.e. the previous slice: teacher forcing).  msx_embed_dense_*: out = scale * (E + cls_emb[classes]) + pe — the
+ * Encoder front end (model.py:89-91, transformer.py:270) when the token embedding is a Dense over the multi-hot slice;
+ * backward: dE = scale * dout, d_cls_emb[classes[b]] += scale * sum_t dout[b, t]. */
+int msx_roll_features(const uint8_t* roll, float* renc, float* rdec, int B, int S, void* stream);
+int msx_embed_dense_fwd(const float* E, const int32_t* classes, const float* cls_emb, const float* pe, float* out, int B, int T,
+                        int D, float scale, void* stream);
+int msx_embed_dense_bwd(const float* dout, const int32_t* classes, float* dE, float* d_cls_emb, int B, int T, int D, float scale,
+                        void* stream);
+
 /* K2g — persistent LSTM recurrence.  Replaces the fused gluon.rnn.LSTM call in LSTMDecoder.forward_train
  * (model.py:148-153,179); gx_inout [B,T,4H] holds x W_i2h^T + b_i2h on entry and the gate activations on exit;
  * h0/c0 are rows of a [B, ld0] buffer (model.py:159-167).  Backward turns the saved activations into

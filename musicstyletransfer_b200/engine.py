@@ -15,6 +15,7 @@ import torch
 from . import ops
 
 NUM_EVENTS = 293     # MIDIUtil/defaults.py:58
+N_PITCH, ROLL_IN = 128, 132      # piano-roll width (defaults.py:51-54) and its 16-byte padded GEMM operand width
 SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 1: ff hidden, 2: ff out}
 
 
@@ -39,8 +40,14 @@ class VAEConfig:
     """Flat mirror of ModelConfig (model.py:11-54) + TransformerConfig (transformer.py:8-21) + LSTMConfig."""
 
     def __init__(self, vocab=NUM_EVENTS, num_classes=2, enc_size=256, enc_layers=2, enc_heads=8, latent=256,
-                 dec_type="lstm", dec_size=128, dec_layers=1, dec_heads=8, enc_dropout=0.0, dec_dropout=0.0):
+                 dec_type="lstm", dec_size=128, dec_layers=1, dec_heads=8, enc_dropout=0.0, dec_dropout=0.0,
+                 featurisation="events"):
         assert dec_type in ("lstm", "transformer")
+        # "events": token ids (the reference's HEAD); "roll": K1's piano-roll windows with the sigmoid-BCE reconstruction
+        # loss (loss.py:27-81) — LSTM decoder only, see forward_roll
+        assert featurisation in ("events", "roll")
+        assert featurisation == "events" or dec_type == "lstm", "the piano-roll path uses the LSTM decoder"
+        self.featurisation = featurisation
         assert enc_size % enc_heads == 0
         if dec_type == "transformer":
             assert dec_size % dec_heads == 0
@@ -75,6 +82,18 @@ def _tf_layer_entries(prefix, D, ln2):
 def param_entries(cfg):
     """(name, shape) in arena order.  Names follow the Gluon attribute paths of model.py / transformer.py."""
     D, Z, V, C, H = cfg.enc_size, cfg.latent, cfg.vocab, cfg.num_classes, cfg.dec_size
+    if getattr(cfg, "featurisation", "events") == "roll":
+        # the Embedding lookups become bias-free Dense layers over [128 pitches | start flag | 3 zero columns]
+        e = [("encoder.class2hid.weight", (C, D)), ("encoder.roll_embedding.weight", (D, ROLL_IN))]
+        for l in range(cfg.enc_layers):
+            e += _tf_layer_entries("encoder.encoder.layer%d." % l, D, "ln2")
+        e += [("encoder.latent_proj.weight", (2 * Z, D)), ("encoder.latent_proj.bias", (2 * Z,)),
+              ("decoder.latent2hid.weight", (2 * H, Z)), ("decoder.latent2hid.bias", (2 * H,)),
+              ("decoder.class2hid.weight", (C, 2 * H)), ("decoder.roll_embedding.weight", (H, ROLL_IN))]
+        for l in range(cfg.dec_layers):
+            e += [("decoder.decoder.l%d_i2h_weight" % l, (4 * H, H)), ("decoder.decoder.l%d_h2h_weight" % l, (4 * H, H)),
+                  ("decoder.decoder.l%d_i2h_bias" % l, (4 * H,)), ("decoder.decoder.l%d_h2h_bias" % l, (4 * H,))]
+        return e + [("decoder.output_layer.weight", (N_PITCH, H)), ("decoder.output_layer.bias", (N_PITCH,))]
     e = [("encoder.class2hid.weight", (C, D)), ("encoder.encoder_embedding.weight", (V, D))]
     for l in range(cfg.enc_layers):
         e += _tf_layer_entries("encoder.encoder.layer%d." % l, D, "ln2")
@@ -568,6 +587,14 @@ class VAEEngine:
         ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
                       self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V,
                       out16=x16)
+        return self._encode_layers(bf, x, x16, mask, B, T, p_drop)
+
+    def _encode_layers(self, bf, x, x16, mask, B, T, p_drop):
+        """Transformer encoder layers + latent projection on an embedded input x [B*T, D] (transformer.py:268-273,
+        model.py:97-103)."""
+        cfg, dev = self.cfg, self.device
+        D, Z = cfg.enc_size, cfg.latent
+        l16 = x16 is not None
         xs = [x]
         self._xs16 = [x16]
         for l in range(cfg.enc_layers):
@@ -782,6 +809,83 @@ class VAEEngine:
         stop = int(done[0]) + 1 if done.numel() else I_max - 1      # sampler.py:250: all current tokens EOS / PAD
         return seq[cur][:, :stop + 1].clone(), score[cur].clone()
 
+    # ------------------------------------------------------------------ LSTM decoder (model.py:131-203)
+    def _lstm_decoder_fwd(self, bf, xe, z, classes, B, T):
+        """LSTMDecoder.forward_train after the input embedding: initial state latent2hid(z) + class2hid[classes] split into
+        (h0, c0) (model.py:159-167), i2h GEMM for all T steps, persistent recurrence.  xe [B*T, H] -> hs [B*T, H]."""
+        cfg, dev = self.cfg, self.device
+        Z, Hd = cfg.latent, cfg.dec_size
+        M = B * T
+        tv = bf.get("dec.tvec", (B, 2 * Hd), dev)
+        ops.embed_fwd(classes, None, None, self._W("decoder.class2hid.weight"), None, None, None, tv, None, B, 1,
+                      2 * Hd, 0, 1.0, cfg.num_classes)
+        self._dense_fwd(z, Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
+                        accumulate=True)
+        gates = bf.get("dec.gates", (M, 4 * Hd), dev)
+        self._dense_fwd(xe, Hd, M, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
+                        4 * Hd, Hd)
+        hs = bf.get("dec.hs", (M, Hd), dev)
+        hprev = bf.get("dec.hprev", (M, Hd), dev)
+        cs = bf.get("dec.cs", (M, Hd), dev)
+        lstm_fwd = ops.lstm_tc_fwd if self._lstm_tc(Hd, tv) else ops.lstm_fwd
+        lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
+                 tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+        return hs
+
+    def _lstm_decoder_bwd(self, bf, c, ddec, dz, B, T):
+        """Backward of _lstm_decoder_fwd: ddec [B*T, H] = gradient of the hidden states.  Accumulates the LSTM / latent2hid /
+        class2hid parameter gradients, writes dz, returns the gradient of the decoder input xe."""
+        cfg, dev = self.cfg, self.device
+        Z, Hd = cfg.latent, cfg.dec_size
+        M = B * T
+        gates = bf.t[("dec.gates", (M, 4 * Hd), torch.float32)]
+        hprev = bf.t[("dec.hprev", (M, Hd), torch.float32)]
+        cs = bf.t[("dec.cs", (M, Hd), torch.float32)]
+        xe = bf.t[("dec.xe", (M, Hd), torch.float32)]
+        tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
+        dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
+        lstm_bwd = ops.lstm_tc_bwd if self._lstm_tc(Hd, tv) else ops.lstm_bwd
+        lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
+                 B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
+                 db_h2h=self._G("decoder.decoder.l0_h2h_bias"))                # gates now hold d(pre-activations)
+        dxe = bf.get("dec.dxe", (M, Hd), dev)
+        self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
+                        self._G("decoder.decoder.l0_i2h_weight"), None, 4 * Hd, Hd, dx=dxe, lddx=Hd)
+        self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"), None, 4 * Hd, Hd)
+        ops.embed_bwd(c["classes"], None, dtv, self._G("decoder.class2hid.weight"), None, None, B, 1, 2 * Hd, 0, 1.0,
+                      cfg.num_classes)
+        self._dense_bwd(dtv, 2 * Hd, B, c["z"], Z, self._W("decoder.latent2hid.weight"),
+                        self._G("decoder.latent2hid.weight"), self._G("decoder.latent2hid.bias"), 2 * Hd, Z,
+                        dx=dz, lddx=Z)
+        return dxe
+
+    def _encode_layers_bwd(self, bf, c, dlat, B, T):
+        """Backward of _encode_layers: dlat [B, 2Z] -> gradient of the embedded encoder input [B*T, D]."""
+        cfg, dev = self.cfg, self.device
+        D, Z = cfg.enc_size, cfg.latent
+        M = B * T
+        xs = c["xs"]
+        if self._sos_only(cfg.enc_layers - 1):
+            dx = bf.get("enc.dx_top_c", (B, D), dev)             # compact: one row per sequence
+            ldt = D
+        else:
+            # only rows b*T are ever written (by the dgrad below); the rest stays zero from the buffer's creation
+            dx = bf.get_zero("enc.dx_top", (M, D), dev)
+            ldt = T * D
+        self._dense_bwd(dlat, 2 * Z, B, xs[-1], ldt, self._W("encoder.latent_proj.weight"),
+                        self._G("encoder.latent_proj.weight"), self._G("encoder.latent_proj.bias"), 2 * Z, D,
+                        dx=dx, lddx=ldt)
+        for l in reversed(range(cfg.enc_layers)):
+            dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
+            if self._layer16_ok(D):
+                self._tf_layer_bwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["xs16"][l], c["mask"], dx,
+                                     dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+            else:
+                self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
+                                   cfg.enc_heads, c["pe"], l * SITE_STRIDE, False, sos_only=self._sos_only(l))
+            dx = dnext
+        return dx
+
     # ------------------------------------------------------------------ forward
     def forward(self, *args, **kwargs):
         """tokens int32 [B,T], seq_lens int32 [B], classes int32 [B], labels int32 [B,T] (optional),
@@ -825,23 +929,10 @@ class VAEEngine:
 
         # ---- decoder
         if cfg.dec_type == "lstm":
-            tv = bf.get("dec.tvec", (B, 2 * Hd), dev)          # latent2hid(z) + class2hid[classes] (model.py:160)
-            ops.embed_fwd(classes, None, None, self._W("decoder.class2hid.weight"), None, None, None, tv, None, B, 1,
-                          2 * Hd, 0, 1.0, cfg.num_classes)
-            self._dense_fwd(z, Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
-                            accumulate=True)
             xe = bf.get("dec.xe", (M, Hd), dev)
             ops.embed_fwd(tokens, None, None, self._W("decoder.embedding.weight"), None, None, None, xe, None, B, T, Hd, 0,
                           1.0, V)
-            gates = bf.get("dec.gates", (M, 4 * Hd), dev)
-            self._dense_fwd(xe, Hd, M, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
-                            4 * Hd, Hd)
-            hs = bf.get("dec.hs", (M, Hd), dev)
-            hprev = bf.get("dec.hprev", (M, Hd), dev)
-            cs = bf.get("dec.cs", (M, Hd), dev)
-            lstm_fwd = ops.lstm_tc_fwd if self._lstm_tc(Hd, tv) else ops.lstm_fwd
-            lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
-                     tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, T)
             dec_out, Td = hs, T
             dmask = None
         else:
@@ -927,26 +1018,8 @@ class VAEEngine:
                         V, Hd, dx=ddec, lddx=Hd)
         dz = bf.get("dz", (B, Z), dev)
         if cfg.dec_type == "lstm":
-            gates = bf.t[("dec.gates", (M, 4 * Hd), torch.float32)]
-            hprev = bf.t[("dec.hprev", (M, Hd), torch.float32)]
-            cs = bf.t[("dec.cs", (M, Hd), torch.float32)]
-            xe = bf.t[("dec.xe", (M, Hd), torch.float32)]
-            tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
-            dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
-            lstm_bwd = ops.lstm_tc_bwd if self._lstm_tc(Hd, tv) else ops.lstm_bwd
-            lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
-                     B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
-                     db_h2h=self._G("decoder.decoder.l0_h2h_bias"))                # gates now hold d(pre-activations)
-            dxe = bf.get("dec.dxe", (M, Hd), dev)
-            self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
-                            self._G("decoder.decoder.l0_i2h_weight"), None, 4 * Hd, Hd, dx=dxe, lddx=Hd)
-            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"), None, 4 * Hd, Hd)
+            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, T)
             ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
-            ops.embed_bwd(c["classes"], None, dtv, self._G("decoder.class2hid.weight"), None, None, B, 1, 2 * Hd, 0, 1.0,
-                          cfg.num_classes)
-            self._dense_bwd(dtv, 2 * Hd, B, c["z"], Z, self._W("decoder.latent2hid.weight"),
-                            self._G("decoder.latent2hid.weight"), self._G("decoder.latent2hid.bias"), 2 * Hd, Z,
-                            dx=dz, lddx=Z)
         else:
             dxs = c["dxs"]
             dcur = ddec
@@ -969,29 +1042,129 @@ class VAEEngine:
         # ---- reparameterisation + KL (model.py:292, loss.py:8-12)
         dlat = bf.get("dlat", (B, 2 * Z), dev)
         ops.reparam_kl_bwd(c["lat"], c["eps"], dz, g_kl, kl_weight, dlat, B, Z)
-        # ---- latent projection on the SOS position (model.py:97-100): rows b*T of the last encoder output
-        xs = c["xs"]
-        if self._sos_only(cfg.enc_layers - 1):
-            dx = bf.get("enc.dx_top_c", (B, D), dev)             # compact: one row per sequence
-            ldt = D
-        else:
-            # only rows b*T are ever written (by the dgrad below); the rest stays zero from the buffer's creation
-            dx = bf.get_zero("enc.dx_top", (M, D), dev)
-            ldt = T * D
-        self._dense_bwd(dlat, 2 * Z, B, xs[-1], ldt, self._W("encoder.latent_proj.weight"),
-                        self._G("encoder.latent_proj.weight"), self._G("encoder.latent_proj.bias"), 2 * Z, D,
-                        dx=dx, lddx=ldt)
-        for l in reversed(range(cfg.enc_layers)):
-            dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
-            if self._layer16_ok(D):
-                self._tf_layer_bwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["xs16"][l], c["mask"], dx,
-                                     dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
-            else:
-                self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
-                                   cfg.enc_heads, c["pe"], l * SITE_STRIDE, False, sos_only=self._sos_only(l))
-            dx = dnext
+        dx = self._encode_layers_bwd(bf, c, dlat, B, T)
         ops.embed_bwd(c["tokens"], c["classes"], dx, self._G("encoder.encoder_embedding.weight"),
                       self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)
+
+    # ------------------------------------------------------------------ piano-roll step (--featurisation roll)
+    def forward_roll(self, roll, classes, eps=None, train=True, label_smoothing=0.0, downweight=True, want_grad=True):
+        """The step over K1's piano-roll windows with the sigmoid-BCE reconstruction loss (BASELINE.json north_star;
+        BinaryCrossEntropy, loss.py:27-81; model side: derived spec oracle/roll_model.py).  roll uint8 [B, S, 128] (CUDA),
+        classes int32 [B].  Encoder input = start row + the S slices (T = S + 1 positions, all real: no key padding), the
+        token Embedding becomes a Dense over the multi-hot slice; LSTM decoder with teacher forcing -> logits [B, S, 128].
+        Returns dict(bce [B], kl, means, stds, logits); want_grad also leaves d bce / d logits for backward_roll."""
+        try:
+            return self._forward_roll(roll, classes, eps, train, label_smoothing, downweight, want_grad)
+        finally:
+            ops.set_step_counter(None)
+
+    def _forward_roll(self, roll, classes, eps, train, label_smoothing, downweight, want_grad):
+        cfg, dev = self.cfg, self.device
+        assert cfg.featurisation == "roll" and not self.bf16, "forward_roll: engine built for token events / bf16 operands"
+        B, S, P = roll.shape
+        assert P == N_PITCH and roll.dtype == torch.uint8 and roll.is_contiguous()
+        T = S + 1
+        D, Z, Hd = cfg.enc_size, cfg.latent, cfg.dec_size
+        M, Ms = B * T, B * S
+        bf = self._buf(B, T)
+        pe_ = cfg.enc_dropout if train else 0.0
+        self.dropout_seed = self.base_seed
+        ops.set_step_counter(self.step_dev)
+        renc = bf.get("roll.renc", (M, ROLL_IN), dev)
+        rdec = bf.get("roll.rdec", (Ms, ROLL_IN), dev)
+        ops.roll_features(roll, renc, rdec, B, S)
+        E = bf.get("roll.E", (M, D), dev)
+        self._dense_fwd(renc, ROLL_IN, M, "encoder.roll_embedding.weight", None, E, D, D, ROLL_IN)
+        x = bf.get("enc.x0", (M, D), dev)
+        ops.embed_dense_fwd(E, classes, self._W("encoder.class2hid.weight"), self.pe_enc, x, B, T, D, math.sqrt(float(D)))
+        mask = bf.t.get(("roll.mask", (M,), torch.float32))
+        if mask is None:
+            mask = bf.get("roll.mask", (M,), dev)
+            mask.fill_(1.0)                                     # every slice is a real key (once per shape)
+        xs, mask, lat = self._encode_layers(bf, x, None, mask, B, T, pe_)
+        if eps is None:
+            eps = bf.get("eps", (B, Z), dev)
+            ops.normal_fill(eps, self.dropout_seed, 0xE95)
+        z = bf.get("z", (B, Z), dev)
+        kl = bf.get("kl", (B,), dev)
+        ops.reparam_kl_fwd(lat, eps, z, kl, B, Z)
+        xe = bf.get("dec.xe", (Ms, Hd), dev)
+        self._dense_fwd(rdec, ROLL_IN, Ms, "decoder.roll_embedding.weight", None, xe, Hd, Hd, ROLL_IN)
+        hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, S)
+        logits = bf.get("roll.logits", (Ms, N_PITCH), dev)
+        self._dense_fwd(hs, Hd, Ms, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, N_PITCH, N_PITCH, Hd)
+        bce = bf.get("roll.bce", (B,), dev)
+        dlogits = bf.get("roll.dlogits", (Ms, N_PITCH), dev) if want_grad else None
+        ops.bce(logits, roll, bce, None, dlogits, B, S * N_PITCH, from_sigmoid=False, label_smoothing=label_smoothing,
+                downweight=downweight)
+        self.ctx = dict(B=B, T=T, S=S, classes=classes, eps=eps, xs=xs, mask=mask, lat=lat, z=z, hs=hs, pe=pe_, bf=bf,
+                        xs16=self._xs16, renc=renc, rdec=rdec, dlogits=dlogits, roll=True)
+        return {"bce": bce, "ce": bce, "kl": kl, "means": lat[:, :Z], "stds": lat[:, Z:], "z": z, "logits": logits.view(B, S, N_PITCH)}
+
+    def backward_roll(self, kl_weight=1.0):
+        """d(sum_b bce_b + kl_weight * kl_b) / d params into the gradient arena (trainer.py:172-176)."""
+        try:
+            c = self.ctx
+            cfg, dev, bf = self.cfg, self.device, c["bf"]
+            assert c.get("roll") and c["dlogits"] is not None, "backward_roll needs forward_roll(want_grad=True)"
+            B, T, S = c["B"], c["T"], c["S"]
+            D, Z, Hd = cfg.enc_size, cfg.latent, cfg.dec_size
+            M, Ms = B * T, B * S
+            ops.set_step_counter(self.step_dev)
+            ddec = bf.get("ddec", (Ms, Hd), dev)
+            self._dense_bwd(c["dlogits"], N_PITCH, Ms, c["hs"], Hd, self._W("decoder.output_layer.weight"),
+                            self._G("decoder.output_layer.weight"), self._G("decoder.output_layer.bias"), N_PITCH, Hd,
+                            dx=ddec, lddx=Hd)
+            dz = bf.get("dz", (B, Z), dev)
+            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, S)
+            self._dense_bwd(dxe, Hd, Ms, c["rdec"], ROLL_IN, None, self._G("decoder.roll_embedding.weight"), None, Hd, ROLL_IN)
+            dlat = bf.get("dlat", (B, 2 * Z), dev)
+            ops.reparam_kl_bwd(c["lat"], c["eps"], dz, None, kl_weight, dlat, B, Z)
+            dx = self._encode_layers_bwd(bf, c, dlat, B, T)
+            dE = bf.get("roll.dE", (M, D), dev)
+            ops.embed_dense_bwd(dx, c["classes"], dE, self._G("encoder.class2hid.weight"), B, T, D, math.sqrt(float(D)))
+            self._dense_bwd(dE, D, M, c["renc"], ROLL_IN, None, self._G("encoder.roll_embedding.weight"), None, D, ROLL_IN)
+        finally:
+            ops.set_step_counter(None)
+
+    def train_step_roll(self, roll, classes, eps=None, kl_weight=1.0, global_batch=None, lr=3e-4, clip_gradient=None,
+                        label_smoothing=0.0, downweight=True, allreduce=None):
+        out = self.forward_roll(roll, classes, eps=eps, train=True, label_smoothing=label_smoothing, downweight=downweight)
+        self.backward_roll(kl_weight)
+        peer = isinstance(allreduce, str) and allreduce == "peer"
+        if allreduce is not None and not peer:
+            allreduce(self.arena.g)
+        self.adam_step(global_batch or roll.shape[0], lr=lr, clip_gradient=clip_gradient, peer=peer)
+        return out
+
+    def train_step_roll_graphed(self, roll, classes, kl_weight=1.0, global_batch=None, lr=3e-4, clip_gradient=None,
+                                label_smoothing=0.0, downweight=True):
+        """train_step_roll replayed from a CUDA graph (single GPU), one graph per batch shape / hyper-parameter set."""
+        B, S, _ = roll.shape
+        key = ("roll", B, S, float(kl_weight), global_batch, float(lr), clip_gradient, float(label_smoothing), bool(downweight))
+        st = self._graphs.get(key)
+        kw = dict(kl_weight=kl_weight, global_batch=global_batch, lr=lr, clip_gradient=clip_gradient,
+                  label_smoothing=label_smoothing, downweight=downweight)
+        if st is None:
+            self._graphs[key] = {"graph": None}
+            return self.train_step_roll(roll, classes, **kw)
+        if st["graph"] is None:
+            from . import lib
+            st["in"] = (torch.empty_like(roll), torch.empty_like(classes))
+            graph = torch.cuda.CUDAGraph()
+            l0 = lib.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = self.train_step_roll(st["in"][0], st["in"][1], **kw)
+            self.step_count -= 1
+            st["graph"], st["out"], st["launches"] = graph, out, lib.LAUNCHES - l0
+            lib.LAUNCHES = l0
+        from . import lib
+        st["in"][0].copy_(roll, non_blocking=True)
+        st["in"][1].copy_(classes, non_blocking=True)
+        st["graph"].replay()
+        lib.LAUNCHES += st["launches"]
+        self.step_count += 1
+        return st["out"]
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, batch_size, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, clip_gradient=None, peer=False):

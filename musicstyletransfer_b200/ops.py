@@ -212,6 +212,19 @@ def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, pr
              _i(D), _i(prefix), _f(scale), _i(vocab), _i(ncls), lib.stream_ptr())
 
 
+def roll_features(roll, renc, rdec, B, S):
+    assert roll.dtype == torch.uint8 and roll.is_contiguous()
+    lib.call("msx_roll_features", P(roll), P(_chk(renc)), P(_chk(rdec)), _i(B), _i(S), lib.stream_ptr())
+
+
+def embed_dense_fwd(E, classes, cls_emb, pe, out, B, T, D, scale):
+    lib.call("msx_embed_dense_fwd", P(E), P(classes), P(cls_emb), P(pe), P(out), _i(B), _i(T), _i(D), _f(scale), lib.stream_ptr())
+
+
+def embed_dense_bwd(dout, classes, dE, d_cls_emb, B, T, D, scale):
+    lib.call("msx_embed_dense_bwd", P(dout), P(classes), P(dE), P(d_cls_emb), _i(B), _i(T), _i(D), _f(scale), lib.stream_ptr())
+
+
 def reparam_kl_fwd(lat, eps, z, kl, B, Z):
     lib.call("msx_reparam_kl_fwd", P(lat), P(eps), P(z), P(kl), _i(B), _i(Z), lib.stream_ptr())
 

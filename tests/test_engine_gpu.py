@@ -427,6 +427,10 @@ def test_sos_rows_only_top_layer_equals_full_layer(prec, tol, dropout):
     for sos in (False, True):
         eng = VAEEngine(VAEConfig(dec_type="lstm", enc_dropout=dropout, dec_dropout=dropout), "cuda:0", seed=2, precision=prec,
                         sos_rows_only=sos)
+        # sigma away from 0 (see _condition_sigma): with raw weights 1 / sigma amplifies the last-bit differences between
+        # the two layouts (B = 48 compact rows run the exact small-shape GEMM, the full layout the 3xTF32 one) to per cents
+        eng.arena.view("encoder.latent_proj.weight")[256:] *= 0.05
+        eng.arena.view("encoder.latent_proj.bias")[256:] = 3.0
         out = eng.forward(*args, eps=_dev(eps, torch.float32), train=True)
         res.append({k: out[k].clone() for k in ("ce", "kl", "means", "stds")})
         eng.backward()
