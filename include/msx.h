@@ -271,7 +271,8 @@ int msx_lstm_tc_bwd(float* gates_inout, const float* w_h2h, const float* cs, con
  * [B*T, ld], ce[b] = sum_t mask*nll / denom, metrics[4] += {sum nll (clamped like mx.metric.Perplexity),
  * tokens, top-1 hits, top-k hits} (trainer.py:107-120,181-186, metrics.py); msx_ce_bwd overwrites the logits
  * with the gradient; msx_softmax_rows / msx_ce_from_probs keep the probability-based API (model.py:296,
- * loss.py:16-23); msx_bce: BinaryCrossEntropy on uint8 piano rolls (loss.py:27-81), value and/or gradient. */
+ * loss.py:16-23); msx_bce: BinaryCrossEntropy on uint8 piano rolls (loss.py:27-81), value and/or gradient; the label of a
+ * cell is (roll != 0), so binary and velocity rolls give the same loss. */
 int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, int B, int Z, void* stream);
 int msx_reparam_kl_bwd(const float* lat, const float* eps, const float* dz, const float* gkl, float kl_weight,
                        float* dlat, int B, int Z, void* stream);

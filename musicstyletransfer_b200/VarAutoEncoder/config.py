@@ -89,6 +89,10 @@ b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32x3f", "tf32
                            "tf32 with the Transformer layers' GEMM operands stored as bfloat16")
 b200_arg.add_argument('--cuda-graph', type=str2bool, default=True,
                       help="replay the train step from a CUDA graph per batch shape (one launch instead of ~70)")
+b200_arg.add_argument('--featurisation', choices=["events", "roll"], default="events",
+                      help="events = token ids (the reference's HEAD); roll = K1's piano-roll windows of --max-seq-len slices with the "
+                           "sigmoid-BCE reconstruction loss (loss.py:27-81; consumes --label-smoothing and "
+                           "--negative-label-downscaling), LSTM decoder")
 b200_arg.add_argument('--device-dataset', type=str2bool, default=True,
                       help="build the dataset rows on the GPU and gather every batch there (A2 on the device); false = the "
                            "host NumPy rows of the reference's MelodyDataset")

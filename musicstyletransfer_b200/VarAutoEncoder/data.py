@@ -259,6 +259,66 @@ class DeviceMelodyDataset(Dataset):
             yield DataBatch([tok, lens, cls], [lab], pad)
 
 
+class RollDataset(Dataset):
+    """Piano-roll windows for ``--featurisation roll``: every track is rasterised by K1 into consecutive windows of
+    ``n_slices`` slices (``featurise.rasterize_windows``, up to 1024 slices per track), each valid window is one row
+    ``uint8 [n_slices, 128]`` with its track's class.  Rows live on the GPU; batches are shuffled / wrap-padded like
+    MelodyDataset's and carry ``data = [roll, classes]``, ``label = [roll]``."""
+
+    def __init__(self, batch_size: int, n_slices: int, melodies: Dict[str, List[Melody]], slices_per_quarter_note=4,
+                 seed: int = 0, device="cuda"):
+        super().__init__(batch_size)
+        from .. import featurise
+        melodies = dict(sorted(melodies.items(), key=lambda x: x[0]))
+        self.n_classes = len(melodies)
+        self.n_slices = int(n_slices)
+        max_windows = max(1, 1024 // self.n_slices)
+        rolls, classes = [], []
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        by_res = {}
+        for c, ms in enumerate(melodies.values()):
+            for m in ms:
+                assert getattr(m, "soa", None) is not None, "RollDataset needs melodies read from MIDI files (note events)"
+                by_res.setdefault(int(m.resolution), []).append((c, m.soa))
+        for res, items in sorted(by_res.items()):
+            lens = [len(s[0]) for _, s in items]
+            offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            cat = lambda i, dt: np.concatenate([np.asarray(s[i], dtype=dt) for _, s in items])
+            roll, n_win = featurise.rasterize_windows(t(cat(0, np.int32)), t(cat(1, np.uint8)), t(cat(2, np.uint8)), t(offs),
+                                                      resolution=res, slices_per_quarter=int(slices_per_quarter_note),
+                                                      n_slices=self.n_slices, max_windows=max_windows)
+            n_win_h = n_win.cpu().numpy()
+            for i, (c, _) in enumerate(items):
+                rolls.append(roll[i, :int(n_win_h[i])])
+                classes += [c] * int(n_win_h[i])
+        self.rolls = torch.cat(rolls, dim=0).contiguous()                       # [R, S, 128] uint8 on the device
+        self.classes = t(np.asarray(classes, np.int32))
+        self.n = int(self.rolls.shape[0])
+        assert self.n > 0, "Empty sequences were found"
+        self.rng = np.random.RandomState(seed)
+        self.order = np.arange(self.n)
+        self.device = device
+        print("Rolls.shape {}".format(tuple(self.rolls.shape)))
+
+    def num_classes(self):
+        return self.n_classes
+
+    def num_tokens(self):
+        return NUM_EVENTS
+
+    def __iter__(self):
+        self.rng.shuffle(self.order)
+        B = self.batch_size
+        for start in range(0, self.n, B):
+            idx = self.order[start:start + B]
+            pad = B - len(idx)
+            if pad > 0:
+                idx = np.concatenate([idx, self.order[:pad]])
+            index = torch.from_numpy(idx.astype(np.int64)).to(self.device, non_blocking=True)
+            roll = self.rolls.index_select(0, index)
+            yield DataBatch([roll, self.classes.index_select(0, index)], [roll], pad)
+
+
 def load_dataset(loader_train: Loader, batch_size: int, split_percentage: float = None, loader_val: Loader = None,
                  device_rows: bool = False):
     """data.py:201-223.  device_rows: build and iterate the rows on the GPU (DeviceMelodyDataset)."""

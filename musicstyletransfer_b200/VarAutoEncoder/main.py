@@ -10,7 +10,7 @@ import torch
 
 from . import model, trainer
 from .config import get_config
-from .data import Loader, ToyData, load_dataset
+from .data import Loader, RollDataset, ToyData, load_dataset
 from .sampler import Sampling
 from .transformer import TransformerConfig
 from .utils import create_directory_if_not_present, log_config, log_model_variables
@@ -104,17 +104,25 @@ def main(argv=None):
     if args.validation_data is not None:
         val_loader = Loader(path=args.validation_data, max_sequence_length=args.max_seq_len,
                             slices_per_quarter_note=args.slices_per_quarter_note)
-    train_dataset, valid_dataset = load_dataset(loader, args.batch_size, args.validation_split, val_loader,
-                                               device_rows=getattr(args, "device_dataset", True))
+    roll_mode = getattr(args, "featurisation", "events") == "roll"
+    if roll_mode:
+        assert args.decoder_type == "lstm", "--featurisation roll uses the LSTM decoder"
+        train_dataset = RollDataset(args.batch_size, args.max_seq_len, loader.melodies, args.slices_per_quarter_note)
+        valid_dataset = (RollDataset(args.batch_size, args.max_seq_len, val_loader.melodies, args.slices_per_quarter_note)
+                         if val_loader is not None else None)
+    else:
+        train_dataset, valid_dataset = load_dataset(loader, args.batch_size, args.validation_split, val_loader,
+                                                    device_rows=getattr(args, "device_dataset", True))
     create_directory_if_not_present(args.model_output)
     if args.out_samples:
         create_directory_if_not_present(args.out_samples)
     cfg = create_model_config(args, train_dataset)
     cfg.save(args.model_output + '/config')
     log_config(cfg)
-    m = model.Model(config=cfg, precision=args.precision, seed=args.seed)
+    m = model.Model(config=cfg, precision=args.precision, seed=args.seed, featurisation="roll" if roll_mode else "events")
     log_model_variables(m)
-    sampler = Sampling(args.model_output, None, None, verbose=args.verbose, model_instance=m)
+    # sampling decodes token events; the piano-roll path trains / validates only
+    sampler = None if roll_mode else Sampling(args.model_output, None, None, verbose=args.verbose, model_instance=m)
     t = trainer.Trainer(config=create_train_config(args), context=None, model=m, sampler=sampler, log_dir=args.log_dir,
                         max_steps=args.max_steps, cuda_graph=getattr(args, "cuda_graph", True))
     t.fit(dataset=train_dataset, validation_dataset=valid_dataset, model_folder=args.model_output, epochs=args.epochs)

@@ -53,10 +53,10 @@ class ModelConfig(Config):
         self.decoder_config = decoder_config
 
 
-def to_engine_config(config: ModelConfig) -> VAEConfig:
+def to_engine_config(config: ModelConfig, featurisation: str = "events") -> VAEConfig:
     e, d = config.encoder_config, config.decoder_config
     et = e.transformer_config
-    kw = dict(vocab=e.input_dim, num_classes=e.num_classes, enc_size=et.model_size, enc_layers=et.num_layers,
+    kw = dict(featurisation=featurisation, vocab=e.input_dim, num_classes=e.num_classes, enc_size=et.model_size, enc_layers=et.num_layers,
               enc_heads=et.num_heads, latent=e.latent_dim, enc_dropout=et.dropout)
     if d.lstm_config is not None:
         kw.update(dec_type="lstm", dec_size=d.lstm_config.hidden_dim, dec_layers=d.lstm_config.n_layers,
@@ -148,7 +148,8 @@ class Decoder(_DecoderBase):
 class Model:
     """model.py:275-296.  ``context`` may be None / 'gpu' / a torch device; there is no CPU context."""
 
-    def __init__(self, config: ModelConfig, context=None, precision="tf32x3f", seed=0, quiet=False, *args, **kwargs):
+    def __init__(self, config: ModelConfig, context=None, precision="tf32x3f", seed=0, quiet=False, featurisation="events",
+                 *args, **kwargs):
         if not quiet:
             print("Creating a model with the following configuration:")
             config.output_to_stream(sys.stdout)
@@ -156,7 +157,7 @@ class Model:
         self.engine_seed = seed                    # --seed: also the seed of initialize() (Trainer._initialize_model)
         device = context if isinstance(context, (torch.device, str)) and str(context).startswith("cuda") else \
             torch.device("cuda", torch.cuda.current_device())
-        self.engine = VAEEngine(to_engine_config(config), device, seed=seed, precision=precision)
+        self.engine = VAEEngine(to_engine_config(config, featurisation), device, seed=seed, precision=precision)
         dcls = LSTMDecoder if config.decoder_config.lstm_config is not None else Decoder
         self.decoder = dcls(config.decoder_config, self.engine)
         self.encoder = Encoder(config.encoder_config, self.engine)

@@ -147,7 +147,33 @@ class Trainer:
         """Data parallelism: rank r takes rows r::world of the global batch (SURVEY.md §8(e))."""
         return t[self.rank::self.world] if self.world > 1 else t
 
+    def _step_roll(self, batch, is_train=True):
+        """Piano-roll batch (data = [roll uint8 [B, S, 128], classes]): BCE reconstruction + KL (--featurisation roll)."""
+        dev = self.engine.device
+        roll = self._shard(batch.data[0]).to(dev).contiguous()
+        classes = to_device_i32(self._shard(batch.data[1]), dev)
+        global_batch = batch.data[0].shape[0]
+        o = self.opt
+        kw = dict(kl_weight=self.config.kl_loss_weight, label_smoothing=self.config.label_smoothing,
+                  downweight=bool(self.config.negative_label_downscaling))
+        if is_train and self.cuda_graph and self.world == 1 and o['beta1'] == 0.9 and o['beta2'] == 0.999 and \
+                o['eps'] == 1e-8 and o['wd'] == 0.0:
+            out = self.engine.train_step_roll_graphed(roll, classes, global_batch=global_batch, lr=o['lr'],
+                                                      clip_gradient=o['clip_gradient'], **kw)
+        else:
+            out = self.engine.forward_roll(roll, classes, train=True, label_smoothing=kw["label_smoothing"],
+                                           downweight=kw["downweight"], want_grad=is_train)
+            if is_train:
+                self.engine.backward_roll(kl_weight=self.config.kl_loss_weight)
+                if self.world > 1:
+                    torch.distributed.all_reduce(self.engine.arena.g)
+                self.engine.adam_step(global_batch, **self.opt)
+        self.metrics.update(out["bce"], out["kl"], self.config.kl_loss_weight)
+        return _LazyLoss(out["bce"], out["kl"], self.config.kl_loss_weight)
+
     def _step(self, batch, is_train=True):
+        if torch.is_tensor(batch.data[0]) and batch.data[0].dtype == torch.uint8 and batch.data[0].dim() == 3:
+            return self._step_roll(batch, is_train)
         dev = self.engine.device
         tokens, seq_lens, classes = [to_device_i32(self._shard(x), dev) for x in batch.data]
         labels = to_device_i32(self._shard(batch.label[0]), dev)

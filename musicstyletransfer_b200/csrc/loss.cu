@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred
   __shared__ float w_sh;
   float npos = 0.f;
   if (cfg.downweight) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) npos += y[i] == 1 ? 1.f : 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) npos += y[i] != 0 ? 1.f : 0.f;
     npos = warp_sum(npos);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = npos;
     __syncthreads();
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float d;
-    acc += bce_elem(x[i], (float)y[i], cfg, w, dpred ? &d : nullptr);
+    acc += bce_elem(x[i], y[i] != 0 ? 1.f : 0.f, cfg, w, dpred ? &d : nullptr);   // label = note sounding (velocity rolls too)
     if (dpred) dpred[(size_t)b * n + i] = d * g;
   }
   acc = warp_sum(acc);

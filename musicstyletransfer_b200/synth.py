@@ -46,3 +46,27 @@ def note_events(n_seq=32768, ev_per_seq=32, seed=0):
     vel[1::2] = 0
     seq_offsets = (np.arange(n_seq + 1, dtype=np.int64) * ev_per_seq).astype(np.int32)
     return dtick, pitch, vel, seq_offsets
+
+
+def midi_files(n_files=512, ev_per_file=2048, seed=3, resolution=120):
+    """Synthetic single-track Standard MIDI Files (bytes) built from note_events(): the input of the end-to-end
+    featurisation leg (.mid bytes -> C++ parser -> K1 -> A2 rows -> train steps).  Returns ([bytes], [class index])."""
+    import struct
+    dtick, pitch, vel, offs = note_events(n_seq=n_files, ev_per_seq=ev_per_file, seed=seed)
+
+    def varlen(v):
+        out = [v & 0x7F]
+        v >>= 7
+        while v:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        return bytes(reversed(out))
+    blobs, classes = [], []
+    for i in range(n_files):
+        body = bytearray(b"\x00\xff\x51\x03\x07\xa1\x20")                      # tempo 120 bpm
+        for e in range(int(offs[i]), int(offs[i + 1])):
+            body += varlen(int(dtick[e])) + bytes([0x90 if vel[e] else 0x80, int(pitch[e]) & 0x7F, int(vel[e]) & 0x7F])
+        body += b"\x01\xff\x2f\x00"
+        blobs.append(b"MThd" + struct.pack(">IHHH", 6, 1, 1, resolution) + b"MTrk" + struct.pack(">I", len(body)) + bytes(body))
+        classes.append(i % 2)
+    return blobs, classes
