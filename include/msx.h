@@ -250,6 +250,11 @@ int msx_embed_dense_fwd(const float* E, const int32_t* classes, const float* cls
 int msx_embed_dense_bwd(const float* dout, const int32_t* classes, float* dE, float* d_cls_emb, int B, int T, int D, float scale,
                         void* stream);
 
+/* out[e] = x[e] * keep(e) / (1 - drop_p) with the step's counter-based masks (seed [+ step counter], site, element): the
+ * dropout between the layers of a stacked LSTM decoder (gluon.rnn.LSTM(dropout=...), model.py:148-153).  The backward is the
+ * same call on the gradient.  n % 4 == 0; in place when out == x. */
+int msx_dropout(const float* x, float* out, long long n, float drop_p, unsigned long long seed, unsigned site, void* stream);
+
 /* K2g — persistent LSTM recurrence.  Replaces the fused gluon.rnn.LSTM call in LSTMDecoder.forward_train
  * (model.py:148-153,179); gx_inout [B,T,4H] holds x W_i2h^T + b_i2h on entry and the gate activations on exit;
  * h0/c0 are rows of a [B, ld0] buffer (model.py:159-167).  Backward turns the saved activations into

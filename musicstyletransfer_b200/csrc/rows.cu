@@ -160,7 +160,35 @@ __global__ void __launch_bounds__(128) rows_gather_kernel(const int* __restrict_
   }
 }
 
+// out[e] = x[e] * keep(e) / (1 - p): the inter-layer dropout of the stacked LSTM decoder (gluon.rnn.LSTM(dropout=...),
+// model.py:148-153); the backward applies the same mask (same seed / site) to the gradient.  In place when out == x.
+__global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* out, long long n4, float p, float inv_keep,
+                                                      unsigned long long seed, const unsigned long long* ctr, unsigned site) {
+  const unsigned long long eff = msx_eff_seed(seed, ctr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    float k[4];
+    dropout_scale4(eff, site, (uint64_t)q, p, inv_keep, k);
+    const float4 v = reinterpret_cast<const float4*>(x)[q];
+    reinterpret_cast<float4*>(out)[q] = make_float4(v.x * k[0], v.y * k[1], v.z * k[2], v.w * k[3]);
+  }
+}
+
 }  // namespace
+
+extern "C" int msx_dropout(const float* x, float* out, long long n, float drop_p, unsigned long long seed, unsigned site,
+                           void* stream) {
+  MSX_REQUIRE(n >= 0 && (n & 3) == 0, "msx_dropout: n must be a non-negative multiple of 4");
+  if (n == 0) return MSX_OK;
+  MSX_REQUIRE(x && out && ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0, "msx_dropout: null or misaligned pointer");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_dropout: dropout probability must be in [0,1)");
+  const long long n4 = n / 4;
+  const long long want = (n4 + 255) / 256;
+  const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
+  dropout_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, n4, drop_p, 1.f / (1.f - drop_p), seed, msx_step_counter(), site);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
 
 extern "C" int msx_rows_plan(const int32_t* n_tokens, const int32_t* class_start, int n_tracks, int n_classes, int max_seq_len,
                              int32_t* row_start, int32_t* dup_row, int32_t* dup_src, int32_t* len_present, void* stream) {

@@ -16,6 +16,7 @@ from . import ops
 
 NUM_EVENTS = 293     # MIDIUtil/defaults.py:58
 N_PITCH, ROLL_IN = 128, 132      # piano-roll width (defaults.py:51-54) and its 16-byte padded GEMM operand width
+LSTM_SITE = 0x400    # dropout sites between the layers of a stacked LSTM decoder: LSTM_SITE + lower layer index
 SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 1: ff hidden, 2: ff out}
 
 
@@ -52,7 +53,7 @@ class VAEConfig:
         if dec_type == "transformer":
             assert dec_size % dec_heads == 0
         else:
-            assert dec_layers == 1, "the fused LSTM path implements n_layers == 1 (scripts/train-vae.sh)"
+            assert dec_layers >= 1 and dec_size in (32, 64, 128), "LSTM decoder: n_layers >= 1, hidden size 32 / 64 / 128"
         self.vocab, self.num_classes = vocab, num_classes
         self.enc_size, self.enc_layers, self.enc_heads = enc_size, enc_layers, enc_heads
         self.latent = latent
@@ -280,12 +281,15 @@ class VAEEngine:
         return self.arena.grad(name)
 
     def _dense_fwd(self, x, ldx, M, name_w, name_b, out, ldo, N, K, relu=False, drop_p=0.0, site=0, accumulate=False,
-                   w=None, b=None, mask_out=None):
+                   w=None, b=None, mask_out=None, decoder=False):
         """mask_out (tensor path only, N % 32 == 0): int32 [M, N/32] bit mask of (out > 0), the ReLU / dropout mask the
-        dgrad of the next layer applies; returns True when it was written."""
+        dgrad of the next layer applies; returns True when it was written.
+        decoder: a GEMM of the LSTM decoder (i2h, output layer).  It only feeds the reconstruction loss, which single-pass
+        TF32 already matches to ~2e-6 (the mean over T x V log-probabilities averages the operand rounding out), so the
+        tf32x3f mode does not spend 3xTF32 on it; the strict fp32x3 mode does."""
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
-        mode = self._gemm_mode(self.x3_fwd, x, ldx, w, K, out, ldo, M, N, K)
+        mode = self._gemm_mode(self.x3_fwd and (self.x3_bwd or not decoder), x, ldx, w, K, out, ldo, M, N, K)
         if mode:
             use_mask = mask_out is not None and N % 32 == 0
             ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
@@ -642,6 +646,7 @@ class VAEEngine:
         The all-rows-emitted-SOS/PAD stop test (:186) is evaluated on the host afterwards, which truncates the
         result exactly where the reference's loop would have stopped.  uniforms: optional fp32 [2T, B]."""
         cfg, dev = self.cfg, self.device
+        assert cfg.dec_type != "lstm" or cfg.dec_layers == 1, "incremental decoding implements the single-layer LSTM decoder"
         B, T = tokens.shape
         Z, V, Hd = cfg.latent, cfg.vocab, cfg.dec_size
         I_max = 2 * T
@@ -758,7 +763,8 @@ class VAEEngine:
         intent of the reference loop, which is inconsistent at HEAD).  Returns (sequences int32 [B*beam, <= 2T],
         scores fp32 [B*beam]); hypotheses of row b are b*beam .. b*beam+beam-1, best first."""
         cfg, dev = self.cfg, self.device
-        assert cfg.dec_type == "lstm", "beam search follows the reference's LSTM-decoder API (sampler.py:222)"
+        assert cfg.dec_type == "lstm" and cfg.dec_layers == 1, \
+            "beam search follows the reference's LSTM-decoder API (sampler.py:222), single layer"
         B, T = tokens.shape
         K, Z, V, Hd = int(beam_size), cfg.latent, cfg.vocab, cfg.dec_size
         I_max, R = 2 * T, B * int(beam_size)
@@ -810,9 +816,10 @@ class VAEEngine:
         return seq[cur][:, :stop + 1].clone(), score[cur].clone()
 
     # ------------------------------------------------------------------ LSTM decoder (model.py:131-203)
-    def _lstm_decoder_fwd(self, bf, xe, z, classes, B, T):
+    def _lstm_decoder_fwd(self, bf, xe, z, classes, B, T, p_drop=0.0):
         """LSTMDecoder.forward_train after the input embedding: initial state latent2hid(z) + class2hid[classes] split into
-        (h0, c0) (model.py:159-167), i2h GEMM for all T steps, persistent recurrence.  xe [B*T, H] -> hs [B*T, H]."""
+        (h0, c0) and shared by every layer (model.py:159-167), then per layer the i2h GEMM for all T steps and the persistent
+        recurrence; dropout between the layers (gluon.rnn.LSTM(dropout=...), model.py:148-153).  xe [B*T, H] -> hs [B*T, H]."""
         cfg, dev = self.cfg, self.device
         Z, Hd = cfg.latent, cfg.dec_size
         M = B * T
@@ -821,43 +828,67 @@ class VAEEngine:
                       2 * Hd, 0, 1.0, cfg.num_classes)
         self._dense_fwd(z, Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
                         accumulate=True)
-        gates = bf.get("dec.gates", (M, 4 * Hd), dev)
-        self._dense_fwd(xe, Hd, M, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias", gates, 4 * Hd,
-                        4 * Hd, Hd)
-        hs = bf.get("dec.hs", (M, Hd), dev)
-        hprev = bf.get("dec.hprev", (M, Hd), dev)
-        cs = bf.get("dec.cs", (M, Hd), dev)
         lstm_fwd = ops.lstm_tc_fwd if self._lstm_tc(Hd, tv) else ops.lstm_fwd
-        lstm_fwd(gates, self._W("decoder.decoder.l0_h2h_weight"), self._W("decoder.decoder.l0_h2h_bias"),
-                 tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
-        return hs
+        x = xe
+        for l in range(cfg.dec_layers):
+            tag = "dec." if l == 0 else "dec.l%d." % l           # layer 0 keeps the single-layer buffer names
+            if l > 0:
+                xin = bf.get(tag + "xin", (M, Hd), dev)          # dropout(h of the layer below): this layer's input
+                if p_drop > 0:
+                    ops.dropout(x, xin, p_drop, self.dropout_seed, LSTM_SITE + l - 1)
+                    x = xin
+                else:
+                    x = x                                        # no dropout: the lower layer's hs is read in place
+            gates = bf.get(tag + "gates", (M, 4 * Hd), dev)
+            self._dense_fwd(x, Hd, M, "decoder.decoder.l%d_i2h_weight" % l, "decoder.decoder.l%d_i2h_bias" % l, gates,
+                            4 * Hd, 4 * Hd, Hd, decoder=True)
+            hs = bf.get(tag + "hs", (M, Hd), dev)
+            hprev = bf.get(tag + "hprev", (M, Hd), dev)
+            cs = bf.get(tag + "cs", (M, Hd), dev)
+            lstm_fwd(gates, self._W("decoder.decoder.l%d_h2h_weight" % l), self._W("decoder.decoder.l%d_h2h_bias" % l),
+                     tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            self._lstm_in = getattr(self, "_lstm_in", {})
+            self._lstm_in[l] = x
+            x = hs
+        return x
 
-    def _lstm_decoder_bwd(self, bf, c, ddec, dz, B, T):
-        """Backward of _lstm_decoder_fwd: ddec [B*T, H] = gradient of the hidden states.  Accumulates the LSTM / latent2hid /
-        class2hid parameter gradients, writes dz, returns the gradient of the decoder input xe."""
+    def _lstm_decoder_bwd(self, bf, c, ddec, dz, B, T, p_drop=0.0):
+        """Backward of _lstm_decoder_fwd: ddec [B*T, H] = gradient of the top layer's hidden states.  Accumulates the LSTM /
+        latent2hid / class2hid parameter gradients, writes dz, returns the gradient of the decoder input xe."""
         cfg, dev = self.cfg, self.device
         Z, Hd = cfg.latent, cfg.dec_size
         M = B * T
-        gates = bf.t[("dec.gates", (M, 4 * Hd), torch.float32)]
-        hprev = bf.t[("dec.hprev", (M, Hd), torch.float32)]
-        cs = bf.t[("dec.cs", (M, Hd), torch.float32)]
-        xe = bf.t[("dec.xe", (M, Hd), torch.float32)]
-        tv = bf.t[("dec.tvec", (B, 2 * Hd), torch.float32)]
+        f32 = torch.float32
+        tv = bf.t[("dec.tvec", (B, 2 * Hd), f32)]
         dtv = bf.get("dec.dtvec", (B, 2 * Hd), dev)
         lstm_bwd = ops.lstm_tc_bwd if self._lstm_tc(Hd, tv) else ops.lstm_bwd
-        lstm_bwd(gates, self._W("decoder.decoder.l0_h2h_weight"), cs, tv[:, Hd:], 2 * Hd, ddec, dtv, dtv[:, Hd:],
-                 B, T, Hd, db_i2h=self._G("decoder.decoder.l0_i2h_bias"),
-                 db_h2h=self._G("decoder.decoder.l0_h2h_bias"))                # gates now hold d(pre-activations)
-        dxe = bf.get("dec.dxe", (M, Hd), dev)
-        self._dense_bwd(gates, 4 * Hd, M, xe, Hd, self._W("decoder.decoder.l0_i2h_weight"),
-                        self._G("decoder.decoder.l0_i2h_weight"), None, 4 * Hd, Hd, dx=dxe, lddx=Hd)
-        self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l0_h2h_weight"), None, 4 * Hd, Hd)
+        dh = ddec
+        for l in reversed(range(cfg.dec_layers)):
+            tag = "dec." if l == 0 else "dec.l%d." % l
+            gates = bf.t[(tag + "gates", (M, 4 * Hd), f32)]
+            hprev = bf.t[(tag + "hprev", (M, Hd), f32)]
+            cs = bf.t[(tag + "cs", (M, Hd), f32)]
+            x_in = self._lstm_in[l]
+            # every layer starts from the same (h0, c0): the top layer writes dtv, the others add theirs
+            dtv_l = dtv if l == cfg.dec_layers - 1 else bf.get(tag + "dtvec", (B, 2 * Hd), dev)
+            lstm_bwd(gates, self._W("decoder.decoder.l%d_h2h_weight" % l), cs, tv[:, Hd:], 2 * Hd, dh, dtv_l, dtv_l[:, Hd:],
+                     B, T, Hd, db_i2h=self._G("decoder.decoder.l%d_i2h_bias" % l),
+                     db_h2h=self._G("decoder.decoder.l%d_h2h_bias" % l))            # gates now hold d(pre-activations)
+            if dtv_l is not dtv:
+                ops.rows_strided(dtv_l, 2 * Hd, dtv, 2 * Hd, B, 2 * Hd, add=True)
+            dx = bf.get(tag + "dxe", (M, Hd), dev)
+            self._dense_bwd(gates, 4 * Hd, M, x_in, Hd, self._W("decoder.decoder.l%d_i2h_weight" % l),
+                            self._G("decoder.decoder.l%d_i2h_weight" % l), None, 4 * Hd, Hd, dx=dx, lddx=Hd)
+            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l%d_h2h_weight" % l), None, 4 * Hd, Hd)
+            if l > 0 and p_drop > 0:
+                ops.dropout(dx, dx, p_drop, self.dropout_seed, LSTM_SITE + l - 1)    # the forward's mask, on the gradient
+            dh = dx
         ops.embed_bwd(c["classes"], None, dtv, self._G("decoder.class2hid.weight"), None, None, B, 1, 2 * Hd, 0, 1.0,
                       cfg.num_classes)
         self._dense_bwd(dtv, 2 * Hd, B, c["z"], Z, self._W("decoder.latent2hid.weight"),
                         self._G("decoder.latent2hid.weight"), self._G("decoder.latent2hid.bias"), 2 * Hd, Z,
                         dx=dz, lddx=Z)
-        return dxe
+        return dh
 
     def _encode_layers_bwd(self, bf, c, dlat, B, T):
         """Backward of _encode_layers: dlat [B, 2Z] -> gradient of the embedded encoder input [B*T, D]."""
@@ -932,7 +963,7 @@ class VAEEngine:
             xe = bf.get("dec.xe", (M, Hd), dev)
             ops.embed_fwd(tokens, None, None, self._W("decoder.embedding.weight"), None, None, None, xe, None, B, T, Hd, 0,
                           1.0, V)
-            hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, T)
+            hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, T, pd_)
             dec_out, Td = hs, T
             dmask = None
         else:
@@ -963,7 +994,7 @@ class VAEEngine:
         Mo = B * Td
         logits = bf.get("logits", (Mo, self.ldv), dev)
         self._dense_fwd(dec_out, Hd, Mo, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V,
-                        Hd)
+                        Hd, decoder=cfg.dec_type == "lstm")
         out = {"kl": kl, "means": lat[:, :Z], "stds": lat[:, Z:], "z": z}
         lab_full = None
         if labels is not None:
@@ -1018,7 +1049,7 @@ class VAEEngine:
                         V, Hd, dx=ddec, lddx=Hd)
         dz = bf.get("dz", (B, Z), dev)
         if cfg.dec_type == "lstm":
-            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, T)
+            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, T, c["pd"])
             ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
         else:
             dxs = c["dxs"]
@@ -1090,7 +1121,8 @@ class VAEEngine:
         ops.reparam_kl_fwd(lat, eps, z, kl, B, Z)
         xe = bf.get("dec.xe", (Ms, Hd), dev)
         self._dense_fwd(rdec, ROLL_IN, Ms, "decoder.roll_embedding.weight", None, xe, Hd, Hd, ROLL_IN)
-        hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, S)
+        pd_ = cfg.dec_dropout if train else 0.0
+        hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, S, pd_)
         logits = bf.get("roll.logits", (Ms, N_PITCH), dev)
         self._dense_fwd(hs, Hd, Ms, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, N_PITCH, N_PITCH, Hd)
         bce = bf.get("roll.bce", (B,), dev)
@@ -1098,7 +1130,7 @@ class VAEEngine:
         ops.bce(logits, roll, bce, None, dlogits, B, S * N_PITCH, from_sigmoid=False, label_smoothing=label_smoothing,
                 downweight=downweight)
         self.ctx = dict(B=B, T=T, S=S, classes=classes, eps=eps, xs=xs, mask=mask, lat=lat, z=z, hs=hs, pe=pe_, bf=bf,
-                        xs16=self._xs16, renc=renc, rdec=rdec, dlogits=dlogits, roll=True)
+                        xs16=self._xs16, renc=renc, rdec=rdec, dlogits=dlogits, roll=True, pd=pd_)
         return {"bce": bce, "ce": bce, "kl": kl, "means": lat[:, :Z], "stds": lat[:, Z:], "z": z, "logits": logits.view(B, S, N_PITCH)}
 
     def backward_roll(self, kl_weight=1.0):
@@ -1116,7 +1148,7 @@ class VAEEngine:
                             self._G("decoder.output_layer.weight"), self._G("decoder.output_layer.bias"), N_PITCH, Hd,
                             dx=ddec, lddx=Hd)
             dz = bf.get("dz", (B, Z), dev)
-            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, S)
+            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, S, c["pd"])
             self._dense_bwd(dxe, Hd, Ms, c["rdec"], ROLL_IN, None, self._G("decoder.roll_embedding.weight"), None, Hd, ROLL_IN)
             dlat = bf.get("dlat", (B, 2 * Z), dev)
             ops.reparam_kl_bwd(c["lat"], c["eps"], dz, None, kl_weight, dlat, B, Z)

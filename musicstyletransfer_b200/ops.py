@@ -134,6 +134,11 @@ def rows_strided(src, ld_src, dst, ld_dst, rows, width, add=False):
              lib.stream_ptr())
 
 
+def dropout(x, out, drop_p, seed, site):
+    """out = x * keep / (1 - p) with the kernels' counter-based mask for (seed, site); in place when out is x."""
+    lib.call("msx_dropout", P(x), P(out), _ll(x.numel()), _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
+
+
 def colsum(X, ld, M, N, out):
     lib.call("msx_colsum", P(X), _i(ld), _ll(M), _i(N), P(out), lib.stream_ptr())
 

@@ -450,3 +450,45 @@ def test_sos_rows_only_top_layer_equals_full_layer(prec, tol, dropout):
         scale = float(full["names"][n].abs().max())
         err = float((full["names"][n] - sos["names"][n]).abs().max())
         assert err <= tol * scale + 1e-5 * gmax, (n, err, scale)
+
+
+@pytest.mark.parametrize("precision,layers,H,dropout", [("fp32", 2, 64, 0.0), ("fp32", 3, 32, 0.3), ("tf32x3f", 2, 128, 0.2),
+                                                        ("fp32x3", 2, 128, 0.0)])
+def test_stacked_lstm_decoder_vs_oracle(precision, layers, H, dropout):
+    """--d-n-layers > 1: gluon.rnn.LSTM(H, n_layers, dropout between layers) with the same (h0, c0) for every layer
+    (model.py:148-153,159-167).  The oracle replays the step with the device's own inter-layer dropout masks."""
+    from musicstyletransfer_b200 import ops
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine, LSTM_SITE
+    cfg_o = om.Cfg(enc_size=64, enc_layers=1, enc_heads=2, latent=32, dec_type="lstm", dec_size=H, dec_layers=layers,
+                   dec_dropout=dropout)
+    p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=5))
+    B, T = 40, 21
+    tokens, seq_lens, classes, labels, eps = _batch(B, T, 293, 2, 32, seed=17, min_len=5)
+    eng = VAEEngine(VAEConfig(enc_size=64, enc_layers=1, enc_heads=2, latent=32, dec_type="lstm", dec_size=H, dec_layers=layers,
+                              dec_dropout=dropout), "cuda:0", precision=precision)
+    assert set(eng.arena.names()) == set(p)
+    eng.arena.load_state(p)
+    out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32), train=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    masks = None
+    if dropout > 0:
+        masks = {}
+        for l in range(layers - 1):
+            m = torch.empty(B * T * H, dtype=torch.uint8, device="cuda:0")
+            ops.dropout_mask(m, dropout, eng.base_seed, LSTM_SITE + l)
+            masks["decoder.decoder.l%d" % l] = m.view(B, T, H).float().cpu()
+    pp = {k: v.clone() for k, v in p.items()}
+    loss, ce, kl, probs, means, stds, grads = om.train_step(cfg_o, pp, om.Adam(pp, clip_gradient=1.0), tokens, seq_lens, classes,
+                                                            labels, eps, masks=masks)
+    tight = precision in ("fp32", "fp32x3")
+    _close("ce", out["ce"], ce, rtol=1e-3 if tight else 2e-3)
+    _close("kl", out["kl"], kl)
+    gscale = max(float(v.abs().max()) for v in grads.values())
+    for name in eng.arena.names():
+        if tight:
+            _grad_close(name, eng.arena.grad(name), grads[name], gscale)
+        else:
+            scale = float(grads[name].abs().max())
+            err = float((eng.arena.grad(name).cpu() - grads[name]).abs().max())
+            assert err <= 5e-2 * scale + 1e-3 * gscale, (name, err, scale)
