@@ -123,7 +123,7 @@ int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B, int ldb, i
 /* Strict-fp32 tensor-core GEMM (the reference step is fp32 end to end, trainer.py:155-179): same contract and epilogues as
  * msx_gemm_tc_ex with fp32 operands, but every operand value is split into hi + lo TF32 parts inside the kernel and a
  * k-block contributes A_lo B_hi + A_hi B_lo + A_hi B_hi ("3xTF32"), fp32 accumulation in TMEM: products carry ~2^-21
- * relative error instead of 2^-11.  cta_group::2 pair tiles only: M > 128 and N >= 64 (msx_gemm_tc_x3_supported; the call
+ * relative error instead of 2^-11.  cta_group::2 pair tiles, any M, N >= 64 (msx_gemm_tc_x3_supported; the call
  * returns MSX_ERR_UNSUPPORTED otherwise and the caller uses msx_gemm_f32).  aux_kind 0 (fp32 matrix) or 2 (bit mask). */
 int msx_gemm_tc_x3_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
                              int K);

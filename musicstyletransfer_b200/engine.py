@@ -870,7 +870,7 @@ class VAEEngine:
             cs = bf.t[(tag + "cs", (M, Hd), f32)]
             x_in = self._lstm_in[l]
             # every layer starts from the same (h0, c0): the top layer writes dtv, the others add theirs
-            dtv_l = dtv if l == cfg.dec_layers - 1 else bf.get(tag + "dtvec", (B, 2 * Hd), dev)
+            dtv_l = dtv if l == cfg.dec_layers - 1 else bf.get("dec.dtvec_l%d" % l, (B, 2 * Hd), dev)
             lstm_bwd(gates, self._W("decoder.decoder.l%d_h2h_weight" % l), cs, tv[:, Hd:], 2 * Hd, dh, dtv_l, dtv_l[:, Hd:],
                      B, T, Hd, db_i2h=self._G("decoder.decoder.l%d_i2h_bias" % l),
                      db_h2h=self._G("decoder.decoder.l%d_h2h_bias" % l))            # gates now hold d(pre-activations)
