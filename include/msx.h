@@ -131,6 +131,16 @@ int msx_gemm_tc_x3(const float* A, int lda, int transA, const float* B, int ldb,
                    int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
                    const void* aux, int ldaux, int aux_kind, float aux_scale, int accumulate, int splitk,
                    float* out_colsum, uint32_t* mask_out, int ldmask, void* stream);
+/* Forward Dense GEMM Y = X W^T (+ bias / ReLU / dropout / ReLU bit mask) with fp32 X [M,K], W [N,K], Y in HBM and "bf16x3"
+ * products: each operand value is split inside the kernel into bf16 hi + lo parts (16 mantissa bits) and a k-step
+ * contributes A_lo B_hi + A_hi B_lo + A_hi B_hi on tcgen05 kind::f16 (twice the TF32 rate: 1.5 single-pass MMAs instead of
+ * the 3 of msx_gemm_tc_x3).  ~2^-17 relative product error instead of TF32's 2^-11.  Any M, N >= 64; accumulate adds into
+ * Y.  Used for the encoder's forward GEMMs (transformer.py:36-40,65-68,88-93,104; model.py:100) in the default mode. */
+int msx_gemm_tc_b3_supported(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int M, int N,
+                             int K);
+int msx_gemm_tc_b3(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                   const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site, int accumulate,
+                   uint32_t* mask_out, int ldmask, void* stream);
 /* dst[i] = bfloat16(src[i]) (round to nearest even), i < n: builds bf16 operands from fp32 tensors (weights shadow,
  * tests).  src and dst 16-byte aligned. */
 int msx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);

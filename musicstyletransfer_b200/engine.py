@@ -20,20 +20,24 @@ LSTM_SITE = 0x400    # dropout sites between the layers of a stacked LSTM decode
 SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 1: ff hidden, 2: ff out}
 
 
-# precision mode -> (single-pass tensor GEMMs, 3xTF32 forward GEMMs, 3xTF32 backward GEMMs, tensor-core attention,
-#                    tensor-core LSTM recurrence).  Storage is fp32 in every mode except the bf16 operand copies of "bf16".
+# precision mode -> (single-pass tensor GEMMs, split of the forward GEMMs' operands, 3xTF32 backward GEMMs, tensor-core
+#                    attention, tensor-core LSTM recurrence).  Storage is fp32 in every mode except the bf16 operand copies of
+#                    "bf16".  Forward split: "x3" = 3xTF32 (msx_gemm_tc_x3, ~2^-21 per product), "b3" = bf16 hi + lo on
+#                    kind::f16 (msx_gemm_tc_b3, ~2^-17 per product at half the tensor time), None = single pass.
 #   fp32      every product exact fp32 on FFMA kernels (reference arithmetic, the slowest)
 #   fp32x3    strict fp32 on the tensor cores: all GEMMs 3xTF32, attention / LSTM exact -> every gradient within 1e-3
-#   tf32x3f   fp32-equivalent FORWARD GEMMs (3xTF32) -> loss / KL / latent means within the north star's 1e-3 with margin;
-#             backward GEMMs, attention and the LSTM recurrence single-pass TF32 (gradients to TF32 accuracy)
+#   tf32x3f   compensated FORWARD: encoder GEMMs 3xTF32, attention scores 3xTF32 -> loss / KL / latent means within the
+#             north star's 1e-3 with 10x margin; backward GEMMs, attention and the LSTM recurrence single-pass TF32
+#   bf16x3f   tf32x3f with the forward encoder GEMMs on the bf16x3 kernel (same forward accuracy class, faster)
 #   tf32      every tensor-core product single-pass TF32
 #   bf16      tf32 with the Transformer layers' GEMM operands stored as bfloat16
 PRECISIONS = {
-    "fp32": (False, False, False, False, False),
-    "fp32x3": (False, True, True, False, False),
-    "tf32x3f": (True, True, False, True, True),
-    "tf32": (True, False, False, True, True),
-    "bf16": (True, False, False, True, True),
+    "fp32": (False, None, False, False, False),
+    "fp32x3": (False, "x3", True, False, False),
+    "tf32x3f": (True, "x3", False, True, True),
+    "bf16x3f": (True, "b3", False, True, True),
+    "tf32": (True, None, False, True, True),
+    "bf16": (True, None, False, True, True),
 }
 
 
@@ -289,12 +293,17 @@ class VAEEngine:
         tf32x3f mode does not spend 3xTF32 on it; the strict fp32x3 mode does."""
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
-        mode = self._gemm_mode(self.x3_fwd and (self.x3_bwd or not decoder), x, ldx, w, K, out, ldo, M, N, K)
+        want = self.x3_fwd if (self.x3_bwd or not decoder) else None
+        mode = self._gemm_mode(want, x, ldx, w, K, out, ldo, M, N, K)
         if mode:
             use_mask = mask_out is not None and N % 32 == 0
-            ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
-                        site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32,
-                        x3=mode == "x3")
+            if mode == "b3":
+                ops.gemm_tc_b3(x, ldx, w, K, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+                               site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32)
+            else:
+                ops.gemm_tc(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
+                            site=site, accumulate=accumulate, mask_out=mask_out if use_mask else None, ldmask=N // 32,
+                            x3=mode == "x3")
             return use_mask
         ops.gemm(x, ldx, 0, w, K, 1, out, ldo, M, N, K, bias=b, relu=relu, drop_p=drop_p, seed=self.dropout_seed,
                  site=site, accumulate=accumulate)
@@ -305,11 +314,14 @@ class VAEEngine:
         return self.lstm_tc and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
 
     def _gemm_mode(self, want_x3, A, lda, B, ldb, C, ldc, M, N, K):
-        """"x3" (3xTF32 on tcgen05), "tc" (single-pass TF32 on tcgen05) or None (exact FFMA kernel) for one GEMM."""
+        """"b3" (bf16x3 on tcgen05, forward form only), "x3" (3xTF32 on tcgen05), "tc" (single-pass TF32 on tcgen05) or None
+        (exact FFMA kernel) for one GEMM.  want_x3: None / False, True or "x3", "b3"."""
         if want_x3:
+            if want_x3 == "b3" and ops.gemm_tc_b3_supported(A, lda, B, ldb, C, ldc, M, N, K):
+                return "b3"
             if ops.gemm_tc_x3_supported(A, lda, B, ldb, C, ldc, M, N, K):
                 return "x3"
-            return None                         # small shapes of a 3xTF32 pass stay exact
+            return None                         # narrow outputs of a compensated pass stay exact
         if self.tensor and ops.gemm_tc_supported(A, lda, B, ldb, C, ldc, M, N, K):
             return "tc"
         return None
@@ -355,7 +367,7 @@ class VAEEngine:
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=self.x3_fwd)
+            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd))
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
             ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:

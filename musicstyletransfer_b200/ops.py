@@ -60,6 +60,22 @@ def _gemm_tc_ex(ab16, A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, bias, re
                  (" aux%d" % ak) if aux is not None else "", " c16" if c16 else "", " mask" if mask_out is not None else "")))
 
 
+def gemm_tc_b3_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
+    return bool(lib.load().msx_gemm_tc_b3_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
+
+
+def gemm_tc_b3(A, lda, B, ldb, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0, accumulate=False,
+               mask_out=None, ldmask=0):
+    """Forward Dense GEMM Cm = A[M,K] @ B[N,K]^T with bf16x3 products (msx_gemm_tc_b3): fp32 in HBM, operands split into
+    bf16 hi + lo inside the kernel, three kind::f16 MMAs per k-step."""
+    nbytes = 4.0 * (M * K + N * K) + M * N * 4.0 * (1 + (1 if accumulate else 0)) + (M * N / 8.0 if mask_out is not None else 0)
+    lib.call("msx_gemm_tc_b3", P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K), P(bias),
+             _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site), _i(1 if accumulate else 0), P(mask_out), _i(ldmask),
+             lib.stream_ptr(),
+             tag=(2.0 * M * N * K, nbytes, "bf16x3 M=%d N=%d K=%d tA=0 tB=1 sk=1%s%s" % (
+                 M, N, K, " acc" if accumulate else "", " mask" if mask_out is not None else "")))
+
+
 def gemm_tc_x3_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
     return bool(lib.load().msx_gemm_tc_x3_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
 

@@ -26,7 +26,7 @@ for B, seed in ((2048, 0), (512, 1), (512, 2), (512, 3)):
         _, ce, kl, _, means, stds = om.step_losses(cfg_o, p, f(tok), f(lens), f(cls), f(lab), eps)
     cases.append((B, seed, p, (tok, lens, cls, lab), eps, ce, kl, means, stds))
 
-modes = [("tf32", {}), ("tf32x3f", {}), ("tf32x3f + exact attention", {"attn_tc": False}), ("fp32x3", {}),
+modes = [("tf32", {}), ("tf32x3f", {}), ("bf16x3f", {}), ("tf32x3f + exact attention", {"attn_tc": False}), ("fp32x3", {}),
          ("fp32x3 + tc attention/lstm", {"attn_tc": True, "lstm_tc": True}), ("fp32", {})]
 for name, over in modes:
     prec = name.split(" ")[0]

@@ -55,10 +55,10 @@ def _engine(precision, params, dropout=0.0, dec_type="lstm", seed=0):
     return eng
 
 
-FWD_TOL = {"tf32x3f": 3e-4, "fp32x3": 1e-4, "tf32": 2.5e-3}
+FWD_TOL = {"tf32x3f": 3e-4, "bf16x3f": 3e-4, "fp32x3": 1e-4, "tf32": 2.5e-3}
 
 
-@pytest.mark.parametrize("precision", ["tf32x3f", "fp32x3", "tf32"])
+@pytest.mark.parametrize("precision", ["tf32x3f", "bf16x3f", "fp32x3", "tf32"])
 @pytest.mark.parametrize("B,seed,conditioned", [(2048, 0, False), (512, 1, False), (512, 2, False), (512, 3, False),
                                                 (512, 1, True), (512, 2, True), (512, 3, True)])
 def test_bench_shape_forward_vs_oracle(precision, B, seed, conditioned):
@@ -89,7 +89,8 @@ def test_bench_shape_forward_vs_oracle(precision, B, seed, conditioned):
         assert tot < tol, tot
 
 
-@pytest.mark.parametrize("precision,gtol,gmean", [("tf32x3f", 5e-2, 2e-2), ("tf32", 5e-2, 2e-2), ("fp32x3", 1e-3, None)])
+@pytest.mark.parametrize("precision,gtol,gmean", [("tf32x3f", 5e-2, 2e-2), ("bf16x3f", 5e-2, 2e-2), ("tf32", 5e-2, 2e-2),
+                                                  ("fp32x3", 1e-3, None)])
 def test_bench_shape_gradients_vs_oracle(precision, gtol, gmean):
     """Every parameter gradient of a B = 512 bench-shaped step (conditioned sigma) against the oracle's autograd."""
     cfg_o = om.Cfg(dec_type="lstm")
@@ -152,7 +153,7 @@ def _device_eps(B, Z, seed):
     return eps.cpu()
 
 
-@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-3), ("tf32x3f", 5e-2), ("tf32", 5e-2), ("fp32x3", 1e-3)])
+@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-3), ("tf32x3f", 5e-2), ("bf16x3f", 5e-2), ("tf32", 5e-2), ("fp32x3", 1e-3)])
 def test_dropout_step_vs_oracle_with_device_masks(precision, gtol):
     """The train step as bench.py runs it (dropout 0.2): the oracle replays the step with the device's own keep masks
     (msx_dropout_mask) and eps (msx_normal_fill) -> losses, latent means and every gradient agree."""
@@ -244,6 +245,57 @@ def test_gemm_tc_at_bench_rows(N, K, tA, tB, what, x3):
     # 3xTF32: what is left is fp32 accumulation order over K terms (measured 2e-6 .. 9e-6)
     assert err < (2e-5 if x3 else 1.5e-3), err
     assert torch.isfinite(C).all()
+
+
+@pytest.mark.parametrize("N,K", [(768, 256), (1024, 256), (256, 1024)])
+def test_gemm_tc_b3_at_bench_rows(N, K):
+    """msx_gemm_tc_b3 (bf16 hi + lo operand split, three kind::f16 MMAs per k-step) on the step's forward shapes at the
+    bench's M = 133 120 rows against float64: ~2^-17 per operand, 30x below single-pass TF32."""
+    from musicstyletransfer_b200 import ops
+    M = 2048 * 65
+    g = torch.Generator(device="cuda").manual_seed(N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.empty(M, N, device="cuda")
+    ops.gemm_tc_b3(A, K, W, K, C, N, M, N, K, bias=bias)
+    torch.cuda.synchronize()
+    rows = torch.cat([torch.arange(0, 4096), torch.arange(M // 2, M // 2 + 2048), torch.arange(M - 4096, M)]).cuda()
+    ref = A[rows].double() @ W.double().t() + bias.double()
+    err = float((C[rows].double() - ref).abs().max() / ref.abs().max())
+    print("bf16x3 M=%d N=%d K=%d: max err / max = %.3e" % (M, N, K, err))
+    assert err < 5e-5, err
+    assert torch.isfinite(C).all()
+
+
+@pytest.mark.parametrize("M,N,K,relu,acc", [(37, 293, 132, False, False), (300, 64, 100, True, False), (2048, 256, 256, False, True),
+                                            (1, 128, 32, False, False), (513, 1024, 160, True, False), (129, 320, 1024, False, False)])
+def test_gemm_tc_b3_shapes_and_epilogues(M, N, K, relu, acc):
+    """Odd numbers of 32-wide k-blocks (the zero-filled half stage), K % 32 != 0, M below one tile, N that pads, ReLU + bit
+    mask, accumulate."""
+    from musicstyletransfer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g)
+    ldc = (N + 3) // 4 * 4
+    C0 = torch.randn(M, ldc, device="cuda", generator=g)
+    C = C0.clone()
+    mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda") if (relu and N % 32 == 0) else None
+    ops.gemm_tc_b3(A, K, W, K, C, ldc, M, N, K, bias=None if acc else bias, relu=relu, accumulate=acc, mask_out=mask,
+                   ldmask=N // 32)
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t()
+    ref = ref + (C0[:, :N].double() if acc else bias.double())
+    if relu:
+        ref = ref.clamp(min=0)
+    err = float((C[:, :N].double() - ref).abs().max() / ref.abs().max())
+    assert err < 5e-5, err
+    if mask is not None:
+        bits = ((mask.view(M, N // 32, 1) >> torch.arange(32, device="cuda").view(1, 1, 32)) & 1).view(M, N).bool()
+        want = ref > 0
+        near = ref.abs() < 1e-4 * ref.abs().max()
+        assert bool(((bits == want) | near).all())
 
 
 @pytest.mark.parametrize("x3", [False, True])
