@@ -429,7 +429,7 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = (const float*)aux; p.ldaux = ldaux;
   p.aux_scale = aux_scale; p.accumulate = accumulate; p.out_colsum = out_colsum; p.c_bf16 = c_bf16; p.aux_bf16 = aux_bf16;
-  p.mask_out = mask_out; p.ldmask = ldmask;
+  p.mask_out = mask_out; p.ldmask = ldmask; p.dbg = 0;
   p.kb_total = msx_ceil_div(K, Op::kBKE);
   // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
   // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)

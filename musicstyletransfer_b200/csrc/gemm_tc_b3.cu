@@ -3,7 +3,7 @@
 // Y = X W^T + b with fp32 X, W, Y in HBM (the gluon.nn.Dense forwards of
 // /root/reference/music_style_transfer/VarAutoEncoder/transformer.py:36-40,65-68,88-93,104 and model.py:100), products to
 // ~2^-17 relative: every fp32 operand value is split inside the kernel into two bfloat16 parts
-//     hi = bf16(x),   lo = bf16(x - hi)            (hi + lo carries 16 mantissa bits)
+//     hi = bf16_trunc(x),   lo = bf16_trunc(x - hi)            (hi + lo carries 16 mantissa bits)
 // and a k-step contributes  A_lo B_hi + A_hi B_lo + A_hi B_hi  on `tcgen05.mma.kind::f16`, which runs at twice the
 // `kind::tf32` rate: the three MMAs cost 1.5 single-pass TF32 MMAs instead of 3 (gemm_tc_x3.cu), and the kernel goes back
 // to being bound by the fp32 operand / result bytes instead of the tensor pipe.  The latent-means error of the whole step
@@ -12,12 +12,13 @@
 //
 // Pipeline per CTA of a cta_group::2 pair (256 x BN2 tiles as in gemm_tc.cu / gemm_tc_x3.cu):
 //   warp 0        TMA producer: raw fp32 k-blocks of 32 (A 128 x 128 B, B BN2/2 x 128 B, SWIZZLE_128B) into a ring of SLOTS;
-//   warps 2..5    CONVERTER: slot (32 k of fp32) -> one half of a 16-bit STAGE (64 k): for row r and output chunk j the two
-//                 fp32 chunks 2j, 2j+1 (at (c ^ r%8) * 16 B of the row) become the hi and lo bf16 chunks at
-//                 ((4 half + j) ^ r%8) * 16 B of the hi / lo tiles — the SWIZZLE_128B K-major layout of a 64-element bf16
-//                 row, written directly; the slot is handed back (sfree), after the second half `fence.proxy.async` and a
-//                 cluster-scope arrive on the leader's conv[stage];
-//   warp 1        MMA issuer (leader CTA): 4 k-steps x 3 tcgen05.mma.cta_group::2.kind::f16 per stage, commit empty[stage];
+//   warps 2..5    CONVERTER: slot (32 k of fp32) -> one UNIT = one half of the 128-byte rows of a 16-bit buffer (a bf16 row of
+//                 the SWIZZLE_128B K-major layout holds 64 k): for row r and output chunk j the two fp32 chunks 2j, 2j+1
+//                 (at (c ^ r%8) * 16 B of the row) become the hi and lo bf16 chunks at ((4 half + j) ^ r%8) * 16 B of the
+//                 hi / lo tiles, written directly in the swizzled layout; the slot is handed back (sfree), then
+//                 `fence.proxy.async` and a cluster-scope arrive on the leader's conv[unit];
+//   warp 1        MMA issuer (leader CTA): per unit 2 k-steps x 3 tcgen05.mma.cta_group::2.kind::f16, commit empty[unit]
+//                 (the two halves of a buffer are independent pipeline stages: one is converted while the other multiplies);
 //   warps 6..13   epilogue (shared with the other tensor GEMMs: bias / ReLU / dropout / ReLU bit mask / TMA store).
 #include "gemm_tc_common.cuh"
 
@@ -28,7 +29,7 @@ namespace {
 constexpr int kConvWarpsB = 4;
 constexpr int kEpiWarpsB = 8;
 constexpr int kThreadsB = 32 * (2 + kConvWarpsB + kEpiWarpsB);
-constexpr int kMaxSlotsB = 4, kStagesB = 2;
+constexpr int kMaxSlotsB = 4, kMaxUnitsB = 4;
 
 template <int BN2>
 struct B3Cfg {
@@ -36,28 +37,39 @@ struct B3Cfg {
   static constexpr int kRows = BM + kBRows;            // operand rows per CTA and k-block (A rows, then B rows)
   static constexpr int kSlot = kRows * 128;            // fp32: 32 k x 4 B = 128 B per row
   static constexpr int kHalf16 = kRows * 128;          // bf16: 64 k x 2 B = 128 B per row; hi tiles (A | B), then lo tiles
-  static constexpr int kStage = 2 * kHalf16;
-  static constexpr int kSlots = BN2 == 256 ? 2 : 4;
+  static constexpr int kStage = 2 * kHalf16;           // one 16-bit BUFFER = 64 k = two pipeline UNITS of 32 k (row halves)
+  static constexpr int kBuffers = BN2 == 256 ? 1 : 2;
+  static constexpr int kUnits = 2 * kBuffers;
+  static constexpr int kSlots = 4;                     // fp32 k-blocks in flight: what hides the TMA round trip
   static constexpr int kTmem = 2 * BN2;
   static constexpr int kChunks = BN2 / 32;
 };
 
 struct __align__(8) BarriersB3 {
-  unsigned long long full[kMaxSlotsB], sfree[kMaxSlotsB], conv[kStagesB], empty[kStagesB], tmem_full[2], tmem_empty[2];
+  unsigned long long full[kMaxSlotsB], sfree[kMaxSlotsB], conv[kMaxUnitsB], empty[kMaxUnitsB], tmem_full[2], tmem_empty[2];
   unsigned tmem_base;
 };
 
-// eight fp32 values (two 16-byte chunks) -> their bf16 hi parts and the bf16 of the remainders
+// eight fp32 values (two 16-byte chunks) -> their bf16 hi parts and the bf16 of the remainders.  Both parts are taken by
+// TRUNCATION (the upper 16 bits of the fp32 word): hi = x & 0xFFFF0000 is exact to subtract, lo = upper half of (x - hi), so
+// the split costs one PRMT per packed pair and two LOP + two FADD per pair instead of four quarter-rate F2F conversions
+// (the converter warps were the pipeline's bottleneck with cvt.rn).  hi + lo then carries 16 mantissa bits truncated:
+// <= 2^-16 relative, one-sided; measured against float64 on the step's shapes it stays below 1e-5 of the output scale.
+__device__ __forceinline__ unsigned hi16_pair(unsigned a, unsigned b) {      // {upper half of b, upper half of a}
+  unsigned r;
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ void split8(const uint4& v0, const uint4& v1, uint4& hi, uint4& lo) {
-  const float x[8] = {__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w),
-                      __uint_as_float(v1.x), __uint_as_float(v1.y), __uint_as_float(v1.z), __uint_as_float(v1.w)};
+  const unsigned x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
   unsigned h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);                       // low half = element 2i, high half = element 2i + 1
-    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
-    const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
-    l[i] = pack_bf16x2(r0, r1);
+    const unsigned a = x[2 * i], b = x[2 * i + 1];
+    h[i] = hi16_pair(a, b);                                              // low half = element 2i, high half = element 2i + 1
+    const float ra = __uint_as_float(a) - __uint_as_float(a & 0xFFFF0000u);
+    const float rb = __uint_as_float(b) - __uint_as_float(b & 0xFFFF0000u);
+    l[i] = hi16_pair(__float_as_uint(ra), __float_as_uint(rb));
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -70,7 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
   using Cfg = B3Cfg<BN2>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stages = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* slots = stages + kStagesB * Cfg::kStage;
+  unsigned char* slots = stages + Cfg::kBuffers * Cfg::kStage;
   unsigned char* stage_out = slots + Cfg::kSlots * Cfg::kSlot;                   // [kEpiWarpsB][32 rows][128 B]
   BarriersB3* bars = reinterpret_cast<BarriersB3*>(stage_out + kEpiWarpsB * kOutBoxBytes);
 
@@ -82,7 +94,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kSlots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->sfree[s], kConvWarpsB); }
-    for (int s = 0; s < kStagesB; ++s) { mbar_init(&bars->conv[s], 2 * kConvWarpsB); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < Cfg::kUnits; ++s) { mbar_init(&bars->conv[s], 2 * kConvWarpsB); mbar_init(&bars->empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 2 * kEpiWarpsB); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -129,7 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
       const unsigned long long ad0 = make_desc(smem_u32(stages), 16, 1024, 2);
       const unsigned long long bd0 = make_desc(smem_u32(stages) + BM * 128, 16, 1024, 2);
       constexpr unsigned long long kLo = (unsigned long long)(Cfg::kHalf16 >> 4);
-      int stage = 0;
+      int unit = 0;
       unsigned phase = 0;
       int local = 0;
       for (int it = pair; it < items; it += npairs, ++local) {
@@ -140,24 +152,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
         mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned tmem_d = tmem_base + buf * BN2;
-        for (int kb = kb0; kb < kb1; kb += 2) {
-          mbar_wait_cluster(&bars->conv[stage], phase);          // both CTAs' 16-bit tiles written and fenced
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_cluster(&bars->conv[unit], phase);           // both CTAs' 16-bit half rows written and fenced
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned long long ad = ad0 + (unsigned long long)(stage * (Cfg::kStage >> 4));
-          const unsigned long long bd = bd0 + (unsigned long long)(stage * (Cfg::kStage >> 4));
+          // unit -> buffer unit / 2, row half unit % 2: the half's two k-steps sit 64 B into the 128 B swizzle row
+          const unsigned long long off = (unsigned long long)((unit >> 1) * (Cfg::kStage >> 4) + (unit & 1) * 4);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                         // 16 bf16 of k = 32 B per step inside the 128 B swizzle row
-              const unsigned long long a = ad + 2 * k, b = bd + 2 * k;
+            for (int k = 0; k < 2; ++k) {                         // 16 bf16 of k = 32 B per step
+              const unsigned long long a = ad0 + off + 2 * k, b = bd0 + off + 2 * k;
               umma_ss_pair<true>(tmem_d, a + kLo, b, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // A_lo B_hi
               umma_ss_pair<true>(tmem_d, a, b + kLo, idesc, 1u);                               // A_hi B_lo
               umma_ss_pair<true>(tmem_d, a, b, idesc, 1u);                                     // A_hi B_hi
             }
-            umma_commit_pair(&bars->empty[stage]);
-            if (kb + 2 >= kb1) umma_commit_pair(&bars->tmem_full[buf]);
+            umma_commit_pair(&bars->empty[unit]);
+            if (kb == kb1 - 1) umma_commit_pair(&bars->tmem_full[buf]);
           }
           __syncwarp();
-          if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+          if (++unit == Cfg::kUnits) { unit = 0; phase ^= 1; }
         }
       }
     }
@@ -165,48 +177,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
     // ================================ converter (both CTAs) ================================
     const int ctid = threadIdx.x - 64;                    // 0 .. 127
     const unsigned conv_leader = mapa_shared(smem_u32(&bars->conv[0]), 0);
-    int slot = 0, stage = 0;
-    unsigned sphase = 0, stphase = 0;
+    int slot = 0, unit = 0;
+    unsigned sphase = 0, uphase = 0;
     for (int it = pair; it < items; it += npairs) {
       const int ks = it / (p.n_tiles * p.m_tiles);
       const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      for (int kb = kb0; kb < kb1; kb += 2) {
-        mbar_wait(&bars->empty[stage], stphase ^ 1);      // the MMAs that read this stage's previous contents have retired
-        unsigned char* hi_t = stages + stage * Cfg::kStage;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bars->empty[unit], uphase ^ 1);        // the MMAs that read this unit's previous contents have retired
+        mbar_wait(&bars->full[slot], sphase);             // this CTA's fp32 k-block has landed
+        unsigned char* hi_t = stages + (unit >> 1) * Cfg::kStage;
         unsigned char* lo_t = hi_t + Cfg::kHalf16;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (kb + half < kb1) {
-            mbar_wait(&bars->full[slot], sphase);         // this CTA's fp32 k-block has landed
-            const unsigned char* src = slots + slot * Cfg::kSlot;
+        const unsigned char* src = slots + slot * Cfg::kSlot;
+        const int half = unit & 1;
 #pragma unroll 2
-            for (int i = ctid; i < Cfg::kRows * 4; i += 32 * kConvWarpsB) {
-              const int r = i >> 2, j = i & 3, sw = r & 7;
-              const uint4 v0 = *reinterpret_cast<const uint4*>(src + r * 128 + (((2 * j) ^ sw) << 4));
-              const uint4 v1 = *reinterpret_cast<const uint4*>(src + r * 128 + (((2 * j + 1) ^ sw) << 4));
-              uint4 h, l;
-              split8(v0, v1, h, l);
-              const int off = r * 128 + (((4 * half + j) ^ sw) << 4);
-              *reinterpret_cast<uint4*>(hi_t + off) = h;
-              *reinterpret_cast<uint4*>(lo_t + off) = l;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->sfree[slot]);       // this warp's reads of the slot are done
-            if (++slot == Cfg::kSlots) { slot = 0; sphase ^= 1; }
-          } else {                                        // odd number of k-blocks: the missing half multiplies as zero
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = ctid; i < Cfg::kRows * 4; i += 32 * kConvWarpsB) {
-              const int r = i >> 2, j = i & 3;
-              const int off = r * 128 + (((4 * half + j) ^ (r & 7)) << 4);
-              *reinterpret_cast<uint4*>(hi_t + off) = z;
-              *reinterpret_cast<uint4*>(lo_t + off) = z;
-            }
-          }
+        for (int i = ctid; i < Cfg::kRows * 4; i += 32 * kConvWarpsB) {
+          const int r = i >> 2, j = i & 3, sw = r & 7;
+          const uint4 v0 = *reinterpret_cast<const uint4*>(src + r * 128 + (((2 * j) ^ sw) << 4));
+          const uint4 v1 = *reinterpret_cast<const uint4*>(src + r * 128 + (((2 * j + 1) ^ sw) << 4));
+          uint4 h, l;
+          split8(v0, v1, h, l);
+          const int off = r * 128 + (((4 * half + j) ^ sw) << 4);
+          *reinterpret_cast<uint4*>(hi_t + off) = h;
+          *reinterpret_cast<uint4*>(lo_t + off) = l;
         }
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+        // generic-proxy writes of this thread -> visible to the async proxy (the tensor core's operand reads, also the
+        // ones the pair leader issues against this CTA's shared memory).  The .shared::cta form is a FENCE.VIEW.ASYNC.S; the
+        // unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU + CCTL.IVALL + ERRBAR per stage (ncu source page: ~12 %
+        // of all stall samples and an L1 invalidation per stage)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(conv_leader + (unsigned)(stage * sizeof(unsigned long long)));
-        if (++stage == kStagesB) { stage = 0; stphase ^= 1; }
+        if (lane == 0) {
+          mbar_arrive(&bars->sfree[slot]);                // this warp's reads of the slot are done
+          mbar_arrive_cluster(conv_leader + (unsigned)(unit * sizeof(unsigned long long)));
+        }
+        if (++slot == Cfg::kSlots) { slot = 0; sphase ^= 1; }
+        if (++unit == Cfg::kUnits) { unit = 0; uphase ^= 1; }
       }
     }
   } else {
@@ -257,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
 
 template <int BN2>
 constexpr size_t b3_smem_bytes() {
-  return 1024 + (size_t)kStagesB * B3Cfg<BN2>::kStage + (size_t)B3Cfg<BN2>::kSlots * B3Cfg<BN2>::kSlot +
+  return 1024 + (size_t)B3Cfg<BN2>::kBuffers * B3Cfg<BN2>::kStage + (size_t)B3Cfg<BN2>::kSlots * B3Cfg<BN2>::kSlot +
          (size_t)kEpiWarpsB * kOutBoxBytes + sizeof(BarriersB3);
 }
 
@@ -310,6 +315,7 @@ extern "C" int msx_gemm_tc_b3(const float* A, int lda, const float* B, int ldb, 
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = nullptr; p.ldaux = 0; p.aux_scale = 1.f;
   p.accumulate = accumulate; p.out_colsum = nullptr; p.c_bf16 = 0; p.aux_bf16 = 0; p.mask_out = mask_out; p.ldmask = ldmask;
+  p.dbg = 0;
   p.kb_total = msx_ceil_div(K, 32);
   p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2);
   p.kb_per_split = p.kb_total;

@@ -47,6 +47,7 @@ struct TcParams {
   int c_bf16;          // C is bf16 [M, ldc] (plain store only); the staging box is 32 rows x 64 B, SWIZZLE_64B
   int aux_bf16;        // aux storage: 0 fp32 [M, ldaux], 1 bf16 [M, ldaux], 2 bit mask uint32 [M, ldaux words] (bit j of word
                        // [m, n / 32] <=> element [m, n] > 0, n = 32 * (n / 32) + j), as written through mask_out
+  int dbg;             // experiments only (MSX_X3_DEBUG): 1 = converter skips its work, 2 = one MMA per k-step instead of three
   unsigned* mask_out;  // optional: bit mask of (C > 0) after the epilogue, [M, ldmask words]; needs N % 32 == 0
   int ldmask;
 };

@@ -164,6 +164,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const unsigned long long a = ad + kAStep * k, b = bd + kBStep * k;
+              if (p.dbg & 2) {
+                umma_ss_pair<false>(tmem_d, a, b, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                continue;
+              }
               umma_ss_pair<false>(tmem_d, a + kLo, b, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // A_lo B_hi
               umma_ss_pair<false>(tmem_d, a, b + kLo, idesc, 1u);                               // A_hi B_lo
               umma_ss_pair<false>(tmem_d, a, b, idesc, 1u);                                     // A_hi B_hi
@@ -190,11 +194,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
         const uint4* hi = reinterpret_cast<const uint4*>(ring + stage * Cfg::kStage);
         uint4* lo = reinterpret_cast<uint4*>(ring + stage * Cfg::kStage + Cfg::kHi);
 #pragma unroll 4
-        for (int i = ctid; i < Cfg::kHi / 16; i += 32 * kConvWarps) {
+        for (int i = ctid; i < ((p.dbg & 1) ? 0 : Cfg::kHi / 16); i += 32 * kConvWarps) {
           const uint4 v = hi[i];
           lo[i] = make_uint4(lo_tf32(v.x), lo_tf32(v.y), lo_tf32(v.z), lo_tf32(v.w));
         }
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+        // generic-proxy writes of this thread -> visible to the async proxy (the tensor core's operand reads, also the
+        // ones the pair leader issues against this CTA's shared memory).  The .shared::cta form is a FENCE.VIEW.ASYNC.S; the
+        // unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU + CCTL.IVALL + ERRBAR per stage (ncu source page: ~12 %
+        // of all stall samples and an L1 invalidation per stage)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(conv_leader + (unsigned)(stage * sizeof(unsigned long long)));
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -306,7 +314,8 @@ extern "C" int msx_gemm_tc_x3(const float* A, int lda, int transA, const float* 
   }
   // tile width: the one that pads N the least (N = 293: three 128-wide tiles, not two 256-wide ones)
   const int pad256 = msx_ceil_div(N, 256) * 256, pad128 = msx_ceil_div(N, 128) * 128;
-  const int bn2 = (N > 128 && pad256 <= pad128) ? 256 : 128;
+  static const int force_bn = [] { const char* e = getenv("MSX_X3_BN"); return e ? atoi(e) : 0; }();
+  const int bn2 = force_bn == 128 ? 128 : (N > 128 && pad256 <= pad128) ? 256 : 128;
   CUtensorMap ta, tb, tc;
   int rc = make_map(&tc, C, M, N, ldc, 32, 32, false, kMapC32);
   if (rc) return rc;
@@ -320,6 +329,8 @@ extern "C" int msx_gemm_tc_x3(const float* A, int lda, int transA, const float* 
   p.seed = seed; p.seed_ctr = msx_step_counter(); p.site = site; p.aux = (const float*)aux; p.ldaux = ldaux;
   p.aux_scale = aux_scale; p.accumulate = accumulate; p.out_colsum = out_colsum; p.c_bf16 = 0; p.aux_bf16 = aux_kind;
   p.mask_out = mask_out; p.ldmask = ldmask;
+  static const int dbg = [] { const char* e = getenv("MSX_X3_DEBUG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   p.kb_total = msx_ceil_div(K, Op::kBKE);
   p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2);
   if (splitk > 1) {                         // about two waves of pairs, as in msx_gemm_tc

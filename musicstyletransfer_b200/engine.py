@@ -239,6 +239,7 @@ class VAEEngine:
         # backward pass (`x3_fwd`, `x3_bwd`: msx_gemm_tc_x3, fp32-equivalent products; shapes the pair tiles do not cover
         # fall back to msx_gemm_f32), tensor-core attention / LSTM recurrence (`attn_tc`, `lstm_tc`) or the exact FFMA ones.
         self.tensor, self.x3_fwd, self.x3_bwd, self.attn_tc, self.lstm_tc = PRECISIONS[precision]
+        self.x3_skip = ()                        # diagnostic: substrings of GEMM names that stay single-pass
         # The encoder output is read at position 0 only (model.py:97-100), so in the top encoder layer everything after the
         # attention is computed for the B SOS rows instead of all B*T rows: same losses, same gradients (the other rows'
         # outputs have no consumer and their gradients are exactly zero), ~30 % less GEMM / LayerNorm work per step.
@@ -285,7 +286,7 @@ class VAEEngine:
         return self.arena.grad(name)
 
     def _dense_fwd(self, x, ldx, M, name_w, name_b, out, ldo, N, K, relu=False, drop_p=0.0, site=0, accumulate=False,
-                   w=None, b=None, mask_out=None, decoder=False):
+                   w=None, b=None, mask_out=None, decoder=False, gemm_name=None):
         """mask_out (tensor path only, N % 32 == 0): int32 [M, N/32] bit mask of (out > 0), the ReLU / dropout mask the
         dgrad of the next layer applies; returns True when it was written.
         decoder: a GEMM of the LSTM decoder (i2h, output layer).  It only feeds the reconstruction loss, which single-pass
@@ -294,6 +295,8 @@ class VAEEngine:
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
         want = self.x3_fwd if (self.x3_bwd or not decoder) else None
+        if want and self.x3_skip and any(k in (gemm_name or name_w or "") for k in self.x3_skip):
+            want = None                          # diagnostic: this GEMM single-pass (profiles/micro/diag_x3_sites.py)
         mode = self._gemm_mode(want, x, ldx, w, K, out, ldo, M, N, K)
         if mode:
             use_mask = mask_out is not None and N % 32 == 0
@@ -364,7 +367,7 @@ class VAEEngine:
         qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
-        self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv)
+        self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv, gemm_name=prefix + "qkv")
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd))

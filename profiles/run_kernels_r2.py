@@ -22,6 +22,8 @@ for N, K in ((768, 256), (1024, 256), (256, 1024)):
     for x3 in (True, False):
         for _ in range(2):
             ops.gemm_tc(a, K, 0, w, K, 1, y, N, M, N, K, bias=b, x3=x3)
+    for _ in range(2):
+        ops.gemm_tc_b3(a, K, w, K, y, N, M, N, K, bias=b)
 torch.cuda.synchronize()
 B, T, H, dh = 2048, 65, 8, 32
 qkv = torch.randn(B * T, 3 * H * dh, device=dev)
