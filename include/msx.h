@@ -155,6 +155,14 @@ int msx_attention_fwd(const float* qkv, const float* mask, float* ctx, int B, in
 int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
                       int dh, void* stream);
 
+/* Any row length (--max-seq-len is a free flag, VarAutoEncoder/config.py:36): key-tiled exact-fp32 kernels that keep nothing
+ * larger than a 32 x 32 tile on chip; the context / the dQ part of dqkv are accumulated with atomics over the key tiles
+ * (both outputs are zero-filled by the call).  msx_attention_fwd / _bwd route here when T x T does not fit one SM's shared
+ * memory (T > ~180 at d_h = 32); the engine uses them for T > 384, beyond the tcgen05 kernels.  d_h <= 64, B * H <= 65535. */
+int msx_attention_tiled_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
+int msx_attention_tiled_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
+                            int dh, void* stream);
+
 /* Tensor-core attention (same contract, d_h == 32 and T <= 128): S = K Q^T and O = P^T V on tcgen05, keys on the TMEM
  * lanes so the query-axis softmax is thread-local. */
 int msx_attention_tc_supported(const float* qkv, int T, int dh);

@@ -296,10 +296,19 @@ int dispatch_attn(bool bwd, const float* qkv, const float* mask, const float* dc
 
 }  // namespace
 
+extern "C" int msx_attention_tiled_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
+                                       void* stream);
+extern "C" int msx_attention_tiled_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T,
+                                       int H, int dh, void* stream);
+
+// rows whose T x T score matrix does not fit one SM's shared memory go to the key-tiled kernel (attention_tiled.cu)
+static bool fits_one_cta(int T, int dh, bool bwd) { return attn_smem_floats(T, dh, bwd) * sizeof(float) <= 227 * 1024; }
+
 extern "C" int msx_attention_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh,
                                  void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_fwd: null pointer");
   MSX_REQUIRE(B > 0 && T > 0 && H > 0, "msx_attention_fwd: bad shape");
+  if (!fits_one_cta(T, dh, false)) return msx_attention_tiled_fwd(qkv, mask, ctx, B, T, H, dh, stream);
   return dispatch_attn(false, qkv, mask, nullptr, ctx, B, T, H, dh, (cudaStream_t)stream);
 }
 
@@ -307,5 +316,6 @@ extern "C" int msx_attention_bwd(const float* qkv, const float* mask, const floa
                                  int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_bwd: null pointer");
   MSX_REQUIRE(B > 0 && T > 0 && H > 0, "msx_attention_bwd: bad shape");
+  if (!fits_one_cta(T, dh, true)) return msx_attention_tiled_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, stream);
   return dispatch_attn(true, qkv, mask, dctx, dqkv, B, T, H, dh, (cudaStream_t)stream);
 }

@@ -479,11 +479,14 @@ class VAEEngine:
         """bf16 GEMM operands need 16-byte aligned rows (D % 8) and the vectorised LayerNorm path (D % 128)."""
         return self.bf16 and D % 128 == 0
 
-    def _tf_layer_fwd16(self, bf, tag, prefix, x_in, x_in16, mask, B, T, D, H, p, site0, decoder):
+    def _tf_layer_fwd16(self, bf, tag, prefix, x_in, x_in16, mask, B, T, D, H, p, site0, decoder, sos_only=False):
         """_tf_layer_fwd with bf16 GEMM operands: x_in16 / ctx / x1 / the FF hidden activation are read by the GEMMs as
         bfloat16 (the hidden activation and the context exist only in bf16), weights come from the bf16 shadow arena;
-        qkv, the projection output, f and the LayerNorm arithmetic stay fp32.  Returns (out fp32, out bf16)."""
+        qkv, the projection output, f and the LayerNorm arithmetic stay fp32.  sos_only: as in _tf_layer_fwd, everything
+        after the attention runs on the B SOS rows.  Returns (out fp32, out bf16)."""
         M = B * T
+        R = B if sos_only else M
+        ldr = T * D if sos_only else D
         dev, a, b16 = self.device, self.arena, torch.bfloat16
         seed = self.dropout_seed
         qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
@@ -499,30 +502,35 @@ class VAEEngine:
             ctx = bf.get(tag + "ctx", (M, D), dev)
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.cast_bf16(ctx, ctx16)
+        if sos_only:
+            xres = bf.get(tag + "xin_c", (B, D), dev)
+            ops.rows_strided(x_in, T * D, xres, D, B, D)
+        else:
+            xres = x_in
         # the projection output and f feed only their LayerNorm (forward + backward): bf16 when LayerNorm reads x and y
         # separately (encoder); the decoder's ln3(f + drop(f)) aliases x and y and keeps f fp32
-        proj = bf.get(tag + "proj16", (M, D), dev, b16)
-        ops.gemm_tc_bf16(ctx16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 1, proj, D, M, D, D,
+        proj = bf.get(tag + "proj16", (R, D), dev, b16)
+        ops.gemm_tc_bf16(ctx16, ldr, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 1, proj, D, R, D, D,
                          bias=self._W(prefix + "self_attention.W_proj.bias"))
-        x1 = bf.get(tag + "x1", (M, D), dev)
-        x1h = bf.get(tag + "x1_16", (M, D), dev, b16)
-        st1 = bf.get(tag + "st1", (2, M), dev)
-        ops.add_ln_fwd(x_in, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], M, D,
+        x1 = bf.get(tag + "x1", (R, D), dev)
+        x1h = bf.get(tag + "x1_16", (R, D), dev, b16)
+        st1 = bf.get(tag + "st1", (2, R), dev)
+        ops.add_ln_fwd(xres, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], R, D,
                        drop_p=p, seed=seed, site=site0, out16=x1h)
-        h16 = bf.get(tag + "h16", (M, 4 * D), dev, b16)
-        hmask = bf.get(tag + "hmask", (M, 4 * D // 32), dev, torch.int32)     # ReLU / dropout bit mask for the FF2 dgrad
-        ops.gemm_tc_bf16(x1h, D, 0, a.view16(prefix + "ff.ff1.weight"), D, 1, h16, 4 * D, M, 4 * D, D,
+        h16 = bf.get(tag + "h16", (R, 4 * D), dev, b16)
+        hmask = bf.get(tag + "hmask", (R, 4 * D // 32), dev, torch.int32)     # ReLU / dropout bit mask for the FF2 dgrad
+        ops.gemm_tc_bf16(x1h, D, 0, a.view16(prefix + "ff.ff1.weight"), D, 1, h16, 4 * D, R, 4 * D, D,
                          bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1,
                          mask_out=hmask, ldmask=4 * D // 32)
-        f = bf.get(tag + "f", (M, D), dev) if decoder else bf.get(tag + "f16", (M, D), dev, b16)
-        ops.gemm_tc_bf16(h16, 4 * D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 1, f, D, M, D, 4 * D,
+        f = bf.get(tag + "f", (R, D), dev) if decoder else bf.get(tag + "f16", (R, D), dev, b16)
+        ops.gemm_tc_bf16(h16, 4 * D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 1, f, D, R, D, 4 * D,
                          bias=self._W(prefix + "ff.ff2.bias"))
-        out = bf.get(tag + "out", (M, D), dev)
-        out16 = bf.get(tag + "out16", (M, D), dev, b16)
-        st2 = bf.get(tag + "st2", (2, M), dev)
+        out = bf.get(tag + "out", (R, D), dev)
+        out16 = bf.get(tag + "out16", (R, D), dev, b16)
+        st2 = bf.get(tag + "st2", (2, R), dev)
         ln2 = "ln3" if decoder else "ln2"
         ops.add_ln_fwd(f if decoder else x1, f, self._W(prefix + ln2 + ".gamma"), self._W(prefix + ln2 + ".beta"), out,
-                       st2[0], st2[1], M, D, drop_p=p, seed=seed, site=site0 + 2, out16=out16)
+                       st2[0], st2[1], R, D, drop_p=p, seed=seed, site=site0 + 2, out16=out16)
         return out, out16
 
     def _wgrad16(self, dy16, lddy, x16, ldx, gw, N, K, M):
@@ -530,50 +538,55 @@ class VAEEngine:
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
         ops.gemm_tc_bf16(dy16, lddy, 1, x16, ldx, 0, gw, K, N, K, M, splitk=sk)
 
-    def _tf_layer_bwd16(self, bf, tag, prefix, x_in, x_in16, mask, dout, dx_in, B, T, D, H, p, site0, decoder):
+    def _tf_layer_bwd16(self, bf, tag, prefix, x_in, x_in16, mask, dout, dx_in, B, T, D, H, p, site0, decoder, sos_only=False):
         """Backward of _tf_layer_fwd16.  Every gradient that only feeds GEMMs (d f, d hidden, d proj, d qkv) is produced
         directly as bfloat16 by the kernel that computes it (LayerNorm backward, dgrad epilogue, attention backward);
-        the residual-stream gradients and all parameter gradients are fp32."""
+        the residual-stream gradients and all parameter gradients are fp32.  sos_only: dout is [B, D] (see _tf_layer_bwd)."""
         M = B * T
+        R = B if sos_only else M
+        ldr = T * D if sos_only else D
         dev, a, b16, f32 = self.device, self.arena, torch.bfloat16, torch.float32
         seed = self.dropout_seed
-        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj16", (M, D), b16)]
+        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj16", (R, D), b16)]
         ctx16 = bf.t[(tag + "ctx16", (M, D), b16)]
-        x1, x1h = bf.t[(tag + "x1", (M, D), f32)], bf.t[(tag + "x1_16", (M, D), b16)]
-        st1, st2 = bf.t[(tag + "st1", (2, M), f32)], bf.t[(tag + "st2", (2, M), f32)]
-        h16 = bf.t[(tag + "h16", (M, 4 * D), b16)]
-        f = bf.t[(tag + "f", (M, D), f32)] if decoder else bf.t[(tag + "f16", (M, D), b16)]
+        x1, x1h = bf.t[(tag + "x1", (R, D), f32)], bf.t[(tag + "x1_16", (R, D), b16)]
+        st1, st2 = bf.t[(tag + "st1", (2, R), f32)], bf.t[(tag + "st2", (2, R), f32)]
+        h16 = bf.t[(tag + "h16", (R, 4 * D), b16)]
+        f = bf.t[(tag + "f", (R, D), f32)] if decoder else bf.t[(tag + "f16", (R, D), b16)]
+        xres = bf.t[(tag + "xin_c", (B, D), f32)] if sos_only else x_in
         inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
         ln2 = "ln3" if decoder else "ln2"
-        dx1 = bf.get(tag + "dx1", (M, D), dev)
-        df16 = bf.get(tag + "df16", (M, D), dev, b16)
+        dx1 = bf.get(tag + "dx1", (R, D), dev)
+        df16 = bf.get(tag + "df16", (R, D), dev, b16)
         if decoder:
-            dfull = bf.get(tag + "df", (M, D), dev)
+            dfull = bf.get(tag + "df", (R, D), dev)
             ops.add_ln_bwd(f, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dfull, None,
-                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p, seed=seed,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), R, D, drop_p=p, seed=seed,
                            site=site0 + 2, fuse_xy=True, dybias=self._G(prefix + "ff.ff2.bias"), dy16=df16)
         else:
             ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, None,
-                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), M, D, drop_p=p, seed=seed,
+                           self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), R, D, drop_p=p, seed=seed,
                            site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"), dy16=df16)
         # ff2: f = h W2^T + b2
-        self._wgrad16(df16, D, h16, 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, M)
-        dh16 = bf.get(tag + "dh16", (M, 4 * D), dev, b16)
-        ops.gemm_tc_bf16(df16, D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 0, dh16, 4 * D, M, 4 * D, D,
-                         aux=bf.t[(tag + "hmask", (M, 4 * D // 32), torch.int32)], ldaux=4 * D // 32, aux_scale=inv_keep,
+        self._wgrad16(df16, D, h16, 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, R)
+        dh16 = bf.get(tag + "dh16", (R, 4 * D), dev, b16)
+        ops.gemm_tc_bf16(df16, D, 0, a.view16(prefix + "ff.ff2.weight"), 4 * D, 0, dh16, 4 * D, R, 4 * D, D,
+                         aux=bf.t[(tag + "hmask", (R, 4 * D // 32), torch.int32)], ldaux=4 * D // 32, aux_scale=inv_keep,
                          out_colsum=self._G(prefix + "ff.ff1.bias"))
         # ff1: h = drop(relu(x1 W1^T + b1)); dh16 holds d(pre-activation)
-        self._wgrad16(dh16, 4 * D, x1h, D, self._G(prefix + "ff.ff1.weight"), 4 * D, D, M)
-        ops.gemm_tc_bf16(dh16, 4 * D, 0, a.view16(prefix + "ff.ff1.weight"), D, 0, dx1, D, M, D, 4 * D,
+        self._wgrad16(dh16, 4 * D, x1h, D, self._G(prefix + "ff.ff1.weight"), 4 * D, D, R)
+        ops.gemm_tc_bf16(dh16, 4 * D, 0, a.view16(prefix + "ff.ff1.weight"), D, 0, dx1, D, R, D, 4 * D,
                          accumulate=not decoder)
-        # ln1(x_in + drop(proj))
-        dproj16 = bf.get(tag + "dproj16", (M, D), dev, b16)
-        ops.add_ln_bwd(x_in, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dx_in, None,
-                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), M, D, drop_p=p, seed=seed, site=site0,
+        # ln1(x_in + drop(proj)); sos_only: the residual gradient of the B rows is added to dx_in at the end
+        dres = bf.get(tag + "dxin_c", (B, D), dev) if sos_only else dx_in
+        dproj16 = bf.get(tag + "dproj16", (R, D), dev, b16)
+        ops.add_ln_bwd(xres, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dres, None,
+                       self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), R, D, drop_p=p, seed=seed, site=site0,
                        dybias=self._G(prefix + "self_attention.W_proj.bias"), dy16=dproj16)
-        self._wgrad16(dproj16, D, ctx16, D, self._G(prefix + "self_attention.W_proj.weight"), D, D, M)
-        dctx = bf.get(tag + "dctx", (M, D), dev)
-        ops.gemm_tc_bf16(dproj16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 0, dctx, D, M, D, D)
+        self._wgrad16(dproj16, D, ctx16, ldr, self._G(prefix + "self_attention.W_proj.weight"), D, D, R)
+        # sos_only: only rows b*T of the context gradient are non-zero; they are written into a buffer zero-filled once
+        dctx = bf.get_zero(tag + "dctx_sos", (M, D), dev) if sos_only else bf.get(tag + "dctx", (M, D), dev)
+        ops.gemm_tc_bf16(dproj16, D, 0, a.view16(prefix + "self_attention.W_proj.weight"), D, 0, dctx, ldr, R, D, D)
         dqkv16 = bf.get(tag + "dqkv16", (M, 3 * D), dev, b16)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
         if ops.attention_tc_supported(qkv, T, D // H):
@@ -589,7 +602,9 @@ class VAEEngine:
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         self._wgrad16(dqkv16, 3 * D, x_in16, D, gwqkv, 3 * D, D, M)
         wqkv = a.span16(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
-        ops.gemm_tc_bf16(dqkv16, 3 * D, 0, wqkv, D, 0, dx_in, D, M, D, 3 * D, accumulate=True)
+        ops.gemm_tc_bf16(dqkv16, 3 * D, 0, wqkv, D, 0, dx_in, D, M, D, 3 * D, accumulate=not sos_only)
+        if sos_only:
+            ops.rows_strided(dres, D, dx_in, T * D, B, D, add=True)
 
     # ------------------------------------------------------------------ encoder
     def _encode(self, bf, tokens, classes, B, T, p_drop):
@@ -619,7 +634,7 @@ class VAEEngine:
         for l in range(cfg.enc_layers):
             if l16:
                 x, x16 = self._tf_layer_fwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
-                                              cfg.enc_heads, p_drop, l * SITE_STRIDE, False)
+                                              cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
                 self._xs16.append(x16)
             else:
                 x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
@@ -633,7 +648,7 @@ class VAEEngine:
 
     def _sos_only(self, l):
         """Encoder layer l is the top layer and runs its row-wise part on the SOS rows only (see _tf_layer_fwd)."""
-        return self.sos_rows_only and l == self.cfg.enc_layers - 1 and not self._layer16_ok(self.cfg.enc_size)
+        return self.sos_rows_only and l == self.cfg.enc_layers - 1
 
     def decoder_initial_state(self, classes, z):
         """latent2hid(z) + class2hid[classes] (model.py:160 / :231): [B, 2H] for the LSTM decoder, [B, D_d] else."""
@@ -925,7 +940,8 @@ class VAEEngine:
             dnext = bf.get("enc%d.dxin" % l, (M, D), dev)
             if self._layer16_ok(D):
                 self._tf_layer_bwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["xs16"][l], c["mask"], dx,
-                                     dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False)
+                                     dnext, B, T, D, cfg.enc_heads, c["pe"], l * SITE_STRIDE, False,
+                                     sos_only=self._sos_only(l))
             else:
                 self._tf_layer_bwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, xs[l], c["mask"], dx, dnext, B, T, D,
                                    cfg.enc_heads, c["pe"], l * SITE_STRIDE, False, sos_only=self._sos_only(l))

@@ -169,6 +169,14 @@ def attention_fwd(qkv, mask, ctx, B, T, H, dh):
     lib.call("msx_attention_fwd", P(qkv), P(mask), P(ctx), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
+def attention_tiled_fwd(qkv, mask, ctx, B, T, H, dh):
+    lib.call("msx_attention_tiled_fwd", P(qkv), P(mask), P(ctx), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
+def attention_tiled_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
+    lib.call("msx_attention_tiled_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+
+
 def attention_tc_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tc_supported(P(qkv), _i(T), _i(dh)))
 

@@ -170,3 +170,31 @@ def test_attention_tc_half_heads(B, T, H, out16):
     assert err < (1e-2 if out16 else 5e-3), err
     wb = wg.sum(0)
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
+
+
+@pytest.mark.parametrize("B,T,H,dh", [(2, 400, 2, 32), (3, 513, 2, 32), (2, 65, 3, 32), (5, 33, 2, 16), (2, 1, 2, 32), (1, 700, 1, 64),
+                                      (2, 200, 4, 8)])
+def test_attention_tiled_any_length(B, T, H, dh):
+    """Key-tiled exact-fp32 attention (attention_tiled.cu): forward and dqkv vs float64 / autograd for rows beyond every other
+    kernel's limit (T = 400, 513, 700) and, for cross-checking, lengths the one-CTA kernel takes as well."""
+    from musicstyletransfer_b200 import ops
+    qkv, mask = _inputs(B, T, H, dh, seed=T + dh)
+    g = torch.Generator().manual_seed(T)
+    dctx = torch.randn(B * T, H * dh, generator=g)
+    x = qkv.double().requires_grad_(True)
+    want = _ref_fwd(x, mask, B, T, H, dh)
+    (want * dctx.double()).sum().backward()
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    ctx = torch.full((B * T, H * dh), 7.0, device="cuda")
+    ops.attention_tiled_fwd(qd, md, ctx, B, T, H, dh)
+    out = torch.full_like(qd, 7.0)
+    ops.attention_tiled_bwd(qd, md, dd, out, B, T, H, dh)
+    torch.cuda.synchronize()
+    ef = float((ctx.double().cpu() - want.detach()).abs().max()) / float(want.abs().max())
+    eb = float((out.double().cpu() - x.grad).abs().max()) / float(x.grad.abs().max())
+    assert ef < 1e-5 and eb < 1e-4, (ef, eb)
+    if T > 384:                      # the generic entry points route long rows to the tiled kernels
+        ctx2 = torch.empty_like(ctx)
+        ops.attention_fwd(qd, md, ctx2, B, T, H, dh)
+        torch.cuda.synchronize()
+        assert float((ctx2 - ctx).abs().max()) <= 1e-5 * float(ctx.abs().max())
