@@ -676,7 +676,6 @@ class VAEEngine:
         The all-rows-emitted-SOS/PAD stop test (:186) is evaluated on the host afterwards, which truncates the
         result exactly where the reference's loop would have stopped.  uniforms: optional fp32 [2T, B]."""
         cfg, dev = self.cfg, self.device
-        assert cfg.dec_type != "lstm" or cfg.dec_layers == 1, "incremental decoding implements the single-layer LSTM decoder"
         B, T = tokens.shape
         Z, V, Hd = cfg.latent, cfg.vocab, cfg.dec_size
         I_max = 2 * T
@@ -698,26 +697,33 @@ class VAEEngine:
                           2 * Hd, 0, 1.0, cfg.num_classes)
             self._dense_fwd(lat, 2 * Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
                             accumulate=True)
-            hb = [bf.get("st.h%d" % i, (B, Hd), dev) for i in range(2)]
-            cb = [bf.get("st.c%d" % i, (B, Hd), dev) for i in range(2)]
+            NL = cfg.dec_layers
+            hb = [[bf.get("st.h%d_%d" % (l, i), (B, Hd), dev) for i in range(2)] for l in range(NL)]
+            cb = [[bf.get("st.c%d_%d" % (l, i), (B, Hd), dev) for i in range(2)] for l in range(NL)]
             hp = bf.get("st.hprev", (B, Hd), dev)
-            xe = bf.get("st.xe", (B, Hd), dev)
             gates = bf.get("st.gates", (B, 4 * Hd), dev)
-            h, c, ld0 = tv, tv[:, Hd:], 2 * Hd
+            # every layer starts from the same (h0, c0) = the two halves of tv (model.py:159-167)
+            state = [(tv, tv[:, Hd:], 2 * Hd) for _ in range(NL)]
             # embedding lookup + i2h Dense of a step (model.py:192-195) = a lookup into the [V, 4H] table
             # emb W_i2h^T + b_i2h, computed once per call: one gather per step instead of a gather and a GEMM
             tab = bf.get("st.i2h_table", (V, 4 * Hd), dev)
             self._dense_fwd(W("decoder.embedding.weight"), Hd, V, "decoder.decoder.l0_i2h_weight",
-                            "decoder.decoder.l0_i2h_bias", tab, 4 * Hd, 4 * Hd, Hd)
+                            "decoder.decoder.l0_i2h_bias", tab, 4 * Hd, 4 * Hd, Hd, decoder=True)
             for i in range(1, I_max):
-                ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, B, 1, 4 * Hd, 0, 1.0, V)
-                # one recurrence step; the tensor-core kernel (W_h2h as mma fragments in registers) in the tensor modes
-                step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
-                step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h, c, ld0,
-                     hb[i & 1], hp, cb[i & 1], B, 1, Hd)                                      # model.py:195
-                h, c, ld0 = hb[i & 1], cb[i & 1], Hd
-                self._dense_fwd(h, Hd, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv,
-                                V, Hd)                                                        # model.py:198
+                for l in range(NL):
+                    if l == 0:
+                        ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, B, 1, 4 * Hd, 0, 1.0, V)
+                    else:                                       # input of layer l = h of the layer below (no dropout at inference)
+                        self._dense_fwd(state[l - 1][0], state[l - 1][2], B, "decoder.decoder.l%d_i2h_weight" % l,
+                                        "decoder.decoder.l%d_i2h_bias" % l, gates, 4 * Hd, 4 * Hd, Hd, decoder=True)
+                    h, c, ld0 = state[l]
+                    # one recurrence step; the tensor-core kernel (W_h2h as mma fragments in registers) in the tensor modes
+                    step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, ld0, h, c)) else ops.lstm_fwd
+                    step(gates, W("decoder.decoder.l%d_h2h_weight" % l), W("decoder.decoder.l%d_h2h_bias" % l), h, c, ld0,
+                         hb[l][i & 1], hp, cb[l][i & 1], B, 1, Hd)                            # model.py:195
+                    state[l] = (hb[l][i & 1], cb[l][i & 1], Hd)
+                self._dense_fwd(state[NL - 1][0], Hd, B, "decoder.output_layer.weight", "decoder.output_layer.bias", logits,
+                                self.ldv, V, Hd, decoder=True)                                # model.py:198
                 ops.sample_multinomial(logits, self.ldv, V, u_at(i), seed, i, nxt, score, seqs, I_max, i, B)
         else:
             D = Hd

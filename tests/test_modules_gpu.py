@@ -92,11 +92,13 @@ def test_loader_tokenises_midi_files_like_the_reference_reader(golden_dir, tmp_p
     assert np.array_equal(ds.tokens, tok) and np.array_equal(ds.labels, lab) and np.array_equal(ds.classes, cls)
 
 
-@pytest.mark.parametrize("dec_type", ["lstm", "transformer"])
-def test_style_transfer_matches_oracle(dec_type):
-    """A12: class swap before encoding, z = means, autoregressive multinomial sampling with shared uniforms."""
+@pytest.mark.parametrize("dec_type,dec_layers", [("lstm", 1), ("transformer", 1), ("lstm", 2)])
+def test_style_transfer_matches_oracle(dec_type, dec_layers):
+    """A12: class swap before encoding, z = means, autoregressive multinomial sampling with shared uniforms (also with a
+    stacked LSTM decoder: --d-n-layers 2)."""
     from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
-    cfg_o = om.Cfg(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type=dec_type, dec_size=32, dec_heads=4)
+    cfg_o = om.Cfg(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type=dec_type, dec_size=32, dec_heads=4,
+                   dec_layers=dec_layers)
     p = om.init_params(cfg_o, seed=5)
     gen = torch.Generator().manual_seed(3)
     for k in p:
@@ -115,7 +117,7 @@ def test_style_transfer_matches_oracle(dec_type):
     else:
         want = om.style_transfer_transformer(cfg_o, p, tokens, target, u)
     eng = VAEEngine(VAEConfig(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type=dec_type, dec_size=32,
-                              dec_heads=4), DEV)
+                              dec_heads=4, dec_layers=dec_layers), DEV)
     eng.arena.load_state(p)
     i32 = lambda t: t.to(torch.int32).to(DEV)
     seqs, score = eng.style_transfer(i32(tokens), i32(lens), i32(target), uniforms=u.to(DEV))
