@@ -95,7 +95,11 @@ __global__ void __launch_bounds__(128 * G, 1)
   unsigned char* sQ = sK + slab;                           // [TQ rows][128 B] K-major SW128
   unsigned char* sV = sQ + TQ * 128;                       // 2 x [TK rows][128 B] MN-major (d contiguous), SW128_32B
   unsigned char* sP = sV + 2 * slab;                       // ceil(TQ/32) slabs x [TK rows][128 B] MN-major (q contiguous)
-  unsigned char* sKQlo = sP + ((TQ + 31) / 32) * slab;     // X3: lo parts of K | Q, same layout as [sK, sQ + TQ rows)
+  // X3: lo parts of K | Q, same layout as [sK, sQ + TQ rows).  They live only from the conversion to the retirement of MMA 1,
+  // P only from the softmax to the retirement of MMA 2 (and the staged output store): the two share the P region when it
+  // is large enough (TQ >= 2 * 32 rows of slabs: always for the rows this kernel is used on), so the compensated scores
+  // cost no pipeline group.
+  unsigned char* sKQlo = (((TQ + 31) / 32) * slab >= (TK + TQ) * 128) ? sP : sP + ((TQ + 31) / 32) * slab;
   unsigned long long* bar_kq = &bars_all[g][0];
   unsigned long long* bar_v = &bars_all[g][1];
   unsigned long long* bar_s = &bars_all[g][3];
@@ -166,19 +170,24 @@ __global__ void __launch_bounds__(128 * G, 1)
     const unsigned par = (unsigned)(n & 1);
     const float mraw = mraw_next;                          // key-padding mask of this item (prefetched one item ahead)
     if (gt < T && nxt < p.items) mraw_next = __ldg(p.mask + (size_t)(nxt / p.H) * T + gt);
+    if (X3) {
+      // lo tiles of K | Q (contiguous [TK + TQ rows][128 B]), written by all four warps of the group: one warp alone took
+      // ~1.4 us per item for the 19 KB (38 dependent LDS -> cvt -> STS rounds), which sat on every item's critical path
+      mbar_wait(bar_kq, par);
+      const uint4* src = reinterpret_cast<const uint4*>(sK);
+      uint4* dst = reinterpret_cast<uint4*>(sKQlo);
+      const int n16 = (TK + TQ) * 8;
+#pragma unroll 2
+      for (int i = gt; i < n16; i += 128) {
+        const uint4 v = src[i];
+        dst[i] = make_uint4(lo_tf32_bits(v.x), lo_tf32_bits(v.y), lo_tf32_bits(v.z), lo_tf32_bits(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      group_sync(g);
+    }
     if (issuer) {                                          // whole warp, warp-uniform control flow
       const int b2 = nxt / p.H, h2 = nxt % p.H;
-      mbar_wait(bar_kq, par);
-      if (X3) {                                            // lo tiles of K | Q (contiguous [TK + TQ rows][128 B])
-        const uint4* src = reinterpret_cast<const uint4*>(sK);
-        uint4* dst = reinterpret_cast<uint4*>(sKQlo);
-        for (int i = lane; i < (TK + TQ) * 8; i += 32) {
-          const uint4 v = src[i];
-          dst[i] = make_uint4(lo_tf32_bits(v.x), lo_tf32_bits(v.y), lo_tf32_bits(v.z), lo_tf32_bits(v.w));
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-      }
+      if (!X3) mbar_wait(bar_kq, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         // MMA 1: S[128 keys x TQ] = K[128 x 32] * Q[TQ x 32]^T, both K-major (+32 B per K = 8 step)
@@ -865,8 +874,9 @@ extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, voi
   p.items = B * H;
   p.inv_scale = 1.f / sqrtf((float)dh);
   // per group: K [TK] + Q [TQ] + 2 x V [TK] + P [ceil(TQ/32) slabs x TK] rows of 128 B, every tile 1024-byte aligned
-  //            (+ the lo parts of K and Q for compensated scores)
-  p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK + (x3_scores ? p.TK + p.TQ : 0)) * 128;
+  //            (+ the lo parts of K and Q for compensated scores when they do not fit into the P region, which they share)
+  const bool lo_in_p = ((p.TQ + 31) / 32) * p.TK >= p.TK + p.TQ;
+  p.group_bytes = (3 * p.TK + p.TQ + ((p.TQ + 31) / 32) * p.TK + ((x3_scores && !lo_in_p) ? p.TK + p.TQ : 0)) * 128;
   const long long rows = (long long)B * T;
   CUtensorMap tk, tq, tv;
   int rc;
@@ -874,14 +884,14 @@ extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, voi
   if ((rc = make_map(&tq, qkv, rows, 3 * D, 3 * D, DH, p.TQ, false, x3_scores != 0))) return rc;
   if ((rc = make_map(&tv, qkv, rows, 3 * D, 3 * D, DH, p.TK, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x3_scores) {                           // the lo tiles cost a pipeline group at the longer rows
+  if (x3_scores) {                           // same group counts: the lo tiles share the P region (short rows: they are tiny)
     switch (p.TQ / 16) {
       case 1: return launch_fwd<1, 3, true>(tk, tq, tv, p, st);
       case 2: return launch_fwd<2, 3, true>(tk, tq, tv, p, st);
       case 3: return launch_fwd<3, 3, true>(tk, tq, tv, p, st);
-      case 4: return launch_fwd<4, 2, true>(tk, tq, tv, p, st);
-      case 5: return launch_fwd<5, 2, true>(tk, tq, tv, p, st);
-      case 6: return launch_fwd<6, 1, true>(tk, tq, tv, p, st);
+      case 4: return launch_fwd<4, 3, true>(tk, tq, tv, p, st);
+      case 5: return launch_fwd<5, 3, true>(tk, tq, tv, p, st);
+      case 6: return launch_fwd<6, 2, true>(tk, tq, tv, p, st);
       case 7: return launch_fwd<7, 1, true>(tk, tq, tv, p, st);
       default: return launch_fwd<8, 1, true>(tk, tq, tv, p, st);
     }
