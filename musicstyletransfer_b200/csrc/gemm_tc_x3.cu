@@ -12,13 +12,14 @@
 // epilogue through swizzled staging boxes + TMA store / reduce-add) plus one stage in the pipeline:
 //   warp 0        TMA producer.  Operands are loaded as FLOAT32 (no rounding in the TMA unit), each CTA's bytes complete
 //                 on its OWN full[s] barrier;
-//   warps 2..5    CONVERTER (both CTAs): wait full[s], read the stage's hi region (raw fp32 tiles in the swizzled layout
+//   warps 2..9    CONVERTER (both CTAs; 8 warps: the LDS -> cvt -> STS rounds are latency-bound per warp, 4 warps measured
+//                 6 % slower): wait full[s], read the stage's hi region (raw fp32 tiles in the swizzled layout
 //                 TMA wrote), write lo = rna_tf32(x - trunc_tf32(x)) at the same offsets of the stage's lo region — the
 //                 split is element-wise, so the swizzle is preserved without being decoded — then fence.proxy.async and
 //                 arrive (cluster scope) on the leader's conv[s];
 //   warp 1        MMA issuer (leader): waits conv[s], issues 3 x 4 tcgen05.mma.cta_group::2.kind::tf32, commits empty[s]
 //                 to both CTAs;
-//   warps 6..13   epilogue (8 warps, one staging box each).
+//   warps 10..17  epilogue (8 warps, one staging box each).
 // Shared memory per stage: hi (A 16 KB + B BN2/2 x 128 B) + the same again for lo; 3 stages (BN2 = 256) or 4 (BN2 = 128).
 // The kernel is tensor-pipe bound (3 MMAs per operand byte), which also hides the converter: per stage it moves 64 KB
 // through shared memory while the 12 MMAs take ~1536 cycles.
@@ -28,7 +29,10 @@ using namespace msx_tc;
 
 namespace {
 
-constexpr int kConvWarps = 4;
+#ifndef MSX_X3_CONV_WARPS
+#define MSX_X3_CONV_WARPS 8
+#endif
+constexpr int kConvWarps = MSX_X3_CONV_WARPS;
 constexpr int kEpiWarpsX3 = 8;
 constexpr int kThreadsX3 = 32 * (2 + kConvWarps + kEpiWarpsX3);
 constexpr int kMaxStagesX3 = 4;
@@ -182,7 +186,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
     }
   } else if (warp < 2 + kConvWarps) {
     // ================================ converter (both CTAs): lo tiles of every stage ================================
-    const int ctid = threadIdx.x - 64;                    // 0 .. 127
+    const int ctid = threadIdx.x - 64;                    // 0 .. 32 * kConvWarps - 1
     const unsigned conv_leader = mapa_shared(smem_u32(&bars->conv[0]), 0);
     int stage = 0;
     unsigned phase = 0;
