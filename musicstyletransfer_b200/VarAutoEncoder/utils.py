@@ -30,9 +30,30 @@ def save_object(object, output_path: str):
         pickle.dump(object, file)
 
 
+class _TrainStateUnpickler(pickle.Unpickler):
+    """train_state.pkl sits in a model folder that may come from somewhere else: only the training-state class of this
+    package (or the reference's module path for it) and plain scalars may be constructed, nothing else is importable."""
+
+    _ALLOWED = {("musicstyletransfer_b200.VarAutoEncoder.trainer", "TrainingState"),
+                ("music_style_transfer.VarAutoEncoder.trainer", "TrainingState"),
+                ("VarAutoEncoder.trainer", "TrainingState")}
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            from . import trainer
+            return trainer.TrainingState
+        if module == "numpy" and name in ("float64", "float32", "dtype"):
+            import numpy
+            return getattr(numpy, name)
+        if (module, name) in (("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar")):
+            import numpy
+            return numpy.core.multiarray.scalar if hasattr(numpy, "core") else numpy._core.multiarray.scalar
+        raise pickle.UnpicklingError("train state files may only hold a TrainingState (found %s.%s)" % (module, name))
+
+
 def load_object(path: str):
     with open(path, "rb") as file:
-        return pickle.load(file)
+        return _TrainStateUnpickler(file).load()
 
 
 def load_model_parameters(model, path: str, context=None):

@@ -213,3 +213,38 @@ def test_cli_accepts_bf16_precision():
     got = cfgmod.get_config(["--precision", "bf16"])
     args = got[0] if isinstance(got, tuple) else got
     assert args.precision == "bf16"
+
+
+def test_model_folder_files_are_data_not_code(tmp_path):
+    """a model folder may come from somewhere else.  `config` is loaded with a SafeLoader that only knows the
+    registered Config classes, `train_state.pkl` with an unpickler that only constructs TrainingState."""
+    import os
+    import pickle
+    from musicstyletransfer_b200.VarAutoEncoder import trainer, utils
+    from musicstyletransfer_b200.VarAutoEncoder.config import Config
+    import yaml
+    (tmp_path / "config").write_text("!!python/object/apply:os.system ['echo pwned']\n")
+    with pytest.raises(yaml.YAMLError):
+        Config.load(str(tmp_path / "config"))
+    st = trainer.TrainingState()
+    st.n_batches, st.best_resconstruction_loss = 7, np.float64(1.5)
+    utils.save_object(st, str(tmp_path / "train_state.pkl"))
+    back = utils.load_object(str(tmp_path / "train_state.pkl"))
+    assert back.n_batches == 7 and float(back.best_resconstruction_loss) == 1.5
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("echo pwned",))
+    with open(tmp_path / "evil.pkl", "wb") as f:
+        pickle.dump(Evil(), f)
+    with pytest.raises(pickle.UnpicklingError):
+        utils.load_object(str(tmp_path / "evil.pkl"))
+
+
+def test_seed_flag_changes_initial_weights_signature():
+    """Model(seed=...) must reach initialize(); checked on the host through the stored attribute (the arena
+    itself needs a GPU: tests/test_modules_gpu.py)."""
+    import inspect
+    from musicstyletransfer_b200.VarAutoEncoder import model
+    src = inspect.getsource(model.Model)
+    assert "self.engine_seed = seed" in src and "engine_seed = 0" not in src
