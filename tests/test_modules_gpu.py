@@ -273,3 +273,18 @@ def test_trainer_graph_replay_matches_eager(tmp_path):
     assert float(a[-1].mean()) < float(a[0].mean())
     # dropout is on in the toy config? the eps draw differs per step but follows the same seed sequence in both runs
     assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max())
+
+
+def test_seed_flag_reaches_the_initial_weights():
+    """`--seed` -> Model(seed=...) -> Trainer._initialize_model: different seeds give different parameters, the
+    same seed the same ones."""
+    from musicstyletransfer_b200.VarAutoEncoder import main as vmain
+    from musicstyletransfer_b200.VarAutoEncoder import model, trainer
+    from musicstyletransfer_b200.VarAutoEncoder.data import ToyData
+    cfg = vmain.create_toy_model_config(ToyData())
+    ws = []
+    for seed in (0, 1, 1):
+        m = model.Model(config=cfg, precision="fp32", seed=seed, quiet=True)
+        trainer.Trainer(config=vmain.create_toy_train_config(), context=None, model=m, sampler=None)
+        ws.append(m.engine.arena.w.clone())
+    assert float((ws[0] - ws[1]).abs().max()) > 1e-3 and torch.equal(ws[1], ws[2])
