@@ -230,6 +230,10 @@ int msx_rows_gather_batch(const int32_t* tokens, const int32_t* labels, const in
                           const int32_t* index, int batch, int ld, int t_out, int32_t* b_tokens, int32_t* b_labels,
                           int32_t* b_classes, int32_t* b_seq_lens, void* stream);
 
+/* out[b, 0] = PAD, out[b, 1 + t] = labels[b, t]: labels for the Transformer decoder's rows, which carry the latent prefix
+ * position in front (model.py:244-253). */
+int msx_prefix_labels(const int32_t* labels, int32_t* out, int B, int T, void* stream);
+
 /* Strided row copy (add = 0) / accumulate (add = 1): out[r, :width] (+)= in[r, :width], row r of X at X + r * ldX.  The
  * encoder output is only read at the SOS position (model.py:97-100), so the top encoder layer runs on one row per sequence
  * after its attention; this moves those rows between the [B*T, D] and [B, D] layouts.  width, ld % 4 == 0. */

@@ -174,7 +174,25 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* out
   }
 }
 
+// labels of the Transformer decoder: its rows carry the latent prefix position in front (model.py:244-253 drops it again
+// after the layers), which never has a target: out[b, 0] = PAD, out[b, 1 + t] = labels[b, t]
+__global__ void __launch_bounds__(256) prefix_labels_kernel(const int* __restrict__ labels, int* __restrict__ out, int B, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * (T + 1)) return;
+  const int b = (int)(i / (T + 1)), t = (int)(i % (T + 1));
+  out[i] = t == 0 ? kPad : labels[(long long)b * T + t - 1];
+}
+
 }  // namespace
+
+extern "C" int msx_prefix_labels(const int32_t* labels, int32_t* out, int B, int T, void* stream) {
+  MSX_REQUIRE(B >= 0 && T >= 1, "msx_prefix_labels: bad sizes");
+  if (B == 0) return MSX_OK;
+  MSX_REQUIRE(labels && out, "msx_prefix_labels: null pointer");
+  prefix_labels_kernel<<<msx_ceil_div((long long)B * (T + 1), 256), 256, 0, (cudaStream_t)stream>>>(labels, out, B, T);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
 
 extern "C" int msx_dropout(const float* x, float* out, long long n, float drop_p, unsigned long long seed, unsigned site,
                            void* stream) {

@@ -1037,8 +1037,7 @@ class VAEEngine:
         if labels is not None:
             if cfg.dec_type == "transformer":
                 lab_full = bf.get("labels_full", (B, Td), dev, torch.int32)
-                lab_full[:, 0] = 0
-                lab_full[:, 1:] = labels
+                ops.prefix_labels(labels, lab_full, B, T)
             else:
                 lab_full = labels
             ce = bf.get("ce", (B,), dev)

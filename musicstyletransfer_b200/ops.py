@@ -144,6 +144,10 @@ def dropout_mask(out, drop_p, seed, site):
     lib.call("msx_dropout_mask", P(out), _ll(out.numel()), _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
 
 
+def prefix_labels(labels, out, B, T):
+    lib.call("msx_prefix_labels", P(labels), P(out), _i(B), _i(T), lib.stream_ptr())
+
+
 def rows_strided(src, ld_src, dst, ld_dst, rows, width, add=False):
     """dst[r, :width] (+)= src[r, :width] with row strides ld_src / ld_dst (elements)."""
     lib.call("msx_rows_strided", P(src), _ll(ld_src), P(dst), _ll(ld_dst), _i(rows), _i(width), _i(1 if add else 0),
