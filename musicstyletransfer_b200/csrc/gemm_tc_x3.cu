@@ -83,7 +83,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->conv[s], 2 * kConvWarps);
+      mbar_init(&bars->conv[s], 2);                 // one arrival per CTA of the pair (after the converter warps' own barrier)
       mbar_init(&bars->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 2 * kEpiWarpsX3); }
@@ -207,8 +207,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
         // unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU + CCTL.IVALL + ERRBAR per stage (ncu source page: ~12 %
         // of all stall samples and an L1 invalidation per stage)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(conv_leader + (unsigned)(stage * sizeof(unsigned long long)));
+        // the converter warps meet on a named barrier and ONE thread signals the pair leader: 2 cluster-scope arrivals per
+        // stage instead of 16 (each remote release-arrive is a DSMEM round trip on the stage's critical path)
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
+        if (ctid == 0) mbar_arrive_cluster(conv_leader + (unsigned)(stage * sizeof(unsigned long long)));
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
