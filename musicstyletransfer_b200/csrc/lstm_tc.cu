@@ -10,7 +10,8 @@
 //   * h_{t-1} (forward) / d(pre-activation) (backward) sit in shared memory in A-fragment order: one LDS.128
 //     yields the four A registers of an MMA;
 //   * a warp's accumulator tile holds all four gates of the same (row, unit) cells, so the cell update is
-//     thread-local; the new h goes to both CTAs' fragment buffers through DSMEM, one cluster barrier per step.
+//     thread-local; the new h goes to both CTAs' fragment buffers: local st.shared + st.async into the peer, completion
+//     counted on an mbarrier in the receiver (no cluster barrier on the recurrence, see the helpers below).
 // Why mma.sync and not tcgen05: UMMA needs M >= 64 batch rows (or the gates on the M axis with a 4-CTA weight
 // split); with B = 2048 that leaves 16-32 CTAs busy.  mma.sync.m16n8k8.tf32 measured 480 FMA/clk/SM on B200
 // (profiles/micro/mma_sync_rate.cu), 3.75x the FFMA pipe, and lets 128 CTAs share the work.
@@ -44,10 +45,50 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// split cluster barrier: the release of `arrive` only has to cover the shared-memory / DSMEM writes issued before it,
-// so the global stores of a step are issued between arrive and wait and drain during the next step's MMAs
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// Per-step exchange between the two CTAs of a cluster WITHOUT a cluster barrier: the halves of the new state travel as
+// st.async stores that complete transaction bytes on an mbarrier in the RECEIVER's shared memory, the local half is
+// covered by one mbarrier.arrive per warp.  A barrier.cluster.arrive.release (the round-1 scheme) also has to make the
+// step's GLOBAL stores (56 KB per CTA) visible at cluster scope before it completes, which put their drain (0.9 us of a
+// 3.5 us step) on the critical path of the recurrence; an mbarrier.arrive releases at CTA scope only and st.async carries
+// its own completion, so the global stores drain behind the next steps' MMAs.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned peer_addr(unsigned local, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(unsigned addr, const float4& v, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2(unsigned addr, const float2& v, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(v.x),
+               "f"(v.y), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 // A operand [32 rows x K] in m16n8k8 fragment order: [m-tile][k-step][lane][4].  The eight k of a step are assigned to
 // the fragment slots as k % 8 = 2 * (lane % 4) + (register / 2) (the MMA sums over k, so any assignment used for both
@@ -60,9 +101,21 @@ __device__ __forceinline__ int afrag_index(int row, int k, int ksteps) {
 
 // ------------------------------------------------------------------------------------ forward
 // gx [B,T,4H] in: x W_i2h^T + b_i2h ; out: gate activations (i,f,g,o).  hs / hprev / cs [B,T,H].
+//
+// Schedule.  The R = 32 rows of a cluster are two independent SUB-BLOCKS of 16 rows (one m16 tile each), and the eight
+// warps two GROUPS (warps 0-3 / 4-7: one warp of each group per SM sub-partition).  Every warp walks
+//     M(A,t) G(A,t) M(B,t) G(B,t) M(A,t+1) ...          M = 64 MMAs of a sub-block, G = gate math + exchange + stores
+// and the second group starts one phase late, so on each sub-partition one warp is in its MMA phase (tensor pipe) while
+// the other is in its gate phase (MUFU, LSU): the phases of a step no longer add up, and the state of a sub-block has the
+// whole next phase to reach the peer CTA before anyone waits for it.  (With all warps in one phase the step cost
+// MMA 0.9 + MUFU 0.3 + stores 0.7 + exchange / waits 1.0 us = 3.1 us, measured with the phases switched off one by one.)
+constexpr int RB = 16;                   // rows of a sub-block
 struct FwdSmem {
-  float hfrag[2][R * H];                 // h_{t-1} in A-fragment order, double-buffered (2 x 16 KB)
-  float gxs[2][R * kRowPitch];           // this CTA's slice of gx for steps t, t+1 (cp.async, one step ahead)
+  float hfrag[2][2][RB * H];             // [sub-block][parity]: h_{t-1} in A-fragment order (4 x 8 KB)
+  float gxs[2][3][RB * kRowPitch];       // [sub-block][t % 3]: this CTA's slice of gx (cp.async, two steps ahead: the loads
+                                         // come from HBM and a phase is shorter than their latency)
+  unsigned long long full[2][2];         // hfrag [sub-block][parity] (+ the gx slab of that step) complete: 8 local warps + 4 KB
+                                         // from the peer
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -78,19 +131,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int ul0 = warp * 8 + 2 * t4;                        // this thread's two local units (accumulator columns 2t, 2t+1)
   const int u0 = crank * UH + ul0;
   const int un = crank * UH + warp * 8 + g;                 // the unit whose W rows this thread holds as B fragments (n = lane / 4)
+  const bool late = warp >= 4;                              // second group: one phase behind
 
   // A cluster is persistent over blocks of R batch rows (grid = min(#row blocks, resident clusters)): W_h2h goes into
   // registers once per CTA.  With T = 1 (one decode step over a large batch: style transfer / beam search) the launch
   // used to be 3-4 waves of CTAs that each re-loaded their 128 KB of W for a single step.
   int b0 = 0;
-  // gx slab of step t -> gxs[t & 1]: 32 rows x 4 gates x 64 units = 2048 16-byte chunks, 8 per thread
-  auto prefetch_gx = [&](int t) {
-    float* dst = sm.gxs[t & 1];
+  // gx slab of (sub-block sb, step t) -> gxs[sb][t % 3]: 16 rows x 4 gates x 64 units = 1024 16-byte chunks, 4 per thread.
+  // Always commits a group (possibly empty) so that the wait_group arithmetic below is the same in every step.
+  auto prefetch_gx = [&](int sb, int t) {
+    float* dst = sm.gxs[sb][t % 3];
+    if (t < T) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ch = tid + i * kThreads, row = ch >> 6, rem = ch & 63, gate = rem >> 4, c4 = (rem & 15) * 4;
-      const int b = min(b0 + row, B - 1);
-      cp_async16(dst + row * kRowPitch + gate * UH + c4, gx + ((size_t)b * T + t) * 4 * H + gate * H + crank * UH + c4);
+      for (int i = 0; i < 4; ++i) {
+        const int ch = tid + i * kThreads, row = ch >> 6, rem = ch & 63, gate = rem >> 4, c4 = (rem & 15) * 4;
+        const int b = min(b0 + sb * RB + row, B - 1);
+        cp_async16(dst + row * kRowPitch + gate * UH + c4, gx + ((size_t)b * T + t) * 4 * H + gate * H + crank * UH + c4);
+      }
     }
     cp_async_commit();
   };
@@ -112,99 +169,120 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     bias[j][0] = __ldg(b_h2h + j * H + u0);
     bias[j][1] = __ldg(b_h2h + j * H + u0 + 1);
   }
-  float* hfrag_peer = cluster.map_shared_rank(&sm.hfrag[0][0], crank ^ 1);
+  const unsigned hfrag_peer = peer_addr(smem_addr(&sm.hfrag[0][0][0]), crank ^ 1);   // shared::cluster addresses in the peer CTA
+  const unsigned full_peer = peer_addr(smem_addr(&sm.full[0][0]), crank ^ 1);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.full[0][0] + i, kThreads / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;                                       // bit 2 sb + i: parity of the next completion of full[sb][i]
   const int n_blocks = (B + R - 1) / R, n_clusters = gridDim.x >> 1;
   for (int blk = blockIdx.x >> 1; blk < n_blocks; blk += n_clusters) {
-  b0 = blk * R;
-  cluster.sync();                                           // both CTAs are done with the previous row block's buffers
-  prefetch_gx(0);
-  for (int i = tid; i < R * H; i += kThreads) {
-    const int r = i / H, k = i % H;
-    sm.hfrag[0][afrag_index(r, k, 16)] = (b0 + r < B) ? tf32r(__ldg(h0 + (size_t)(b0 + r) * ld0 + k)) : 0.f;
-  }
-  // cells of this thread: rows 16m + 8hi + g (index q = 2m + hi), units u0, u0 + 1
-  float c[4][2], hp[4][2];
-  int brow[4];
+    b0 = blk * R;
+    cluster.sync();                                         // both CTAs are done with the previous row block's buffers
+    prefetch_gx(0, 0);
+    prefetch_gx(1, 0);
+    prefetch_gx(0, 1);
+    prefetch_gx(1, 1);
+    for (int i = tid; i < R * H; i += kThreads) {
+      const int r = i / H, k = i % H;
+      sm.hfrag[r >> 4][0][afrag_index(r & 15, k, 16)] = (b0 + r < B) ? tf32r(__ldg(h0 + (size_t)(b0 + r) * ld0 + k)) : 0.f;
+    }
+    // cells of this thread: sub-block sb, rows 8 hi + g, units u0, u0 + 1
+    float c[2][2][2], hp[2][2][2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    brow[q] = b0 + 16 * (q >> 1) + 8 * (q & 1) + g;
-    const int b = min(brow[q], B - 1);
-    c[q][0] = __ldg(c0 + (size_t)b * ld0 + u0);
-    c[q][1] = __ldg(c0 + (size_t)b * ld0 + u0 + 1);
-    hp[q][0] = __ldg(h0 + (size_t)b * ld0 + u0);
-    hp[q][1] = __ldg(h0 + (size_t)b * ld0 + u0 + 1);
-  }
-  cp_async_wait_all();
-  cluster.sync();
+    for (int sb = 0; sb < 2; ++sb)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const int b = min(b0 + sb * RB + 8 * hi + g, B - 1);
+        c[sb][hi][0] = __ldg(c0 + (size_t)b * ld0 + u0);
+        c[sb][hi][1] = __ldg(c0 + (size_t)b * ld0 + u0 + 1);
+        hp[sb][hi][0] = __ldg(h0 + (size_t)b * ld0 + u0);
+        hp[sb][hi][1] = __ldg(h0 + (size_t)b * ld0 + u0 + 1);
+      }
+    asm volatile("cp.async.wait_group 2;" ::: "memory");    // the slabs of step 0
+    cluster.sync();
+    // one-time skew: the second group starts when the first has issued its first MMA phase
+    if (late) asm volatile("bar.sync 1, 256;" ::: "memory");
 
-  for (int t = 0; t < T; ++t) {
-    if (t + 1 < T) prefetch_gx(t + 1);                      // its buffer was last read in step t-1
-    const float4* hcur = reinterpret_cast<const float4*>(sm.hfrag[t & 1]);
-    float acc[2][4][4];
+    for (int t = 0; t < T; ++t) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+      for (int sb = 0; sb < 2; ++sb) {
+        unsigned long long* bar_cur = &sm.full[sb][t & 1];
+        if (t > 0) {                                        // h_{t-1} (both halves) and the gx slab of step t are in place
+          mbar_wait(bar_cur, (phase >> (2 * sb + (t & 1))) & 1u);
+          phase ^= 1u << (2 * sb + (t & 1));
+        }
+        prefetch_gx(sb, t + 2);                             // its buffer was last read in step t-1 (every warp arrived since)
+        const float4* hcur = reinterpret_cast<const float4*>(sm.hfrag[sb][t & 1]);
+        float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[m][j][0] = acc[m][j][2] = bias[j][0];
-        acc[m][j][1] = acc[m][j][3] = bias[j][1];
+        for (int j = 0; j < 4; ++j) {
+          acc[j][0] = acc[j][2] = bias[j][0];
+          acc[j][1] = acc[j][3] = bias[j][1];
+        }
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          const float4 a = hcur[s * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_tf32(acc[j], a, breg[j][s][0], breg[j][s][1]);
+        }
+        if (t == 0 && sb == 0 && !late) asm volatile("bar.arrive 1, 256;" ::: "memory");
+        const float* gxc = sm.gxs[sb][t % 3];
+        float2 iv[2], fv[2], gv[2], ov[2], cv[2], hv[2];
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const float* gp = gxc + (8 * hi + g) * kRowPitch + ul0;
+          const float2 xi = *reinterpret_cast<const float2*>(gp), xf = *reinterpret_cast<const float2*>(gp + UH);
+          const float2 xg = *reinterpret_cast<const float2*>(gp + 2 * UH), xo = *reinterpret_cast<const float2*>(gp + 3 * UH);
+          iv[hi] = make_float2(sigmoidf_(acc[0][2 * hi] + xi.x), sigmoidf_(acc[0][2 * hi + 1] + xi.y));
+          fv[hi] = make_float2(sigmoidf_(acc[1][2 * hi] + xf.x), sigmoidf_(acc[1][2 * hi + 1] + xf.y));
+          gv[hi] = make_float2(tanhf(acc[2][2 * hi] + xg.x), tanhf(acc[2][2 * hi + 1] + xg.y));
+          ov[hi] = make_float2(sigmoidf_(acc[3][2 * hi] + xo.x), sigmoidf_(acc[3][2 * hi + 1] + xo.y));
+          c[sb][hi][0] = fv[hi].x * c[sb][hi][0] + iv[hi].x * gv[hi].x;
+          c[sb][hi][1] = fv[hi].y * c[sb][hi][1] + iv[hi].y * gv[hi].y;
+          cv[hi] = make_float2(c[sb][hi][0], c[sb][hi][1]);
+          hv[hi] = make_float2(ov[hi].x * tanhf(c[sb][hi][0]), ov[hi].y * tanhf(c[sb][hi][1]));
+        }
+        // new h of (rows g, g+8) x (units u0, u0+1) is one float4 of the fragment buffer (see afrag_index).  The peer's copy
+        // completes 16 bytes on the peer's full[sb][(t+1) & 1]; the buffer it lands in was last read by the peer in step
+        // t-1, and the peer has sent its step-(t-1) halves (which this CTA waited for above) after those reads.
+        if (t + 1 < T) {
+          const float4 hf = make_float4(tf32r(hv[0].x), tf32r(hv[1].x), tf32r(hv[0].y), tf32r(hv[1].y));
+          const int fi = (((u0 >> 3)) * 32 + g * 4 + t4) * 4;
+          const int slot = 2 * sb + ((t + 1) & 1);
+          st_async_v4(hfrag_peer + (slot * RB * H + fi) * 4, hf, full_peer + slot * 8);
+          *reinterpret_cast<float4*>(&sm.hfrag[0][0][0] + slot * RB * H + fi) = hf;
+          // this thread's chunks of the slab (sb, t+1) have landed: issued one step ago, two younger groups may be in flight
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (warp == 0) mbar_arrive_expect_tx(&sm.full[0][0] + slot, RB * UH * 4);   // the peer's half: 4 KB
+            else mbar_arrive(&sm.full[0][0] + slot);
+          }
+        }
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const int brow = b0 + sb * RB + 8 * hi + g;
+          if (brow < B) {
+            const size_t o = (size_t)brow * T + t;
+            float* gp = gx + o * 4 * H + u0;
+            *reinterpret_cast<float2*>(gp) = iv[hi];
+            *reinterpret_cast<float2*>(gp + H) = fv[hi];
+            *reinterpret_cast<float2*>(gp + 2 * H) = gv[hi];
+            *reinterpret_cast<float2*>(gp + 3 * H) = ov[hi];
+            *reinterpret_cast<float2*>(hs + o * H + u0) = hv[hi];
+            *reinterpret_cast<float2*>(hprev + o * H + u0) = make_float2(hp[sb][hi][0], hp[sb][hi][1]);
+            *reinterpret_cast<float2*>(cs + o * H + u0) = cv[hi];
+          }
+          hp[sb][hi][0] = hv[hi].x;
+          hp[sb][hi][1] = hv[hi].y;
+        }
       }
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const float4 a = hcur[(m * 16 + s) * 32 + lane];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], a, breg[j][s][0], breg[j][s][1]);
-      }
     }
-    const float* gxc = sm.gxs[t & 1];
-    float* hnext = sm.hfrag[(t + 1) & 1];
-    float* hnext_peer = hfrag_peer + ((t + 1) & 1) * R * H;
-    float2 iv[4], fv[4], gv[4], ov[4], cv[4], hv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int m = q >> 1, hi = q & 1, row = 16 * m + 8 * hi + g;
-      const float* gp = gxc + row * kRowPitch + ul0;
-      const float2 xi = *reinterpret_cast<const float2*>(gp), xf = *reinterpret_cast<const float2*>(gp + UH);
-      const float2 xg = *reinterpret_cast<const float2*>(gp + 2 * UH), xo = *reinterpret_cast<const float2*>(gp + 3 * UH);
-      iv[q] = make_float2(sigmoidf_(acc[m][0][2 * hi] + xi.x), sigmoidf_(acc[m][0][2 * hi + 1] + xi.y));
-      fv[q] = make_float2(sigmoidf_(acc[m][1][2 * hi] + xf.x), sigmoidf_(acc[m][1][2 * hi + 1] + xf.y));
-      gv[q] = make_float2(tanhf(acc[m][2][2 * hi] + xg.x), tanhf(acc[m][2][2 * hi + 1] + xg.y));
-      ov[q] = make_float2(sigmoidf_(acc[m][3][2 * hi] + xo.x), sigmoidf_(acc[m][3][2 * hi + 1] + xo.y));
-      c[q][0] = fv[q].x * c[q][0] + iv[q].x * gv[q].x;
-      c[q][1] = fv[q].y * c[q][1] + iv[q].y * gv[q].y;
-      cv[q] = make_float2(c[q][0], c[q][1]);
-      hv[q] = make_float2(ov[q].x * tanhf(c[q][0]), ov[q].y * tanhf(c[q][1]));
-    }
-    // new h of (rows g, g+8) x (units u0, u0+1) of m-tile m is one float4 of the fragment buffer (see afrag_index)
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const float4 hf = make_float4(tf32r(hv[2 * m].x), tf32r(hv[2 * m + 1].x), tf32r(hv[2 * m].y), tf32r(hv[2 * m + 1].y));
-      const int fi = ((m * 16 + (u0 >> 3)) * 32 + g * 4 + t4) * 4;
-      *reinterpret_cast<float4*>(hnext + fi) = hf;
-      *reinterpret_cast<float4*>(hnext_peer + fi) = hf;
-    }
-    cp_async_wait_all();                                    // gx of step t+1 has landed (visible to all after the barrier)
-    cluster_arrive();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (brow[q] < B) {
-        const size_t o = (size_t)brow[q] * T + t;
-        float* gp = gx + o * 4 * H + u0;
-        *reinterpret_cast<float2*>(gp) = iv[q];
-        *reinterpret_cast<float2*>(gp + H) = fv[q];
-        *reinterpret_cast<float2*>(gp + 2 * H) = gv[q];
-        *reinterpret_cast<float2*>(gp + 3 * H) = ov[q];
-        *reinterpret_cast<float2*>(hs + o * H + u0) = hv[q];
-        *reinterpret_cast<float2*>(hprev + o * H + u0) = make_float2(hp[q][0], hp[q][1]);
-        *reinterpret_cast<float2*>(cs + o * H + u0) = cv[q];
-      }
-      hp[q][0] = hv[q].x;
-      hp[q][1] = hv[q].y;
-    }
-    cluster_wait();
-  }
   }                                                         // row blocks
+  cluster.sync();                                           // no CTA leaves while its peer could still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -220,6 +298,7 @@ struct BwdSmem {
   float gts[2][R * kRowPitch];           // saved gate activations of steps t, t-1 (cp.async, one step ahead)
   float cst[2][R * kColPitch];           // c_{t-1}
   float dht[2][R * kColPitch];           // dhs
+  unsigned long long full[2];            // partials of step t in dhrec / dhin[t & 1] and the slabs of step t-1: 8 local warps + 8 KB
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -292,13 +371,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   for (int j = 0; j < 4; ++j) bsum[j][0] = bsum[j][1] = 0.f;
   // hidden columns [16 warp, 16 warp + 16): warps 0-3 produce CTA 0's units, warps 4-7 CTA 1's
   const bool mine = (warp >> 2) == crank;
-  float* dst_base = mine ? &sm.dhrec[0][0] : cluster.map_shared_rank(&sm.dhin[0][0], crank ^ 1);
+  const unsigned dhin_peer = peer_addr(smem_addr(&sm.dhin[0][0]), crank ^ 1);   // shared::cluster addresses in the peer CTA
+  const unsigned full_peer = peer_addr(smem_addr(&sm.full[0]), crank ^ 1);
+  if (tid == 0) {
+    mbar_init(&sm.full[0], kThreads / 32);
+    mbar_init(&sm.full[1], kThreads / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;                                         // bit i: parity of the next completion of full[i]
   cp_async_wait_all();
   cluster.sync();
 
   for (int t = T - 1; t >= 0; --t) {
     const int buf = t & 1;
-    if (t > 0) prefetch(t - 1);                             // its buffers were last read in step t+1
+    if (t < T - 1) {                                        // step t+1 is complete in both CTAs, the slabs of step t have landed
+      mbar_wait(&sm.full[buf ^ 1], (phase >> (buf ^ 1)) & 1u);
+      phase ^= 1u << (buf ^ 1);
+    }
+    if (t > 0) prefetch(t - 1);                             // its buffers were last read in step t+1 (every warp arrived since)
     // ---- cell backward (thread-local), operands from the staged slabs
     float2 di[4], df[4], dg2[4], dou[4];
 #pragma unroll
@@ -372,13 +462,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) {
         const int col = ((16 * warp + 8 * nn) & 63) + 2 * t4;   // local unit in the owning CTA
-        float* d = dst_base + buf * R * kColPitch;
-        *reinterpret_cast<float2*>(d + (16 * m + g) * kColPitch + col) = make_float2(acc[m][nn][0], acc[m][nn][1]);
-        *reinterpret_cast<float2*>(d + (16 * m + g + 8) * kColPitch + col) = make_float2(acc[m][nn][2], acc[m][nn][3]);
+        const int o0 = buf * R * kColPitch + (16 * m + g) * kColPitch + col, o1 = o0 + 8 * kColPitch;
+        if (mine) {
+          *reinterpret_cast<float2*>(&sm.dhrec[0][0] + o0) = make_float2(acc[m][nn][0], acc[m][nn][1]);
+          *reinterpret_cast<float2*>(&sm.dhrec[0][0] + o1) = make_float2(acc[m][nn][2], acc[m][nn][3]);
+        } else {                                             // the peer's units: 8 bytes each on the peer's full[buf]
+          st_async_v2(dhin_peer + o0 * 4, make_float2(acc[m][nn][0], acc[m][nn][1]), full_peer + buf * 8);
+          st_async_v2(dhin_peer + o1 * 4, make_float2(acc[m][nn][2], acc[m][nn][3]), full_peer + buf * 8);
+        }
       }
-    cp_async_wait_all();                                    // slabs of step t-1 have landed
-    cluster.sync();                                         // dhrec / dhin of step t-1 complete in both CTAs
+    cp_async_wait_all();                                    // this thread's chunks of the slabs of step t-1 have landed
+    __syncwarp();
+    if (lane == 0) {
+      if (warp == 0) mbar_arrive_expect_tx(&sm.full[buf], R * UH * 4);   // the peer's partial of this CTA's units: 8 KB per step
+      else mbar_arrive(&sm.full[buf]);
+    }
   }
+  mbar_wait(&sm.full[0], phase & 1u);                       // step 0 complete in both CTAs
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -403,6 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       *reinterpret_cast<float2*>(dc0 + (size_t)brow[q] * ld0 + u0) = make_float2(dc[q][0], dc[q][1]);
     }
   }
+  cluster.sync();                                           // no CTA leaves while its peer could still address its shared memory
 }
 
 }  // namespace
