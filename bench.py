@@ -31,6 +31,7 @@ def emit(line):
 
 METRIC = "vae_train_sequences_per_sec"
 UNIT = "sequences/s"
+HEADLINE = "bf16p3f"     # precision mode of the headline line (engine.PRECISIONS); its parity: tests/test_parity_bench_gpu.py
 
 
 def parse_args():
@@ -43,9 +44,10 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--dec-type", default="lstm", choices=["lstm", "transformer"])
     ap.add_argument("--dropout", type=float, default=0.2)
-    ap.add_argument("--precision", default="tf32x3f", choices=["fp32", "fp32x3", "tf32x3f", "bf16x3f", "tf32", "bf16"],
-                    help="engine precision mode (musicstyletransfer_b200/engine.py PRECISIONS): tf32x3f (default) = fp32-equivalent "
-                         "forward (3xTF32 GEMMs, compensated attention scores), TF32 backward; tf32 = every product single-pass TF32; "
+    ap.add_argument("--precision", default=HEADLINE, choices=["fp32", "fp32x3", "tf32x3f", "bf16x3f", "bf16p3f", "tf32", "bf16"],
+                    help="engine precision mode (musicstyletransfer_b200/engine.py PRECISIONS): bf16p3f (default) = fp32-class forward "
+                         "(GEMM operands as bf16 hi + lo planes, compensated attention scores), TF32 backward; tf32x3f = the same "
+                         "with 3xTF32 GEMMs; tf32 = every product single-pass TF32; "
                          "fp32x3 = strict fp32 on the tensor cores; fp32 = exact FFMA; bf16 = BASELINE config 4")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="rows per oracle step of the CPU arm (0 = the GPU arm's per-GPU batch, i.e. the same step)")
@@ -80,6 +82,10 @@ PRECISION_NOTE = {
     "tf32x3f": "fp32 storage; FORWARD GEMMs 3xTF32 on tcgen05 (fp32-equivalent products) and attention scores compensated the "
                "same way -> loss / KL / latent means within 1e-3 of the fp32 oracle with 10x margin (measured 1.0e-4); BACKWARD "
                "GEMMs, attention and the LSTM recurrence single-pass TF32 (fp32 accumulate)",
+    "bf16p3f": "fp32 storage; FORWARD encoder GEMMs on msx_gemm_tc_p3: both operands arrive as bf16 hi / lo planes written by "
+               "the producing kernels (embedding, LayerNorm, attention, FF1 epilogue; weights split once per step), three walks "
+               "hi*hi + hi*lo + lo*hi on tcgen05 kind::f16, ~2^-17 per product, attention scores compensated the same way; "
+               "backward GEMMs, LSTM recurrence single-pass TF32 (two weight gradients read the bf16 hi plane)",
     "bf16x3f": "fp32 storage; FORWARD encoder GEMMs with bf16x3 products on tcgen05 kind::f16 (operands split into bf16 hi + lo "
                "inside the kernel, ~2^-17 per product) and attention scores 3xTF32 -> loss / KL / latent means within 1e-3 of the "
                "fp32 oracle with margin; BACKWARD GEMMs, decoder GEMMs, attention and the LSTM recurrence single-pass TF32",
@@ -563,10 +569,13 @@ def run_ours(args):
 
     # ---- bf16 variant (BASELINE config 4), stated separately: same model, batch, data and timing protocol with
     # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
-    bf16_variant = fp32_variant = b32 = None
+    bf16_variant = fp32_variant = b32 = x3_variant = None
     strong = []
     tf32_variant = None
-    if args.precision == "tf32x3f" and not args.no_variants:
+    if args.precision == HEADLINE and not args.no_variants:
+        # ---- round 2's first headline: the same forward accuracy class with the operand split INSIDE the GEMM (3xTF32)
+        x3_variant = time_variant("tf32x3f", B, gbatch, K, W)
+        x3_variant.update({"dtype": "f32 forward (3xTF32) / tf32 backward", "what": PRECISION_NOTE["tf32x3f"]})
         tf32_variant = time_variant("tf32", B, gbatch, K, W)
         tf32_variant.update({"dtype": "tf32", "what": PRECISION_NOTE["tf32"]})
         bf16_variant = time_variant("bf16", B, gbatch, K, W)
@@ -611,13 +620,13 @@ def run_ours(args):
                "ms_per_step": per_step * 1e3}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32", "tf32x3f": "f32 forward (3xTF32) / tf32 backward", "bf16x3f": "f32 storage, bf16x3 / 3xTF32 forward, tf32 backward", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32", "tf32x3f": "f32 forward (3xTF32) / tf32 backward", "bf16x3f": "f32 storage, bf16x3 / 3xTF32 forward, tf32 backward", "bf16p3f": "f32 storage, forward products from bf16 hi+lo planes (~2^-17) / tf32 backward", "tf32": "tf32", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
         "config": config_dict(args, world),
         "run": {"precision": PRECISION_NOTE[args.precision], "cuda_graph": not args.no_graph, "dp_exchange": dp_exchange, "ranks_identical": ranks_identical,
                 "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                       (B * T * 4 * 40e3 / 1e9 / 10)},
-        "roofline": roofline, "roofline_other": roofline_other, "rasteriser": raster, "cpu_baseline": cpu, "tf32_variant": tf32_variant, "bf16_variant": bf16_variant,
+        "roofline": roofline, "roofline_other": roofline_other, "rasteriser": raster, "cpu_baseline": cpu, "tf32x3f_variant": x3_variant, "tf32_variant": tf32_variant, "bf16_variant": bf16_variant,
         "fp32_variant": fp32_variant, "strong_scaling": strong or None, "b32": b32, "e2e_from_midi": e2e_from_midi,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},

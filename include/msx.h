@@ -120,6 +120,19 @@ int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B, int ldb, i
                    int K, int ab_bf16, int c_bf16, const float* bias, int relu, float drop_p, unsigned long long seed,
                    unsigned site, const void* aux, int ldaux, int aux_kind, float aux_scale, int accumulate, int splitk,
                    float* out_colsum, uint32_t* mask_out, int ldmask, void* stream);
+/* "p3" forward GEMM (the gluon.nn.Dense forwards of transformer.py:36-40,65-68,88-93,104): Y = X W^T + b with both operands
+ * given as bfloat16 hi / lo PLANES (hi = rn_bf16(x), lo = rn_bf16(x - hi)) written by the kernels that produce x
+ * (msx_embed_fwd_p, msx_add_ln_fwd_p, msx_attention_tc_fwd_p, this function's C planes, msx_split_planes for weights).
+ * The reduction is walked three times, A_hi B_hi + A_hi B_lo + A_lo B_hi, on kind::f16 with fp32 accumulation: products
+ * to ~2^-17 relative (the accuracy class of 3xTF32 for this step) with no in-kernel conversion stage.  A [M,K], B [N,K]
+ * K-major, K % 64 == 0.  c_kind 0: fp32 C; 2: C / C_lo receive the bf16 hi / lo planes of the result (plain store). */
+int msx_gemm_tc_p3_supported(const void* A_hi, int lda, const void* B_hi, int ldb, const void* C, int ldc, int c_kind, int M,
+                             int N, int K);
+int msx_gemm_tc_p3(const void* A_hi, const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, void* C,
+                   void* C_lo, int ldc, int c_kind, int M, int N, int K, const float* bias, int relu, float drop_p,
+                   unsigned long long seed, unsigned site, int accumulate, uint32_t* mask_out, int ldmask, void* stream);
+/* fp32 -> bf16 hi / lo planes, n % 4 == 0 (the weight arena once per step; small activations no kernel emits as planes). */
+int msx_split_planes(const float* src, void* hi, void* lo, long long n, void* stream);
 /* Strict-fp32 tensor-core GEMM (the reference step is fp32 end to end, trainer.py:155-179): same contract and epilogues as
  * msx_gemm_tc_ex with fp32 operands, but every operand value is split into hi + lo TF32 parts inside the kernel and a
  * k-block contributes A_lo B_hi + A_hi B_lo + A_hi B_hi ("3xTF32"), fp32 accumulation in TMEM: products carry ~2^-21
@@ -179,6 +192,10 @@ int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int 
  * single-pass TF32 scores the largest forward error of the step. */
 int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B, int T, int H,
                              int dh, void* stream);
+/* p3 planes: ctx (bfloat16, ctx_bf16 != 0) receives the hi plane rn_bf16(o) and ctx_lo (optional) rn_bf16(o - hi): the two
+ * operands of the p3 W_proj GEMM (msx_gemm_tc_p3); the context then never exists in fp32. */
+int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores, int B,
+                           int T, int H, int dh, void* stream);
 int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
                             int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);
@@ -208,6 +225,10 @@ int msx_add_ln_bwd(const float* x, const float* y, const float* gamma, const flo
 int msx_add_ln_fwd_ex(const float* x, const void* y, int y_bf16, const float* gamma, const float* beta, float* out,
                       void* out_bf16, float* mean, float* rstd, long long M, int D, float eps, float drop_p,
                       unsigned long long seed, unsigned site, void* stream);
+/* p3 planes: out_bf16 / out_bf16_lo receive rn_bf16(out) and rn_bf16(out - hi) (operands of msx_gemm_tc_p3). */
+int msx_add_ln_fwd_p(const float* x, const void* y, int y_bf16, const float* gamma, const float* beta, float* out,
+                     void* out_bf16, void* out_bf16_lo, float* mean, float* rstd, long long M, int D, float eps, float drop_p,
+                     unsigned long long seed, unsigned site, void* stream);
 int msx_add_ln_bwd_ex(const float* x, const void* y, int y_bf16, const float* gamma, const float* mean, const float* rstd,
                       const float* dout, float* dres, float* dy, void* dy_bf16, float* dgamma, float* dbeta, float* dybias,
                       long long M, int D, float drop_p, unsigned long long seed, unsigned site, int accumulate_dres,
@@ -251,6 +272,10 @@ int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, const int32_t* 
 int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
                      const float* cls_emb, const float* prefix_vec, const float* pe, float* out, void* out_bf16, float* mask,
                      int B, int T, int D, int prefix, float scale, int vocab, void* stream);
+/* p3 planes: as msx_embed_fwd_ex plus the lo plane rn_bf16(row - hi) next to the bfloat16 (hi) copy. */
+int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
+                    const float* cls_emb, const float* prefix_vec, const float* pe, float* out, void* out_bf16,
+                    void* out_bf16_lo, float* mask, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                   float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 

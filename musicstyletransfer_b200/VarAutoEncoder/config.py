@@ -82,9 +82,10 @@ b200_arg = add_argument_group('B200')
 b200_arg.add_argument('--decoder-type', choices=["lstm", "transformer"], default="lstm",
                       help="lstm = the decoder scripts/train-vae.sh's --d-* flags describe (model.py:131-203); "
                            "transformer = the decoder class Model instantiates at HEAD (model.py:206-272)")
-b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32x3f", "bf16x3f", "tf32", "bf16"], default="tf32x3f",
-                      help="precision mode (engine.PRECISIONS): tf32x3f = fp32-equivalent forward (3xTF32 GEMMs, compensated "
-                           "attention scores) with a TF32 backward; tf32 = every tensor-core product single-pass TF32; fp32x3 = "
+b200_arg.add_argument('--precision', choices=["fp32", "fp32x3", "tf32x3f", "bf16x3f", "bf16p3f", "tf32", "bf16"], default="bf16p3f",
+                      help="precision mode (engine.PRECISIONS): bf16p3f (default) = fp32-class forward (encoder GEMMs from bf16 "
+                           "hi + lo operand planes, ~2^-17 per product, compensated attention scores) with a TF32 backward; "
+                           "tf32x3f = the same with the operand split inside the GEMM (3xTF32); tf32 = every tensor-core product single-pass TF32; fp32x3 = "
                            "strict fp32 on the tensor cores (3xTF32 everywhere, exact attention / LSTM); fp32 = exact FFMA; bf16 = "
                            "tf32 with the Transformer layers' GEMM operands stored as bfloat16")
 b200_arg.add_argument('--cuda-graph', type=str2bool, default=True,

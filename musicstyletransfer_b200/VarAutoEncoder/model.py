@@ -148,7 +148,7 @@ class Decoder(_DecoderBase):
 class Model:
     """model.py:275-296.  ``context`` may be None / 'gpu' / a torch device; there is no CPU context."""
 
-    def __init__(self, config: ModelConfig, context=None, precision="tf32x3f", seed=0, quiet=False, featurisation="events",
+    def __init__(self, config: ModelConfig, context=None, precision="bf16p3f", seed=0, quiet=False, featurisation="events",
                  *args, **kwargs):
         if not quiet:
             print("Creating a model with the following configuration:")

@@ -16,7 +16,7 @@ from ..MIDIUtil.Melody import get_melody_from_ids
 from ..MIDIUtil.midi_io import MelodyWriter
 
 
-def load_inference_model(model_folder: str, context, checkpoint: Optional[int], precision="tf32x3f"):
+def load_inference_model(model_folder: str, context, checkpoint: Optional[int], precision="bf16p3f"):
     c = config.Config.load(os.path.join(model_folder, 'config'))
     utils.log_config(c)
     m = model.Model(c, context=context, precision=precision)
@@ -39,7 +39,7 @@ def get_sampler(type: str, model_folder: str, context, checkpoint: Optional[int]
 
 
 class SamplerBase:
-    def __init__(self, model_folder: str, context, checkpoint: int, verbose: bool = False, precision="tf32x3f",
+    def __init__(self, model_folder: str, context, checkpoint: int, verbose: bool = False, precision="bf16p3f",
                  model_instance=None):
         self.model = model_instance if model_instance is not None else \
             load_inference_model(model_folder, context, checkpoint, precision)

@@ -20,6 +20,7 @@ namespace {
 struct AttnTcParams {
   const float* mask;   // [B*T]
   float* ctx;          // [B*T, H*32] fp32, or bf16 when out_bf16 (the operand of the bf16 W_proj GEMM)
+  void* ctx_lo;        // optional (out_bf16 only): lo plane, ctx then holds the hi plane (operands of the p3 W_proj GEMM)
   int out_bf16;
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
   int dh;              // head width: 32, or 16 ("half heads": 32-wide tiles are still loaded, the score MMAs reduce over the
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(128 * G, 1)
         store_tile32_coalesced(sP + w4 * 4096, p.ctx, p.out_bf16 != 0, ((size_t)b * T + w4 * 32) * D + h * kDh, (size_t)D,
                                T - w4 * 32, o, lane);
       } else if (q < T) {
-        store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * kDh, o, kDh);
+        if (p.ctx_lo) store_row32_planes(p.ctx, p.ctx_lo, ((size_t)b * T + q) * D + h * kDh, o, kDh);
+        else store_row32(p.ctx, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * kDh, o, kDh);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -849,8 +851,12 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
 }
 }  // namespace
 
+extern "C" int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores,
+                                      int B, int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B,
-                                        int T, int H, int dh, void* stream);
+                                        int T, int H, int dh, void* stream) {
+  return msx_attention_tc_fwd_p(qkv, mask, ctx, nullptr, ctx_bf16, x3_scores, B, T, H, dh, stream);
+}
 extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
                                        int dh, void* stream) {
   return msx_attention_tc_fwd_ex2(qkv, mask, ctx, ctx_bf16, 0, B, T, H, dh, stream);
@@ -860,15 +866,16 @@ extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* 
   return msx_attention_tc_fwd_ex2(qkv, mask, ctx, 0, 0, B, T, H, dh, stream);
 }
 
-extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B,
-                                        int T, int H, int dh, void* stream) {
+extern "C" int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores,
+                                      int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
+  MSX_REQUIRE(!ctx_lo || (ctx_bf16 && ((uintptr_t)ctx_lo & 15) == 0), "msx_attention_tc_fwd_p: the lo plane needs a bf16 ctx and 16-byte alignment");
   MSX_REQUIRE(((uintptr_t)ctx & 15) == 0, "msx_attention_tc_fwd: ctx must be 16-byte aligned");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
   if (B == 0) return MSX_OK;
   const int D = H * dh;
   AttnTcParams p;
-  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H; p.dh = dh;
+  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.ctx_lo = ctx_lo; p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H; p.dh = dh;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.items = B * H;

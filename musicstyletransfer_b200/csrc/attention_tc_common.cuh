@@ -137,6 +137,21 @@ __device__ __forceinline__ void store_row32(void* base, bool bf16, size_t elem, 
   }
 }
 
+// hi / lo bf16 planes of one row (operands of the p3 GEMMs): hi = rn_bf16(o) at hi_base, rn_bf16(o - hi) at lo_base
+__device__ __forceinline__ void store_row32_planes(void* hi_base, void* lo_base, size_t elem, const float* o, int ncols = 32) {
+  uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(hi_base) + elem);
+  uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo_base) + elem);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (8 * j >= ncols) break;
+    uint2 h0, l0, h1, l1;
+    split4_bf16(o[8 * j], o[8 * j + 1], o[8 * j + 2], o[8 * j + 3], h0, l0);
+    split4_bf16(o[8 * j + 4], o[8 * j + 5], o[8 * j + 6], o[8 * j + 7], h1, l1);
+    dh[j] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    dl[j] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  }
+}
+
 // Coalesced form of store_row32 for a whole warp: lane l holds row l of a 32-row x 32-column tile; the tile goes through
 // a 4 KB shared-memory staging area `wst` (private to the warp, swizzled so that both directions are conflict-free) and
 // leaves with every quarter-warp writing one full 128-byte (bf16: eighth-warp, 64-byte) row segment.  With one row per

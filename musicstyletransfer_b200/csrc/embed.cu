@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
                                                         const float* __restrict__ prefix_vec,
                                                         const float* __restrict__ pe, float* __restrict__ out,
                                                         unsigned short* __restrict__ out16,
+                                                        unsigned short* __restrict__ out16lo,
                                                         float* __restrict__ mask, int B, int T, int D, int prefix,
                                                         float scale, int vocab) {
   const int TP = T + prefix;
@@ -51,6 +52,11 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
       unsigned r;
       asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
       dst16[e] = (unsigned short)(r & 0xFFFFu);
+      if (out16lo) {                        // lo plane of the p3 GEMM operand: rn_bf16(v - hi)
+        unsigned l;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(0.f), "f"(v - __uint_as_float(r << 16)));
+        out16lo[(size_t)row * D + e] = (unsigned short)(l & 0xFFFFu);
+      }
     }
   }
   if (mask && lane == 0) {
@@ -227,19 +233,32 @@ extern "C" int msx_embed_fwd(const int32_t* tokens, const int32_t* classes, cons
                           scale, vocab, stream);
 }
 
+extern "C" int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
+                               const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
+                               float* out, void* out_bf16, void* out_bf16_lo, float* mask, int B, int T, int D, int prefix,
+                               float scale, int vocab, void* stream);
 extern "C" int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
                                 const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
                                 float* out, void* out_bf16, float* mask, int B, int T, int D, int prefix, float scale,
                                 int vocab, void* stream) {
+  return msx_embed_fwd_p(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, out_bf16, nullptr, mask, B, T, D,
+                         prefix, scale, vocab, stream);
+}
+
+extern "C" int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens,
+                               const float* tok_emb, const float* cls_emb, const float* prefix_vec, const float* pe,
+                               float* out, void* out_bf16, void* out_bf16_lo, float* mask, int B, int T, int D, int prefix,
+                               float scale, int vocab, void* stream) {
   MSX_REQUIRE(tokens && tok_emb && (out || out_bf16), "msx_embed_fwd: null pointer");
+  MSX_REQUIRE(!out_bf16_lo || out_bf16, "msx_embed_fwd_p: a lo plane needs the hi plane");
   MSX_REQUIRE(prefix == 0 || prefix_vec, "msx_embed_fwd: prefix rows need prefix_vec");
   MSX_REQUIRE(!cls_emb || classes, "msx_embed_fwd: class embedding needs classes");
   if (B == 0 || T + prefix == 0) return MSX_OK;
   const long long rows = (long long)B * (T + prefix);
   const int wpb = 8;
   embed_fwd_kernel<<<msx_ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, reinterpret_cast<unsigned short*>(out_bf16), mask, B, T,
-      D, prefix, scale, vocab);
+      tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, reinterpret_cast<unsigned short*>(out_bf16),
+      reinterpret_cast<unsigned short*>(out_bf16_lo), mask, B, T, D, prefix, scale, vocab);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -32,7 +32,7 @@ namespace {
 template <bool A_MN, bool B_MN, bool BF, int EW>
 __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ P3Maps mx, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
         if (elect_one()) {
           mbar_expect_tx(&bars->full[stage], kStageBytes);
           using Op = OpCfg<BF>;
+          if (BF && !A_MN && !B_MN && p.x3_kb) {                                      // p3: hi*hi | hi*lo | lo*hi walks
+            const int seg = kb / p.x3_kb, kk = (kb - seg * p.x3_kb) * Op::kBKE;
+            tma_load_2d(sa, seg == 2 ? &mx.a_lo : &tmA, &bars->full[stage], kk, mt * BM);
+            tma_load_2d(sb, seg == 1 ? &mx.b_lo : &tmB, &bars->full[stage], kk, nt * BN);
+          } else {
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &bars->full[stage], kb * Op::kBKE, mt * BM);     // box {128 B of k, 128 rows}
           } else {
@@ -89,6 +94,7 @@ __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
 #pragma unroll
             for (int s = 0; s < BN / Op::kSlabMN; ++s)
               tma_load_2d(sb + s * Op::kSlabBytes, &tmB, &bars->full[stage], nt * BN + s * Op::kSlabMN, kb * Op::kBKE);
+          }
           }
         }
         __syncwarp();
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
+          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask, &mx.c_lo);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
 template <int BN2, bool A_MN, bool B_MN, bool BF, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ P3Maps mx, const TcParams p) {
   using Cfg = PairCfg<BN2>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -245,6 +251,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads
         if (elect_one()) {
           using Op = OpCfg<BF>;
           if (leader) mbar_expect_tx(&bars->full[stage], 2 * Cfg::kStage);
+          if (BF && !A_MN && !B_MN && p.x3_kb) {                                      // p3: hi*hi | hi*lo | lo*hi walks
+            const int seg = kb / p.x3_kb, kk = (kb - seg * p.x3_kb) * Op::kBKE;
+            tma_load_2d_pair(sa, seg == 2 ? &mx.a_lo : &tmA, fb, kk, m0);
+            tma_load_2d_pair(sb, seg == 1 ? &mx.b_lo : &tmB, fb, kk, n0);
+          } else {
           if (!A_MN) {
             tma_load_2d_pair(sa, &tmA, fb, kb * Op::kBKE, m0);                     // box {128 B of k, 128 rows}
           } else {
@@ -258,6 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads
 #pragma unroll
             for (int s = 0; s < Cfg::kBRows / Op::kSlabMN; ++s)
               tma_load_2d_pair(sb + s * Op::kSlabBytes, &tmB, fb, n0 + s * Op::kSlabMN, kb * Op::kBKE);
+          }
           }
         }
         __syncwarp();
@@ -334,7 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(lg * 32) << 16) + buf * BN2 + ch * 32, v);
         if (col0 < p.N && row0 < p.M) {          // warp-uniform
-          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask);
+          epilogue_chunk<EW>(p, &tmC, v, row0, my_row, col0, lane, st, sbuf, pending, reduce, amask, &mx.c_lo);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -357,18 +369,18 @@ constexpr size_t smem_bytes_1cta() {
 }
 
 template <bool A_MN, bool B_MN, bool BF, int EW>
-int launch_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+int launch_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const P3Maps& mx, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = smem_bytes_1cta<EW>();
   MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int grid = items < msx_num_sms() ? items : msx_num_sms();
-  gemm_tc_kernel<A_MN, B_MN, BF, EW><<<grid, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, p);
+  gemm_tc_kernel<A_MN, B_MN, BF, EW><<<grid, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, mx, p);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
 template <bool A_MN, bool B_MN, bool BF>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
-  return launch_ew<A_MN, B_MN, BF, 8>(ta, tb, tc, p, st);        // K < 256 here: mainloop too short for pair tiles, 8 warps
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const P3Maps& mx, const TcParams& p, cudaStream_t st) {
+  return launch_ew<A_MN, B_MN, BF, 8>(ta, tb, tc, mx, p, st);        // K < 256 here: mainloop too short for pair tiles, 8 warps
 }
 
 template <int BN2, int EW>
@@ -377,25 +389,25 @@ constexpr size_t pair_smem_bytes() {
 }
 
 template <int BN2, bool A_MN, bool B_MN, bool BF, int EW>
-int launch_pair_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+int launch_pair_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const P3Maps& mx, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = pair_smem_bytes<BN2, EW>();
   static_assert(smem <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
   MSX_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW><<<2 * pairs, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, p);   // static cluster dims (2,1,1)
+  gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW><<<2 * pairs, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, mx, p);   // static cluster dims (2,1,1)
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
 // epilogue-paced shapes (short K, wide N, plain stores) take 16 epilogue warps: see EpiCfg
 
 template <int BN2, bool A_MN, bool B_MN, bool BF>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const P3Maps& mx, const TcParams& p, cudaStream_t st) {
   static const int forced = [] { const char* e = getenv("MSX_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
   const bool wide = forced == 16 || (forced != 8 && p.K <= 256 && p.N >= 512 && !p.accumulate && p.splitk == 1);
-  if (wide) return launch_pair_ew<BN2, A_MN, B_MN, BF, 16>(ta, tb, tc, p, st);
-  return launch_pair_ew<BN2, A_MN, B_MN, BF, 8>(ta, tb, tc, p, st);
+  if (wide) return launch_pair_ew<BN2, A_MN, B_MN, BF, 16>(ta, tb, tc, mx, p, st);
+  return launch_pair_ew<BN2, A_MN, B_MN, BF, 8>(ta, tb, tc, mx, p, st);
 }
 
 // 2-CTA path switch: MSX_GEMM_PAIR=0 in the environment or msx_gemm_tc_set_pair(0) forces the 1-CTA kernel
@@ -409,11 +421,18 @@ bool pair_enabled() {
   return g_pair_mode == 1;
 }
 
+// hi / lo planes of a p3 launch: A / B / C of gemm_tc_impl are the hi planes, these the lo planes (C_lo optional)
+struct P3Args {
+  const void* A_lo;
+  const void* B_lo;
+  void* C_lo;
+};
+
 template <bool BF>
 int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int transB, void* C, int ldc, int c_bf16,
                  int M, int N, int K, const float* bias, int relu, float drop_p, unsigned long long seed, unsigned site,
                  const void* aux, int ldaux, int aux_bf16, float aux_scale, int accumulate, int splitk, float* out_colsum,
-                 void* stream, unsigned* mask_out = nullptr, int ldmask = 0) {
+                 void* stream, unsigned* mask_out = nullptr, int ldmask = 0, const P3Args* p3 = nullptr) {
   using Op = OpCfg<BF>;
   constexpr MapKind kOp = BF ? kMapBf16 : kMapTf32;
   if (splitk < 1) splitk = 1;
@@ -431,6 +450,14 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
   p.aux_scale = aux_scale; p.accumulate = accumulate; p.out_colsum = out_colsum; p.c_bf16 = c_bf16; p.aux_bf16 = aux_bf16;
   p.mask_out = mask_out; p.ldmask = ldmask; p.dbg = 0;
   p.kb_total = msx_ceil_div(K, Op::kBKE);
+  P3Maps mx;
+  if (p3) {                                   // three walks over the reduction: hi*hi | hi*lo | lo*hi
+    p.x3_kb = p.kb_total;
+    p.kb_total *= 3;
+    p.c_planes = p3->C_lo ? 1 : 0;
+  }
+  mx.c_lo = tc;
+  if (p3 && p3->C_lo && (rc = make_map(&mx.c_lo, p3->C_lo, M, N, ldc, 32, 32, false, kMapC16))) return rc;
   // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
   // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
   if (pair_enabled() && M > BM && N >= 64 && K >= 256) {
@@ -440,6 +467,9 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
     if (rc) return rc;
     if (!b_mn) rc = make_map(&tb, B, N, K, ldb, Op::kBKE, bn2 / 2, false, kOp); else rc = make_map(&tb, B, K, N, ldb, Op::kSlabMN, Op::kBKE, true, kOp);
     if (rc) return rc;
+    mx.a_lo = ta; mx.b_lo = tb;
+    if (p3 && ((rc = make_map(&mx.a_lo, p3->A_lo, M, K, lda, Op::kBKE, BM, false, kOp)) ||
+               (rc = make_map(&mx.b_lo, p3->B_lo, N, K, ldb, Op::kBKE, bn2 / 2, false, kOp)))) return rc;
     p.m_tiles = msx_ceil_div(M, 2 * BM); p.n_tiles = msx_ceil_div(N, bn2);
     if (splitk > 1) {                         // re-derive the split for pair tiles: about two waves of pairs
       const int tiles = p.m_tiles * p.n_tiles, pairs = msx_num_sms() / 2;
@@ -451,13 +481,13 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
     p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
     if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
     if (bn2 == 256) {
-      if (!a_mn && !b_mn) return launch_pair<256, false, false, BF>(ta, tb, tc, p, st);
-      if (!a_mn && b_mn) return launch_pair<256, false, true, BF>(ta, tb, tc, p, st);
-      if (a_mn && b_mn) return launch_pair<256, true, true, BF>(ta, tb, tc, p, st);
+      if (!a_mn && !b_mn) return launch_pair<256, false, false, BF>(ta, tb, tc, mx, p, st);
+      if (!a_mn && b_mn) return launch_pair<256, false, true, BF>(ta, tb, tc, mx, p, st);
+      if (a_mn && b_mn) return launch_pair<256, true, true, BF>(ta, tb, tc, mx, p, st);
     } else {
-      if (!a_mn && !b_mn) return launch_pair<128, false, false, BF>(ta, tb, tc, p, st);
-      if (!a_mn && b_mn) return launch_pair<128, false, true, BF>(ta, tb, tc, p, st);
-      if (a_mn && b_mn) return launch_pair<128, true, true, BF>(ta, tb, tc, p, st);
+      if (!a_mn && !b_mn) return launch_pair<128, false, false, BF>(ta, tb, tc, mx, p, st);
+      if (!a_mn && b_mn) return launch_pair<128, false, true, BF>(ta, tb, tc, mx, p, st);
+      if (a_mn && b_mn) return launch_pair<128, true, true, BF>(ta, tb, tc, mx, p, st);
     }
     msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
     return MSX_ERR_UNSUPPORTED;
@@ -466,14 +496,17 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
   if (rc) return rc;
   if (!b_mn) rc = make_map(&tb, B, N, K, ldb, Op::kBKE, BN, false, kOp); else rc = make_map(&tb, B, K, N, ldb, Op::kSlabMN, Op::kBKE, true, kOp);
   if (rc) return rc;
+  mx.a_lo = ta; mx.b_lo = tb;
+  if (p3 && ((rc = make_map(&mx.a_lo, p3->A_lo, M, K, lda, Op::kBKE, BM, false, kOp)) ||
+             (rc = make_map(&mx.b_lo, p3->B_lo, N, K, ldb, Op::kBKE, BN, false, kOp)))) return rc;
   p.m_tiles = msx_ceil_div(M, BM); p.n_tiles = msx_ceil_div(N, BN);
   if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = msx_ceil_div(p.kb_total, splitk);
   p.splitk = msx_ceil_div(p.kb_total, p.kb_per_split);
   if (p.splitk == 1 && splitk > 1) { p.splitk = 2; p.kb_per_split = p.kb_total; }   // keep the atomic-add contract
-  if (!a_mn && !b_mn) return launch<false, false, BF>(ta, tb, tc, p, st);
-  if (!a_mn && b_mn) return launch<false, true, BF>(ta, tb, tc, p, st);
-  if (a_mn && b_mn) return launch<true, true, BF>(ta, tb, tc, p, st);
+  if (!a_mn && !b_mn) return launch<false, false, BF>(ta, tb, tc, mx, p, st);
+  if (!a_mn && b_mn) return launch<false, true, BF>(ta, tb, tc, mx, p, st);
+  if (a_mn && b_mn) return launch<true, true, BF>(ta, tb, tc, mx, p, st);
   msx_set_error("msx_gemm_tc: operand major combination (A MN-major, B K-major) is not instantiated");
   return MSX_ERR_UNSUPPORTED;
 }
@@ -579,4 +612,65 @@ extern "C" int msx_gemm_tc_ex(const void* A, int lda, int transA, const void* B,
                               ldaux, aux_kind, aux_scale, accumulate, splitk, out_colsum, stream, mask_out, ldmask);
   return gemm_tc_impl<false>(A, lda, transA, B, ldb, transB, C, ldc, 0, M, N, K, bias, relu, drop_p, seed, site, aux, ldaux,
                              aux_kind, aux_scale, accumulate, splitk, out_colsum, stream, mask_out, ldmask);
+}
+
+// "p3" forward GEMM: Y = X W^T (+ bias, ReLU, dropout, ReLU bit mask) with BOTH operands given as bfloat16 hi / lo planes
+// (hi = rn_bf16(x), lo = rn_bf16(x - hi), written by the kernels that produce x: msx_embed_fwd_p, msx_add_ln_fwd_p,
+// msx_attention_tc_fwd_p, this function's own C planes, msx_split_planes for the weights).  The kernel walks the
+// reduction three times, A_hi B_hi + A_hi B_lo + A_lo B_hi, on kind::f16 with fp32 accumulation in TMEM: products to
+// ~2^-17 relative, the precision class of 3xTF32 for this step, at 1.5 single-pass TF32 MMAs and with no conversion stage
+// between TMA and the tensor pipe.  A [M, K] / B [N, K] K-major, K % 64 == 0.  c_kind: 0 = fp32 C; 2 = C as bf16 hi / lo
+// planes C / C_lo (the next p3 GEMM's operand, e.g. the FF hidden activation, which then never exists in fp32).
+extern "C" int msx_gemm_tc_p3_supported(const void* A_hi, int lda, const void* B_hi, int ldb, const void* C, int ldc, int c_kind,
+                                        int M, int N, int K) {
+  if (K % 64 != 0) return 0;
+  return msx_gemm_tc_bf16_supported(A_hi, lda, B_hi, ldb, C, ldc, c_kind == 2 ? 1 : 0, M, N, K);
+}
+
+extern "C" int msx_gemm_tc_p3(const void* A_hi, const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, void* C,
+                              void* C_lo, int ldc, int c_kind, int M, int N, int K, const float* bias, int relu, float drop_p,
+                              unsigned long long seed, unsigned site, int accumulate, unsigned* mask_out, int ldmask,
+                              void* stream) {
+  MSX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "msx_gemm_tc_p3: negative dimension");
+  if (M == 0 || N == 0) return MSX_OK;
+  MSX_REQUIRE(A_hi && A_lo && B_hi && B_lo && C, "msx_gemm_tc_p3: null operand");
+  MSX_REQUIRE(c_kind == 0 || c_kind == 2, "msx_gemm_tc_p3: c_kind must be 0 (fp32) or 2 (bf16 hi / lo planes)");
+  MSX_REQUIRE((c_kind == 2) == (C_lo != nullptr), "msx_gemm_tc_p3: C_lo goes with c_kind == 2");
+  MSX_REQUIRE(msx_gemm_tc_p3_supported(A_hi, lda, B_hi, ldb, C, ldc, c_kind, M, N, K) &&
+                  (((uintptr_t)A_lo | (uintptr_t)B_lo | (uintptr_t)C_lo) & 15) == 0,
+              "msx_gemm_tc_p3: planes must be 16-byte aligned, leading dimensions %% 8 == 0, K %% 64 == 0");
+  MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_gemm_tc_p3: dropout probability must be in [0,1)");
+  MSX_REQUIRE(!(c_kind == 2 && accumulate), "msx_gemm_tc_p3: plane outputs take plain stores only");
+  MSX_REQUIRE(!(mask_out && ((N & 31) || accumulate || ldmask < N / 32)), "msx_gemm_tc_p3: mask_out needs N %% 32 == 0, a plain store and ldmask >= N / 32");
+  const P3Args p3{A_lo, B_lo, C_lo};
+  return gemm_tc_impl<true>(A_hi, lda, 0, B_hi, ldb, 1, C, ldc, c_kind == 2 ? 1 : 0, M, N, K, bias, relu, drop_p, seed, site,
+                            nullptr, 0, 0, 1.f, accumulate, 1, nullptr, stream, mask_out, ldmask, &p3);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) split_planes_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
+                                                           uint2* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    uint2 h, l;
+    split4_bf16(v.x, v.y, v.z, v.w, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+}  // namespace
+
+// fp32 -> bf16 hi / lo planes (n % 4 == 0, 16-byte aligned src, 8-byte aligned planes): the weight arena once per step,
+// and the few small activations no kernel produces as planes
+extern "C" int msx_split_planes(const float* src, void* hi, void* lo, long long n, void* stream) {
+  MSX_REQUIRE(src && hi && lo, "msx_split_planes: null pointer");
+  MSX_REQUIRE(n >= 0 && (n & 3) == 0 && ((uintptr_t)src & 15) == 0 && (((uintptr_t)hi | (uintptr_t)lo) & 7) == 0,
+              "msx_split_planes: n %% 4 == 0, src 16-byte and planes 8-byte aligned");
+  if (n == 0) return MSX_OK;
+  const long long n4 = n / 4;
+  const long long want = (n4 + 255) / 256, cap = (long long)msx_num_sms() * 8;
+  split_planes_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), n4);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
 }

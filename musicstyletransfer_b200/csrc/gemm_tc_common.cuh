@@ -50,6 +50,16 @@ struct TcParams {
   int dbg;             // experiments only (MSX_X3_DEBUG): 1 = converter skips its work, 2 = one MMA per k-step instead of three
   unsigned* mask_out;  // optional: bit mask of (C > 0) after the epilogue, [M, ldmask words]; needs N % 32 == 0
   int ldmask;
+  // "p3" products (bf16 hi / lo PLANES of both operands, split by the kernels that produce them): the k-block sequence
+  // walks the reduction three times, hi*hi | hi*lo | lo*hi, as if the operands were [A_hi A_hi A_lo] and [B_hi B_lo B_hi]
+  // (K-major operands, kind::f16: ~2^-17 per product at 1.5 single-pass TF32 tensor time, no conversion stage).
+  int x3_kb = 0;       // k-blocks of ONE walk (kb_total = 3 * x3_kb); 0 = plain GEMM
+  int c_planes = 0;    // C leaves as bf16 hi / lo planes (tmC / P3Maps::c_lo), c_bf16 must be set
+};
+
+// extra tensor maps of a p3 launch (copies of the plain maps otherwise)
+struct P3Maps {
+  CUtensorMap a_lo, b_lo, c_lo;
 };
 
 struct __align__(8) Barriers {
@@ -232,7 +242,8 @@ __device__ __forceinline__ unsigned aux_mask(const TcParams& p, const AuxPref& a
 template <int EW, int kBoxesT = EpiCfg<EW>::kBoxes>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensorMap* tmc, float (&v)[32], int row0,
                                                int my_row, int col0, int lane, unsigned char* st, int& sbuf,
-                                               int& pending, bool reduce, unsigned amask) {
+                                               int& pending, bool reduce, unsigned amask,
+                                               const CUtensorMap* tmc_lo = nullptr) {
     // ---- row-owner layout: this lane holds 32 consecutive columns of row my_row
     if (p.bias) {
       if (col0 + 32 <= p.N && (((uintptr_t)(p.bias + col0)) & 15) == 0) {   // warp-uniform
@@ -292,7 +303,18 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
       }
       __syncwarp();
     }
-    if (p.c_bf16) {
+    if (p.c_planes) {
+      // hi box in the first, lo box in the second half of the staging box (each 32 rows x 64 B, SWIZZLE_64B)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint2 h0, l0, h1, l1;
+        split4_bf16(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], h0, l0);
+        split4_bf16(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], h1, l1);
+        const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+    } else if (p.c_bf16) {
       // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk index XOR-ed with (row / 2) % 4
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -315,6 +337,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const CUtensor
       else
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmc),
                      "r"(smem_u32(box)), "r"(col0), "r"(row0)
+                     : "memory");
+      if (p.c_planes)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmc_lo),
+                     "r"(smem_u32(box) + 2048), "r"(col0), "r"(row0)
                      : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ out,
                                                                  unsigned short* __restrict__ out16,
+                                                                 unsigned short* __restrict__ out16lo,
                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                  long long M, int D, float eps, float p, float inv_keep,
                                                                  unsigned long long seed, const unsigned long long* seed_ctr,
@@ -119,7 +120,14 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
         o.z = (s[i][2 % VEC] - mean) * rstd * g.z + b.z;
         o.w = (s[i][3 % VEC] - mean) * rstd * g.w + b.w;
         *reinterpret_cast<float4*>(out + (size_t)row * D + e) = o;
-        if (out16) *reinterpret_cast<uint2*>(out16 + (size_t)row * D + e) = pack4_bf16(o.x, o.y, o.z, o.w);
+        if (out16lo) {                                   // hi / lo planes for the p3 GEMMs
+          uint2 hi, lo;
+          split4_bf16(o.x, o.y, o.z, o.w, hi, lo);
+          *reinterpret_cast<uint2*>(out16 + (size_t)row * D + e) = hi;
+          *reinterpret_cast<uint2*>(out16lo + (size_t)row * D + e) = lo;
+        } else if (out16) {
+          *reinterpret_cast<uint2*>(out16 + (size_t)row * D + e) = pack4_bf16(o.x, o.y, o.z, o.w);
+        }
       } else {
         const int e = i * 32 + lane;
         out[(size_t)row * D + e] = (s[i][0] - mean) * rstd * __ldg(gamma + e) + __ldg(beta + e);
@@ -313,10 +321,13 @@ static int ln_wave_grid(K kernel, int dyn_smem, long long M) {
   return (int)(want < wave ? want : wave);
 }
 
-extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* beta,
-                                 float* out, void* out_bf16, float* mean, float* rstd, long long M, int D, float eps,
-                                 float drop_p, unsigned long long seed, unsigned site, void* stream) {
+extern "C" int msx_add_ln_fwd_p(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* beta,
+                                float* out, void* out_bf16, void* out_bf16_lo, float* mean, float* rstd, long long M, int D,
+                                float eps, float drop_p, unsigned long long seed, unsigned site, void* stream) {
   const float* y = reinterpret_cast<const float*>(y_any);
+  MSX_REQUIRE(!out_bf16_lo || out_bf16, "msx_add_ln_fwd_p: a lo plane needs the hi plane");
+  MSX_REQUIRE(((uintptr_t)out_bf16_lo & 7) == 0, "msx_add_ln_fwd_p: the lo plane must be 8-byte aligned");
+  unsigned short* out16lo = reinterpret_cast<unsigned short*>(out_bf16_lo);
   MSX_REQUIRE(x && y && gamma && beta && out && mean && rstd, "msx_add_ln_fwd: null pointer");
   MSX_REQUIRE(D % 32 == 0 && D >= 32, "msx_add_ln_fwd: D must be a multiple of 32");
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_add_ln_fwd: bad dropout");
@@ -327,7 +338,7 @@ extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, 
   MSX_REQUIRE(!(out_bf16 || y_bf16) || vec, "msx_add_ln_fwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* out16 = reinterpret_cast<unsigned short*>(out_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<ln_wave_grid(add_ln_fwd_kernel<V, P>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
+#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<ln_wave_grid(add_ln_fwd_kernel<V, P>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, out16lo, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -340,6 +351,12 @@ extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, 
 #undef LN_FWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
+}
+
+extern "C" int msx_add_ln_fwd_ex(const float* x, const void* y_any, int y_bf16, const float* gamma, const float* beta,
+                                 float* out, void* out_bf16, float* mean, float* rstd, long long M, int D, float eps,
+                                 float drop_p, unsigned long long seed, unsigned site, void* stream) {
+  return msx_add_ln_fwd_p(x, y_any, y_bf16, gamma, beta, out, out_bf16, nullptr, mean, rstd, M, D, eps, drop_p, seed, site, stream);
 }
 
 extern "C" int msx_add_ln_fwd(const float* x, const float* y, const float* gamma, const float* beta, float* out,

@@ -97,6 +97,16 @@ struct Philox {
 __device__ __forceinline__ unsigned long long msx_eff_seed(unsigned long long seed, const unsigned long long* ctr) {
   return ctr ? seed + __ldg(ctr) : seed;
 }
+// bf16 hi / lo planes (operands of the "p3" forward GEMMs: hi*hi + hi*lo + lo*hi on kind::f16, ~2^-17 per product):
+// hi = rn_bf16(x), lo = rn_bf16(x - hi), four values -> two packed 8-byte words (element 0 in the low half of .x)
+__device__ __forceinline__ void split4_bf16(float a, float b, float c, float d, uint2& hi, uint2& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(b), "f"(a));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(d), "f"(c));
+  const float ra = a - __uint_as_float(hi.x << 16), rb = b - __uint_as_float(hi.x & 0xFFFF0000u);
+  const float rc = c - __uint_as_float(hi.y << 16), rd = d - __uint_as_float(hi.y & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo.x) : "f"(rb), "f"(ra));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo.y) : "f"(rd), "f"(rc));
+}
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
 // Dropout keep-mask for elements 4*idx4 .. 4*idx4+3 of dropout site `site`: keep iff u >= p.  Forward and

@@ -29,6 +29,10 @@ SITE_STRIDE = 16     # dropout site ids: layer*SITE_STRIDE + {0: attention out, 
 #   tf32x3f   compensated FORWARD: encoder GEMMs 3xTF32, attention scores 3xTF32 -> loss / KL / latent means within the
 #             north star's 1e-3 with 10x margin; backward GEMMs, attention and the LSTM recurrence single-pass TF32
 #   bf16x3f   tf32x3f with the forward encoder GEMMs on the bf16x3 kernel (same forward accuracy class, faster)
+#   bf16p3f   tf32x3f with the forward encoder GEMMs on the p3 kernel: both operands arrive as bf16 hi / lo PLANES written by
+#             the kernels that produce them (embedding, LayerNorm, attention, FF1 epilogue; weights split once per step), the
+#             GEMM walks hi*hi + hi*lo + lo*hi on kind::f16 with no conversion stage (~2^-17 per product); the context and
+#             the FF hidden activation exist only as planes, their two weight gradients read the hi plane on kind::f16
 #   tf32      every tensor-core product single-pass TF32
 #   bf16      tf32 with the Transformer layers' GEMM operands stored as bfloat16
 PRECISIONS = {
@@ -36,6 +40,7 @@ PRECISIONS = {
     "fp32x3": (False, "x3", True, False, False),
     "tf32x3f": (True, "x3", False, True, True),
     "bf16x3f": (True, "b3", False, True, True),
+    "bf16p3f": (True, "p3", False, True, True),
     "tf32": (True, None, False, True, True),
     "bf16": (True, None, False, True, True),
 }
@@ -153,6 +158,24 @@ class ParamArena:
     def refresh_bf16_shadow(self):
         ops.cast_bf16(self.w, self.w16, self.numel)
 
+    def enable_p3_planes(self):
+        """bf16 hi / lo planes of w at the same element offsets (w16 = hi, w16lo = lo): the B operands of the p3 GEMMs."""
+        if self.w16 is None:
+            self.w16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.w.device)
+        self.w16lo = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.w.device)
+
+    def refresh_p3_planes(self):
+        ops.split_planes(self.w, self.w16, self.w16lo, self.numel)
+
+    def view16lo(self, name):
+        off, n, shape = self.offsets[name]
+        return self.w16lo[off:off + n].view(shape)
+
+    def span16lo(self, first, last):
+        a = self.offsets[first][0]
+        off, n, _ = self.offsets[last]
+        return self.w16lo[a:off + n]
+
     def view16(self, name):
         off, n, shape = self.offsets[name]
         return self.w16[off:off + n].view(shape)
@@ -251,6 +274,9 @@ class VAEEngine:
         self.arena.init_xavier(seed)
         if self.bf16:
             self.arena.enable_bf16_shadow()
+        self.p3 = self.x3_fwd == "p3"
+        if self.p3:
+            self.arena.enable_p3_planes()
         self.pe_enc = torch.from_numpy(positional_encodings(cfg.enc_size, max_len)).to(self.device)
         self.pe_dec = (torch.from_numpy(positional_encodings(cfg.dec_size, max_len)).to(self.device)
                        if cfg.dec_type == "transformer" else None)
@@ -319,7 +345,7 @@ class VAEEngine:
     def _gemm_mode(self, want_x3, A, lda, B, ldb, C, ldc, M, N, K):
         """"b3" (bf16x3 on tcgen05, forward form only), "x3" (3xTF32 on tcgen05), "tc" (single-pass TF32 on tcgen05) or None
         (exact FFMA kernel) for one GEMM.  want_x3: None / False, True or "x3", "b3"."""
-        if want_x3:
+        if want_x3:                             # "p3": GEMMs outside the planes layers (latent heads, tiny D) run 3xTF32
             if want_x3 == "b3" and ops.gemm_tc_b3_supported(A, lda, B, ldb, C, ldc, M, N, K):
                 return "b3"
             if ops.gemm_tc_x3_supported(A, lda, B, ldb, C, ldc, M, N, K):
@@ -330,13 +356,15 @@ class VAEEngine:
         return None
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
-                   accumulate_dx=False, dx_colsum=None):
+                   accumulate_dx=False, dx_colsum=None, skip_wgrad=False):
         """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy) (gb=None: the kernel that produced dy already added it),
         dx [M,K] (=|+=) dy w (optionally masked by aux).  dx_colsum: bias-gradient buffer of the layer whose
         pre-activation gradient dx is; returns True when the dgrad epilogue accumulated it (tensor path)."""
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
-        mode = self._gemm_mode(self.x3_bwd, dy, lddy, x, ldx, gw, K, N, K, M)
-        if mode:
+        mode = None if skip_wgrad else self._gemm_mode(self.x3_bwd, dy, lddy, x, ldx, gw, K, N, K, M)
+        if skip_wgrad:                          # the caller computes the weight gradient (planes layers: bf16 hi plane of x)
+            assert gb is None
+        elif mode:
             ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=mode == "x3")
             if gb is not None:
                 ops.colsum(dy, lddy, M, N, gb)
@@ -409,11 +437,17 @@ class VAEEngine:
         ldr = T * D if sos_only else D
         dev = self.device
         a = self.arena
-        f32 = torch.float32
-        qkv, ctx, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "ctx", (M, D), f32)], bf.t[(tag + "proj", (R, D), f32)]
+        f32, b16 = torch.float32, torch.bfloat16
+        # planes layer (_tf_layer_fwd_p3): the context and the hidden activation exist only as bf16 hi / lo planes; their
+        # weight gradients read the hi plane together with a bf16 copy of the output gradient (kind::f16, fp32 accumulate)
+        p3 = not decoder and self._layer_p3_ok(D)
+        qkv, proj = bf.t[(tag + "qkv", (M, 3 * D), f32)], bf.t[(tag + "proj", (R, D), f32)]
+        ctx = None if p3 else bf.t[(tag + "ctx", (M, D), f32)]
         x1, st1 = bf.t[(tag + "x1", (R, D), f32)], bf.t[(tag + "st1", (2, R), f32)]
-        h, f = bf.t[(tag + "h", (R, 4 * D), f32)], bf.t[(tag + "f", (R, D), f32)]
+        h, f = None if p3 else bf.t[(tag + "h", (R, 4 * D), f32)], bf.t[(tag + "f", (R, D), f32)]
         st2 = bf.t[(tag + "st2", (2, R), f32)]
+        df16 = bf.get(tag + "df16", (R, D), dev, b16) if p3 else None
+        dproj16 = bf.get(tag + "dproj16", (R, D), dev, b16) if p3 else None
         xres = bf.t[(tag + "xin_c", (B, D), f32)] if sos_only else x_in
         inv_keep = 1.0 / (1.0 - p) if p > 0 else 1.0
         ln2 = "ln3" if decoder else "ln2"
@@ -426,7 +460,7 @@ class VAEEngine:
         else:
             ops.add_ln_bwd(x1, f, self._W(prefix + ln2 + ".gamma"), st2[0], st2[1], dout, dx1, df if p > 0 else None,
                            self._G(prefix + ln2 + ".gamma"), self._G(prefix + ln2 + ".beta"), R, D, drop_p=p,
-                           seed=self.dropout_seed, site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"))
+                           seed=self.dropout_seed, site=site0 + 2, dybias=self._G(prefix + "ff.ff2.bias"), dy16=df16)
             if p <= 0:
                 df = dx1
         # ff2: f = h W2^T + b2
@@ -437,9 +471,11 @@ class VAEEngine:
             aux, ldaux = bf.t[(tag + "hmask", (R, (4 * D + 31) // 32), torch.int32)], 4 * D // 32
         else:
             aux, ldaux = h, 4 * D
+        if p3:
+            self._wgrad16(df16, D, bf.t[(tag + "h_p", (2, R, 4 * D), b16)][0], 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, R)
         fused = self._dense_bwd(df, D, R, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
                                 None, D, 4 * D, dx=dh, lddx=4 * D, aux=aux, ldaux=ldaux, aux_scale=inv_keep,
-                                dx_colsum=self._G(prefix + "ff.ff1.bias"))
+                                dx_colsum=self._G(prefix + "ff.ff1.bias"), skip_wgrad=p3)
         # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
         self._dense_bwd(dh, 4 * D, R, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
                         None if fused else self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D,
@@ -449,14 +485,18 @@ class VAEEngine:
         dproj = bf.get(tag + "dproj", (R, D), dev)
         ops.add_ln_bwd(xres, proj, self._W(prefix + "ln1.gamma"), st1[0], st1[1], dx1, dres, dproj if p > 0 else None,
                        self._G(prefix + "ln1.gamma"), self._G(prefix + "ln1.beta"), R, D, drop_p=p,
-                       seed=self.dropout_seed, site=site0, dybias=self._G(prefix + "self_attention.W_proj.bias"))
+                       seed=self.dropout_seed, site=site0, dybias=self._G(prefix + "self_attention.W_proj.bias"),
+                       dy16=dproj16)
         if p <= 0:
             dproj = dres
         # sos_only: the context gradient is non-zero at rows b*T only; the dgrad writes exactly those rows of a buffer that
         # was zero-filled when it was created and is written by nothing else
         dctx = bf.get_zero(tag + "dctx_sos", (M, D), dev) if sos_only else bf.get(tag + "dctx", (M, D), dev)
+        if p3:
+            self._wgrad16(dproj16, D, bf.t[(tag + "ctx_p", (2, M, D), b16)][0], ldr,
+                          self._G(prefix + "self_attention.W_proj.weight"), D, D, R)
         self._dense_bwd(dproj, D, R, ctx, ldr, self._W(prefix + "self_attention.W_proj.weight"),
-                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=ldr)
+                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=ldr, skip_wgrad=p3)
         dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
@@ -473,6 +513,67 @@ class VAEEngine:
         self._dense_bwd(dqkv, 3 * D, M, x_in, D, wqkv, gwqkv, gbqkv, 3 * D, D, dx=dx_in, lddx=D, accumulate_dx=not sos_only)
         if sos_only:
             ops.rows_strided(dres, D, dx_in, T * D, B, D, add=True)
+
+    # ------------------------------------------------------------------ transformer layer, hi / lo plane operands (p3)
+    def _layer_p3_ok(self, D):
+        """p3 GEMM operands need K % 64 == 0 and the vectorised LayerNorm path (D % 128 == 0)."""
+        return self.p3 and D % 128 == 0
+
+    def _tf_layer_fwd_p3(self, bf, tag, prefix, x_in, x_in_p, mask, B, T, D, H, p, site0, decoder, sos_only=False):
+        """_tf_layer_fwd with every GEMM operand as bf16 hi / lo planes (msx_gemm_tc_p3): x_in_p [2, B*T, D] comes from the
+        kernel that produced x_in; the context and the FF hidden activation exist ONLY as planes; qkv, the projection
+        output, f, the residual stream and the LayerNorm arithmetic are fp32.  Returns (out fp32, out planes)."""
+        M = B * T
+        R = B if sos_only else M
+        ldr = T * D if sos_only else D
+        dev, a, b16 = self.device, self.arena, torch.bfloat16
+        seed = self.dropout_seed
+        qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
+        kq, vq = prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight"
+        bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
+        ops.gemm_tc_p3(x_in_p[0], x_in_p[1], D, a.span16(kq, vq), a.span16lo(kq, vq), D, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
+        ctxp = bf.get(tag + "ctx_p", (2, M, D), dev, b16)
+        if ops.attention_tc_supported(qkv, T, D // H):
+            ops.attention_tc_fwd(qkv, mask, ctxp[0], B, T, H, D // H, x3_scores=True, ctx_lo=ctxp[1])
+        else:                                           # longer rows: fp32 context from the kernel that takes them, one split
+            ctx = bf.get(tag + "ctx", (M, D), dev)
+            if ops.attention_tcl_supported(qkv, T, D // H):
+                ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
+            else:
+                ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
+            ops.split_planes(ctx, ctxp[0], ctxp[1])
+        if sos_only:
+            xres = bf.get(tag + "xin_c", (B, D), dev)
+            ops.rows_strided(x_in, T * D, xres, D, B, D)
+        else:
+            xres = x_in
+        wn = prefix + "self_attention.W_proj.weight"
+        proj = bf.get(tag + "proj", (R, D), dev)
+        ops.gemm_tc_p3(ctxp[0], ctxp[1], ldr, a.view16(wn), a.view16lo(wn), D, proj, D, R, D, D,
+                       bias=self._W(prefix + "self_attention.W_proj.bias"))
+        x1 = bf.get(tag + "x1", (R, D), dev)
+        x1p = bf.get(tag + "x1_p", (2, R, D), dev, b16)
+        st1 = bf.get(tag + "st1", (2, R), dev)
+        ops.add_ln_fwd(xres, proj, self._W(prefix + "ln1.gamma"), self._W(prefix + "ln1.beta"), x1, st1[0], st1[1], R, D,
+                       drop_p=p, seed=seed, site=site0, out16=x1p[0], out16lo=x1p[1])
+        hp = bf.get(tag + "h_p", (2, R, 4 * D), dev, b16)
+        hmask = bf.get(tag + "hmask", (R, 4 * D // 32), dev, torch.int32)     # ReLU / dropout bit mask for the FF2 dgrad
+        wn = prefix + "ff.ff1.weight"
+        ops.gemm_tc_p3(x1p[0], x1p[1], D, a.view16(wn), a.view16lo(wn), D, hp[0], 4 * D, R, 4 * D, D,
+                       bias=self._W(prefix + "ff.ff1.bias"), relu=True, drop_p=p, seed=seed, site=site0 + 1, mask_out=hmask,
+                       ldmask=4 * D // 32, C_lo=hp[1])
+        self._hmask_ok[tag] = True
+        wn = prefix + "ff.ff2.weight"
+        f = bf.get(tag + "f", (R, D), dev)
+        ops.gemm_tc_p3(hp[0], hp[1], 4 * D, a.view16(wn), a.view16lo(wn), 4 * D, f, D, R, D, 4 * D,
+                       bias=self._W(prefix + "ff.ff2.bias"))
+        out = bf.get(tag + "out", (R, D), dev)
+        outp = bf.get(tag + "out_p", (2, R, D), dev, b16)
+        st2 = bf.get(tag + "st2", (2, R), dev)
+        ln2 = "ln3" if decoder else "ln2"
+        ops.add_ln_fwd(f if decoder else x1, f, self._W(prefix + ln2 + ".gamma"), self._W(prefix + ln2 + ".beta"), out,
+                       st2[0], st2[1], R, D, drop_p=p, seed=seed, site=site0 + 2, out16=outp[0], out16lo=outp[1])
+        return out, outp
 
     # ------------------------------------------------------------------ transformer layer, bf16 variant
     def _layer16_ok(self, D):
@@ -618,9 +719,15 @@ class VAEEngine:
         x16 = bf.get("enc.x0_16", (M, D), dev, torch.bfloat16) if l16 else None
         if l16:
             self.arena.refresh_bf16_shadow()          # 8 MB read + 4 MB written per step; always current, also under graphs
+        xlo = None
+        if self._layer_p3_ok(D):                      # hi / lo planes of the embedded rows and of the weights
+            xp = bf.get("enc.x0_p", (2, M, D), dev, torch.bfloat16)
+            x16, xlo = xp[0], xp[1]
         ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
                       self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V,
-                      out16=x16)
+                      out16=x16, out16lo=xlo)
+        if xlo is not None:
+            x16 = xp
         return self._encode_layers(bf, x, x16, mask, B, T, p_drop)
 
     def _encode_layers(self, bf, x, x16, mask, B, T, p_drop):
@@ -628,11 +735,20 @@ class VAEEngine:
         model.py:97-103)."""
         cfg, dev = self.cfg, self.device
         D, Z = cfg.enc_size, cfg.latent
-        l16 = x16 is not None
+        l16 = x16 is not None and not self._layer_p3_ok(D)
+        if self._layer_p3_ok(D):
+            self.arena.refresh_p3_planes()               # weights -> hi / lo planes: 8 MB read + 8 MB written per step
         xs = [x]
         self._xs16 = [x16]
         for l in range(cfg.enc_layers):
-            if l16:
+            if self._layer_p3_ok(D):
+                if x16 is None:                          # an input no kernel wrote as planes (the roll path's dense embedding)
+                    x16 = bf.get("enc.x0_p", (2, B * T, D), dev, torch.bfloat16)
+                    ops.split_planes(x, x16[0], x16[1])
+                x, x16 = self._tf_layer_fwd_p3(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
+                                               cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
+                self._xs16.append(x16)
+            elif l16:
                 x, x16 = self._tf_layer_fwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
                                               cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
                 self._xs16.append(x16)

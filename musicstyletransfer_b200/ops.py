@@ -76,6 +76,32 @@ def gemm_tc_b3(A, lda, B, ldb, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0
                  M, N, K, " acc" if accumulate else "", " mask" if mask_out is not None else "")))
 
 
+def gemm_tc_p3_supported(A_hi, lda, B_hi, ldb, Cm, ldc, M, N, K):
+    return bool(lib.load().msx_gemm_tc_p3_supported(P(A_hi), _i(lda), P(B_hi), _i(ldb), P(Cm), _i(ldc),
+                                                    _i(2 if Cm.dtype == torch.bfloat16 else 0), _i(M), _i(N), _i(K)))
+
+
+def gemm_tc_p3(A_hi, A_lo, lda, B_hi, B_lo, ldb, Cm, ldc, M, N, K, bias=None, relu=False, drop_p=0.0, seed=0, site=0,
+               accumulate=False, mask_out=None, ldmask=0, C_lo=None):
+    """Forward Dense GEMM Cm = A[M,K] @ B[N,K]^T from bf16 hi / lo planes of both operands (msx_gemm_tc_p3: three walks
+    hi*hi + hi*lo + lo*hi on kind::f16).  Cm fp32, or bfloat16 together with C_lo: the result leaves as planes."""
+    assert A_hi.dtype == A_lo.dtype == B_hi.dtype == B_lo.dtype == torch.bfloat16
+    planes = C_lo is not None
+    assert planes == (Cm.dtype == torch.bfloat16)
+    nbytes = 4.0 * (M * K + N * K) + M * N * 4.0 * (1 + (1 if accumulate else 0)) + (M * N / 8.0 if mask_out is not None else 0)
+    lib.call("msx_gemm_tc_p3", P(A_hi), P(A_lo), _i(lda), P(B_hi), P(B_lo), _i(ldb), P(Cm), P(C_lo), _i(ldc),
+             _i(2 if planes else 0), _i(M), _i(N), _i(K), P(bias), _i(1 if relu else 0), _f(drop_p), _u64(seed), _u32(site),
+             _i(1 if accumulate else 0), P(mask_out), _i(ldmask), lib.stream_ptr(),
+             tag=(2.0 * M * N * K, nbytes, "bf16p3 M=%d N=%d K=%d tA=0 tB=1 sk=1%s%s%s" % (
+                 M, N, K, " acc" if accumulate else "", " mask" if mask_out is not None else "", " cplanes" if planes else "")))
+
+
+def split_planes(src, hi, lo, n=None):
+    """hi = rn_bf16(src), lo = rn_bf16(src - hi) (bfloat16 planes of an fp32 tensor, n % 4 == 0)."""
+    assert src.dtype == torch.float32 and hi.dtype == lo.dtype == torch.bfloat16
+    lib.call("msx_split_planes", P(src), P(hi), P(lo), _ll(src.numel() if n is None else n), lib.stream_ptr())
+
+
 def gemm_tc_x3_supported(A, lda, B, ldb, Cm, ldc, M, N, K):
     return bool(lib.load().msx_gemm_tc_x3_supported(P(A), _i(lda), P(B), _i(ldb), P(Cm), _i(ldc), _i(M), _i(N), _i(K)))
 
@@ -185,10 +211,11 @@ def attention_tc_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tc_supported(P(qkv), _i(T), _i(dh)))
 
 
-def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False):
+def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False, ctx_lo=None):
     """ctx: fp32, or bfloat16 (bf16 variant: the context only feeds the W_proj GEMMs).  x3_scores: S = K Q^T with 3xTF32
-    operand splitting (fp32-equivalent scores; the softmax turns their absolute error into a relative error of P)."""
-    lib.call("msx_attention_tc_fwd_ex2", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0),
+    operand splitting (fp32-equivalent scores; the softmax turns their absolute error into a relative error of P).
+    ctx_lo: bfloat16 lo plane next to a bfloat16 ctx (= hi plane), the operands of the p3 W_proj GEMM."""
+    lib.call("msx_attention_tc_fwd_p", P(qkv), P(mask), P(ctx), P(ctx_lo), _i(1 if ctx.dtype == torch.bfloat16 else 0),
              _i(1 if x3_scores else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
@@ -217,10 +244,10 @@ def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):
     lib.call("msx_attention_bwd", P(qkv), P(mask), P(dctx), P(dqkv), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
-def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0, out16=None):
-    """out16: optional bfloat16 copy of the output (operand of the bf16 GEMMs)."""
-    lib.call("msx_add_ln_fwd_ex", P(x), P(y), _i(1 if y.dtype == torch.bfloat16 else 0), P(gamma), P(beta), P(out), P(out16),
-             P(mean), P(rstd), _ll(M), _i(D), _f(eps),
+def add_ln_fwd(x, y, gamma, beta, out, mean, rstd, M, D, eps=1e-5, drop_p=0.0, seed=0, site=0, out16=None, out16lo=None):
+    """out16: optional bfloat16 copy of the output (operand of the bf16 GEMMs); with out16lo: its hi / lo planes."""
+    lib.call("msx_add_ln_fwd_p", P(x), P(y), _i(1 if y.dtype == torch.bfloat16 else 0), P(gamma), P(beta), P(out), P(out16),
+             P(out16lo), P(mean), P(rstd), _ll(M), _i(D), _f(eps),
              _f(drop_p), _u64(seed), _u32(site), lib.stream_ptr())
 
 
@@ -234,9 +261,9 @@ def add_ln_bwd(x, y, gamma, mean, rstd, dout, dres, dy, dgamma, dbeta, M, D, dro
 
 
 def embed_fwd(tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, mask, B, T, D, prefix, scale, vocab,
-              out16=None):
-    lib.call("msx_embed_fwd_ex", P(tokens), P(classes), P(seq_lens), P(tok_emb), P(cls_emb), P(prefix_vec), P(pe),
-             P(out), P(out16), P(mask), _i(B), _i(T), _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
+              out16=None, out16lo=None):
+    lib.call("msx_embed_fwd_p", P(tokens), P(classes), P(seq_lens), P(tok_emb), P(cls_emb), P(prefix_vec), P(pe),
+             P(out), P(out16), P(out16lo), P(mask), _i(B), _i(T), _i(D), _i(prefix), _f(scale), _i(vocab), lib.stream_ptr())
 
 
 def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, prefix, scale, vocab):

@@ -19,8 +19,9 @@ def run():
     assert np.array_equal(tok.cpu().numpy(), otok) and np.array_equal(roll.cpu().numpy(), oroll)
     assert np.array_equal(cnt.cpu().numpy(), ocnt)
     # one train step of the scripts/train-vae.sh model (enc 2x256 / 8 heads, Z = 256, LSTM decoder 1x128; B = 64, T = 65)
-    # on the paths the bench times: precision "tf32" (gemm_tc2 / gemm_tc, attn_tc_*, lstm_tc_* kernels) and the strict-fp32
-    # "fp32x3" mode (gemm_tc2x3), both against the fp32 oracle at the north star's 1e-3
+    # on the paths the bench times: the headline mode "bf16p3f" (gemm_tc2 / gemm_tc on kind::f16 planes forward and
+    # kind::tf32 backward, attn_tc_* with compensated scores, lstm_tc_*) and the strict-fp32 "fp32x3" mode (gemm_tc2x3),
+    # both against the fp32 oracle at the north star's 1e-3
     cfg_o = om.Cfg(dec_type="lstm")
     params = om.init_params(cfg_o, seed=0)
     Z = cfg_o.latent
@@ -32,7 +33,7 @@ def run():
     _, ce, kl, _, means, _ = om.step_losses(cfg_o, params, f(tokens), f(lens), f(classes), f(labels), eps)
     rel = lambda a, b: float((a.float().cpu() - b).abs().max() / b.abs().max())
     msg = []
-    for precision in ("tf32", "fp32x3"):
+    for precision in ("bf16p3f", "fp32x3"):
         eng = VAEEngine(VAEConfig(dec_type="lstm"), dev, precision=precision)
         eng.arena.load_state(params)
         out = eng.train_step(t(tokens), t(lens), t(classes), t(labels), eps=eps.to(dev), clip_gradient=1.0)

@@ -55,10 +55,10 @@ def _engine(precision, params, dropout=0.0, dec_type="lstm", seed=0):
     return eng
 
 
-FWD_TOL = {"tf32x3f": 3e-4, "bf16x3f": 3e-4, "fp32x3": 1e-4, "tf32": 2.5e-3}
+FWD_TOL = {"tf32x3f": 3e-4, "bf16x3f": 3e-4, "bf16p3f": 3e-4, "fp32x3": 1e-4, "tf32": 2.5e-3}
 
 
-@pytest.mark.parametrize("precision", ["tf32x3f", "bf16x3f", "fp32x3", "tf32"])
+@pytest.mark.parametrize("precision", ["tf32x3f", "bf16x3f", "bf16p3f", "fp32x3", "tf32"])
 @pytest.mark.parametrize("B,seed,conditioned", [(2048, 0, False), (512, 1, False), (512, 2, False), (512, 3, False),
                                                 (512, 1, True), (512, 2, True), (512, 3, True)])
 def test_bench_shape_forward_vs_oracle(precision, B, seed, conditioned):
@@ -89,7 +89,7 @@ def test_bench_shape_forward_vs_oracle(precision, B, seed, conditioned):
         assert tot < tol, tot
 
 
-@pytest.mark.parametrize("precision,gtol,gmean", [("tf32x3f", 5e-2, 2e-2), ("bf16x3f", 5e-2, 2e-2), ("tf32", 5e-2, 2e-2),
+@pytest.mark.parametrize("precision,gtol,gmean", [("tf32x3f", 5e-2, 2e-2), ("bf16x3f", 5e-2, 2e-2), ("bf16p3f", 5e-2, 2e-2), ("tf32", 5e-2, 2e-2),
                                                   ("fp32x3", 1e-3, None)])
 def test_bench_shape_gradients_vs_oracle(precision, gtol, gmean):
     """Every parameter gradient of a B = 512 bench-shaped step (conditioned sigma) against the oracle's autograd."""
@@ -153,7 +153,7 @@ def _device_eps(B, Z, seed):
     return eps.cpu()
 
 
-@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-3), ("tf32x3f", 5e-2), ("bf16x3f", 5e-2), ("tf32", 5e-2), ("fp32x3", 1e-3)])
+@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-3), ("tf32x3f", 5e-2), ("bf16x3f", 5e-2), ("bf16p3f", 5e-2), ("tf32", 5e-2), ("fp32x3", 1e-3)])
 def test_dropout_step_vs_oracle_with_device_masks(precision, gtol):
     """The train step as bench.py runs it (dropout 0.2): the oracle replays the step with the device's own keep masks
     (msx_dropout_mask) and eps (msx_normal_fill) -> losses, latent means and every gradient agree."""
@@ -352,3 +352,82 @@ def test_lstm_tc_vs_oracle_lstm_layer(B, T):
     dev["dW_h2h"] = rel(dW.float(), po["l0_h2h_weight"].grad)
     print("lstm_tc vs oracle B=%d T=%d:" % (B, T), dev)
     assert dev["hs"] < 3e-3 and dev["dtv"] < 1e-2 and dev["dbh"] < 1e-2 and dev["dbi"] < 1e-2 and dev["dW_h2h"] < 1e-2, dev
+
+
+def _planes(x):
+    from musicstyletransfer_b200 import ops
+    hi, lo = torch.empty_like(x, dtype=torch.bfloat16), torch.empty_like(x, dtype=torch.bfloat16)
+    ops.split_planes(x, hi, lo)
+    return hi, lo
+
+
+def test_split_planes_carry_16_mantissa_bits():
+    from musicstyletransfer_b200 import ops  # noqa: F401
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(1024, 256, device="cuda", generator=g) * torch.logspace(-6, 3, 256, device="cuda")
+    hi, lo = _planes(x)
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
+    rel = ((hi.double() + lo.double() - x.double()).abs() / x.double().abs().clamp(min=1e-30)).max()
+    assert float(rel) < 2.0 ** -16, float(rel)
+
+
+@pytest.mark.parametrize("N,K", [(768, 256), (1024, 256), (256, 1024)])
+def test_gemm_tc_p3_at_bench_rows(N, K):
+    """msx_gemm_tc_p3 (operands as bf16 hi / lo planes, hi*hi + hi*lo + lo*hi walks on kind::f16) on the step's forward
+    shapes at the bench's M = 133 120 rows against float64."""
+    from musicstyletransfer_b200 import ops
+    M = 2048 * 65
+    g = torch.Generator(device="cuda").manual_seed(N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.empty(M, N, device="cuda")
+    (Ah, Al), (Wh, Wl) = _planes(A), _planes(W)
+    assert ops.gemm_tc_p3_supported(Ah, K, Wh, K, C, N, M, N, K)
+    ops.gemm_tc_p3(Ah, Al, K, Wh, Wl, K, C, N, M, N, K, bias=bias)
+    torch.cuda.synchronize()
+    rows = torch.cat([torch.arange(0, 4096), torch.arange(M // 2, M // 2 + 2048), torch.arange(M - 4096, M)]).cuda()
+    ref = A[rows].double() @ W.double().t() + bias.double()
+    err = float((C[rows].double() - ref).abs().max() / ref.abs().max())
+    print("bf16p3 M=%d N=%d K=%d: max err / max = %.3e" % (M, N, K, err))
+    assert err < 2e-5, err
+    assert torch.isfinite(C).all()
+
+
+@pytest.mark.parametrize("M,N,K,relu,acc,cplanes", [(37, 293, 128, False, False, False), (300, 64, 64, True, False, False),
+                                                    (2048, 256, 256, False, True, False), (1, 128, 64, False, False, False),
+                                                    (513, 1024, 192, True, False, True), (129, 320, 1024, False, False, True),
+                                                    (4160, 1024, 256, True, False, True)])
+def test_gemm_tc_p3_shapes_and_epilogues(M, N, K, relu, acc, cplanes):
+    """1-CTA and pair kernels, M below one tile, N that pads, ReLU + dropout-free bit mask, accumulate, result as planes."""
+    from musicstyletransfer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g)
+    ldc = (N + 7) // 8 * 8
+    C0 = torch.randn(M, ldc, device="cuda", generator=g)
+    (Ah, Al), (Wh, Wl) = _planes(A), _planes(W)
+    mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda") if (relu and N % 32 == 0) else None
+    if cplanes:
+        Ch = torch.zeros(M, ldc, device="cuda", dtype=torch.bfloat16)
+        Cl = torch.zeros(M, ldc, device="cuda", dtype=torch.bfloat16)
+        ops.gemm_tc_p3(Ah, Al, K, Wh, Wl, K, Ch, ldc, M, N, K, bias=bias, relu=relu, mask_out=mask, ldmask=N // 32, C_lo=Cl)
+        C = Ch.float() + Cl.float()
+    else:
+        C = C0.clone()
+        ops.gemm_tc_p3(Ah, Al, K, Wh, Wl, K, C, ldc, M, N, K, bias=None if acc else bias, relu=relu, accumulate=acc,
+                       mask_out=mask, ldmask=N // 32)
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t()
+    ref = ref + (C0[:, :N].double() if acc else bias.double())
+    if relu:
+        ref = ref.clamp(min=0)
+    err = float((C[:, :N].double() - ref).abs().max() / ref.abs().max())
+    assert err < 3e-5, err
+    if mask is not None:
+        bits = ((mask.view(M, N // 32, 1) >> torch.arange(32, device="cuda").view(1, 1, 32)) & 1).view(M, N).bool()
+        want = ref > 0
+        near = ref.abs() < 1e-4 * ref.abs().max()
+        assert bool(((bits == want) | near).all())

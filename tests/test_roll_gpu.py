@@ -54,7 +54,7 @@ def test_roll_features_match_oracle():
     assert torch.equal(renc.cpu().view(5, 8, 132), want_e) and torch.equal(rdec.cpu().view(5, 7, 132), want_d)
 
 
-@pytest.mark.parametrize("precision,ftol,gtol", [("fp32", 1e-4, 1e-3), ("fp32x3", 1e-4, 1e-3), ("tf32x3f", 3e-4, 5e-2)])
+@pytest.mark.parametrize("precision,ftol,gtol", [("fp32", 1e-4, 1e-3), ("fp32x3", 1e-4, 1e-3), ("tf32x3f", 3e-4, 5e-2), ("bf16p3f", 3e-4, 5e-2)])
 @pytest.mark.parametrize("smoothing,downweight", [(0.0, True), (0.1, False)])
 def test_roll_step_vs_oracle(precision, ftol, gtol, smoothing, downweight):
     cfg_o = om.Cfg(dec_type="lstm")                        # scripts/train-vae.sh sizes: enc 2x256/8h, Z=256, dec 1x128

@@ -21,7 +21,7 @@ def _batch(B, T):
     return d(tokens), d(lens), d(classes), d(labels)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp32x3", "tf32x3f", "bf16x3f", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32x3", "tf32x3f", "bf16x3f", "bf16p3f", "tf32", "bf16"])
 @pytest.mark.parametrize("dec_type", ["lstm", "transformer"])
 def test_small_train_step(precision, dec_type):
     from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
