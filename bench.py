@@ -459,6 +459,8 @@ def run_ours(args):
                         "MMAs per k-block, cta_group::2 pair tiles, TMA)",
               "bf16x3": "gemm_tc2b3_kernel (msx_gemm_tc_b3: fp32 operands split into bf16 hi + lo inside the kernel, three tcgen05 "
                         "kind::f16 MMAs per k-step, cta_group::2 pair tiles, TMA)",
+              "bf16p3": "gemm_tc2_kernel / gemm_tc_kernel (msx_gemm_tc_p3: operands as bf16 hi + lo planes from the producing kernels, "
+                        "three walks hi*hi + hi*lo + lo*hi of the reduction on tcgen05 kind::f16, cta_group::2 pair tiles, TMA)",
               "ffma": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)", "f32": "sgemm_kernel (msx_gemm_f32, fp32 FFMA path)"}
         groups = {}
         for a_, b_, f_ in prof["events"]:
@@ -473,7 +475,7 @@ def run_ours(args):
             common = {"kernel": KN.get(kind, kind), "share_of_step": tms / step_ms, "launches_per_step": cnt / psteps,
                       "avg_launch_ms": tms / cnt, "algorithmic_bytes_per_launch": by / cnt, "algorithmic_flops_per_launch": fl / cnt,
                       "measured": "CUDA events around every launch of %d eager steps (the graph-replayed step is what `value` times)" % psteps}
-            if kind == "bf16x3":
+            if kind in ("bf16x3", "bf16p3"):
                 # three kind::f16 MMAs per multiply-add = 1.5 TF32-equivalents: on these shapes the kernel is back under the
                 # HBM roof of its fp32 operand / result bytes
                 rl.append(dict(common, bound="hbm", achieved=gbk, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbk / peaks["hbm_gbs"],
