@@ -193,9 +193,12 @@ int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int 
 int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B, int T, int H,
                              int dh, void* stream);
 /* p3 planes: ctx (bfloat16, ctx_bf16 != 0) receives the hi plane rn_bf16(o) and ctx_lo (optional) rn_bf16(o - hi): the two
- * operands of the p3 W_proj GEMM (msx_gemm_tc_p3); the context then never exists in fp32. */
-int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores, int B,
-                           int T, int H, int dh, void* stream);
+ * operands of the p3 W_proj GEMM (msx_gemm_tc_p3); the context then never exists in fp32.
+ * q0_only (d_h == 32): only the context row of query 0 of every sequence is computed and written (the encoder's top layer is
+ * read at position 0 only, model.py:97-100): scores and the query-axis softmax as before, then O[0] = sum_k P[k][0] V[k]
+ * as a reduction over the key rows; the other rows of ctx are left untouched. */
+int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores,
+                           int q0_only, int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
                             int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);

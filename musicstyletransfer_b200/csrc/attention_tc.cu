@@ -21,6 +21,7 @@ struct AttnTcParams {
   const float* mask;   // [B*T]
   float* ctx;          // [B*T, H*32] fp32, or bf16 when out_bf16 (the operand of the bf16 W_proj GEMM)
   void* ctx_lo;        // optional (out_bf16 only): lo plane, ctx then holds the hi plane (operands of the p3 W_proj GEMM)
+  const float* qkv;    // Q0 kernels only: the V rows are read straight from the projection
   int out_bf16;
   int T, H, TQ, TK;    // TQ = roundup16(T) (MMA N), TK = roundup8(T) (reduction length of MMA 2)
   int dh;              // head width: 32, or 16 ("half heads": 32-wide tiles are still loaded, the score MMAs reduce over the
@@ -74,7 +75,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // with exact ones).  With X3 the K / Q tiles arrive as raw fp32 (FLOAT32 maps), the issuer warp writes their lo parts
 // (x - trunc_tf32(x), element-wise, so the TMA swizzle is preserved) to a second pair of tiles and MMA 1 accumulates
 // K_lo Q_hi + K_hi Q_lo + K_hi Q_hi (kind::tf32 reads the raw words truncated = hi): fp32-equivalent scores.
-template <int NCH, int G, bool STAGE, int kDh, bool X3>
+// Q0 (the encoder's top layer, whose output is read at position 0 only, model.py:97-100): only the context row of
+// query 0 is produced.  The scores and the query-axis softmax still cover every query (each key row's normaliser), but
+// O[0] = sum_k P[k][0] V[k] is a reduction over the key rows: no P tile, no MMA 2, no V tile, one 128-byte row stored per
+// (batch, head) instead of T rows.
+template <int NCH, int G, bool STAGE, int kDh, bool X3, bool Q0 = false>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(128 * G, 1)
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ unsigned long long bars_all[G][6];            // kq, v0, v1, s_full, o_full, p_ready
   __shared__ unsigned tmem_slot;
+  __shared__ float red_q0[Q0 ? G : 1][2][4][32];           // Q0: per-warp partial sums of P[k][0] V[k], double-buffered
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform as far as the compiler can tell
@@ -153,8 +159,10 @@ __global__ void __launch_bounds__(128 * G, 1)
       mbar_expect_tx(bar_kq, (unsigned)((TK + TQ) * 128));
       tma_load_2d(sK, &tmK, bar_kq, h * kDh, b * T);
       tma_load_2d(sQ, &tmQ, bar_kq, D + h * kDh, b * T);
-      mbar_expect_tx(&bar_v[0], (unsigned)slab);
-      tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * kDh, b * T);
+      if (!Q0) {
+        mbar_expect_tx(&bar_v[0], (unsigned)slab);
+        tma_load_2d(sV, &tmV, &bar_v[0], 2 * D + h * kDh, b * T);
+      }
     }
     __syncwarp();
   }
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(128 * G, 1)
           }
         }
         umma_commit(bar_s);
-        if (nxt < p.items) {                               // V of the next item into the other V buffer (free since o_full(n-1))
+        if (!Q0 && nxt < p.items) {                        // V of the next item into the other V buffer (free since o_full(n-1))
           mbar_expect_tx(&bar_v[(n + 1) & 1], (unsigned)slab);
           tma_load_2d(sV + ((n + 1) & 1) * slab, &tmV, &bar_v[(n + 1) & 1], 2 * D + h2 * kDh, b2 * T);
         }
@@ -221,6 +229,16 @@ __global__ void __launch_bounds__(128 * G, 1)
       const int k = gt;                                    // this thread's key row
       const bool valid = k < T;
       const float rowmask = (valid && mraw > 0.f) ? 0.f : -1e9f;
+      float vrow[Q0 ? 32 : 1];
+      if (Q0) {                                            // this key's V row, in flight while MMA 1 runs (rows >= T: any finite row)
+        const float4* vp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + min(k, T - 1)) * 3 * D + 2 * D + h * kDh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v4 = __ldg(vp + j);
+          vrow[(4 * j) % (Q0 ? 32 : 1)] = v4.x; vrow[(4 * j + 1) % (Q0 ? 32 : 1)] = v4.y;
+          vrow[(4 * j + 2) % (Q0 ? 32 : 1)] = v4.z; vrow[(4 * j + 3) % (Q0 ? 32 : 1)] = v4.w;
+        }
+      }
       mbar_wait(bar_s, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the key row's TQ scores live in registers: softmax over the QUERY axis is thread-local
@@ -247,7 +265,14 @@ __global__ void __launch_bounds__(128 * G, 1)
         sum4[j & 3] += sc[j];
       }
       const float inv = valid ? 1.f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) : 0.f;
-      if (k < TK) {                                        // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
+      if (Q0) {                                            // this warp's share of O[0] = sum_k P[k][0] V[k]: lane j <- column j
+        const float p0 = sc[0] * inv;
+        float t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = vrow[j % (Q0 ? 32 : 1)] * p0;
+        red_q0[Q0 ? g : 0][n & 1][warp & 3][lane] = warp_colsum32(t, lane);
+      }
+      if (!Q0 && k < TK) {                                 // rows T..TK-1 are the zero padding of MMA 2's reduction dimension
 #pragma unroll
         for (int j = 0; j < TQ; j += 4)
           *reinterpret_cast<float4*>(sP + mn_major_off(j, k, TK)) =
@@ -255,9 +280,34 @@ __global__ void __launch_bounds__(128 * G, 1)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (Q0) {
+      red_q0[Q0 ? g : 0][n & 1][warp & 3][lane] = 0.f;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);                     // this warp's rows of P are staged (and its reads of S, O(n-1) are done)
+    if (Q0) {
+      // the issuer may overwrite S (MMA 1 of the next item) once every warp has read its rows: p_ready says so
+      if (issuer) mbar_wait(bar_p, par);
+      group_sync(g);                                       // the four partial sums are in place
+      if ((warp & 3) == 0 && lane < kDh) {
+        const float (*r)[32] = red_q0[Q0 ? g : 0][n & 1];
+        const float o = (r[0][lane] + r[1][lane]) + (r[2][lane] + r[3][lane]);
+        const size_t e = (size_t)b * T * D + h * kDh + lane;
+        if (p.out_bf16) {
+          unsigned hi, lo;
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(0.f), "f"(o));
+          reinterpret_cast<unsigned short*>(p.ctx)[e] = (unsigned short)(hi & 0xFFFFu);
+          if (p.ctx_lo) {
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(0.f), "f"(o - __uint_as_float(hi << 16)));
+            reinterpret_cast<unsigned short*>(p.ctx_lo)[e] = (unsigned short)(lo & 0xFFFFu);
+          }
+        } else {
+          p.ctx[e] = o;
+        }
+      }
+      continue;                                            // next item: red_q0[(n + 1) & 1]; this buffer is rewritten at n + 2,
+                                                           // behind the group barrier of item n + 1
+    }
     if (issuer) {
       mbar_wait(bar_p, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -827,7 +877,7 @@ extern "C" int msx_attention_tc_supported(const float* qkv, int T, int dh) {
 
 namespace {
 template <int NCH, int G, bool X3>
-int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& tv, AttnTcParams p, cudaStream_t st) {
+int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& tv, AttnTcParams p, cudaStream_t st, bool q0 = false) {
   // the last group's MMA descriptors address 128 K rows / 4 P slabs: keep the tail inside the allocation
   const size_t smem = 1024 + (size_t)G * p.group_bytes + 16 * 1024;
   p.smem_bytes = (int)smem - 1024;
@@ -836,7 +886,10 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
   const int grid = want < msx_num_sms() ? want : msx_num_sms();
   // fp32 context rows leave through the dead P tile (coalesced) when the per-warp staging slices fit into it
   const bool stage = !p.out_bf16 && p.dh == 32 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
-  if (p.dh == 16) {
+  if (q0) {
+    MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32, X3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<NCH, G, false, 32, X3, true><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+  } else if (p.dh == 16) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_tc_fwd_kernel<NCH, G, false, 16, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
   } else if (stage) {
@@ -852,10 +905,10 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
 }  // namespace
 
 extern "C" int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores,
-                                      int B, int T, int H, int dh, void* stream);
+                                      int q0_only, int B, int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tc_fwd_ex2(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int x3_scores, int B,
                                         int T, int H, int dh, void* stream) {
-  return msx_attention_tc_fwd_p(qkv, mask, ctx, nullptr, ctx_bf16, x3_scores, B, T, H, dh, stream);
+  return msx_attention_tc_fwd_p(qkv, mask, ctx, nullptr, ctx_bf16, x3_scores, 0, B, T, H, dh, stream);
 }
 extern "C" int msx_attention_tc_fwd_ex(const float* qkv, const float* mask, void* ctx, int ctx_bf16, int B, int T, int H,
                                        int dh, void* stream) {
@@ -867,15 +920,16 @@ extern "C" int msx_attention_tc_fwd(const float* qkv, const float* mask, float* 
 }
 
 extern "C" int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, int x3_scores,
-                                      int B, int T, int H, int dh, void* stream) {
+                                      int q0_only, int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx, "msx_attention_tc_fwd: null pointer");
+  MSX_REQUIRE(!q0_only || dh == 32, "msx_attention_tc_fwd_p: q0_only needs d_h == 32");
   MSX_REQUIRE(!ctx_lo || (ctx_bf16 && ((uintptr_t)ctx_lo & 15) == 0), "msx_attention_tc_fwd_p: the lo plane needs a bf16 ctx and 16-byte alignment");
   MSX_REQUIRE(((uintptr_t)ctx & 15) == 0, "msx_attention_tc_fwd: ctx must be 16-byte aligned");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh), "msx_attention_tc_fwd: needs d_h == 32, T <= 128, 16-byte aligned qkv");
   if (B == 0) return MSX_OK;
   const int D = H * dh;
   AttnTcParams p;
-  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.ctx_lo = ctx_lo; p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H; p.dh = dh;
+  p.mask = mask; p.ctx = reinterpret_cast<float*>(ctx); p.ctx_lo = ctx_lo; p.qkv = qkv; p.out_bf16 = ctx_bf16 ? 1 : 0; p.T = T; p.H = H; p.dh = dh;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
   p.items = B * H;
@@ -893,25 +947,25 @@ extern "C" int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void*
   cudaStream_t st = (cudaStream_t)stream;
   if (x3_scores) {                           // same group counts: the lo tiles share the P region (short rows: they are tiny)
     switch (p.TQ / 16) {
-      case 1: return launch_fwd<1, 3, true>(tk, tq, tv, p, st);
-      case 2: return launch_fwd<2, 3, true>(tk, tq, tv, p, st);
-      case 3: return launch_fwd<3, 3, true>(tk, tq, tv, p, st);
-      case 4: return launch_fwd<4, 3, true>(tk, tq, tv, p, st);
-      case 5: return launch_fwd<5, 3, true>(tk, tq, tv, p, st);
-      case 6: return launch_fwd<6, 2, true>(tk, tq, tv, p, st);
-      case 7: return launch_fwd<7, 1, true>(tk, tq, tv, p, st);
-      default: return launch_fwd<8, 1, true>(tk, tq, tv, p, st);
+      case 1: return launch_fwd<1, 3, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 2: return launch_fwd<2, 3, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 3: return launch_fwd<3, 3, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 4: return launch_fwd<4, 3, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 5: return launch_fwd<5, 3, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 6: return launch_fwd<6, 2, true>(tk, tq, tv, p, st, q0_only != 0);
+      case 7: return launch_fwd<7, 1, true>(tk, tq, tv, p, st, q0_only != 0);
+      default: return launch_fwd<8, 1, true>(tk, tq, tv, p, st, q0_only != 0);
     }
   }
   switch (p.TQ / 16) {
-    case 1: return launch_fwd<1, 3, false>(tk, tq, tv, p, st);
-    case 2: return launch_fwd<2, 3, false>(tk, tq, tv, p, st);
-    case 3: return launch_fwd<3, 3, false>(tk, tq, tv, p, st);
-    case 4: return launch_fwd<4, 3, false>(tk, tq, tv, p, st);
-    case 5: return launch_fwd<5, 3, false>(tk, tq, tv, p, st);
-    case 6: return launch_fwd<6, 2, false>(tk, tq, tv, p, st);
-    case 7: return launch_fwd<7, 1, false>(tk, tq, tv, p, st);
-    default: return launch_fwd<8, 1, false>(tk, tq, tv, p, st);
+    case 1: return launch_fwd<1, 3, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 2: return launch_fwd<2, 3, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 3: return launch_fwd<3, 3, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 4: return launch_fwd<4, 3, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 5: return launch_fwd<5, 3, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 6: return launch_fwd<6, 2, false>(tk, tq, tv, p, st, q0_only != 0);
+    case 7: return launch_fwd<7, 1, false>(tk, tq, tv, p, st, q0_only != 0);
+    default: return launch_fwd<8, 1, false>(tk, tq, tv, p, st, q0_only != 0);
   }
 }
 

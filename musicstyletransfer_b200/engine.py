@@ -398,7 +398,8 @@ class VAEEngine:
         self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv, gemm_name=prefix + "qkv")
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd))
+            ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd),
+                                 q0_only=sos_only and D // H == 32)
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
             ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:
@@ -534,7 +535,8 @@ class VAEEngine:
         ops.gemm_tc_p3(x_in_p[0], x_in_p[1], D, a.span16(kq, vq), a.span16lo(kq, vq), D, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
         ctxp = bf.get(tag + "ctx_p", (2, M, D), dev, b16)
         if ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_fwd(qkv, mask, ctxp[0], B, T, H, D // H, x3_scores=True, ctx_lo=ctxp[1])
+            ops.attention_tc_fwd(qkv, mask, ctxp[0], B, T, H, D // H, x3_scores=True, ctx_lo=ctxp[1],
+                                 q0_only=sos_only and D // H == 32)
         else:                                           # longer rows: fp32 context from the kernel that takes them, one split
             ctx = bf.get(tag + "ctx", (M, D), dev)
             if ops.attention_tcl_supported(qkv, T, D // H):
@@ -596,7 +598,7 @@ class VAEEngine:
         ops.gemm_tc_bf16(x_in16, D, 0, wqkv, D, 1, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
         ctx16 = bf.get(tag + "ctx16", (M, D), dev, b16)
         if ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H)
+            ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H, q0_only=sos_only and D // H == 32)
         elif ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_fwd(qkv, mask, ctx16, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
         else:                                           # T > 384: FFMA attention in fp32, then one cast

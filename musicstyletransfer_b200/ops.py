@@ -211,12 +211,13 @@ def attention_tc_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tc_supported(P(qkv), _i(T), _i(dh)))
 
 
-def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False, ctx_lo=None):
+def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False, ctx_lo=None, q0_only=False):
     """ctx: fp32, or bfloat16 (bf16 variant: the context only feeds the W_proj GEMMs).  x3_scores: S = K Q^T with 3xTF32
     operand splitting (fp32-equivalent scores; the softmax turns their absolute error into a relative error of P).
-    ctx_lo: bfloat16 lo plane next to a bfloat16 ctx (= hi plane), the operands of the p3 W_proj GEMM."""
+    ctx_lo: bfloat16 lo plane next to a bfloat16 ctx (= hi plane), the operands of the p3 W_proj GEMM.
+    q0_only: compute / write the context row of query 0 of every sequence only (d_h == 32)."""
     lib.call("msx_attention_tc_fwd_p", P(qkv), P(mask), P(ctx), P(ctx_lo), _i(1 if ctx.dtype == torch.bfloat16 else 0),
-             _i(1 if x3_scores else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+             _i(1 if x3_scores else 0), _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
 def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):

@@ -72,6 +72,35 @@ def test_attention_tc_forward_compensated_scores(B, T, H, dh):
     assert outs[1] < 0.7 * outs[0] or T == 1, outs   # T == 1: one query, P == 1 whatever the score
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (300, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (500, 97, 2)])
+@pytest.mark.parametrize("x3,planes", [(False, False), (True, False), (True, True)])
+def test_attention_tc_forward_query0_only(B, T, H, x3, planes):
+    """q0_only (encoder top layer): the context row of query 0 equals the full kernel's / the float64 reference's, every
+    other row of the output buffer is left untouched; fp32 output and bf16 hi / lo planes."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    qkv, mask = _inputs(B, T, H, dh, seed=T + 3)
+    want = _ref_fwd(qkv, mask, B, T, H, dh).view(B, T, H * dh)[:, 0]
+    qd, md = qkv.cuda(), mask.cuda()
+    if planes:
+        hi = torch.full((B * T, H * dh), 3.0, device="cuda", dtype=torch.bfloat16)
+        lo = torch.full((B * T, H * dh), 3.0, device="cuda", dtype=torch.bfloat16)
+        ops.attention_tc_fwd(qd, md, hi, B, T, H, dh, x3_scores=x3, ctx_lo=lo, q0_only=True)
+        torch.cuda.synchronize()
+        ctx = (hi.float() + lo.float()).view(B, T, H * dh)
+        untouched = 6.0
+    else:
+        ctx = torch.full((B * T, H * dh), 3.0, device="cuda")
+        ops.attention_tc_fwd(qd, md, ctx, B, T, H, dh, x3_scores=x3, q0_only=True)
+        torch.cuda.synchronize()
+        ctx = ctx.view(B, T, H * dh)
+        untouched = 3.0
+    err = float((ctx[:, 0].double().cpu() - want).abs().max()) / float(want.abs().max())
+    assert err < (6e-4 if x3 else 3e-3), err
+    if T > 1:
+        assert bool((ctx[:, 1:] == untouched).all())
+
+
 # T <= 80 runs the pipelined kernel (the larger B cases give every pipeline group several items; H = 3 makes the head
 # change between the items of a group, which exercises the bias-gradient flush), T > 80 the one-shot kernel
 @pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (2, 128, 2), (7, 1, 2), (3, 2, 8),

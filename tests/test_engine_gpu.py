@@ -413,7 +413,10 @@ def test_fused_ce_backward_equals_two_pass(prec):
     assert float((g0 - g1).abs().max()) <= 2e-5 * float(g0.abs().max())        # atomics: summation order only
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 2e-3), ("fp32x3", 2e-5), ("bf16", 5e-3)])
+# tensor modes: the SOS-rows layout takes its one context row per (sequence, head) from the q0_only attention kernel, which
+# sums P[k][0] V[k] in fp32, the full layout from the P^T V MMA with TF32 operands: the two differ by that rounding (bf16:
+# one ulp of the bf16 context flips ReLU decisions of the top layer's hidden units; its own bar vs the oracle is 10 % / 3 %)
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 5e-3), ("fp32x3", 2e-5), ("bf16", 3e-2), ("bf16p3f", 5e-3)])
 @pytest.mark.parametrize("dropout", [0.0, 0.2])
 def test_sos_rows_only_top_layer_equals_full_layer(prec, tol, dropout):
     """The encoder output is read at position 0 only (model.py:97-100).  sos_rows_only=True runs the top encoder layer's
