@@ -201,6 +201,11 @@ int msx_attention_tc_fwd_p(const float* qkv, const float* mask, void* ctx, void*
                            int q0_only, int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
                             int B, int T, int H, int dh, void* stream);
+/* q0_only: dctx is non-zero in the row of query 0 of every sequence only (the encoder's top layer under SOS-rows-only,
+ * model.py:97-100).  For T <= 80, d_h == 32 a specialised pipeline runs: dV and dS are thread-local (no dP / dV MMAs, no
+ * dO tiles); other shapes take the general kernels, which give the same result. */
+int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
+                            int q0_only, int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);
 /* Long rows, 128 < T <= 384 (the L = 128 / 256 sweep points): key tiles and query chunks of 128, flash-attention style
  * backward.  stats [B*H*T, 2] fp32 (row max * log2 e, 1 / row sum of every key row) is written by the forward and read

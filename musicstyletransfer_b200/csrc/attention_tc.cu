@@ -375,6 +375,8 @@ __global__ void __launch_bounds__(128 * G, 1)
 struct AttnTcBwdParams {
   const float* mask;   // [B*T]
   float* dqkv;         // [B*T, 3*H*32] fp32, or bf16 when out_bf16 (operand of the bf16 K|Q|V dgrad / wgrad GEMMs)
+  const float* qkv;    // Q0 kernels only: V rows and the context gradient of query 0 are read straight from global memory
+  const float* dctx;
   int out_bf16;
   float* dbias;        // optional [3*H*32]: += column sums of dqkv (bias gradient of the fused K|Q|V projection)
   int T, H, TQ, TK;    // TQ = roundup16(T), TK = roundup8(T)
@@ -575,7 +577,11 @@ __global__ void __launch_bounds__(128)
 //   * the K-major tiles of the first two MMAs are double-buffered and prefetched one item ahead; the dS^T staging
 //     tile aliases the current stage once its MMAs have retired;
 //   * the bias-gradient column sums accumulate in registers across the items of a group (flushed when the head changes).
-template <int NCH, bool STAGE, int kDh>
+// Q0 (the encoder's top layer under sos_rows_only): dO is non-zero for query 0 only, g = dO[0].  Then dP = V dO^T has one
+// non-zero column a_k = V[k] . g, and with c_k = a_k P[k][0]
+//     dV[k] = P[k][0] g            dS[k][q] = (-c_k P[k][q] + [q == 0] c_k) / sqrt(d_h)
+// are thread-local: no dP MMA, no dV MMA, no dO tiles, no P back in TMEM; two output MMAs (dK, dQ) instead of three.
+template <int NCH, bool STAGE, int kDh, bool Q0 = false>
 __global__ void __launch_bounds__(256, 1)
     attn_tc_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmQk,
                             const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
@@ -648,11 +654,11 @@ __global__ void __launch_bounds__(256, 1)
   auto load_a = [&](int item, int stage) {                  // K-major tiles of MMA S and MMA dP
     const int b = item / p.H, h = item % p.H;
     unsigned char* st = gbase + stage * stage_bytes;
-    mbar_expect_tx(&bar_a[stage], (unsigned)stage_bytes);
+    mbar_expect_tx(&bar_a[stage], Q0 ? (unsigned)(slab + TQ * 128) : (unsigned)stage_bytes);
     tma_load_2d(st, &tmKk, &bar_a[stage], h * kDh, b * T);
-    tma_load_2d(st + slab, &tmKk, &bar_a[stage], 2 * D + h * kDh, b * T);
+    if (!Q0) tma_load_2d(st + slab, &tmKk, &bar_a[stage], 2 * D + h * kDh, b * T);
     tma_load_2d(st + 2 * slab, &tmQk, &bar_a[stage], D + h * kDh, b * T);
-    tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * kDh, b * T);
+    if (!Q0) tma_load_2d(st + 2 * slab + TQ * 128, &tmDOk, &bar_a[stage], h * kDh, b * T);
   };
   // descriptors of stage 0 / the MN-major tiles, advanced by constant increments (see the forward kernel)
   const unsigned long long dKk = make_desc(smem_u32(gbase), 16, 1024, 2);
@@ -710,8 +716,8 @@ __global__ void __launch_bounds__(256, 1)
       MSX_STAMP(0);
       if (elect_one()) {
         // MN-major tiles of the output MMAs (free: the previous item's output MMAs have retired)
-        mbar_expect_tx(bar_b, (unsigned)(3 * slab));
-        tma_load_2d(sBm, &tmDOm, bar_b, h * kDh, b * T);
+        mbar_expect_tx(bar_b, (unsigned)((Q0 ? 2 : 3) * slab));
+        if (!Q0) tma_load_2d(sBm, &tmDOm, bar_b, h * kDh, b * T);
         tma_load_2d(sBm + slab, &tmQKVm, bar_b, D + h * kDh, b * T);
         tma_load_2d(sBm + 2 * slab, &tmQKVm, bar_b, h * kDh, b * T);
         if (nxt < items) load_a(nxt, stg ^ 1);              // the other stage held item n-1 (its MMAs and dS^T are consumed)
@@ -726,7 +732,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
         for (int k = 0; k < kDh / 8; ++k) {
           umma_tf32(tm_S, kk + 2 * k, qk + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-          umma_tf32(tm_dP, vk + 2 * k, dok + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+          if (!Q0) umma_tf32(tm_dP, vk + 2 * k, dok + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
         }
         umma_commit(bar_ma);
       }
@@ -734,10 +740,24 @@ __global__ void __launch_bounds__(256, 1)
       MSX_STAMP(2);
     }
     __syncwarp();
+    float p0_keep = 0.f;
     if (warp_live) {
       const int k = gt;
       const bool valid = k < T;
       const float rowmask = (valid && mraw > 0.f) ? 0.f : -1e9f;
+      float a_k = 0.f;
+      if (Q0) {                                             // g = dO[0] of this (batch, head) and a_k = V[k] . g, in flight during MMA S
+        const float4* gp4 = reinterpret_cast<const float4*>(p.dctx + (size_t)b * T * D + h * kDh);
+        const float4* vp4 = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + min(k, T - 1)) * 3 * D + 2 * D + h * kDh);
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g4 = __ldg(gp4 + j), v4 = __ldg(vp4 + j);
+          d4[0] = fmaf(g4.x, v4.x, d4[0]); d4[1] = fmaf(g4.y, v4.y, d4[1]);
+          d4[2] = fmaf(g4.z, v4.z, d4[2]); d4[3] = fmaf(g4.w, v4.w, d4[3]);
+        }
+        a_k = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+      }
       mbar_wait(bar_ma, par);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the key row's scores stay in registers; dP is re-read from TMEM in 16-column chunks (two cheap passes)
@@ -761,9 +781,26 @@ __global__ void __launch_bounds__(256, 1)
         sum4[j & 3] += sc[j];
       }
       const float inv = valid ? 1.f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) : 0.f;
+      if (Q0) {
+        const float p0 = sc[0] * inv, ck = a_k * p0;
+        p0_keep = p0;                                       // dV[k] = P[k][0] g leaves with the other two rows in the epilogue
+        const float cs = -ck * inv * p.inv_scale;           // dS[k][q] = cs * e[q] (+ ck / sqrt(d_h) for q == 0)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float gp[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gp[j] = to_tf32(fmaf(cs, sc[c * 16 + j], (c == 0 && j == 0) ? ck * p.inv_scale : 0.f));
+          tmem_st16(tm_dP + lane_off + c * 16, gp);
+          if (k < TK) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(sY + mn_major_off(c * 16 + j, k, TK)) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+          }
+        }
+      }
       float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < (Q0 ? 0 : NCH); ++c) {
         float gp[16];
         tmem_ld16_issue(tm_dP + lane_off + c * 16, gp);
         tmem_ld16_wait(gp);
@@ -775,7 +812,7 @@ __global__ void __launch_bounds__(256, 1)
       }
       const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < (Q0 ? 0 : NCH); ++c) {
         float gp[16];
         tmem_ld16_issue(tm_dP + lane_off + c * 16, gp);
         tmem_ld16_wait(gp);
@@ -813,7 +850,7 @@ __global__ void __launch_bounds__(256, 1)
         //   dQ[queries x 32] = dS^T[q x keys] K[keys x 32]                                     (A from shared memory)
 #pragma unroll 3
         for (int j = 0; j < nk; ++j) {
-          umma_tf32_ts(tm_dV, tm_S + j * 8, dom + 64 * j, idesc_ts, j > 0 ? 1u : 0u);
+          if (!Q0) umma_tf32_ts(tm_dV, tm_S + j * 8, dom + 64 * j, idesc_ts, j > 0 ? 1u : 0u);
           umma_tf32_ts(tm_dK, tm_dP + j * 8, qm + 64 * j, idesc_ts, j > 0 ? 1u : 0u);
           umma_tf32(tm_dQ, ym + 64 * j, km + 64 * j, idesc_mm, j > 0 ? 1u : 0u);
         }
@@ -833,10 +870,19 @@ __global__ void __launch_bounds__(256, 1)
       for (int m = 0; m < 3; ++m) {
         float o[32];
         const unsigned src = m == 0 ? tm_dK : m == 1 ? tm_dQ : tm_dV;
-        tmem_ld16_issue(src + lane_off, o);
-        tmem_ld16_issue(src + lane_off + 16, o + 16);
-        tmem_ld16_wait(o);
-        tmem_ld16_wait(o + 16);
+        if (Q0 && m == 2) {                                 // dV[k] = P[k][0] g (g: a 128-byte row every thread of the item reads)
+          const float4* gp4 = reinterpret_cast<const float4*>(p.dctx + (size_t)b * T * D + h * kDh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(gp4 + j);
+            o[4 * j] = p0_keep * g4.x; o[4 * j + 1] = p0_keep * g4.y; o[4 * j + 2] = p0_keep * g4.z; o[4 * j + 3] = p0_keep * g4.w;
+          }
+        } else {
+          tmem_ld16_issue(src + lane_off, o);
+          tmem_ld16_issue(src + lane_off + 16, o + 16);
+          tmem_ld16_wait(o);
+          tmem_ld16_wait(o + 16);
+        }
         // the stage (K-major tiles / dS^T) is dead once the output MMAs have retired: the warp's 4 KB slice of it stages
         // the rows for a coalesced store
         if (stage_ok) {
@@ -980,6 +1026,8 @@ extern "C" int msx_attention_tc_set_trace(long long* buf) {
 
 extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
                                        float* dbias, int B, int T, int H, int dh, void* stream);
+extern "C" int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
+                                       float* dbias, int q0_only, int B, int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, float* dbias,
                                     int B, int T, int H, int dh, void* stream) {
   return msx_attention_tc_bwd_ex(qkv, mask, dctx, dqkv, 0, dbias, B, T, H, dh, stream);
@@ -987,6 +1035,11 @@ extern "C" int msx_attention_tc_bwd(const float* qkv, const float* mask, const f
 
 extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
                                        float* dbias, int B, int T, int H, int dh, void* stream) {
+  return msx_attention_tc_bwd_q0(qkv, mask, dctx, dqkv, dqkv_bf16, dbias, 0, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16,
+                                       float* dbias, int q0_only, int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && dqkv, "msx_attention_tc_bwd: null pointer");
   MSX_REQUIRE(msx_attention_tc_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
               "msx_attention_tc_bwd: needs d_h == 32, T <= 128, 16-byte aligned buffers");
@@ -994,7 +1047,7 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
   const int D = H * dh;
   AttnTcBwdParams p;
   p.mask = mask; p.dqkv = reinterpret_cast<float*>(dqkv); p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias; p.T = T; p.H = H;
-  p.dh = dh;
+  p.dh = dh; p.qkv = qkv; p.dctx = dctx;
   p.trace = g_attn_trace;
   p.TQ = (T + 15) / 16 * 16;
   p.TK = (T + 7) / 8 * 8;
@@ -1027,7 +1080,13 @@ extern "C" int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, cons
     const bool stage = !p.out_bf16 && dh == 32 && ((T + 31) / 32) * 4096 <= stage_bytes;
 #define MSX_BWD_PIPE(NCH)                                                                                              \
   case NCH:                                                                                                            \
-    if (dh == 16) {                                                                                                    \
+    if (q0_only && dh == 32 && stage) {                                                                                \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, true, 32, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    } else if (q0_only && dh == 32) {                                                                                  \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attn_tc_bwd_pipe_kernel<NCH, false, 32, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+    } else if (dh == 16) {                                                                                                    \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attn_tc_bwd_pipe_kernel<NCH, false, 16><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
     } else if (stage) {                                                                                                \

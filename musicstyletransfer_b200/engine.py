@@ -503,7 +503,7 @@ class VAEEngine:
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv)
+            ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H, dbias=gbqkv, q0_only=sos_only)
             gbqkv = None
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), torch.float32)], dqkv, B, T, H,
@@ -693,7 +693,7 @@ class VAEEngine:
         dqkv16 = bf.get(tag + "dqkv16", (M, 3 * D), dev, b16)
         gbqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias", a.g)
         if ops.attention_tc_supported(qkv, T, D // H):
-            ops.attention_tc_bwd(qkv, mask, dctx, dqkv16, B, T, H, D // H, dbias=gbqkv)
+            ops.attention_tc_bwd(qkv, mask, dctx, dqkv16, B, T, H, D // H, dbias=gbqkv, q0_only=sos_only)
         elif ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), f32)], dqkv16, B, T, H, D // H,
                                   dbias=gbqkv)

@@ -220,10 +220,11 @@ def attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=False, ctx_lo=None, 
              _i(1 if x3_scores else 0), _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
-def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None):
-    """dqkv: fp32, or bfloat16 (bf16 variant: it only feeds the K|Q|V dgrad / wgrad GEMMs)."""
-    lib.call("msx_attention_tc_bwd_ex", P(qkv), P(mask), P(dctx), P(dqkv), _i(1 if dqkv.dtype == torch.bfloat16 else 0),
-             P(dbias), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None, q0_only=False):
+    """dqkv: fp32, or bfloat16 (bf16 variant: it only feeds the K|Q|V dgrad / wgrad GEMMs).
+    q0_only: the caller guarantees dctx == 0 outside the row of query 0 of every sequence."""
+    lib.call("msx_attention_tc_bwd_q0", P(qkv), P(mask), P(dctx), P(dqkv), _i(1 if dqkv.dtype == torch.bfloat16 else 0),
+             P(dbias), _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
 def attention_tcl_supported(qkv, T, dh):

@@ -12,6 +12,7 @@ ctx = torch.empty(B * T, D, device="cuda")
 hi = torch.empty(B * T, D, device="cuda", dtype=torch.bfloat16); lo = torch.empty_like(hi)
 dctx = torch.randn(B * T, D, device="cuda")
 dqkv = torch.empty(B * T, 3 * D, device="cuda")
+dctx0 = torch.zeros(B, T, D, device="cuda"); dctx0[:, 0] = torch.randn(B, D, device="cuda"); dctx0 = dctx0.view(B * T, D)
 fns = {
     "fwd fp32 out": lambda: ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, dh),
     "fwd x3 fp32 out": lambda: ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, x3_scores=True),
@@ -19,6 +20,7 @@ fns = {
     "fwd x3 planes q0": lambda: ops.attention_tc_fwd(qkv, mask, hi, B, T, H, dh, x3_scores=True, ctx_lo=lo, q0_only=True),
     "fwd q0 fp32": lambda: ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, dh, q0_only=True),
     "bwd": lambda: ops.attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh),
+    "bwd q0": lambda: ops.attention_tc_bwd(qkv, mask, dctx0, dqkv, B, T, H, dh, q0_only=True),
 }
 for name, fn in fns.items():
     for _ in range(3):

@@ -131,6 +131,34 @@ def test_attention_backward(B, T, H):
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 65, 8), (5, 66, 2), (2, 16, 4), (4, 97, 3), (7, 1, 2), (3, 2, 8), (70, 65, 8), (300, 65, 8),
+                                   (220, 66, 3), (400, 33, 2)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_attention_backward_query0_only(B, T, H, out16):
+    """q0_only: the context gradient is non-zero in the row of query 0 of every sequence only (the encoder's top layer).
+    dqkv and the bias gradient vs torch autograd (float64); T > 80 takes the general kernel through the same entry point."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    qkv, mask = _inputs(B, T, H, dh, seed=200 + T)
+    g = torch.Generator().manual_seed(T + 1)
+    dctx = torch.zeros(B, T, H * dh)
+    dctx[:, 0] = torch.randn(B, H * dh, generator=g)
+    dctx = dctx.view(B * T, H * dh)
+    x = qkv.double().requires_grad_(True)
+    (_ref_fwd(x, mask, B, T, H, dh) * dctx.double()).sum().backward()
+    want = x.grad
+    scale = float(want.abs().max())
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    out = torch.full(qd.shape, 5.0, device="cuda", dtype=torch.bfloat16 if out16 else torch.float32)
+    db = torch.zeros(3 * H * dh, device="cuda")
+    ops.attention_tc_bwd(qd, md, dd, out, B, T, H, dh, dbias=db, q0_only=True)
+    torch.cuda.synchronize()
+    err = float((out.double().cpu() - want).abs().max()) / scale
+    assert err < (1.2e-2 if out16 else 5e-3), err
+    wb = want.sum(0)
+    assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ long rows (T > 128)
 @pytest.mark.parametrize("B,T,H", [(2, 129, 2), (3, 257, 2), (2, 200, 3), (5, 256, 1), (2, 384, 2), (40, 129, 8), (3, 144, 2)])
 @pytest.mark.parametrize("out16", [False, True])
