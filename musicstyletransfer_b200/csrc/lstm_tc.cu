@@ -118,6 +118,9 @@ struct FwdSmem {
                                          // from the peer
 };
 
+// NSB = 2: the schedule above (32 rows per cluster).  NSB = 1: 16 rows per cluster, every warp in the same phase: twice as many
+// clusters for small batches, where SMs are idle and only the length of the step chain matters (B = 32: 2 clusters).
+template <int NSB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_tc_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_h2h, const float* __restrict__ b_h2h,
                        const float* __restrict__ h0, const float* __restrict__ c0, int ld0, float* __restrict__ hs,
@@ -131,7 +134,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int ul0 = warp * 8 + 2 * t4;                        // this thread's two local units (accumulator columns 2t, 2t+1)
   const int u0 = crank * UH + ul0;
   const int un = crank * UH + warp * 8 + g;                 // the unit whose W rows this thread holds as B fragments (n = lane / 4)
-  const bool late = warp >= 4;                              // second group: one phase behind
+  const bool late = NSB == 2 && warp >= 4;                  // second group: one phase behind
+  constexpr int RC = RB * NSB;                              // rows per cluster
 
   // A cluster is persistent over blocks of R batch rows (grid = min(#row blocks, resident clusters)): W_h2h goes into
   // registers once per CTA.  With T = 1 (one decode step over a large batch: style transfer / beam search) the launch
@@ -177,22 +181,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   unsigned phase = 0;                                       // bit 2 sb + i: parity of the next completion of full[sb][i]
-  const int n_blocks = (B + R - 1) / R, n_clusters = gridDim.x >> 1;
+  const int n_blocks = (B + RC - 1) / RC, n_clusters = gridDim.x >> 1;
   for (int blk = blockIdx.x >> 1; blk < n_blocks; blk += n_clusters) {
-    b0 = blk * R;
+    b0 = blk * RC;
     cluster.sync();                                         // both CTAs are done with the previous row block's buffers
+    // always four groups in flight before step 0 (NSB = 1: two of them empty), so that the wait_group counts below hold
     prefetch_gx(0, 0);
-    prefetch_gx(1, 0);
+    if (NSB == 2) prefetch_gx(1, 0); else cp_async_commit();
     prefetch_gx(0, 1);
-    prefetch_gx(1, 1);
-    for (int i = tid; i < R * H; i += kThreads) {
+    if (NSB == 2) prefetch_gx(1, 1); else cp_async_commit();
+    for (int i = tid; i < RC * H; i += kThreads) {
       const int r = i / H, k = i % H;
       sm.hfrag[r >> 4][0][afrag_index(r & 15, k, 16)] = (b0 + r < B) ? tf32r(__ldg(h0 + (size_t)(b0 + r) * ld0 + k)) : 0.f;
     }
     // cells of this thread: sub-block sb, rows 8 hi + g, units u0, u0 + 1
-    float c[2][2][2], hp[2][2][2];
+    float c[NSB][2][2], hp[NSB][2][2];
 #pragma unroll
-    for (int sb = 0; sb < 2; ++sb)
+    for (int sb = 0; sb < NSB; ++sb)
 #pragma unroll
       for (int hi = 0; hi < 2; ++hi) {
         const int b = min(b0 + sb * RB + 8 * hi + g, B - 1);
@@ -208,13 +213,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
     for (int t = 0; t < T; ++t) {
 #pragma unroll
-      for (int sb = 0; sb < 2; ++sb) {
+      for (int sb = 0; sb < NSB; ++sb) {
         unsigned long long* bar_cur = &sm.full[sb][t & 1];
         if (t > 0) {                                        // h_{t-1} (both halves) and the gx slab of step t are in place
           mbar_wait(bar_cur, (phase >> (2 * sb + (t & 1))) & 1u);
           phase ^= 1u << (2 * sb + (t & 1));
         }
         prefetch_gx(sb, t + 2);                             // its buffer was last read in step t-1 (every warp arrived since)
+        if (NSB == 1) cp_async_commit();                    // the group the second sub-block would have committed
         const float4* hcur = reinterpret_cast<const float4*>(sm.hfrag[sb][t & 1]);
         float acc[4][4];
 #pragma unroll
@@ -228,7 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int j = 0; j < 4; ++j) mma_tf32(acc[j], a, breg[j][s][0], breg[j][s][1]);
         }
-        if (t == 0 && sb == 0 && !late) asm volatile("bar.arrive 1, 256;" ::: "memory");
+        if (NSB == 2 && t == 0 && sb == 0 && !late) asm volatile("bar.arrive 1, 256;" ::: "memory");
         const float* gxc = sm.gxs[sb][t % 3];
         float2 iv[2], fv[2], gv[2], ov[2], cv[2], hv[2];
 #pragma unroll
@@ -301,6 +307,8 @@ struct BwdSmem {
   unsigned long long full[2];            // partials of step t in dhrec / dhin[t & 1] and the slabs of step t-1: 8 local warps + 8 KB
 };
 
+// MT = 2: 32 rows per cluster (two m16 tiles per warp).  MT = 1: 16 rows per cluster for small batches (see the forward kernel).
+template <int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_tc_bwd_kernel(float* __restrict__ gates, const float* __restrict__ w_h2h, const float* __restrict__ cs,
                        const float* __restrict__ c0, int ld0, const float* __restrict__ dhs, float* __restrict__ dh0,
@@ -311,7 +319,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int crank = (int)cluster.block_rank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int b0 = (blockIdx.x >> 1) * R;
+  constexpr int RR = 16 * MT;                               // rows per cluster
+  const int b0 = (blockIdx.x >> 1) * RR;
   const int ul0 = warp * 8 + 2 * t4;                        // cell mapping: local units ul0, ul0 + 1 (as in the forward kernel)
   const int u0 = crank * UH + ul0;
 
@@ -319,13 +328,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   auto prefetch = [&](int t) {
     const int buf = t & 1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4 * MT; ++i) {
       const int ch = tid + i * kThreads, row = ch >> 6, rem = ch & 63, gate = rem >> 4, c4 = (rem & 15) * 4;
       const int b = min(b0 + row, B - 1);
       cp_async16(sm.gts[buf] + row * kRowPitch + gate * UH + c4, gates + ((size_t)b * T + t) * 4 * H + gate * H + crank * UH + c4);
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MT; ++i) {
       const int ch = tid + i * kThreads, row = ch >> 4, c4 = (ch & 15) * 4;
       const int b = min(b0 + row, B - 1);
       cp_async16(sm.dht[buf] + row * kColPitch + c4, dhs + ((size_t)b * T + t) * H + crank * UH + c4);
@@ -357,10 +366,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
   }
   for (int i = tid; i < 2 * R * kColPitch; i += kThreads) { (&sm.dhrec[0][0])[i] = 0.f; (&sm.dhin[0][0])[i] = 0.f; }
-  float dc[4][2], bsum[4][2], cnext[4][2];                  // cnext: c_t of the step about to be processed
-  int brow[4];
+  float dc[2 * MT][2], bsum[4][2], cnext[2 * MT][2];                  // cnext: c_t of the step about to be processed
+  int brow[2 * MT];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2 * MT; ++q) {
     brow[q] = b0 + 16 * (q >> 1) + 8 * (q & 1) + g;
     const int b = min(brow[q], B - 1);
     const float2 cv = *reinterpret_cast<const float2*>(cs + ((size_t)b * T + (T - 1)) * H + u0);
@@ -390,9 +399,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     if (t > 0) prefetch(t - 1);                             // its buffers were last read in step t+1 (every warp arrived since)
     // ---- cell backward (thread-local), operands from the staged slabs
-    float2 di[4], df[4], dg2[4], dou[4];
+    float2 di[2 * MT], df[2 * MT], dg2[2 * MT], dou[2 * MT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2 * MT; ++q) {
       const int row = 16 * (q >> 1) + 8 * (q & 1) + g;
       const float* gp = sm.gts[buf] + row * kRowPitch + ul0;
       const float2 iv = *reinterpret_cast<const float2*>(gp), fv = *reinterpret_cast<const float2*>(gp + UH);
@@ -422,7 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     // dg of (rows g, g+8) x (units ul0, ul0+1) of m-tile m and one gate is one float4 of the fragment buffer
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < MT; ++m) {
       const int fb = (m * 32 + (ul0 >> 3)) * 32 + g * 4 + t4;
       float4* dstf = reinterpret_cast<float4*>(sm.dgfrag);
       dstf[fb + 0 * 8 * 32] = make_float4(tf32r(di[2 * m].x), tf32r(di[2 * m + 1].x), tf32r(di[2 * m].y), tf32r(di[2 * m + 1].y));
@@ -432,7 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     __syncthreads();                                        // dg complete
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                           // global stores drain during the MMAs
+    for (int q = 0; q < 2 * MT; ++q) {                           // global stores drain during the MMAs
       if (brow[q] < B) {
         float* gp = gates + ((size_t)brow[q] * T + t) * 4 * H + u0;
         *reinterpret_cast<float2*>(gp) = di[q];
@@ -442,23 +451,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
     // ---- partial dh_rec = dg Wn over all 256 local gate columns for this warp's 16 hidden columns
-    float acc[2][2][4];
+    float acc[MT][2][4];
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) acc[m][nn][0] = acc[m][nn][1] = acc[m][nn][2] = acc[m][nn][3] = 0.f;
     const float4* af = reinterpret_cast<const float4*>(sm.dgfrag);
 #pragma unroll
     for (int s = 0; s < 32; ++s) {
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MT; ++m) {
         const float4 a = af[(m * 32 + s) * 32 + lane];
         mma_tf32(acc[m][0], a, breg[0][s][0], breg[0][s][1]);
         mma_tf32(acc[m][1], a, breg[1][s][0], breg[1][s][1]);
       }
     }
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) {
         const int col = ((16 * warp + 8 * nn) & 63) + 2 * t4;   // local unit in the owning CTA
@@ -474,7 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     cp_async_wait_all();                                    // this thread's chunks of the slabs of step t-1 have landed
     __syncwarp();
     if (lane == 0) {
-      if (warp == 0) mbar_arrive_expect_tx(&sm.full[buf], R * UH * 4);   // the peer's partial of this CTA's units: 8 KB per step
+      if (warp == 0) mbar_arrive_expect_tx(&sm.full[buf], RR * UH * 4);   // the peer's partial of this CTA's units: 8 KB per step
       else mbar_arrive(&sm.full[buf]);
     }
   }
@@ -494,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2 * MT; ++q) {
     const int row = 16 * (q >> 1) + 8 * (q & 1) + g;
     if (brow[q] < B) {
       const float* r1 = sm.dhrec[0] + row * kColPitch + ul0;   // written by step t = 0
@@ -518,13 +527,21 @@ extern "C" int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float*
   MSX_REQUIRE(gx_inout && w_h2h && b_h2h && h0 && c0 && hs && hprev && cs, "msx_lstm_tc_fwd: null pointer");
   MSX_REQUIRE(msx_lstm_tc_supported(H_, ld0, h0, c0), "msx_lstm_tc_fwd: needs H == 128, even ld0, 8-byte aligned h0 / c0");
   if (B == 0 || T == 0) return MSX_OK;
-  // persistent clusters: one 2-CTA cluster per SM pair at most, each walks its row blocks with W_h2h kept in registers
-  const int blocks = (B + R - 1) / R;
+  // persistent clusters: one 2-CTA cluster per SM pair at most, each walks its row blocks with W_h2h kept in registers;
+  // 16-row clusters while they all fit at once (small batches: more SMs on the same chain of T steps)
   const int resident = msx_num_sms() / 2;
-  const int clusters = blocks < resident ? blocks : resident;
-  MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-  lstm_tc_fwd_kernel<<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0, hs,
-                                                                                       hprev, cs, B, T);
+  if ((B + RB - 1) / RB <= resident) {
+    const int clusters = (B + RB - 1) / RB;
+    MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    lstm_tc_fwd_kernel<1><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0,
+                                                                                            hs, hprev, cs, B, T);
+  } else {
+    const int blocks = (B + R - 1) / R;
+    const int clusters = blocks < resident ? blocks : resident;
+    MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    lstm_tc_fwd_kernel<2><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0,
+                                                                                            hs, hprev, cs, B, T);
+  }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -536,10 +553,17 @@ extern "C" int msx_lstm_tc_bwd(float* gates_inout, const float* w_h2h, const flo
   MSX_REQUIRE(msx_lstm_tc_supported(H_, ld0, dh0, c0) && ((uintptr_t)dc0 & 7) == 0,
               "msx_lstm_tc_bwd: needs H == 128, even ld0, 8-byte aligned c0 / dh0 / dc0");
   if (B == 0 || T == 0) return MSX_OK;
-  const int clusters = (B + R - 1) / R;
-  MSX_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-  lstm_tc_bwd_kernel<<<clusters * 2, kThreads, sizeof(BwdSmem), (cudaStream_t)stream>>>(gates_inout, w_h2h, cs, c0, ld0, dhs, dh0,
-                                                                                       dc0, db_i2h, db_h2h, B, T);
+  if ((B + 15) / 16 <= msx_num_sms() / 2) {                 // small batches: 16-row clusters, all resident at once
+    const int clusters = (B + 15) / 16;
+    MSX_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    lstm_tc_bwd_kernel<1><<<clusters * 2, kThreads, sizeof(BwdSmem), (cudaStream_t)stream>>>(gates_inout, w_h2h, cs, c0, ld0, dhs,
+                                                                                            dh0, dc0, db_i2h, db_h2h, B, T);
+  } else {
+    const int clusters = (B + R - 1) / R;
+    MSX_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    lstm_tc_bwd_kernel<2><<<clusters * 2, kThreads, sizeof(BwdSmem), (cudaStream_t)stream>>>(gates_inout, w_h2h, cs, c0, ld0, dhs,
+                                                                                            dh0, dc0, db_i2h, db_h2h, B, T);
+  }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -6,6 +6,7 @@ Host-side orchestration of the hot path the reference runs as
 ``gluon.Trainer.step(batch_size)``.  Every device operation is a libmsx kernel (ops.py); torch only
 owns the buffers and the stream.  The schedule is static, so a whole step is CUDA-graph capturable.
 """
+import contextlib
 import math
 from collections import OrderedDict
 
@@ -296,6 +297,12 @@ class VAEEngine:
         self.ctx = None
         self._graphs = {}
         self._hmask_ok = {}                   # layer tag -> the FF1 forward wrote the ReLU bit mask
+        # Weight-gradient GEMMs have no consumer before the optimiser step.  With few rows (the reference's own batch of 32:
+        # every kernel fills a fraction of the GPU and the step is a chain of ~75 dependent launches) they leave the chain:
+        # forked onto a side stream behind the kernel that produced dY, joined before Adam (also inside captured graphs).
+        self.wgrad_side_rows = 16384          # fork when the reduction has at most this many rows; 0 disables
+        self._side = None
+        self._side_used = False
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, B, T):
@@ -338,6 +345,27 @@ class VAEEngine:
                  site=site, accumulate=accumulate)
         return False
 
+    def _wgrad_stream(self, rows, ok=True):
+        """Context for a weight-gradient launch: the side stream (ordered after everything enqueued so far) when the problem
+        is small, else the current stream.  ok=False: the caller's dY buffer is written again later in this backward pass."""
+        if not ok or rows > self.wgrad_side_rows:
+            return contextlib.nullcontext()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side.wait_event(ev)
+        self._side_used = True
+        return torch.cuda.stream(self._side)
+
+    def _wgrad_join(self):
+        """The optimiser (current stream) waits for the forked weight gradients."""
+        if self._side_used:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_used = False
+
     def _lstm_tc(self, Hd, tv):
         """Tensor-core LSTM recurrence (TF32 mma.sync, W_h2h in registers), H = 128."""
         return self.lstm_tc and ops.lstm_tc_supported(Hd, 2 * Hd, tv, tv[:, Hd:])
@@ -356,7 +384,7 @@ class VAEEngine:
         return None
 
     def _dense_bwd(self, dy, lddy, M, x, ldx, w, gw, gb, N, K, dx=None, lddx=0, aux=None, ldaux=0, aux_scale=1.0,
-                   accumulate_dx=False, dx_colsum=None, skip_wgrad=False):
+                   accumulate_dx=False, dx_colsum=None, skip_wgrad=False, fork_ok=True):
         """dy [M,N] -> gw [N,K] += dy^T x, gb [N] += colsum(dy) (gb=None: the kernel that produced dy already added it),
         dx [M,K] (=|+=) dy w (optionally masked by aux).  dx_colsum: bias-gradient buffer of the layer whose
         pre-activation gradient dx is; returns True when the dgrad epilogue accumulated it (tensor path)."""
@@ -364,12 +392,14 @@ class VAEEngine:
         mode = None if skip_wgrad else self._gemm_mode(self.x3_bwd, dy, lddy, x, ldx, gw, K, N, K, M)
         if skip_wgrad:                          # the caller computes the weight gradient (planes layers: bf16 hi plane of x)
             assert gb is None
-        elif mode:
-            ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=mode == "x3")
-            if gb is not None:
-                ops.colsum(dy, lddy, M, N, gb)
         else:
-            ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, colsum=gb)
+            with self._wgrad_stream(M, fork_ok):
+                if mode:
+                    ops.gemm_tc(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, x3=mode == "x3")
+                    if gb is not None:
+                        ops.colsum(dy, lddy, M, N, gb)
+                else:
+                    ops.gemm(dy, lddy, 1, x, ldx, 0, gw, K, N, K, M, splitk=sk, colsum=gb)
         fused = False
         if dx is not None:
             mode = self._gemm_mode(self.x3_bwd, dy, lddy, w, K, dx, lddx, M, K, N)
@@ -474,9 +504,10 @@ class VAEEngine:
             aux, ldaux = h, 4 * D
         if p3:
             self._wgrad16(df16, D, bf.t[(tag + "h_p", (2, R, 4 * D), b16)][0], 4 * D, self._G(prefix + "ff.ff2.weight"), D, 4 * D, R)
+        # p == 0: df aliases dx1 (and dproj aliases dres below), which later kernels of this pass accumulate into
         fused = self._dense_bwd(df, D, R, h, 4 * D, self._W(prefix + "ff.ff2.weight"), self._G(prefix + "ff.ff2.weight"),
                                 None, D, 4 * D, dx=dh, lddx=4 * D, aux=aux, ldaux=ldaux, aux_scale=inv_keep,
-                                dx_colsum=self._G(prefix + "ff.ff1.bias"), skip_wgrad=p3)
+                                dx_colsum=self._G(prefix + "ff.ff1.bias"), skip_wgrad=p3, fork_ok=p > 0)
         # ff1: h = drop(relu(x1 W1^T + b1));  dh already holds d(pre-activation)
         self._dense_bwd(dh, 4 * D, R, x1, D, self._W(prefix + "ff.ff1.weight"), self._G(prefix + "ff.ff1.weight"),
                         None if fused else self._G(prefix + "ff.ff1.bias"), 4 * D, D, dx=dx1, lddx=D,
@@ -497,7 +528,8 @@ class VAEEngine:
             self._wgrad16(dproj16, D, bf.t[(tag + "ctx_p", (2, M, D), b16)][0], ldr,
                           self._G(prefix + "self_attention.W_proj.weight"), D, D, R)
         self._dense_bwd(dproj, D, R, ctx, ldr, self._W(prefix + "self_attention.W_proj.weight"),
-                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=ldr, skip_wgrad=p3)
+                        self._G(prefix + "self_attention.W_proj.weight"), None, D, D, dx=dctx, lddx=ldr, skip_wgrad=p3,
+                        fork_ok=p > 0)
         dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         gwqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight", a.g)
@@ -639,7 +671,8 @@ class VAEEngine:
     def _wgrad16(self, dy16, lddy, x16, ldx, gw, N, K, M):
         """gw [N,K] += dy16[M,N]^T x16[M,K] (bf16 operands, fp32 split-K reduce-adds into the gradient arena)."""
         sk = max(ops.wgrad_splitk(N, K, M, self.sms), 2)
-        ops.gemm_tc_bf16(dy16, lddy, 1, x16, ldx, 0, gw, K, N, K, M, splitk=sk)
+        with self._wgrad_stream(M):
+            ops.gemm_tc_bf16(dy16, lddy, 1, x16, ldx, 0, gw, K, N, K, M, splitk=sk)
 
     def _tf_layer_bwd16(self, bf, tag, prefix, x_in, x_in16, mask, dout, dx_in, B, T, D, H, p, site0, decoder, sos_only=False):
         """Backward of _tf_layer_fwd16.  Every gradient that only feeds GEMMs (d f, d hidden, d proj, d qkv) is produced
@@ -1230,6 +1263,7 @@ class VAEEngine:
         dx = self._encode_layers_bwd(bf, c, dlat, B, T)
         ops.embed_bwd(c["tokens"], c["classes"], dx, self._G("encoder.encoder_embedding.weight"),
                       self._G("encoder.class2hid.weight"), None, B, T, D, 0, math.sqrt(float(D)), V)
+        self._wgrad_join()
 
     # ------------------------------------------------------------------ piano-roll step (--featurisation roll)
     def forward_roll(self, roll, classes, eps=None, train=True, label_smoothing=0.0, downweight=True, want_grad=True):
@@ -1310,6 +1344,7 @@ class VAEEngine:
             dE = bf.get("roll.dE", (M, D), dev)
             ops.embed_dense_bwd(dx, c["classes"], dE, self._G("encoder.class2hid.weight"), B, T, D, math.sqrt(float(D)))
             self._dense_bwd(dE, D, M, c["renc"], ROLL_IN, None, self._G("encoder.roll_embedding.weight"), None, D, ROLL_IN)
+            self._wgrad_join()
         finally:
             ops.set_step_counter(None)
 

@@ -6,7 +6,7 @@ import torch
 from musicstyletransfer_b200 import ops
 
 H = 128
-for B, T in ((2048, 65), (32, 65), (8192, 1)):
+for B, T in ((2048, 65), (32, 65), (256, 65), (1024, 65), (8192, 1)):
     g = torch.Generator().manual_seed(1)
     gx = (torch.randn(B * T, 4 * H, generator=g) * 0.8).cuda()
     w = (torch.randn(4 * H, H, generator=g) * 0.12).cuda()

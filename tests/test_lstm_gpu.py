@@ -17,7 +17,9 @@ def _case(B, T, seed):
     return H, gx, w, bh, tv, dhs
 
 
-@pytest.mark.parametrize("B,T", [(32, 5), (64, 65), (37, 19), (1, 3), (300, 8)])
+# B <= 16 * 74 runs the 16-rows-per-cluster kernels (all clusters resident), larger batches the 32-row kernels (forward:
+# two sub-blocks with the warp groups one phase apart, persistent over row blocks)
+@pytest.mark.parametrize("B,T", [(32, 5), (64, 65), (37, 19), (1, 3), (300, 8), (1200, 4), (1500, 33), (2500, 7), (5000, 1)])
 def test_lstm_tc_matches_fp32_kernel(B, T):
     from musicstyletransfer_b200 import ops
     H, gx, w, bh, tv, dhs = _case(B, T, seed=B * 100 + T)

@@ -316,7 +316,7 @@ def test_gemm_tc_wgrad_at_bench_rows(x3):
 
 
 # ------------------------------------------------------------------------------------------------ LSTM recurrence
-@pytest.mark.parametrize("B,T", [(64, 65), (37, 19), (256, 33)])
+@pytest.mark.parametrize("B,T", [(64, 65), (37, 19), (256, 33), (1300, 9)])
 def test_lstm_tc_vs_oracle_lstm_layer(B, T):
     """lstm_tc (TF32 mma.sync recurrence) directly against oracle.lstm_layer (gluon.rnn.LSTM restatement, model.py:148-153):
     hidden states forward; d(pre-activations), dh0 / dc0 and the bias gradients against its autograd."""
