@@ -460,7 +460,17 @@ int gemm_tc_impl(const void* A, int lda, int transA, const void* B, int ldb, int
   if (p3 && p3->C_lo && (rc = make_map(&mx.c_lo, p3->C_lo, M, N, ldc, 32, 32, false, kMapC16))) return rc;
   // pair tiles pay off once the mainloop is long enough to hide the 128 x 256 epilogue (measured on the step's
   // shapes: K = 128 forward GEMMs are faster on 128 x 128 tiles, K >= 256 ones 1.2-1.35x faster on pair tiles)
-  if (pair_enabled() && M > BM && N >= 64 && K >= 256) {
+  // ... and once there are enough of them: with less than a wave of pair tiles (small batches: M = 2 080 rows at the
+  // reference's batch of 32) the 128 x 128 tiles of the 1-CTA kernel put 2-4x as many SMs on the problem.  Per-SM work of a
+  // tile: 128 x 128 x K (1-CTA) vs 128 x bn2 x K (pair); the pair kernel earns its 1.25x only on full waves.
+  bool use_pair = pair_enabled() && M > BM && N >= 64 && K >= 256;
+  if (use_pair && splitk <= 1) {
+    const int bn2 = N > 128 ? 256 : 128;
+    const long long t1 = (long long)msx_ceil_div(M, BM) * msx_ceil_div(N, BN), tp = (long long)msx_ceil_div(M, 2 * BM) * msx_ceil_div(N, bn2);
+    const long long w1 = (t1 + msx_num_sms() - 1) / msx_num_sms(), wp = (tp + msx_num_sms() / 2 - 1) / (msx_num_sms() / 2);
+    if (5 * w1 * BN < 4 * wp * bn2) use_pair = false;
+  }
+  if (use_pair) {
     // ---- 2-CTA path: 256 x 256 (N > 128) or 256 x 128 pair tiles
     const int bn2 = N > 128 ? 256 : 128;
     if (!a_mn) rc = make_map(&ta, A, M, K, lda, Op::kBKE, BM, false, kOp); else rc = make_map(&ta, A, K, M, lda, Op::kSlabMN, Op::kBKE, true, kOp);
