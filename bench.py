@@ -476,10 +476,18 @@ def run_ours(args):
                       "avg_launch_ms": tms / cnt, "algorithmic_bytes_per_launch": by / cnt, "algorithmic_flops_per_launch": fl / cnt,
                       "measured": "CUDA events around every launch of %d eager steps (the graph-replayed step is what `value` times)" % psteps}
             if kind in ("bf16x3", "bf16p3"):
+                traffic3 = None
+                tpath3 = os.path.join(REPO, "profiles", "traffic_gemm_p3.json")
+                if kind == "bf16p3" and os.path.exists(tpath3):
+                    with open(tpath3) as f:
+                        traffic3 = json.load(f).get("dram_bytes_per_launch")
                 # three kind::f16 MMAs per multiply-add = 1.5 TF32-equivalents: on these shapes the kernel is back under the
                 # HBM roof of its fp32 operand / result bytes
                 rl.append(dict(common, bound="hbm", achieved=gbk, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbk / peaks["hbm_gbs"],
-                               traffic=None, peak_source=peaks["src"] + " HBM copy bandwidth",
+                               traffic=traffic3, traffic_source="one ncu --set full capture of the three large forward shapes "
+                               "(profiles/traffic_gemm_p3.json), mean per launch; the bench's mean also covers the five small "
+                               "top-layer launches" if traffic3 else None,
+                               peak_source=peaks["src"] + " HBM copy bandwidth",
                                tensor={"achieved": tfk, "executed_tflops": 3 * tfk, "peak": peaks["tflops"], "unit": "TFLOP/s",
                                        "executed_frac": 3 * tfk / peaks["tflops"],
                                        "peak_source": peaks["src"] + " bf16 sustained (cuBLAS); the kernel executes 3 bf16 MMAs "

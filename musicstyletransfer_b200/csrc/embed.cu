@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
                                                         unsigned short* __restrict__ out16,
                                                         unsigned short* __restrict__ out16lo,
                                                         float* __restrict__ mask, int B, int T, int D, int prefix,
-                                                        float scale, int vocab) {
+                                                        float scale, int vocab, int vec) {
   const int TP = T + prefix;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -42,6 +42,32 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
   const float* pr = pe ? pe + (size_t)pos * D : nullptr;
   float* dst = out ? out + (size_t)row * D : nullptr;
   unsigned short* dst16 = out16 ? out16 + (size_t)row * D : nullptr;
+  if (vec) {                                // vector path (host: D % 4 == 0 and 16-byte aligned tables / outputs)
+    for (int e = lane * 4; e < D; e += 128) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+      if (cls) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cls + e));
+        v.x += c4.x; v.y += c4.y; v.z += c4.z; v.w += c4.w;
+      }
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      if (pr) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(pr + e));
+        v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+      }
+      if (dst) *reinterpret_cast<float4*>(dst + e) = v;
+      if (out16lo) {
+        uint2 hi, lo;
+        split4_bf16(v.x, v.y, v.z, v.w, hi, lo);
+        *reinterpret_cast<uint2*>(dst16 + e) = hi;
+        *reinterpret_cast<uint2*>(out16lo + (size_t)row * D + e) = lo;
+      } else if (dst16) {
+        uint2 hi;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(v.w), "f"(v.z));
+        *reinterpret_cast<uint2*>(dst16 + e) = hi;
+      }
+    }
+  } else
   for (int e = lane; e < D; e += 32) {
     float v = __ldg(src + e);
     if (cls) v += __ldg(cls + e);
@@ -256,9 +282,11 @@ extern "C" int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, co
   if (B == 0 || T + prefix == 0) return MSX_OK;
   const long long rows = (long long)B * (T + prefix);
   const int wpb = 8;
+  const int vec = (D & 3) == 0 && (((uintptr_t)tok_emb | (uintptr_t)cls_emb | (uintptr_t)prefix_vec | (uintptr_t)pe | (uintptr_t)out |
+                                    (uintptr_t)out_bf16 | (uintptr_t)out_bf16_lo) & 15) == 0;
   embed_fwd_kernel<<<msx_ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, reinterpret_cast<unsigned short*>(out_bf16),
-      reinterpret_cast<unsigned short*>(out_bf16_lo), mask, B, T, D, prefix, scale, vocab);
+      reinterpret_cast<unsigned short*>(out_bf16_lo), mask, B, T, D, prefix, scale, vocab, vec);
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
