@@ -284,6 +284,15 @@ int msx_embed_fwd_ex(const int32_t* tokens, const int32_t* classes, const int32_
 int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, const int32_t* seq_lens, const float* tok_emb,
                     const float* cls_emb, const float* prefix_vec, const float* pe, float* out, void* out_bf16,
                     void* out_bf16_lo, float* mask, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
+/* Per-token row sums: out[v, :] += scale * sum of X[r, :] over the rows with tokens[r] == v — the Embedding backward
+ * (model.py:141,175) as sort + segmented sum, D up to 1024.  msx_token_sort: counting sort of the row indices by token
+ * (workspace int32 [3 V]; perm / sorted_tok int32 [M]); msx_rows_sum_by_token: one coalesced read of every row of X [M, ld],
+ * one 16-byte red per column group and token change of a 128-row slice of the sorted order.  In the LSTM decoder's table
+ * mode (msx_lstm_tc_fwd_tab) X = d(pre-activations) [B*T, 4H] and out is the gradient of the [V, 4H] i2h table. */
+int msx_token_sort(const int32_t* tokens, long long M, int V, int32_t* perm, int32_t* sorted_tok, int32_t* workspace,
+                   void* stream);
+int msx_rows_sum_by_token(const float* X, int ld, int D, const int32_t* perm, const int32_t* sorted_tok, long long M,
+                          float scale, float* out, void* stream);
 int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                   float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 
@@ -323,6 +332,12 @@ int msx_lstm_bwd(float* gates_inout, const float* w_h2h, const float* cs, const 
 int msx_lstm_tc_supported(int H, int ld0, const float* h0, const float* c0);
 int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const float* h0, const float* c0, int ld0,
                     float* hs, float* hprev, float* cs, int B, int T, int H, void* stream);
+/* Table mode: the layer's input is an embedding lookup (LSTMDecoder.forward_train, model.py:175-179: embedding -> LSTM), so
+ * x_t W_i2h^T + b_i2h is row tokens[b, t] of table [V, 4H] = emb W_i2h^T + b_i2h.  The kernel fetches the rows itself (the
+ * [B*T, 4H] input pre-activations never exist); gates_out [B*T, 4H] receives the gate activations.  tokens in [0, V). */
+int msx_lstm_tc_fwd_tab(float* gates_out, const int32_t* tokens, const float* table, const float* w_h2h, const float* b_h2h,
+                        const float* h0, const float* c0, int ld0, float* hs, float* hprev, float* cs, int B, int T, int H,
+                        void* stream);
 int msx_lstm_tc_bwd(float* gates_inout, const float* w_h2h, const float* cs, const float* c0, int ld0, const float* dhs,
                     float* dh0, float* dc0, float* db_i2h, float* db_h2h, int B, int T, int H, void* stream);
 

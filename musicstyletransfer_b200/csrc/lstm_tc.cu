@@ -122,7 +122,8 @@ struct FwdSmem {
 // clusters for small batches, where SMs are idle and only the length of the step chain matters (B = 32: 2 clusters).
 template <int NSB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    lstm_tc_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_h2h, const float* __restrict__ b_h2h,
+    lstm_tc_fwd_kernel(float* __restrict__ gx, const int* __restrict__ tokens, const float* __restrict__ table,
+                       const float* __restrict__ w_h2h, const float* __restrict__ b_h2h,
                        const float* __restrict__ h0, const float* __restrict__ c0, int ld0, float* __restrict__ hs,
                        float* __restrict__ hprev, float* __restrict__ cs, int B, int T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,7 +151,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       for (int i = 0; i < 4; ++i) {
         const int ch = tid + i * kThreads, row = ch >> 6, rem = ch & 63, gate = rem >> 4, c4 = (rem & 15) * 4;
         const int b = min(b0 + sb * RB + row, B - 1);
-        cp_async16(dst + row * kRowPitch + gate * UH + c4, gx + ((size_t)b * T + t) * 4 * H + gate * H + crank * UH + c4);
+        // table mode: the input pre-activations of row (b, t) are row tokens[b, t] of the [V, 4H] table emb W_i2h^T + b_i2h
+        // (2.4 KB rows of an L2-resident 600 KB table): the [B*T, 4H] input never exists, gx only receives the activations
+        const float* src = tokens ? table + (size_t)__ldg(tokens + (size_t)b * T + t) * 4 * H
+                                  : gx + ((size_t)b * T + t) * 4 * H;
+        cp_async16(dst + row * kRowPitch + gate * UH + c4, src + gate * H + crank * UH + c4);
       }
     }
     cp_async_commit();
@@ -522,9 +527,23 @@ extern "C" int msx_lstm_tc_supported(int H_, int ld0, const float* h0, const flo
   return (H_ == H && (ld0 & 1) == 0 && h0 && c0 && ((uintptr_t)h0 & 7) == 0 && ((uintptr_t)c0 & 7) == 0) ? 1 : 0;
 }
 
+extern "C" int msx_lstm_tc_fwd_tab(float* gates_out, const int32_t* tokens, const float* table, const float* w_h2h,
+                                   const float* b_h2h, const float* h0, const float* c0, int ld0, float* hs, float* hprev,
+                                   float* cs, int B, int T, int H_, void* stream);
 extern "C" int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float* b_h2h, const float* h0, const float* c0,
                                int ld0, float* hs, float* hprev, float* cs, int B, int T, int H_, void* stream) {
+  return msx_lstm_tc_fwd_tab(gx_inout, nullptr, nullptr, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H_, stream);
+}
+
+// Table mode (tokens != NULL): the layer's input is an embedding lookup, so x_t W_i2h^T + b_i2h is row tokens[b, t] of
+// table [V, 4H] = emb W_i2h^T + b_i2h (one tiny GEMM per step).  The kernel fetches those rows itself; gates_out receives the
+// gate activations as before.  Token ids must lie in [0, V): the caller's table has V rows.
+extern "C" int msx_lstm_tc_fwd_tab(float* gx_inout, const int32_t* tokens, const float* table, const float* w_h2h,
+                                   const float* b_h2h, const float* h0, const float* c0, int ld0, float* hs, float* hprev,
+                                   float* cs, int B, int T, int H_, void* stream) {
   MSX_REQUIRE(gx_inout && w_h2h && b_h2h && h0 && c0 && hs && hprev && cs, "msx_lstm_tc_fwd: null pointer");
+  MSX_REQUIRE((tokens == nullptr) == (table == nullptr) && ((uintptr_t)table & 15) == 0,
+              "msx_lstm_tc_fwd_tab: tokens and a 16-byte aligned table go together");
   MSX_REQUIRE(msx_lstm_tc_supported(H_, ld0, h0, c0), "msx_lstm_tc_fwd: needs H == 128, even ld0, 8-byte aligned h0 / c0");
   if (B == 0 || T == 0) return MSX_OK;
   // persistent clusters: one 2-CTA cluster per SM pair at most, each walks its row blocks with W_h2h kept in registers;
@@ -533,14 +552,14 @@ extern "C" int msx_lstm_tc_fwd(float* gx_inout, const float* w_h2h, const float*
   if ((B + RB - 1) / RB <= resident) {
     const int clusters = (B + RB - 1) / RB;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    lstm_tc_fwd_kernel<1><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0,
-                                                                                            hs, hprev, cs, B, T);
+    lstm_tc_fwd_kernel<1><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, tokens, table, w_h2h, b_h2h,
+                                                                                            h0, c0, ld0, hs, hprev, cs, B, T);
   } else {
     const int blocks = (B + R - 1) / R;
     const int clusters = blocks < resident ? blocks : resident;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    lstm_tc_fwd_kernel<2><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, w_h2h, b_h2h, h0, c0, ld0,
-                                                                                            hs, hprev, cs, B, T);
+    lstm_tc_fwd_kernel<2><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, tokens, table, w_h2h, b_h2h,
+                                                                                            h0, c0, ld0, hs, hprev, cs, B, T);
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;

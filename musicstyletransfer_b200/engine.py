@@ -301,6 +301,7 @@ class VAEEngine:
         # every kernel fills a fraction of the GPU and the step is a chain of ~75 dependent launches) they leave the chain:
         # forked onto a side stream behind the kernel that produced dY, joined before Adam (also inside captured graphs).
         self.wgrad_side_rows = 16384          # fork when the reduction has at most this many rows; 0 disables
+        self.dec_table = True                 # token-event LSTM decoder: first layer's i2h product as a [V, 4H] table
         self._side = None
         self._side_used = False
 
@@ -1003,10 +1004,17 @@ class VAEEngine:
         return seq[cur][:, :stop + 1].clone(), score[cur].clone()
 
     # ------------------------------------------------------------------ LSTM decoder (model.py:131-203)
-    def _lstm_decoder_fwd(self, bf, xe, z, classes, B, T, p_drop=0.0):
+    def _dec_table_ok(self):
+        """The token-event LSTM decoder feeds its first layer from the [V, 4H] table emb W_i2h^T + b_i2h (tensor LSTM kernel)."""
+        return self.lstm_tc and self.cfg.dec_type == "lstm" and self.cfg.dec_size == 128 and self.dec_table
+
+    def _lstm_decoder_fwd(self, bf, xe, z, classes, B, T, p_drop=0.0, tokens=None):
         """LSTMDecoder.forward_train after the input embedding: initial state latent2hid(z) + class2hid[classes] split into
         (h0, c0) and shared by every layer (model.py:159-167), then per layer the i2h GEMM for all T steps and the persistent
-        recurrence; dropout between the layers (gluon.rnn.LSTM(dropout=...), model.py:148-153).  xe [B*T, H] -> hs [B*T, H]."""
+        recurrence; dropout between the layers (gluon.rnn.LSTM(dropout=...), model.py:148-153).  xe [B*T, H] -> hs [B*T, H].
+        tokens (xe None): table mode.  The first layer's input is the embedding of `tokens` (model.py:175-179), so its i2h
+        product is a row of table [V, 4H] = emb W_i2h^T + b_i2h: one 293-row GEMM per step instead of the embedding gather and
+        a [B*T, H] x [H, 4H] GEMM; the recurrence kernel fetches the table rows itself."""
         cfg, dev = self.cfg, self.device
         Z, Hd = cfg.latent, cfg.dec_size
         M = B * T
@@ -1027,21 +1035,30 @@ class VAEEngine:
                 else:
                     x = x                                        # no dropout: the lower layer's hs is read in place
             gates = bf.get(tag + "gates", (M, 4 * Hd), dev)
-            self._dense_fwd(x, Hd, M, "decoder.decoder.l%d_i2h_weight" % l, "decoder.decoder.l%d_i2h_bias" % l, gates,
-                            4 * Hd, 4 * Hd, Hd, decoder=True)
             hs = bf.get(tag + "hs", (M, Hd), dev)
             hprev = bf.get(tag + "hprev", (M, Hd), dev)
             cs = bf.get(tag + "cs", (M, Hd), dev)
-            lstm_fwd(gates, self._W("decoder.decoder.l%d_h2h_weight" % l), self._W("decoder.decoder.l%d_h2h_bias" % l),
-                     tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            if l == 0 and x is None:                             # table mode
+                V = cfg.vocab
+                tab = bf.get("dec.i2h_table", (V, 4 * Hd), dev)
+                self._dense_fwd(self._W("decoder.embedding.weight"), Hd, V, "decoder.decoder.l0_i2h_weight",
+                                "decoder.decoder.l0_i2h_bias", tab, 4 * Hd, 4 * Hd, Hd, decoder=True)
+                ops.lstm_tc_fwd_tab(gates, tokens, tab, self._W("decoder.decoder.l0_h2h_weight"),
+                                    self._W("decoder.decoder.l0_h2h_bias"), tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
+            else:
+                self._dense_fwd(x, Hd, M, "decoder.decoder.l%d_i2h_weight" % l, "decoder.decoder.l%d_i2h_bias" % l, gates,
+                                4 * Hd, 4 * Hd, Hd, decoder=True)
+                lstm_fwd(gates, self._W("decoder.decoder.l%d_h2h_weight" % l), self._W("decoder.decoder.l%d_h2h_bias" % l),
+                         tv, tv[:, Hd:], 2 * Hd, hs, hprev, cs, B, T, Hd)
             self._lstm_in = getattr(self, "_lstm_in", {})
             self._lstm_in[l] = x
             x = hs
         return x
 
-    def _lstm_decoder_bwd(self, bf, c, ddec, dz, B, T, p_drop=0.0):
+    def _lstm_decoder_bwd(self, bf, c, ddec, dz, B, T, p_drop=0.0, tokens=None):
         """Backward of _lstm_decoder_fwd: ddec [B*T, H] = gradient of the top layer's hidden states.  Accumulates the LSTM /
-        latent2hid / class2hid parameter gradients, writes dz, returns the gradient of the decoder input xe."""
+        latent2hid / class2hid parameter gradients, writes dz, returns the gradient of the decoder input xe (None in table
+        mode, where the embedding / i2h gradients are taken from the per-token sums of d(pre-activations) instead)."""
         cfg, dev = self.cfg, self.device
         Z, Hd = cfg.latent, cfg.dec_size
         M = B * T
@@ -1063,10 +1080,24 @@ class VAEEngine:
                      db_h2h=self._G("decoder.decoder.l%d_h2h_bias" % l))            # gates now hold d(pre-activations)
             if dtv_l is not dtv:
                 ops.rows_strided(dtv_l, 2 * Hd, dtv, 2 * Hd, B, 2 * Hd, add=True)
+            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l%d_h2h_weight" % l), None, 4 * Hd, Hd)
+            if l == 0 and x_in is None:
+                # table mode: d table[v] = sum of d(pre-activations) over the rows with token v (the sorted-segment row sums
+                # of the embedding backward, 512 wide); then d emb += d table W_i2h and d W_i2h += d table^T emb, 293 rows each
+                V = cfg.vocab
+                dtab = bf.get("dec.d_i2h_table", (V, 4 * Hd), dev)
+                dtab.zero_()                                     # 600 KB memset node
+                perm, stok = bf.get("dec.tok_perm", (M,), dev, torch.int32), bf.get("dec.tok_sorted", (M,), dev, torch.int32)
+                ops.token_sort(tokens, V, perm, stok, bf.get("dec.tok_ws", (3 * V,), dev, torch.int32), M=M)
+                ops.rows_sum_by_token(gates, 4 * Hd, 4 * Hd, perm, stok, dtab, M=M)
+                self._dense_bwd(dtab, 4 * Hd, V, self._W("decoder.embedding.weight"), Hd,
+                                self._W("decoder.decoder.l0_i2h_weight"), self._G("decoder.decoder.l0_i2h_weight"), None,
+                                4 * Hd, Hd, dx=self._G("decoder.embedding.weight"), lddx=Hd, accumulate_dx=True)
+                dh = None
+                continue
             dx = bf.get(tag + "dxe", (M, Hd), dev)
             self._dense_bwd(gates, 4 * Hd, M, x_in, Hd, self._W("decoder.decoder.l%d_i2h_weight" % l),
                             self._G("decoder.decoder.l%d_i2h_weight" % l), None, 4 * Hd, Hd, dx=dx, lddx=Hd)
-            self._dense_bwd(gates, 4 * Hd, M, hprev, Hd, None, self._G("decoder.decoder.l%d_h2h_weight" % l), None, 4 * Hd, Hd)
             if l > 0 and p_drop > 0:
                 ops.dropout(dx, dx, p_drop, self.dropout_seed, LSTM_SITE + l - 1)    # the forward's mask, on the gradient
             dh = dx
@@ -1148,10 +1179,13 @@ class VAEEngine:
 
         # ---- decoder
         if cfg.dec_type == "lstm":
-            xe = bf.get("dec.xe", (M, Hd), dev)
-            ops.embed_fwd(tokens, None, None, self._W("decoder.embedding.weight"), None, None, None, xe, None, B, T, Hd, 0,
-                          1.0, V)
-            hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, T, pd_)
+            if self._dec_table_ok():
+                hs = self._lstm_decoder_fwd(bf, None, z, classes, B, T, pd_, tokens=tokens)
+            else:
+                xe = bf.get("dec.xe", (M, Hd), dev)
+                ops.embed_fwd(tokens, None, None, self._W("decoder.embedding.weight"), None, None, None, xe, None, B, T, Hd, 0,
+                              1.0, V)
+                hs = self._lstm_decoder_fwd(bf, xe, z, classes, B, T, pd_)
             dec_out, Td = hs, T
             dmask = None
         else:
@@ -1236,8 +1270,9 @@ class VAEEngine:
                         V, Hd, dx=ddec, lddx=Hd)
         dz = bf.get("dz", (B, Z), dev)
         if cfg.dec_type == "lstm":
-            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, T, c["pd"])
-            ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
+            dxe = self._lstm_decoder_bwd(bf, c, ddec, dz, B, T, c["pd"], tokens=c["tokens"])
+            if dxe is not None:
+                ops.embed_bwd(c["tokens"], None, dxe, self._G("decoder.embedding.weight"), None, None, B, T, Hd, 0, 1.0, V)
         else:
             dxs = c["dxs"]
             dcur = ddec

@@ -45,7 +45,7 @@ def stream_ptr():
 
 
 # kernels enqueued per C-ABI call (for the bench's gpu_launches claim)
-_KERNELS_PER_CALL = {"msx_adam_step": 2}
+_KERNELS_PER_CALL = {"msx_adam_step": 2, "msx_token_sort": 3}
 LAUNCHES = 0
 _profile = None     # optional {"match": substring, "events": [(start, end, tag)]} set by bench.py
 

@@ -274,6 +274,18 @@ def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, pr
              _i(D), _i(prefix), _f(scale), _i(vocab), _i(ncls), lib.stream_ptr())
 
 
+def token_sort(tokens, V, perm, sorted_tok, workspace, M=None):
+    """Counting sort of the row indices 0..M-1 by tokens[r] (int32 tensors; workspace int32 [3 V])."""
+    lib.call("msx_token_sort", P(tokens), _ll(tokens.numel() if M is None else M), _i(V), P(perm), P(sorted_tok), P(workspace),
+             lib.stream_ptr())
+
+
+def rows_sum_by_token(X, ld, D, perm, sorted_tok, out, M=None, scale=1.0):
+    """out [V, D] += scale * per-token sums of the rows of X [M, ld] (perm / sorted_tok from token_sort)."""
+    lib.call("msx_rows_sum_by_token", P(X), _i(ld), _i(D), P(perm), P(sorted_tok), _ll(perm.numel() if M is None else M),
+             _f(scale), P(out), lib.stream_ptr())
+
+
 def roll_features(roll, renc, rdec, B, S):
     assert roll.dtype == torch.uint8 and roll.is_contiguous()
     lib.call("msx_roll_features", P(roll), P(_chk(renc)), P(_chk(rdec)), _i(B), _i(S), lib.stream_ptr())
@@ -355,6 +367,12 @@ def lstm_tc_supported(H, ld0, h0, c0):
 def lstm_tc_fwd(gx, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H):
     lib.call("msx_lstm_tc_fwd", P(gx), P(w_h2h), P(b_h2h), P(h0), P(c0), _i(ld0), P(hs), P(hprev), P(cs), _i(B), _i(T),
              _i(H), lib.stream_ptr())
+
+
+def lstm_tc_fwd_tab(gates, tokens, table, w_h2h, b_h2h, h0, c0, ld0, hs, hprev, cs, B, T, H):
+    """lstm_tc_fwd whose input pre-activations are rows tokens[b, t] of table [V, 4H] (= emb W_i2h^T + b_i2h)."""
+    lib.call("msx_lstm_tc_fwd_tab", P(gates), P(tokens), P(table), P(w_h2h), P(b_h2h), P(h0), P(c0), _i(ld0), P(hs), P(hprev),
+             P(cs), _i(B), _i(T), _i(H), lib.stream_ptr())
 
 
 def lstm_tc_bwd(gates, w_h2h, cs, c0, ld0, dhs, dh0, dc0, B, T, H, db_i2h=None, db_h2h=None):

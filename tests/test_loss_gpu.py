@@ -120,3 +120,33 @@ def test_softmax_rows_probs_api_and_sampling():
     assert bool(close.all())
     assert bool((seq[:, 2].cpu().long() == got).all())
     assert float((score.double().cpu() + torch.log(want[torch.arange(rows), got])).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("M,V,D,ld", [(133120, 293, 512, 512), (2080, 293, 512, 512), (5000, 7, 128, 160), (129, 4096, 256, 256),
+                                      (1, 3, 4, 4)])
+def test_token_sort_and_rows_sum_by_token(M, V, D, ld):
+    """msx_token_sort + msx_rows_sum_by_token (Embedding backward as sort + segmented sum, model.py:141,175) vs index_add in
+    float64; skewed token distribution (a few dozen hot tokens, as the 4/4 rows have), tokens outside [0, V) are clamped."""
+    from musicstyletransfer_b200 import ops
+    g = torch.Generator().manual_seed(M + V)
+    hot = torch.randint(0, V, (max(1, min(V, 24)),), generator=g)
+    tok = hot[torch.randint(0, hot.numel(), (M,), generator=g)]
+    rare = torch.rand(M, generator=g) < 0.05
+    tok = torch.where(rare, torch.randint(-2, V + 2, (M,), generator=g), tok).to(torch.int32)
+    X = torch.randn(M, ld, generator=g)
+    out0 = torch.randn(V, D, generator=g)
+    want = out0.double().clone()
+    want.index_add_(0, tok.clamp(0, V - 1).long(), 0.5 * X[:, :D].double())
+    td, Xd, out = tok.cuda(), X.cuda(), out0.cuda()
+    perm = torch.empty(M, dtype=torch.int32, device="cuda")
+    stok = torch.empty(M, dtype=torch.int32, device="cuda")
+    ws = torch.empty(3 * V, dtype=torch.int32, device="cuda")
+    ops.token_sort(td, V, perm, stok, ws)
+    ops.rows_sum_by_token(Xd, ld, D, perm, stok, out, scale=0.5)
+    torch.cuda.synchronize()
+    p = perm.cpu().long()
+    assert torch.equal(torch.sort(p).values, torch.arange(M))                       # a permutation
+    assert torch.equal(stok.cpu(), tok.clamp(0, V - 1)[p])                          # tokens travel with their rows
+    assert bool((stok.cpu()[1:] >= stok.cpu()[:-1]).all())                          # sorted
+    err = float((out.double().cpu() - want).abs().max()) / float(want.abs().max())
+    assert err < 1e-5, err
