@@ -293,6 +293,11 @@ int msx_token_sort(const int32_t* tokens, long long M, int V, int32_t* perm, int
                    void* stream);
 int msx_rows_sum_by_token(const float* X, int ld, int D, const int32_t* perm, const int32_t* sorted_tok, long long M,
                           float scale, float* out, void* stream);
+/* First encoder layer's K|Q|V projection from tables: x0 = scale * (emb[token] + class2hid[class]) + pe[position]
+ * (model.py:84-93, transformer.py:204-231), hence x0 W^T + b = scale * (tab[C + token] + tab[class]) + postab[position] with
+ * tab [C + V, N] = [class2hid; emb] W^T and postab [T, N] = pe[:T] W^T + b computed once per step.  out [B*T, N]. */
+int msx_rows_from_tables(const int32_t* tokens, const int32_t* classes, const float* tab, const float* postab, float* out,
+                         int B, int T, int N, int C, int V, float scale, void* stream);
 int msx_embed_bwd(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb, float* d_cls_emb,
                   float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab, void* stream);
 

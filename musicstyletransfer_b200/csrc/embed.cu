@@ -291,6 +291,58 @@ extern "C" int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, co
   return MSX_OK;
 }
 
+namespace {
+// out[b*T + t, :] = scale * (tab[C + tokens[b, t], :] + tab[classes[b], :]) + postab[t, :]; blockDim.x = N / 4.
+// A CTA owns ONE position t and walks a slice of the batch: the position row stays in registers, the C class rows stay in
+// L1, so per output row only the token row travels from L2 (three table rows per output row made the kernel L2-bound).
+__global__ void __launch_bounds__(256) rows_from_tables_kernel(const int* __restrict__ tokens, const int* __restrict__ classes,
+                                                               const float* __restrict__ tab, const float* __restrict__ postab,
+                                                               float* __restrict__ out, int B, int T, int N, int C, int V,
+                                                               float scale, int bchunks) {
+  const int c = threadIdx.x * 4;
+  const int t = blockIdx.x % T, chunk = blockIdx.x / T;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(postab + (size_t)t * N + c));
+  constexpr int U = 4;                                      // batch rows per iteration
+  for (int b0 = chunk * U; b0 < B; b0 += bchunks * U) {
+    float4 a[U], k[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int b = min(b0 + u, B - 1);
+      const int tok = min(max(__ldg(tokens + (size_t)b * T + t), 0), V - 1), cls = min(max(__ldg(classes + b), 0), C - 1);
+      a[u] = __ldg(reinterpret_cast<const float4*>(tab + (size_t)(C + tok) * N + c));
+      k[u] = __ldg(reinterpret_cast<const float4*>(tab + (size_t)cls * N + c));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (b0 + u < B)
+        *reinterpret_cast<float4*>(out + ((size_t)(b0 + u) * T + t) * N + c) =
+            make_float4(fmaf(scale, a[u].x + k[u].x, p.x), fmaf(scale, a[u].y + k[u].y, p.y), fmaf(scale, a[u].z + k[u].z, p.z),
+                        fmaf(scale, a[u].w + k[u].w, p.w));
+  }
+}
+}  // namespace
+
+// The first encoder layer's K|Q|V projection without a [B*T, D] x [D, 3D] GEMM.  Its input is
+// x0 = scale * (emb[token] + class2hid[class]) + pe[position] (Encoder.hybrid_forward, model.py:84-93, PositionalEmbeddings,
+// transformer.py:204-231), so x0 W^T + b = scale * (tab[C + token] + tab[class]) + postab[position] with the per-step tables
+// tab [C + V, N] = [class2hid; emb] W^T and postab [T, N] = pe[:T] W^T + b (two GEMMs over 295 and T rows).  One 3 KB row
+// written per position, three L2-resident table rows read.
+extern "C" int msx_rows_from_tables(const int32_t* tokens, const int32_t* classes, const float* tab, const float* postab,
+                                    float* out, int B, int T, int N, int C, int V, float scale, void* stream) {
+  MSX_REQUIRE(tokens && classes && tab && postab && out, "msx_rows_from_tables: null pointer");
+  MSX_REQUIRE(N >= 4 && N <= 1024 && (N & 3) == 0 && (((uintptr_t)tab | (uintptr_t)postab | (uintptr_t)out) & 15) == 0,
+              "msx_rows_from_tables: N %% 4 == 0, N <= 1024, 16-byte aligned tables and output");
+  MSX_REQUIRE(C >= 1 && V >= 1, "msx_rows_from_tables: empty table");
+  if (B == 0 || T == 0) return MSX_OK;
+  // T x bchunks CTAs: about 8 resident CTAs per SM
+  int bchunks = (msx_num_sms() * 8 + T - 1) / T;
+  if (bchunks > (B + 3) / 4) bchunks = (B + 3) / 4;
+  rows_from_tables_kernel<<<T * bchunks, N / 4, 0, (cudaStream_t)stream>>>(tokens, classes, tab, postab, out, B, T, N, C, V, scale,
+                                                                          bchunks);
+  MSX_LAUNCH_CHECK();
+  return MSX_OK;
+}
+
 extern "C" int msx_embed_bwd_ex(const int32_t* tokens, const int32_t* classes, const float* dout, float* d_tok_emb,
                                 float* d_cls_emb, float* d_prefix, int B, int T, int D, int prefix, float scale, int vocab,
                                 int num_classes, void* stream);

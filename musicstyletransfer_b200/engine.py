@@ -302,6 +302,7 @@ class VAEEngine:
         # forked onto a side stream behind the kernel that produced dY, joined before Adam (also inside captured graphs).
         self.wgrad_side_rows = 16384          # fork when the reduction has at most this many rows; 0 disables
         self.dec_table = True                 # token-event LSTM decoder: first layer's i2h product as a [V, 4H] table
+        self.qkv0_table = True                # token-event encoder: first layer's K|Q|V projection from per-step tables
         self._side = None
         self._side_used = False
 
@@ -320,7 +321,7 @@ class VAEEngine:
         return self.arena.grad(name)
 
     def _dense_fwd(self, x, ldx, M, name_w, name_b, out, ldo, N, K, relu=False, drop_p=0.0, site=0, accumulate=False,
-                   w=None, b=None, mask_out=None, decoder=False, gemm_name=None):
+                   w=None, b=None, mask_out=None, decoder=False, gemm_name=None, force_x3=False):
         """mask_out (tensor path only, N % 32 == 0): int32 [M, N/32] bit mask of (out > 0), the ReLU / dropout mask the
         dgrad of the next layer applies; returns True when it was written.
         decoder: a GEMM of the LSTM decoder (i2h, output layer).  It only feeds the reconstruction loss, which single-pass
@@ -329,6 +330,8 @@ class VAEEngine:
         w = self._W(name_w) if w is None else w
         b = (self._W(name_b) if name_b else None) if b is None else b
         want = self.x3_fwd if (self.x3_bwd or not decoder) else None
+        if force_x3:
+            want = "x3"                          # per-step tables (a few hundred rows): always compensated, in every tensor mode
         if want and self.x3_skip and any(k in (gemm_name or name_w or "") for k in self.x3_skip):
             want = None                          # diagnostic: this GEMM single-pass (profiles/micro/diag_x3_sites.py)
         mode = self._gemm_mode(want, x, ldx, w, K, out, ldo, M, N, K)
@@ -414,7 +417,7 @@ class VAEEngine:
         return fused
 
     # ------------------------------------------------------------------ transformer layer
-    def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder, sos_only=False):
+    def _tf_layer_fwd(self, bf, tag, prefix, x_in, mask, B, T, D, H, p, site0, decoder, sos_only=False, qkv_src=None):
         """One post-LN Transformer layer (transformer.py:151-159 / :192-201).  sos_only: the caller reads the layer's output
         at position 0 of every sequence only (the encoder's top layer: model.py:97-100 takes `out[:, 0, :]`), so everything
         after the attention — projection, LayerNorms, feed-forward — runs on those B rows instead of B*T; attention itself
@@ -426,7 +429,10 @@ class VAEEngine:
         qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
         wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
-        self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv, gemm_name=prefix + "qkv")
+        if qkv_src is not None:
+            self._qkv0_from_tables(bf, qkv, qkv_src, prefix, B, T, D)
+        else:
+            self._dense_fwd(x_in, D, M, None, None, qkv, 3 * D, 3 * D, D, w=wqkv, b=bqkv, gemm_name=prefix + "qkv")
         ctx = bf.get(tag + "ctx", (M, D), dev)
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd),
@@ -553,7 +559,8 @@ class VAEEngine:
         """p3 GEMM operands need K % 64 == 0 and the vectorised LayerNorm path (D % 128 == 0)."""
         return self.p3 and D % 128 == 0
 
-    def _tf_layer_fwd_p3(self, bf, tag, prefix, x_in, x_in_p, mask, B, T, D, H, p, site0, decoder, sos_only=False):
+    def _tf_layer_fwd_p3(self, bf, tag, prefix, x_in, x_in_p, mask, B, T, D, H, p, site0, decoder, sos_only=False,
+                         qkv_src=None):
         """_tf_layer_fwd with every GEMM operand as bf16 hi / lo planes (msx_gemm_tc_p3): x_in_p [2, B*T, D] comes from the
         kernel that produced x_in; the context and the FF hidden activation exist ONLY as planes; qkv, the projection
         output, f, the residual stream and the LayerNorm arithmetic are fp32.  Returns (out fp32, out planes)."""
@@ -565,7 +572,10 @@ class VAEEngine:
         qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
         kq, vq = prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight"
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
-        ops.gemm_tc_p3(x_in_p[0], x_in_p[1], D, a.span16(kq, vq), a.span16lo(kq, vq), D, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
+        if qkv_src is not None:
+            self._qkv0_from_tables(bf, qkv, qkv_src, prefix, B, T, D)
+        else:
+            ops.gemm_tc_p3(x_in_p[0], x_in_p[1], D, a.span16(kq, vq), a.span16lo(kq, vq), D, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
         ctxp = bf.get(tag + "ctx_p", (2, M, D), dev, b16)
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctxp[0], B, T, H, D // H, x3_scores=True, ctx_lo=ctxp[1],
@@ -615,7 +625,8 @@ class VAEEngine:
         """bf16 GEMM operands need 16-byte aligned rows (D % 8) and the vectorised LayerNorm path (D % 128)."""
         return self.bf16 and D % 128 == 0
 
-    def _tf_layer_fwd16(self, bf, tag, prefix, x_in, x_in16, mask, B, T, D, H, p, site0, decoder, sos_only=False):
+    def _tf_layer_fwd16(self, bf, tag, prefix, x_in, x_in16, mask, B, T, D, H, p, site0, decoder, sos_only=False,
+                        qkv_src=None):
         """_tf_layer_fwd with bf16 GEMM operands: x_in16 / ctx / x1 / the FF hidden activation are read by the GEMMs as
         bfloat16 (the hidden activation and the context exist only in bf16), weights come from the bf16 shadow arena;
         qkv, the projection output, f and the LayerNorm arithmetic stay fp32.  sos_only: as in _tf_layer_fwd, everything
@@ -628,7 +639,10 @@ class VAEEngine:
         qkv = bf.get(tag + "qkv", (M, 3 * D), dev)
         wqkv = a.span16(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
         bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
-        ops.gemm_tc_bf16(x_in16, D, 0, wqkv, D, 1, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
+        if qkv_src is not None:
+            self._qkv0_from_tables(bf, qkv, qkv_src, prefix, B, T, D)
+        else:
+            ops.gemm_tc_bf16(x_in16, D, 0, wqkv, D, 1, qkv, 3 * D, M, 3 * D, D, bias=bqkv)
         ctx16 = bf.get(tag + "ctx16", (M, D), dev, b16)
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H, q0_only=sos_only and D // H == 32)
@@ -755,18 +769,40 @@ class VAEEngine:
         x16 = bf.get("enc.x0_16", (M, D), dev, torch.bfloat16) if l16 else None
         if l16:
             self.arena.refresh_bf16_shadow()          # 8 MB read + 4 MB written per step; always current, also under graphs
+        # first layer's K|Q|V projection from tables (msx_rows_from_tables): x0 is a sum of three table rows, so is x0 W^T + b
+        a = self.arena
+        cname, ename = "encoder.class2hid.weight", "encoder.encoder_embedding.weight"
+        C = cfg.num_classes
+        qkv_src = None
+        if (self.qkv0_table and self.tensor and (3 * D) % 4 == 0 and 3 * D <= 1024 and M >= 8 * (C + V + T) and
+                a.offsets[ename][0] == a.offsets[cname][0] + C * D):   # small batches: the GEMM is cheaper than three launches
+            qkv_src = (tokens, classes)
         xlo = None
-        if self._layer_p3_ok(D):                      # hi / lo planes of the embedded rows and of the weights
+        if self._layer_p3_ok(D) and qkv_src is None:  # hi / lo planes of the embedded rows (the only reader is that projection)
             xp = bf.get("enc.x0_p", (2, M, D), dev, torch.bfloat16)
             x16, xlo = xp[0], xp[1]
-        ops.embed_fwd(tokens, classes, None, self._W("encoder.encoder_embedding.weight"),
-                      self._W("encoder.class2hid.weight"), None, self.pe_enc, x, mask, B, T, D, 0, math.sqrt(float(D)), V,
-                      out16=x16, out16lo=xlo)
+        ops.embed_fwd(tokens, classes, None, self._W(ename), self._W(cname), None, self.pe_enc, x, mask, B, T, D, 0,
+                      math.sqrt(float(D)), V, out16=x16, out16lo=xlo)
         if xlo is not None:
             x16 = xp
-        return self._encode_layers(bf, x, x16, mask, B, T, p_drop)
+        return self._encode_layers(bf, x, x16, mask, B, T, p_drop, qkv_src=qkv_src)
 
-    def _encode_layers(self, bf, x, x16, mask, B, T, p_drop):
+    def _qkv0_from_tables(self, bf, qkv, qkv_src, prefix, B, T, D):
+        """qkv [B*T, 3D] of the first encoder layer = scale * (tab[C + token] + tab[class]) + postab[position]: two GEMMs over
+        C + V and T rows (compensated like the projection they replace) and one gather-add pass."""
+        cfg, dev, a = self.cfg, self.device, self.arena
+        C, V = cfg.num_classes, cfg.vocab
+        tokens, classes = qkv_src
+        wqkv = a.span(prefix + "self_attention.W_k.weight", prefix + "self_attention.W_v.weight")
+        bqkv = a.span(prefix + "self_attention.W_k.bias", prefix + "self_attention.W_v.bias")
+        tab = bf.get("enc.qkv0_tab", (C + V, 3 * D), dev)
+        postab = bf.get("enc.qkv0_postab", (T, 3 * D), dev)
+        src = a.span("encoder.class2hid.weight", "encoder.encoder_embedding.weight")       # [C + V, D], adjacent in the arena
+        self._dense_fwd(src, D, C + V, None, None, tab, 3 * D, 3 * D, D, w=wqkv, force_x3=True)
+        self._dense_fwd(self.pe_enc, D, T, None, None, postab, 3 * D, 3 * D, D, w=wqkv, b=bqkv, force_x3=True)
+        ops.rows_from_tables(tokens, classes, tab, postab, qkv, B, T, 3 * D, C, V, math.sqrt(float(D)))
+
+    def _encode_layers(self, bf, x, x16, mask, B, T, p_drop, qkv_src=None):
         """Transformer encoder layers + latent projection on an embedded input x [B*T, D] (transformer.py:268-273,
         model.py:97-103)."""
         cfg, dev = self.cfg, self.device
@@ -777,20 +813,23 @@ class VAEEngine:
         xs = [x]
         self._xs16 = [x16]
         for l in range(cfg.enc_layers):
+            qs = qkv_src if l == 0 else None
             if self._layer_p3_ok(D):
-                if x16 is None:                          # an input no kernel wrote as planes (the roll path's dense embedding)
+                if x16 is None and qs is None:           # an input no kernel wrote as planes (the roll path's dense embedding)
                     x16 = bf.get("enc.x0_p", (2, B * T, D), dev, torch.bfloat16)
                     ops.split_planes(x, x16[0], x16[1])
                 x, x16 = self._tf_layer_fwd_p3(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
-                                               cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
+                                               cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l),
+                                               qkv_src=qs)
                 self._xs16.append(x16)
             elif l16:
                 x, x16 = self._tf_layer_fwd16(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, x16, mask, B, T, D,
-                                              cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
+                                              cfg.enc_heads, p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l),
+                                              qkv_src=qs)
                 self._xs16.append(x16)
             else:
                 x = self._tf_layer_fwd(bf, "enc%d." % l, "encoder.encoder.layer%d." % l, x, mask, B, T, D, cfg.enc_heads,
-                                       p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l))
+                                       p_drop, l * SITE_STRIDE, False, sos_only=self._sos_only(l), qkv_src=qs)
             xs.append(x)
         lat = bf.get("lat", (B, 2 * Z), dev)
         # latent projection on the SOS position (model.py:97-100): row b of the compact top-layer output, else row b*T

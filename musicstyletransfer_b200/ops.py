@@ -274,6 +274,12 @@ def embed_bwd(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D, pr
              _i(D), _i(prefix), _f(scale), _i(vocab), _i(ncls), lib.stream_ptr())
 
 
+def rows_from_tables(tokens, classes, tab, postab, out, B, T, N, C, V, scale):
+    """out[b*T + t] = scale * (tab[C + tokens[b, t]] + tab[classes[b]]) + postab[t] (rows of N floats)."""
+    lib.call("msx_rows_from_tables", P(tokens), P(classes), P(tab), P(postab), P(out), _i(B), _i(T), _i(N), _i(C), _i(V),
+             _f(scale), lib.stream_ptr())
+
+
 def token_sort(tokens, V, perm, sorted_tok, workspace, M=None):
     """Counting sort of the row indices 0..M-1 by tokens[r] (int32 tensors; workspace int32 [3 V])."""
     lib.call("msx_token_sort", P(tokens), _ll(tokens.numel() if M is None else M), _i(V), P(perm), P(sorted_tok), P(workspace),
