@@ -37,6 +37,12 @@ int msx_device_sm_count(void);
  * the end of the captured step).  The gluon loop this replaces draws fresh masks per call (trainer.py:166-168). */
 int msx_set_step_counter(unsigned long long* dev_counter);
 int msx_step_counter_tick(unsigned long long* dev_counter, void* stream);
+/* Programmatic dependent launch of the library's kernels (default on; MSX_PDL=0 in the environment also turns it off):
+ * a kernel's grid is scheduled while its stream predecessor still runs and waits on the device for it to complete, in
+ * eager streams and captured graphs alike.  Results are identical either way; the gluon loop this replaces has no
+ * counterpart (one engine push per operator, trainer.py:155-179). */
+int msx_set_pdl(int on);
+int msx_get_pdl(void);
 
 /* Keep-mask of one dropout site exactly as the step's kernels draw it: out[e] = 1 when element e (row-major index into
  * the site's [rows, width] activation) is kept, for (seed [+ registered step counter], site, drop_p).  Sites of Transformer

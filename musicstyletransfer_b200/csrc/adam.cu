@@ -13,6 +13,7 @@
 namespace {
 
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr, float b1, float b2) {
+  pdl_entry();
   // state[0] = t (as float, exact up to 2^24 steps), state[1] = lr_t
   const float t = state[0] + 1.f;
   state[0] = t;
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
                                                    float* __restrict__ v, long long n4, long long n,
                                                    const float* __restrict__ state, float b1, float b2, float eps,
                                                    float wd, float rescale, float clip, int zero_grad) {
+  pdl_entry();
   const float lr_t = state[1];
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
 
 // shared with adam_nvlink.cu
 extern "C" void msx_adam_tick_launch(float* state, float lr, float b1, float b2, void* stream) {
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, b1, b2);
+  (void)msx_launch(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state, lr, b1, b2);
 }
 
 extern "C" int msx_adam_step(float* w, float* g, float* m, float* v, long long n, float* state, float lr, float beta1,
@@ -67,10 +69,10 @@ extern "C" int msx_adam_step(float* w, float* g, float* m, float* v, long long n
   MSX_REQUIRE((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "msx_adam_step: arenas must be 16-byte aligned");
   if (n == 0) return MSX_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
+  MSX_CUDA(msx_launch(adam_tick_kernel, dim3(1), dim3(1), 0, st, state, lr, beta1, beta2));
   const long long n4 = n / 4;
   const int grid = (int)min((long long)msx_num_sms() * 8, (n4 + 255) / 256 + 1);
-  adam_kernel<<<grid, 256, 0, st>>>(w, g, m, v, n4, n, state, beta1, beta2, eps, wd, rescale, clip, zero_grad);
+  MSX_CUDA(msx_launch(adam_kernel, dim3(grid), dim3(256), 0, st, w, g, m, v, n4, n, state, beta1, beta2, eps, wd, rescale, clip, zero_grad));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

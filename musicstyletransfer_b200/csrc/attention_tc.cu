@@ -83,6 +83,7 @@ template <int NCH, int G, bool STAGE, int kDh, bool X3, bool Q0 = false>
 __global__ void __launch_bounds__(128 * G, 1)
     attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmQ,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  pdl_entry();
   constexpr int TQ = NCH * 16;
   constexpr int kTmemStride = (TQ + 2 * DH + 31) / 32 * 32;  // per group: O even [0,32) | O odd [32,64) | S [64, 64+TQ)
   constexpr int kTmemCols = G * kTmemStride <= 128 ? 128 : G * kTmemStride <= 256 ? 256 : 512;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(128)
     attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK128, const __grid_constant__ CUtensorMap tmQk,
                        const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
                        const __grid_constant__ CUtensorMap tmQKVm, const AttnTcBwdParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int T = p.T, TQ = p.TQ, TK = p.TK;
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(256, 1)
                             const __grid_constant__ CUtensorMap tmDOk, const __grid_constant__ CUtensorMap tmDOm,
                             const __grid_constant__ CUtensorMap tmQKVm, const AttnTcBwdParams p, const int items,
                             const int group_bytes, const int smem_bytes) {
+  pdl_entry();
   constexpr int G = 2;
   constexpr int TQ = NCH * 16;
   constexpr int kTmemStride = 256;                         // dV | dK | dQ | S/P [TQ] | dP/dS [TQ]
@@ -934,16 +937,16 @@ int launch_fwd(const CUtensorMap& tk, const CUtensorMap& tq, const CUtensorMap& 
   const bool stage = !p.out_bf16 && p.dh == 32 && ((p.T + 31) / 32) * 4096 <= ((p.TQ + 31) / 32) * p.TK * 128;
   if (q0) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32, X3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false, 32, X3, true><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(msx_launch(attn_tc_fwd_kernel<NCH, G, false, 32, X3, true>, dim3(grid), dim3(128 * G), smem, st, tk, tq, tv, p));
   } else if (p.dh == 16) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false, 16, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(msx_launch(attn_tc_fwd_kernel<NCH, G, false, 16, X3>, dim3(grid), dim3(128 * G), smem, st, tk, tq, tv, p));
   } else if (stage) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, true, 32, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, true, 32, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(msx_launch(attn_tc_fwd_kernel<NCH, G, true, 32, X3>, dim3(grid), dim3(128 * G), smem, st, tk, tq, tv, p));
   } else {
     MSX_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH, G, false, 32, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<NCH, G, false, 32, X3><<<grid, 128 * G, smem, st>>>(tk, tq, tv, p);
+    MSX_CUDA(msx_launch(attn_tc_fwd_kernel<NCH, G, false, 32, X3>, dim3(grid), dim3(128 * G), smem, st, tk, tq, tv, p));
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
@@ -1082,19 +1085,19 @@ extern "C" int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, cons
   case NCH:                                                                                                            \
     if (q0_only && dh == 32 && stage) {                                                                                \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, true, 32, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(msx_launch(attn_tc_bwd_pipe_kernel<NCH, true, 32, true>, dim3(grid), dim3(256), smem, st, tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024)); \
     } else if (q0_only && dh == 32) {                                                                                  \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, false, 32, true><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(msx_launch(attn_tc_bwd_pipe_kernel<NCH, false, 32, true>, dim3(grid), dim3(256), smem, st, tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024)); \
     } else if (dh == 16) {                                                                                                    \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, false, 16><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(msx_launch(attn_tc_bwd_pipe_kernel<NCH, false, 16>, dim3(grid), dim3(256), smem, st, tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024)); \
     } else if (stage) {                                                                                                \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, true, 32><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(msx_launch(attn_tc_bwd_pipe_kernel<NCH, true, 32>, dim3(grid), dim3(256), smem, st, tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024)); \
     } else {                                                                                                           \
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_pipe_kernel<NCH, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attn_tc_bwd_pipe_kernel<NCH, false, 32><<<grid, 256, smem, st>>>(tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024); \
+      MSX_CUDA(msx_launch(attn_tc_bwd_pipe_kernel<NCH, false, 32>, dim3(grid), dim3(256), smem, st, tKk, tQk, tDOk, tDOm, tQKVm, p, items, group_bytes, (int)smem - 1024)); \
     }                                                                                                                  \
     break;
     switch (p.TQ / 16) {
@@ -1116,18 +1119,18 @@ extern "C" int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, cons
   if (96 + 2 * p.TQ <= 256) {
     if (dh == 16) {
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attn_tc_bwd_kernel<256, 16><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+      MSX_CUDA(msx_launch(attn_tc_bwd_kernel<256, 16>, dim3(B * H), dim3(128), smem, st, tK128, tQk, tDOk, tDOm, tQKVm, p));
     } else {
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attn_tc_bwd_kernel<256, 32><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+      MSX_CUDA(msx_launch(attn_tc_bwd_kernel<256, 32>, dim3(B * H), dim3(128), smem, st, tK128, tQk, tDOk, tDOm, tQKVm, p));
     }
   } else {
     if (dh == 16) {
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attn_tc_bwd_kernel<512, 16><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+      MSX_CUDA(msx_launch(attn_tc_bwd_kernel<512, 16>, dim3(B * H), dim3(128), smem, st, tK128, tQk, tDOk, tDOm, tQKVm, p));
     } else {
       MSX_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attn_tc_bwd_kernel<512, 32><<<B * H, 128, smem, st>>>(tK128, tQk, tDOk, tDOm, tQKVm, p);
+      MSX_CUDA(msx_launch(attn_tc_bwd_kernel<512, 32>, dim3(B * H), dim3(128), smem, st, tK128, tQk, tDOk, tDOm, tQKVm, p));
     }
   }
   MSX_LAUNCH_CHECK();

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(128, 1)
     attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
                         const AttnLongParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sQ = base;                          // NT K-major tiles: all queries of the (batch, head)
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(128, 1)
                         const __grid_constant__ CUtensorMap tmDOk /* K-major {32,128} over dctx */,
                         const __grid_constant__ CUtensorMap tmDOm /* MN-major {32,128} over dctx */,
                         const AttnLongParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sKk = base;                         // per key tile: K K-major, V K-major, K MN-major
@@ -466,10 +468,10 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (T <= 2 * kTile) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(2)));
-    attn_tcl_fwd_kernel<2><<<B * H, 128, fwd_smem(2), st>>>(tk, tm, p);
+    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<2>, dim3(B * H), dim3(128), fwd_smem(2), st, tk, tm, p));
   } else {
     MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(3)));
-    attn_tcl_fwd_kernel<3><<<B * H, 128, fwd_smem(3), st>>>(tk, tm, p);
+    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<3>, dim3(B * H), dim3(128), fwd_smem(3), st, tk, tm, p));
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
@@ -496,10 +498,10 @@ extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (T <= 2 * kTile) {
     MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    attn_tcl_bwd_kernel<2><<<B * H, 128, kBwdSmem, st>>>(tk, tm, tdk, tdm, p);
+    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<2>, dim3(B * H), dim3(128), kBwdSmem, st, tk, tm, tdk, tdm, p));
   } else {
     MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    attn_tcl_bwd_kernel<3><<<B * H, 128, kBwdSmem, st>>>(tk, tm, tdk, tdm, p);
+    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<3>, dim3(B * H), dim3(128), kBwdSmem, st, tk, tm, tdk, tdm, p));
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
                                                         unsigned short* __restrict__ out16lo,
                                                         float* __restrict__ mask, int B, int T, int D, int prefix,
                                                         float scale, int vocab, int vec) {
+  pdl_entry();
   const int TP = T + prefix;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ 
                                                         const float* __restrict__ dout, float* __restrict__ d_tok_emb,
                                                         float* __restrict__ d_cls_emb, float* __restrict__ d_prefix,
                                                         int B, int T, int D, int prefix, float scale, int vocab) {
+  pdl_entry();
   const int b = blockIdx.x;
   const int TP = T + prefix;
   const int c = d_cls_emb ? __ldg(classes + b) : 0;
@@ -129,6 +131,7 @@ constexpr int kSortThreads = 256, kSortWarps = 8, kSortSeg = 512, kSortMaxV = 51
 __global__ void __launch_bounds__(kSortThreads) embed_bwd_sorted_kernel(
     const int* __restrict__ tokens, const int* __restrict__ classes, const float* __restrict__ dout,
     float* __restrict__ d_tok_emb, float* __restrict__ d_cls_emb, long long rows, int T, int D, float scale, int vocab) {
+  pdl_entry();
   __shared__ int cnt[kSortMaxV];
   __shared__ int start[kSortMaxV];
   __shared__ int sorted[kSortSeg];
@@ -284,9 +287,9 @@ extern "C" int msx_embed_fwd_p(const int32_t* tokens, const int32_t* classes, co
   const int wpb = 8;
   const int vec = (D & 3) == 0 && (((uintptr_t)tok_emb | (uintptr_t)cls_emb | (uintptr_t)prefix_vec | (uintptr_t)pe | (uintptr_t)out |
                                     (uintptr_t)out_bf16 | (uintptr_t)out_bf16_lo) & 15) == 0;
-  embed_fwd_kernel<<<msx_ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+  MSX_CUDA(msx_launch(embed_fwd_kernel, dim3(msx_ceil_div(rows, wpb)), dim3(wpb * 32), 0, (cudaStream_t)stream, 
       tokens, classes, seq_lens, tok_emb, cls_emb, prefix_vec, pe, out, reinterpret_cast<unsigned short*>(out_bf16),
-      reinterpret_cast<unsigned short*>(out_bf16_lo), mask, B, T, D, prefix, scale, vocab, vec);
+      reinterpret_cast<unsigned short*>(out_bf16_lo), mask, B, T, D, prefix, scale, vocab, vec));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(256) rows_from_tables_kernel(const int* __rest
                                                                const float* __restrict__ tab, const float* __restrict__ postab,
                                                                float* __restrict__ out, int B, int T, int N, int C, int V,
                                                                float scale, int bchunks) {
+  pdl_entry();
   const int c = threadIdx.x * 4;
   const int t = blockIdx.x % T, chunk = blockIdx.x / T;
   const float4 p = __ldg(reinterpret_cast<const float4*>(postab + (size_t)t * N + c));
@@ -337,8 +341,8 @@ extern "C" int msx_rows_from_tables(const int32_t* tokens, const int32_t* classe
   // T x bchunks CTAs: about 8 resident CTAs per SM
   int bchunks = (msx_num_sms() * 8 + T - 1) / T;
   if (bchunks > (B + 3) / 4) bchunks = (B + 3) / 4;
-  rows_from_tables_kernel<<<T * bchunks, N / 4, 0, (cudaStream_t)stream>>>(tokens, classes, tab, postab, out, B, T, N, C, V, scale,
-                                                                          bchunks);
+  MSX_CUDA(msx_launch(rows_from_tables_kernel, dim3(T * bchunks), dim3(N / 4), 0, (cudaStream_t)stream, tokens, classes, tab, postab, out, B, T, N, C, V, scale,
+                                                                          bchunks));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -367,15 +371,15 @@ extern "C" int msx_embed_bwd_ex(const int32_t* tokens, const int32_t* classes, c
       ((((uintptr_t)dout) | ((uintptr_t)d_tok_emb) | ((uintptr_t)d_cls_emb)) & 15) == 0 &&
       (!d_cls_emb || (num_classes >= 1 && num_classes <= 2))) {
     const int grid = (int)((rows + kSortSeg - 1) / kSortSeg);
-    embed_bwd_sorted_kernel<<<grid, kSortThreads, 0, (cudaStream_t)stream>>>(tokens, classes, dout, d_tok_emb, d_cls_emb, rows,
-                                                                             T, D, scale, vocab);
+    MSX_CUDA(msx_launch(embed_bwd_sorted_kernel, dim3(grid), dim3(kSortThreads), 0, (cudaStream_t)stream, tokens, classes, dout, d_tok_emb, d_cls_emb, rows,
+                                                                             T, D, scale, vocab));
     MSX_LAUNCH_CHECK();
     return MSX_OK;
   }
   // (a variant that accumulated a 64-column slice of the table with shared-memory atomics was 6x SLOWER: float
   // atomicAdd on shared memory is a CAS loop and the synthetic 4/4 rows hit few distinct tokens)
-  embed_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D,
-                                                        prefix, scale, vocab);
+  MSX_CUDA(msx_launch(embed_bwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, tokens, classes, dout, d_tok_emb, d_cls_emb, d_prefix, B, T, D,
+                                                        prefix, scale, vocab));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -41,6 +41,7 @@ struct GemmParams {
 
 template <int TA, int TB>
 __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
+  pdl_entry();
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -236,10 +237,10 @@ extern "C" int msx_gemm_f32(const float* A, int lda, int transA, const float* B,
   dim3 grid(msx_ceil_div(N, BN), msx_ceil_div(M, BM), p.splitk);
   MSX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "msx_gemm_f32: grid too large (M=%d)", M);
   cudaStream_t st = (cudaStream_t)stream;
-  if (transA == 0 && transB == 1) sgemm_kernel<0, 1><<<grid, NT, 0, st>>>(p);
-  else if (transA == 0 && transB == 0) sgemm_kernel<0, 0><<<grid, NT, 0, st>>>(p);
-  else if (transA == 1 && transB == 0) sgemm_kernel<1, 0><<<grid, NT, 0, st>>>(p);
-  else sgemm_kernel<1, 1><<<grid, NT, 0, st>>>(p);
+  if (transA == 0 && transB == 1) MSX_CUDA(msx_launch(sgemm_kernel<0, 1>, dim3(grid), dim3(NT), 0, st, p));
+  else if (transA == 0 && transB == 0) MSX_CUDA(msx_launch(sgemm_kernel<0, 0>, dim3(grid), dim3(NT), 0, st, p));
+  else if (transA == 1 && transB == 0) MSX_CUDA(msx_launch(sgemm_kernel<1, 0>, dim3(grid), dim3(NT), 0, st, p));
+  else MSX_CUDA(msx_launch(sgemm_kernel<1, 1>, dim3(grid), dim3(NT), 0, st, p));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -249,6 +250,7 @@ extern "C" int msx_gemm_f32(const float* A, int lda, int transA, const float* B,
 namespace {
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, long long M, int N,
                                                      float* __restrict__ out) {
+  pdl_entry();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -272,7 +274,7 @@ extern "C" int msx_colsum(const float* X, int ld, long long M, int N, float* out
   const int gx = msx_ceil_div(N, 32);
   int gy = (int)min((long long)msx_ceil_div(msx_num_sms() * 8, gx), (M + 63) / 64);
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, out);
+  MSX_CUDA(msx_launch(colsum_kernel, dim3(dim3(gx, gy)), dim3(256), 0, (cudaStream_t)stream, X, ld, M, N, out));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -33,6 +33,7 @@ template <bool A_MN, bool B_MN, bool BF, int EW>
 __global__ void __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ P3Maps mx, const TcParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -202,6 +203,7 @@ template <int BN2, bool A_MN, bool B_MN, bool BF, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EW>::kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ P3Maps mx, const TcParams p) {
+  pdl_entry();
   using Cfg = PairCfg<BN2>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -374,7 +376,7 @@ int launch_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   MSX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int grid = items < msx_num_sms() ? items : msx_num_sms();
-  gemm_tc_kernel<A_MN, B_MN, BF, EW><<<grid, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, mx, p);
+  MSX_CUDA(msx_launch(gemm_tc_kernel<A_MN, B_MN, BF, EW>, dim3(grid), dim3(EpiCfg<EW>::kThreads), smem, st, ta, tb, tc, mx, p));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -396,7 +398,7 @@ int launch_pair_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW><<<2 * pairs, EpiCfg<EW>::kThreads, smem, st>>>(ta, tb, tc, mx, p);   // static cluster dims (2,1,1)
+  MSX_CUDA(msx_launch(gemm_tc2_kernel<BN2, A_MN, B_MN, BF, EW>, dim3(2 * pairs), dim3(EpiCfg<EW>::kThreads), smem, st, ta, tb, tc, mx, p));   // static cluster dims (2,1,1)
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -660,6 +662,7 @@ extern "C" int msx_gemm_tc_p3(const void* A_hi, const void* A_lo, int lda, const
 namespace {
 __global__ void __launch_bounds__(256) split_planes_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
                                                            uint2* __restrict__ lo, long long n4) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(src + i);
     uint2 h, l;
@@ -679,8 +682,8 @@ extern "C" int msx_split_planes(const float* src, void* hi, void* lo, long long 
   if (n == 0) return MSX_OK;
   const long long n4 = n / 4;
   const long long want = (n4 + 255) / 256, cap = (long long)msx_num_sms() * 8;
-  split_planes_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), n4);
+  MSX_CUDA(msx_launch(split_planes_kernel, dim3((int)(want < cap ? want : cap)), dim3(256), 0, (cudaStream_t)stream, 
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), n4));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

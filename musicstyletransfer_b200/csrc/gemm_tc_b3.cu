@@ -79,6 +79,7 @@ template <int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
     gemm_tc2b3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  pdl_entry();
   using Cfg = B3Cfg<BN2>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stages = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -274,7 +275,7 @@ int launch_b3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2b3_kernel<BN2><<<2 * pairs, kThreadsB, smem, st>>>(ta, tb, tc, p);
+  MSX_CUDA(msx_launch(gemm_tc2b3_kernel<BN2>, dim3(2 * pairs), dim3(kThreadsB), smem, st, ta, tb, tc, p));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

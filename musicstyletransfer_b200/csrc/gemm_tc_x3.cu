@@ -67,6 +67,7 @@ template <int BN2, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsX3, 1)
     gemm_tc2x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  pdl_entry();
   using Cfg = X3Cfg<BN2>;
   using Op = OpCfg<false>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -273,7 +274,7 @@ int launch_x3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   const int items = p.m_tiles * p.n_tiles * p.splitk;
   const int max_pairs = msx_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  gemm_tc2x3_kernel<BN2, A_MN, B_MN><<<2 * pairs, kThreadsX3, smem, st>>>(ta, tb, tc, p);
+  MSX_CUDA(msx_launch(gemm_tc2x3_kernel<BN2, A_MN, B_MN>, dim3(2 * pairs), dim3(kThreadsX3), smem, st, ta, tb, tc, p));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kWarps * 32) add_ln_fwd_kernel(const float* __
                                                                  long long M, int D, float eps, float p, float inv_keep,
                                                                  unsigned long long seed, const unsigned long long* seed_ctr,
                                                                  unsigned site) {
+  pdl_entry();
   seed = msx_eff_seed(seed, seed_ctr);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nper = D / (32 * VEC);
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kWarps * 32, (kAsync ? 2 : (kPer <= 2 ? 3 : 1)
     float* __restrict__ dres, float* __restrict__ dy, unsigned short* __restrict__ dy16, float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ dybias, long long M, int D, float p, float inv_keep, unsigned long long seed,
     const unsigned long long* seed_ctr, unsigned site, int accumulate_dres, int fuse_xy) {
+  pdl_entry();
   seed = msx_eff_seed(seed, seed_ctr);
   __shared__ float red[kWarps][32 * VEC + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -338,7 +340,7 @@ extern "C" int msx_add_ln_fwd_p(const float* x, const void* y_any, int y_bf16, c
   MSX_REQUIRE(!(out_bf16 || y_bf16) || vec, "msx_add_ln_fwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* out16 = reinterpret_cast<unsigned short*>(out_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V, P) add_ln_fwd_kernel<V, P><<<ln_wave_grid(add_ln_fwd_kernel<V, P>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, beta, out, out16, out16lo, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site)
+#define LN_FWD(V, P) MSX_CUDA(msx_launch(add_ln_fwd_kernel<V, P>, dim3(ln_wave_grid(add_ln_fwd_kernel<V, P>, 0, M)), dim3(kWarps * 32), 0, st, x, y, y_bf16, gamma, beta, out, out16, out16lo, mean, rstd, M, D, eps, drop_p, inv_keep, seed, msx_step_counter(), site))
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_fwd: D too large");
     const int nper = D / 128;
@@ -380,13 +382,13 @@ extern "C" int msx_add_ln_bwd_ex(const float* x, const void* y_any, int y_bf16, 
   MSX_REQUIRE(!(dy_bf16 || y_bf16) || vec, "msx_add_ln_bwd: bf16 tensors need D %% 128 == 0 and 16-byte aligned tensors");
   unsigned short* dy16 = reinterpret_cast<unsigned short*>(dy_bf16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(V, P) add_ln_bwd_kernel<V, P, false><<<ln_wave_grid(add_ln_bwd_kernel<V, P, false>, 0, M), kWarps * 32, 0, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy)
+#define LN_BWD(V, P) MSX_CUDA(msx_launch(add_ln_bwd_kernel<V, P, false>, dim3(ln_wave_grid(add_ln_bwd_kernel<V, P, false>, 0, M)), dim3(kWarps * 32), 0, st, x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16, dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy))
 #define LN_BWD_ASYNC(P)                                                                                                   \
   do {                                                                                                                    \
     const int dyn = kWarps * kLnStages * 3 * P * 128 * 4;                                                                 \
     MSX_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<4, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));      \
-    add_ln_bwd_kernel<4, P, true><<<ln_wave_grid(add_ln_bwd_kernel<4, P, true>, dyn, M), kWarps * 32, dyn, st>>>(x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16,  \
-        dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy);         \
+    MSX_CUDA(msx_launch(add_ln_bwd_kernel<4, P, true>, dim3(ln_wave_grid(add_ln_bwd_kernel<4, P, true>, dyn, M)), dim3(kWarps * 32), dyn, st, x, y, y_bf16, gamma, mean, rstd, dout, dres, dy, dy16,  \
+        dgamma, dbeta, dybias, M, D, drop_p, inv_keep, seed, msx_step_counter(), site, accumulate_dres, fuse_xy));         \
   } while (0)
   if (vec) {
     MSX_REQUIRE(D <= 128 * kMaxPer, "msx_add_ln_bwd: D too large");

@@ -16,6 +16,7 @@ namespace {
 // lat [B, 2Z] = [means | stds];  z = m + eps * s;  kl_b = sum 0.5 (s^2 + m^2 - 1 - log(s^2))
 __global__ void __launch_bounds__(128) reparam_kl_fwd_kernel(const float* __restrict__ lat, const float* __restrict__ eps,
                                                              float* __restrict__ z, float* __restrict__ kl, int Z) {
+  pdl_entry();
   const int b = blockIdx.x;
   float acc = 0.f;
   for (int i = threadIdx.x; i < Z; i += blockDim.x) {
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(128) reparam_kl_fwd_kernel(const float* __rest
 __global__ void reparam_kl_bwd_kernel(const float* __restrict__ lat, const float* __restrict__ eps,
                                       const float* __restrict__ dz, const float* __restrict__ gkl, float kl_weight,
                                       float* __restrict__ dlat, int B, int Z) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * Z) return;
   const int b = (int)(i / Z), j = (int)(i % Z);
@@ -50,6 +52,7 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ lat, const float
 
 __global__ void normal_fill_kernel(float* __restrict__ out, long long n, unsigned long long seed,
                                    const unsigned long long* seed_ctr, unsigned long long offset) {
+  pdl_entry();
   seed = msx_eff_seed(seed, seed_ctr);
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
                                                      const int* __restrict__ labels, float* __restrict__ ce,
                                                      float* __restrict__ lse_out, float* __restrict__ metrics, int rows,
                                                      int T, int V, int top_k, float inv_denom) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
   for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(256) ce_fwd_big_kernel(const float* __restrict
                                                          const int* __restrict__ labels, float* __restrict__ ce,
                                                          float* __restrict__ lse_out, float* __restrict__ metrics, int rows,
                                                          int T, int V, int top_k, float inv_denom) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
     const float* x = logits + (size_t)row * ld;
@@ -190,6 +195,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
                                                      const float* __restrict__ lse, const float* __restrict__ gout,
                                                      int rows, int T, int V, float inv_denom, float* __restrict__ dbias) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float bs[kCeMaxPerLane];
 #pragma unroll
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(float* __restrict__ log
                                                          float* __restrict__ ce, float* __restrict__ lse_out,
                                                          float* __restrict__ metrics, int rows, int T, int V, int top_k,
                                                          float inv_denom, float* __restrict__ dbias) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float m_nll = 0.f, m_tok = 0.f, m_hit = 0.f, m_topk = 0.f;
   float bs[kCeMaxPerLane];
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(float* __restrict__ log
 __global__ void __launch_bounds__(256) ce_bwd_big_kernel(float* __restrict__ logits, int ld, const int* __restrict__ labels,
                                                          const float* __restrict__ lse, const float* __restrict__ gout,
                                                          int rows, int T, int V, float inv_denom) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
     float* x = logits + (size_t)row * ld;
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(256) ce_bwd_big_kernel(float* __restrict__ log
 // probs = softmax(logits) (API parity with Model.hybrid_forward's first return value)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ logits, int ld,
                                                            float* __restrict__ probs, long long rows, int V) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 __global__ void __launch_bounds__(128) ce_from_probs_kernel(const float* __restrict__ probs,
                                                             const int* __restrict__ labels, float* __restrict__ ce,
                                                             int T, int V) {
+  pdl_entry();
   const int b = blockIdx.x;
   float acc = 0.f;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -394,6 +404,7 @@ __device__ __forceinline__ float bce_elem(float x, float y, const BceCfg& c, flo
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ label,
                                                   float* __restrict__ out, const float* __restrict__ gout,
                                                   float* __restrict__ dpred, int n, BceCfg cfg) {
+  pdl_entry();
   const int b = blockIdx.x;
   const float* x = pred + (size_t)b * n;
   const uint8_t* y = label + (size_t)b * n;
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ pred
 // running sums of the step metrics (trainer.py:107-120 CustomMetric means): sums += {sum kl, sum (ce + w kl), B}
 __global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict__ ce, const float* __restrict__ kl,
                                                         float kl_weight, float* __restrict__ sums, int B) {
+  pdl_entry();
   __shared__ float red[2][8];
   float a = 0.f, t = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -460,7 +472,7 @@ extern "C" int msx_loss_sums(const float* ce, const float* kl, float kl_weight, 
   MSX_REQUIRE(B >= 0, "msx_loss_sums: B < 0");
   if (B == 0) return MSX_OK;
   MSX_REQUIRE(ce && kl && sums, "msx_loss_sums: null pointer");
-  loss_sums_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ce, kl, kl_weight, sums, B);
+  MSX_CUDA(msx_launch(loss_sums_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, ce, kl, kl_weight, sums, B));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -468,7 +480,7 @@ extern "C" int msx_loss_sums(const float* ce, const float* kl, float kl_weight, 
 extern "C" int msx_reparam_kl_fwd(const float* lat, const float* eps, float* z, float* kl, int B, int Z, void* stream) {
   MSX_REQUIRE(lat && eps && z && kl, "msx_reparam_kl_fwd: null pointer");
   if (B == 0) return MSX_OK;
-  reparam_kl_fwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(lat, eps, z, kl, Z);
+  MSX_CUDA(msx_launch(reparam_kl_fwd_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, lat, eps, z, kl, Z));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -478,7 +490,7 @@ extern "C" int msx_reparam_kl_bwd(const float* lat, const float* eps, const floa
   MSX_REQUIRE(lat && eps && dlat, "msx_reparam_kl_bwd: null pointer");
   if (B == 0) return MSX_OK;
   const long long n = (long long)B * Z;
-  reparam_kl_bwd_kernel<<<msx_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(lat, eps, dz, gkl, kl_weight, dlat, B, Z);
+  MSX_CUDA(msx_launch(reparam_kl_bwd_kernel, dim3(msx_ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, lat, eps, dz, gkl, kl_weight, dlat, B, Z));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -487,7 +499,7 @@ extern "C" int msx_normal_fill(float* out, long long n, unsigned long long seed,
                                void* stream) {
   MSX_REQUIRE(out || n == 0, "msx_normal_fill: null pointer");
   if (n == 0) return MSX_OK;
-  normal_fill_kernel<<<msx_ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, msx_step_counter(), offset);
+  MSX_CUDA(msx_launch(normal_fill_kernel, dim3(msx_ceil_div((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, out, n, seed, msx_step_counter(), offset));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -505,11 +517,11 @@ extern "C" int msx_ce_fwd(const float* logits, int ld, const int32_t* labels, fl
   const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
   const bool vec4 = (ld & 3) == 0 && ((uintptr_t)logits & 15) == 0;
   if (V > 32 * kCeMaxPerLane)
-    ce_fwd_big_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
+    MSX_CUDA(msx_launch(ce_fwd_big_kernel, dim3(grid), dim3(256), 0, st, logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom));
   else if (vec4)
-    ce_fwd_kernel<true><<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
+    MSX_CUDA(msx_launch(ce_fwd_kernel<true>, dim3(grid), dim3(256), 0, st, logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom));
   else
-    ce_fwd_kernel<false><<<grid, 256, 0, st>>>(logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom);
+    MSX_CUDA(msx_launch(ce_fwd_kernel<false>, dim3(grid), dim3(256), 0, st, logits, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -525,11 +537,11 @@ extern "C" int msx_ce_bwd(float* logits_inout, int ld, const int32_t* labels, co
   const int grid = min(msx_num_sms() * 8, (rows + 7) / 8);
   const bool vec4 = (ld & 3) == 0 && ((uintptr_t)logits_inout & 15) == 0;
   if (V > 32 * kCeMaxPerLane)
-    ce_bwd_big_kernel<<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom);
+    MSX_CUDA(msx_launch(ce_bwd_big_kernel, dim3(grid), dim3(256), 0, st, logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom));
   else if (vec4)
-    ce_bwd_kernel<true><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
+    MSX_CUDA(msx_launch(ce_bwd_kernel<true>, dim3(grid), dim3(256), 0, st, logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias));
   else
-    ce_bwd_kernel<false><<<grid, 256, 0, st>>>(logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias);
+    MSX_CUDA(msx_launch(ce_bwd_kernel<false>, dim3(grid), dim3(256), 0, st, logits_inout, ld, labels, lse, gout, rows, T, V, 1.f / denom, dbias));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -554,7 +566,7 @@ extern "C" int msx_ce_fwd_bwd(float* logits_inout, int ld, const int32_t* labels
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ce_fwd_bwd_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
   const int grid = min(msx_num_sms() * per_sm, (rows + 7) / 8);
-  ce_fwd_bwd_kernel<<<grid, 256, 0, st>>>(logits_inout, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom, dbias);
+  MSX_CUDA(msx_launch(ce_fwd_bwd_kernel, dim3(grid), dim3(256), 0, st, logits_inout, ld, labels, ce, lse, metrics, rows, T, V, top_k, 1.f / denom, dbias));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -562,7 +574,7 @@ extern "C" int msx_ce_fwd_bwd(float* logits_inout, int ld, const int32_t* labels
 extern "C" int msx_softmax_rows(const float* logits, int ld, float* probs, long long rows, int V, void* stream) {
   MSX_REQUIRE(logits && probs, "msx_softmax_rows: null pointer");
   if (rows == 0) return MSX_OK;
-  softmax_rows_kernel<<<msx_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, probs, rows, V);
+  MSX_CUDA(msx_launch(softmax_rows_kernel, dim3(msx_ceil_div(rows, 8)), dim3(256), 0, (cudaStream_t)stream, logits, ld, probs, rows, V));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -571,7 +583,7 @@ extern "C" int msx_ce_from_probs(const float* probs, const int32_t* labels, floa
                                  void* stream) {
   MSX_REQUIRE(probs && labels && ce, "msx_ce_from_probs: null pointer");
   if (B == 0) return MSX_OK;
-  ce_from_probs_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(probs, labels, ce, T, V);
+  MSX_CUDA(msx_launch(ce_from_probs_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, probs, labels, ce, T, V));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -581,7 +593,7 @@ extern "C" int msx_bce(const float* pred, const uint8_t* label, float* out, cons
   MSX_REQUIRE(pred && label && (out || dpred), "msx_bce: null pointer");
   if (B == 0) return MSX_OK;
   BceCfg cfg{from_sigmoid, label_smoothing, downweight};
-  bce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pred, label, out, gout, dpred, n_per_sample, cfg);
+  MSX_CUDA(msx_launch(bce_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, pred, label, out, gout, dpred, n_per_sample, cfg));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

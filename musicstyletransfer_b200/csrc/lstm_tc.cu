@@ -126,6 +126,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                        const float* __restrict__ w_h2h, const float* __restrict__ b_h2h,
                        const float* __restrict__ h0, const float* __restrict__ c0, int ld0, float* __restrict__ hs,
                        float* __restrict__ hprev, float* __restrict__ cs, int B, int T) {
+  pdl_entry();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -318,6 +319,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_tc_bwd_kernel(float* __restrict__ gates, const float* __restrict__ w_h2h, const float* __restrict__ cs,
                        const float* __restrict__ c0, int ld0, const float* __restrict__ dhs, float* __restrict__ dh0,
                        float* __restrict__ dc0, float* __restrict__ db_i2h, float* __restrict__ db_h2h, int B, int T) {
+  pdl_entry();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -552,14 +554,14 @@ extern "C" int msx_lstm_tc_fwd_tab(float* gx_inout, const int32_t* tokens, const
   if ((B + RB - 1) / RB <= resident) {
     const int clusters = (B + RB - 1) / RB;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    lstm_tc_fwd_kernel<1><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, tokens, table, w_h2h, b_h2h,
-                                                                                            h0, c0, ld0, hs, hprev, cs, B, T);
+    MSX_CUDA(msx_launch(lstm_tc_fwd_kernel<1>, dim3(clusters * 2), dim3(kThreads), sizeof(FwdSmem), (cudaStream_t)stream, gx_inout, tokens, table, w_h2h, b_h2h,
+                                                                                            h0, c0, ld0, hs, hprev, cs, B, T));
   } else {
     const int blocks = (B + R - 1) / R;
     const int clusters = blocks < resident ? blocks : resident;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    lstm_tc_fwd_kernel<2><<<clusters * 2, kThreads, sizeof(FwdSmem), (cudaStream_t)stream>>>(gx_inout, tokens, table, w_h2h, b_h2h,
-                                                                                            h0, c0, ld0, hs, hprev, cs, B, T);
+    MSX_CUDA(msx_launch(lstm_tc_fwd_kernel<2>, dim3(clusters * 2), dim3(kThreads), sizeof(FwdSmem), (cudaStream_t)stream, gx_inout, tokens, table, w_h2h, b_h2h,
+                                                                                            h0, c0, ld0, hs, hprev, cs, B, T));
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;
@@ -575,13 +577,13 @@ extern "C" int msx_lstm_tc_bwd(float* gates_inout, const float* w_h2h, const flo
   if ((B + 15) / 16 <= msx_num_sms() / 2) {                 // small batches: 16-row clusters, all resident at once
     const int clusters = (B + 15) / 16;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    lstm_tc_bwd_kernel<1><<<clusters * 2, kThreads, sizeof(BwdSmem), (cudaStream_t)stream>>>(gates_inout, w_h2h, cs, c0, ld0, dhs,
-                                                                                            dh0, dc0, db_i2h, db_h2h, B, T);
+    MSX_CUDA(msx_launch(lstm_tc_bwd_kernel<1>, dim3(clusters * 2), dim3(kThreads), sizeof(BwdSmem), (cudaStream_t)stream, gates_inout, w_h2h, cs, c0, ld0, dhs,
+                                                                                            dh0, dc0, db_i2h, db_h2h, B, T));
   } else {
     const int clusters = (B + R - 1) / R;
     MSX_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    lstm_tc_bwd_kernel<2><<<clusters * 2, kThreads, sizeof(BwdSmem), (cudaStream_t)stream>>>(gates_inout, w_h2h, cs, c0, ld0, dhs,
-                                                                                            dh0, dc0, db_i2h, db_h2h, B, T);
+    MSX_CUDA(msx_launch(lstm_tc_bwd_kernel<2>, dim3(clusters * 2), dim3(kThreads), sizeof(BwdSmem), (cudaStream_t)stream, gates_inout, w_h2h, cs, c0, ld0, dhs,
+                                                                                            dh0, dc0, db_i2h, db_h2h, B, T));
   }
   MSX_LAUNCH_CHECK();
   return MSX_OK;

@@ -47,8 +47,39 @@ const unsigned long long* msx_step_counter();
 
 static inline int msx_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (msx_set_pdl / MSX_PDL, default on).  A kernel that calls pdl_entry() as its first
+// statement may be launched through msx_launch(): its grid is then scheduled while the previous kernel of the stream is
+// still running (CTA launch, parameter and constant loads overlap the predecessor's tail) and blocks in
+// griddepcontrol.wait until every prerequisite grid has completed and flushed, so the stream's memory ordering is
+// unchanged.  A step is a chain of 60-75 dependent launches; inside a CUDA graph the hand-over between two kernels
+// otherwise costs 2-3 us each.  Kernels launched with <<< >>> keep the full serialisation (griddepcontrol is a no-op there).
+int msx_pdl_enabled();
+
 #ifdef __CUDACC__
 #define MSX_FULL 0xffffffffu
+
+// First statement of every kernel launched through msx_launch(): let the next kernel of the stream be scheduled, then wait
+// for the previous one(s).  Nothing before the wait may touch global memory or allocate tensor memory (a dependent CTA that
+// held TMEM columns while a predecessor CTA on the same SM still waits for its own would deadlock).
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t msx_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = msx_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -1,5 +1,6 @@
 // libmsx.so core: version, thread-local error string, device properties cache.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "msx_common.cuh"
@@ -27,6 +28,21 @@ int msx_num_sms() {
 
 extern "C" int msx_version(void) { return 100; }  // 0.1.0
 
+// ---- programmatic dependent launch switch (see msx_common.cuh): MSX_PDL=0 in the environment or msx_set_pdl(0) turn it off
+static int g_pdl = -1;
+int msx_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MSX_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+extern "C" int msx_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return MSX_OK;
+}
+extern "C" int msx_get_pdl(void) { return msx_pdl_enabled(); }
+
 extern "C" const char* msx_last_error(void) { return g_last_error; }
 
 extern "C" int msx_device_sm_count(void) { return msx_num_sms(); }
@@ -40,11 +56,12 @@ extern "C" int msx_set_step_counter(unsigned long long* dev_counter) {
   return MSX_OK;
 }
 
-static __global__ void step_counter_tick_kernel(unsigned long long* c) { *c += 1ull; }
+static __global__ void step_counter_tick_kernel(unsigned long long* c) {
+  pdl_entry(); *c += 1ull; }
 
 extern "C" int msx_step_counter_tick(unsigned long long* dev_counter, void* stream) {
   MSX_REQUIRE(dev_counter, "msx_step_counter_tick: null pointer");
-  step_counter_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_counter);
+  MSX_CUDA(msx_launch(step_counter_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, dev_counter));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -52,6 +69,7 @@ extern "C" int msx_step_counter_tick(unsigned long long* dev_counter, void* stre
 // ---- fp32 -> bf16 cast (operands of the bf16 GEMM variant)
 static __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, unsigned* __restrict__ dst,
                                                                     long long n) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -80,7 +98,7 @@ extern "C" int msx_cast_f32_bf16(const float* src, void* dst, long long n, void*
   MSX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "msx_cast_f32_bf16: pointers must be 16-byte aligned");
   const long long want = (n + 8 * 256 - 1) / (8 * 256);
   const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
-  cast_f32_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<unsigned*>(dst), n);
+  MSX_CUDA(msx_launch(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, reinterpret_cast<unsigned*>(dst), n));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -90,6 +108,7 @@ extern "C" int msx_cast_f32_bf16(const float* src, void* dst, long long n, void*
 static __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ out, long long n, float p,
                                                                    unsigned long long seed, const unsigned long long* ctr,
                                                                    unsigned site) {
+  pdl_entry();
   const unsigned long long eff = msx_eff_seed(seed, ctr);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
@@ -107,7 +126,7 @@ extern "C" int msx_dropout_mask(uint8_t* out, long long n, float drop_p, unsigne
   MSX_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "msx_dropout_mask: dropout probability must be in [0,1)");
   const long long want = (n / 4 + 256) / 256;
   const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
-  dropout_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, seed, msx_step_counter(), site);
+  MSX_CUDA(msx_launch(dropout_mask_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, out, n, drop_p, seed, msx_step_counter(), site));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

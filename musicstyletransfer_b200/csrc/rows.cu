@@ -17,6 +17,7 @@ namespace {
 template <bool ADD>
 __global__ void __launch_bounds__(256) rows_strided_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out,
                                                            long long ld_out, int rows, int width4) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * width4) return;
   const long long r = i / width4;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(kPlanThreads) rows_plan_kernel(const int* __re
                                                                 int n_tracks, int n_classes, int L, int* __restrict__ row_start,
                                                                 int* __restrict__ dup_row, int* __restrict__ dup_src,
                                                                 int* __restrict__ len_present) {
+  pdl_entry();
   __shared__ int scan[kPlanThreads];
   __shared__ int carry;
   const int tid = threadIdx.x;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(128) rows_build_kernel(const int* __restrict__
                                                          const int* __restrict__ len_present, int* __restrict__ tok,
                                                          int* __restrict__ lab, int* __restrict__ classes,
                                                          int* __restrict__ seq_lens) {
+  pdl_entry();
   const int b = blockIdx.x;
   if (b < n_tracks) {
     const int n = n_tokens[b];
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(128) rows_gather_kernel(const int* __restrict_
                                                           const int* __restrict__ index, int ld, int T_out,
                                                           int* __restrict__ btok, int* __restrict__ blab, int* __restrict__ bcls,
                                                           int* __restrict__ blen) {
+  pdl_entry();
   const int b = blockIdx.x;
   const long long r = index[b];
   for (int j = threadIdx.x; j < T_out; j += blockDim.x) {
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(128) rows_gather_kernel(const int* __restrict_
 // model.py:148-153); the backward applies the same mask (same seed / site) to the gradient.  In place when out == x.
 __global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* out, long long n4, float p, float inv_keep,
                                                       unsigned long long seed, const unsigned long long* ctr, unsigned site) {
+  pdl_entry();
   const unsigned long long eff = msx_eff_seed(seed, ctr);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* out
 // labels of the Transformer decoder: its rows carry the latent prefix position in front (model.py:244-253 drops it again
 // after the layers), which never has a target: out[b, 0] = PAD, out[b, 1 + t] = labels[b, t]
 __global__ void __launch_bounds__(256) prefix_labels_kernel(const int* __restrict__ labels, int* __restrict__ out, int B, int T) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * (T + 1)) return;
   const int b = (int)(i / (T + 1)), t = (int)(i % (T + 1));
@@ -189,7 +195,7 @@ extern "C" int msx_prefix_labels(const int32_t* labels, int32_t* out, int B, int
   MSX_REQUIRE(B >= 0 && T >= 1, "msx_prefix_labels: bad sizes");
   if (B == 0) return MSX_OK;
   MSX_REQUIRE(labels && out, "msx_prefix_labels: null pointer");
-  prefix_labels_kernel<<<msx_ceil_div((long long)B * (T + 1), 256), 256, 0, (cudaStream_t)stream>>>(labels, out, B, T);
+  MSX_CUDA(msx_launch(prefix_labels_kernel, dim3(msx_ceil_div((long long)B * (T + 1), 256)), dim3(256), 0, (cudaStream_t)stream, labels, out, B, T));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -203,7 +209,7 @@ extern "C" int msx_dropout(const float* x, float* out, long long n, float drop_p
   const long long n4 = n / 4;
   const long long want = (n4 + 255) / 256;
   const int grid = (int)(want < (long long)msx_num_sms() * 8 ? want : (long long)msx_num_sms() * 8);
-  dropout_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, n4, drop_p, 1.f / (1.f - drop_p), seed, msx_step_counter(), site);
+  MSX_CUDA(msx_launch(dropout_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, out, n4, drop_p, 1.f / (1.f - drop_p), seed, msx_step_counter(), site));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -212,8 +218,8 @@ extern "C" int msx_rows_plan(const int32_t* n_tokens, const int32_t* class_start
                              int32_t* row_start, int32_t* dup_row, int32_t* dup_src, int32_t* len_present, void* stream) {
   MSX_REQUIRE(n_tracks >= 0 && n_classes >= 1 && max_seq_len >= 1, "msx_rows_plan: bad sizes");
   MSX_REQUIRE(n_tokens && class_start && row_start && dup_row && dup_src && len_present, "msx_rows_plan: null pointer");
-  rows_plan_kernel<<<1, kPlanThreads, 0, (cudaStream_t)stream>>>(n_tokens, class_start, n_tracks, n_classes, max_seq_len,
-                                                                 row_start, dup_row, dup_src, len_present);
+  MSX_CUDA(msx_launch(rows_plan_kernel, dim3(1), dim3(kPlanThreads), 0, (cudaStream_t)stream, n_tokens, class_start, n_tracks, n_classes, max_seq_len,
+                                                                 row_start, dup_row, dup_src, len_present));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -226,9 +232,9 @@ extern "C" int msx_rows_build(const int32_t* ids, long long ld, int col0, const 
   if (n_tracks == 0) return MSX_OK;
   MSX_REQUIRE(ids && n_tokens && track_class && row_start && dup_row && dup_src && len_present && tokens && labels && classes &&
                   seq_lens, "msx_rows_build: null pointer");
-  rows_build_kernel<<<n_tracks + n_classes, 128, 0, (cudaStream_t)stream>>>(ids, ld, col0, n_tokens, track_class, n_tracks,
+  MSX_CUDA(msx_launch(rows_build_kernel, dim3(n_tracks + n_classes), dim3(128), 0, (cudaStream_t)stream, ids, ld, col0, n_tokens, track_class, n_tracks,
                                                                             n_classes, max_seq_len, row_start, dup_row, dup_src,
-                                                                            len_present, tokens, labels, classes, seq_lens);
+                                                                            len_present, tokens, labels, classes, seq_lens));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -240,8 +246,8 @@ extern "C" int msx_rows_gather_batch(const int32_t* tokens, const int32_t* label
   if (batch == 0) return MSX_OK;
   MSX_REQUIRE(tokens && labels && classes && seq_lens && index && b_tokens && b_labels && b_classes && b_seq_lens,
               "msx_rows_gather_batch: null pointer");
-  rows_gather_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(tokens, labels, classes, seq_lens, index, ld, t_out, b_tokens,
-                                                              b_labels, b_classes, b_seq_lens);
+  MSX_CUDA(msx_launch(rows_gather_kernel, dim3(batch), dim3(128), 0, (cudaStream_t)stream, tokens, labels, classes, seq_lens, index, ld, t_out, b_tokens,
+                                                              b_labels, b_classes, b_seq_lens));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -255,9 +261,9 @@ extern "C" int msx_rows_strided(const float* in, long long ld_in, float* out, lo
               "msx_rows_strided: width and leading dimensions must be multiples of 4, pointers 16-byte aligned");
   const long long n = (long long)rows * (width / 4);
   if (add)
-    rows_strided_kernel<true><<<msx_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, width / 4);
+    MSX_CUDA(msx_launch(rows_strided_kernel<true>, dim3(msx_ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, out, ld_out, rows, width / 4));
   else
-    rows_strided_kernel<false><<<msx_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, width / 4);
+    MSX_CUDA(msx_launch(rows_strided_kernel<false>, dim3(msx_ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, out, ld_out, rows, width / 4));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -24,6 +24,7 @@ constexpr int kMaxV = 4096;
 __device__ __forceinline__ int clamp_tok(int t, int V) { return min(max(t, 0), V - 1); }
 
 __global__ void __launch_bounds__(256) tok_hist_kernel(const int* __restrict__ tokens, long long M, int V, int* __restrict__ counts) {
+  pdl_entry();
   extern __shared__ int bins[];
   for (int i = threadIdx.x; i < V; i += blockDim.x) bins[i] = 0;
   __syncthreads();
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) tok_hist_kernel(const int* __restrict__ t
 // counts[V] -> offsets[V] (exclusive), cursors[V] = offsets; one block
 __global__ void __launch_bounds__(1024) tok_scan_kernel(const int* __restrict__ counts, int V, int* __restrict__ offsets,
                                                         int* __restrict__ cursors) {
+  pdl_entry();
   __shared__ int part[1024];
   const int per = (V + blockDim.x - 1) / blockDim.x;
   const int lo = threadIdx.x * per, hi = min(V, lo + per);
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(1024) tok_scan_kernel(const int* __restrict__ 
 constexpr int kScatterChunk = 2048;
 __global__ void __launch_bounds__(256) tok_scatter_kernel(const int* __restrict__ tokens, long long M, int V, int* __restrict__ cursors,
                                                           int* __restrict__ perm, int* __restrict__ sorted_tok) {
+  pdl_entry();
   extern __shared__ int sm[];                               // bins[V] | base[V]
   int* bins = sm;
   int* base = sm + V;
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(256) tok_scatter_kernel(const int* __restrict_
 __global__ void __launch_bounds__(256) rows_sum_by_token_kernel(const float* __restrict__ X, int ld, int D, const int* __restrict__ perm,
                                                                 const int* __restrict__ sorted_tok, long long M, float scale,
                                                                 float* __restrict__ out) {
+  pdl_entry();
   __shared__ int s_row[kSliceRows], s_tok[kSliceRows];
   const long long i0 = (long long)blockIdx.x * kSliceRows;
   const int n = (int)min((long long)kSliceRows, M - i0);
@@ -133,10 +137,10 @@ extern "C" int msx_token_sort(const int32_t* tokens, long long M, int V, int32_t
   MSX_CUDA(cudaMemsetAsync(workspace, 0, (size_t)V * sizeof(int), st));
   const long long want = (M + 255) / 256;
   const int grid = (int)(want < 2ll * msx_num_sms() ? want : 2ll * msx_num_sms());
-  tok_hist_kernel<<<grid, 256, (size_t)V * sizeof(int), st>>>(tokens, M, V, workspace);
-  tok_scan_kernel<<<1, 1024, 0, st>>>(workspace, V, workspace + V, workspace + 2 * V);
-  tok_scatter_kernel<<<(int)((M + kScatterChunk - 1) / kScatterChunk), 256, 2 * (size_t)V * sizeof(int), st>>>(
-      tokens, M, V, workspace + 2 * V, perm, sorted_tok);
+  MSX_CUDA(msx_launch(tok_hist_kernel, dim3(grid), dim3(256), (size_t)V * sizeof(int), st, tokens, M, V, workspace));
+  MSX_CUDA(msx_launch(tok_scan_kernel, dim3(1), dim3(1024), 0, st, workspace, V, workspace + V, workspace + 2 * V));
+  MSX_CUDA(msx_launch(tok_scatter_kernel, dim3((int)((M + kScatterChunk - 1) / kScatterChunk)), dim3(256), 2 * (size_t)V * sizeof(int), st, 
+      tokens, M, V, workspace + 2 * V, perm, sorted_tok));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -149,7 +153,7 @@ extern "C" int msx_rows_sum_by_token(const float* X, int ld, int D, const int32_
               "msx_rows_sum_by_token: D %% 4 == 0, D <= 1024, 16-byte aligned rows");
   if (M == 0) return MSX_OK;
   const int grid = (int)((M + kSliceRows - 1) / kSliceRows);
-  rows_sum_by_token_kernel<<<grid, D / 4, 0, (cudaStream_t)stream>>>(X, ld, D, perm, sorted_tok, M, scale, out);
+  MSX_CUDA(msx_launch(rows_sum_by_token_kernel, dim3(grid), dim3(D / 4), 0, (cudaStream_t)stream, X, ld, D, perm, sorted_tok, M, scale, out));
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -160,6 +160,13 @@ def set_step_counter(counter):
     lib.check(lib.load().msx_set_step_counter(P(counter)), "msx_set_step_counter")
 
 
+def set_pdl(enable):
+    """Programmatic dependent launch of the library's kernels on / off; returns the previous setting."""
+    prev = int(lib.load().msx_get_pdl())
+    lib.load().msx_set_pdl(_i(1 if enable else 0))
+    return prev
+
+
 def step_counter_tick(counter):
     lib.call("msx_step_counter_tick", P(counter), lib.stream_ptr())
 
