@@ -63,7 +63,9 @@ class VAEConfig:
         if dec_type == "transformer":
             assert dec_size % dec_heads == 0
         else:
-            assert dec_layers >= 1 and dec_size in (32, 64, 128), "LSTM decoder: n_layers >= 1, hidden size 32 / 64 / 128"
+            # 32 / 64 / 128: recurrence kernels with W_h2h resident per CTA pair (128 also on the tensor cores); any other
+            # size up to 512 takes the L2-streaming kernels of lstm.cu
+            assert dec_layers >= 1 and 1 <= dec_size <= 512, "LSTM decoder: n_layers >= 1, hidden size 1 .. 512"
         self.vocab, self.num_classes = vocab, num_classes
         self.enc_size, self.enc_layers, self.enc_heads = enc_size, enc_layers, enc_heads
         self.latent = latent

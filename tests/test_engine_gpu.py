@@ -526,3 +526,18 @@ def test_rows_longer_than_384_positions(precision, T):
             scale = float(grads[name].abs().max())
             err = float((eng.arena.grad(name).cpu() - grads[name]).abs().max())
             assert err <= 5e-2 * scale + 1e-3 * gscale, (name, err, scale)
+
+
+@pytest.mark.parametrize("dec_size,dec_layers", [(96, 1), (100, 2), (50, 1)])
+def test_lstm_decoder_any_hidden_size_step(dec_size, dec_layers):
+    """--d-hidden is free in the reference's CLI (main.py:109-117, LSTMConfig): hidden sizes other than 32 / 64 / 128 run the
+    L2-streaming recurrence kernels; the whole step (forward, every gradient, Adam) against the oracle at the fp32 bar."""
+    cfg = om.Cfg(vocab=293, num_classes=2, enc_size=64, enc_layers=1, enc_heads=4, latent=32,
+                 dec_type="lstm", dec_size=dec_size, dec_layers=dec_layers)
+    p = om.init_params(cfg, seed=dec_size)
+    gen = torch.Generator().manual_seed(dec_size)
+    for k in p:
+        if k.endswith("bias") or k.endswith("beta"):
+            p[k] = torch.randn(p[k].shape, generator=gen) * 0.05
+    tokens, seq_lens, classes, labels, eps = _batch(11, 17, cfg.vocab, cfg.num_classes, cfg.latent, seed=dec_size + 1)
+    _run_case(cfg, p, tokens, seq_lens, classes, labels, eps, condition=True)
