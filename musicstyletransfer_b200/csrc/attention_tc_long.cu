@@ -18,6 +18,7 @@
 //   phase 2 (over query chunks):  dP = V dO^T,  dS = P (dP - delta) / sqrt(d_h) -> TMEM and, transposed, shared memory
 //                                 dK += dS Q (A from TMEM),  dQ[chunk] += dS^T K (A MN-major from shared memory)
 // dQ accumulates over key tiles in TMEM (32 columns per query chunk).
+#include <cuda_bf16.h>
 #include "attention_tc_common.cuh"
 
 namespace {
@@ -25,7 +26,22 @@ namespace {
 constexpr int kTile = 128;                  // keys per key tile = queries per query chunk
 constexpr int kTileBytes = kTile * 128;     // one [128 rows][128 B] operand tile (K-major or MN-major)
 
+// Trailing key rows.  The reference's rows are T = L + 1 long (SOS / EOS, VarAutoEncoder/data.py:150-170), so the sweep's
+// row lengths are 128 n + 1: a key tile of their own would cost a full tile pass for ONE key.  Up to kTailMax trailing keys
+// (T = 128 n + tail) are taken off the tensor path instead: a key row's scores against every query are 32-long dot products,
+// one or two per thread (thread = query), its softmax over the query axis two block reductions, and it enters the outputs
+// as rank-1 updates in the epilogue (forward: O[q] += P[k*][q] V[k*]; backward: dQ[q] += dS[k*][q] K[k*], with dV[k*] / dK[k*]
+// block column sums).  Operands are rounded to TF32 exactly where the tensor path rounds them (K, Q of the scores), so the
+// forward's saved statistics and the backward's recomputed P agree bit for bit.
+constexpr int kTailMax = 4;
+__host__ __device__ inline int tail_keys(int T) {
+  const int t = T % 128;
+  return (t >= 1 && t <= kTailMax) ? t : 0;
+}
+
 struct AttnLongParams {
+  const float* qkv;    // [B*T, 3*H*32]: the tail-key path reads rows directly
+  const float* dctx;   // bwd: [B*T, H*32]
   const float* mask;   // [B*T]
   float* stats;        // [B*H*T, 2]: (row max * log2 e, 1 / row sum) of every key row; written by fwd, read by bwd
   void* out;           // fwd: ctx [B*T, H*32]; bwd: dqkv [B*T, 3*H*32]; fp32, or bf16 when out_bf16
@@ -39,6 +55,46 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// all-thread max / sum over the 128 threads of the CTA through red[4] (two barriers: the result is read before the next use)
+__device__ __forceinline__ float block_max128(float v, float* red, int tid) {
+  v = warp_max(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  v = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  return v;
+}
+__device__ __forceinline__ float block_sum128(float v, float* red, int tid) {
+  v = warp_sum(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  v = (red[0] + red[1]) + (red[2] + red[3]);
+  __syncthreads();
+  return v;
+}
+// column sums of a [128 threads x 32] register matrix: afterwards every thread holds the total of column (tid & 31)
+__device__ __forceinline__ float block_colsum128(float (&v)[32], float* red /* [128] */, int tid) {
+  red[tid] = warp_colsum32(v, tid & 31);
+  __syncthreads();
+  const int c = tid & 31;
+  const float t = (red[c] + red[32 + c]) + (red[64 + c] + red[96 + c]);
+  __syncthreads();
+  return t;
+}
+// 32-long dot product of a TF32-rounded K row (global, the same address for every thread: an L1 broadcast) with a query row
+__device__ __forceinline__ float dot32_tf32(const float* __restrict__ krow, const float (&q)[32]) {
+  float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 k4 = __ldg(reinterpret_cast<const float4*>(krow) + c);
+    d4[0] = fmaf(to_tf32(k4.x), q[4 * c], d4[0]);
+    d4[1] = fmaf(to_tf32(k4.y), q[4 * c + 1], d4[1]);
+    d4[2] = fmaf(to_tf32(k4.z), q[4 * c + 2], d4[2]);
+    d4[3] = fmaf(to_tf32(k4.w), q[4 * c + 3], d4[3]);
+  }
+  return (d4[0] + d4[1]) + (d4[2] + d4[3]);
+}
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int NT>
@@ -64,6 +120,9 @@ __global__ void __launch_bounds__(128, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int T = p.T, TQ = p.TQ, D = p.H * DH;
+  const int ntail = tail_keys(T);                    // trailing keys handled off the tensor path (see kTailMax)
+  const int nkt = NT - (ntail ? 1 : 0);              // key tiles on the tensor path (NT = query chunks = ceil(T / 128))
+  __shared__ float red_t[4];
 
   // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
   for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -96,7 +155,7 @@ __global__ void __launch_bounds__(128, 1)
     tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
   }
   int n = 0;                                          // running (key tile, query chunk) counter: P buffer = n & 1
-  for (int kt = 0; kt < NT; ++kt) {
+  for (int kt = 0; kt < nkt; ++kt) {
     const unsigned par = (unsigned)(kt & 1);
     if (tid == 0) {
       if (kt == 0) mbar_wait(bar_q, 0);
@@ -116,7 +175,7 @@ __global__ void __launch_bounds__(128, 1)
     __syncwarp();
     mbar_wait(bar_s, par);
     tc_fence_after();
-    if (tid == 0 && kt + 1 < NT) {                    // the K tile is free once MMA 1 has retired
+    if (tid == 0 && kt + 1 < nkt) {                   // the K tile is free once MMA 1 has retired
       mbar_expect_tx(bar_k, (unsigned)kTileBytes);
       tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
     }
@@ -182,7 +241,7 @@ __global__ void __launch_bounds__(128, 1)
       }
       __syncwarp();
     }
-    if (tid == 0 && kt + 1 < NT) {                    // V tile is free once the last MMA 2 of this key tile has retired
+    if (tid == 0 && kt + 1 < nkt) {                   // V tile is free once the last MMA 2 of this key tile has retired
       const int last = n - 1;
       mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
       mbar_expect_tx(bar_v, (unsigned)kTileBytes);
@@ -195,11 +254,60 @@ __global__ void __launch_bounds__(128, 1)
     mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
     tc_fence_after();
   }
+  // trailing key rows: scores of key k* against this thread's queries (rows of the resident, TF32-rounded Q tiles), softmax
+  // over the query axis across the CTA, P[k*][q] kept for the rank-1 update of the output rows
+  float ptail[NT][kTailMax];
+#pragma unroll
+  for (int i = 0; i < kTailMax; ++i) {
+    if (i < ntail) {                                   // CTA-uniform
+      const int ks = (NT - 1) * kTile + i;
+      const float rowmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+      const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
+      float sc[NT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int qc = 0; qc < NT; ++qc) {
+        float qr[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 q4 = *reinterpret_cast<const float4*>(sQ + qc * kTileBytes + tid * 128 + ((c ^ (tid & 7)) << 4));
+          qr[4 * c] = q4.x; qr[4 * c + 1] = q4.y; qr[4 * c + 2] = q4.z; qr[4 * c + 3] = q4.w;
+        }
+        sc[qc] = fmaf(dot32_tf32(krow, qr), p.inv_scale, rowmask);
+        if (qc * kTile + tid < T) mx = fmaxf(mx, sc[qc]);
+      }
+      const float mxl = block_max128(mx, red_t, tid) * kLog2e;
+      float sum = 0.f;
+#pragma unroll
+      for (int qc = 0; qc < NT; ++qc) {
+        sc[qc] = (qc * kTile + tid < T) ? exp2f(fmaf(sc[qc], kLog2e, -mxl)) : 0.f;
+        sum += sc[qc];
+      }
+      const float inv = 1.f / block_sum128(sum, red_t, tid);
+#pragma unroll
+      for (int qc = 0; qc < NT; ++qc) ptail[qc][i] = sc[qc] * inv;
+      if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
+    }
+  }
+#pragma unroll
   for (int qc = 0; qc < NT; ++qc) {
     const int q = qc * kTile + tid;                    // lanes = queries
     float o[32];
     tmem_ld16(tm_O + lane_off + qc * DH, o);
     tmem_ld16(tm_O + lane_off + qc * DH + 16, o + 16);
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) {
+      if (i < ntail) {                                 // O[q] += P[k*][q] V[k*]
+        const float4* vp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + (NT - 1) * kTile + i) * 3 * D + 2 * D + h * DH);
+        const float pt = ptail[qc][i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v4 = __ldg(vp + c);
+          o[4 * c] = fmaf(pt, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pt, v4.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(pt, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pt, v4.w, o[4 * c + 3]);
+        }
+      }
+    }
     if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
   }
   tc_fence_before();
@@ -237,6 +345,8 @@ __global__ void __launch_bounds__(128, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int T = p.T, TQ = p.TQ, D = p.H * DH;
+  const int ntail = tail_keys(T);                    // trailing keys handled off the tensor path (see kTailMax)
+  const int nkt = NT - (ntail ? 1 : 0);
 
   for (int i = tid * 16; i < 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sY + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_async_smem();
@@ -264,7 +374,7 @@ __global__ void __launch_bounds__(128, 1)
   for (int j = 0; j < 32; ++j) acc_k[j] = acc_v[j] = acc_q[j] = 0.f;
 
   unsigned step = 0;                                        // bar_qc / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
-  for (int kt = 0; kt < NT; ++kt) {
+  for (int kt = 0; kt < nkt; ++kt) {
     const int kg = kt * kTile + tid;
     const bool valid = kg < T;
     const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
@@ -415,11 +525,107 @@ __global__ void __launch_bounds__(128, 1)
     __syncthreads();                           // every thread has read dV / dK before the next key tile overwrites them
     tc_fence_after();
   }
+  // trailing key rows (thread = query, Q / dO rows straight from global memory): P from the forward's statistics,
+  // dP = V[k*] . dO[q], delta = sum_q P dP, dS = P (dP - delta) / sqrt(d_h); dV[k*] = sum_q P dO[q] and dK[k*] = sum_q dS Q[q]
+  // are block column sums, dQ[q] += dS K[k*] joins the epilogue below
+  float dst[NT][kTailMax];
+#pragma unroll
+  for (int i = 0; i < kTailMax; ++i) {
+    if (i < ntail) {                                 // CTA-uniform
+      const int ks = (NT - 1) * kTile + i;
+      const float rowmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+      const float2 stt = __ldg(reinterpret_cast<const float2*>(p.stats) + ((size_t)(b * p.H + h) * T + ks));
+      const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
+      const float4* vrow = reinterpret_cast<const float4*>(krow + 2 * D);
+      float pv[NT], dpv[NT];
+      float col[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) col[j] = 0.f;
+      float dl = 0.f;
+#pragma unroll
+      for (int qc = 0; qc < NT; ++qc) {
+        const int q = qc * kTile + tid;
+        pv[qc] = dpv[qc] = 0.f;
+        if (q < T) {
+          float qr[32], dor[32];
+          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+          const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = __ldg(vrow + c);
+            qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
+            dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
+            d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
+            d4[2] = fmaf(v4.z, g4.z, d4[2]); d4[3] = fmaf(v4.w, g4.w, d4[3]);
+          }
+          const float sc = fmaf(dot32_tf32(krow, qr), p.inv_scale, rowmask);
+          const float pr = exp2f(fmaf(sc, kLog2e, -stt.x)) * stt.y;
+          const float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          pv[qc] = pr;
+          dpv[qc] = dp;
+          dl = fmaf(pr, dp, dl);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) col[j] = fmaf(pr, dor[j], col[j]);
+        }
+      }
+      const float delta = block_sum128(dl, red, tid);
+      const float dv = block_colsum128(col, red, tid);        // dV[k*][tid & 31] in every thread
+#pragma unroll
+      for (int j = 0; j < 32; ++j) col[j] = 0.f;
+#pragma unroll
+      for (int qc = 0; qc < NT; ++qc) {
+        const int q = qc * kTile + tid;
+        const float ds = pv[qc] * ((dpv[qc] - delta) * p.inv_scale);
+        dst[qc][i] = ds;
+        if (q < T) {
+          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 q4 = __ldg(qp + c);
+            col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
+            col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
+          }
+        }
+      }
+      const float dk = block_colsum128(col, red, tid);        // dK[k*][tid & 31]
+      if (tid < 32) {
+        const size_t e = ((size_t)b * T + ks) * 3 * D + h * DH + tid;
+        if (p.out_bf16) {
+          unsigned short* o16 = reinterpret_cast<unsigned short*>(p.out);
+          o16[e] = __bfloat16_as_ushort(__float2bfloat16_rn(dk));
+          o16[e + 2 * D] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
+        } else {
+          float* o32 = reinterpret_cast<float*>(p.out);
+          o32[e] = dk;
+          o32[e + 2 * D] = dv;
+        }
+        if (p.dbias) {
+          atomicAdd(p.dbias + 0 * D + h * DH + tid, dk);
+          atomicAdd(p.dbias + 2 * D + h * DH + tid, dv);
+        }
+      }
+    }
+  }
+#pragma unroll
   for (int qc = 0; qc < NT; ++qc) {
     const int q = qc * kTile + tid;            // lanes = queries
     float o[32];
     tmem_ld16(tm_dQ + lane_off + qc * DH, o);
     tmem_ld16(tm_dQ + lane_off + qc * DH + 16, o + 16);
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) {
+      if (i < ntail) {                         // dQ[q] += dS[k*][q] K[k*]
+        const float4* kp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + (NT - 1) * kTile + i) * 3 * D + h * DH);
+        const float ds = dst[qc][i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 k4 = __ldg(kp + c);
+          o[4 * c] = fmaf(ds, k4.x, o[4 * c]); o[4 * c + 1] = fmaf(ds, k4.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(ds, k4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(ds, k4.w, o[4 * c + 3]);
+        }
+      }
+    }
     if (q < T) {
       store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * 3 * D + D + h * DH, o);
 #pragma unroll
@@ -458,6 +664,7 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnLongParams p;
+  p.qkv = qkv; p.dctx = nullptr;
   p.mask = mask; p.stats = stats; p.out = ctx; p.out_bf16 = ctx_bf16 ? 1 : 0; p.dbias = nullptr;
   p.T = T; p.H = H; p.TQ = (T + 15) / 16 * 16; p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;
@@ -486,6 +693,7 @@ extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const 
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnLongParams p;
+  p.qkv = qkv; p.dctx = dctx;
   p.mask = mask; p.stats = const_cast<float*>(stats); p.out = dqkv; p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias;
   p.T = T; p.H = H; p.TQ = (T + 15) / 16 * 16; p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;

@@ -160,7 +160,8 @@ def test_attention_backward_query0_only(B, T, H, out16):
 
 
 # ------------------------------------------------------------------------------------------------ long rows (T > 128)
-@pytest.mark.parametrize("B,T,H", [(2, 129, 2), (3, 257, 2), (2, 200, 3), (5, 256, 1), (2, 384, 2), (40, 129, 8), (3, 144, 2)])
+@pytest.mark.parametrize("B,T,H", [(2, 129, 2), (3, 257, 2), (2, 200, 3), (5, 256, 1), (2, 384, 2), (40, 129, 8), (3, 144, 2),
+                                   (3, 130, 2), (4, 131, 3), (3, 132, 2), (2, 133, 2), (4, 258, 2), (3, 260, 1), (300, 129, 8)])
 @pytest.mark.parametrize("out16", [False, True])
 def test_attention_long_rows(B, T, H, out16):
     """msx_attention_tcl_fwd / _bwd (key tiles + query chunks of 128) vs the float64 reference formula and autograd."""
