@@ -33,6 +33,14 @@ constexpr int kTileBytes = kTile * 128;     // one [128 rows][128 B] operand til
 // as rank-1 updates in the epilogue (forward: O[q] += P[k*][q] V[k*]; backward: dQ[q] += dS[k*][q] K[k*], with dV[k*] / dK[k*]
 // block column sums).  Operands are rounded to TF32 exactly where the tensor path rounds them (K, Q of the scores), so the
 // forward's saved statistics and the backward's recomputed P agree bit for bit.
+//
+// The same trailing positions are taken off the tensor path as QUERIES: the thread that owns key row k adds the scores
+// K_k . Q_q* of the trailing queries (32-long dot products, thread-local) to its row maximum / sum, and the trailing
+// queries' outputs (forward: O[q*] = sum_k P[k][q*] V[k]; backward: dQ[q*] = sum_k dS[k][q*] K[k]) are block column sums,
+// while dV_k += P[k][q*] dO[q*] and dK_k += dS[k][q*] Q[q*] are thread-local rank-1 updates of the key thread's rows.  So
+// T = 128 n + tail runs n x n tiles instead of (n + 1) x (n + 1); T = 129 ... 132 is ONE tile: the forward then aliases
+// the P staging onto the (dead) Q / K tiles and allocates 256 TMEM columns, so two CTAs share an SM, and the backward
+// loads its seven operand tiles once and issues S = K Q^T and dP = V dO^T together.
 constexpr int kTailMax = 4;
 __host__ __device__ inline int tail_keys(int T) {
   const int t = T % 128;
@@ -47,7 +55,7 @@ struct AttnLongParams {
   void* out;           // fwd: ctx [B*T, H*32]; bwd: dqkv [B*T, 3*H*32]; fp32, or bf16 when out_bf16
   int out_bf16;
   float* dbias;        // bwd, optional [3*H*32]: += column sums of dqkv
-  int T, H, TQ;        // TQ = roundup16(T)
+  int T, H, TQ;        // TQ = score columns on the tensor path: roundup16(T), or T - tail when trailing positions leave it
   float inv_scale;
 };
 
@@ -96,9 +104,50 @@ __device__ __forceinline__ float dot32_tf32(const float* __restrict__ krow, cons
   return (d4[0] + d4[1]) + (d4[2] + d4[3]);
 }
 
+// same accumulation order as dot32_tf32, both rows in registers
+__device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32]) {
+  float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    d4[0] = fmaf(a[4 * c], b[4 * c], d4[0]);
+    d4[1] = fmaf(a[4 * c + 1], b[4 * c + 1], d4[1]);
+    d4[2] = fmaf(a[4 * c + 2], b[4 * c + 2], d4[2]);
+    d4[3] = fmaf(a[4 * c + 3], b[4 * c + 3], d4[3]);
+  }
+  return (d4[0] + d4[1]) + (d4[2] + d4[3]);
+}
+// row r of a K-major SWIZZLE_128B tile [128 rows][32 floats] (as TMA wrote it: TF32-rounded)
+__device__ __forceinline__ void load_row_km(const unsigned char* tile, int r, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 x = *reinterpret_cast<const float4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+    v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+  }
+}
+// row r (one key's 32 head columns) of an MN-major SWIZZLE_128B_ATOM_32B tile (mn_major_off with mn = column, k = r)
+__device__ __forceinline__ void load_row_mn(const unsigned char* tile, int r, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 x = *reinterpret_cast<const float4*>(tile + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4));
+    v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+  }
+}
+// a 32-float row of global memory (the same address for every thread: a broadcast), optionally rounded to TF32
+template <bool ROUND>
+__device__ __forceinline__ void load_row_global(const float* row, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(row) + c);
+    v[4 * c] = ROUND ? to_tf32(x.x) : x.x; v[4 * c + 1] = ROUND ? to_tf32(x.y) : x.y;
+    v[4 * c + 2] = ROUND ? to_tf32(x.z) : x.z; v[4 * c + 3] = ROUND ? to_tf32(x.w) : x.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-template <int NT>
-__global__ void __launch_bounds__(128, 1)
+// ALIAS (T = 129 ... 132: one key tile x one query chunk on the tensor path): P staging (single buffer) lies over the Q / K
+// tiles, 256 TMEM columns, 81 KB of shared memory: two CTAs per SM.
+template <int NT, int NKT, bool ALIAS>
+__global__ void __launch_bounds__(128, ALIAS ? 2 : 1)
     attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
                         const AttnLongParams p) {
@@ -107,32 +156,41 @@ __global__ void __launch_bounds__(128, 1)
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sQ = base;                          // NT K-major tiles: all queries of the (batch, head)
   unsigned char* sK = sQ + NT * kTileBytes;          // K-major key tile
-  unsigned char* sV = sK + kTileBytes;               // MN-major value tile (d contiguous, 128 key rows)
-  unsigned char* sP = sV + kTileBytes;               // 2 x 4 slabs: P chunk, q contiguous, 128 key rows per slab
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sP + 2 * 4 * kTileBytes);
+  unsigned char* sV = ALIAS ? base + 4 * kTileBytes : sK + kTileBytes;   // MN-major value tile (d contiguous, 128 key rows)
+  // P chunk, q contiguous, 4 slabs of 128 key rows; two buffers, or ONE lying over sQ / sK (dead once MMA 1 has retired)
+  unsigned char* sP = ALIAS ? base : sV + kTileBytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ALIAS ? sV + kTileBytes : sP + 2 * 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_q = &bars[0];
   unsigned long long* bar_k = &bars[1];
   unsigned long long* bar_v = &bars[2];
   unsigned long long* bar_s = &bars[3];
   unsigned long long* bar_o = &bars[4];              // [2]
+  constexpr int kTmemCols = ALIAS ? 256 : 512;
+  static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
+  static_assert(!ALIAS || (NT == 2 && NKT == 1), "ALIAS: one full tile + trailing positions");
+  constexpr bool TAIL = NKT < NT;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int T = p.T, TQ = p.TQ, D = p.H * DH;
-  const int ntail = tail_keys(T);                    // trailing keys handled off the tensor path (see kTailMax)
-  const int nkt = NT - (ntail ? 1 : 0);              // key tiles on the tensor path (NT = query chunks = ceil(T / 128))
+  const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
+  constexpr int nkt = NKT;                           // key tiles = query chunks on the tensor path (NT = ceil(T / 128))
   __shared__ float red_t[4];
+  __shared__ float red_c[128];
+  __shared__ float ot_s[kTailMax][32];
 
-  // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
-  for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  fence_async_smem();
+  if (!ALIAS) {
+    // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
+    for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
+  }
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -140,7 +198,7 @@ __global__ void __launch_bounds__(128, 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_O = tmem, tm_S = tmem + 128;     // O: NT x 32 columns; S: up to 384 columns
+  const unsigned tm_O = tmem, tm_S = tmem + 128;     // O: 32 columns per query chunk; S: up to 384 columns (ALIAS: 128)
   const unsigned lane_off = (unsigned)(warp * 32) << 16;
   // MMA 2: A = P^T MN-major (queries contiguous), B = V MN-major (d contiguous), M = 128 queries, N = 32
   const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
@@ -154,6 +212,10 @@ __global__ void __launch_bounds__(128, 1)
     mbar_expect_tx(bar_v, (unsigned)kTileBytes);
     tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
   }
+  float ptail[NT][kTailMax];                          // P[trailing key i][this thread's query of chunk qc]
+  float ot[kTailMax];                                 // O[trailing query i][column tid & 31], summed over the key tiles
+#pragma unroll
+  for (int i = 0; i < kTailMax; ++i) ot[i] = 0.f;
   int n = 0;                                          // running (key tile, query chunk) counter: P buffer = n & 1
   for (int kt = 0; kt < nkt; ++kt) {
     const unsigned par = (unsigned)(kt & 1);
@@ -162,7 +224,7 @@ __global__ void __launch_bounds__(128, 1)
       mbar_wait(bar_k, par);
       tc_fence_after();
       // MMA 1: S[128 keys x TQ] = K Q^T in query chunks of <= 128 columns (both operands K-major, +32 B per k-step)
-      for (int qc = 0; qc < NT; ++qc) {
+      for (int qc = 0; qc < nkt; ++qc) {
         const int nq = min(kTile, TQ - qc * kTile);
         const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
 #pragma unroll
@@ -173,15 +235,69 @@ __global__ void __launch_bounds__(128, 1)
       umma_commit(bar_s);
     }
     __syncwarp();
+    const int kg = kt * kTile + tid;                  // this thread's key row
+    const bool valid = kg < T;
+    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
+    // while MMA 1 runs: this key row's scores against the trailing queries (rows 0 .. ntail-1 of the last Q tile) and,
+    // once per item, the trailing KEY rows (thread = query; independent of the tensor path)
+    float st[kTailMax];
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) st[i] = 0.f;
+    if (TAIL) {
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, par);
+      {
+        float kr[32];
+        load_row_km(sK, tid, kr);
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) {
+          if (i < ntail) {
+            float qr[32];
+            load_row_km(sQ + (NT - 1) * kTileBytes, i, qr);
+            st[i] = fmaf(dot32(kr, qr), p.inv_scale, rowmask);
+          }
+        }
+      }
+      if (kt == 0) {
+        // trailing key rows: scores of key k* against this thread's queries (rows of the resident, TF32-rounded Q tiles),
+        // softmax over the query axis across the CTA, P[k*][q] kept for the rank-1 update of the output rows
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) {
+          if (i < ntail) {
+            const int ks = (NT - 1) * kTile + i;
+            const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+            const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
+            float sc[NT];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int qc = 0; qc < NT; ++qc) {
+              float qr[32];
+              load_row_km(sQ + qc * kTileBytes, tid, qr);
+              sc[qc] = fmaf(dot32_tf32(krow, qr), p.inv_scale, rmask);
+              if (qc * kTile + tid < T) mx = fmaxf(mx, sc[qc]);
+            }
+            const float mxl = block_max128(mx, red_t, tid) * kLog2e;
+            float sum = 0.f;
+#pragma unroll
+            for (int qc = 0; qc < NT; ++qc) {
+              sc[qc] = (qc * kTile + tid < T) ? exp2f(fmaf(sc[qc], kLog2e, -mxl)) : 0.f;
+              sum += sc[qc];
+            }
+            const float inv = 1.f / block_sum128(sum, red_t, tid);
+#pragma unroll
+            for (int qc = 0; qc < NT; ++qc) ptail[qc][i] = sc[qc] * inv;
+            if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
+          }
+        }
+      }
+      __syncthreads();                                // every thread has read its K / Q rows: the tiles may be reused
+    }
     mbar_wait(bar_s, par);
     tc_fence_after();
     if (tid == 0 && kt + 1 < nkt) {                   // the K tile is free once MMA 1 has retired
       mbar_expect_tx(bar_k, (unsigned)kTileBytes);
       tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
     }
-    const int kg = kt * kTile + tid;                  // this thread's key row
-    const bool valid = kg < T;
-    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
     // pass 1: row maximum over the T queries
     float mx = -INFINITY;
     for (int c = 0; c < TQ; c += 16) {
@@ -189,8 +305,11 @@ __global__ void __launch_bounds__(128, 1)
       tmem_ld16(tm_S + lane_off + c, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (c + j < T) mx = fmaxf(mx, fmaf(v[j], p.inv_scale, rowmask));
+        if (TAIL || c + j < T) mx = fmaxf(mx, fmaf(v[j], p.inv_scale, rowmask));
     }
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i)
+      if (i < ntail) mx = fmaxf(mx, st[i]);
     const float mxl = mx * kLog2e;
     // pass 2: e = exp2(s * log2 e - max * log2 e) back into TMEM, row sum
     float sum = 0.f;
@@ -199,20 +318,27 @@ __global__ void __launch_bounds__(128, 1)
       tmem_ld16(tm_S + lane_off + c, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        v[j] = (c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) : 0.f;
+        v[j] = (TAIL || c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) : 0.f;
         sum += v[j];
       }
       tmem_st16(tm_S + lane_off + c, v);
     }
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) {
+      if (i < ntail) {
+        st[i] = exp2f(fmaf(st[i], kLog2e, -mxl));
+        sum += st[i];
+      }
+    }
     tmem_st_wait();
     const float inv = valid ? 1.f / sum : 0.f;        // rows beyond T (neighbouring sequence / zeros) contribute nothing
     if (valid) {
-      float2* st = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
-      *st = make_float2(mxl, inv);
+      float2* stp = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
+      *stp = make_float2(mxl, inv);
     }
     // pass 3: normalised row -> shared memory, one query chunk at a time, each chunk followed by its MMA 2
-    for (int qc = 0; qc < NT; ++qc, ++n) {
-      const int buf = n & 1;
+    for (int qc = 0; qc < nkt; ++qc, ++n) {
+      const int buf = ALIAS ? 0 : (n & 1);
       unsigned char* pb = sP + buf * 4 * kTileBytes;
       if (n >= 2) {                                    // the MMA that read this buffer two chunks ago has retired
         mbar_wait(&bar_o[buf], (unsigned)(((n >> 1) - 1) & 1));
@@ -241,6 +367,22 @@ __global__ void __launch_bounds__(128, 1)
       }
       __syncwarp();
     }
+    if (TAIL) {
+      // while the MMA 2s run: O[q*] += sum over this tile's keys of P[k][q*] V[k] (V row as the MMA sees it)
+      mbar_wait(bar_v, par);
+      float vr[32];
+      load_row_mn(sV, tid, vr);
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i) {
+        if (i < ntail) {
+          const float pt = st[i] * inv;
+          float c[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = pt * vr[j];
+          ot[i] += block_colsum128(c, red_c, tid);      // ends with a barrier: every thread has read its V row
+        }
+      }
+    }
     if (tid == 0 && kt + 1 < nkt) {                   // V tile is free once the last MMA 2 of this key tile has retired
       const int last = n - 1;
       mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
@@ -251,50 +393,27 @@ __global__ void __launch_bounds__(128, 1)
   }
   {
     const int last = n - 1;                            // commits complete in order: the last one covers every MMA
-    mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+    mbar_wait(&bar_o[ALIAS ? 0 : (last & 1)], (unsigned)((last >> 1) & 1));
     tc_fence_after();
   }
-  // trailing key rows: scores of key k* against this thread's queries (rows of the resident, TF32-rounded Q tiles), softmax
-  // over the query axis across the CTA, P[k*][q] kept for the rank-1 update of the output rows
-  float ptail[NT][kTailMax];
+  if (TAIL) {
+    if (tid < 32) {
 #pragma unroll
-  for (int i = 0; i < kTailMax; ++i) {
-    if (i < ntail) {                                   // CTA-uniform
-      const int ks = (NT - 1) * kTile + i;
-      const float rowmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
-      const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
-      float sc[NT];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int qc = 0; qc < NT; ++qc) {
-        float qr[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 q4 = *reinterpret_cast<const float4*>(sQ + qc * kTileBytes + tid * 128 + ((c ^ (tid & 7)) << 4));
-          qr[4 * c] = q4.x; qr[4 * c + 1] = q4.y; qr[4 * c + 2] = q4.z; qr[4 * c + 3] = q4.w;
-        }
-        sc[qc] = fmaf(dot32_tf32(krow, qr), p.inv_scale, rowmask);
-        if (qc * kTile + tid < T) mx = fmaxf(mx, sc[qc]);
-      }
-      const float mxl = block_max128(mx, red_t, tid) * kLog2e;
-      float sum = 0.f;
-#pragma unroll
-      for (int qc = 0; qc < NT; ++qc) {
-        sc[qc] = (qc * kTile + tid < T) ? exp2f(fmaf(sc[qc], kLog2e, -mxl)) : 0.f;
-        sum += sc[qc];
-      }
-      const float inv = 1.f / block_sum128(sum, red_t, tid);
-#pragma unroll
-      for (int qc = 0; qc < NT; ++qc) ptail[qc][i] = sc[qc] * inv;
-      if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
+      for (int i = 0; i < kTailMax; ++i) ot_s[i][tid] = ot[i];
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int qc = 0; qc < NT; ++qc) {
     const int q = qc * kTile + tid;                    // lanes = queries
     float o[32];
-    tmem_ld16(tm_O + lane_off + qc * DH, o);
-    tmem_ld16(tm_O + lane_off + qc * DH + 16, o + 16);
+    if (qc < nkt) {
+      tmem_ld16(tm_O + lane_off + qc * DH, o);
+      tmem_ld16(tm_O + lane_off + qc * DH + 16, o + 16);
+    } else {                                           // the trailing queries' rows: threads 0 .. ntail-1
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = ot_s[tid & (kTailMax - 1)][j];
+    }
 #pragma unroll
     for (int i = 0; i < kTailMax; ++i) {
       if (i < ntail) {                                 // O[q] += P[k*][q] V[k*]
@@ -312,18 +431,84 @@ __global__ void __launch_bounds__(128, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int NT>
-__global__ void __launch_bounds__(128, 1)
+// 256 threads: warps w and w + 4 share the TMEM lane quarter w & 3 (a warp reaches lanes 32 (w % 4) ... + 31), i.e. two
+// threads own one key row (one query row in the dQ epilogue) and split its columns — 64 + 64 score columns in the P and dS
+// passes, 16 + 16 head columns in the row epilogues.  The kernel is bound by the instruction stream of the row owners
+// (ncu, 128-thread version: 6.8 k instructions per warp and item at 18 % issue utilisation, one warp per scheduler), so
+// halving the columns per thread halves the critical path.
+//
+// NKT = key tiles = query chunks on the tensor path (NT, or NT - 1 when T = 128 (NT - 1) + 1 ... 4: trailing positions).
+// SINGLE (NT = 2, NKT = 1: T = 129 ... 132): the seven operand tiles are loaded once, S = K Q^T and dP = V dO^T are issued
+// together, P goes to its own TMEM columns so that S survives for the dS pass: one TMA round trip and three MMA round trips
+// per (batch, head) instead of four and eight.
+constexpr int kBwdThreads = 256;
+
+__device__ __forceinline__ float block_sum256(float v, float* red8, int tid) {
+  v = warp_sum(v);
+  if ((tid & 31) == 0) red8[tid >> 5] = v;
+  __syncthreads();
+  v = ((red8[0] + red8[1]) + (red8[2] + red8[3])) + ((red8[4] + red8[5]) + (red8[6] + red8[7]));
+  __syncthreads();
+  return v;
+}
+// column sums of a [256 threads x 32] register matrix: afterwards every thread holds the total of column (tid & 31)
+__device__ __forceinline__ float block_colsum256(float (&v)[32], float* red /* [256] */, int tid) {
+  red[tid] = warp_colsum32(v, tid & 31);
+  __syncthreads();
+  const int c = tid & 31;
+  const float t = ((red[c] + red[32 + c]) + (red[64 + c] + red[96 + c])) + ((red[128 + c] + red[160 + c]) + (red[192 + c] + red[224 + c]));
+  __syncthreads();
+  return t;
+}
+// the same over the 128 threads of each half of the CTA separately (threads 0 .. 127 and 128 .. 255 hold different matrices)
+__device__ __forceinline__ float half_colsum128(float (&v)[32], float* red /* [256] */, int tid) {
+  red[tid] = warp_colsum32(v, tid & 31);
+  __syncthreads();
+  const int c = (tid & 128) + (tid & 31);
+  const float t = (red[c] + red[32 + c]) + (red[64 + c] + red[96 + c]);
+  __syncthreads();
+  return t;
+}
+// every lane holds v[0..15]; afterwards lane L holds the sum over all lanes of v[L & 15]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (up ? v[i + s] : v[i]) + recv;
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+// 16 consecutive floats of a global row (same address for the threads of a warp: a broadcast)
+__device__ __forceinline__ void axpy16_global(float a, const float* row16, float (&o)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(row16) + c);
+    o[4 * c] = fmaf(a, x.x, o[4 * c]); o[4 * c + 1] = fmaf(a, x.y, o[4 * c + 1]);
+    o[4 * c + 2] = fmaf(a, x.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(a, x.w, o[4 * c + 3]);
+  }
+}
+
+template <int NT, int NKT, bool SINGLE>
+__global__ void __launch_bounds__(kBwdThreads, 1)
     attn_tcl_bwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmDOk /* K-major {32,128} over dctx */,
                         const __grid_constant__ CUtensorMap tmDOm /* MN-major {32,128} over dctx */,
                         const AttnLongParams p) {
   pdl_entry();
+  constexpr bool TAIL = NKT < NT;
+  static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
+  static_assert(!SINGLE || (NT == 2 && NKT == 1), "SINGLE: one full tile + trailing positions");
+  constexpr int NQQ = (NT * kTile + kBwdThreads - 1) / kBwdThreads;    // queries per thread in the trailing-key section
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sKk = base;                         // per key tile: K K-major, V K-major, K MN-major
@@ -340,16 +525,25 @@ __global__ void __launch_bounds__(128, 1)
   unsigned long long* bar_qc = &bars[1];
   unsigned long long* bar_m1 = &bars[2];
   unsigned long long* bar_m2 = &bars[3];
-  __shared__ float red[3 * 128];
+  __shared__ float red[256];
+  __shared__ float red8[8];
+  __shared__ float red_b[3][8][16];
+  __shared__ float tp_s[2][kTailMax][kTile];         // P / dP of (key row, trailing query), exchanged between the row's two threads
+  __shared__ float dq_s[kTailMax][32];               // dQ rows of the trailing queries
+  __shared__ float ds_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // dS[trailing key][query]
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;               // key row of the tile (query row of the chunk in the dQ epilogue)
+  const int c0 = half * 64, h16 = half * 16;         // this thread's score columns [c0, c0 + 64) and head columns [h16, h16 + 16)
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int T = p.T, TQ = p.TQ, D = p.H * DH;
-  const int ntail = tail_keys(T);                    // trailing keys handled off the tensor path (see kTailMax)
-  const int nkt = NT - (ntail ? 1 : 0);
+  const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
 
-  for (int i = tid * 16; i < 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sY + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  fence_async_smem();
+  if (!TAIL) {                                       // a short last chunk leaves part of the dS^T staging unwritten
+    for (int i = tid * 16; i < 4 * kTileBytes; i += kBwdThreads * 16) *reinterpret_cast<float4*>(sY + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
+  }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -364,18 +558,22 @@ __global__ void __launch_bounds__(128, 1)
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
   const unsigned tm_dV = tmem, tm_dK = tmem + 32, tm_dQ = tmem + 64, tm_S = tmem + 256, tm_dP = tmem + 384;
-  const unsigned lane_off = (unsigned)(warp * 32) << 16;
+  const unsigned tm_P = SINGLE ? tmem + 128 : tm_S;         // SINGLE: dQ takes 32 columns, 128 .. 255 are free
+  const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   const unsigned idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
                             ((unsigned)(128 >> 4) << 24);   // A from TMEM, B MN-major, N = 32
   const unsigned idesc_mm = idesc_ts | (1u << 15);          // A MN-major from shared memory, B MN-major
 
-  float acc_k[32], acc_v[32], acc_q[32];                    // column sums of dK / dV / dQ rows (bias gradient)
+  float acc_k[16], acc_v[16], acc_q[16];                    // column sums of this thread's dK / dV / dQ half rows (bias gradient)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc_k[j] = acc_v[j] = acc_q[j] = 0.f;
+  for (int j = 0; j < 16; ++j) acc_k[j] = acc_v[j] = acc_q[j] = 0.f;
+  float dqt[2] = {0.f, 0.f};                                // dQ[trailing query 2 ii + half][column lane], summed over the key tiles
+  const size_t tail_row0 = (size_t)b * T + (size_t)(NT - 1) * kTile;   // first trailing position (TAIL)
 
   unsigned step = 0;                                        // bar_qc / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
-  for (int kt = 0; kt < nkt; ++kt) {
-    const int kg = kt * kTile + tid;
+#pragma unroll 1
+  for (int kt = 0; kt < NKT; ++kt) {
+    const int kg = kt * kTile + row;
     const bool valid = kg < T;
     const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
     float mxl = 0.f, inv = 0.f;
@@ -385,40 +583,80 @@ __global__ void __launch_bounds__(128, 1)
       inv = st.y;
     }
     if (tid == 0) {                                         // every MMA that read the previous key tile has retired (bar_m2 waits)
-      mbar_expect_tx(bar_kt, (unsigned)(3 * kTileBytes));
+      mbar_expect_tx(bar_kt, (unsigned)((SINGLE ? 7 : 3) * kTileBytes));
       tma_load_2d(sKk, &tmKm, bar_kt, h * DH, b * T + kt * kTile);
       tma_load_2d(sVk, &tmKm, bar_kt, 2 * D + h * DH, b * T + kt * kTile);
+      if (SINGLE) {
+        tma_load_2d(sQk, &tmKm, bar_kt, D + h * DH, b * T);
+        tma_load_2d(sDOk, &tmDOk, bar_kt, h * DH, b * T);
+        tma_load_2d(sDOm, &tmDOm, bar_kt, h * DH, b * T);
+        tma_load_2d(sQm, &tmMn, bar_kt, D + h * DH, b * T);
+      }
       tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);
     }
     // ---------------- phase 1: dV[keys x 32] = sum over query chunks of P[keys x q] dO[q x 32]
-    for (int qc = 0; qc < NT; ++qc, ++step) {
+#pragma unroll 1
+    for (int qc = 0; qc < NKT; ++qc, ++step) {
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
       if (tid == 0) {
-        mbar_expect_tx(bar_qc, (unsigned)(2 * kTileBytes));
-        tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
-        tma_load_2d(sDOm, &tmDOm, bar_qc, h * DH, b * T + qc * kTile);
+        if (!SINGLE) {
+          mbar_expect_tx(bar_qc, (unsigned)(2 * kTileBytes));
+          tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
+          tma_load_2d(sDOm, &tmDOm, bar_qc, h * DH, b * T + qc * kTile);
+        }
         if (qc == 0) mbar_wait(bar_kt, (unsigned)(kt & 1));
-        mbar_wait(bar_qc, par);
+        if (!SINGLE) mbar_wait(bar_qc, par);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
+        for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T (SINGLE: and dP = V dO^T, two independent chains)
           umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
                     idesc_s, k > 0 ? 1u : 0u);
+          if (SINGLE)
+            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
+                      idesc_s, k > 0 ? 1u : 0u);
+        }
         umma_commit(bar_m1);
       }
       __syncwarp();
+      if (TAIL && qc == 0) {
+        // while the MMA runs: P (first thread of the row) and dP (second thread) of this key row against the trailing
+        // queries — thread-local dot products; K / V rows as the MMAs see them, Q rounded like the TMA unit rounds it so
+        // that P matches the forward's statistics
+        mbar_wait(bar_kt, (unsigned)(kt & 1));
+        float kv[32];
+        load_row_km(half ? sVk : sKk, row, kv);
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) {
+          if (i < ntail) {
+            float r[32];
+            float val;
+            if (half == 0) {
+              load_row_global<true>(p.qkv + (tail_row0 + i) * 3 * D + D + h * DH, r);
+              const float sc = fmaf(dot32(kv, r), p.inv_scale, rowmask);
+              val = valid ? exp2f(fmaf(sc, kLog2e, -mxl)) * inv : 0.f;
+            } else {
+              load_row_global<false>(p.dctx + (tail_row0 + i) * D + h * DH, r);
+              val = dot32(kv, r);
+            }
+            tp_s[half][i][row] = val;          // read after the barrier that follows the P pass
+          }
+        }
+      }
       mbar_wait(bar_m1, par);
       tc_fence_after();
-      for (int c = 0; c < nq; c += 16) {
-        float v[16];
-        tmem_ld16(tm_S + lane_off + c, v);
+      {
+        const int cend = min(nq, c0 + 64);
+        for (int c = c0; c < cend; c += 16) {
+          float v[16];
+          tmem_ld16(tm_S + lane_off + c, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = (qc * kTile + c + j < T)
-                     ? to_tf32(exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv) : 0.f;
-        tmem_st16(tm_S + lane_off + c, v);
+          for (int j = 0; j < 16; ++j)
+            v[j] = (TAIL || qc * kTile + c + j < T)
+                       ? to_tf32(exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv) : 0.f;
+          tmem_st16(tm_P + lane_off + c, v);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -426,72 +664,185 @@ __global__ void __launch_bounds__(128, 1)
       if (tid == 0) {
         tc_fence_after();
         for (int j = 0; j < nq / 8; ++j)       // A = P from TMEM (8 query columns per k-step), B = dO MN-major (+8 query rows)
-          umma_tf32_ts(tm_dV, tm_S + j * 8, make_desc(smem_u32(sDOm) + j * 1024, kTileBytes, 512, 1), idesc_ts,
+          umma_tf32_ts(tm_dV, tm_P + j * 8, make_desc(smem_u32(sDOm) + j * 1024, kTileBytes, 512, 1), idesc_ts,
                        (qc > 0 || j > 0) ? 1u : 0u);
         umma_commit(bar_m2);
       }
       __syncwarp();
+      if (TAIL && kt == 0 && qc == NKT - 1) {
+        // while the last dV MMA of the first key tile runs — trailing key rows (thread = query, Q / dO rows straight from
+        // global memory): P from the forward's statistics, dP = V[k*] . dO[q], delta = sum_q P dP, dS = P (dP - delta) / sqrt(d_h);
+        // dV[k*] = sum_q P dO[q] and dK[k*] = sum_q dS Q[q] are block column sums, dQ[q] += dS K[k*] joins the last epilogue
+#pragma unroll 1
+        for (int i = 0; i < ntail; ++i) {                    // CTA-uniform
+          const int ks = (NT - 1) * kTile + i;
+          const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+          const float2 stt = __ldg(reinterpret_cast<const float2*>(p.stats) + ((size_t)(b * p.H + h) * T + ks));
+          const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
+          const float4* vrow = reinterpret_cast<const float4*>(krow + 2 * D);
+          float pv[NQQ], dpv[NQQ];
+          float col[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) col[j] = 0.f;
+          float dl = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < NQQ; ++qq) {
+            const int q = qq * kBwdThreads + tid;
+            pv[qq] = dpv[qq] = 0.f;
+            if (q < T) {
+              float qr[32], dor[32];
+              const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+              const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
+              float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = __ldg(vrow + c);
+                qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
+                dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
+                d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
+                d4[2] = fmaf(v4.z, g4.z, d4[2]); d4[3] = fmaf(v4.w, g4.w, d4[3]);
+              }
+              const float sc = fmaf(dot32_tf32(krow, qr), p.inv_scale, rmask);
+              const float pr = exp2f(fmaf(sc, kLog2e, -stt.x)) * stt.y;
+              const float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+              pv[qq] = pr;
+              dpv[qq] = dp;
+              dl = fmaf(pr, dp, dl);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) col[j] = fmaf(pr, dor[j], col[j]);
+            }
+          }
+          const float delta = block_sum256(dl, red8, tid);
+          const float dv = block_colsum256(col, red, tid);        // dV[k*][lane] in every thread
+#pragma unroll
+          for (int j = 0; j < 32; ++j) col[j] = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < NQQ; ++qq) {
+            const int q = qq * kBwdThreads + tid;
+            const float ds = pv[qq] * ((dpv[qq] - delta) * p.inv_scale);
+            if (q < T) {
+              ds_s[i][q] = ds;
+              const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 q4 = __ldg(qp + c);
+                col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
+                col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
+              }
+            }
+          }
+          const float dk = block_colsum256(col, red, tid);        // dK[k*][lane]
+          if (tid < 32) {
+            const size_t e = ((size_t)b * T + ks) * 3 * D + h * DH + tid;
+            if (p.out_bf16) {
+              unsigned short* o16 = reinterpret_cast<unsigned short*>(p.out);
+              o16[e] = __bfloat16_as_ushort(__float2bfloat16_rn(dk));
+              o16[e + 2 * D] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
+            } else {
+              float* o32 = reinterpret_cast<float*>(p.out);
+              o32[e] = dk;
+              o32[e + 2 * D] = dv;
+            }
+            if (p.dbias) {
+              atomicAdd(p.dbias + 0 * D + h * DH + tid, dk);
+              atomicAdd(p.dbias + 2 * D + h * DH + tid, dv);
+            }
+          }
+        }
+      }
       mbar_wait(bar_m2, par);                  // S and the chunk tiles are free again
       tc_fence_after();
     }
-    // ---------------- delta_k = V_k . dV_k; dV row out
+    // ---------------- delta_k = V_k . dV_k (both threads of the row, over all 32 columns); dV half row out
+    float pt[kTailMax], dpt[kTailMax];         // P / dP of (this key row, trailing query i); below pt = dS
     float delta = 0.f;
     {
       float o[32];
       tmem_ld16(tm_dV + lane_off, o);
       tmem_ld16(tm_dV + lane_off + 16, o + 16);
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i) {
+        pt[i] = dpt[i] = 0.f;
+        if (i < ntail) {                       // dV_k += P[k][q*] dO[q*]
+          pt[i] = tp_s[0][i][row];
+          dpt[i] = tp_s[1][i][row];
+          const float4* gp = reinterpret_cast<const float4*>(p.dctx + (tail_row0 + i) * D + h * DH);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 g4 = __ldg(gp + c);
+            o[4 * c] = fmaf(pt[i], g4.x, o[4 * c]); o[4 * c + 1] = fmaf(pt[i], g4.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(pt[i], g4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pt[i], g4.w, o[4 * c + 3]);
+          }
+        }
+      }
       // V row of this key from the K-major SWIZZLE_128B tile (as the MMAs saw it: TF32-rounded by TMA)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 v4 = *reinterpret_cast<const float4*>(sVk + tid * 128 + ((c ^ (tid & 7)) << 4));
+        const float4 v4 = *reinterpret_cast<const float4*>(sVk + row * 128 + ((c ^ (row & 7)) << 4));
         delta = fmaf(v4.x, o[4 * c], delta);
         delta = fmaf(v4.y, o[4 * c + 1], delta);
         delta = fmaf(v4.z, o[4 * c + 2], delta);
         delta = fmaf(v4.w, o[4 * c + 3], delta);
       }
       if (valid) {
-        store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + 2 * D + h * DH, o);
+        if (half == 0) {
+          store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + 2 * D + h * DH, o, 16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc_v[j] += o[j];
+          for (int j = 0; j < 16; ++j) acc_v[j] += o[j];
+        } else {
+          store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + 2 * D + h * DH + 16, o + 16, 16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc_v[j] += o[16 + j];
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((dpt[i] - delta) * p.inv_scale);   // dS[k][q*]
     // ---------------- phase 2: dK += dS Q, dQ[chunk] += dS^T K
-    for (int qc = 0; qc < NT; ++qc, ++step) {
+#pragma unroll 1
+    for (int qc = 0; qc < NKT; ++qc, ++step) {
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-      if (tid == 0) {
-        mbar_expect_tx(bar_qc, (unsigned)(3 * kTileBytes));
-        tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
-        tma_load_2d(sQm, &tmMn, bar_qc, D + h * DH, b * T + qc * kTile);
-        tma_load_2d(sDOk, &tmDOk, bar_qc, h * DH, b * T + qc * kTile);
-        mbar_wait(bar_qc, par);
+      if (!SINGLE) {
+        if (tid == 0) {
+          mbar_expect_tx(bar_qc, (unsigned)(3 * kTileBytes));
+          tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
+          tma_load_2d(sQm, &tmMn, bar_qc, D + h * DH, b * T + qc * kTile);
+          tma_load_2d(sDOk, &tmDOk, bar_qc, h * DH, b * T + qc * kTile);
+          mbar_wait(bar_qc, par);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T and dP = V dO^T, two independent chains
+            umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
+                      idesc_s, k > 0 ? 1u : 0u);
+            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
+                      idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_m1);
+        }
+        __syncwarp();
+        mbar_wait(bar_m1, par);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T and dP = V dO^T, two independent chains
-          umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
-                    idesc_s, k > 0 ? 1u : 0u);
-          umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
-                    idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(bar_m1);
       }
-      __syncwarp();
-      mbar_wait(bar_m1, par);
-      tc_fence_after();
-      for (int c = 0; c < nq; c += 16) {
-        float v[16], g[16];
-        tmem_ld16(tm_S + lane_off + c, v);
-        tmem_ld16(tm_dP + lane_off + c, g);
+      {
+        const int cend = min(nq, c0 + 64);
+        for (int c = c0; c < cend; c += 16) {
+          float v[16], g[16];
+          tmem_ld16_issue(tm_S + lane_off + c, v);
+          tmem_ld16_issue(tm_dP + lane_off + c, g);
+          tmem_ld16_wait(v);
+          tmem_ld16_wait(g);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float pr = (qc * kTile + c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f;
-          g[j] = to_tf32(pr * ((g[j] - delta) * p.inv_scale));      // dS
+          for (int j = 0; j < 16; ++j) {
+            const float pr = (TAIL || qc * kTile + c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f;
+            g[j] = to_tf32(pr * ((g[j] - delta) * p.inv_scale));      // dS
+          }
+          tmem_st16(tm_dP + lane_off + c, g);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(sY + mn_major_off(c + j, row, kTile)) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
         }
-        tmem_st16(tm_dP + lane_off + c, g);
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(sY + mn_major_off(c + j, tid, kTile)) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
       }
       tmem_st_wait();
       fence_async_smem();
@@ -508,138 +859,81 @@ __global__ void __launch_bounds__(128, 1)
         umma_commit(bar_m2);
       }
       __syncwarp();
+      if (TAIL && qc == NKT - 1) {
+        // while the last MMAs of the key tile run: dQ[q*] += sum over this tile's keys of dS[k][q*] K[k]; the first
+        // threads of the rows take the even trailing queries, the second threads the odd ones
+        float kr[32];
+        load_row_km(sKk, row, kr);
+#pragma unroll
+        for (int ii = 0; ii < kTailMax / 2; ++ii) {
+          if (2 * ii < ntail) {                // CTA-uniform
+            const float a = (half == 0) ? pt[2 * ii] : pt[2 * ii + 1];     // 0 beyond ntail
+            float c[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[j] = a * kr[j];
+            dqt[ii] += half_colsum128(c, red, tid);
+          }
+        }
+      }
       mbar_wait(bar_m2, par);
       tc_fence_after();
     }
     {
-      float o[32];
-      tmem_ld16(tm_dK + lane_off, o);
-      tmem_ld16(tm_dK + lane_off + 16, o + 16);
-      if (valid) {
-        store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + h * DH, o);
+      float o[16];
+      tmem_ld16(tm_dK + lane_off + h16, o);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc_k[j] += o[j];
+      for (int i = 0; i < kTailMax; ++i)
+        if (i < ntail) axpy16_global(pt[i], p.qkv + (tail_row0 + i) * 3 * D + D + h * DH + h16, o);   // dK_k += dS[k][q*] Q[q*]
+      if (valid) {
+        store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + h * DH + h16, o, 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc_k[j] += o[j];
       }
     }
     tc_fence_before();
     __syncthreads();                           // every thread has read dV / dK before the next key tile overwrites them
     tc_fence_after();
   }
-  // trailing key rows (thread = query, Q / dO rows straight from global memory): P from the forward's statistics,
-  // dP = V[k*] . dO[q], delta = sum_q P dP, dS = P (dP - delta) / sqrt(d_h); dV[k*] = sum_q P dO[q] and dK[k*] = sum_q dS Q[q]
-  // are block column sums, dQ[q] += dS K[k*] joins the epilogue below
-  float dst[NT][kTailMax];
+  if (TAIL) {
+    if (quarter == 0) {
 #pragma unroll
-  for (int i = 0; i < kTailMax; ++i) {
-    if (i < ntail) {                                 // CTA-uniform
-      const int ks = (NT - 1) * kTile + i;
-      const float rowmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
-      const float2 stt = __ldg(reinterpret_cast<const float2*>(p.stats) + ((size_t)(b * p.H + h) * T + ks));
-      const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
-      const float4* vrow = reinterpret_cast<const float4*>(krow + 2 * D);
-      float pv[NT], dpv[NT];
-      float col[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) col[j] = 0.f;
-      float dl = 0.f;
-#pragma unroll
-      for (int qc = 0; qc < NT; ++qc) {
-        const int q = qc * kTile + tid;
-        pv[qc] = dpv[qc] = 0.f;
-        if (q < T) {
-          float qr[32], dor[32];
-          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
-          const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
-          float d4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = __ldg(vrow + c);
-            qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
-            dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
-            d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
-            d4[2] = fmaf(v4.z, g4.z, d4[2]); d4[3] = fmaf(v4.w, g4.w, d4[3]);
-          }
-          const float sc = fmaf(dot32_tf32(krow, qr), p.inv_scale, rowmask);
-          const float pr = exp2f(fmaf(sc, kLog2e, -stt.x)) * stt.y;
-          const float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-          pv[qc] = pr;
-          dpv[qc] = dp;
-          dl = fmaf(pr, dp, dl);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) col[j] = fmaf(pr, dor[j], col[j]);
-        }
-      }
-      const float delta = block_sum128(dl, red, tid);
-      const float dv = block_colsum128(col, red, tid);        // dV[k*][tid & 31] in every thread
-#pragma unroll
-      for (int j = 0; j < 32; ++j) col[j] = 0.f;
-#pragma unroll
-      for (int qc = 0; qc < NT; ++qc) {
-        const int q = qc * kTile + tid;
-        const float ds = pv[qc] * ((dpv[qc] - delta) * p.inv_scale);
-        dst[qc][i] = ds;
-        if (q < T) {
-          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 q4 = __ldg(qp + c);
-            col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
-            col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
-          }
-        }
-      }
-      const float dk = block_colsum128(col, red, tid);        // dK[k*][tid & 31]
-      if (tid < 32) {
-        const size_t e = ((size_t)b * T + ks) * 3 * D + h * DH + tid;
-        if (p.out_bf16) {
-          unsigned short* o16 = reinterpret_cast<unsigned short*>(p.out);
-          o16[e] = __bfloat16_as_ushort(__float2bfloat16_rn(dk));
-          o16[e + 2 * D] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
-        } else {
-          float* o32 = reinterpret_cast<float*>(p.out);
-          o32[e] = dk;
-          o32[e + 2 * D] = dv;
-        }
-        if (p.dbias) {
-          atomicAdd(p.dbias + 0 * D + h * DH + tid, dk);
-          atomicAdd(p.dbias + 2 * D + h * DH + tid, dv);
-        }
-      }
+      for (int ii = 0; ii < kTailMax / 2; ++ii) dq_s[2 * ii + half][lane] = dqt[ii];
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int qc = 0; qc < NT; ++qc) {
-    const int q = qc * kTile + tid;            // lanes = queries
-    float o[32];
-    tmem_ld16(tm_dQ + lane_off + qc * DH, o);
-    tmem_ld16(tm_dQ + lane_off + qc * DH + 16, o + 16);
+    const int q = qc * kTile + row;            // lanes = queries
+    float o[16];
+    if (qc < NKT) {
+      tmem_ld16(tm_dQ + lane_off + qc * DH + h16, o);
+    } else {                                   // the trailing queries' rows: the threads of rows 0 .. ntail-1
 #pragma unroll
-    for (int i = 0; i < kTailMax; ++i) {
-      if (i < ntail) {                         // dQ[q] += dS[k*][q] K[k*]
-        const float4* kp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + (NT - 1) * kTile + i) * 3 * D + h * DH);
-        const float ds = dst[qc][i];
+      for (int j = 0; j < 16; ++j) o[j] = dq_s[row & (kTailMax - 1)][h16 + j];
+    }
+    if (TAIL && q < T) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 k4 = __ldg(kp + c);
-          o[4 * c] = fmaf(ds, k4.x, o[4 * c]); o[4 * c + 1] = fmaf(ds, k4.y, o[4 * c + 1]);
-          o[4 * c + 2] = fmaf(ds, k4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(ds, k4.w, o[4 * c + 3]);
-        }
-      }
+      for (int i = 0; i < kTailMax; ++i)       // dQ[q] += dS[k*][q] K[k*]
+        if (i < ntail) axpy16_global(ds_s[i][q], p.qkv + (tail_row0 + i) * 3 * D + h * DH + h16, o);
     }
     if (q < T) {
-      store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * 3 * D + D + h * DH, o);
+      store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * 3 * D + D + h * DH + h16, o, 16);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc_q[j] += o[j];
+      for (int j = 0; j < 16; ++j) acc_q[j] += o[j];
     }
   }
   if (p.dbias) {
-    red[0 * 128 + tid] = warp_colsum32(acc_k, tid & 31);
-    red[1 * 128 + tid] = warp_colsum32(acc_q, tid & 31);
-    red[2 * 128 + tid] = warp_colsum32(acc_v, tid & 31);
+    const float sk = warp_colsum16(acc_k, lane), sq = warp_colsum16(acc_q, lane), sv = warp_colsum16(acc_v, lane);
+    if (lane < 16) {
+      red_b[0][warp][lane] = sk;
+      red_b[1][warp][lane] = sq;
+      red_b[2][warp][lane] = sv;
+    }
     __syncthreads();
     if (tid < 96) {
-      const int m = tid >> 5, c = tid & 31;
-      atomicAdd(p.dbias + m * D + h * DH + c, red[m * 128 + c] + red[m * 128 + 32 + c] + red[m * 128 + 64 + c] + red[m * 128 + 96 + c]);
+      const int m = tid >> 5, c = tid & 31, w0 = (c >> 4) * 4;
+      atomicAdd(p.dbias + m * D + h * DH + c,
+                (red_b[m][w0][c & 15] + red_b[m][w0 + 1][c & 15]) + (red_b[m][w0 + 2][c & 15] + red_b[m][w0 + 3][c & 15]));
     }
   }
   tc_fence_before();
@@ -648,6 +942,9 @@ __global__ void __launch_bounds__(128, 1)
 }
 
 constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBytes + 128; }
+constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
+// score columns on the tensor path
+inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t kBwdSmem = 1024 + (size_t)(7 + 4) * kTileBytes + 128;
 
 }  // namespace
@@ -666,20 +963,28 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
   AttnLongParams p;
   p.qkv = qkv; p.dctx = nullptr;
   p.mask = mask; p.stats = stats; p.out = ctx; p.out_bf16 = ctx_bf16 ? 1 : 0; p.dbias = nullptr;
-  p.T = T; p.H = H; p.TQ = (T + 15) / 16 * 16; p.inv_scale = 1.f / sqrtf((float)DH);
+  p.T = T; p.H = H; p.TQ = tensor_queries(T); p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;
   CUtensorMap tk, tm;
   int rc;
   if ((rc = make_map(&tk, qkv, rows, 3 * D, 3 * D, DH, kTile, false))) return rc;
   if ((rc = make_map(&tm, qkv, rows, 3 * D, 3 * D, DH, kTile, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+#define MSX_TCL_FWD(NT_, NKT_, ALIAS_, SMEM_)                                                                              \
+  do {                                                                                                                   \
+    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                  (int)(SMEM_)));                                                                        \
+    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, dim3(B * H), dim3(128), (SMEM_), st, tk, tm, p));         \
+  } while (0)
+  const bool tail = tail_keys(T) != 0;
   if (T <= 2 * kTile) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(2)));
-    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<2>, dim3(B * H), dim3(128), fwd_smem(2), st, tk, tm, p));
+    if (tail) MSX_TCL_FWD(2, 1, true, kFwdAliasSmem);  // T = 129 ... 132: one tile on the tensor path, two CTAs per SM
+    else MSX_TCL_FWD(2, 2, false, fwd_smem(2));
   } else {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(3)));
-    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<3>, dim3(B * H), dim3(128), fwd_smem(3), st, tk, tm, p));
+    if (tail) MSX_TCL_FWD(3, 2, false, fwd_smem(3));   // T = 257 ... 260
+    else MSX_TCL_FWD(3, 3, false, fwd_smem(3));
   }
+#undef MSX_TCL_FWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }
@@ -695,7 +1000,7 @@ extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const 
   AttnLongParams p;
   p.qkv = qkv; p.dctx = dctx;
   p.mask = mask; p.stats = const_cast<float*>(stats); p.out = dqkv; p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias;
-  p.T = T; p.H = H; p.TQ = (T + 15) / 16 * 16; p.inv_scale = 1.f / sqrtf((float)DH);
+  p.T = T; p.H = H; p.TQ = tensor_queries(T); p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;
   CUtensorMap tk, tm, tdk, tdm;
   int rc;
@@ -704,13 +1009,22 @@ extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const 
   if ((rc = make_map(&tdk, dctx, rows, D, D, DH, kTile, false))) return rc;
   if ((rc = make_map(&tdm, dctx, rows, D, D, DH, kTile, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+#define MSX_TCL_BWD(NT_, NKT_, SINGLE_)                                                                                     \
+  do {                                                                                                                   \
+    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)kBwdSmem));                                                                       \
+    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_>, dim3(B * H), dim3(kBwdThreads), kBwdSmem, st, tk, tm,   \
+                        tdk, tdm, p));                                                                                   \
+  } while (0)
+  const bool tail = tail_keys(T) != 0;
   if (T <= 2 * kTile) {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<2>, dim3(B * H), dim3(128), kBwdSmem, st, tk, tm, tdk, tdm, p));
+    if (tail) MSX_TCL_BWD(2, 1, true);                 // T = 129 ... 132: one tile on the tensor path
+    else MSX_TCL_BWD(2, 2, false);
   } else {
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<3>, dim3(B * H), dim3(128), kBwdSmem, st, tk, tm, tdk, tdm, p));
+    if (tail) MSX_TCL_BWD(3, 2, false);                // T = 257 ... 260
+    else MSX_TCL_BWD(3, 3, false);
   }
+#undef MSX_TCL_BWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
 }

@@ -1,0 +1,14 @@
+import sys, os
+sys.path.insert(0, "/root/repo")
+import torch
+from musicstyletransfer_b200 import ops
+H, dh, T = 8, 32, int(sys.argv[1]) if len(sys.argv) > 1 else 129
+D = H * dh
+B = 2048 * 129 // T
+qkv = torch.randn(B * T, 3 * D, device="cuda"); mask = torch.ones(B * T, device="cuda"); dctx = torch.randn(B * T, D, device="cuda")
+ctx = torch.empty(B * T, D, device="cuda"); dqkv = torch.empty(B * T, 3 * D, device="cuda"); db = torch.zeros(3 * D, device="cuda")
+stats = torch.zeros(B * H * T, 2, device="cuda")
+for _ in range(2):
+    ops.attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh)
+    ops.attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=db)
+torch.cuda.synchronize()
