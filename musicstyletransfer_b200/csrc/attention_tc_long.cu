@@ -64,38 +64,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// all-thread max / sum over the 128 threads of the CTA through red[4] (two barriers: the result is read before the next use)
-__device__ __forceinline__ float block_max128(float v, float* red, int tid) {
-  v = warp_max(v);
-  if ((tid & 31) == 0) red[tid >> 5] = v;
-  __syncthreads();
-  v = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  return v;
-}
-__device__ __forceinline__ float block_sum128(float v, float* red, int tid) {
-  v = warp_sum(v);
-  if ((tid & 31) == 0) red[tid >> 5] = v;
-  __syncthreads();
-  v = (red[0] + red[1]) + (red[2] + red[3]);
-  __syncthreads();
-  return v;
-}
-// column sums of a [128 threads x 32] register matrix: afterwards every thread holds the total of column (tid & 31)
-__device__ __forceinline__ float block_colsum128(float (&v)[32], float* red /* [128] */, int tid) {
-  red[tid] = warp_colsum32(v, tid & 31);
-  __syncthreads();
-  const int c = tid & 31;
-  const float t = (red[c] + red[32 + c]) + (red[64 + c] + red[96 + c]);
-  __syncthreads();
-  return t;
-}
-// 32-long dot product of a TF32-rounded K row (global, the same address for every thread: an L1 broadcast) with a query row
+// 32-long dot product of a K row (shared memory, the same address for every thread: a broadcast; rounded to TF32 here) with a query row
 __device__ __forceinline__ float dot32_tf32(const float* __restrict__ krow, const float (&q)[32]) {
   float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 k4 = __ldg(reinterpret_cast<const float4*>(krow) + c);
+    const float4 k4 = *(reinterpret_cast<const float4*>(krow) + c);
     d4[0] = fmaf(to_tf32(k4.x), q[4 * c], d4[0]);
     d4[1] = fmaf(to_tf32(k4.y), q[4 * c + 1], d4[1]);
     d4[2] = fmaf(to_tf32(k4.z), q[4 * c + 2], d4[2]);
@@ -132,320 +106,34 @@ __device__ __forceinline__ void load_row_mn(const unsigned char* tile, int r, fl
     v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
   }
 }
-// a 32-float row of global memory (the same address for every thread: a broadcast), optionally rounded to TF32
-template <bool ROUND>
-__device__ __forceinline__ void load_row_global(const float* row, float (&v)[32]) {
+// a 32-float row held in shared memory (the same address for every thread: a broadcast)
+__device__ __forceinline__ void load_row32(const float* row, float (&v)[32]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(row) + c);
-    v[4 * c] = ROUND ? to_tf32(x.x) : x.x; v[4 * c + 1] = ROUND ? to_tf32(x.y) : x.y;
-    v[4 * c + 2] = ROUND ? to_tf32(x.z) : x.z; v[4 * c + 3] = ROUND ? to_tf32(x.w) : x.w;
+    const float4 x = *(reinterpret_cast<const float4*>(row) + c);
+    v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+  }
+}
+// The rows of the trailing positions, fetched once per (batch, head) into shared memory when the kernel starts (their
+// DRAM / L2 latency hides behind the first TMA loads): [0] Q rounded to TF32, [1] Q, [2] dO (backward), [3] K, [4] V
+enum { kTrQt = 0, kTrQ = 1, kTrDO = 2, kTrK = 3, kTrV = 4 };
+template <int NWARPS>
+__device__ __forceinline__ void fetch_tail_rows(float (*tr)[kTailMax][32], const float* qkv, const float* dctx, size_t row0, int ntail,
+                                                int D, int h, int warp, int lane) {
+  for (int r = warp; r < 5 * ntail; r += NWARPS) {
+    const int ty = r / ntail, i = r - ty * ntail;
+    const size_t pos = row0 + i;
+    float v = 0.f;
+    if (ty == kTrQt) v = to_tf32(__ldg(qkv + pos * 3 * D + D + h * DH + lane));
+    else if (ty == kTrQ) v = __ldg(qkv + pos * 3 * D + D + h * DH + lane);
+    else if (ty == kTrDO) v = dctx ? __ldg(dctx + pos * D + h * DH + lane) : 0.f;
+    else if (ty == kTrK) v = __ldg(qkv + pos * 3 * D + h * DH + lane);
+    else v = __ldg(qkv + pos * 3 * D + 2 * D + h * DH + lane);
+    tr[ty][i][lane] = v;
   }
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-// ALIAS (T = 129 ... 132: one key tile x one query chunk on the tensor path): P staging (single buffer) lies over the Q / K
-// tiles, 256 TMEM columns, 81 KB of shared memory: two CTAs per SM.
-template <int NT, int NKT, bool ALIAS>
-__global__ void __launch_bounds__(128, ALIAS ? 2 : 1)
-    attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
-                        const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
-                        const AttnLongParams p) {
-  pdl_entry();
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sQ = base;                          // NT K-major tiles: all queries of the (batch, head)
-  unsigned char* sK = sQ + NT * kTileBytes;          // K-major key tile
-  unsigned char* sV = ALIAS ? base + 4 * kTileBytes : sK + kTileBytes;   // MN-major value tile (d contiguous, 128 key rows)
-  // P chunk, q contiguous, 4 slabs of 128 key rows; two buffers, or ONE lying over sQ / sK (dead once MMA 1 has retired)
-  unsigned char* sP = ALIAS ? base : sV + kTileBytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ALIAS ? sV + kTileBytes : sP + 2 * 4 * kTileBytes);
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
-  unsigned long long* bar_q = &bars[0];
-  unsigned long long* bar_k = &bars[1];
-  unsigned long long* bar_v = &bars[2];
-  unsigned long long* bar_s = &bars[3];
-  unsigned long long* bar_o = &bars[4];              // [2]
-  constexpr int kTmemCols = ALIAS ? 256 : 512;
-  static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
-  static_assert(!ALIAS || (NT == 2 && NKT == 1), "ALIAS: one full tile + trailing positions");
-  constexpr bool TAIL = NKT < NT;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int T = p.T, TQ = p.TQ, D = p.H * DH;
-  const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
-  constexpr int nkt = NKT;                           // key tiles = query chunks on the tensor path (NT = ceil(T / 128))
-  __shared__ float red_t[4];
-  __shared__ float red_c[128];
-  __shared__ float ot_s[kTailMax][32];
-
-  if (!ALIAS) {
-    // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
-    for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += 128 * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_async_smem();
-  }
-  if (tid == 0) {
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const unsigned tmem = *tmem_slot;
-  const unsigned tm_O = tmem, tm_S = tmem + 128;     // O: 32 columns per query chunk; S: up to 384 columns (ALIAS: 128)
-  const unsigned lane_off = (unsigned)(warp * 32) << 16;
-  // MMA 2: A = P^T MN-major (queries contiguous), B = V MN-major (d contiguous), M = 128 queries, N = 32
-  const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
-                          ((unsigned)(128 >> 4) << 24);
-
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, (unsigned)(NT * kTileBytes));
-    for (int qc = 0; qc < NT; ++qc) tma_load_2d(sQ + qc * kTileBytes, &tmKm, bar_q, D + h * DH, b * T + qc * kTile);
-    mbar_expect_tx(bar_k, (unsigned)kTileBytes);
-    tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T);
-    mbar_expect_tx(bar_v, (unsigned)kTileBytes);
-    tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
-  }
-  float ptail[NT][kTailMax];                          // P[trailing key i][this thread's query of chunk qc]
-  float ot[kTailMax];                                 // O[trailing query i][column tid & 31], summed over the key tiles
-#pragma unroll
-  for (int i = 0; i < kTailMax; ++i) ot[i] = 0.f;
-  int n = 0;                                          // running (key tile, query chunk) counter: P buffer = n & 1
-  for (int kt = 0; kt < nkt; ++kt) {
-    const unsigned par = (unsigned)(kt & 1);
-    if (tid == 0) {
-      if (kt == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, par);
-      tc_fence_after();
-      // MMA 1: S[128 keys x TQ] = K Q^T in query chunks of <= 128 columns (both operands K-major, +32 B per k-step)
-      for (int qc = 0; qc < nkt; ++qc) {
-        const int nq = min(kTile, TQ - qc * kTile);
-        const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-#pragma unroll
-        for (int k = 0; k < DH / 8; ++k)
-          umma_tf32(tm_S + qc * kTile, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2),
-                    make_desc(smem_u32(sQ) + qc * kTileBytes + k * 32, 16, 1024, 2), idesc1, k > 0 ? 1u : 0u);
-      }
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    const int kg = kt * kTile + tid;                  // this thread's key row
-    const bool valid = kg < T;
-    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
-    // while MMA 1 runs: this key row's scores against the trailing queries (rows 0 .. ntail-1 of the last Q tile) and,
-    // once per item, the trailing KEY rows (thread = query; independent of the tensor path)
-    float st[kTailMax];
-#pragma unroll
-    for (int i = 0; i < kTailMax; ++i) st[i] = 0.f;
-    if (TAIL) {
-      if (kt == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, par);
-      {
-        float kr[32];
-        load_row_km(sK, tid, kr);
-#pragma unroll
-        for (int i = 0; i < kTailMax; ++i) {
-          if (i < ntail) {
-            float qr[32];
-            load_row_km(sQ + (NT - 1) * kTileBytes, i, qr);
-            st[i] = fmaf(dot32(kr, qr), p.inv_scale, rowmask);
-          }
-        }
-      }
-      if (kt == 0) {
-        // trailing key rows: scores of key k* against this thread's queries (rows of the resident, TF32-rounded Q tiles),
-        // softmax over the query axis across the CTA, P[k*][q] kept for the rank-1 update of the output rows
-#pragma unroll
-        for (int i = 0; i < kTailMax; ++i) {
-          if (i < ntail) {
-            const int ks = (NT - 1) * kTile + i;
-            const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
-            const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
-            float sc[NT];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int qc = 0; qc < NT; ++qc) {
-              float qr[32];
-              load_row_km(sQ + qc * kTileBytes, tid, qr);
-              sc[qc] = fmaf(dot32_tf32(krow, qr), p.inv_scale, rmask);
-              if (qc * kTile + tid < T) mx = fmaxf(mx, sc[qc]);
-            }
-            const float mxl = block_max128(mx, red_t, tid) * kLog2e;
-            float sum = 0.f;
-#pragma unroll
-            for (int qc = 0; qc < NT; ++qc) {
-              sc[qc] = (qc * kTile + tid < T) ? exp2f(fmaf(sc[qc], kLog2e, -mxl)) : 0.f;
-              sum += sc[qc];
-            }
-            const float inv = 1.f / block_sum128(sum, red_t, tid);
-#pragma unroll
-            for (int qc = 0; qc < NT; ++qc) ptail[qc][i] = sc[qc] * inv;
-            if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
-          }
-        }
-      }
-      __syncthreads();                                // every thread has read its K / Q rows: the tiles may be reused
-    }
-    mbar_wait(bar_s, par);
-    tc_fence_after();
-    if (tid == 0 && kt + 1 < nkt) {                   // the K tile is free once MMA 1 has retired
-      mbar_expect_tx(bar_k, (unsigned)kTileBytes);
-      tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
-    }
-    // pass 1: row maximum over the T queries
-    float mx = -INFINITY;
-    for (int c = 0; c < TQ; c += 16) {
-      float v[16];
-      tmem_ld16(tm_S + lane_off + c, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (TAIL || c + j < T) mx = fmaxf(mx, fmaf(v[j], p.inv_scale, rowmask));
-    }
-#pragma unroll
-    for (int i = 0; i < kTailMax; ++i)
-      if (i < ntail) mx = fmaxf(mx, st[i]);
-    const float mxl = mx * kLog2e;
-    // pass 2: e = exp2(s * log2 e - max * log2 e) back into TMEM, row sum
-    float sum = 0.f;
-    for (int c = 0; c < TQ; c += 16) {
-      float v[16];
-      tmem_ld16(tm_S + lane_off + c, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = (TAIL || c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) : 0.f;
-        sum += v[j];
-      }
-      tmem_st16(tm_S + lane_off + c, v);
-    }
-#pragma unroll
-    for (int i = 0; i < kTailMax; ++i) {
-      if (i < ntail) {
-        st[i] = exp2f(fmaf(st[i], kLog2e, -mxl));
-        sum += st[i];
-      }
-    }
-    tmem_st_wait();
-    const float inv = valid ? 1.f / sum : 0.f;        // rows beyond T (neighbouring sequence / zeros) contribute nothing
-    if (valid) {
-      float2* stp = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
-      *stp = make_float2(mxl, inv);
-    }
-    // pass 3: normalised row -> shared memory, one query chunk at a time, each chunk followed by its MMA 2
-    for (int qc = 0; qc < nkt; ++qc, ++n) {
-      const int buf = ALIAS ? 0 : (n & 1);
-      unsigned char* pb = sP + buf * 4 * kTileBytes;
-      if (n >= 2) {                                    // the MMA that read this buffer two chunks ago has retired
-        mbar_wait(&bar_o[buf], (unsigned)(((n >> 1) - 1) & 1));
-        tc_fence_after();
-      }
-      const int nq = min(kTile, TQ - qc * kTile);
-      for (int c = 0; c < nq; c += 16) {
-        float v[16];
-        tmem_ld16(tm_S + lane_off + qc * kTile + c, v);
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(pb + mn_major_off(c + j, tid, kTile)) =
-              make_float4(to_tf32(v[j] * inv), to_tf32(v[j + 1] * inv), to_tf32(v[j + 2] * inv), to_tf32(v[j + 3] * inv));
-      }
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        if (qc == 0) mbar_wait(bar_v, par);
-        // MMA 2: O[chunk][128 queries x 32] += P^T[128 q x 128 keys] V[128 keys x 32], 16 k-steps of 8 key rows
-        for (int j = 0; j < kTile / 8; ++j)
-          umma_tf32(tm_O + qc * DH, make_desc(smem_u32(pb) + j * 1024, kTileBytes, 512, 1),
-                    make_desc(smem_u32(sV) + j * 1024, kTileBytes, 512, 1), idesc2, (kt > 0 || j > 0) ? 1u : 0u);
-        umma_commit(&bar_o[buf]);
-      }
-      __syncwarp();
-    }
-    if (TAIL) {
-      // while the MMA 2s run: O[q*] += sum over this tile's keys of P[k][q*] V[k] (V row as the MMA sees it)
-      mbar_wait(bar_v, par);
-      float vr[32];
-      load_row_mn(sV, tid, vr);
-#pragma unroll
-      for (int i = 0; i < kTailMax; ++i) {
-        if (i < ntail) {
-          const float pt = st[i] * inv;
-          float c[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) c[j] = pt * vr[j];
-          ot[i] += block_colsum128(c, red_c, tid);      // ends with a barrier: every thread has read its V row
-        }
-      }
-    }
-    if (tid == 0 && kt + 1 < nkt) {                   // V tile is free once the last MMA 2 of this key tile has retired
-      const int last = n - 1;
-      mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
-      mbar_expect_tx(bar_v, (unsigned)kTileBytes);
-      tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
-    }
-    __syncwarp();
-  }
-  {
-    const int last = n - 1;                            // commits complete in order: the last one covers every MMA
-    mbar_wait(&bar_o[ALIAS ? 0 : (last & 1)], (unsigned)((last >> 1) & 1));
-    tc_fence_after();
-  }
-  if (TAIL) {
-    if (tid < 32) {
-#pragma unroll
-      for (int i = 0; i < kTailMax; ++i) ot_s[i][tid] = ot[i];
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int qc = 0; qc < NT; ++qc) {
-    const int q = qc * kTile + tid;                    // lanes = queries
-    float o[32];
-    if (qc < nkt) {
-      tmem_ld16(tm_O + lane_off + qc * DH, o);
-      tmem_ld16(tm_O + lane_off + qc * DH + 16, o + 16);
-    } else {                                           // the trailing queries' rows: threads 0 .. ntail-1
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = ot_s[tid & (kTailMax - 1)][j];
-    }
-#pragma unroll
-    for (int i = 0; i < kTailMax; ++i) {
-      if (i < ntail) {                                 // O[q] += P[k*][q] V[k*]
-        const float4* vp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + (NT - 1) * kTile + i) * 3 * D + 2 * D + h * DH);
-        const float pt = ptail[qc][i];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v4 = __ldg(vp + c);
-          o[4 * c] = fmaf(pt, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pt, v4.y, o[4 * c + 1]);
-          o[4 * c + 2] = fmaf(pt, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pt, v4.w, o[4 * c + 3]);
-        }
-      }
-    }
-    if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH, o);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------ backward
-// 256 threads: warps w and w + 4 share the TMEM lane quarter w & 3 (a warp reaches lanes 32 (w % 4) ... + 31), i.e. two
-// threads own one key row (one query row in the dQ epilogue) and split its columns — 64 + 64 score columns in the P and dS
-// passes, 16 + 16 head columns in the row epilogues.  The kernel is bound by the instruction stream of the row owners
-// (ncu, 128-thread version: 6.8 k instructions per warp and item at 18 % issue utilisation, one warp per scheduler), so
-// halving the columns per thread halves the critical path.
-//
-// NKT = key tiles = query chunks on the tensor path (NT, or NT - 1 when T = 128 (NT - 1) + 1 ... 4: trailing positions).
-// SINGLE (NT = 2, NKT = 1: T = 129 ... 132): the seven operand tiles are loaded once, S = K Q^T and dP = V dO^T are issued
-// together, P goes to its own TMEM columns so that S survives for the dS pass: one TMA round trip and three MMA round trips
-// per (batch, head) instead of four and eight.
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 256, kFwdThreads = 256;
 
 __device__ __forceinline__ float block_sum256(float v, float* red8, int tid) {
   v = warp_sum(v);
@@ -461,6 +149,18 @@ __device__ __forceinline__ float block_colsum256(float (&v)[32], float* red /* [
   __syncthreads();
   const int c = tid & 31;
   const float t = ((red[c] + red[32 + c]) + (red[64 + c] + red[96 + c])) + ((red[128 + c] + red[160 + c]) + (red[192 + c] + red[224 + c]));
+  __syncthreads();
+  return t;
+}
+// block_colsum256 and block_sum256 of a second value behind one pair of barriers
+__device__ __forceinline__ float block_colsum256_sum(float (&v)[32], float x, float* red /* [256] */, float* red8, int tid, float* xsum) {
+  red[tid] = warp_colsum32(v, tid & 31);
+  x = warp_sum(x);
+  if ((tid & 31) == 0) red8[tid >> 5] = x;
+  __syncthreads();
+  const int c = tid & 31;
+  const float t = ((red[c] + red[32 + c]) + (red[64 + c] + red[96 + c])) + ((red[128 + c] + red[160 + c]) + (red[192 + c] + red[224 + c]));
+  *xsum = ((red8[0] + red8[1]) + (red8[2] + red8[3])) + ((red8[4] + red8[5]) + (red8[6] + red8[7]));
   __syncthreads();
   return t;
 }
@@ -487,16 +187,350 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
-// 16 consecutive floats of a global row (same address for the threads of a warp: a broadcast)
-__device__ __forceinline__ void axpy16_global(float a, const float* row16, float (&o)[16]) {
+// o += a * (16 consecutive floats of a row held in shared memory; the same address for the threads of a warp: a broadcast)
+__device__ __forceinline__ void axpy16(float a, const float* row16, float (&o)[16]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(row16) + c);
+    const float4 x = *(reinterpret_cast<const float4*>(row16) + c);
     o[4 * c] = fmaf(a, x.x, o[4 * c]); o[4 * c + 1] = fmaf(a, x.y, o[4 * c + 1]);
     o[4 * c + 2] = fmaf(a, x.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(a, x.w, o[4 * c + 3]);
   }
 }
 
+__device__ __forceinline__ float block_max256(float v, float* red8, int tid) {
+  v = warp_max(v);
+  if ((tid & 31) == 0) red8[tid >> 5] = v;
+  __syncthreads();
+  v = fmaxf(fmaxf(fmaxf(red8[0], red8[1]), fmaxf(red8[2], red8[3])), fmaxf(fmaxf(red8[4], red8[5]), fmaxf(red8[6], red8[7])));
+  __syncthreads();
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// 256 threads: warps w and w + 4 share the TMEM lane quarter w & 3, i.e. two threads own one key row (one query row in the
+// epilogue) and split its columns — the two 64-column halves of every 128-wide query chunk in the three softmax passes
+// (partial row maxima / sums meet in shared memory), 16 + 16 head columns in the output rows.  As in the backward, the
+// kernel is bound by the instruction stream of the row owners, not by the tensor pipe or HBM.
+// NKT = key tiles = query chunks on the tensor path (NT, or NT - 1 with trailing positions).
+// ALIAS (NT = 2, NKT = 1: T = 129 ... 132, one key tile x one query chunk on the tensor path): P staging (single buffer)
+// lies over the Q / K tiles, 256 TMEM columns, 81 KB of shared memory: two CTAs per SM.
+template <int NT, int NKT, bool ALIAS>
+__global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
+    attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
+                        const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
+                        const AttnLongParams p) {
+  pdl_entry();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sQ = base;                          // NT K-major tiles: all queries of the (batch, head)
+  unsigned char* sK = sQ + NT * kTileBytes;          // K-major key tile
+  unsigned char* sV = ALIAS ? base + 4 * kTileBytes : sK + kTileBytes;   // MN-major value tile (d contiguous, 128 key rows)
+  // P chunk, q contiguous, 4 slabs of 128 key rows; two buffers, or ONE lying over sQ / sK (dead once MMA 1 has retired)
+  unsigned char* sP = ALIAS ? base : sV + kTileBytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ALIAS ? sV + kTileBytes : sP + 2 * 4 * kTileBytes);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+  unsigned long long* bar_q = &bars[0];
+  unsigned long long* bar_k = &bars[1];
+  unsigned long long* bar_v = &bars[2];
+  unsigned long long* bar_s = &bars[3];
+  unsigned long long* bar_o = &bars[4];              // [2]
+  constexpr int kTmemCols = ALIAS ? 256 : 512;
+  static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
+  static_assert(!ALIAS || (NT == 2 && NKT == 1), "ALIAS: one full tile + trailing positions");
+  constexpr bool TAIL = NKT < NT;
+  constexpr int NQQ = (NT * kTile + kFwdThreads - 1) / kFwdThreads;    // queries per thread in the trailing-key section
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;               // key row of the tile (query row of the chunk in the epilogue)
+  const int c0 = half * 64, h16 = half * 16;         // this thread's columns of a query chunk / of a head row
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T, TQ = p.TQ, D = p.H * DH;
+  const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
+  __shared__ float xs[2][kTile];                     // partial row maxima, then partial row sums, of the two column halves
+  __shared__ float red8[8];
+  __shared__ float red[TAIL ? 256 : 1];
+  __shared__ float ot_s[kTailMax][32];               // output rows of the trailing queries
+  __shared__ float pt_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // P[trailing key][query]
+  __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
+  if (TAIL) fetch_tail_rows<kFwdThreads / 32>(tr_s, p.qkv, nullptr, (size_t)b * T + (size_t)(NT - 1) * kTile, ntail, D, h, warp, lane);
+
+  if (!TAIL) {
+    // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
+    for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += kFwdThreads * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = *tmem_slot;
+  const unsigned tm_O = tmem, tm_S = tmem + 128;     // O: 32 columns per query chunk; S: up to 384 columns (ALIAS: 128)
+  const unsigned lane_off = (unsigned)(quarter * 32) << 16;
+  // MMA 2: A = P^T MN-major (queries contiguous), B = V MN-major (d contiguous), M = 128 queries, N = 32
+  const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                          ((unsigned)(128 >> 4) << 24);
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, (unsigned)(NT * kTileBytes));
+    for (int qc = 0; qc < NT; ++qc) tma_load_2d(sQ + qc * kTileBytes, &tmKm, bar_q, D + h * DH, b * T + qc * kTile);
+    mbar_expect_tx(bar_k, (unsigned)kTileBytes);
+    tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T);
+    mbar_expect_tx(bar_v, (unsigned)kTileBytes);
+    tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
+  }
+  float ot[kTailMax / 2];                             // O[trailing query 2 ii + half][column lane], summed over the key tiles
+#pragma unroll
+  for (int i = 0; i < kTailMax / 2; ++i) ot[i] = 0.f;
+  int n = 0;                                          // running (key tile, query chunk) counter: P buffer = n & 1
+#pragma unroll 1
+  for (int kt = 0; kt < NKT; ++kt) {
+    const unsigned par = (unsigned)(kt & 1);
+    if (tid == 0) {
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, par);
+      tc_fence_after();
+      // MMA 1: S[128 keys x TQ] = K Q^T in query chunks of <= 128 columns (both operands K-major, +32 B per k-step)
+      for (int qc = 0; qc < NKT; ++qc) {
+        const int nq = min(kTile, TQ - qc * kTile);
+        const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+#pragma unroll
+        for (int k = 0; k < DH / 8; ++k)
+          umma_tf32(tm_S + qc * kTile, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2),
+                    make_desc(smem_u32(sQ) + qc * kTileBytes + k * 32, 16, 1024, 2), idesc1, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    const int kg = kt * kTile + row;                  // this thread's key row
+    const bool valid = kg < T;
+    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
+    // while MMA 1 runs: this key row's scores against the trailing queries (rows 0 .. ntail-1 of the last Q tile; both
+    // threads of the row)
+    float st[kTailMax];
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) st[i] = 0.f;
+    if (TAIL) {
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, par);
+      {
+        float kr[32];
+        load_row_km(sK, row, kr);
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) {
+          if (i < ntail) {
+            float qr[32];
+            load_row_km(sQ + (NT - 1) * kTileBytes, i, qr);
+            st[i] = fmaf(dot32(kr, qr), p.inv_scale, rowmask);
+          }
+        }
+      }
+      if (kt == 0) {
+        // once per item, the trailing KEY rows (thread = query; independent of the tensor path): scores of key k* against
+        // this thread's queries (rows of the resident, TF32-rounded Q tiles; K[k*] from the fetch at kernel start), softmax
+        // over the query axis across the CTA, P[k*][q] kept for the rank-1 update of the output rows
+#pragma unroll 1
+        for (int i = 0; i < ntail; ++i) {
+          const int ks = (NT - 1) * kTile + i;
+          const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+          float sc[NQQ];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int qq = 0; qq < NQQ; ++qq) {
+            const int q = qq * kFwdThreads + tid;
+            sc[qq] = 0.f;
+            if (q < T) {
+              float qr[32];
+              load_row_km(sQ + (q >> 7) * kTileBytes, q & 127, qr);
+              sc[qq] = fmaf(dot32_tf32(tr_s[kTrK][i], qr), p.inv_scale, rmask);
+              mx = fmaxf(mx, sc[qq]);
+            }
+          }
+          const float mxl = block_max256(mx, red8, tid) * kLog2e;
+          float sum = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < NQQ; ++qq) {
+            sc[qq] = (qq * kFwdThreads + tid < T) ? exp2f(fmaf(sc[qq], kLog2e, -mxl)) : 0.f;
+            sum += sc[qq];
+          }
+          const float inv = 1.f / block_sum256(sum, red8, tid);
+#pragma unroll
+          for (int qq = 0; qq < NQQ; ++qq)
+            if (qq * kFwdThreads + tid < T) pt_s[i][qq * kFwdThreads + tid] = sc[qq] * inv;
+          if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
+        }
+      }
+      __syncthreads();                                // every thread has read its K / Q rows: the tiles may be reused
+    }
+    mbar_wait(bar_s, par);
+    tc_fence_after();
+    if (tid == 0 && kt + 1 < NKT) {                   // the K tile is free once MMA 1 has retired
+      mbar_expect_tx(bar_k, (unsigned)kTileBytes);
+      tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
+    }
+    // pass 1: row maximum over this thread's half of every query chunk
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int qc = 0; qc < NKT; ++qc) {
+      const int cend = qc * kTile + min(min(kTile, TQ - qc * kTile), c0 + 64);
+      for (int c = qc * kTile + c0; c < cend; c += 16) {
+        float v[16];
+        tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (TAIL || c + j < T) mx = fmaxf(mx, fmaf(v[j], p.inv_scale, rowmask));
+      }
+    }
+    if (TAIL && half == 0) {
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i)
+        if (i < ntail) mx = fmaxf(mx, st[i]);
+    }
+    xs[half][row] = mx;
+    __syncthreads();
+    const float mxl = fmaxf(xs[0][row], xs[1][row]) * kLog2e;
+    __syncthreads();
+    // pass 2: e = exp2(s * log2 e - max * log2 e) back into TMEM, row sum
+    float sum = 0.f;
+#pragma unroll 1
+    for (int qc = 0; qc < NKT; ++qc) {
+      const int cend = qc * kTile + min(min(kTile, TQ - qc * kTile), c0 + 64);
+      for (int c = qc * kTile + c0; c < cend; c += 16) {
+        float v[16];
+        tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = (TAIL || c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) : 0.f;
+          sum += v[j];
+        }
+        tmem_st16(tm_S + lane_off + c, v);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) {
+      if (i < ntail) {
+        st[i] = exp2f(fmaf(st[i], kLog2e, -mxl));
+        if (half == 0) sum += st[i];
+      }
+    }
+    tmem_st_wait();
+    xs[half][row] = sum;
+    __syncthreads();
+    const float inv = valid ? 1.f / (xs[0][row] + xs[1][row]) : 0.f;   // rows beyond T (neighbouring sequence / zeros) contribute nothing
+    if (valid && half == 0) {
+      float2* stp = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
+      *stp = make_float2(mxl, inv);
+    }
+    // pass 3: normalised row -> shared memory, one query chunk at a time, each chunk followed by its MMA 2
+#pragma unroll 1
+    for (int qc = 0; qc < NKT; ++qc, ++n) {
+      const int buf = ALIAS ? 0 : (n & 1);
+      unsigned char* pb = sP + buf * 4 * kTileBytes;
+      if (n >= 2) {                                    // the MMA that read this buffer two chunks ago has retired
+        mbar_wait(&bar_o[buf], (unsigned)(((n >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const int cend = min(min(kTile, TQ - qc * kTile), c0 + 64);
+      for (int c = c0; c < cend; c += 16) {
+        float v[16];
+        tmem_ld16(tm_S + lane_off + qc * kTile + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(pb + mn_major_off(c + j, row, kTile)) =
+              make_float4(to_tf32(v[j] * inv), to_tf32(v[j + 1] * inv), to_tf32(v[j + 2] * inv), to_tf32(v[j + 3] * inv));
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        if (qc == 0) mbar_wait(bar_v, par);
+        // MMA 2: O[chunk][128 queries x 32] += P^T[128 q x 128 keys] V[128 keys x 32], 16 k-steps of 8 key rows
+        for (int j = 0; j < kTile / 8; ++j)
+          umma_tf32(tm_O + qc * DH, make_desc(smem_u32(pb) + j * 1024, kTileBytes, 512, 1),
+                    make_desc(smem_u32(sV) + j * 1024, kTileBytes, 512, 1), idesc2, (kt > 0 || j > 0) ? 1u : 0u);
+        umma_commit(&bar_o[buf]);
+      }
+      __syncwarp();
+    }
+    if (TAIL) {
+      // while the MMA 2s run: O[q*] += sum over this tile's keys of P[k][q*] V[k] (V row as the MMA sees it); the first
+      // threads of the rows take the even trailing queries, the second threads the odd ones
+      mbar_wait(bar_v, par);
+      float vr[32];
+      load_row_mn(sV, row, vr);
+#pragma unroll
+      for (int ii = 0; ii < kTailMax / 2; ++ii) {
+        if (2 * ii < ntail) {                          // CTA-uniform
+          const float pt = ((half == 0) ? st[2 * ii] : st[2 * ii + 1]) * inv;      // 0 beyond ntail
+          float c[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = pt * vr[j];
+          ot[ii] += half_colsum128(c, red, tid);        // ends with a barrier: every thread has read its V row
+        }
+      }
+    }
+    if (tid == 0 && kt + 1 < NKT) {                   // V tile is free once the last MMA 2 of this key tile has retired
+      const int last = n - 1;
+      mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+      mbar_expect_tx(bar_v, (unsigned)kTileBytes);
+      tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
+    }
+    __syncthreads();                                  // xs is rewritten by the next key tile
+  }
+  {
+    const int last = n - 1;                            // commits complete in order: the last one covers every MMA
+    mbar_wait(&bar_o[ALIAS ? 0 : (last & 1)], (unsigned)((last >> 1) & 1));
+    tc_fence_after();
+  }
+  if (TAIL) {
+    if (quarter == 0) {
+#pragma unroll
+      for (int ii = 0; ii < kTailMax / 2; ++ii) ot_s[2 * ii + half][lane] = ot[ii];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int qc = 0; qc < NT; ++qc) {
+    const int q = qc * kTile + row;                    // lanes = queries
+    float o[16];
+    if (qc < NKT) {
+      tmem_ld16(tm_O + lane_off + qc * DH + h16, o);
+    } else {                                           // the trailing queries' rows: the threads of rows 0 .. ntail-1
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = ot_s[row & (kTailMax - 1)][h16 + j];
+    }
+    if (TAIL && q < T) {
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i)               // O[q] += P[k*][q] V[k*]
+        if (i < ntail) axpy16(pt_s[i][q], tr_s[kTrV][i] + h16, o);
+    }
+    if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH + h16, o, 16);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// 256 threads: warps w and w + 4 share the TMEM lane quarter w & 3 (a warp reaches lanes 32 (w % 4) ... + 31), i.e. two
+// threads own one key row (one query row in the dQ epilogue) and split its columns — 64 + 64 score columns in the P and dS
+// passes, 16 + 16 head columns in the row epilogues.  The kernel is bound by the instruction stream of the row owners
+// (ncu, 128-thread version: 6.8 k instructions per warp and item at 18 % issue utilisation, one warp per scheduler), so
+// halving the columns per thread halves the critical path.
+//
+// NKT = key tiles = query chunks on the tensor path (NT, or NT - 1 when T = 128 (NT - 1) + 1 ... 4: trailing positions).
+// SINGLE (NT = 2, NKT = 1: T = 129 ... 132): the seven operand tiles are loaded once, S = K Q^T and dP = V dO^T are issued
+// together, P goes to its own TMEM columns so that S survives for the dS pass: one TMA round trip and three MMA round trips
+// per (batch, head) instead of four and eight.
 template <int NT, int NKT, bool SINGLE>
 __global__ void __launch_bounds__(kBwdThreads, 1)
     attn_tcl_bwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32,128} over qkv */,
@@ -530,6 +564,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __shared__ float red_b[3][8][16];
   __shared__ float tp_s[2][kTailMax][kTile];         // P / dP of (key row, trailing query), exchanged between the row's two threads
   __shared__ float dq_s[kTailMax][32];               // dQ rows of the trailing queries
+  __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
   __shared__ float ds_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // dS[trailing key][query]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -540,6 +575,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   const int T = p.T, TQ = p.TQ, D = p.H * DH;
   const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
 
+  const size_t tail_row0 = (size_t)b * T + (size_t)(NT - 1) * kTile;   // first trailing position (TAIL)
+  if (TAIL) fetch_tail_rows<kBwdThreads / 32>(tr_s, p.qkv, p.dctx, tail_row0, ntail, D, h, warp, lane);
   if (!TAIL) {                                       // a short last chunk leaves part of the dS^T staging unwritten
     for (int i = tid * 16; i < 4 * kTileBytes; i += kBwdThreads * 16) *reinterpret_cast<float4*>(sY + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
@@ -568,7 +605,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc_k[j] = acc_v[j] = acc_q[j] = 0.f;
   float dqt[2] = {0.f, 0.f};                                // dQ[trailing query 2 ii + half][column lane], summed over the key tiles
-  const size_t tail_row0 = (size_t)b * T + (size_t)(NT - 1) * kTile;   // first trailing position (TAIL)
 
   unsigned step = 0;                                        // bar_qc / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
 #pragma unroll 1
@@ -593,6 +629,87 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tma_load_2d(sQm, &tmMn, bar_kt, D + h * DH, b * T);
       }
       tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);
+    }
+    if (TAIL && kt == 0) {
+      // while the first TMA loads are in flight — trailing key rows (thread = query, Q / dO rows straight from global
+      // memory, K[k*] / V[k*] from the rows fetched at kernel start): P from the forward's statistics, dP = V[k*] . dO[q], delta = sum_q P dP, dS = P (dP - delta) / sqrt(d_h);
+      // dV[k*] = sum_q P dO[q] and dK[k*] = sum_q dS Q[q] are block column sums, dQ[q] += dS K[k*] joins the last epilogue
+#pragma unroll 1
+      for (int i = 0; i < ntail; ++i) {                    // CTA-uniform
+        const int ks = (NT - 1) * kTile + i;
+        const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+        const float2 stt = __ldg(reinterpret_cast<const float2*>(p.stats) + ((size_t)(b * p.H + h) * T + ks));
+        const float* krow = tr_s[kTrK][i];
+        const float4* vrow = reinterpret_cast<const float4*>(tr_s[kTrV][i]);
+        float pv[NQQ], dpv[NQQ];
+        float col[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) col[j] = 0.f;
+        float dl = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < NQQ; ++qq) {
+          const int q = qq * kBwdThreads + tid;
+          pv[qq] = dpv[qq] = 0.f;
+          if (q < T) {
+            float qr[32], dor[32];
+            const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+            const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = vrow[c];
+              qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
+              dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
+              d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
+              d4[2] = fmaf(v4.z, g4.z, d4[2]); d4[3] = fmaf(v4.w, g4.w, d4[3]);
+            }
+            const float sc = fmaf(dot32_tf32(krow, qr), p.inv_scale, rmask);
+            const float pr = exp2f(fmaf(sc, kLog2e, -stt.x)) * stt.y;
+            const float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+            pv[qq] = pr;
+            dpv[qq] = dp;
+            dl = fmaf(pr, dp, dl);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) col[j] = fmaf(pr, dor[j], col[j]);
+          }
+        }
+        float delta;
+        const float dv = block_colsum256_sum(col, dl, red, red8, tid, &delta);   // dV[k*][lane] in every thread
+#pragma unroll
+        for (int j = 0; j < 32; ++j) col[j] = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < NQQ; ++qq) {
+          const int q = qq * kBwdThreads + tid;
+          const float ds = pv[qq] * ((dpv[qq] - delta) * p.inv_scale);
+          if (q < T) {
+            ds_s[i][q] = ds;
+            const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 q4 = __ldg(qp + c);
+              col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
+              col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
+            }
+          }
+        }
+        const float dk = block_colsum256(col, red, tid);        // dK[k*][lane]
+        if (tid < 32) {
+          const size_t e = ((size_t)b * T + ks) * 3 * D + h * DH + tid;
+          if (p.out_bf16) {
+            unsigned short* o16 = reinterpret_cast<unsigned short*>(p.out);
+            o16[e] = __bfloat16_as_ushort(__float2bfloat16_rn(dk));
+            o16[e + 2 * D] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
+          } else {
+            float* o32 = reinterpret_cast<float*>(p.out);
+            o32[e] = dk;
+            o32[e + 2 * D] = dv;
+          }
+          if (p.dbias) {
+            atomicAdd(p.dbias + 0 * D + h * DH + tid, dk);
+            atomicAdd(p.dbias + 2 * D + h * DH + tid, dv);
+          }
+        }
+      }
     }
     // ---------------- phase 1: dV[keys x 32] = sum over query chunks of P[keys x q] dO[q x 32]
 #pragma unroll 1
@@ -622,8 +739,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       __syncwarp();
       if (TAIL && qc == 0) {
         // while the MMA runs: P (first thread of the row) and dP (second thread) of this key row against the trailing
-        // queries — thread-local dot products; K / V rows as the MMAs see them, Q rounded like the TMA unit rounds it so
-        // that P matches the forward's statistics
+        // queries — thread-local dot products; K / V rows as the MMAs see them, Q / dO rows from the fetch at kernel start
+        // (Q rounded like the TMA unit rounds it so that P matches the forward's statistics)
         mbar_wait(bar_kt, (unsigned)(kt & 1));
         float kv[32];
         load_row_km(half ? sVk : sKk, row, kv);
@@ -633,11 +750,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
             float r[32];
             float val;
             if (half == 0) {
-              load_row_global<true>(p.qkv + (tail_row0 + i) * 3 * D + D + h * DH, r);
+              load_row32(tr_s[kTrQt][i], r);
               const float sc = fmaf(dot32(kv, r), p.inv_scale, rowmask);
               val = valid ? exp2f(fmaf(sc, kLog2e, -mxl)) * inv : 0.f;
             } else {
-              load_row_global<false>(p.dctx + (tail_row0 + i) * D + h * DH, r);
+              load_row32(tr_s[kTrDO][i], r);
               val = dot32(kv, r);
             }
             tp_s[half][i][row] = val;          // read after the barrier that follows the P pass
@@ -669,87 +786,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         umma_commit(bar_m2);
       }
       __syncwarp();
-      if (TAIL && kt == 0 && qc == NKT - 1) {
-        // while the last dV MMA of the first key tile runs — trailing key rows (thread = query, Q / dO rows straight from
-        // global memory): P from the forward's statistics, dP = V[k*] . dO[q], delta = sum_q P dP, dS = P (dP - delta) / sqrt(d_h);
-        // dV[k*] = sum_q P dO[q] and dK[k*] = sum_q dS Q[q] are block column sums, dQ[q] += dS K[k*] joins the last epilogue
-#pragma unroll 1
-        for (int i = 0; i < ntail; ++i) {                    // CTA-uniform
-          const int ks = (NT - 1) * kTile + i;
-          const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
-          const float2 stt = __ldg(reinterpret_cast<const float2*>(p.stats) + ((size_t)(b * p.H + h) * T + ks));
-          const float* krow = p.qkv + ((size_t)b * T + ks) * 3 * D + h * DH;
-          const float4* vrow = reinterpret_cast<const float4*>(krow + 2 * D);
-          float pv[NQQ], dpv[NQQ];
-          float col[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) col[j] = 0.f;
-          float dl = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < NQQ; ++qq) {
-            const int q = qq * kBwdThreads + tid;
-            pv[qq] = dpv[qq] = 0.f;
-            if (q < T) {
-              float qr[32], dor[32];
-              const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
-              const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
-              float d4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = __ldg(vrow + c);
-                qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
-                dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
-                d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
-                d4[2] = fmaf(v4.z, g4.z, d4[2]); d4[3] = fmaf(v4.w, g4.w, d4[3]);
-              }
-              const float sc = fmaf(dot32_tf32(krow, qr), p.inv_scale, rmask);
-              const float pr = exp2f(fmaf(sc, kLog2e, -stt.x)) * stt.y;
-              const float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-              pv[qq] = pr;
-              dpv[qq] = dp;
-              dl = fmaf(pr, dp, dl);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) col[j] = fmaf(pr, dor[j], col[j]);
-            }
-          }
-          const float delta = block_sum256(dl, red8, tid);
-          const float dv = block_colsum256(col, red, tid);        // dV[k*][lane] in every thread
-#pragma unroll
-          for (int j = 0; j < 32; ++j) col[j] = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < NQQ; ++qq) {
-            const int q = qq * kBwdThreads + tid;
-            const float ds = pv[qq] * ((dpv[qq] - delta) * p.inv_scale);
-            if (q < T) {
-              ds_s[i][q] = ds;
-              const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 q4 = __ldg(qp + c);
-                col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
-                col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
-              }
-            }
-          }
-          const float dk = block_colsum256(col, red, tid);        // dK[k*][lane]
-          if (tid < 32) {
-            const size_t e = ((size_t)b * T + ks) * 3 * D + h * DH + tid;
-            if (p.out_bf16) {
-              unsigned short* o16 = reinterpret_cast<unsigned short*>(p.out);
-              o16[e] = __bfloat16_as_ushort(__float2bfloat16_rn(dk));
-              o16[e + 2 * D] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
-            } else {
-              float* o32 = reinterpret_cast<float*>(p.out);
-              o32[e] = dk;
-              o32[e + 2 * D] = dv;
-            }
-            if (p.dbias) {
-              atomicAdd(p.dbias + 0 * D + h * DH + tid, dk);
-              atomicAdd(p.dbias + 2 * D + h * DH + tid, dv);
-            }
-          }
-        }
-      }
       mbar_wait(bar_m2, par);                  // S and the chunk tiles are free again
       tc_fence_after();
     }
@@ -766,10 +802,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         if (i < ntail) {                       // dV_k += P[k][q*] dO[q*]
           pt[i] = tp_s[0][i][row];
           dpt[i] = tp_s[1][i][row];
-          const float4* gp = reinterpret_cast<const float4*>(p.dctx + (tail_row0 + i) * D + h * DH);
+          const float4* gp = reinterpret_cast<const float4*>(tr_s[kTrDO][i]);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 g4 = __ldg(gp + c);
+            const float4 g4 = gp[c];
             o[4 * c] = fmaf(pt[i], g4.x, o[4 * c]); o[4 * c + 1] = fmaf(pt[i], g4.y, o[4 * c + 1]);
             o[4 * c + 2] = fmaf(pt[i], g4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pt[i], g4.w, o[4 * c + 3]);
           }
@@ -883,7 +919,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       tmem_ld16(tm_dK + lane_off + h16, o);
 #pragma unroll
       for (int i = 0; i < kTailMax; ++i)
-        if (i < ntail) axpy16_global(pt[i], p.qkv + (tail_row0 + i) * 3 * D + D + h * DH + h16, o);   // dK_k += dS[k][q*] Q[q*]
+        if (i < ntail) axpy16(pt[i], tr_s[kTrQ][i] + h16, o);   // dK_k += dS[k][q*] Q[q*]
       if (valid) {
         store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + h * DH + h16, o, 16);
 #pragma unroll
@@ -914,7 +950,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     if (TAIL && q < T) {
 #pragma unroll
       for (int i = 0; i < kTailMax; ++i)       // dQ[q] += dS[k*][q] K[k*]
-        if (i < ntail) axpy16_global(ds_s[i][q], p.qkv + (tail_row0 + i) * 3 * D + h * DH + h16, o);
+        if (i < ntail) axpy16(ds_s[i][q], tr_s[kTrK][i] + h16, o);
     }
     if (q < T) {
       store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * 3 * D + D + h * DH + h16, o, 16);
@@ -974,7 +1010,7 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
   do {                                                                                                                   \
     MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                   (int)(SMEM_)));                                                                        \
-    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, dim3(B * H), dim3(128), (SMEM_), st, tk, tm, p));         \
+    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, dim3(B * H), dim3(kFwdThreads), (SMEM_), st, tk, tm, p)); \
   } while (0)
   const bool tail = tail_keys(T) != 0;
   if (T <= 2 * kTile) {
