@@ -221,6 +221,15 @@ int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* ctx, int ct
                           int dh, void* stream);
 int msx_attention_tcl_bwd(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
                           int dqkv_bf16, float* dbias, int B, int T, int H, int dh, void* stream);   /* dbias (optional) [3*H*dh] += column sums of dqkv */
+/* q0_only as msx_attention_tc_fwd_p / msx_attention_tc_bwd_q0 (the encoder's top layer is read at position 0 only,
+ * model.py:97-100).  Forward: only the context row of query 0 of every sequence is computed and written (a column sum over
+ * the key rows: no P staging, no second MMA); stats cover every key row as before.  Backward: the caller guarantees that
+ * dctx is zero outside the row of query 0 of every sequence; dV and dS are then thread-local (no dP / dV MMAs, no dO
+ * tiles) and only that row of dctx is read. */
+int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int q0_only, int B,
+                             int T, int H, int dh, void* stream);
+int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
+                             int dqkv_bf16, float* dbias, int q0_only, int B, int T, int H, int dh, void* stream);
 
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
  * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);

@@ -214,7 +214,10 @@ __device__ __forceinline__ float block_max256(float v, float* red8, int tid) {
 // NKT = key tiles = query chunks on the tensor path (NT, or NT - 1 with trailing positions).
 // ALIAS (NT = 2, NKT = 1: T = 129 ... 132, one key tile x one query chunk on the tensor path): P staging (single buffer)
 // lies over the Q / K tiles, 256 TMEM columns, 81 KB of shared memory: two CTAs per SM.
-template <int NT, int NKT, bool ALIAS>
+// Q0 (the encoder's top layer under SOS-rows-only, model.py:97-100 reads position 0): scores and the query-axis softmax
+// cover every query as before (each key row's normaliser), then O[0] = sum_k P[k][0] V[k] is a column sum over the key
+// threads — no P staging, no MMA 2, one 128-byte row written per (batch, head); the other rows of ctx stay untouched.
+template <int NT, int NKT, bool ALIAS, bool Q0>
 __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
     attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
@@ -250,12 +253,13 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
   __shared__ float xs[2][kTile];                     // partial row maxima, then partial row sums, of the two column halves
   __shared__ float red8[8];
   __shared__ float red[TAIL ? 256 : 1];
+  __shared__ float red_q[Q0 ? 256 : 1];
   __shared__ float ot_s[kTailMax][32];               // output rows of the trailing queries
   __shared__ float pt_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // P[trailing key][query]
   __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
   if (TAIL) fetch_tail_rows<kFwdThreads / 32>(tr_s, p.qkv, nullptr, (size_t)b * T + (size_t)(NT - 1) * kTile, ntail, D, h, warp, lane);
 
-  if (!TAIL) {
+  if (!TAIL && !Q0) {
     // P staging must hold finite values everywhere the MMAs read (short last query chunk): zero it once
     for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += kFwdThreads * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
@@ -287,6 +291,7 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
     mbar_expect_tx(bar_v, (unsigned)kTileBytes);
     tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
   }
+  float o0 = 0.f, e0 = 0.f;                           // Q0: O[0][column lane] summed over the key tiles; exp of (key row, query 0)
   float ot[kTailMax / 2];                             // O[trailing query 2 ii + half][column lane], summed over the key tiles
 #pragma unroll
   for (int i = 0; i < kTailMax / 2; ++i) ot[i] = 0.f;
@@ -411,7 +416,11 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
           v[j] = (TAIL || c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) : 0.f;
           sum += v[j];
         }
-        tmem_st16(tm_S + lane_off + c, v);
+        if (Q0) {
+          if (c == 0) e0 = v[0];                        // query 0: first column of the first thread of the row
+        } else {
+          tmem_st16(tm_S + lane_off + c, v);
+        }
       }
     }
 #pragma unroll
@@ -429,9 +438,23 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
       float2* stp = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
       *stp = make_float2(mxl, inv);
     }
+    if (Q0) {
+      // O[0] += sum over this tile's keys of P[k][0] V[k] (the second threads of the rows add zeros)
+      mbar_wait(bar_v, par);
+      float c[32];
+      load_row_mn(sV, row, c);
+      const float p0 = (half == 0) ? e0 * inv : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c[j] *= p0;
+      o0 += half_colsum128(c, red_q, tid);              // ends with a barrier: every thread has read its V row
+      if (tid == 0 && kt + 1 < NKT) {
+        mbar_expect_tx(bar_v, (unsigned)kTileBytes);
+        tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
+      }
+    }
     // pass 3: normalised row -> shared memory, one query chunk at a time, each chunk followed by its MMA 2
 #pragma unroll 1
-    for (int qc = 0; qc < NKT; ++qc, ++n) {
+    for (int qc = 0; qc < (Q0 ? 0 : NKT); ++qc, ++n) {
       const int buf = ALIAS ? 0 : (n & 1);
       unsigned char* pb = sP + buf * 4 * kTileBytes;
       if (n >= 2) {                                    // the MMA that read this buffer two chunks ago has retired
@@ -461,7 +484,7 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
       }
       __syncwarp();
     }
-    if (TAIL) {
+    if (TAIL && !Q0) {
       // while the MMA 2s run: O[q*] += sum over this tile's keys of P[k][q*] V[k] (V row as the MMA sees it); the first
       // threads of the rows take the even trailing queries, the second threads the odd ones
       mbar_wait(bar_v, par);
@@ -478,13 +501,29 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
         }
       }
     }
-    if (tid == 0 && kt + 1 < NKT) {                   // V tile is free once the last MMA 2 of this key tile has retired
+    if (!Q0 && tid == 0 && kt + 1 < NKT) {            // V tile is free once the last MMA 2 of this key tile has retired
       const int last = n - 1;
       mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
       mbar_expect_tx(bar_v, (unsigned)kTileBytes);
       tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
     }
     __syncthreads();                                  // xs is rewritten by the next key tile
+  }
+  if (Q0) {
+    if (warp == 0) {                                   // the row of query 0: column `lane`
+      if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i)             // O[0] += P[k*][0] V[k*]
+          if (i < ntail) o0 = fmaf(pt_s[i][0], tr_s[kTrV][i][lane], o0);
+      }
+      const size_t e = (size_t)b * T * D + h * DH + lane;
+      if (p.out_bf16) reinterpret_cast<unsigned short*>(p.out)[e] = __bfloat16_as_ushort(__float2bfloat16_rn(o0));
+      else reinterpret_cast<float*>(p.out)[e] = o0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    return;
   }
   {
     const int last = n - 1;                            // commits complete in order: the last one covers every MMA
@@ -531,7 +570,10 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
 // SINGLE (NT = 2, NKT = 1: T = 129 ... 132): the seven operand tiles are loaded once, S = K Q^T and dP = V dO^T are issued
 // together, P goes to its own TMEM columns so that S survives for the dS pass: one TMA round trip and three MMA round trips
 // per (batch, head) instead of four and eight.
-template <int NT, int NKT, bool SINGLE>
+// Q0 (the encoder's top layer under SOS-rows-only): dctx is non-zero in the row of query 0 only.  With g = dO[0],
+// a_k = V_k . g, c_k = a_k P[k][0]:  dV_k = P[k][0] g  and  dS[k][q] = P[k][q] ([q = 0] a_k - c_k) / sqrt(d_h)  are thread-local,
+// so phase 1 (P pass, dV MMA), the dP MMA, the dO tiles and the second TMEM read of the dS pass all disappear.
+template <int NT, int NKT, bool SINGLE, bool Q0>
 __global__ void __launch_bounds__(kBwdThreads, 1)
     attn_tcl_bwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32,128} over qkv */,
@@ -564,6 +606,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __shared__ float red_b[3][8][16];
   __shared__ float tp_s[2][kTailMax][kTile];         // P / dP of (key row, trailing query), exchanged between the row's two threads
   __shared__ float dq_s[kTailMax][32];               // dQ rows of the trailing queries
+  __shared__ __align__(16) float g_s[32];            // Q0: dO[query 0]
   __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
   __shared__ float ds_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // dS[trailing key][query]
 
@@ -576,7 +619,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   const int ntail = TAIL ? tail_keys(T) : 0;         // trailing positions handled off the tensor path (see kTailMax)
 
   const size_t tail_row0 = (size_t)b * T + (size_t)(NT - 1) * kTile;   // first trailing position (TAIL)
-  if (TAIL) fetch_tail_rows<kBwdThreads / 32>(tr_s, p.qkv, p.dctx, tail_row0, ntail, D, h, warp, lane);
+  if (TAIL) fetch_tail_rows<kBwdThreads / 32>(tr_s, p.qkv, Q0 ? nullptr : p.dctx, tail_row0, ntail, D, h, warp, lane);
+  if (Q0 && warp == 7) g_s[lane] = __ldg(p.dctx + (size_t)b * T * D + h * DH + lane);
   if (!TAIL) {                                       // a short last chunk leaves part of the dS^T staging unwritten
     for (int i = tid * 16; i < 4 * kTileBytes; i += kBwdThreads * 16) *reinterpret_cast<float4*>(sY + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
@@ -619,13 +663,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       inv = st.y;
     }
     if (tid == 0) {                                         // every MMA that read the previous key tile has retired (bar_m2 waits)
-      mbar_expect_tx(bar_kt, (unsigned)((SINGLE ? 7 : 3) * kTileBytes));
+      mbar_expect_tx(bar_kt, (unsigned)((SINGLE ? (Q0 ? 5 : 7) : 3) * kTileBytes));
       tma_load_2d(sKk, &tmKm, bar_kt, h * DH, b * T + kt * kTile);
       tma_load_2d(sVk, &tmKm, bar_kt, 2 * D + h * DH, b * T + kt * kTile);
       if (SINGLE) {
         tma_load_2d(sQk, &tmKm, bar_kt, D + h * DH, b * T);
-        tma_load_2d(sDOk, &tmDOk, bar_kt, h * DH, b * T);
-        tma_load_2d(sDOm, &tmDOm, bar_kt, h * DH, b * T);
+        if (!Q0) {
+          tma_load_2d(sDOk, &tmDOk, bar_kt, h * DH, b * T);
+          tma_load_2d(sDOm, &tmDOm, bar_kt, h * DH, b * T);
+        }
         tma_load_2d(sQm, &tmMn, bar_kt, D + h * DH, b * T);
       }
       tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);
@@ -657,7 +703,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 q4 = __ldg(qp + c), g4 = __ldg(dp4 + c), v4 = vrow[c];
+              const float4 q4 = __ldg(qp + c), v4 = vrow[c];
+              const float4 g4 = Q0 ? (q == 0 ? reinterpret_cast<const float4*>(g_s)[c] : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(dp4 + c);
               qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
               dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
               d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
@@ -713,7 +760,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     }
     // ---------------- phase 1: dV[keys x 32] = sum over query chunks of P[keys x q] dO[q x 32]
 #pragma unroll 1
-    for (int qc = 0; qc < NKT; ++qc, ++step) {
+    for (int qc = 0; qc < (Q0 ? 0 : NKT); ++qc, ++step) {
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
@@ -792,7 +839,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     // ---------------- delta_k = V_k . dV_k (both threads of the row, over all 32 columns); dV half row out
     float pt[kTailMax], dpt[kTailMax];         // P / dP of (this key row, trailing query i); below pt = dS
     float delta = 0.f;
-    {
+    float a_k = 0.f;                           // Q0: V_k . dO[0]
+    if (Q0) {
+      mbar_wait(bar_kt, (unsigned)(kt & 1));
+      float r[32], g[32];
+      load_row_km(sVk, row, r);
+      load_row32(g_s, g);
+      a_k = dot32(r, g);
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i) pt[i] = dpt[i] = 0.f;
+      if (TAIL) {                              // P of this key row against the trailing queries (both threads of the row)
+        load_row_km(sKk, row, r);
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) {
+          if (i < ntail) {
+            load_row32(tr_s[kTrQt][i], g);
+            const float sc = fmaf(dot32(r, g), p.inv_scale, rowmask);
+            pt[i] = valid ? exp2f(fmaf(sc, kLog2e, -mxl)) * inv : 0.f;
+          }
+        }
+      }
+    } else {
       float o[32];
       tmem_ld16(tm_dV + lane_off, o);
       tmem_ld16(tm_dV + lane_off + 16, o + 16);
@@ -832,28 +899,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         }
       }
     }
+    if (!Q0) {
 #pragma unroll
-    for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((dpt[i] - delta) * p.inv_scale);   // dS[k][q*]
+      for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((dpt[i] - delta) * p.inv_scale);   // dS[k][q*]
+    }
     // ---------------- phase 2: dK += dS Q, dQ[chunk] += dS^T K
 #pragma unroll 1
     for (int qc = 0; qc < NKT; ++qc, ++step) {
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-      if (!SINGLE) {
+      if (!SINGLE || Q0) {
         if (tid == 0) {
-          mbar_expect_tx(bar_qc, (unsigned)(3 * kTileBytes));
-          tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
-          tma_load_2d(sQm, &tmMn, bar_qc, D + h * DH, b * T + qc * kTile);
-          tma_load_2d(sDOk, &tmDOk, bar_qc, h * DH, b * T + qc * kTile);
-          mbar_wait(bar_qc, par);
+          if (!SINGLE) {
+            mbar_expect_tx(bar_qc, (unsigned)((Q0 ? 2 : 3) * kTileBytes));
+            tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
+            tma_load_2d(sQm, &tmMn, bar_qc, D + h * DH, b * T + qc * kTile);
+            if (!Q0) tma_load_2d(sDOk, &tmDOk, bar_qc, h * DH, b * T + qc * kTile);
+            mbar_wait(bar_qc, par);
+          }
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T and dP = V dO^T, two independent chains
             umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
                       idesc_s, k > 0 ? 1u : 0u);
-            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
-                      idesc_s, k > 0 ? 1u : 0u);
+            if (!Q0)
+              umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
+                        idesc_s, k > 0 ? 1u : 0u);
           }
           umma_commit(bar_m1);
         }
@@ -861,14 +933,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         mbar_wait(bar_m1, par);
         tc_fence_after();
       }
+      if (Q0 && qc == 0) {
+        // P[k][0] from the first score column (read by both threads of the row): delta, the dV half row, dS of the trailing queries
+        float v[16];
+        tmem_ld16(tm_S + lane_off, v);
+        const float p0 = valid ? exp2f(fmaf(fmaf(v[0], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f;
+        delta = p0 * a_k;
+        if (valid) {
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = p0 * g_s[h16 + j];
+          store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + kg) * 3 * D + 2 * D + h * DH + h16, o, 16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc_v[j] += o[j];
+        }
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((0.f - delta) * p.inv_scale);   // dS[k][q*]: dP = 0 there
+      }
       {
         const int cend = min(nq, c0 + 64);
         for (int c = c0; c < cend; c += 16) {
           float v[16], g[16];
-          tmem_ld16_issue(tm_S + lane_off + c, v);
-          tmem_ld16_issue(tm_dP + lane_off + c, g);
-          tmem_ld16_wait(v);
-          tmem_ld16_wait(g);
+          if (Q0) {
+            tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = 0.f;
+            if (qc == 0 && c == 0) g[0] = a_k;                          // dP[k][q] = [q = 0] V_k . dO[0]
+          } else {
+            tmem_ld16_issue(tm_S + lane_off + c, v);
+            tmem_ld16_issue(tm_dP + lane_off + c, g);
+            tmem_ld16_wait(v);
+            tmem_ld16_wait(g);
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float pr = (TAIL || qc * kTile + c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f;
@@ -989,8 +1085,18 @@ extern "C" int msx_attention_tcl_supported(const float* qkv, int T, int dh) {
   return (qkv && dh == 32 && T > 128 && T <= 3 * kTile && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
 }
 
+extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int q0_only,
+                                        int B, int T, int H, int dh, void* stream);
+extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
+                                        int dqkv_bf16, float* dbias, int q0_only, int B, int T, int H, int dh, void* stream);
+
 extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int B, int T,
                                      int H, int dh, void* stream) {
+  return msx_attention_tcl_fwd_q0(qkv, mask, ctx, ctx_bf16, stats, 0, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int q0_only,
+                                        int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx && stats, "msx_attention_tcl_fwd: null pointer");
   MSX_REQUIRE(msx_attention_tcl_supported(qkv, T, dh) && ((uintptr_t)ctx & 15) == 0 && ((uintptr_t)stats & 7) == 0,
               "msx_attention_tcl_fwd: needs d_h == 32, 128 < T <= 384, 16-byte aligned buffers");
@@ -1008,9 +1114,17 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
   cudaStream_t st = (cudaStream_t)stream;
 #define MSX_TCL_FWD(NT_, NKT_, ALIAS_, SMEM_)                                                                              \
   do {                                                                                                                   \
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                  (int)(SMEM_)));                                                                        \
-    MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_>, dim3(B * H), dim3(kFwdThreads), (SMEM_), st, tk, tm, p)); \
+    if (q0_only) {                                                                                                       \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, true>,                                        \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)));                         \
+      MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, true>, dim3(B * H), dim3(kFwdThreads), (SMEM_), st, tk, \
+                          tm, p));                                                                                       \
+    } else {                                                                                                             \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, false>,                                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)));                         \
+      MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, false>, dim3(B * H), dim3(kFwdThreads), (SMEM_), st,    \
+                          tk, tm, p));                                                                                   \
+    }                                                                                                                    \
   } while (0)
   const bool tail = tail_keys(T) != 0;
   if (T <= 2 * kTile) {
@@ -1027,6 +1141,11 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
 
 extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
                                      int dqkv_bf16, float* dbias, int B, int T, int H, int dh, void* stream) {
+  return msx_attention_tcl_bwd_q0(qkv, mask, dctx, stats, dqkv, dqkv_bf16, dbias, 0, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
+                                        int dqkv_bf16, float* dbias, int q0_only, int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && dctx && stats && dqkv, "msx_attention_tcl_bwd: null pointer");
   MSX_REQUIRE(msx_attention_tcl_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0 &&
                   ((uintptr_t)stats & 7) == 0,
@@ -1047,10 +1166,17 @@ extern "C" int msx_attention_tcl_bwd(const float* qkv, const float* mask, const 
   cudaStream_t st = (cudaStream_t)stream;
 #define MSX_TCL_BWD(NT_, NKT_, SINGLE_)                                                                                     \
   do {                                                                                                                   \
-    MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)kBwdSmem));                                                                       \
-    MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_>, dim3(B * H), dim3(kBwdThreads), kBwdSmem, st, tk, tm,   \
-                        tdk, tdm, p));                                                                                   \
+    if (q0_only) {                                                                                                       \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, true>,                                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));                        \
+      MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, true>, dim3(B * H), dim3(kBwdThreads), kBwdSmem, st,   \
+                          tk, tm, tdk, tdm, p));                                                                         \
+    } else {                                                                                                             \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, false>,                                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));                        \
+      MSX_CUDA(msx_launch(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, false>, dim3(B * H), dim3(kBwdThreads), kBwdSmem, st,  \
+                          tk, tm, tdk, tdm, p));                                                                         \
+    }                                                                                                                    \
   } while (0)
   const bool tail = tail_keys(T) != 0;
   if (T <= 2 * kTile) {

@@ -447,7 +447,8 @@ class VAEEngine:
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd),
                                  q0_only=sos_only and D // H == 32)
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
-            ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
+            ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
+                                  q0_only=sos_only)
         else:
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
         if sos_only:
@@ -555,7 +556,7 @@ class VAEEngine:
             gbqkv = None
         elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), torch.float32)], dqkv, B, T, H,
-                                  D // H, dbias=gbqkv)
+                                  D // H, dbias=gbqkv, q0_only=sos_only)
             gbqkv = None
         else:
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)
@@ -592,7 +593,8 @@ class VAEEngine:
         else:                                           # longer rows: fp32 context from the kernel that takes them, one split
             ctx = bf.get(tag + "ctx", (M, D), dev)
             if ops.attention_tcl_supported(qkv, T, D // H):
-                ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
+                ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
+                                      q0_only=sos_only)
             else:
                 ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.split_planes(ctx, ctxp[0], ctxp[1])
@@ -656,7 +658,8 @@ class VAEEngine:
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx16, B, T, H, D // H, q0_only=sos_only and D // H == 32)
         elif ops.attention_tcl_supported(qkv, T, D // H):
-            ops.attention_tcl_fwd(qkv, mask, ctx16, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H)
+            ops.attention_tcl_fwd(qkv, mask, ctx16, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
+                                  q0_only=sos_only)
         else:                                           # T > 384: FFMA attention in fp32, then one cast
             ctx = bf.get(tag + "ctx", (M, D), dev)
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
@@ -753,7 +756,7 @@ class VAEEngine:
             ops.attention_tc_bwd(qkv, mask, dctx, dqkv16, B, T, H, D // H, dbias=gbqkv, q0_only=sos_only)
         elif ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_bwd(qkv, mask, dctx, bf.t[(tag + "attn_stats", (B * H * T, 2), f32)], dqkv16, B, T, H, D // H,
-                                  dbias=gbqkv)
+                                  dbias=gbqkv, q0_only=sos_only)
         else:
             dqkv = bf.get(tag + "dqkv", (M, 3 * D), dev)
             ops.attention_bwd(qkv, mask, dctx, dqkv, B, T, H, D // H)

@@ -239,14 +239,17 @@ def attention_tcl_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tcl_supported(P(qkv), _i(T), _i(dh)))
 
 
-def attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh):
-    lib.call("msx_attention_tcl_fwd", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), P(stats), _i(B),
-             _i(T), _i(H), _i(dh), lib.stream_ptr())
+def attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh, q0_only=False):
+    """q0_only: compute / write the context row of query 0 of every sequence only (the other rows of ctx stay untouched)."""
+    lib.call("msx_attention_tcl_fwd_q0", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), P(stats),
+             _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 
-def attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=None):
-    lib.call("msx_attention_tcl_bwd", P(qkv), P(mask), P(dctx), P(stats), P(dqkv),
-             _i(1 if dqkv.dtype == torch.bfloat16 else 0), P(dbias), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
+def attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=None, q0_only=False):
+    """q0_only: the caller guarantees dctx == 0 outside the row of query 0 of every sequence."""
+    lib.call("msx_attention_tcl_bwd_q0", P(qkv), P(mask), P(dctx), P(stats), P(dqkv),
+             _i(1 if dqkv.dtype == torch.bfloat16 else 0), P(dbias), _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh),
+             lib.stream_ptr())
 
 
 def attention_bwd(qkv, mask, dctx, dqkv, B, T, H, dh):

@@ -41,6 +41,9 @@ for T in [int(a) for a in sys.argv[1:]] or (65, 128, 129, 130, 132, 133, 193, 25
         f = timed(lambda: ops.attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh))
         b = timed(lambda: ops.attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=db))
         name = "attn_tcl"
+        f0 = timed(lambda: ops.attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh, q0_only=True))
+        b0 = timed(lambda: ops.attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=db, q0_only=True))
+        print("attn_tcl T=%3d B=%4d: q0_only fwd %7.1f us   bwd %7.1f us" % (T, B, f0, b0))
     items = B * H
     print("%s T=%3d B=%4d: fwd %7.1f us (%5.2f us per (b,h) per SM)   bwd %7.1f us (%5.2f)   fwd %.1f / bwd %.1f ns per token"
           % (name, T, B, f, f * 148 / items, b, b * 148 / items, f * 1e3 / (B * T), b * 1e3 / (B * T)))

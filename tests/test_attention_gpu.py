@@ -196,6 +196,53 @@ def test_attention_long_rows(B, T, H, out16):
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 129, 2), (2, 130, 3), (3, 132, 2), (2, 133, 2), (2, 200, 2), (3, 256, 1), (3, 257, 2), (2, 260, 2),
+                                   (2, 384, 2), (200, 129, 8)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_attention_long_rows_q0(B, T, H, out16):
+    """q0_only variants of the long-row kernels (the encoder's top layer under SOS-rows-only): the forward writes the context
+    row of query 0 of every sequence only, the backward takes a context gradient that is zero outside those rows; both vs
+    the float64 reference formula / autograd, and the statistics the forward saves vs the full forward's."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    D = H * dh
+    qkv, mask = _inputs(B, T, H, dh, seed=T + 7)
+    g = torch.Generator().manual_seed(T)
+    dctx = torch.zeros(B * T, D)
+    dctx[::T] = torch.randn(B, D, generator=g)
+    x = qkv.double().requires_grad_(True)
+    want = _ref_fwd(x, mask, B, T, H, dh)
+    (want * dctx.double()).sum().backward()
+    wg = x.grad
+    want = want.detach()
+    qd, md, dd = qkv.cuda(), mask.cuda(), dctx.cuda()
+    odt = torch.bfloat16 if out16 else torch.float32
+    ctx = torch.full((B * T, D), 3.0, device="cuda", dtype=odt)
+    stats = torch.zeros((B * H * T, 2), device="cuda")
+    ops.attention_tcl_fwd(qd, md, ctx, stats, B, T, H, dh, q0_only=True)
+    torch.cuda.synchronize()
+    got = ctx.double().cpu()
+    scale = float(want.abs().max())
+    err = float((got[::T] - want[::T]).abs().max()) / scale
+    assert err < (8e-3 if out16 else 3e-3), err
+    rest = torch.ones(B * T, dtype=torch.bool)
+    rest[::T] = False
+    assert bool((got[rest] == 3.0).all()), "q0_only forward must leave the other context rows untouched"
+    stats_full = torch.zeros_like(stats)
+    ops.attention_tcl_fwd(qd, md, torch.empty_like(ctx), stats_full, B, T, H, dh)
+    torch.cuda.synchronize()
+    assert torch.equal(stats, stats_full)
+    out = torch.full((B * T, 3 * D), 5.0, device="cuda", dtype=odt)
+    db = torch.zeros(3 * D, device="cuda")
+    ops.attention_tcl_bwd(qd, md, dd, stats, out, B, T, H, dh, dbias=db, q0_only=True)
+    torch.cuda.synchronize()
+    gs = float(wg.abs().max())
+    err = float((out.double().cpu() - wg).abs().max()) / gs
+    assert err < (1e-2 if out16 else 5e-3), err
+    wb = wg.sum(0)
+    assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ 16-wide heads
 @pytest.mark.parametrize("B,T,H", [(3, 66, 8), (5, 65, 3), (2, 16, 4), (4, 97, 2), (2, 128, 8), (300, 66, 8)])
 @pytest.mark.parametrize("out16", [False, True])

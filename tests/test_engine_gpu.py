@@ -388,7 +388,13 @@ def test_tf32_long_rows_step_vs_oracle(T):
     devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
                    if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
     print("tf32 long-row gradient deviation, worst tensors:", devs[:4])
-    assert devs[0][0] < 5e-2
+    # The feed-forward's first layer sits behind a ReLU: with 8 rows a single unit whose pre-activation is within the TF32
+    # rounding of zero flips its mask and moves ff1.weight / ff1.bias by a few per cent of their scale, whichever kernel
+    # produced the rounding (profiles/micro/diag_long_rows_r2.txt: 2e-2 ... 8e-2 for every seed under single-pass TF32,
+    # 2e-3 under bf16p3f; every other tensor <= 1.3e-2).  Those two tensors get the looser bound.
+    relu = lambda n: n.endswith("ff.ff1.weight") or n.endswith("ff.ff1.bias")
+    assert max(d for d, n in devs if relu(n)) < 1.5e-1
+    assert max(d for d, n in devs if not relu(n)) < 2e-2
     assert sum(d for d, _ in devs) / len(devs) < 2e-2
 
 
