@@ -590,15 +590,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   unsigned char* sKk = base;                         // per key tile: K K-major, V K-major, K MN-major
   unsigned char* sVk = sKk + kTileBytes;
   unsigned char* sKm = sVk + kTileBytes;
-  unsigned char* sQk = sKm + kTileBytes;             // per query chunk: Q K-major, Q MN-major, dO K-major, dO MN-major
-  unsigned char* sQm = sQk + kTileBytes;
-  unsigned char* sDOk = sQm + kTileBytes;
-  unsigned char* sDOm = sDOk + kTileBytes;
-  unsigned char* sY = sDOm + kTileBytes;             // dS^T chunk, q contiguous: 4 slabs x 128 key rows
+  // Per query chunk, slots of three tiles: {Q K-major, dO MN-major, -} in phase 1 and {Q K-major, Q MN-major, dO K-major}
+  // in phase 2.  DB (rows without trailing positions): two slots, slot = step & 1, and the loads of step s + 1 are issued
+  // when step s starts (its slot was last read by step s - 1, whose MMAs have retired), so their latency hides behind a
+  // whole step: T = 193 bwd 2.95 -> 2.71 ms, T = 384 3.33 -> 3.07 ms.  With trailing positions the extra 48 KB of shared memory
+  // cost the trailing-key section its L1 hits (230 KB of shared memory leave 28 KB of L1: T = 260 3.25 -> 3.77 ms), so those
+  // variants keep one slot and load at the start of the step.  SINGLE: four tiles, loaded once.
+  constexpr bool DB = !TAIL;
+  constexpr int kChunkTiles = SINGLE ? 4 : (DB ? 6 : 3);
+  unsigned char* sC = sKm + kTileBytes;
+  unsigned char* sY = sC + kChunkTiles * kTileBytes;   // dS^T chunk, q contiguous: 4 slabs x 128 key rows
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sY + 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_kt = &bars[0];
-  unsigned long long* bar_qc = &bars[1];
+  unsigned long long* bar_ld = &bars[4];             // [2]: chunk tiles of a slot have landed
   unsigned long long* bar_m1 = &bars[2];
   unsigned long long* bar_m2 = &bars[3];
   __shared__ float red[256];
@@ -626,7 +631,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     fence_async_smem();
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -650,7 +655,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   for (int j = 0; j < 16; ++j) acc_k[j] = acc_v[j] = acc_q[j] = 0.f;
   float dqt[2] = {0.f, 0.f};                                // dQ[trailing query 2 ii + half][column lane], summed over the key tiles
 
-  unsigned step = 0;                                        // bar_qc / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
+  // chunk loads of step s of a key tile (s < NKT: phase 1, else phase 2) into the slot of global step g; thread 0 only
+  auto issue_chunk = [&](int s, unsigned g) {
+    const int slot = DB ? (int)(g & 1) : 0;
+    unsigned char* t0 = sC + slot * 3 * kTileBytes;
+    const int r0 = b * T + (s < NKT ? s : s - NKT) * kTile;
+    if (s < NKT) {
+      mbar_expect_tx(&bar_ld[slot], (unsigned)(2 * kTileBytes));
+      tma_load_2d(t0, &tmKm, &bar_ld[slot], D + h * DH, r0);
+      tma_load_2d(t0 + kTileBytes, &tmDOm, &bar_ld[slot], h * DH, r0);
+    } else {
+      mbar_expect_tx(&bar_ld[slot], (unsigned)((Q0 ? 2 : 3) * kTileBytes));
+      tma_load_2d(t0, &tmKm, &bar_ld[slot], D + h * DH, r0);
+      tma_load_2d(t0 + kTileBytes, &tmMn, &bar_ld[slot], D + h * DH, r0);
+      if (!Q0) tma_load_2d(t0 + 2 * kTileBytes, &tmDOk, &bar_ld[slot], h * DH, r0);
+    }
+  };
+  unsigned char* const sDOk1 = sC + 2 * kTileBytes;         // SINGLE: dO K-major (read by the dP MMA issued with phase 1)
+  unsigned char* const sQm1 = sC + 3 * kTileBytes;          // SINGLE: Q MN-major
+  unsigned step = 0;                                        // bar_ld / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
 #pragma unroll 1
   for (int kt = 0; kt < NKT; ++kt) {
     const int kg = kt * kTile + row;
@@ -667,14 +690,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       tma_load_2d(sKk, &tmKm, bar_kt, h * DH, b * T + kt * kTile);
       tma_load_2d(sVk, &tmKm, bar_kt, 2 * D + h * DH, b * T + kt * kTile);
       if (SINGLE) {
-        tma_load_2d(sQk, &tmKm, bar_kt, D + h * DH, b * T);
+        tma_load_2d(sC, &tmKm, bar_kt, D + h * DH, b * T);                       // phase 1 = step 0 = slot 0: Q K-major, dO MN-major
         if (!Q0) {
-          tma_load_2d(sDOk, &tmDOk, bar_kt, h * DH, b * T);
-          tma_load_2d(sDOm, &tmDOm, bar_kt, h * DH, b * T);
+          tma_load_2d(sDOk1, &tmDOk, bar_kt, h * DH, b * T);
+          tma_load_2d(sC + kTileBytes, &tmDOm, bar_kt, h * DH, b * T);
         }
-        tma_load_2d(sQm, &tmMn, bar_kt, D + h * DH, b * T);
+        tma_load_2d(sQm1, &tmMn, bar_kt, D + h * DH, b * T);
       }
       tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);
+      if (DB && !SINGLE) issue_chunk(Q0 ? NKT : 0, step);
     }
     if (TAIL && kt == 0) {
       // while the first TMA loads are in flight — trailing key rows (thread = query, Q / dO rows straight from global
@@ -764,21 +788,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      const int slot = DB ? (int)(step & 1) : 0;
+      unsigned char* const sQk = sC + slot * 3 * kTileBytes;
+      unsigned char* const sDOm = sQk + kTileBytes;
       if (tid == 0) {
         if (!SINGLE) {
-          mbar_expect_tx(bar_qc, (unsigned)(2 * kTileBytes));
-          tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
-          tma_load_2d(sDOm, &tmDOm, bar_qc, h * DH, b * T + qc * kTile);
+          if (DB) issue_chunk(qc + 1, step + 1);           // the next step of this key tile (phase 1 or the first of phase 2)
+          else issue_chunk(qc, step);
         }
         if (qc == 0) mbar_wait(bar_kt, (unsigned)(kt & 1));
-        if (!SINGLE) mbar_wait(bar_qc, par);
+        if (!SINGLE) mbar_wait(&bar_ld[slot], DB ? ((step >> 1) & 1) : (step & 1));
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T (SINGLE: and dP = V dO^T, two independent chains)
           umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
                     idesc_s, k > 0 ? 1u : 0u);
           if (SINGLE)
-            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk) + k * 32, 16, 1024, 2),
+            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk1) + k * 32, 16, 1024, 2),
                       idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(bar_m1);
@@ -909,14 +935,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       const unsigned par = step & 1;
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      const int slot = DB ? (int)(step & 1) : 0;
+      unsigned char* const sQk = sC + slot * 3 * kTileBytes;
+      unsigned char* const sQm = SINGLE ? sQm1 : sQk + kTileBytes;
+      unsigned char* const sDOk = sQk + 2 * kTileBytes;
       if (!SINGLE || Q0) {
         if (tid == 0) {
           if (!SINGLE) {
-            mbar_expect_tx(bar_qc, (unsigned)((Q0 ? 2 : 3) * kTileBytes));
-            tma_load_2d(sQk, &tmKm, bar_qc, D + h * DH, b * T + qc * kTile);
-            tma_load_2d(sQm, &tmMn, bar_qc, D + h * DH, b * T + qc * kTile);
-            if (!Q0) tma_load_2d(sDOk, &tmDOk, bar_qc, h * DH, b * T + qc * kTile);
-            mbar_wait(bar_qc, par);
+            if (!DB) issue_chunk(NKT + qc, step);
+            else if (qc + 1 < NKT) issue_chunk(NKT + qc + 1, step + 1);
+            mbar_wait(&bar_ld[slot], DB ? ((step >> 1) & 1) : (step & 1));
           }
           tc_fence_after();
 #pragma unroll
@@ -1077,7 +1105,7 @@ constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBy
 constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
-constexpr size_t kBwdSmem = 1024 + (size_t)(7 + 4) * kTileBytes + 128;
+constexpr size_t bwd_smem(bool single, bool tail) { return 1024 + (size_t)(3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128; }
 
 }  // namespace
 
@@ -1166,6 +1194,7 @@ extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, con
   cudaStream_t st = (cudaStream_t)stream;
 #define MSX_TCL_BWD(NT_, NKT_, SINGLE_)                                                                                     \
   do {                                                                                                                   \
+    const size_t kBwdSmem = bwd_smem(SINGLE_, NKT_ < NT_);                                                               \
     if (q0_only) {                                                                                                       \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, true>,                                       \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));                        \
