@@ -365,14 +365,16 @@ def test_bf16_graphed_step_runs():
         assert float((res[0][i] - res[1][i]).abs().max()) < 2e-3 * scale, i
 
 
-@pytest.mark.parametrize("T", [129, 257])
-def test_tf32_long_rows_step_vs_oracle(T):
-    """The L = 128 / 256 sweep points: the step with the long-row tcgen05 attention (msx_attention_tcl_*) vs the oracle."""
+@pytest.mark.parametrize("T", [129, 130, 257])
+@pytest.mark.parametrize("precision", ["tf32", "bf16p3f"])
+def test_tf32_long_rows_step_vs_oracle(T, precision):
+    """The L = 128 / 256 sweep points: the step with the long-row tcgen05 attention (msx_attention_tcl_*, the q0_only variants
+    in the top layer) vs the oracle, in single-pass TF32 and in the headline precision."""
     from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
     cfg_o = om.Cfg(dec_type="lstm")
     p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=0))
     tokens, seq_lens, classes, labels, eps = _batch(8, T, 293, 2, 256, seed=T, min_len=T // 2)
-    eng = VAEEngine(VAEConfig(dec_type="lstm"), "cuda:0", precision="tf32")
+    eng = VAEEngine(VAEConfig(dec_type="lstm"), "cuda:0", precision=precision)
     eng.arena.load_state(p)
     out = eng.forward(_dev(tokens), _dev(seq_lens), _dev(classes), _dev(labels), eps=_dev(eps, torch.float32))
     opt = om.Adam({k: v.clone() for k, v in p.items()}, clip_gradient=1.0)
@@ -381,13 +383,14 @@ def test_tf32_long_rows_step_vs_oracle(T):
     rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
     dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
     print("tf32 long-row forward deviation:", dev)
-    assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 1e-3, dev
+    ftol = 5e-4 if precision == "bf16p3f" else 1e-3       # measured: means 2.4e-4 ... 4.1e-4 (bf16p3f), 6.8e-4 ... 8.1e-4 (tf32)
+    assert dev["ce"] < ftol and dev["kl"] < ftol and dev["means"] < ftol, dev
     eng.backward()
     torch.cuda.synchronize()
     gmax = max(float(g.abs().max()) for g in grads.values())
     devs = sorted(((rel(eng.arena.grad(n), grads[n]), n) for n in eng.arena.names()
                    if float(grads[n].abs().max()) > 1e-4 * gmax), reverse=True)
-    print("tf32 long-row gradient deviation, worst tensors:", devs[:4])
+    print("long-row gradient deviation, worst tensors:", devs[:4])
     # The feed-forward's first layer sits behind a ReLU: with 8 rows a single unit whose pre-activation is within the TF32
     # rounding of zero flips its mask and moves ff1.weight / ff1.bias by a few per cent of their scale, whichever kernel
     # produced the rounding (profiles/micro/diag_long_rows_r2.txt: 2e-2 ... 8e-2 for every seed under single-pass TF32,
