@@ -6,11 +6,14 @@
 // _mask_logits, /root/reference/music_style_transfer/VarAutoEncoder/transformer.py:91-126):
 //   S[k][q] = K_k . Q_q / sqrt(d_h) + (key k padded ? -1e9 : 0);  P = softmax over the QUERY axis;  O[q] = sum_k P[k][q] V[k]
 //
-// The softmax normalises each KEY row over all queries, so key tiles are independent: one CTA (128 threads) per
+// The softmax normalises each KEY row over all queries, so key tiles are independent: one CTA (256 threads) per
 // (batch, head) walks the key tiles of 128; for a key tile the scores of ALL queries accumulate in TMEM with the keys
-// on the lanes (S[128 x TQ], up to 384 columns), the thread that owns a key row does max / exp2 / sum over its TMEM
-// columns, and the normalised row goes out in query chunks of 128 as the MN-major A operand of O[chunk] += P^T V
-// (double-buffered in shared memory), O accumulating over key tiles in TMEM.  The forward saves (max * log2 e,
+// on the lanes (S[128 x TQ], up to 384 columns), the TWO threads that own a key row (warps w and w + 4 reach the same
+// TMEM lane quarter) do max / exp2 / sum over their halves of its TMEM columns, and the normalised row goes out in
+// query chunks of 128 as the MN-major A operand of O[chunk] += P^T V (double-buffered in shared memory), O accumulating
+// over key tiles in TMEM.  Both kernels are bound by the instruction stream of the row owners (ncu: 18 % issue utilisation
+// with 128 threads, stall samples spread evenly over a straight-line stream), hence two threads per row, the single-tile
+// specialisations and the q0_only variants below; measurements in profiles/micro/attn_long_rate_r2.txt.  The forward saves (max * log2 e,
 // 1 / sum) per key row; the backward rebuilds P from them chunk by chunk (flash-attention style), so it never needs
 // more than 128 score columns at a time:
 //   phase 1 (per key tile, over query chunks):  P -> TMEM,  dV += P dO            (A operand from TMEM)
