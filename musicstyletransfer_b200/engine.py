@@ -1004,10 +1004,9 @@ class VAEEngine:
         intent of the reference loop, which is inconsistent at HEAD).  Returns (sequences int32 [B*beam, <= 2T],
         scores fp32 [B*beam]); hypotheses of row b are b*beam .. b*beam+beam-1, best first."""
         cfg, dev = self.cfg, self.device
-        assert cfg.dec_type == "lstm" and cfg.dec_layers == 1, \
-            "beam search follows the reference's LSTM-decoder API (sampler.py:222), single layer"
+        assert cfg.dec_type == "lstm", "beam search follows the reference's LSTM-decoder API (sampler.py:222)"
         B, T = tokens.shape
-        K, Z, V, Hd = int(beam_size), cfg.latent, cfg.vocab, cfg.dec_size
+        K, Z, V, Hd, NL = int(beam_size), cfg.latent, cfg.vocab, cfg.dec_size, cfg.dec_layers
         I_max, R = 2 * T, B * int(beam_size)
         bf = self._buf(B, T)
         _, _, lat = self._encode(bf, tokens, classes_target, B, T, 0.0)
@@ -1018,11 +1017,15 @@ class VAEEngine:
         self._dense_fwd(lat, 2 * Z, B, "decoder.latent2hid.weight", "decoder.latent2hid.bias", tv, 2 * Hd, 2 * Hd, Z,
                         accumulate=True)
         bb = self._buf(R, -3)
-        h = [bb.get("bs.h%d" % i, (R, Hd), dev) for i in range(2)]
-        c = [bb.get("bs.c%d" % i, (R, Hd), dev) for i in range(2)]
-        h[0].copy_(tv[:, :Hd].repeat_interleave(K, dim=0))           # mx.nd.repeat(state, beam_size, axis=1), sampler.py:212
-        c[0].copy_(tv[:, Hd:].repeat_interleave(K, dim=0))
-        hn, cn, hp = bb.get("bs.hn", (R, Hd), dev), bb.get("bs.cn", (R, Hd), dev), bb.get("bs.hp", (R, Hd), dev)
+        # per layer two (h, c) pairs: the states the step reads and the reordered states of the winners
+        h = [[bb.get("bs.h%d_%d" % (l, i), (R, Hd), dev) for i in range(2)] for l in range(NL)]
+        c = [[bb.get("bs.c%d_%d" % (l, i), (R, Hd), dev) for i in range(2)] for l in range(NL)]
+        for l in range(NL):                                            # every layer starts from (h0, c0), model.py:159-167;
+            h[l][0].copy_(tv[:, :Hd].repeat_interleave(K, dim=0))      # mx.nd.repeat(state, beam_size, axis=1), sampler.py:212
+            c[l][0].copy_(tv[:, Hd:].repeat_interleave(K, dim=0))
+        hn = [bb.get("bs.hn%d" % l, (R, Hd), dev) for l in range(NL)]
+        cn = [bb.get("bs.cn%d" % l, (R, Hd), dev) for l in range(NL)]
+        hp = bb.get("bs.hp", (R, Hd), dev)
         seq = [bb.get("bs.seq%d" % i, (R, I_max), dev, torch.int32) for i in range(2)]
         for sq in seq:
             sq.zero_()
@@ -1034,22 +1037,28 @@ class VAEEngine:
         parent = bb.get("bs.parent", (R,), dev, torch.int32)
         unfinished = bb.get("bs.unfinished", (I_max,), dev, torch.int32)
         unfinished.zero_()
-        xe, gates = bb.get("bs.xe", (R, Hd), dev), bb.get("bs.gates", (R, 4 * Hd), dev)
+        gates = bb.get("bs.gates", (R, 4 * Hd), dev)
         logits = bb.get("bs.logits", (R, self.ldv), dev)
         cur = 0
         tab = bb.get("bs.i2h_table", (V, 4 * Hd), dev)              # emb W_i2h^T + b_i2h, see style_transfer
         self._dense_fwd(W("decoder.embedding.weight"), Hd, V, "decoder.decoder.l0_i2h_weight", "decoder.decoder.l0_i2h_bias",
                         tab, 4 * Hd, 4 * Hd, Hd)
         for i in range(1, I_max):
-            ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, R, 1, 4 * Hd, 0, 1.0, V)
-            step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, Hd, h[cur], c[cur])) else ops.lstm_fwd
-            step(gates, W("decoder.decoder.l0_h2h_weight"), W("decoder.decoder.l0_h2h_bias"), h[cur], c[cur], Hd,
-                 hn, hp, cn, R, 1, Hd)
-            self._dense_fwd(hn, Hd, R, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V, Hd)
+            for l in range(NL):
+                if l == 0:
+                    ops.embed_fwd(nxt, None, None, tab, None, None, None, gates, None, R, 1, 4 * Hd, 0, 1.0, V)
+                else:                                               # input of layer l = h of the layer below (model.py:192-195)
+                    self._dense_fwd(hn[l - 1], Hd, R, "decoder.decoder.l%d_i2h_weight" % l, "decoder.decoder.l%d_i2h_bias" % l,
+                                    gates, 4 * Hd, 4 * Hd, Hd, decoder=True)
+                step = ops.lstm_tc_fwd if (self.lstm_tc and ops.lstm_tc_supported(Hd, Hd, h[l][cur], c[l][cur])) else ops.lstm_fwd
+                step(gates, W("decoder.decoder.l%d_h2h_weight" % l), W("decoder.decoder.l%d_h2h_bias" % l), h[l][cur], c[l][cur],
+                     Hd, hn[l], hp, cn[l], R, 1, Hd)
+            self._dense_fwd(hn[NL - 1], Hd, R, "decoder.output_layer.weight", "decoder.output_layer.bias", logits, self.ldv, V, Hd)
             ops.beam_step(logits, self.ldv, V, B, K, seq[cur], seq[cur ^ 1], I_max, i, score[cur], score[cur ^ 1], parent,
                           nxt, unfinished)
-            ops.gather_rows(hn, h[cur ^ 1], parent, R, Hd)
-            ops.gather_rows(cn, c[cur ^ 1], parent, R, Hd)
+            for l in range(NL):
+                ops.gather_rows(hn[l], h[l][cur ^ 1], parent, R, Hd)
+                ops.gather_rows(cn[l], c[l][cur ^ 1], parent, R, Hd)
             cur ^= 1
         left = unfinished.cpu()[1:]
         done = (left == 0).nonzero()

@@ -164,6 +164,37 @@ def test_beam_search_matches_oracle(beam):
     sc = score.cpu().view(B, beam)
     assert bool((sc[:, 1:] >= sc[:, :-1] - 1e-6).all())
 
+@pytest.mark.parametrize("layers,dec_size", [(2, 32), (3, 48)])
+def test_beam_search_stacked_lstm_decoder(layers, dec_size):
+    """Beam search with n_layers > 1 (model.py:148-153, 185-203: every layer keeps its own (h, c), all start from the same
+    initial state, layer l reads h of layer l - 1): the winners' states of EVERY layer are reordered; vs the oracle."""
+    from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
+    kw = dict(enc_size=64, enc_layers=1, enc_heads=4, latent=16, dec_type="lstm", dec_size=dec_size, dec_layers=layers)
+    cfg_o = om.Cfg(**kw)
+    p = om.init_params(cfg_o, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    for k in p:
+        if k.endswith("bias"):
+            p[k] = 0.1 * torch.randn(p[k].shape, generator=gen)
+    p["decoder.output_layer.weight"] *= 3.0
+    p["decoder.output_layer.bias"][2] += 0.5
+    B, T, beam = 4, 6, 3
+    tokens = torch.randint(3, 293, (B, T), generator=gen).float()
+    tokens[:, 0] = 1
+    tokens[2, 3:] = 0
+    lens = (tokens != 0).sum(1).float()
+    target = torch.full((B,), 1.0)
+    want_seq, want_score = om.beam_search_lstm(cfg_o, p, tokens, target, beam)
+    eng = VAEEngine(VAEConfig(**kw), DEV)
+    eng.arena.load_state(p)
+    i32 = lambda t: t.to(torch.int32).to(DEV)
+    seqs, score = eng.beam_search(i32(tokens), i32(lens), i32(target), beam)
+    got = seqs.cpu().float()
+    assert got.shape == want_seq.shape, (got.shape, want_seq.shape)
+    assert bool((got == want_seq).all()), (got, want_seq)
+    assert float((score.cpu() - want_score).abs().max()) < 1e-3 * (1.0 + float(want_score.abs().max()))
+
+
 
 def test_model_entry_points_and_toy_training(tmp_path):
     """Model(config)(tokens, seq_lens, classes) -> (probs, means, vars); Trainer.fit on ToyData (main.py:58-76) lowers
