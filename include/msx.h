@@ -213,8 +213,8 @@ int msx_attention_tc_bwd_ex(const float* qkv, const float* mask, const float* dc
 int msx_attention_tc_bwd_q0(const float* qkv, const float* mask, const float* dctx, void* dqkv, int dqkv_bf16, float* dbias,
                             int q0_only, int B, int T, int H, int dh, void* stream);
 int msx_attention_tc_set_trace(long long* buf);
-/* Long rows, 128 < T <= 384 (the L = 128 / 256 sweep points): key tiles and query chunks of 128, flash-attention style
- * backward.  stats [B*H*T, 2] fp32 (row max * log2 e, 1 / row sum of every key row) is written by the forward and read
+/* Long rows, 128 < T <= 768 (the L = 128 / 256 sweep points and beyond; T > 384: two-sweep forward): key tiles and query
+ * chunks of 128, flash-attention style backward.  stats [B*H*T, 2] fp32 (row max * log2 e, 1 / row sum of every key row) is written by the forward and read
  * by the backward; ctx / dqkv are fp32 or bfloat16 by flag; dbias as msx_attention_tc_bwd. */
 int msx_attention_tcl_supported(const float* qkv, int T, int dh);
 int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int B, int T, int H,

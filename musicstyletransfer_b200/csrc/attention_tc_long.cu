@@ -1,4 +1,4 @@
-// K2c (tensor-core path, long rows) — attention in the reference's convention on tcgen05 for 128 < T <= 384, d_h = 32:
+// K2c (tensor-core path, long rows) — attention in the reference's convention on tcgen05 for 128 < T <= 768, d_h = 32:
 // the L = 128 / 256 points of the BASELINE config 3 sweep (T = 129 / 257), which attention_tc.cu (one key tile on the
 // 128 TMEM lanes) does not take.
 //
@@ -562,6 +562,354 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ forward, two sweeps
+// 384 < T <= 768 (NT = 4 ... 6 query chunks): the scores of a key tile against ALL queries no longer fit TMEM and the Q
+// tiles no longer fit shared memory next to the P staging.  Per key tile the query chunks are walked twice, one chunk of
+// 128 score columns at a time (Q chunks through a two-deep ring, the next one in flight while a chunk is processed;
+// MMA 1 is issued again in the second sweep — four small MMAs per chunk):
+//   sweep 1: running row maximum / sum over the chunks (online softmax) -> the statistics of the key rows
+//   sweep 2: P = exp2(s - max) / sum -> shared memory -> O[chunk] += P^T V      (Q0: one column sum for query 0 instead)
+// Thread layout, trailing positions and epilogue as in attn_tcl_fwd_kernel.
+template <int NT, int NKT, bool Q0>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+    attn_tcl_fwd2_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
+                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
+                         const AttnLongParams p) {
+  pdl_entry();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sQ = base;                          // two K-major query-chunk tiles (ring)
+  unsigned char* sK = sQ + 2 * kTileBytes;           // K-major key tile
+  unsigned char* sV = sK + kTileBytes;               // MN-major value tile
+  unsigned char* sP = sV + kTileBytes;               // 2 x 4 slabs: P chunk, q contiguous, 128 key rows per slab
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sP + 2 * 4 * kTileBytes);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+  unsigned long long* bar_q = &bars[0];              // [2]
+  unsigned long long* bar_k = &bars[2];
+  unsigned long long* bar_v = &bars[3];
+  unsigned long long* bar_s = &bars[4];
+  unsigned long long* bar_o = &bars[5];              // [2]
+  static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
+  static_assert(NT * DH <= 256, "O accumulators: TMEM columns 0 .. 255, S in 256 .. 383");
+  constexpr bool TAIL = NKT < NT;
+  constexpr int NQQ = (NT * kTile + kFwdThreads - 1) / kFwdThreads;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;
+  const int c0 = half * 64, h16 = half * 16;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T, TQ = p.TQ, D = p.H * DH;
+  const int ntail = TAIL ? tail_keys(T) : 0;
+  __shared__ float xs_m[2][kTile], xs_l[2][kTile];   // running (max, sum) of the two column halves of every key row
+  __shared__ float red8[8];
+  __shared__ float red[TAIL ? 256 : 1];
+  __shared__ float red_q[Q0 ? 256 : 1];
+  __shared__ float ot_s[kTailMax][32];
+  __shared__ float pt_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];
+  __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];
+  if (TAIL) fetch_tail_rows<kFwdThreads / 32>(tr_s, p.qkv, nullptr, (size_t)b * T + (size_t)(NT - 1) * kTile, ntail, D, h, warp, lane);
+
+  if (!TAIL && !Q0) {                                // short last query chunk: the MMAs read the whole staging tile
+    for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += kFwdThreads * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = *tmem_slot;
+  const unsigned tm_O = tmem, tm_S = tmem + 256;
+  const unsigned lane_off = (unsigned)(quarter * 32) << 16;
+  const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
+                          ((unsigned)(128 >> 4) << 24);
+
+  // Q chunk qc into the ring slot of global step gg (thread 0; the slot's previous reader, step gg - 2, has retired)
+  auto issue_q = [&](int qc, unsigned gg) {
+    const int slot = (int)(gg & 1);
+    mbar_expect_tx(&bar_q[slot], (unsigned)kTileBytes);
+    tma_load_2d(sQ + slot * kTileBytes, &tmKm, &bar_q[slot], D + h * DH, b * T + qc * kTile);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(bar_k, (unsigned)kTileBytes);
+    tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T);
+    mbar_expect_tx(bar_v, (unsigned)kTileBytes);
+    tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T);
+    issue_q(0, 0);
+  }
+  if (TAIL) {
+    // trailing key rows (thread = query, Q rows straight from global memory, rounded like the TMA unit rounds them; K[k*] from
+    // the fetch at kernel start): softmax over the query axis across the CTA, P[k*][q] kept for the output rows
+#pragma unroll 1
+    for (int i = 0; i < ntail; ++i) {
+      const int ks = (NT - 1) * kTile + i;
+      const float rmask = __ldg(p.mask + (size_t)b * T + ks) > 0.f ? 0.f : -1e9f;
+      float sc[NQQ];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int qq = 0; qq < NQQ; ++qq) {
+        const int q = qq * kFwdThreads + tid;
+        sc[qq] = 0.f;
+        if (q < T) {
+          float qr[32];
+          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 q4 = __ldg(qp + c);
+            qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
+          }
+          sc[qq] = fmaf(dot32_tf32(tr_s[kTrK][i], qr), p.inv_scale, rmask);
+          mx = fmaxf(mx, sc[qq]);
+        }
+      }
+      const float mxl = block_max256(mx, red8, tid) * kLog2e;
+      float sum = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < NQQ; ++qq) {
+        sc[qq] = (qq * kFwdThreads + tid < T) ? exp2f(fmaf(sc[qq], kLog2e, -mxl)) : 0.f;
+        sum += sc[qq];
+      }
+      const float inv = 1.f / block_sum256(sum, red8, tid);
+#pragma unroll
+      for (int qq = 0; qq < NQQ; ++qq)
+        if (qq * kFwdThreads + tid < T) pt_s[i][qq * kFwdThreads + tid] = sc[qq] * inv;
+      if (tid == 0) reinterpret_cast<float2*>(p.stats)[(size_t)(b * p.H + h) * T + ks] = make_float2(mxl, inv);
+    }
+  }
+  float o0 = 0.f;                                     // Q0: O[0][column lane]
+  float ot[kTailMax / 2];
+#pragma unroll
+  for (int i = 0; i < kTailMax / 2; ++i) ot[i] = 0.f;
+  unsigned g = 0;                                     // global step: Q ring slot g & 1, bar_s parity g & 1
+  int n = 0;                                          // MMA 2 counter: P buffer n & 1
+  constexpr int kSteps = (Q0 ? 1 : 2) * NKT;          // steps per key tile
+#pragma unroll 1
+  for (int kt = 0; kt < NKT; ++kt) {
+    const unsigned par = (unsigned)(kt & 1);
+    const int kg = kt * kTile + row;
+    const bool valid = kg < T;
+    const float rowmask = (valid && __ldg(p.mask + (size_t)b * T + kg) > 0.f) ? 0.f : -1e9f;
+    float st[kTailMax];
+#pragma unroll
+    for (int i = 0; i < kTailMax; ++i) st[i] = 0.f;
+    if (TAIL) {                                       // this key row's scores against the trailing queries (both threads)
+      mbar_wait(bar_k, par);
+      float kr[32];
+      load_row_km(sK, row, kr);
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i) {
+        if (i < ntail) {
+          float qr[32];
+          load_row32(tr_s[kTrQt][i], qr);
+          st[i] = fmaf(dot32(kr, qr), p.inv_scale, rowmask);
+        }
+      }
+    }
+    float m = -INFINITY, l = 0.f, s0 = 0.f, mxl = 0.f, inv = 0.f;
+#pragma unroll 1
+    for (int u = 0; u < kSteps; ++u, ++g) {
+      const int qc = u < NKT ? u : u - NKT;
+      const bool sweep2 = u >= NKT;
+      const int nq = min(kTile, TQ - qc * kTile);
+      if (tid == 0) {
+        mbar_wait(&bar_q[g & 1], (g >> 1) & 1);
+        if (u == 0) mbar_wait(bar_k, par);
+        tc_fence_after();
+        const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+#pragma unroll
+        for (int k = 0; k < DH / 8; ++k)
+          umma_tf32(tm_S, make_desc(smem_u32(sK) + k * 32, 16, 1024, 2),
+                    make_desc(smem_u32(sQ) + (g & 1) * kTileBytes + k * 32, 16, 1024, 2), idesc1, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        // the next chunk (this key tile's next step, or the first of the next key tile) into the other ring slot
+        if (u + 1 < kSteps) issue_q(u + 1 < NKT ? u + 1 : u + 1 - NKT, g + 1);
+        else if (kt + 1 < NKT) issue_q(0, g + 1);
+      }
+      __syncwarp();
+      mbar_wait(bar_s, g & 1);
+      tc_fence_after();
+      const int cend = min(nq, c0 + 64);
+      if (!sweep2) {
+        // sweep 1: chunk maximum, then the running sum rescaled to the new maximum
+        float cm = -INFINITY;
+        for (int c = c0; c < cend; c += 16) {
+          float v[16];
+          tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (TAIL || qc * kTile + c + j < T) cm = fmaxf(cm, fmaf(v[j], p.inv_scale, rowmask));
+          if (Q0 && qc == 0 && c == 0) s0 = fmaf(v[0], p.inv_scale, rowmask);
+        }
+        // Rescale by the difference of the two ROUNDED products max * log2 e, the very numbers the element exponents
+        // fmaf(s, log2 e, -ml) are taken against: for a padded key row s = -1e9 + x collapses to -1e9, max * log2 e carries a
+        // rounding error of up to 2^6 and that error must enter sum and elements as the same factor (it cancels in P).
+        if (cm > m) {                                  // exp2(-inf) = 0 covers the first chunk
+          l *= exp2f(__fmul_rn(m, kLog2e) - __fmul_rn(cm, kLog2e));      // __fmul_rn: never contracted into an FMA
+          m = cm;
+        }
+        const float ml = __fmul_rn(m, kLog2e);
+        for (int c = c0; c < cend; c += 16) {
+          float v[16];
+          tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (TAIL || qc * kTile + c + j < T) l += exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -ml));
+        }
+        tc_fence_before();
+        __syncthreads();                               // every thread has read S: the next MMA 1 may overwrite it
+        if (u == NKT - 1) {
+          // the row's statistics: both column halves and the trailing queries (both threads compute the same values)
+          xs_m[half][row] = m;
+          xs_l[half][row] = l;
+          __syncthreads();
+          float M = fmaxf(xs_m[0][row], xs_m[1][row]);
+#pragma unroll
+          for (int i = 0; i < kTailMax; ++i)
+            if (i < ntail) M = fmaxf(M, st[i]);
+          mxl = __fmul_rn(M, kLog2e);
+          float L = xs_l[0][row] * exp2f(__fmul_rn(xs_m[0][row], kLog2e) - mxl) + xs_l[1][row] * exp2f(__fmul_rn(xs_m[1][row], kLog2e) - mxl);
+#pragma unroll
+          for (int i = 0; i < kTailMax; ++i) {
+            if (i < ntail) {
+              st[i] = exp2f(fmaf(st[i], kLog2e, -mxl));
+              L += st[i];
+            }
+          }
+          inv = valid ? 1.f / L : 0.f;
+          if (valid && half == 0) {
+            float2* stp = reinterpret_cast<float2*>(p.stats) + ((size_t)(b * p.H + h) * T + kg);
+            *stp = make_float2(mxl, inv);
+          }
+        }
+      } else {
+        // sweep 2: normalised chunk -> shared memory -> MMA 2
+        const int buf = n & 1;
+        unsigned char* pb = sP + buf * 4 * kTileBytes;
+        if (n >= 2) {
+          mbar_wait(&bar_o[buf], (unsigned)(((n >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        for (int c = c0; c < cend; c += 16) {
+          float v[16];
+          tmem_ld16(tm_S + lane_off + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (TAIL || qc * kTile + c + j < T) ? to_tf32(exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(pb + mn_major_off(c + j, row, kTile)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();                               // P staged, S read by every thread
+        if (tid == 0) {
+          tc_fence_after();
+          if (qc == 0) mbar_wait(bar_v, par);
+          for (int j = 0; j < kTile / 8; ++j)
+            umma_tf32(tm_O + qc * DH, make_desc(smem_u32(pb) + j * 1024, kTileBytes, 512, 1),
+                      make_desc(smem_u32(sV) + j * 1024, kTileBytes, 512, 1), idesc2, (kt > 0 || j > 0) ? 1u : 0u);
+          umma_commit(&bar_o[buf]);
+        }
+        __syncwarp();
+        ++n;
+      }
+    }
+    if (Q0) {
+      // O[0] += sum over this tile's keys of P[k][0] V[k] (the second threads of the rows add zeros)
+      mbar_wait(bar_v, par);
+      float c[32];
+      load_row_mn(sV, row, c);
+      const float p0 = (half == 0) ? exp2f(fmaf(s0, kLog2e, -mxl)) * inv : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c[j] *= p0;
+      o0 += half_colsum128(c, red_q, tid);
+    } else if (TAIL) {
+      // while the MMA 2s run: O[q*] += sum over this tile's keys of P[k][q*] V[k]
+      mbar_wait(bar_v, par);
+      float vr[32];
+      load_row_mn(sV, row, vr);
+#pragma unroll
+      for (int ii = 0; ii < kTailMax / 2; ++ii) {
+        if (2 * ii < ntail) {
+          const float pt = ((half == 0) ? st[2 * ii] : st[2 * ii + 1]) * inv;
+          float c[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = pt * vr[j];
+          ot[ii] += half_colsum128(c, red, tid);
+        }
+      }
+    }
+    if (tid == 0 && kt + 1 < NKT) {
+      // the key tile's K and V are free: every MMA 1 has retired (bar_s waits), the last MMA 2 is waited for here
+      if (!Q0) {
+        const int last = n - 1;
+        mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+      }
+      mbar_expect_tx(bar_k, (unsigned)kTileBytes);
+      tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
+      mbar_expect_tx(bar_v, (unsigned)kTileBytes);
+      tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
+    }
+    __syncthreads();                                  // xs_* / V row reads are done before the next key tile
+  }
+  if (Q0) {
+    if (warp == 0) {
+      if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < kTailMax; ++i)
+          if (i < ntail) o0 = fmaf(pt_s[i][0], tr_s[kTrV][i][lane], o0);
+      }
+      const size_t e = (size_t)b * T * D + h * DH + lane;
+      if (p.out_bf16) reinterpret_cast<unsigned short*>(p.out)[e] = __bfloat16_as_ushort(__float2bfloat16_rn(o0));
+      else reinterpret_cast<float*>(p.out)[e] = o0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    return;
+  }
+  {
+    const int last = n - 1;
+    mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+    tc_fence_after();
+  }
+  if (TAIL) {
+    if (quarter == 0) {
+#pragma unroll
+      for (int ii = 0; ii < kTailMax / 2; ++ii) ot_s[2 * ii + half][lane] = ot[ii];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int qc = 0; qc < NT; ++qc) {
+    const int q = qc * kTile + row;
+    float o[16];
+    if (qc < NKT) {
+      tmem_ld16(tm_O + lane_off + qc * DH + h16, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = ot_s[row & (kTailMax - 1)][h16 + j];
+    }
+    if (TAIL && q < T) {
+#pragma unroll
+      for (int i = 0; i < kTailMax; ++i)
+        if (i < ntail) axpy16(pt_s[i][q], tr_s[kTrV][i] + h16, o);
+    }
+    if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH + h16, o, 16);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 // 256 threads: warps w and w + 4 share the TMEM lane quarter w & 3 (a warp reaches lanes 32 (w % 4) ... + 31), i.e. two
 // threads own one key row (one query row in the dQ epilogue) and split its columns — 64 + 64 score columns in the P and dS
@@ -1106,6 +1454,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 
 constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBytes + 128; }
 constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
+constexpr size_t kFwd2Smem = 1024 + (size_t)(2 + 2 + 8) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t bwd_smem(bool single, bool tail) { return 1024 + (size_t)(3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128; }
@@ -1113,7 +1462,7 @@ constexpr size_t bwd_smem(bool single, bool tail) { return 1024 + (size_t)(3 + (
 }  // namespace
 
 extern "C" int msx_attention_tcl_supported(const float* qkv, int T, int dh) {
-  return (qkv && dh == 32 && T > 128 && T <= 3 * kTile && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
+  return (qkv && dh == 32 && T > 128 && T <= 6 * kTile && ((uintptr_t)qkv & 15) == 0) ? 1 : 0;
 }
 
 extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int q0_only,
@@ -1130,7 +1479,7 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
                                         int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx && stats, "msx_attention_tcl_fwd: null pointer");
   MSX_REQUIRE(msx_attention_tcl_supported(qkv, T, dh) && ((uintptr_t)ctx & 15) == 0 && ((uintptr_t)stats & 7) == 0,
-              "msx_attention_tcl_fwd: needs d_h == 32, 128 < T <= 384, 16-byte aligned buffers");
+              "msx_attention_tcl_fwd: needs d_h == 32, 128 < T <= 768, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnLongParams p;
@@ -1157,14 +1506,39 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
                           tk, tm, p));                                                                                   \
     }                                                                                                                    \
   } while (0)
+#define MSX_TCL_FWD2(NT_, NKT_)                                                                                            \
+  do {                                                                                                                   \
+    if (q0_only) {                                                                                                       \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)kFwd2Smem));                                                                    \
+      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, true>, dim3(B * H), dim3(kFwdThreads), kFwd2Smem, st, tk, tm,  \
+                          p));                                                                                           \
+    } else {                                                                                                             \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kFwd2Smem));                                                                    \
+      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, false>, dim3(B * H), dim3(kFwdThreads), kFwd2Smem, st, tk, tm, \
+                          p));                                                                                           \
+    }                                                                                                                    \
+  } while (0)
   const bool tail = tail_keys(T) != 0;
-  if (T <= 2 * kTile) {
+  const int nt = (T + kTile - 1) / kTile;
+  if (nt == 2) {
     if (tail) MSX_TCL_FWD(2, 1, true, kFwdAliasSmem);  // T = 129 ... 132: one tile on the tensor path, two CTAs per SM
     else MSX_TCL_FWD(2, 2, false, fwd_smem(2));
-  } else {
+  } else if (nt == 3) {
     if (tail) MSX_TCL_FWD(3, 2, false, fwd_smem(3));   // T = 257 ... 260
     else MSX_TCL_FWD(3, 3, false, fwd_smem(3));
+  } else if (nt == 4) {                                // 384 < T <= 768: two sweeps over the query chunks
+    if (tail) MSX_TCL_FWD2(4, 3);
+    else MSX_TCL_FWD2(4, 4);
+  } else if (nt == 5) {
+    if (tail) MSX_TCL_FWD2(5, 4);
+    else MSX_TCL_FWD2(5, 5);
+  } else {
+    if (tail) MSX_TCL_FWD2(6, 5);
+    else MSX_TCL_FWD2(6, 6);
   }
+#undef MSX_TCL_FWD2
 #undef MSX_TCL_FWD
   MSX_LAUNCH_CHECK();
   return MSX_OK;
@@ -1180,7 +1554,7 @@ extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, con
   MSX_REQUIRE(qkv && mask && dctx && stats && dqkv, "msx_attention_tcl_bwd: null pointer");
   MSX_REQUIRE(msx_attention_tcl_supported(qkv, T, dh) && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)dqkv & 15) == 0 &&
                   ((uintptr_t)stats & 7) == 0,
-              "msx_attention_tcl_bwd: needs d_h == 32, 128 < T <= 384, 16-byte aligned buffers");
+              "msx_attention_tcl_bwd: needs d_h == 32, 128 < T <= 768, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnLongParams p;
@@ -1211,12 +1585,22 @@ extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, con
     }                                                                                                                    \
   } while (0)
   const bool tail = tail_keys(T) != 0;
-  if (T <= 2 * kTile) {
+  const int nt = (T + kTile - 1) / kTile;
+  if (nt == 2) {
     if (tail) MSX_TCL_BWD(2, 1, true);                 // T = 129 ... 132: one tile on the tensor path
     else MSX_TCL_BWD(2, 2, false);
-  } else {
+  } else if (nt == 3) {
     if (tail) MSX_TCL_BWD(3, 2, false);                // T = 257 ... 260
     else MSX_TCL_BWD(3, 3, false);
+  } else if (nt == 4) {                                // 384 < T <= 768: dQ accumulators fill TMEM columns 64 .. 255
+    if (tail) MSX_TCL_BWD(4, 3, false);
+    else MSX_TCL_BWD(4, 4, false);
+  } else if (nt == 5) {
+    if (tail) MSX_TCL_BWD(5, 4, false);
+    else MSX_TCL_BWD(5, 5, false);
+  } else {
+    if (tail) MSX_TCL_BWD(6, 5, false);
+    else MSX_TCL_BWD(6, 6, false);
   }
 #undef MSX_TCL_BWD
   MSX_LAUNCH_CHECK();

@@ -235,7 +235,7 @@ def attention_tc_bwd(qkv, mask, dctx, dqkv, B, T, H, dh, dbias=None, q0_only=Fal
 
 
 def attention_tcl_supported(qkv, T, dh):
-    """tcgen05 attention for long rows (128 < T <= 384)."""
+    """tcgen05 attention for long rows (128 < T <= 768)."""
     return bool(lib.load().msx_attention_tcl_supported(P(qkv), _i(T), _i(dh)))
 
 

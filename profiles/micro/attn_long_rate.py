@@ -24,7 +24,7 @@ def timed(fn, n=10):
     return e0.elapsed_time(e1) * 1000 / n
 
 
-for T in [int(a) for a in sys.argv[1:]] or (65, 128, 129, 130, 132, 133, 193, 257, 260, 384):
+for T in [int(a) for a in sys.argv[1:]] or (65, 128, 129, 130, 132, 133, 193, 257, 260, 384, 513, 768):
     B = max(1, TOK // T)
     qkv = torch.randn(B * T, 3 * D, device="cuda")
     mask = torch.ones(B * T, device="cuda")
@@ -44,6 +44,10 @@ for T in [int(a) for a in sys.argv[1:]] or (65, 128, 129, 130, 132, 133, 193, 25
         f0 = timed(lambda: ops.attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh, q0_only=True))
         b0 = timed(lambda: ops.attention_tcl_bwd(qkv, mask, dctx, stats, dqkv, B, T, H, dh, dbias=db, q0_only=True))
         print("attn_tcl T=%3d B=%4d: q0_only fwd %7.1f us   bwd %7.1f us" % (T, B, f0, b0))
+    if T > 384:                                   # what ran these rows before the two-sweep forward: the exact FFMA key-tiled kernels
+        ft = timed(lambda: ops.attention_tiled_fwd(qkv, mask, ctx, B, T, H, dh), n=3)
+        bt = timed(lambda: ops.attention_tiled_bwd(qkv, mask, dctx, dqkv, B, T, H, dh), n=3)
+        print("attn_tiled (FFMA) T=%3d B=%4d: fwd %7.1f us   bwd %7.1f us" % (T, B, ft, bt))
     items = B * H
     print("%s T=%3d B=%4d: fwd %7.1f us (%5.2f us per (b,h) per SM)   bwd %7.1f us (%5.2f)   fwd %.1f / bwd %.1f ns per token"
           % (name, T, B, f, f * 148 / items, b, b * 148 / items, f * 1e3 / (B * T), b * 1e3 / (B * T)))

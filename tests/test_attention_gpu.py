@@ -161,10 +161,13 @@ def test_attention_backward_query0_only(B, T, H, out16):
 
 # ------------------------------------------------------------------------------------------------ long rows (T > 128)
 @pytest.mark.parametrize("B,T,H", [(2, 129, 2), (3, 257, 2), (2, 200, 3), (5, 256, 1), (2, 384, 2), (40, 129, 8), (3, 144, 2),
-                                   (3, 130, 2), (4, 131, 3), (3, 132, 2), (2, 133, 2), (4, 258, 2), (3, 260, 1), (300, 129, 8)])
+                                   (3, 130, 2), (4, 131, 3), (3, 132, 2), (2, 133, 2), (4, 258, 2), (3, 260, 1), (300, 129, 8),
+                                   (2, 385, 2), (3, 388, 1), (2, 400, 2), (2, 512, 1), (3, 513, 2), (2, 516, 1), (2, 600, 2),
+                                   (2, 641, 1), (2, 700, 2), (2, 768, 1), (40, 513, 8)])
 @pytest.mark.parametrize("out16", [False, True])
 def test_attention_long_rows(B, T, H, out16):
-    """msx_attention_tcl_fwd / _bwd (key tiles + query chunks of 128) vs the float64 reference formula and autograd."""
+    """msx_attention_tcl_fwd / _bwd (key tiles + query chunks of 128; T > 384: the two-sweep forward) vs the float64 reference
+    formula and autograd."""
     from musicstyletransfer_b200 import ops
     dh = 32
     qkv, mask = _inputs(B, T, H, dh, seed=T)
@@ -197,7 +200,8 @@ def test_attention_long_rows(B, T, H, out16):
 
 
 @pytest.mark.parametrize("B,T,H", [(3, 129, 2), (2, 130, 3), (3, 132, 2), (2, 133, 2), (2, 200, 2), (3, 256, 1), (3, 257, 2), (2, 260, 2),
-                                   (2, 384, 2), (200, 129, 8)])
+                                   (2, 384, 2), (200, 129, 8), (2, 385, 2), (2, 400, 1), (3, 513, 2), (2, 516, 1), (2, 640, 2),
+                                   (2, 645, 1), (2, 768, 2)])
 @pytest.mark.parametrize("out16", [False, True])
 def test_attention_long_rows_q0(B, T, H, out16):
     """q0_only variants of the long-row kernels (the encoder's top layer under SOS-rows-only): the forward writes the context

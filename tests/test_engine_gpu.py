@@ -508,10 +508,10 @@ def test_stacked_lstm_decoder_vs_oracle(precision, layers, H, dropout):
             assert err <= 5e-2 * scale + 2e-5 * gscale, (name, err, scale)
 
 
-@pytest.mark.parametrize("precision,T", [("fp32", 400), ("tf32x3f", 513)])
+@pytest.mark.parametrize("precision,T", [("fp32", 400), ("tf32x3f", 513), ("tf32x3f", 800)])
 def test_rows_longer_than_384_positions(precision, T):
-    """--max-seq-len beyond the tensor-core attention kernels (T > 384): the step runs on the key-tiled exact attention and
-    matches the oracle."""
+    """--max-seq-len beyond 384 positions: 384 < T <= 768 runs the two-sweep tensor-core forward and the chunked backward
+    (tensor modes), anything longer — and the exact modes — the key-tiled exact attention; the step matches the oracle."""
     from musicstyletransfer_b200.engine import VAEConfig, VAEEngine
     cfg_o = om.Cfg(enc_size=64, enc_layers=2, enc_heads=2, latent=32, dec_type="lstm", dec_size=64)
     p = _condition_sigma(cfg_o, om.init_params(cfg_o, seed=2))
@@ -526,9 +526,15 @@ def test_rows_longer_than_384_positions(precision, T):
     pp = {k: v.clone() for k, v in p.items()}
     loss, ce, kl, probs, means, stds, grads = om.train_step(cfg_o, pp, om.Adam(pp, clip_gradient=1.0), tokens, seq_lens, classes,
                                                             labels, eps)
-    _close("ce", out["ce"], ce)
-    _close("kl", out["kl"], kl)
-    _close("means", out["means"], means)
+    if precision == "fp32" or T > 768:                  # exact attention: element-wise
+        _close("ce", out["ce"], ce)
+        _close("kl", out["kl"], kl)
+        _close("means", out["means"], means)
+    else:                                               # tensor-core attention with single-pass TF32 scores: the north star's 1e-3
+        rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
+        dev = {"ce": rel(out["ce"], ce), "kl": rel(out["kl"], kl), "means": rel(out["means"], means)}
+        print("long-row forward deviation:", dev)
+        assert dev["ce"] < 1e-3 and dev["kl"] < 1e-3 and dev["means"] < 1e-3, dev
     gscale = max(float(v.abs().max()) for v in grads.values())
     for name in eng.arena.names():
         if precision == "fp32":
