@@ -177,7 +177,7 @@ int msx_attention_bwd(const float* qkv, const float* mask, const float* dctx, fl
 /* Any row length (--max-seq-len is a free flag, VarAutoEncoder/config.py:36): key-tiled exact-fp32 kernels that keep nothing
  * larger than a 32 x 32 tile on chip; the context / the dQ part of dqkv are accumulated with atomics over the key tiles
  * (both outputs are zero-filled by the call).  msx_attention_fwd / _bwd route here when T x T does not fit one SM's shared
- * memory (T > ~180 at d_h = 32); the engine uses them for T > 384, beyond the tcgen05 kernels.  d_h <= 64, B * H <= 65535. */
+ * memory (T > ~180 at d_h = 32); the engine uses them for T > 768, beyond the tcgen05 kernels, and in the exact modes.  d_h <= 64, B * H <= 65535. */
 int msx_attention_tiled_fwd(const float* qkv, const float* mask, float* ctx, int B, int T, int H, int dh, void* stream);
 int msx_attention_tiled_bwd(const float* qkv, const float* mask, const float* dctx, float* dqkv, int B, int T, int H,
                             int dh, void* stream);

@@ -446,7 +446,7 @@ class VAEEngine:
         if self.attn_tc and ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctx, B, T, H, D // H, x3_scores=bool(self.x3_fwd),
                                  q0_only=sos_only and D // H == 32)
-        elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 384: key tiles of 128
+        elif self.attn_tc and ops.attention_tcl_supported(qkv, T, D // H):      # 128 < T <= 768: key tiles of 128
             ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
                                   q0_only=sos_only)
         else:
@@ -660,7 +660,7 @@ class VAEEngine:
         elif ops.attention_tcl_supported(qkv, T, D // H):
             ops.attention_tcl_fwd(qkv, mask, ctx16, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
                                   q0_only=sos_only)
-        else:                                           # T > 384: FFMA attention in fp32, then one cast
+        else:                                           # T > 768: FFMA attention in fp32, then one cast
             ctx = bf.get(tag + "ctx", (M, D), dev)
             ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.cast_bf16(ctx, ctx16)
