@@ -667,8 +667,10 @@ def run_sweep(args):
     dev = torch.device("cuda", 0)
     lib.load()
     cfg = VAEConfig(dec_type=args.dec_type, enc_dropout=args.dropout, dec_dropout=args.dropout)
-    for L in (64, 128, 256):
+    for L in (64, 128, 256, 512):
         for B in (32, 128, 512, 2048, 8192):
+            if L == 512 and B > 2048:                       # 4 M positions: the saved activations alone would be ~130 GB
+                continue
             eng = VAEEngine(cfg, dev, seed=0, precision=args.precision)
             tok, lens, cls, lab = synth.token_rows_4_4(B * 2, L, seed=7)
             bat = [tuple(torch.from_numpy(a[i * B:(i + 1) * B].copy()).to(dev) for a in (tok, lens, cls, lab)) for i in range(2)]
