@@ -247,6 +247,44 @@ def test_attention_long_rows_q0(B, T, H, out16):
     assert float((db.double().cpu() - wb).abs().max()) <= 5e-3 * float(wb.abs().max()) + 1e-4
 
 
+@pytest.mark.parametrize("T", [129, 257, 400, 513])
+@pytest.mark.parametrize("q0", [False, True])
+def test_attention_long_rows_batch_invariance(T, q0):
+    """Size-independent property at a bench-like grid (B * H = 4736 CTAs, 32 waves): a (batch, head) item is computed by one
+    CTA from its own rows only, so the context / statistics / dqkv of a large batch equal, bit for bit, those of the same rows
+    processed in four smaller calls (a race between concurrently resident CTAs or a stale shared-memory tile would show here)."""
+    from musicstyletransfer_b200 import ops
+    B, H, dh = 592, 8, 32
+    D = H * dh
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B * T, 3 * D, generator=g).cuda()
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().reshape(-1).cuda()
+    dctx = torch.randn(B * T, D, generator=g)
+    if q0:
+        keep = torch.zeros(B * T, 1)
+        keep[::T] = 1.0
+        dctx = dctx * keep
+    dctx = dctx.cuda()
+
+    def run(lo, hi):
+        n = hi - lo
+        q, m, d = qkv[lo * T:hi * T], mask[lo * T:hi * T], dctx[lo * T:hi * T]
+        ctx = torch.zeros(n * T, D, device="cuda")
+        stats = torch.zeros(n * H * T, 2, device="cuda")
+        out = torch.zeros(n * T, 3 * D, device="cuda")
+        ops.attention_tcl_fwd(q, m, ctx, stats, n, T, H, dh, q0_only=q0)
+        ops.attention_tcl_bwd(q, m, d, stats, out, n, T, H, dh, q0_only=q0)
+        return ctx, stats, out
+
+    full = run(0, B)
+    parts = [run(i * 148, (i + 1) * 148) for i in range(4)]
+    torch.cuda.synchronize()
+    for k, name in enumerate(("ctx", "stats", "dqkv")):
+        assert torch.equal(full[k], torch.cat([p[k] for p in parts])), name
+    assert bool(torch.isfinite(full[2]).all())
+
+
 # ------------------------------------------------------------------------------------------------ 16-wide heads
 @pytest.mark.parametrize("B,T,H", [(3, 66, 8), (5, 65, 3), (2, 16, 4), (4, 97, 2), (2, 128, 8), (300, 66, 8)])
 @pytest.mark.parametrize("out16", [False, True])
