@@ -220,8 +220,10 @@ __device__ __forceinline__ float block_max256(float v, float* red8, int tid) {
 // Q0 (the encoder's top layer under SOS-rows-only, model.py:97-100 reads position 0): scores and the query-axis softmax
 // cover every query as before (each key row's normaliser), then O[0] = sum_k P[k][0] V[k] is a column sum over the key
 // threads — no P staging, no MMA 2, one 128-byte row written per (batch, head); the other rows of ctx stay untouched.
+// Q0 needs neither the P staging nor the O accumulators: with at most 256 score columns (NKT <= 2) it allocates 256 TMEM
+// columns and (NT + 2) tiles of shared memory, so two CTAs share an SM (T = 257: 628 -> see attn_long_rate_r2.txt).
 template <int NT, int NKT, bool ALIAS, bool Q0>
-__global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
+__global__ void __launch_bounds__(kFwdThreads, (ALIAS || (Q0 && NKT <= 2)) ? 2 : 1)
     attn_tcl_fwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
                         const AttnLongParams p) {
@@ -233,14 +235,15 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
   unsigned char* sV = ALIAS ? base + 4 * kTileBytes : sK + kTileBytes;   // MN-major value tile (d contiguous, 128 key rows)
   // P chunk, q contiguous, 4 slabs of 128 key rows; two buffers, or ONE lying over sQ / sK (dead once MMA 1 has retired)
   unsigned char* sP = ALIAS ? base : sV + kTileBytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ALIAS ? sV + kTileBytes : sP + 2 * 4 * kTileBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>((ALIAS || Q0) ? sV + kTileBytes : sP + 2 * 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_q = &bars[0];
   unsigned long long* bar_k = &bars[1];
   unsigned long long* bar_v = &bars[2];
   unsigned long long* bar_s = &bars[3];
   unsigned long long* bar_o = &bars[4];              // [2]
-  constexpr int kTmemCols = ALIAS ? 256 : 512;
+  constexpr bool Q0SMALL = Q0 && !ALIAS && NKT <= 2;   // S (<= 256 columns) is all the TMEM the kernel needs
+  constexpr int kTmemCols = (ALIAS || Q0SMALL) ? 256 : 512;
   static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
   static_assert(!ALIAS || (NT == 2 && NKT == 1), "ALIAS: one full tile + trailing positions");
   constexpr bool TAIL = NKT < NT;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kFwdThreads, ALIAS ? 2 : 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_O = tmem, tm_S = tmem + 128;     // O: 32 columns per query chunk; S: up to 384 columns (ALIAS: 128)
+  const unsigned tm_O = tmem, tm_S = Q0SMALL ? tmem : tmem + 128;   // O: 32 columns per query chunk; S: up to 384 columns (ALIAS: 128)
   const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   // MMA 2: A = P^T MN-major (queries contiguous), B = V MN-major (d contiguous), M = 128 queries, N = 32
   const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
@@ -1454,6 +1457,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 
 constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBytes + 128; }
 constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
+constexpr size_t fwd_q0_smem(int nt) { return 1024 + (size_t)(nt + 2) * kTileBytes + 128; }   // no P staging
 constexpr size_t kFwd2Smem = 1024 + (size_t)(2 + 2 + 8) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
@@ -1495,9 +1499,10 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
 #define MSX_TCL_FWD(NT_, NKT_, ALIAS_, SMEM_)                                                                              \
   do {                                                                                                                   \
     if (q0_only) {                                                                                                       \
+      const size_t q0smem = (ALIAS_) ? (size_t)(SMEM_) : fwd_q0_smem(NT_);                                               \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, true>,                                        \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)));                         \
-      MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, true>, dim3(B * H), dim3(kFwdThreads), (SMEM_), st, tk, \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q0smem));                          \
+      MSX_CUDA(msx_launch(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, true>, dim3(B * H), dim3(kFwdThreads), q0smem, st, tk,  \
                           tm, p));                                                                                       \
     } else {                                                                                                             \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd_kernel<NT_, NKT_, ALIAS_, false>,                                       \
