@@ -573,8 +573,9 @@ __global__ void __launch_bounds__(kFwdThreads, (ALIAS || (Q0 && NKT <= 2)) ? 2 :
 //   sweep 1: running row maximum / sum over the chunks (online softmax) -> the statistics of the key rows
 //   sweep 2: P = exp2(s - max) / sum -> shared memory -> O[chunk] += P^T V      (Q0: one column sum for query 0 instead)
 // Thread layout, trailing positions and epilogue as in attn_tcl_fwd_kernel.
+// Q0: no P staging and no O accumulators — four tiles of shared memory and 128 score columns, two CTAs per SM.
 template <int NT, int NKT, bool Q0>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
     attn_tcl_fwd2_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                          const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
                          const AttnLongParams p) {
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   unsigned char* sK = sQ + 2 * kTileBytes;           // K-major key tile
   unsigned char* sV = sK + kTileBytes;               // MN-major value tile
   unsigned char* sP = sV + kTileBytes;               // 2 x 4 slabs: P chunk, q contiguous, 128 key rows per slab
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sP + 2 * 4 * kTileBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Q0 ? sP : sP + 2 * 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_q = &bars[0];              // [2]
   unsigned long long* bar_k = &bars[2];
@@ -596,6 +597,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   static_assert(NT * DH <= 256, "O accumulators: TMEM columns 0 .. 255, S in 256 .. 383");
   constexpr bool TAIL = NKT < NT;
   constexpr int NQQ = (NT * kTile + kFwdThreads - 1) / kFwdThreads;
+  constexpr int kTmemCols = Q0 ? 256 : 512;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_O = tmem, tm_S = tmem + 256;
+  const unsigned tm_O = tmem, tm_S = Q0 ? tmem : tmem + 256;
   const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
                           ((unsigned)(128 >> 4) << 24);
@@ -876,7 +878,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
     return;
   }
   {
@@ -910,7 +912,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -1459,6 +1461,7 @@ constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBy
 constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
 constexpr size_t fwd_q0_smem(int nt) { return 1024 + (size_t)(nt + 2) * kTileBytes + 128; }   // no P staging
 constexpr size_t kFwd2Smem = 1024 + (size_t)(2 + 2 + 8) * kTileBytes + 128;
+constexpr size_t kFwd2Q0Smem = 1024 + (size_t)(2 + 2) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t bwd_smem(bool single, bool tail) { return 1024 + (size_t)(3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128; }
@@ -1515,9 +1518,9 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
   do {                                                                                                                   \
     if (q0_only) {                                                                                                       \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    (int)kFwd2Smem));                                                                    \
-      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, true>, dim3(B * H), dim3(kFwdThreads), kFwd2Smem, st, tk, tm,  \
-                          p));                                                                                           \
+                                    (int)kFwd2Q0Smem));                                                                  \
+      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, true>, dim3(B * H), dim3(kFwdThreads), kFwd2Q0Smem, st, tk,    \
+                          tm, p));                                                                                       \
     } else {                                                                                                             \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kFwd2Smem));                                                                    \
@@ -1532,6 +1535,7 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
     else MSX_TCL_FWD(2, 2, false, fwd_smem(2));
   } else if (nt == 3) {
     if (tail) MSX_TCL_FWD(3, 2, false, fwd_smem(3));   // T = 257 ... 260
+    else if (q0_only) MSX_TCL_FWD2(3, 3);              // 384 score columns: the chunked kernel runs two CTAs per SM
     else MSX_TCL_FWD(3, 3, false, fwd_smem(3));
   } else if (nt == 4) {                                // 384 < T <= 768: two sweeps over the query chunks
     if (tail) MSX_TCL_FWD2(4, 3);

@@ -235,7 +235,9 @@ def test_attention_long_rows_q0(B, T, H, out16):
     stats_full = torch.zeros_like(stats)
     ops.attention_tcl_fwd(qd, md, torch.empty_like(ctx), stats_full, B, T, H, dh)
     torch.cuda.synchronize()
-    assert torch.equal(stats, stats_full)
+    # the same row maxima bit for bit; the sums may be taken in another order (T = 261 ... 384: q0_only runs the chunked kernel)
+    assert torch.equal(stats[:, 0], stats_full[:, 0])
+    assert torch.allclose(stats[:, 1], stats_full[:, 1], rtol=2e-6, atol=0.0)
     out = torch.full((B * T, 3 * D), 5.0, device="cuda", dtype=odt)
     db = torch.zeros(3 * D, device="cuda")
     ops.attention_tcl_bwd(qd, md, dd, stats, out, B, T, H, dh, dbias=db, q0_only=True)
