@@ -929,8 +929,11 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
 // Q0 (the encoder's top layer under SOS-rows-only): dctx is non-zero in the row of query 0 only.  With g = dO[0],
 // a_k = V_k . g, c_k = a_k P[k][0]:  dV_k = P[k][0] g  and  dS[k][q] = P[k][q] ([q = 0] a_k - c_k) / sqrt(d_h)  are thread-local,
 // so phase 1 (P pass, dV MMA), the dP MMA, the dO tiles and the second TMEM read of the dS pass all disappear.
+// SINGLE && Q0 (the top layer's backward at T = 129 ... 132): 224 TMEM columns are enough (dK | dQ | S, dS written in place of
+// S) and the dS^T staging lies over the K-major K / Q / V tiles, dead once S = K Q^T has retired and the threads have read
+// their K / V rows: six tiles of shared memory, 256 TMEM columns, two CTAs per SM.
 template <int NT, int NKT, bool SINGLE, bool Q0>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
     attn_tcl_bwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmDOk /* K-major {32,128} over dctx */,
@@ -941,11 +944,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
   static_assert(!SINGLE || (NT == 2 && NKT == 1), "SINGLE: one full tile + trailing positions");
   constexpr int NQQ = (NT * kTile + kBwdThreads - 1) / kBwdThreads;    // queries per thread in the trailing-key section
+  constexpr int kTmemCols = (SINGLE && Q0) ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr bool SQ = SINGLE && Q0;                  // tiles: [Kk | Qk | Vk | -] = dS^T staging later, then Km, Qm
   unsigned char* sKk = base;                         // per key tile: K K-major, V K-major, K MN-major
-  unsigned char* sVk = sKk + kTileBytes;
-  unsigned char* sKm = sVk + kTileBytes;
+  unsigned char* sVk = SQ ? base + 2 * kTileBytes : sKk + kTileBytes;
+  unsigned char* sKm = SQ ? base + 4 * kTileBytes : sVk + kTileBytes;
   // Per query chunk, slots of three tiles: {Q K-major, dO MN-major, -} in phase 1 and {Q K-major, Q MN-major, dO K-major}
   // in phase 2.  DB (rows without trailing positions): two slots, slot = step & 1, and the loads of step s + 1 are issued
   // when step s starts (its slot was last read by step s - 1, whose MMAs have retired), so their latency hides behind a
@@ -954,9 +959,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   // variants keep one slot and load at the start of the step.  SINGLE: four tiles, loaded once.
   constexpr bool DB = !TAIL;
   constexpr int kChunkTiles = SINGLE ? 4 : (DB ? 6 : 3);
-  unsigned char* sC = sKm + kTileBytes;
-  unsigned char* sY = sC + kChunkTiles * kTileBytes;   // dS^T chunk, q contiguous: 4 slabs x 128 key rows
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sY + 4 * kTileBytes);
+  unsigned char* sC = SQ ? base + kTileBytes : sKm + kTileBytes;       // SQ: only the Q K-major tile of "slot 0"
+  unsigned char* sY = SQ ? base : sC + kChunkTiles * kTileBytes;      // dS^T chunk, q contiguous: 4 slabs x 128 key rows
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(SQ ? base + 6 * kTileBytes : sY + 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_kt = &bars[0];
   unsigned long long* bar_ld = &bars[4];             // [2]: chunk tiles of a slot have landed
@@ -965,7 +970,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __shared__ float red[256];
   __shared__ float red8[8];
   __shared__ float red_b[3][8][16];
-  __shared__ float tp_s[2][kTailMax][kTile];         // P / dP of (key row, trailing query), exchanged between the row's two threads
+  __shared__ float tp_s[Q0 ? 1 : 2][Q0 ? 1 : kTailMax][Q0 ? 1 : kTile];   // P / dP of (key row, trailing query), exchanged between the row's two threads
   __shared__ float dq_s[kTailMax][32];               // dQ rows of the trailing queries
   __shared__ __align__(16) float g_s[32];            // Q0: dO[query 0]
   __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
@@ -991,7 +996,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -999,7 +1004,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_dV = tmem, tm_dK = tmem + 32, tm_dQ = tmem + 64, tm_S = tmem + 256, tm_dP = tmem + 384;
+  const unsigned tm_dV = tmem, tm_dK = SQ ? tmem : tmem + 32, tm_dQ = SQ ? tmem + 32 : tmem + 64;
+  const unsigned tm_S = SQ ? tmem + 128 : tmem + 256, tm_dP = SQ ? tmem + 128 : tmem + 384;    // SQ: dS in place of S
   const unsigned tm_P = SINGLE ? tmem + 128 : tm_S;         // SINGLE: dQ takes 32 columns, 128 .. 255 are free
   const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   const unsigned idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
@@ -1028,7 +1034,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     }
   };
   unsigned char* const sDOk1 = sC + 2 * kTileBytes;         // SINGLE: dO K-major (read by the dP MMA issued with phase 1)
-  unsigned char* const sQm1 = sC + 3 * kTileBytes;          // SINGLE: Q MN-major
+  unsigned char* const sQm1 = SQ ? base + 5 * kTileBytes : sC + 3 * kTileBytes;   // SINGLE: Q MN-major
   unsigned step = 0;                                        // bar_ld / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
 #pragma unroll 1
   for (int kt = 0; kt < NKT; ++kt) {
@@ -1186,7 +1192,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
               load_row32(tr_s[kTrDO][i], r);
               val = dot32(kv, r);
             }
-            tp_s[half][i][row] = val;          // read after the barrier that follows the P pass
+            if (!Q0) tp_s[half][i][row] = val;   // read after the barrier that follows the P pass
           }
         }
       }
@@ -1249,8 +1255,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       for (int i = 0; i < kTailMax; ++i) {
         pt[i] = dpt[i] = 0.f;
         if (i < ntail) {                       // dV_k += P[k][q*] dO[q*]
-          pt[i] = tp_s[0][i][row];
-          dpt[i] = tp_s[1][i][row];
+          pt[i] = tp_s[0][Q0 ? 0 : i][Q0 ? 0 : row];
+          dpt[i] = tp_s[Q0 ? 0 : 1][Q0 ? 0 : i][Q0 ? 0 : row];
           const float4* gp = reinterpret_cast<const float4*>(tr_s[kTrDO][i]);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -1333,6 +1339,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         }
 #pragma unroll
         for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((0.f - delta) * p.inv_scale);   // dS[k][q*]: dP = 0 there
+        if (SQ) {
+          // dS goes over S and the dS^T staging over the K / Q / V tiles: both threads of every row have read S[k][0],
+          // every thread its K / V rows
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+        }
       }
       {
         const int cend = min(nq, c0 + 64);
@@ -1379,7 +1392,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         // while the last MMAs of the key tile run: dQ[q*] += sum over this tile's keys of dS[k][q*] K[k]; the first
         // threads of the rows take the even trailing queries, the second threads the odd ones
         float kr[32];
-        load_row_km(sKk, row, kr);
+        if (SQ) load_row_mn(sKm, row, kr);     // the K-major tile lies under the dS^T staging
+        else load_row_km(sKk, row, kr);
 #pragma unroll
         for (int ii = 0; ii < kTailMax / 2; ++ii) {
           if (2 * ii < ntail) {                // CTA-uniform
@@ -1454,7 +1468,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
 constexpr size_t fwd_smem(int nt) { return 1024 + (size_t)(nt + 2 + 8) * kTileBytes + 128; }
@@ -1464,7 +1478,9 @@ constexpr size_t kFwd2Smem = 1024 + (size_t)(2 + 2 + 8) * kTileBytes + 128;
 constexpr size_t kFwd2Q0Smem = 1024 + (size_t)(2 + 2) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
-constexpr size_t bwd_smem(bool single, bool tail) { return 1024 + (size_t)(3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128; }
+constexpr size_t bwd_smem(bool single, bool tail, bool q0 = false) {
+  return 1024 + (size_t)((single && q0) ? 6 : 3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128;
+}
 
 }  // namespace
 
@@ -1580,7 +1596,7 @@ extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, con
   cudaStream_t st = (cudaStream_t)stream;
 #define MSX_TCL_BWD(NT_, NKT_, SINGLE_)                                                                                     \
   do {                                                                                                                   \
-    const size_t kBwdSmem = bwd_smem(SINGLE_, NKT_ < NT_);                                                               \
+    const size_t kBwdSmem = bwd_smem(SINGLE_, NKT_ < NT_, q0_only != 0);                                                 \
     if (q0_only) {                                                                                                       \
       MSX_CUDA(cudaFuncSetAttribute(attn_tcl_bwd_kernel<NT_, NKT_, SINGLE_, true>,                                       \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));                        \
