@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
 // S) and the dS^T staging lies over the K-major K / Q / V tiles, dead once S = K Q^T has retired and the threads have read
 // their K / V rows: six tiles of shared memory, 256 TMEM columns, two CTAs per SM.
 template <int NT, int NKT, bool SINGLE, bool Q0>
-__global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
+__global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
     attn_tcl_bwd_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmMn /* MN-major {32,128} over qkv */,
                         const __grid_constant__ CUtensorMap tmDOk /* K-major {32,128} over dctx */,
@@ -944,13 +944,17 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
   static_assert(NKT == NT || NKT == NT - 1, "at most one chunk of trailing positions");
   static_assert(!SINGLE || (NT == 2 && NKT == 1), "SINGLE: one full tile + trailing positions");
   constexpr int NQQ = (NT * kTile + kBwdThreads - 1) / kBwdThreads;    // queries per thread in the trailing-key section
-  constexpr int kTmemCols = (SINGLE && Q0) ? 256 : 512;
+  constexpr int kTmemCols = SINGLE ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr bool SQ = SINGLE && Q0;                  // tiles: [Kk | Qk | Vk | -] = dS^T staging later, then Km, Qm
-  unsigned char* sKk = base;                         // per key tile: K K-major, V K-major, K MN-major
-  unsigned char* sVk = SQ ? base + 2 * kTileBytes : sKk + kTileBytes;
-  unsigned char* sKm = SQ ? base + 4 * kTileBytes : sVk + kTileBytes;
+  // S2 = SINGLE && !Q0, also two CTAs per SM — tiles: [Qk | dOm | Vk | dOk] = dS^T staging later, then Kk (reloaded as Km once
+  // S = K Q^T has retired), Qm; TMEM: columns 128 .. 255 hold S, then P in place, then dK | dQ; columns 0 .. 127 hold dV and,
+  // once every thread has read dV, dP (its MMA is issued then: one MMA round trip more than the 512-column layout) and dS.
+  constexpr bool S2 = SINGLE && !Q0;
+  unsigned char* sKk = S2 ? base + 4 * kTileBytes : base;              // per key tile: K K-major, V K-major, K MN-major
+  unsigned char* sVk = SINGLE ? base + 2 * kTileBytes : sKk + kTileBytes;
+  unsigned char* sKm = SINGLE ? base + 4 * kTileBytes : sVk + kTileBytes;
   // Per query chunk, slots of three tiles: {Q K-major, dO MN-major, -} in phase 1 and {Q K-major, Q MN-major, dO K-major}
   // in phase 2.  DB (rows without trailing positions): two slots, slot = step & 1, and the loads of step s + 1 are issued
   // when step s starts (its slot was last read by step s - 1, whose MMAs have retired), so their latency hides behind a
@@ -959,9 +963,9 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
   // variants keep one slot and load at the start of the step.  SINGLE: four tiles, loaded once.
   constexpr bool DB = !TAIL;
   constexpr int kChunkTiles = SINGLE ? 4 : (DB ? 6 : 3);
-  unsigned char* sC = SQ ? base + kTileBytes : sKm + kTileBytes;       // SQ: only the Q K-major tile of "slot 0"
-  unsigned char* sY = SQ ? base : sC + kChunkTiles * kTileBytes;      // dS^T chunk, q contiguous: 4 slabs x 128 key rows
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(SQ ? base + 6 * kTileBytes : sY + 4 * kTileBytes);
+  unsigned char* sC = SQ ? base + kTileBytes : (S2 ? base : sKm + kTileBytes);   // SINGLE: Q K-major (S2: and dO MN-major) of "slot 0"
+  unsigned char* sY = SINGLE ? base : sC + kChunkTiles * kTileBytes;  // dS^T chunk, q contiguous: 4 slabs x 128 key rows
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(SINGLE ? base + 6 * kTileBytes : sY + 4 * kTileBytes);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_kt = &bars[0];
   unsigned long long* bar_ld = &bars[4];             // [2]: chunk tiles of a slot have landed
@@ -974,7 +978,7 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
   __shared__ float dq_s[kTailMax][32];               // dQ rows of the trailing queries
   __shared__ __align__(16) float g_s[32];            // Q0: dO[query 0]
   __shared__ __align__(16) float tr_s[TAIL ? 5 : 1][kTailMax][32];     // rows of the trailing positions (fetch_tail_rows)
-  __shared__ float ds_s[TAIL ? kTailMax : 1][TAIL ? NT * kTile : 1];   // dS[trailing key][query]
+  __shared__ float ds_s[TAIL ? kTailMax : 1][TAIL ? (SINGLE ? kTile + 8 : NT * kTile) : 1];   // dS[trailing key][query]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -1004,9 +1008,10 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_dV = tmem, tm_dK = SQ ? tmem : tmem + 32, tm_dQ = SQ ? tmem + 32 : tmem + 64;
-  const unsigned tm_S = SQ ? tmem + 128 : tmem + 256, tm_dP = SQ ? tmem + 128 : tmem + 384;    // SQ: dS in place of S
-  const unsigned tm_P = SINGLE ? tmem + 128 : tm_S;         // SINGLE: dQ takes 32 columns, 128 .. 255 are free
+  const unsigned tm_dV = tmem, tm_dK = SQ ? tmem : (S2 ? tmem + 128 : tmem + 32), tm_dQ = SQ ? tmem + 32 : (S2 ? tmem + 160 : tmem + 64);
+  const unsigned tm_S = SINGLE ? tmem + 128 : tmem + 256;              // SQ: dS in place of S
+  const unsigned tm_dP = SQ ? tmem + 128 : (S2 ? tmem : tmem + 384);   // S2: over dV, issued once dV has been read
+  const unsigned tm_P = tm_S;                               // P in place of S
   const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   const unsigned idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
                             ((unsigned)(128 >> 4) << 24);   // A from TMEM, B MN-major, N = 32
@@ -1033,8 +1038,8 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
       if (!Q0) tma_load_2d(t0 + 2 * kTileBytes, &tmDOk, &bar_ld[slot], h * DH, r0);
     }
   };
-  unsigned char* const sDOk1 = sC + 2 * kTileBytes;         // SINGLE: dO K-major (read by the dP MMA issued with phase 1)
-  unsigned char* const sQm1 = SQ ? base + 5 * kTileBytes : sC + 3 * kTileBytes;   // SINGLE: Q MN-major
+  unsigned char* const sDOk1 = base + 3 * kTileBytes;       // S2: dO K-major (read by the dP MMA)
+  unsigned char* const sQm1 = base + 5 * kTileBytes;        // SINGLE: Q MN-major
   unsigned step = 0;                                        // bar_ld / bar_m1 / bar_m2 complete once per (key tile, phase, chunk)
 #pragma unroll 1
   for (int kt = 0; kt < NKT; ++kt) {
@@ -1048,7 +1053,7 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
       inv = st.y;
     }
     if (tid == 0) {                                         // every MMA that read the previous key tile has retired (bar_m2 waits)
-      mbar_expect_tx(bar_kt, (unsigned)((SINGLE ? (Q0 ? 5 : 7) : 3) * kTileBytes));
+      mbar_expect_tx(bar_kt, (unsigned)((SINGLE ? (Q0 ? 5 : 6) : 3) * kTileBytes));
       tma_load_2d(sKk, &tmKm, bar_kt, h * DH, b * T + kt * kTile);
       tma_load_2d(sVk, &tmKm, bar_kt, 2 * D + h * DH, b * T + kt * kTile);
       if (SINGLE) {
@@ -1059,7 +1064,7 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
         }
         tma_load_2d(sQm1, &tmMn, bar_kt, D + h * DH, b * T);
       }
-      tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);
+      if (!S2) tma_load_2d(sKm, &tmMn, bar_kt, h * DH, b * T + kt * kTile);   // S2: lands in the K-major tile's place later
       if (DB && !SINGLE) issue_chunk(Q0 ? NKT : 0, step);
     }
     if (TAIL && kt == 0) {
@@ -1162,13 +1167,9 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
         if (!SINGLE) mbar_wait(&bar_ld[slot], DB ? ((step >> 1) & 1) : (step & 1));
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < DH / 8; ++k) {     // S = K Q^T (SINGLE: and dP = V dO^T, two independent chains)
+        for (int k = 0; k < DH / 8; ++k)       // S = K Q^T
           umma_tf32(tm_S, make_desc(smem_u32(sKk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sQk) + k * 32, 16, 1024, 2),
                     idesc_s, k > 0 ? 1u : 0u);
-          if (SINGLE)
-            umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk1) + k * 32, 16, 1024, 2),
-                      idesc_s, k > 0 ? 1u : 0u);
-        }
         umma_commit(bar_m1);
       }
       __syncwarp();
@@ -1219,6 +1220,10 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
           umma_tf32_ts(tm_dV, tm_P + j * 8, make_desc(smem_u32(sDOm) + j * 1024, kTileBytes, 512, 1), idesc_ts,
                        (qc > 0 || j > 0) ? 1u : 0u);
         umma_commit(bar_m2);
+        if (S2) {                              // S = K Q^T has retired and every thread has read its K row: K MN-major over K K-major
+          mbar_expect_tx(&bar_ld[0], (unsigned)kTileBytes);
+          tma_load_2d(sKm, &tmMn, &bar_ld[0], h * DH, b * T);
+        }
       }
       __syncwarp();
       mbar_wait(bar_m2, par);                  // S and the chunk tiles are free again
@@ -1290,6 +1295,23 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
     if (!Q0) {
 #pragma unroll
       for (int i = 0; i < kTailMax; ++i) pt[i] = pt[i] * ((dpt[i] - delta) * p.inv_scale);   // dS[k][q*]
+    }
+    if (S2) {
+      // every thread has read dV (and its V row): dP = V dO^T goes over the dV columns
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const unsigned idesc_p = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTile >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+#pragma unroll
+        for (int k = 0; k < DH / 8; ++k)
+          umma_tf32(tm_dP, make_desc(smem_u32(sVk) + k * 32, 16, 1024, 2), make_desc(smem_u32(sDOk1) + k * 32, 16, 1024, 2),
+                    idesc_p, k > 0 ? 1u : 0u);
+        umma_commit(bar_m1);
+      }
+      __syncwarp();
+      mbar_wait(bar_m1, 1u);                   // second completion of bar_m1 (the first was S = K Q^T)
+      tc_fence_after();
     }
     // ---------------- phase 2: dK += dS Q, dQ[chunk] += dS^T K
 #pragma unroll 1
@@ -1364,7 +1386,9 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float pr = (TAIL || qc * kTile + c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f;
+            // S2: the S columns hold P (rounded to TF32 for the dV MMA) — taken as it is
+            const float pr = S2 ? v[j]
+                                : ((TAIL || qc * kTile + c + j < T) ? exp2f(fmaf(fmaf(v[j], p.inv_scale, rowmask), kLog2e, -mxl)) * inv : 0.f);
             g[j] = to_tf32(pr * ((g[j] - delta) * p.inv_scale));      // dS
           }
           tmem_st16(tm_dP + lane_off + c, g);
@@ -1378,6 +1402,7 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
+        if (S2) mbar_wait(&bar_ld[0], 0u);
         tc_fence_after();
         for (int j = 0; j < nq / 8; ++j)       // dK[keys x 32] += dS[keys x q] Q[q x 32]: A from TMEM, B = Q MN-major
           umma_tf32_ts(tm_dK, tm_dP + j * 8, make_desc(smem_u32(sQm) + j * 1024, kTileBytes, 512, 1), idesc_ts,
@@ -1392,7 +1417,8 @@ __global__ void __launch_bounds__(kBwdThreads, (SINGLE && Q0) ? 2 : 1)
         // while the last MMAs of the key tile run: dQ[q*] += sum over this tile's keys of dS[k][q*] K[k]; the first
         // threads of the rows take the even trailing queries, the second threads the odd ones
         float kr[32];
-        if (SQ) load_row_mn(sKm, row, kr);     // the K-major tile lies under the dS^T staging
+        if (S2) mbar_wait(&bar_ld[0], 0u);
+        if (SINGLE) load_row_mn(sKm, row, kr);  // the K-major tile lies under the dS^T staging / was replaced by this copy
         else load_row_km(sKk, row, kr);
 #pragma unroll
         for (int ii = 0; ii < kTailMax / 2; ++ii) {
@@ -1479,7 +1505,7 @@ constexpr size_t kFwd2Q0Smem = 1024 + (size_t)(2 + 2) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t bwd_smem(bool single, bool tail, bool q0 = false) {
-  return 1024 + (size_t)((single && q0) ? 6 : 3 + (single ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128;
+  return 1024 + (size_t)(single ? 6 : 3 + (tail ? 3 : 6) + 4) * kTileBytes + 128;
 }
 
 }  // namespace
