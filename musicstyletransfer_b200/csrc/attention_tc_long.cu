@@ -665,10 +665,11 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
         sc[qq] = 0.f;
         if (q < T) {
           float qr[32];
-          const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+          const float4* qp = (q >= NKT * kTile) ? reinterpret_cast<const float4*>(tr_s[kTrQ][q - NKT * kTile])
+                                                : reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 q4 = __ldg(qp + c);
+            const float4 q4 = qp[c];
             qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
           }
           sc[qq] = fmaf(dot32_tf32(tr_s[kTrK][i], qr), p.inv_scale, rmask);
@@ -1089,13 +1090,17 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
           pv[qq] = dpv[qq] = 0.f;
           if (q < T) {
             float qr[32], dor[32];
-            const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
-            const float4* dp4 = reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
+            // rows of the trailing queries come from the fetch at kernel start (shared memory), the others from global memory
+            const bool tq = q >= NKT * kTile;
+            const float4* qp = tq ? reinterpret_cast<const float4*>(tr_s[kTrQ][q - NKT * kTile])
+                                  : reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+            const float4* dp4 = (tq && !Q0) ? reinterpret_cast<const float4*>(tr_s[kTrDO][q - NKT * kTile])
+                                            : reinterpret_cast<const float4*>(p.dctx + ((size_t)b * T + q) * D + h * DH);
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 q4 = __ldg(qp + c), v4 = vrow[c];
-              const float4 g4 = Q0 ? (q == 0 ? reinterpret_cast<const float4*>(g_s)[c] : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(dp4 + c);
+              const float4 q4 = qp[c], v4 = vrow[c];
+              const float4 g4 = Q0 ? (q == 0 ? reinterpret_cast<const float4*>(g_s)[c] : make_float4(0.f, 0.f, 0.f, 0.f)) : dp4[c];
               qr[4 * c] = to_tf32(q4.x); qr[4 * c + 1] = to_tf32(q4.y); qr[4 * c + 2] = to_tf32(q4.z); qr[4 * c + 3] = to_tf32(q4.w);
               dor[4 * c] = g4.x; dor[4 * c + 1] = g4.y; dor[4 * c + 2] = g4.z; dor[4 * c + 3] = g4.w;
               d4[0] = fmaf(v4.x, g4.x, d4[0]); d4[1] = fmaf(v4.y, g4.y, d4[1]);
@@ -1121,10 +1126,11 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
           const float ds = pv[qq] * ((dpv[qq] - delta) * p.inv_scale);
           if (q < T) {
             ds_s[i][q] = ds;
-            const float4* qp = reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
+            const float4* qp = (q >= NKT * kTile) ? reinterpret_cast<const float4*>(tr_s[kTrQ][q - NKT * kTile])
+                                                  : reinterpret_cast<const float4*>(p.qkv + ((size_t)b * T + q) * 3 * D + D + h * DH);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 q4 = __ldg(qp + c);
+              const float4 q4 = qp[c];
               col[4 * c] = fmaf(ds, q4.x, col[4 * c]); col[4 * c + 1] = fmaf(ds, q4.y, col[4 * c + 1]);
               col[4 * c + 2] = fmaf(ds, q4.z, col[4 * c + 2]); col[4 * c + 3] = fmaf(ds, q4.w, col[4 * c + 3]);
             }
