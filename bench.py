@@ -552,9 +552,11 @@ def run_ours(args):
         dist.all_gather(allchk, chk)
         ranks_identical = bool(all(torch.equal(c, allchk[0]) for c in allchk))
 
-    def time_variant(precision, B_v, gbatch_v, steps_v, warm_v, seed_off=0):
+    def time_variant(precision, B_v, gbatch_v, steps_v, warm_v, seed_off=0, L_v=None):
         """Same model / data generator / timing protocol on a fresh engine: `precision`, B_v rows per GPU per step,
-        gradients averaged over gbatch_v rows.  Data parallel runs take the same exchange as the headline."""
+        gradients averaged over gbatch_v rows, rows of L_v tokens (default: the headline's).  Data parallel runs take the
+        same exchange as the headline."""
+        L_v = L if L_v is None else L_v
         eng_v = VAEEngine(cfg, dev, seed=0, precision=precision)
         ar_v = None
         exch = "none"
@@ -566,7 +568,7 @@ def run_ours(args):
                     ar_v, exch = "peer", "fused NVLink optimiser step (msx_adam_nvlink_step)"
                 except Exception as exc:
                     print("bench: peer optimiser unavailable for the %s variant (%s)" % (precision, exc), file=sys.stderr)
-        tok_v, lens_v, cls_v, lab_v = synth.token_rows_4_4(B_v * n_batches, L, seed=200 + seed_off + rank)
+        tok_v, lens_v, cls_v, lab_v = synth.token_rows_4_4(B_v * n_batches, L_v, seed=200 + seed_off + rank)
         res_v = [tuple(torch.from_numpy(a[i * B_v:(i + 1) * B_v].copy()).to(dev) for a in (tok_v, lens_v, cls_v, lab_v))
                  for i in range(n_batches)]
         train_v = eng_v.train_step if args.no_graph else eng_v.train_step_graphed
@@ -587,7 +589,7 @@ def run_ours(args):
 
     # ---- bf16 variant (BASELINE config 4), stated separately: same model, batch, data and timing protocol with
     # precision="bf16"; its tolerances are the bf16 ones of tests/test_engine_gpu.py, not the fp32 bar of the headline.
-    bf16_variant = fp32_variant = b32 = x3_variant = None
+    bf16_variant = fp32_variant = b32 = x3_variant = seq_sweep = None
     strong = []
     tf32_variant = None
     if args.precision == HEADLINE and not args.no_variants:
@@ -615,6 +617,14 @@ def run_ours(args):
         if world == 1:
             b32 = time_variant(args.precision, 32, 32, 200, 10, seed_off=11)
             b32["what"] = "scripts/train-vae.sh batch size (32 rows, L=64), CUDA-graph replay"
+        # ---- BASELINE config 3's sequence-length axis at the headline batch: the long-row tcgen05 attention
+        # (csrc/attention_tc_long.cu) takes T = L + 1 = 129 / 257; tokens/s next to the headline's
+        if world == 1 and L == 64:
+            seq_sweep = []
+            for L_s in (128, 256):
+                sv = time_variant(args.precision, B, gbatch, 10, 3, seed_off=13, L_v=L_s)
+                sv.update({"seq_len": L_s, "tokens_per_s": sv["value"] * L_s})
+                seq_sweep.append(sv)
     e2e_from_midi = None
     if world == 1 and not args.no_variants and args.dec_type == "lstm":
         e2e_from_midi = bench_from_midi(args, cfg, dev)
@@ -645,7 +655,8 @@ def run_ours(args):
                 "l2": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; 4 input batches rotate" %
                       (B * T * 4 * 40e3 / 1e9 / 10)},
         "roofline": roofline, "roofline_other": roofline_other, "rasteriser": raster, "cpu_baseline": cpu, "tf32x3f_variant": x3_variant, "tf32_variant": tf32_variant, "bf16_variant": bf16_variant,
-        "fp32_variant": fp32_variant, "strong_scaling": strong or None, "b32": b32, "e2e_from_midi": e2e_from_midi,
+        "fp32_variant": fp32_variant, "strong_scaling": strong or None, "b32": b32, "seq_len_sweep": seq_sweep,
+        "e2e_from_midi": e2e_from_midi,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches, "clocks": clocks,
