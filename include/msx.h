@@ -230,6 +230,10 @@ int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int
                              int T, int H, int dh, void* stream);
 int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
                              int dqkv_bf16, float* dbias, int q0_only, int B, int T, int H, int dh, void* stream);
+/* p3 planes (as msx_attention_tc_fwd_p): ctx (bfloat16) receives the hi plane rn_bf16(o), ctx_lo (optional) rn_bf16(o - hi) —
+ * the operands of the p3 W_proj GEMM; the context then never exists in fp32 and no msx_split_planes pass follows. */
+int msx_attention_tcl_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, float* stats,
+                            int q0_only, int B, int T, int H, int dh, void* stream);
 
 /* K2d — out = LayerNorm(x + dropout(y)).  Replaces transformer.py:155,158,200 (gluon Dropout + add +
  * gluon.nn.LayerNorm, eps 1e-5).  Backward: dres = ds, dy = ds*keep (dy may be NULL when drop_p == 0);

@@ -56,6 +56,7 @@ struct AttnLongParams {
   const float* mask;   // [B*T]
   float* stats;        // [B*H*T, 2]: (row max * log2 e, 1 / row sum) of every key row; written by fwd, read by bwd
   void* out;           // fwd: ctx [B*T, H*32]; bwd: dqkv [B*T, 3*H*32]; fp32, or bf16 when out_bf16
+  void* out_lo;        // fwd, optional (out_bf16): the context as bf16 hi (out) / lo planes, the operands of the p3 W_proj GEMM
   int out_bf16;
   float* dbias;        // bwd, optional [3*H*32]: += column sums of dqkv
   int T, H, TQ;        // TQ = score columns on the tensor path: roundup16(T), or T - tail when trailing positions leave it
@@ -207,6 +208,21 @@ __device__ __forceinline__ float block_max256(float v, float* red8, int tid) {
   v = fmaxf(fmaxf(fmaxf(red8[0], red8[1]), fmaxf(red8[2], red8[3])), fmaxf(fmaxf(red8[4], red8[5]), fmaxf(red8[6], red8[7])));
   __syncthreads();
   return v;
+}
+
+// 16 columns of a context row: fp32, bf16, or bf16 hi / lo planes (hi = rn_bf16(o), lo = rn_bf16(o - hi))
+__device__ __forceinline__ void store_ctx16(const AttnLongParams& p, size_t elem, const float* o) {
+  if (p.out_lo) store_row32_planes(p.out, p.out_lo, elem, o, 16);
+  else store_row32(p.out, p.out_bf16 != 0, elem, o, 16);
+}
+__device__ __forceinline__ void store_ctx1(const AttnLongParams& p, size_t elem, float o) {
+  if (p.out_bf16) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+    reinterpret_cast<unsigned short*>(p.out)[elem] = __bfloat16_as_ushort(hi);
+    if (p.out_lo) reinterpret_cast<unsigned short*>(p.out_lo)[elem] = __bfloat16_as_ushort(__float2bfloat16_rn(o - __bfloat162float(hi)));
+  } else {
+    reinterpret_cast<float*>(p.out)[elem] = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -523,8 +539,7 @@ __global__ void __launch_bounds__(kFwdThreads, (ALIAS || (Q0 && NKT <= 2)) ? 2 :
           if (i < ntail) o0 = fmaf(pt_s[i][0], tr_s[kTrV][i][lane], o0);
       }
       const size_t e = (size_t)b * T * D + h * DH + lane;
-      if (p.out_bf16) reinterpret_cast<unsigned short*>(p.out)[e] = __bfloat16_as_ushort(__float2bfloat16_rn(o0));
-      else reinterpret_cast<float*>(p.out)[e] = o0;
+      store_ctx1(p, e, o0);
     }
     tc_fence_before();
     __syncthreads();
@@ -558,7 +573,7 @@ __global__ void __launch_bounds__(kFwdThreads, (ALIAS || (Q0 && NKT <= 2)) ? 2 :
       for (int i = 0; i < kTailMax; ++i)               // O[q] += P[k*][q] V[k*]
         if (i < ntail) axpy16(pt_s[i][q], tr_s[kTrV][i] + h16, o);
     }
-    if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH + h16, o, 16);
+    if (q < T) store_ctx16(p, ((size_t)b * T + q) * D + h * DH + h16, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -874,8 +889,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
           if (i < ntail) o0 = fmaf(pt_s[i][0], tr_s[kTrV][i][lane], o0);
       }
       const size_t e = (size_t)b * T * D + h * DH + lane;
-      if (p.out_bf16) reinterpret_cast<unsigned short*>(p.out)[e] = __bfloat16_as_ushort(__float2bfloat16_rn(o0));
-      else reinterpret_cast<float*>(p.out)[e] = o0;
+      store_ctx1(p, e, o0);
     }
     tc_fence_before();
     __syncthreads();
@@ -909,7 +923,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
       for (int i = 0; i < kTailMax; ++i)
         if (i < ntail) axpy16(pt_s[i][q], tr_s[kTrV][i] + h16, o);
     }
-    if (q < T) store_row32(p.out, p.out_bf16 != 0, ((size_t)b * T + q) * D + h * DH + h16, o, 16);
+    if (q < T) store_ctx16(p, ((size_t)b * T + q) * D + h * DH + h16, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -1524,6 +1538,8 @@ extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, voi
                                         int B, int T, int H, int dh, void* stream);
 extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, const float* dctx, const float* stats, void* dqkv,
                                         int dqkv_bf16, float* dbias, int q0_only, int B, int T, int H, int dh, void* stream);
+extern "C" int msx_attention_tcl_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, float* stats,
+                                       int q0_only, int B, int T, int H, int dh, void* stream);
 
 extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int B, int T,
                                      int H, int dh, void* stream) {
@@ -1532,14 +1548,20 @@ extern "C" int msx_attention_tcl_fwd(const float* qkv, const float* mask, void* 
 
 extern "C" int msx_attention_tcl_fwd_q0(const float* qkv, const float* mask, void* ctx, int ctx_bf16, float* stats, int q0_only,
                                         int B, int T, int H, int dh, void* stream) {
+  return msx_attention_tcl_fwd_p(qkv, mask, ctx, nullptr, ctx_bf16, stats, q0_only, B, T, H, dh, stream);
+}
+
+extern "C" int msx_attention_tcl_fwd_p(const float* qkv, const float* mask, void* ctx, void* ctx_lo, int ctx_bf16, float* stats,
+                                       int q0_only, int B, int T, int H, int dh, void* stream) {
   MSX_REQUIRE(qkv && mask && ctx && stats, "msx_attention_tcl_fwd: null pointer");
+  MSX_REQUIRE(!ctx_lo || (ctx_bf16 && ((uintptr_t)ctx_lo & 15) == 0), "msx_attention_tcl_fwd: ctx_lo needs a bfloat16 ctx and 16-byte alignment");
   MSX_REQUIRE(msx_attention_tcl_supported(qkv, T, dh) && ((uintptr_t)ctx & 15) == 0 && ((uintptr_t)stats & 7) == 0,
               "msx_attention_tcl_fwd: needs d_h == 32, 128 < T <= 768, 16-byte aligned buffers");
   if (B == 0) return MSX_OK;
   const int D = H * DH;
   AttnLongParams p;
   p.qkv = qkv; p.dctx = nullptr;
-  p.mask = mask; p.stats = stats; p.out = ctx; p.out_bf16 = ctx_bf16 ? 1 : 0; p.dbias = nullptr;
+  p.mask = mask; p.stats = stats; p.out = ctx; p.out_lo = ctx_lo; p.out_bf16 = ctx_bf16 ? 1 : 0; p.dbias = nullptr;
   p.T = T; p.H = H; p.TQ = tensor_queries(T); p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;
   CUtensorMap tk, tm;
@@ -1616,7 +1638,7 @@ extern "C" int msx_attention_tcl_bwd_q0(const float* qkv, const float* mask, con
   const int D = H * DH;
   AttnLongParams p;
   p.qkv = qkv; p.dctx = dctx;
-  p.mask = mask; p.stats = const_cast<float*>(stats); p.out = dqkv; p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias;
+  p.mask = mask; p.stats = const_cast<float*>(stats); p.out = dqkv; p.out_lo = nullptr; p.out_bf16 = dqkv_bf16 ? 1 : 0; p.dbias = dbias;
   p.T = T; p.H = H; p.TQ = tensor_queries(T); p.inv_scale = 1.f / sqrtf((float)DH);
   const long long rows = (long long)B * T;
   CUtensorMap tk, tm, tdk, tdm;

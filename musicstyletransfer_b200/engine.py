@@ -590,14 +590,12 @@ class VAEEngine:
         if ops.attention_tc_supported(qkv, T, D // H):
             ops.attention_tc_fwd(qkv, mask, ctxp[0], B, T, H, D // H, x3_scores=True, ctx_lo=ctxp[1],
                                  q0_only=sos_only and D // H == 32)
-        else:                                           # longer rows: fp32 context from the kernel that takes them, one split
-            # q0_only writes the rows of query 0 only: zero-filled once, so the split never reads uninitialised memory
-            ctx = (bf.get_zero if sos_only else bf.get)(tag + "ctx", (M, D), dev)
-            if ops.attention_tcl_supported(qkv, T, D // H):
-                ops.attention_tcl_fwd(qkv, mask, ctx, bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
-                                      q0_only=sos_only)
-            else:
-                ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
+        elif ops.attention_tcl_supported(qkv, T, D // H):  # 128 < T <= 768: the long-row kernels write the planes themselves
+            ops.attention_tcl_fwd(qkv, mask, ctxp[0], bf.get(tag + "attn_stats", (B * H * T, 2), dev), B, T, H, D // H,
+                                  q0_only=sos_only, ctx_lo=ctxp[1])
+        else:                                           # longer rows: fp32 context from the exact kernel, one split
+            ctx = bf.get(tag + "ctx", (M, D), dev)
+            ops.attention_fwd(qkv, mask, ctx, B, T, H, D // H)
             ops.split_planes(ctx, ctxp[0], ctxp[1])
         if sos_only:
             xres = bf.get(tag + "xin_c", (B, D), dev)

@@ -239,9 +239,10 @@ def attention_tcl_supported(qkv, T, dh):
     return bool(lib.load().msx_attention_tcl_supported(P(qkv), _i(T), _i(dh)))
 
 
-def attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh, q0_only=False):
-    """q0_only: compute / write the context row of query 0 of every sequence only (the other rows of ctx stay untouched)."""
-    lib.call("msx_attention_tcl_fwd_q0", P(qkv), P(mask), P(ctx), _i(1 if ctx.dtype == torch.bfloat16 else 0), P(stats),
+def attention_tcl_fwd(qkv, mask, ctx, stats, B, T, H, dh, q0_only=False, ctx_lo=None):
+    """q0_only: compute / write the context row of query 0 of every sequence only (the other rows of ctx stay untouched).
+    ctx_lo: bfloat16 lo plane next to a bfloat16 ctx (= hi plane), the operands of the p3 W_proj GEMM."""
+    lib.call("msx_attention_tcl_fwd_p", P(qkv), P(mask), P(ctx), P(ctx_lo), _i(1 if ctx.dtype == torch.bfloat16 else 0), P(stats),
              _i(1 if q0_only else 0), _i(B), _i(T), _i(H), _i(dh), lib.stream_ptr())
 
 

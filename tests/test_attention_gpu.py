@@ -287,6 +287,35 @@ def test_attention_long_rows_batch_invariance(T, q0):
     assert bool(torch.isfinite(full[2]).all())
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 129, 2), (2, 200, 2), (3, 257, 2), (2, 384, 1), (2, 513, 2)])
+@pytest.mark.parametrize("q0", [False, True])
+def test_attention_long_rows_planes(B, T, H, q0):
+    """ctx as bf16 hi / lo planes straight from the long-row forward (msx_attention_tcl_fwd_p): hi = rn_bf16(o),
+    lo = rn_bf16(o - hi) of the very values the fp32 output holds (16 mantissa bits together)."""
+    from musicstyletransfer_b200 import ops
+    dh = 32
+    D = H * dh
+    qkv, mask = _inputs(B, T, H, dh, seed=T + 3)
+    qd, md = qkv.cuda(), mask.cuda()
+    ctx = torch.zeros(B * T, D, device="cuda")
+    stats = torch.zeros(B * H * T, 2, device="cuda")
+    ops.attention_tcl_fwd(qd, md, ctx, stats, B, T, H, dh, q0_only=q0)
+    planes = torch.full((2, B * T, D), 3.0, device="cuda", dtype=torch.bfloat16)
+    stats2 = torch.zeros_like(stats)
+    ops.attention_tcl_fwd(qd, md, planes[0], stats2, B, T, H, dh, q0_only=q0, ctx_lo=planes[1])
+    torch.cuda.synchronize()
+    assert torch.equal(stats, stats2)
+    rows = slice(0, None, T) if q0 else slice(None)
+    want = ctx[rows]
+    hi = want.to(torch.bfloat16)
+    lo = (want - hi.float()).to(torch.bfloat16)
+    assert torch.equal(planes[0][rows], hi) and torch.equal(planes[1][rows], lo)
+    if q0:
+        rest = torch.ones(B * T, dtype=torch.bool, device="cuda")
+        rest[::T] = False
+        assert bool((planes[:, rest] == 3.0).all())
+
+
 # ------------------------------------------------------------------------------------------------ 16-wide heads
 @pytest.mark.parametrize("B,T,H", [(3, 66, 8), (5, 65, 3), (2, 16, 4), (4, 97, 2), (2, 128, 8), (300, 66, 8)])
 @pytest.mark.parametrize("out16", [False, True])
