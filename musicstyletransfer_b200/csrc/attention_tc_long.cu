@@ -976,8 +976,11 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
   // whole step: T = 193 bwd 2.95 -> 2.71 ms, T = 384 3.33 -> 3.07 ms.  With trailing positions the extra 48 KB of shared memory
   // cost the trailing-key section its L1 hits (230 KB of shared memory leave 28 KB of L1: T = 260 3.25 -> 3.77 ms), so those
   // variants keep one slot and load at the start of the step.  SINGLE: four tiles, loaded once.
-  constexpr bool DB = !TAIL;
-  constexpr int kChunkTiles = SINGLE ? 4 : (DB ? 6 : 3);
+  // Q0 needs two tiles per slot (Q K-major, Q MN-major) and its trailing-key section reads no dO rows: double-buffered too
+  // (193 KB of shared memory keep the 196 KB carve-out, i.e. 60 KB of L1).
+  constexpr bool DB = !TAIL || Q0;
+  constexpr int kSlotTiles = Q0 ? 2 : 3;
+  constexpr int kChunkTiles = SINGLE ? 4 : (DB ? 2 * kSlotTiles : kSlotTiles);
   unsigned char* sC = SQ ? base + kTileBytes : (S2 ? base : sKm + kTileBytes);   // SINGLE: Q K-major (S2: and dO MN-major) of "slot 0"
   unsigned char* sY = SINGLE ? base : sC + kChunkTiles * kTileBytes;  // dS^T chunk, q contiguous: 4 slabs x 128 key rows
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(SINGLE ? base + 6 * kTileBytes : sY + 4 * kTileBytes);
@@ -1040,7 +1043,7 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
   // chunk loads of step s of a key tile (s < NKT: phase 1, else phase 2) into the slot of global step g; thread 0 only
   auto issue_chunk = [&](int s, unsigned g) {
     const int slot = DB ? (int)(g & 1) : 0;
-    unsigned char* t0 = sC + slot * 3 * kTileBytes;
+    unsigned char* t0 = sC + slot * kSlotTiles * kTileBytes;
     const int r0 = b * T + (s < NKT ? s : s - NKT) * kTile;
     if (s < NKT) {
       mbar_expect_tx(&bar_ld[slot], (unsigned)(2 * kTileBytes));
@@ -1176,7 +1179,7 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
       const int slot = DB ? (int)(step & 1) : 0;
-      unsigned char* const sQk = sC + slot * 3 * kTileBytes;
+      unsigned char* const sQk = sC + slot * kSlotTiles * kTileBytes;
       unsigned char* const sDOm = sQk + kTileBytes;
       if (tid == 0) {
         if (!SINGLE) {
@@ -1340,7 +1343,7 @@ __global__ void __launch_bounds__(kBwdThreads, SINGLE ? 2 : 1)
       const int nq = min(kTile, TQ - qc * kTile);
       const unsigned idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(nq >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
       const int slot = DB ? (int)(step & 1) : 0;
-      unsigned char* const sQk = sC + slot * 3 * kTileBytes;
+      unsigned char* const sQk = sC + slot * kSlotTiles * kTileBytes;
       unsigned char* const sQm = SINGLE ? sQm1 : sQk + kTileBytes;
       unsigned char* const sDOk = sQk + 2 * kTileBytes;
       if (!SINGLE || Q0) {
@@ -1525,7 +1528,7 @@ constexpr size_t kFwd2Q0Smem = 1024 + (size_t)(2 + 2) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t bwd_smem(bool single, bool tail, bool q0 = false) {
-  return 1024 + (size_t)(single ? 6 : 3 + (tail ? 3 : 6) + 4) * kTileBytes + 128;
+  return 1024 + (size_t)(single ? 6 : 3 + (q0 ? 4 : (tail ? 3 : 6)) + 4) * kTileBytes + 128;
 }
 
 }  // namespace
