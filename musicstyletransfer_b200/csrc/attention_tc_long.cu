@@ -22,6 +22,7 @@
 //                                 dK += dS Q (A from TMEM),  dQ[chunk] += dS^T K (A MN-major from shared memory)
 // dQ accumulates over key tiles in TMEM (32 columns per query chunk).
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "attention_tc_common.cuh"
 
 namespace {
@@ -589,19 +590,24 @@ __global__ void __launch_bounds__(kFwdThreads, (ALIAS || (Q0 && NKT <= 2)) ? 2 :
 //   sweep 2: P = exp2(s - max) / sum -> shared memory -> O[chunk] += P^T V      (Q0: one column sum for query 0 instead)
 // Thread layout, trailing positions and epilogue as in attn_tcl_fwd_kernel.
 // Q0: no P staging and no O accumulators — four tiles of shared memory and 128 score columns, two CTAs per SM.
-template <int NT, int NKT, bool Q0>
-__global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
+// CP (compact, up to four query chunks): ONE P buffer with the Q ring lying in its first two slabs, O in TMEM columns 0 .. 127
+// and S in 128 .. 255 — six tiles and 256 columns, two CTAs per SM.  The second sweep then runs without prefetch (a Q chunk
+// may only land once the MMA 2 that read the P buffer has retired); the other CTA on the SM fills those gaps.
+template <int NT, int NKT, bool Q0, bool CP>
+__global__ void __launch_bounds__(kFwdThreads, (Q0 || CP) ? 2 : 1)
     attn_tcl_fwd2_kernel(const __grid_constant__ CUtensorMap tmKm /* K-major {32, 128} box over qkv */,
                          const __grid_constant__ CUtensorMap tmMn /* MN-major {32, 128} box over qkv */,
                          const AttnLongParams p) {
   pdl_entry();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sQ = base;                          // two K-major query-chunk tiles (ring)
-  unsigned char* sK = sQ + 2 * kTileBytes;           // K-major key tile
+  static_assert(!(Q0 && CP), "Q0 stages no P");
+  static_assert(!CP || NT <= 4, "CP: O accumulators in TMEM columns 0 .. 127");
+  unsigned char* sQ = base;                          // two K-major query-chunk tiles (ring); CP: slabs 0 / 1 of the P buffer
+  unsigned char* sK = CP ? base + 4 * kTileBytes : sQ + 2 * kTileBytes;   // K-major key tile
   unsigned char* sV = sK + kTileBytes;               // MN-major value tile
-  unsigned char* sP = sV + kTileBytes;               // 2 x 4 slabs: P chunk, q contiguous, 128 key rows per slab
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Q0 ? sP : sP + 2 * 4 * kTileBytes);
+  unsigned char* sP = CP ? base : sV + kTileBytes;   // (CP: 1, else 2) x 4 slabs: P chunk, q contiguous, 128 key rows per slab
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Q0 ? sP : (CP ? base + 6 * kTileBytes : sP + 2 * 4 * kTileBytes));
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   unsigned long long* bar_q = &bars[0];              // [2]
   unsigned long long* bar_k = &bars[2];
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
   static_assert(NT * DH <= 256, "O accumulators: TMEM columns 0 .. 255, S in 256 .. 383");
   constexpr bool TAIL = NKT < NT;
   constexpr int NQQ = (NT * kTile + kFwdThreads - 1) / kFwdThreads;
-  constexpr int kTmemCols = Q0 ? 256 : 512;
+  constexpr int kTmemCols = (Q0 || CP) ? 256 : 512;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
   if (TAIL) fetch_tail_rows<kFwdThreads / 32>(tr_s, p.qkv, nullptr, (size_t)b * T + (size_t)(NT - 1) * kTile, ntail, D, h, warp, lane);
 
   if (!TAIL && !Q0) {                                // short last query chunk: the MMAs read the whole staging tile
-    for (int i = tid * 16; i < 2 * 4 * kTileBytes; i += kFwdThreads * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid * 16; i < (CP ? 1 : 2) * 4 * kTileBytes; i += kFwdThreads * 16) *reinterpret_cast<float4*>(sP + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
   }
   if (tid == 0) {
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tmem_slot;
-  const unsigned tm_O = tmem, tm_S = Q0 ? tmem : tmem + 256;
+  const unsigned tm_O = tmem, tm_S = Q0 ? tmem : (CP ? tmem + 128 : tmem + 256);
   const unsigned lane_off = (unsigned)(quarter * 32) << 16;
   const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(DH >> 3) << 17) |
                           ((unsigned)(128 >> 4) << 24);
@@ -741,6 +747,10 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
       const bool sweep2 = u >= NKT;
       const int nq = min(kTile, TQ - qc * kTile);
       if (tid == 0) {
+        if (CP && u > NKT) {                           // a later step of sweep 2: its Q chunk lands in the P buffer, free once
+          mbar_wait(&bar_o[0], (unsigned)((n - 1) & 1));   // the previous MMA 2 has retired
+          issue_q(qc, g);
+        }
         mbar_wait(&bar_q[g & 1], (g >> 1) & 1);
         if (u == 0) mbar_wait(bar_k, par);
         tc_fence_after();
@@ -751,8 +761,12 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
                     make_desc(smem_u32(sQ) + (g & 1) * kTileBytes + k * 32, 16, 1024, 2), idesc1, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
         // the next chunk (this key tile's next step, or the first of the next key tile) into the other ring slot
-        if (u + 1 < kSteps) issue_q(u + 1 < NKT ? u + 1 : u + 1 - NKT, g + 1);
-        else if (kt + 1 < NKT) issue_q(0, g + 1);
+        if (CP) {
+          if (u + 1 <= NKT) issue_q(u + 1 < NKT ? u + 1 : 0, g + 1);      // sweep 1 (P idle): the next chunk / the first of sweep 2
+        } else {
+          if (u + 1 < kSteps) issue_q(u + 1 < NKT ? u + 1 : u + 1 - NKT, g + 1);
+          else if (kt + 1 < NKT) issue_q(0, g + 1);
+        }
       }
       __syncwarp();
       mbar_wait(bar_s, g & 1);
@@ -812,9 +826,14 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
         }
       } else {
         // sweep 2: normalised chunk -> shared memory -> MMA 2
-        const int buf = n & 1;
+        const int buf = CP ? 0 : (n & 1);
         unsigned char* pb = sP + buf * 4 * kTileBytes;
-        if (n >= 2) {
+        if (CP) {
+          if (n >= 1) {
+            mbar_wait(&bar_o[0], (unsigned)((n - 1) & 1));
+            tc_fence_after();
+          }
+        } else if (n >= 2) {
           mbar_wait(&bar_o[buf], (unsigned)(((n >> 1) - 1) & 1));
           tc_fence_after();
         }
@@ -872,12 +891,14 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
       // the key tile's K and V are free: every MMA 1 has retired (bar_s waits), the last MMA 2 is waited for here
       if (!Q0) {
         const int last = n - 1;
-        mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+        if (CP) mbar_wait(&bar_o[0], (unsigned)(last & 1));
+        else mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
       }
       mbar_expect_tx(bar_k, (unsigned)kTileBytes);
       tma_load_2d(sK, &tmKm, bar_k, h * DH, b * T + (kt + 1) * kTile);
       mbar_expect_tx(bar_v, (unsigned)kTileBytes);
       tma_load_2d(sV, &tmMn, bar_v, 2 * D + h * DH, b * T + (kt + 1) * kTile);
+      if (CP) issue_q(0, g);                           // the P buffer is free: first chunk of the next key tile
     }
     __syncthreads();                                  // xs_* / V row reads are done before the next key tile
   }
@@ -898,7 +919,8 @@ __global__ void __launch_bounds__(kFwdThreads, Q0 ? 2 : 1)
   }
   {
     const int last = n - 1;
-    mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
+    if (CP) mbar_wait(&bar_o[0], (unsigned)(last & 1));
+    else mbar_wait(&bar_o[last & 1], (unsigned)((last >> 1) & 1));
     tc_fence_after();
   }
   if (TAIL) {
@@ -1525,6 +1547,7 @@ constexpr size_t kFwdAliasSmem = 1024 + (size_t)5 * kTileBytes + 128;
 constexpr size_t fwd_q0_smem(int nt) { return 1024 + (size_t)(nt + 2) * kTileBytes + 128; }   // no P staging
 constexpr size_t kFwd2Smem = 1024 + (size_t)(2 + 2 + 8) * kTileBytes + 128;
 constexpr size_t kFwd2Q0Smem = 1024 + (size_t)(2 + 2) * kTileBytes + 128;
+constexpr size_t kFwd2CpSmem = 1024 + (size_t)(4 + 2) * kTileBytes + 128;
 // score columns on the tensor path
 inline int tensor_queries(int T) { const int t = tail_keys(T); return t ? T - t : (T + 15) / 16 * 16; }
 constexpr size_t bwd_smem(bool single, bool tail, bool q0 = false) {
@@ -1590,25 +1613,34 @@ extern "C" int msx_attention_tcl_fwd_p(const float* qkv, const float* mask, void
 #define MSX_TCL_FWD2(NT_, NKT_)                                                                                            \
   do {                                                                                                                   \
     if (q0_only) {                                                                                                       \
-      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    (int)kFwd2Q0Smem));                                                                  \
-      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, true>, dim3(B * H), dim3(kFwdThreads), kFwd2Q0Smem, st, tk,    \
-                          tm, p));                                                                                       \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, true, false>,                                        \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwd2Q0Smem));                     \
+      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, true, false>, dim3(B * H), dim3(kFwdThreads), kFwd2Q0Smem, st, \
+                          tk, tm, p));                                                                                   \
     } else {                                                                                                             \
-      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)kFwd2Smem));                                                                    \
-      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, false>, dim3(B * H), dim3(kFwdThreads), kFwd2Smem, st, tk, tm, \
+      constexpr bool kCp = (NT_) <= 4;                                                                                   \
+      const size_t sm2 = kCp ? kFwd2CpSmem : kFwd2Smem;                                                                  \
+      MSX_CUDA(cudaFuncSetAttribute(attn_tcl_fwd2_kernel<NT_, NKT_, false, kCp>,                                         \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));                             \
+      MSX_CUDA(msx_launch(attn_tcl_fwd2_kernel<NT_, NKT_, false, kCp>, dim3(B * H), dim3(kFwdThreads), sm2, st, tk, tm,  \
                           p));                                                                                           \
     }                                                                                                                    \
   } while (0)
   const bool tail = tail_keys(T) != 0;
   const int nt = (T + kTile - 1) / kTile;
+  // Full forward, one-pass kernel (one CTA per SM, everything prefetched) vs compact chunked kernel (two CTAs per SM, serial
+  // second sweep), per call of 264 k rows: T = 257 1032 / 928 us, T = 260 1298 / 1348, T = 193 1194 / 1243, T = 384 1220 / 1455:
+  // the compact kernel wins with one trailing position and few chunks; MSX_TCL_COMPACT=1 / 0 forces it on / off for experiments.
+  static const char* cp_env = getenv("MSX_TCL_COMPACT");
+  const bool compact3 = cp_env ? cp_env[0] == '1' : tail_keys(T) == 1;
   if (nt == 2) {
     if (tail) MSX_TCL_FWD(2, 1, true, kFwdAliasSmem);  // T = 129 ... 132: one tile on the tensor path, two CTAs per SM
+    else if (!q0_only && cp_env && cp_env[0] == '1') MSX_TCL_FWD2(2, 2);
     else MSX_TCL_FWD(2, 2, false, fwd_smem(2));
   } else if (nt == 3) {
-    if (tail) MSX_TCL_FWD(3, 2, false, fwd_smem(3));   // T = 257 ... 260
-    else if (q0_only) MSX_TCL_FWD2(3, 3);              // 384 score columns: the chunked kernel runs two CTAs per SM
+    if (tail && !q0_only && compact3) MSX_TCL_FWD2(3, 2);                    // T = 257
+    else if (tail) MSX_TCL_FWD(3, 2, false, fwd_smem(3));                     // T = 258 ... 260, q0_only at T = 257 ... 260
+    else if (q0_only || (cp_env && cp_env[0] == '1')) MSX_TCL_FWD2(3, 3);     // 384 score columns: chunked, two CTAs per SM
     else MSX_TCL_FWD(3, 3, false, fwd_smem(3));
   } else if (nt == 4) {                                // 384 < T <= 768: two sweeps over the query chunks
     if (tail) MSX_TCL_FWD2(4, 3);
